@@ -1,0 +1,108 @@
+"""In-tree build of the sm_100a extension (``_colearn_C*.so`` next to this file).
+
+``nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo`` for every ``.cu`` (they do not include
+torch headers, so each compiles in seconds), ``g++`` for ``bindings.cpp``, one link step.  The
+result is git-ignored but travels with the gpurun snapshot; ``__graft_entry__.build()`` calls
+:func:`build_all`.  Objects are cached under ``csrc/_obj`` keyed by source mtime+flags.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+from concurrent.futures import ThreadPoolExecutor
+from typing import List
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+EXT_NAME = "_colearn_C"
+
+CU_SOURCES = ["mlp_persistent.cu", "elementwise.cu", "comm.cu", "gemm_tcgen05.cu"]
+CPP_SOURCES = ["bindings.cpp"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
+              "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# --use_fast_math would change expf/logf/division semantics in the loss kernels; keep IEEE there.
+NVCC_FLAGS.remove("--use_fast_math")
+
+
+def ext_path() -> str:
+    suffix = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+    return os.path.join(HERE, EXT_NAME + suffix)
+
+
+def _nvcc() -> str:
+    cand = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+    return cand if os.path.exists(cand) else (shutil.which("nvcc") or "nvcc")
+
+
+def _stamp(src: str, flags: List[str]) -> str:
+    h = hashlib.sha1()
+    with open(src, "rb") as f:
+        h.update(f.read())
+    with open(os.path.join(CSRC, "colearn_kernels.h"), "rb") as f:
+        h.update(f.read())
+    h.update(" ".join(flags).encode())
+    return h.hexdigest()[:16]
+
+
+def _run(cmd: List[str], log_name: str) -> None:
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(os.path.join(OBJ, log_name + ".log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError(f"build step failed: {' '.join(cmd)}\n{proc.stdout}")
+
+
+def build_all(force: bool = False, verbose: bool = True) -> str:
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    os.makedirs(OBJ, exist_ok=True)
+    out = ext_path()
+    objs, jobs = [], []
+
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    for src in CU_SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ, f"{src}.{_stamp(path, NVCC_FLAGS)}.o")
+        objs.append(obj)
+        if force or not os.path.exists(obj):
+            jobs.append(([_nvcc(), *NVCC_FLAGS, "-I", CSRC, "-c", path, "-o", obj], src))
+
+    inc = [f"-I{p}" for p in ce.include_paths(device_type="cuda")] + [f"-I{sysconfig.get_paths()['include']}", f"-I{CSRC}"]
+    cxx_flags = ["-O2", "-std=c++17", "-fPIC", f"-DTORCH_EXTENSION_NAME={EXT_NAME}",
+                 "-DTORCH_API_INCLUDE_EXTENSION_H", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+                 "-Wno-deprecated-declarations"]
+    for src in CPP_SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ, f"{src}.{_stamp(path, cxx_flags)}.o")
+        objs.append(obj)
+        if force or not os.path.exists(obj):
+            jobs.append((["g++", *cxx_flags, *inc, "-c", path, "-o", obj], src))
+
+    if jobs:
+        if verbose:
+            print(f"[colearn build] compiling {len(jobs)} translation unit(s) for sm_100a", file=sys.stderr)
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
+            list(pool.map(lambda j: _run(j[0], j[1]), jobs))
+
+    if jobs or force or not os.path.exists(out):
+        lib_dirs = ce.library_paths(device_type="cuda")
+        link = ["g++", "-shared", *objs, "-o", out]
+        for d in lib_dirs:
+            link += [f"-L{d}", f"-Wl,-rpath,{d}"]
+        link += [f"-L{os.path.join(cuda_home, 'lib64')}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda",
+                 "-ltorch", "-ltorch_python", "-lcudart"]
+        _run(link, "link")
+        if verbose:
+            print(f"[colearn build] linked {out}", file=sys.stderr)
+    return out
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv))

@@ -1,0 +1,179 @@
+// Shared declarations between the sm_100a kernels (.cu) and the torch bindings (bindings.cpp).
+// The .cu files deliberately do NOT include torch headers: they compile in seconds and expose
+// plain C++ launchers taking raw pointers + a cudaStream_t.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace colearn {
+
+// ---------------------------------------------------------------------------------------------
+// Persistent whole-network local SGD (mlp_persistent.cu)
+// ---------------------------------------------------------------------------------------------
+enum LossKind : int { LOSS_BCE = 0, LOSS_SSE = 1, LOSS_XENT = 2, LOSS_MSE = 3 };
+enum NetKind : int { NET_FFNN = 0, NET_MLP64 = 1, NET_TESTING_REMOTE = 2 };
+
+// One descriptor per client (= one CTA).  A "client" is a federated worker: it starts from
+// theta_in, runs its local SGD over its private shard and emits out_scale * theta_k (or the
+// scaled delta) to theta_out — which may be a *peer GPU's* memory (model-gather leg).
+struct ClientDesc {
+  const float* x;          // [n, d_in] row-major features
+  const float* y;          // [n, y_dim] targets (xent: class index stored as float, y_dim = 1)
+  const int* perm;         // [perm_rows, n] sample order, or nullptr for identity
+  const float* theta_in;   // flat arena to start from (state-dict order, unpadded)
+  float* theta_out;        // where out_scale * theta_k (or delta) goes; may alias theta_in
+  float* loss_out;         // [2]: {last batch loss, mean loss over all steps}; may be peer memory
+  const uint32_t* wait_flag;  // if non-null: spin (ld.acquire.sys) until *wait_flag >= wait_value
+  uint32_t* signal_flag;      // if non-null: st.release.sys signal_value after theta_out is written
+  int n;
+  int perm_rows;
+  int y_dim;
+  uint32_t wait_value;
+  uint32_t signal_value;
+  float out_scale;         // FedAvg weight w_k pre-applied by the producer
+  int delta_mode;          // 0: out = w*theta_k ; 1: out = w*(theta_k - theta_in)
+  int _pad;
+};
+
+struct SgdHyper {
+  int batch_size;
+  int epochs;
+  int max_steps;   // <= 0: unlimited (PySyft max_nr_batches semantics)
+  int loss;        // LossKind
+  float lr;
+};
+
+// Returns cudaError_t from the launch.  descs lives in device memory ([n_clients]).
+cudaError_t launch_mlp_local_sgd(int net_kind, const ClientDesc* descs, int n_clients,
+                                 SgdHyper hp, cudaStream_t stream);
+int mlp_local_sgd_smem_bytes(int net_kind, int batch_size);
+int mlp_net_num_params(int net_kind);
+
+// Forward-only batched inference/eval for the small nets: out[n, d_out] (post-activation).
+cudaError_t launch_mlp_forward(int net_kind, const float* theta, const float* x, float* out,
+                               int n, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// Elementwise / reduction kernels (elementwise.cu)
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_sgd_step(float* param, const float* grad, float lr, int64_t n, cudaStream_t s);
+cudaError_t launch_sgd_step_bf16grad(float* param, const void* grad_bf16, float lr, int64_t n,
+                                     cudaStream_t s);
+// theta <- theta + server_lr * (sum_k w[k] * slots[k*stride .. ] - theta)   (weights sum to 1)
+cudaError_t launch_fedavg_apply(float* theta, const float* slots, int64_t slot_stride,
+                                const float* weights, int k, float server_lr, int64_t n,
+                                cudaStream_t s);
+// out = sum_k w[k] * slots[k]
+cudaError_t launch_fedavg_flat(float* out, const float* slots, int64_t slot_stride,
+                               const float* weights, int k, int64_t n, cudaStream_t s);
+// Fused loss forward+backward.  loss_out is a single float (mean or sum per LossKind).
+cudaError_t launch_sigmoid_bce(const float* z, const float* y, float* dz, float* loss_out,
+                               int64_t n, cudaStream_t s);
+cudaError_t launch_sse(const float* out, const float* y, float* dz, float* loss_out, int64_t n,
+                       float scale, cudaStream_t s);
+cudaError_t launch_softmax_xent(const void* logits, int logits_is_bf16, const int64_t* labels,
+                                float* dlogits, void* dlogits_bf16, float* loss_out, int rows,
+                                int cols, cudaStream_t s);
+// Eval: sum BCE + number of correct round(p) predictions (cf.py:233-253)
+cudaError_t launch_eval_binary(const float* p, const float* y, float* loss_sum, int* correct,
+                               int64_t n, cudaStream_t s);
+cudaError_t launch_argmax_rows(const float* x, int64_t* out, int rows, int cols, cudaStream_t s);
+// Column-wise min/max scaling to [0,1] (NetworkTrafficDataset preprocessing, ds.py:31-32)
+cudaError_t launch_minmax_scale(const float* x, float* out, int rows, int cols, cudaStream_t s);
+// Philox-keyed random permutation of [0, n): writes sort keys; caller argsorts? No — full device
+// Fisher-Yates is serial; we use a keyed bijection (Feistel network over the next power of two,
+// cycle-walking) so each index is computed independently in O(1).
+cudaError_t launch_feistel_permutation(int* out, int n, int rows, uint64_t seed, cudaStream_t s);
+cudaError_t launch_fp32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t s);
+cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// Cross-GPU collectives over NVLink peer memory (comm.cu)
+// ---------------------------------------------------------------------------------------------
+// Coordinator-side "star" round step for small models:
+//   wait until every selected worker k published w_k*theta_k into slots[k] (flag >= epoch),
+//   theta <- theta + server_lr*(sum_k slots[k] - theta)  [weights already applied by producers],
+//   then push theta into every selected peer's inbox and raise their bcast flag (= epoch+1).
+// One kernel = FedAvg reduce + server apply + next-round broadcast (SURVEY K1+K2+K3+K4).
+struct StarRoundArgs {
+  float* theta;                 // coordinator's global model (local memory)
+  const float* slots;           // [world, slot_stride] local slot buffer peers push into
+  int64_t slot_stride;
+  const uint32_t* arrive_flags; // [world] local flags raised by workers (value = round epoch)
+  uint32_t arrive_epoch;
+  float* peer_inbox[16];        // each rank's theta_in buffer (peer pointers; [rank]=local)
+  uint32_t* peer_bcast_flag[16];
+  uint32_t bcast_epoch;
+  float* mc_inbox;              // multicast alias of the inbox (nullptr -> unicast P2P stores)
+  uint32_t select_mask;         // bit k set = worker k participates this round
+  int world;
+  float server_lr;
+  int64_t n;
+  int do_reduce;                // 0: broadcast only (round 0)
+  int do_bcast;                 // 0: reduce/apply only (last round)
+  uint32_t* grid_counter;       // device scratch for the in-kernel grid barrier
+};
+cudaError_t launch_star_round(const StarRoundArgs& a, int n_blocks, cudaStream_t s);
+
+// Bandwidth-optimal symmetric "two-shot" FedAvg for large models.  Chunk c of the arena is owned
+// by rank (c % world): the owner pulls that chunk of theta_k from every selected peer's work
+// arena (P2P ld), forms sum_k w_k*theta_k, applies the server update and writes the new chunk
+// into every peer's fp32 work arena AND bf16 shadow arena (fp32->bf16 fused into the
+// broadcast), then raises the chunk's ready flag on every peer.  The next round's first
+// consumer GEMM polls those flags from its TMA producer warp (fused broadcast -> GEMM, SURVEY
+// K1); non-GEMM consumers use launch_wait_flags.
+struct TwoShotArgs {
+  float* work[16];              // per-rank fp32 arenas (peer pointers; trained params in, theta out)
+  void* shadow_bf16[16];        // per-rank bf16 shadows (peer pointers) or nullptr
+  uint32_t* chunk_flags[16];    // per-rank [n_chunks] ready flags (peer pointers)
+  const uint32_t* arrive_flags; // local [world]: rank k finished local training (value >= epoch)
+  const float* weights;         // local device [world]: normalised FedAvg weights
+  float* theta_prev;            // local previous global model (needed iff server_lr != 1) or null
+  uint32_t epoch;
+  uint32_t select_mask;
+  float server_lr;
+  int64_t n;                    // total elements (multiple of 4)
+  int64_t chunk_elems;          // flag granularity (multiple of 4)
+  int world;
+  int rank;
+};
+cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s);
+
+// Tiny helpers used by the host engine / tests.
+cudaError_t launch_set_flag(uint32_t* flag, uint32_t value, cudaStream_t s);
+cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t s);
+cudaError_t launch_wait_flags(const uint32_t* flags, int count, uint32_t value, cudaStream_t s);
+// raise flag_ptrs[k][0] = value on every rank k < world (release, system scope)
+struct PeerFlags { uint32_t* ptr[16]; };
+cudaError_t launch_signal_peers(const PeerFlags& flags, int world, uint32_t value, cudaStream_t s);
+cudaError_t launch_p2p_copy(float* dst, const float* src, int64_t n, uint32_t* flag,
+                            uint32_t flag_value, int n_blocks, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 GEMM family (gemm_tcgen05.cu):  C[M,N] = A[M,K] * B[N,K]^T  (both operands K-major bf16)
+// ---------------------------------------------------------------------------------------------
+struct GemmEpilogue {
+  const float* bias;        // [N] or nullptr
+  int relu;                 // apply max(0, .)
+  const void* relu_mask;    // bf16 [M,N]: multiply by (mask > 0) — dgrad through ReLU; or nullptr
+  void* out_bf16;           // [M,N] bf16 or nullptr
+  float* out_f32;           // [M,N] fp32 or nullptr
+  void* out_bf16_t;         // [N,M] bf16 transposed copy or nullptr
+  // fused SGD (wgrad epilogue): master[M,N] -= lr * acc ; shadow bf16 copies refreshed
+  float* sgd_master;
+  float sgd_lr;
+  void* sgd_shadow;         // bf16 [M,N]
+  void* sgd_shadow_t;       // bf16 [N,M]
+  float* colsum;            // [N] += column sums of acc (bias gradient), atomicAdd; or nullptr
+  // fused broadcast consumption: before loading B rows [n0, n0+BN) the TMA producer waits until
+  // ready_flags[(n0*K*elem)/chunk] >= ready_epoch  (peer-written weights)
+  const uint32_t* ready_flags;
+  uint32_t ready_epoch;
+  int64_t ready_chunk_rows;  // rows of B per flag
+};
+// A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
+cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,
+                                const GemmEpilogue& ep, cudaStream_t s);
+const char* gemm_tcgen05_last_error();
+
+}  // namespace colearn

@@ -1,0 +1,274 @@
+// Cross-GPU collectives written directly against NVLink peer memory (no NCCL on these paths).
+//
+// The reference moves models with PySyft websocket RPC: train_config.send(worker)  (broadcast leg,
+// client_federated.py:209), model_ptr.get() (gather leg, :211) and utils.federated_avg (CPU mean,
+// federated_coordinator.py:373,568).  On an NVSwitch box every GPU maps every peer's symmetric
+// arena, so those three legs become plain ld/st (or multimem.st) on peer addresses issued from
+// inside the kernels that produce / consume the data:
+//
+//   star_round_kernel      (small models, latency-optimal, coordinator-centric)
+//       wait(arrive flags) -> theta += lr_s * (sum_k slot_k - theta) -> st theta to every selected
+//       peer inbox (P2P or NVLS multicast) -> last CTA raises the peers' bcast flags.
+//       = FedAvg reduce + sample-count scale (pre-applied by producers) + server apply + next
+//         round's broadcast in ONE kernel (SURVEY K1+K2+K3+K4).
+//   twoshot_fedavg_kernel  (large models, bandwidth-optimal, symmetric)
+//       rank r owns slice r: pulls w_k*theta_k[slice r] from every selected peer (P2P ld), applies
+//       the server update, pushes the new slice into every peer's fp32 arena AND its bf16 shadow
+//       (fp32->bf16 conversion fused into the broadcast), raising per-chunk ready flags that the
+//       next round's first consumer GEMM polls from its TMA producer warp (fused broadcast->GEMM).
+//
+// Memory model: data stores are weak; a CTA finishes with __threadfence_system() and the flag is
+// written with st.release.sys; consumers spin with ld.acquire.sys (and add fence.proxy.async before
+// TMA reads — see gemm_tcgen05.cu).  Flags carry monotonically increasing epochs, never reset.
+#include "colearn_kernels.h"
+
+#include <cuda_bf16.h>
+
+namespace colearn {
+namespace {
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
+  // peer reads bypass L2 of the local GPU anyway; keep them out of L1 too (single use)
+  float4 v;
+  asm volatile("ld.global.relaxed.sys.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer_f4(float4* p, const float4& v) {
+  asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f4(float4* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  return r;
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+star_round_kernel(StarRoundArgs a) {
+  const int tid = threadIdx.x;
+  // (1) wait for every selected worker's contribution of this round
+  if (a.do_reduce) {
+    if (tid < a.world && ((a.select_mask >> tid) & 1u)) {
+      while (ld_acquire_sys(a.arrive_flags + tid) < a.arrive_epoch) __nanosleep(20);
+    }
+    __syncthreads();
+  }
+  const int64_t n4 = a.n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float4* theta4 = reinterpret_cast<float4*>(a.theta);
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + tid; j < n4; j += stride) {
+    float4 t = theta4[j];
+    if (a.do_reduce) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < a.world; ++k) {
+        if (!((a.select_mask >> k) & 1u)) continue;
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(a.slots + k * a.slot_stride) + j);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      t.x = fmaf(a.server_lr, acc.x - t.x, t.x); t.y = fmaf(a.server_lr, acc.y - t.y, t.y);
+      t.z = fmaf(a.server_lr, acc.z - t.z, t.z); t.w = fmaf(a.server_lr, acc.w - t.w, t.w);
+      theta4[j] = t;
+    }
+    if (a.do_bcast) {
+      if (a.mc_inbox != nullptr) {
+        multimem_st_f4(reinterpret_cast<float4*>(a.mc_inbox) + j, t);
+      } else {
+        for (int k = 0; k < a.world; ++k)
+          if ((a.select_mask >> k) & 1u) st_peer_f4(reinterpret_cast<float4*>(a.peer_inbox[k]) + j, t);
+      }
+    }
+  }
+  // scalar tail (n not a multiple of 4)
+  for (int64_t j = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + tid; j < a.n; j += stride) {
+    float t = a.theta[j];
+    if (a.do_reduce) {
+      float acc = 0.f;
+      for (int k = 0; k < a.world; ++k)
+        if ((a.select_mask >> k) & 1u) acc += __ldcg(a.slots + k * a.slot_stride + j);
+      t = fmaf(a.server_lr, acc - t, t);
+      a.theta[j] = t;
+    }
+    if (a.do_bcast)
+      for (int k = 0; k < a.world; ++k)
+        if ((a.select_mask >> k) & 1u) a.peer_inbox[k][j] = t;
+  }
+  // (3) last CTA publishes the broadcast epoch to every selected peer
+  if (a.do_bcast) {
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(a.grid_counter, 1u);
+      is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      if (tid == 0) *a.grid_counter = 0u;
+      __threadfence_system();
+      if (tid < a.world && ((a.select_mask >> tid) & 1u)) st_release_sys(a.peer_bcast_flag[tid], a.bcast_epoch);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Two-shot FedAvg.  Work decomposition: the arena is cut into chunks of chunk_elems floats; chunk c
+// belongs to rank (c % world) (interleaved ownership keeps every rank's NVLink ports busy for the
+// whole kernel and lets early layers become ready first on every peer).  A CTA processes whole
+// chunks so that it can publish the chunk's ready flag by itself.
+__global__ void __launch_bounds__(512)
+twoshot_fedavg_kernel(TwoShotArgs a) {
+  const int tid = threadIdx.x;
+  __shared__ float sw[16];
+  if (tid < a.world) {
+    sw[tid] = a.weights[tid];
+    if ((a.select_mask >> tid) & 1u)
+      while (ld_acquire_sys(a.arrive_flags + tid) < a.epoch) __nanosleep(20);
+  }
+  __syncthreads();
+  const int64_t n_chunks = (a.n + a.chunk_elems - 1) / a.chunk_elems;
+  // chunks owned by this rank: c = rank, rank + world, ...
+  for (int64_t oc = blockIdx.x; ; oc += gridDim.x) {
+    const int64_t c = a.rank + oc * a.world;
+    if (c >= n_chunks) break;
+    const int64_t lo = c * a.chunk_elems;
+    const int64_t hi = (lo + a.chunk_elems < a.n) ? lo + a.chunk_elems : a.n;
+    const int64_t len4 = (hi - lo) >> 2;  // n and chunk_elems are multiples of 4
+    for (int64_t j = tid; j < len4; j += blockDim.x) {
+      const int64_t e4 = (lo >> 2) + j;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int k = 0; k < a.world; ++k) {
+        if (!((a.select_mask >> k) & 1u)) continue;
+        const float4 v = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4);
+        const float w = sw[k];
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+      if (a.theta_prev != nullptr) {
+        float4 t = reinterpret_cast<float4*>(a.theta_prev)[e4];
+        t.x = fmaf(a.server_lr, acc.x - t.x, t.x); t.y = fmaf(a.server_lr, acc.y - t.y, t.y);
+        t.z = fmaf(a.server_lr, acc.z - t.z, t.z); t.w = fmaf(a.server_lr, acc.w - t.w, t.w);
+        reinterpret_cast<float4*>(a.theta_prev)[e4] = t;
+        acc = t;
+      }
+      const uint2 packed = pack_bf16x4(acc);
+#pragma unroll 4
+      for (int k = 0; k < a.world; ++k) {
+        st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4, acc);
+        if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4] = packed;
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < a.world) {
+      __threadfence_system();
+      st_release_sys(a.chunk_flags[tid] + c, a.epoch);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void set_flag_kernel(uint32_t* flag, uint32_t value) {
+  __threadfence_system();
+  st_release_sys(flag, value);
+}
+__global__ void signal_peers_kernel(PeerFlags f, int world, uint32_t value) {
+  __threadfence_system();
+  if ((int)threadIdx.x < world) st_release_sys(f.ptr[threadIdx.x], value);
+}
+__global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value) {
+  while (ld_acquire_sys(flag) < value) __nanosleep(50);
+}
+// wait until every one of `count` consecutive flags reached `value`
+__global__ void wait_flags_kernel(const uint32_t* flags, int count, uint32_t value) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x)
+    while (ld_acquire_sys(flags + i) < value) __nanosleep(50);
+}
+
+__global__ void __launch_bounds__(512)
+p2p_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, uint32_t* flag,
+                uint32_t flag_value, uint32_t* counter) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t j = i0; j < n4; j += stride) {
+    const float4 v = ld_peer_f4(reinterpret_cast<const float4*>(src) + j);
+    st_peer_f4(reinterpret_cast<float4*>(dst) + j, v);
+  }
+  for (int64_t j = (n4 << 2) + i0; j < n; j += stride) dst[j] = src[j];
+  if (flag != nullptr) {
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+      *counter = 0u;
+      __threadfence_system();
+      st_release_sys(flag, flag_value);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_star_round(const StarRoundArgs& a, int n_blocks, cudaStream_t s) {
+  if (a.world > 16) return cudaErrorInvalidValue;
+  if (n_blocks < 1) n_blocks = 1;
+  star_round_kernel<<<n_blocks, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s) {
+  if (a.world > 16 || (a.n & 3) || (a.chunk_elems & 3)) return cudaErrorInvalidValue;
+  if (n_blocks < 1) n_blocks = 1;
+  twoshot_fedavg_kernel<<<n_blocks, 512, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_signal_peers(const PeerFlags& flags, int world, uint32_t value, cudaStream_t s) {
+  if (world > 16) return cudaErrorInvalidValue;
+  signal_peers_kernel<<<1, 32, 0, s>>>(flags, world, value);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_flag(uint32_t* flag, uint32_t value, cudaStream_t s) {
+  set_flag_kernel<<<1, 1, 0, s>>>(flag, value);
+  return cudaGetLastError();
+}
+cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t s) {
+  wait_flag_kernel<<<1, 1, 0, s>>>(flag, value);
+  return cudaGetLastError();
+}
+cudaError_t launch_wait_flags(const uint32_t* flags, int count, uint32_t value, cudaStream_t s) {
+  wait_flags_kernel<<<1, 128, 0, s>>>(flags, count, value);
+  return cudaGetLastError();
+}
+cudaError_t launch_p2p_copy(float* dst, const float* src, int64_t n, uint32_t* flag, uint32_t flag_value,
+                            int n_blocks, cudaStream_t s) {
+  static uint32_t* counter = nullptr;
+  if (flag != nullptr && counter == nullptr) {
+    cudaError_t e = cudaMalloc(&counter, sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    cudaMemset(counter, 0, sizeof(uint32_t));
+  }
+  if (n_blocks < 1) n_blocks = 1;
+  p2p_copy_kernel<<<n_blocks, 512, 0, s>>>(dst, src, n, flag, flag_value, counter);
+  return cudaGetLastError();
+}
+
+}  // namespace colearn

@@ -1,0 +1,386 @@
+// Memory-bound kernels: SGD step, FedAvg on flat arenas, fused loss fwd+bwd, eval, argmax,
+// min-max scaling, keyed permutation, dtype conversion.  All are single-pass, 128-bit vectorised
+// where alignment allows, and sized as a persistent grid (148 SMs x 8 CTAs) with grid-stride loops.
+//
+// Parity map: K9 sigmoid+BCE (client_federated.py:65,79), K10 softmax-xent (BASELINE
+// 2-logit configs), K11 SSE (cf.py:112,158), K12 SGD (fc.py:355; cf.py:206-207), K13 MinMax
+// (datasets.py:31-32), K14 shuffled sampling (cf.py:203), K15 eval (cf.py:233-253), K16 argmax
+// (fc.py:252-256), K3 FedAvg (fc.py:373,568).
+#include "colearn_kernels.h"
+
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace colearn {
+namespace {
+
+constexpr int kThreads = 256;
+inline int grid_for(int64_t n, int per_thread = 4) {
+  int64_t b = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+  const int64_t cap = 148 * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* scratch /*[32]*/) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < (blockDim.x >> 5) ? scratch[lane] : 0.f;
+    v = warp_sum(v);
+  }
+  __syncthreads();
+  return v;  // valid in warp 0
+}
+
+// ---- SGD ---------------------------------------------------------------------------------------
+__global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float lr, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g)) & 15) == 0;
+  if (aligned) {
+    const int64_t n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int64_t j = i; j < n4; j += stride) {
+      float4 a = p4[j];
+      const float4 b = __ldg(g4 + j);
+      a.x = fmaf(-lr, b.x, a.x); a.y = fmaf(-lr, b.y, a.y);
+      a.z = fmaf(-lr, b.z, a.z); a.w = fmaf(-lr, b.w, a.w);
+      p4[j] = a;
+    }
+    for (int64_t j = (n4 << 2) + i; j < n; j += stride) p[j] = fmaf(-lr, g[j], p[j]);
+  } else {
+    for (; i < n; i += stride) p[i] = fmaf(-lr, g[i], p[i]);
+  }
+}
+
+__global__ void sgd_step_bf16grad_kernel(float* __restrict__ p, const __nv_bfloat16* __restrict__ g,
+                                         float lr, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    p[i] = fmaf(-lr, __bfloat162float(g[i]), p[i]);
+}
+
+// ---- FedAvg on flat arenas ------------------------------------------------------------------------
+template <bool APPLY>
+__global__ void fedavg_kernel(float* __restrict__ theta, const float* __restrict__ slots,
+                              int64_t slot_stride, const float* __restrict__ weights, int k,
+                              float server_lr, int64_t n) {
+  __shared__ float sw[64];
+  if (threadIdx.x < k && threadIdx.x < 64) sw[threadIdx.x] = weights[threadIdx.x];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool aligned = (((uintptr_t)theta | (uintptr_t)slots) & 15) == 0 && (slot_stride & 3) == 0;
+  if (aligned) {
+    const int64_t n4 = n >> 2;
+    for (int64_t j = i0; j < n4; j += stride) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < k; ++c) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(slots + c * slot_stride) + j);
+        const float w = sw[c];
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+      float4* t4 = reinterpret_cast<float4*>(theta) + j;
+      if (APPLY) {
+        float4 t = *t4;
+        t.x = fmaf(server_lr, acc.x - t.x, t.x); t.y = fmaf(server_lr, acc.y - t.y, t.y);
+        t.z = fmaf(server_lr, acc.z - t.z, t.z); t.w = fmaf(server_lr, acc.w - t.w, t.w);
+        *t4 = t;
+      } else {
+        *t4 = acc;
+      }
+    }
+    for (int64_t j = (n4 << 2) + i0; j < n; j += stride) {
+      float acc = 0.f;
+      for (int c = 0; c < k; ++c) acc = fmaf(sw[c], slots[c * slot_stride + j], acc);
+      theta[j] = APPLY ? fmaf(server_lr, acc - theta[j], theta[j]) : acc;
+    }
+  } else {
+    for (int64_t j = i0; j < n; j += stride) {
+      float acc = 0.f;
+      for (int c = 0; c < k; ++c) acc = fmaf(sw[c], slots[c * slot_stride + j], acc);
+      theta[j] = APPLY ? fmaf(server_lr, acc - theta[j], theta[j]) : acc;
+    }
+  }
+}
+
+// ---- losses ---------------------------------------------------------------------------------------
+__global__ void sigmoid_bce_kernel(const float* __restrict__ z, const float* __restrict__ y,
+                                   float* __restrict__ dz, float* __restrict__ loss_out, int64_t n) {
+  __shared__ float scratch[32];
+  const float inv_n = 1.f / (float)n;
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float p = 1.f / (1.f + __expf(-z[i]));
+    const float t = y[i];
+    const float lp = fmaxf(__logf(p), -100.f), l1p = fmaxf(log1pf(-p), -100.f);
+    acc -= t * lp + (1.f - t) * l1p;
+    if (dz) dz[i] = (p - t) * inv_n;
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) atomicAdd(loss_out, acc * inv_n);
+}
+
+__global__ void sse_kernel(const float* __restrict__ out, const float* __restrict__ y,
+                           float* __restrict__ dz, float* __restrict__ loss_out, int64_t n, float scale) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = out[i] - y[i];
+    acc = fmaf(d, d, acc);
+    if (dz) dz[i] = 2.f * d * scale;
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) atomicAdd(loss_out, acc * scale);
+}
+
+// One warp per row; cols <= 1024.  Reads logits once, writes dlogits (fp32 and/or bf16).
+template <bool BF16_IN>
+__global__ void softmax_xent_kernel(const void* __restrict__ logits_, const int64_t* __restrict__ labels,
+                                    float* __restrict__ dl, __nv_bfloat16* __restrict__ dl_bf16,
+                                    float* __restrict__ loss_out, int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_rows = 1.f / (float)rows;
+  float loss_acc = 0.f;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    auto load = [&](int c) -> float {
+      if (BF16_IN) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(logits_)[(size_t)r * cols + c]);
+      return reinterpret_cast<const float*>(logits_)[(size_t)r * cols + c];
+    };
+    float m = -INFINITY;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, load(c));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += __expf(load(c) - m);
+    s = warp_sum(s);
+    const int label = (int)labels[r];
+    const float inv_s = 1.f / s;
+    for (int c = lane; c < cols; c += 32) {
+      const float z = load(c);
+      const float g = (__expf(z - m) * inv_s - (c == label ? 1.f : 0.f)) * inv_rows;
+      if (dl) dl[(size_t)r * cols + c] = g;
+      if (dl_bf16) dl_bf16[(size_t)r * cols + c] = __float2bfloat16(g);
+      if (c == label) loss_acc += (__logf(s) + m) - z;
+    }
+  }
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc * inv_rows);
+}
+
+__global__ void eval_binary_kernel(const float* __restrict__ p, const float* __restrict__ y,
+                                   float* __restrict__ loss_sum, int* __restrict__ correct, int64_t n) {
+  __shared__ float scratch[32];
+  float acc = 0.f;
+  int ok = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float q = p[i], t = y[i];
+    const float lp = fmaxf(__logf(q), -100.f), l1p = fmaxf(log1pf(-q), -100.f);
+    acc -= t * lp + (1.f - t) * l1p;
+    ok += (rintf(q) == t) ? 1 : 0;
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, acc);
+  ok = __reduce_add_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && ok) atomicAdd(correct, ok);
+}
+
+__global__ void argmax_rows_kernel(const float* __restrict__ x, int64_t* __restrict__ out, int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < cols; c += 32) {
+      const float v = x[(size_t)r * cols + c];
+      if (v > best || (v == best && c < bi)) { best = v; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) out[r] = bi;
+  }
+}
+
+// MinMax: one block per column pass 1 (min/max), pass 2 scale.  cols is tiny (10).
+__global__ void minmax_scale_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols) {
+  __shared__ float smin[32], smax[32];
+  const int c = blockIdx.x;
+  float lo = INFINITY, hi = -INFINITY;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float v = x[(size_t)r * cols + c];
+    lo = fminf(lo, v); hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { smin[w] = lo; smax[w] = hi; }
+  __syncthreads();
+  lo = smin[0]; hi = smax[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) { lo = fminf(lo, smin[i]); hi = fmaxf(hi, smax[i]); }
+  float rng = hi - lo;
+  if (rng == 0.f) rng = 1.f;
+  const float inv = 1.f / rng;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x)
+    out[(size_t)r * cols + c] = (x[(size_t)r * cols + c] - lo) * inv;
+}
+
+// Keyed bijection on [0, n): 4-round Feistel network over 2*hb bits with cycle walking.
+__device__ __forceinline__ uint32_t mix32(uint32_t x, uint32_t k) {
+  x ^= k; x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+  return x;
+}
+__global__ void feistel_perm_kernel(int* __restrict__ out, int n, int rows, uint64_t seed) {
+  int bits = 1;
+  while ((1u << bits) < (uint32_t)n) ++bits;
+  const int hb = (bits + 1) >> 1;  // half width
+  const uint32_t mask = (1u << hb) - 1u;
+  const int64_t total = (int64_t)n * rows;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int row = (int)(e / n);
+    uint32_t v = (uint32_t)(e - (int64_t)row * n);
+    const uint32_t k0 = (uint32_t)seed ^ (0x51ED270Bu * (uint32_t)(row + 1));
+    const uint32_t k1 = (uint32_t)(seed >> 32) + 0x68E31DA4u * (uint32_t)(row + 1);
+    do {
+      uint32_t l = v >> hb, r = v & mask;
+#pragma unroll
+      for (int round = 0; round < 4; ++round) {
+        const uint32_t f = mix32(r, (round & 1 ? k1 : k0) + 0x9E3779B9u * round) & mask;
+        const uint32_t nl = r;
+        r = l ^ f;
+        l = nl;
+      }
+      v = (l << hb) | r;
+    } while (v >= (uint32_t)n);
+    out[e] = (int)v;
+  }
+}
+
+__global__ void fp32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((((uintptr_t)in) & 15) == 0) && ((((uintptr_t)out) & 7) == 0)) {
+    const int64_t n4 = n >> 2;
+    for (int64_t j = i0; j < n4; j += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(in) + j);
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(out)[j] = pk;
+    }
+    for (int64_t j = (n4 << 2) + i0; j < n; j += stride) out[j] = __float2bfloat16(in[j]);
+  } else {
+    for (int64_t j = i0; j < n; j += stride) out[j] = __float2bfloat16(in[j]);
+  }
+}
+
+__global__ void l2_flush_kernel(float* __restrict__ buf, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = (float)i;
+}
+
+}  // namespace
+
+cudaError_t launch_sgd_step(float* p, const float* g, float lr, int64_t n, cudaStream_t s) {
+  sgd_step_kernel<<<grid_for(n), kThreads, 0, s>>>(p, g, lr, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_sgd_step_bf16grad(float* p, const void* g, float lr, int64_t n, cudaStream_t s) {
+  sgd_step_bf16grad_kernel<<<grid_for(n), kThreads, 0, s>>>(p, reinterpret_cast<const __nv_bfloat16*>(g), lr, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_fedavg_apply(float* theta, const float* slots, int64_t slot_stride, const float* weights,
+                                int k, float server_lr, int64_t n, cudaStream_t s) {
+  if (k > 64) return cudaErrorInvalidValue;
+  fedavg_kernel<true><<<grid_for(n), kThreads, 0, s>>>(theta, slots, slot_stride, weights, k, server_lr, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_fedavg_flat(float* out, const float* slots, int64_t slot_stride, const float* weights,
+                               int k, int64_t n, cudaStream_t s) {
+  if (k > 64) return cudaErrorInvalidValue;
+  fedavg_kernel<false><<<grid_for(n), kThreads, 0, s>>>(out, slots, slot_stride, weights, k, 1.f, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_sigmoid_bce(const float* z, const float* y, float* dz, float* loss_out, int64_t n, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(loss_out, 0, sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  sigmoid_bce_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(z, y, dz, loss_out, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_sse(const float* out, const float* y, float* dz, float* loss_out, int64_t n, float scale, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(loss_out, 0, sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  sse_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(out, y, dz, loss_out, n, scale);
+  return cudaGetLastError();
+}
+cudaError_t launch_softmax_xent(const void* logits, int is_bf16, const int64_t* labels, float* dl, void* dl_bf16,
+                                float* loss_out, int rows, int cols, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(loss_out, 0, sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  const int wpb = kThreads / 32;
+  int blocks = (rows + wpb - 1) / wpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  if (is_bf16)
+    softmax_xent_kernel<true><<<blocks, kThreads, 0, s>>>(logits, labels, dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16), loss_out, rows, cols);
+  else
+    softmax_xent_kernel<false><<<blocks, kThreads, 0, s>>>(logits, labels, dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16), loss_out, rows, cols);
+  return cudaGetLastError();
+}
+cudaError_t launch_eval_binary(const float* p, const float* y, float* loss_sum, int* correct, int64_t n, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(loss_sum, 0, sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(correct, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  eval_binary_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(p, y, loss_sum, correct, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_argmax_rows(const float* x, int64_t* out, int rows, int cols, cudaStream_t s) {
+  const int wpb = kThreads / 32;
+  int blocks = (rows + wpb - 1) / wpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  argmax_rows_kernel<<<blocks, kThreads, 0, s>>>(x, out, rows, cols);
+  return cudaGetLastError();
+}
+cudaError_t launch_minmax_scale(const float* x, float* out, int rows, int cols, cudaStream_t s) {
+  minmax_scale_kernel<<<cols, 1024, 0, s>>>(x, out, rows, cols);
+  return cudaGetLastError();
+}
+cudaError_t launch_feistel_permutation(int* out, int n, int rows, uint64_t seed, cudaStream_t s) {
+  feistel_perm_kernel<<<grid_for((int64_t)n * rows, 1), kThreads, 0, s>>>(out, n, rows, seed);
+  return cudaGetLastError();
+}
+cudaError_t launch_fp32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t s) {
+  fp32_to_bf16_kernel<<<grid_for(n), kThreads, 0, s>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  return cudaGetLastError();
+}
+cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s) {
+  l2_flush_kernel<<<148 * 8, kThreads, 0, s>>>(buf, n);
+  return cudaGetLastError();
+}
+
+}  // namespace colearn

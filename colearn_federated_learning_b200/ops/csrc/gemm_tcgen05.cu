@@ -1,0 +1,411 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] . B[N,K]^T   (bf16 in, fp32 accumulate)
+//
+// Serves the Linear layers of the wide models: forward (bias+ReLU epilogue),
+// dgrad (ReLU-mask epilogue) and wgrad (fused bias-grad column sums + fused SGD update of the fp32
+// master weights and refresh of the bf16 shadows W / W^T).  All three are expressed as the same
+// "both operands K-major" product by keeping transposed bf16 copies that the producing epilogue
+// writes for free (out_bf16_t: lanes of a warp hold 32 consecutive rows, so the transposed store is
+// naturally coalesced).
+//
+// Fused broadcast -> GEMM: when ep.ready_flags is set, the TMA producer warp polls
+// (ld.acquire.sys) the per-chunk ready flag of the B rows it is about to fetch — flags that the
+// two-shot FedAvg kernel on a PEER GPU raises after writing the new weights over NVLink — then
+// issues fence.proxy.async before the cp.async.bulk.tensor, so the first layer's GEMM starts on
+// the tiles that have landed while later chunks are still in flight.
+//
+// Structure (persistent, 1 CTA / SM, 192 threads):
+//   warp 0   : TMA producer  (1 elected lane)     smem ring of kStages x {A 128x64, B 128x64} bf16, SW128
+//   warp 1   : TMEM alloc + MMA issuer (1 lane)   tcgen05.mma.cta_group::1.kind::f16, UMMA 128x128x16
+//   warps 2-5: epilogue                           tcgen05.ld 32x32b.x32 -> regs -> fused epilogue -> global
+//   TMEM     : 2 accumulator stages x 128 columns (epilogue of tile i overlaps mainloop of tile i+1)
+#include "colearn_kernels.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+namespace colearn {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int kStages = 6;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * BN;  // 256
+constexpr int kThreads = 192;
+constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+std::string g_last_error;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// K-major, 128B-swizzled smem operand descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, ignored for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct SharedBarriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    int M, int N, int K, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kStageBytesA;
+  SharedBarriers* bars = reinterpret_cast<SharedBarriers*>(smem + kStages * kStageBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = M / BM, n_tiles = N / BN, num_kb = K / BK;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+        if (ep.ready_flags != nullptr) {
+          // wait for the peer-written weight rows [n0, n0+BN) of this round, then make them
+          // visible to the async proxy before TMA touches them
+          const int64_t c_lo = n0 / ep.ready_chunk_rows, c_hi = (n0 + BN - 1) / ep.ready_chunk_rows;
+          for (int64_t c = c_lo; c <= c_hi; ++c)
+            while (ld_acquire_sys(ep.ready_flags + c) < ep.ready_epoch) __nanosleep(64);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+          tma_load_2d(smem_a + stage * kStageBytesA, &tmap_a, kb * BK, m0, &bars->full[stage]);
+          tma_load_2d(smem_b + stage * kStageBytesB, &tmap_b, kb * BK, n0, &bars->full[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * kStageBytesA));
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * kStageBytesB));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in (addr>>4) units
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->tmem_full[as]);
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        tmem_ld_wait();
+        const int col = n0 + c0;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (ep.colsum != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float s = f[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == (j & 31)) atomicAdd(ep.colsum + col + j, s);
+          }
+        }
+        if (ep.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(ep.bias + col + j);
+        }
+        if (ep.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (ep.relu_mask != nullptr) {
+          const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.relu_mask) + (size_t)row * N + col);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 mv = __ldg(mp + g);
+            const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+              const uint32_t lo = w[h] & 0xFFFFu, hi = w[h] >> 16;
+              if (!(lo != 0 && !(lo & 0x8000u))) f[g * 8 + h * 2] = 0.f;
+              if (!(hi != 0 && !(hi & 0x8000u))) f[g * 8 + h * 2 + 1] = 0.f;
+            }
+          }
+        }
+        if (ep.sgd_master != nullptr) {
+          float4* mp = reinterpret_cast<float4*>(ep.sgd_master + (size_t)row * N + col);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 w = mp[g];
+            w.x = fmaf(-ep.sgd_lr, f[g * 4 + 0], w.x); w.y = fmaf(-ep.sgd_lr, f[g * 4 + 1], w.y);
+            w.z = fmaf(-ep.sgd_lr, f[g * 4 + 2], w.z); w.w = fmaf(-ep.sgd_lr, f[g * 4 + 3], w.w);
+            mp[g] = w;
+            f[g * 4 + 0] = w.x; f[g * 4 + 1] = w.y; f[g * 4 + 2] = w.z; f[g * 4 + 3] = w.w;  // f now holds the new weights
+          }
+          if (ep.sgd_shadow != nullptr) {
+            uint4* sp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.sgd_shadow) + (size_t)row * N + col);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              sp[g] = make_uint4(pack2(f[g * 8], f[g * 8 + 1]), pack2(f[g * 8 + 2], f[g * 8 + 3]),
+                                 pack2(f[g * 8 + 4], f[g * 8 + 5]), pack2(f[g * 8 + 6], f[g * 8 + 7]));
+          }
+          if (ep.sgd_shadow_t != nullptr) {
+            __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(ep.sgd_shadow_t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tp[(size_t)(col + j) * M + row] = __float2bfloat16(f[j]);
+          }
+        } else {
+          if (ep.out_f32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * N + col);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) op[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+          }
+          if (ep.out_bf16 != nullptr) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + (size_t)row * N + col);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              op[g] = make_uint4(pack2(f[g * 8], f[g * 8 + 1]), pack2(f[g * 8 + 2], f[g * 8 + 3]),
+                                 pack2(f[g * 8 + 4], f[g * 8 + 5]), pack2(f[g * 8 + 6], f[g * 8 + 7]));
+          }
+          if (ep.out_bf16_t != nullptr) {
+            __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(ep.out_bf16_t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tp[(size_t)(col + j) * M + row] = __float2bfloat16(f[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int rows, cols;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 1000003u) ^ (std::hash<int>()(k.cols) * 10007u);
+  }
+};
+
+bool make_tmap(const void* ptr, int rows, int cols, CUtensorMap* out) {
+  // row-major [rows, cols] bf16; box = [128 rows, 64 cols] (64 bf16 = one 128-byte swizzle row)
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  MapKey key{ptr, rows, cols};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) { g_last_error = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return false; }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
+
+}  // namespace
+
+const char* gemm_tcgen05_last_error() { return g_last_error.c_str(); }
+
+cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0 || (M % BM) || (N % BN) || (K % BK)) {
+    g_last_error = "shape must satisfy M%128==0, N%128==0, K%64==0";
+    return cudaErrorInvalidValue;
+  }
+  if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
+  CUtensorMap ta, tb;
+  if (!make_tmap(A, M, K, &ta) || !make_tmap(B, N, K, &tb)) return cudaErrorInvalidValue;
+  static bool configured[64] = {false};
+  static int num_sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem) failed"; return e; }
+    cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    configured[dev & 63] = true;
+  }
+  const int tiles = (M / BM) * (N / BN);
+  int grid = tiles < num_sms[dev & 63] ? tiles : num_sms[dev & 63];
+  if (grid < 1) grid = 1;
+  gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+  return cudaGetLastError();
+}
+
+}  // namespace colearn

@@ -1,0 +1,63 @@
+"""tcgen05 GEMM front-end (csrc/gemm_tcgen05.cu) — SURVEY K7/K8.
+
+``C[M,N] = A[M,K] · B[N,K]^T`` with both operands K-major bf16, fp32 accumulation in TMEM and a
+fused epilogue (bias / ReLU / ReLU-mask / fp32+bf16+transposed outputs / fused SGD / bias-grad
+column sums / fused broadcast-consumption flags).  Shapes must satisfy ``M%128 == N%128 == 0``
+and ``K%64 == 0``; callers pad (see ``fl/layerwise.py``).  CPU tensors use the fp32 reference.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _ext
+
+
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] = None, relu: bool = False,
+              relu_mask: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
+              out_f32: Optional[torch.Tensor] = None, out_bf16_t: Optional[torch.Tensor] = None,
+              sgd_master: Optional[torch.Tensor] = None, sgd_lr: float = 0.0,
+              sgd_shadow: Optional[torch.Tensor] = None, sgd_shadow_t: Optional[torch.Tensor] = None,
+              colsum: Optional[torch.Tensor] = None, ready_flags: int = 0, ready_epoch: int = 0,
+              ready_chunk_rows: int = 1) -> None:
+    """Launch the tcgen05 GEMM; results land in the provided output tensors."""
+    if not a.is_cuda:
+        acc = a.float() @ b.float().t()
+        if colsum is not None:
+            colsum += acc.sum(0)
+        if bias is not None:
+            acc = acc + bias
+        if relu:
+            acc = torch.relu(acc)
+        if relu_mask is not None:
+            acc = acc * (relu_mask.float() > 0)
+        if sgd_master is not None:
+            sgd_master.sub_(sgd_lr * acc)
+            if sgd_shadow is not None:
+                sgd_shadow.copy_(sgd_master.to(torch.bfloat16))
+            if sgd_shadow_t is not None:
+                sgd_shadow_t.copy_(sgd_master.t().to(torch.bfloat16))
+            return
+        if out_f32 is not None:
+            out_f32.copy_(acc)
+        if out_bf16 is not None:
+            out_bf16.copy_(acc.to(torch.bfloat16))
+        if out_bf16_t is not None:
+            out_bf16_t.copy_(acc.t().to(torch.bfloat16))
+        return
+    _ext.require().gemm_tcgen05(a, b, bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
+                                float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(ready_flags), int(ready_epoch),
+                                int(ready_chunk_rows))
+
+
+def linear_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+                   out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """``relu?(x @ w.T + bias)`` for bf16 ``x[M,K]``, ``w[N,K]`` (tile-aligned shapes)."""
+    m, n = x.shape[0], w.shape[0]
+    out = torch.empty(m, n, device=x.device, dtype=out_dtype)
+    if out_dtype == torch.bfloat16:
+        gemm_bf16(x, w, bias=bias, relu=relu, out_bf16=out)
+    else:
+        gemm_bf16(x, w, bias=bias, relu=relu, out_f32=out)
+    return out

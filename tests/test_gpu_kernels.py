@@ -1,0 +1,185 @@
+"""sm_100a kernel numerics vs the plain-PyTorch fp32 reference of the same op (needs a GPU)."""
+import pytest
+import torch
+
+from colearn_federated_learning_b200 import ops
+from colearn_federated_learning_b200.models import FFNN, MLP, TestingRemote, flatten_params
+from colearn_federated_learning_b200.ops import reference as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def test_extension_loaded():
+    from colearn_federated_learning_b200.ops import _ext
+    assert _ext.require() is not None
+    assert _ext.so_path() is not None
+
+
+@pytest.mark.parametrize("ctor,loss", [(FFNN, "bce"), (FFNN, "sse"), (MLP, "xent"), (TestingRemote, "sse"), (TestingRemote, "mse")])
+@pytest.mark.parametrize("bsz,n,epochs,max_b", [(1, 97, 1, -1), (1, 200, 2, 150), (8, 203, 2, -1), (32, 64, 3, 5)])
+def test_persistent_mlp_matches_reference(ctor, loss, bsz, n, epochs, max_b):
+    torch.manual_seed(0)
+    model = ctor()
+    spec = model.spec
+    flat0 = flatten_params(model).clone()
+    x = torch.rand(n, spec.dims[0])
+    if loss == "xent":
+        y = torch.randint(0, spec.dims[-1], (n, 1)).float()
+    else:
+        y = (torch.rand(n, spec.dims[-1]) > 0.5).float()
+    perm = R.make_permutation(n, epochs, seed=5)
+    ref = flat0.clone()
+    ref_last = R.mlp_local_sgd(ref, spec.dims, x, y, perm, bsz, 0.05, epochs, max_b, loss, spec.out_activation)
+    got = flat0.clone().to(_dev())
+    last = ops.mlp_local_sgd(got, spec.dims, x.to(_dev()), y.to(_dev()), perm.to(_dev()), bsz, 0.05, epochs, max_b,
+                             loss, spec.out_activation)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.cpu(), ref, atol=2e-4, rtol=2e-3), (got.cpu() - ref).abs().max()
+    assert torch.allclose(last.cpu(), ref_last, atol=1e-3, rtol=1e-2)
+
+
+def test_persistent_mlp_multi_client_scale_and_delta():
+    torch.manual_seed(1)
+    model = MLP()
+    spec = model.spec
+    dev = _dev()
+    theta = flatten_params(model).clone().to(dev)
+    k, n = 5, 64
+    xs = [torch.rand(n, 10, device=dev) for _ in range(k)]
+    ys = [torch.randint(0, 2, (n, 1), device=dev).float() for _ in range(k)]
+    perm = R.make_permutation(n, 1, 9).to(dev)
+    slots = torch.zeros(k, theta.numel(), device=dev)
+    losses = torch.zeros(k, 2, device=dev)
+    w = [0.1, 0.2, 0.3, 0.15, 0.25]
+    tasks = [ops.ClientTask(x=xs[i], y=ys[i], theta_in=theta, theta_out=slots[i], perm=perm, loss_out=losses[i],
+                            out_scale=w[i], delta_mode=(i % 2 == 1)) for i in range(k)]
+    descs = ops.build_client_descs(tasks, dev)
+    ops.mlp_local_sgd_multi(spec.dims, spec.out_activation, descs, k, batch_size=1, lr=0.05, loss="xent")
+    torch.cuda.synchronize()
+    for i in range(k):
+        ref = theta.cpu().clone()
+        R.mlp_local_sgd(ref, spec.dims, xs[i].cpu(), ys[i].cpu(), perm.cpu(), 1, 0.05, 1, -1, "xent")
+        want = w[i] * (ref - theta.cpu()) if i % 2 == 1 else w[i] * ref
+        assert torch.allclose(slots[i].cpu(), want, atol=2e-4, rtol=2e-3)
+
+
+def test_mlp_forward():
+    torch.manual_seed(2)
+    for ctor in (FFNN, MLP, TestingRemote):
+        m = ctor()
+        flat = flatten_params(m).to(_dev())
+        x = torch.rand(300, m.spec.dims[0])
+        out = ops.mlp_forward(flat, m.spec.dims, x.to(_dev()), m.spec.out_activation)
+        assert torch.allclose(out.cpu(), m(x).detach(), atol=1e-5, rtol=1e-4)
+
+
+def test_sgd_and_fedavg():
+    dev = _dev()
+    torch.manual_seed(3)
+    for n in (5, 4994, 1 << 20, (1 << 20) + 3):
+        p, g = torch.randn(n, device=dev), torch.randn(n, device=dev)
+        want = p - 0.01 * g
+        ops.sgd_step(p, g, 0.01)
+        assert torch.allclose(p, want, atol=1e-6)
+    models = torch.randn(8, 4994, device=dev)
+    w = torch.rand(8, device=dev)
+    w = w / w.sum()
+    assert torch.allclose(ops.fedavg_flat(models, w), R.fedavg_flat(models, w), atol=1e-5)
+    theta = torch.randn(4994, device=dev)
+    want = R.fedavg_apply(theta.clone(), models, w, 0.7)
+    ops.fedavg_apply(theta, models, w, 0.7)
+    assert torch.allclose(theta, want, atol=1e-5)
+
+
+def test_losses():
+    dev = _dev()
+    torch.manual_seed(4)
+    z, y = torch.randn(1000, 1, device=dev) * 3, (torch.rand(1000, 1, device=dev) > 0.5).float()
+    l, dz = ops.sigmoid_bce(z, y)
+    rl, rdz = R.sigmoid_bce(z.cpu(), y.cpu())
+    assert torch.allclose(l.cpu(), rl, atol=1e-5) and torch.allclose(dz.cpu(), rdz, atol=1e-6)
+    out = torch.randn(500, 3, device=dev)
+    tgt = torch.randn(500, 3, device=dev)
+    l, d = ops.sse_loss(out, tgt)
+    assert torch.allclose(l.cpu(), ((out - tgt) ** 2).sum().cpu(), rtol=1e-5)
+    assert torch.allclose(d, 2 * (out - tgt), atol=1e-6)
+    for cols in (2, 10, 100):
+        logits = torch.randn(777, cols, device=dev) * 2
+        labels = torch.randint(0, cols, (777,), device=dev)
+        l, d = ops.softmax_xent(logits, labels)
+        rl, rd = R.softmax_xent(logits.cpu(), labels.cpu())
+        assert torch.allclose(l.cpu(), rl, atol=1e-5, rtol=1e-5)
+        assert torch.allclose(d.cpu(), rd, atol=1e-6)
+        lb, db = ops.softmax_xent(logits.to(torch.bfloat16), labels, bf16_grad=True)
+        assert db.dtype == torch.bfloat16 and abs(lb.item() - rl.item()) < 0.05
+
+
+def test_eval_argmax_minmax_perm_convert():
+    dev = _dev()
+    torch.manual_seed(5)
+    p = torch.rand(999, device=dev).clamp(1e-4, 1 - 1e-4)
+    y = (torch.rand(999, device=dev) > 0.5).float()
+    l, c = ops.eval_binary(p, y)
+    rl, rc = R.eval_binary(p.cpu(), y.cpu())
+    assert torch.allclose(l.cpu(), rl, rtol=1e-5) and int(c) == int(rc)
+    x = torch.randn(257, 10, device=dev)
+    assert torch.equal(ops.argmax_rows(x).cpu(), x.cpu().argmax(1, keepdim=True))
+    s = ops.minmax_scale(x)
+    assert torch.allclose(s.min(0).values, torch.zeros(10, device=dev), atol=1e-6)
+    assert torch.allclose(s.max(0).values, torch.ones(10, device=dev), atol=1e-6)
+    for n in (1, 2, 7, 1000, 4099):
+        pm = ops.device_permutation(n, 3, seed=11, device=dev).cpu()
+        for r in range(3):
+            assert sorted(pm[r].tolist()) == list(range(n))
+        if n > 100:
+            assert not torch.equal(pm[0], pm[1])
+    v = torch.randn(1003, device=dev)
+    assert torch.equal(ops.fp32_to_bf16(v), v.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 384, 512), (1024, 4096, 4096)])
+def test_gemm_tcgen05_plain(m, n, k):
+    dev = _dev()
+    torch.manual_seed(6)
+    a = (torch.randn(m, k, device=dev) * 0.5).to(torch.bfloat16)
+    b = (torch.randn(n, k, device=dev) * 0.5).to(torch.bfloat16)
+    out = torch.empty(m, n, device=dev, dtype=torch.float32)
+    ops.gemm_bf16(a, b, out_f32=out)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t()
+    err = (out - ref).abs().max().item()
+    assert err < 1e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_gemm_tcgen05_epilogues():
+    dev = _dev()
+    torch.manual_seed(7)
+    m, n, k = 256, 256, 192
+    a = (torch.randn(m, k, device=dev) * 0.3).to(torch.bfloat16)
+    b = (torch.randn(n, k, device=dev) * 0.3).to(torch.bfloat16)
+    bias = torch.randn(n, device=dev)
+    ref = a.float() @ b.float().t()
+    # bias + relu, bf16 + transposed outputs
+    o, ot = torch.empty(m, n, device=dev, dtype=torch.bfloat16), torch.empty(n, m, device=dev, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, b, bias=bias, relu=True, out_bf16=o, out_bf16_t=ot)
+    want = torch.relu(ref + bias)
+    assert torch.allclose(o.float(), want, atol=5e-2, rtol=2e-2)
+    assert torch.equal(ot, o.t().contiguous())
+    # relu mask (dgrad) + column sums (bias grad)
+    mask = (torch.randn(m, n, device=dev)).to(torch.bfloat16)
+    of = torch.empty(m, n, device=dev)
+    cs = torch.zeros(n, device=dev)
+    ops.gemm_bf16(a, b, relu_mask=mask, out_f32=of, colsum=cs)
+    assert torch.allclose(of, ref * (mask.float() > 0), atol=1e-2, rtol=1e-2)
+    assert torch.allclose(cs, ref.sum(0), atol=5e-2, rtol=1e-2)
+    # fused SGD on the fp32 master + shadow refresh
+    master = torch.randn(m, n, device=dev)
+    want_master = master - 0.1 * ref
+    sh, sht = torch.empty(m, n, device=dev, dtype=torch.bfloat16), torch.empty(n, m, device=dev, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, b, sgd_master=master, sgd_lr=0.1, sgd_shadow=sh, sgd_shadow_t=sht)
+    assert torch.allclose(master, want_master, atol=1e-2, rtol=1e-2)
+    assert torch.equal(sh, master.to(torch.bfloat16)) and torch.equal(sht, master.t().contiguous().to(torch.bfloat16))
