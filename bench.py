@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""Headline benchmark: FL rounds/sec on N GPUs of one box (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 3
+
+One **step = one federated round**: broadcast θ from the coordinator (rank 0) to the selected
+workers → each worker runs its local epoch(s) of SGD (forward, loss, backward, optimizer step —
+nothing skipped) on its private shard → FedAvg weighted reduce → server apply.  Default config is
+BASELINE.json config 2 (``mlp`` 10→64→64→2, batch 1 like the reference's ``Arguments``, 1 local
+epoch, sample-count-weighted FedAvg) with a FIXED total dataset that ``federate()`` splits into N
+contiguous shards (reference ``dataset.federate(workers)``, fc.py:347-350) — i.e. strong scaling.
+
+Timing: W untimed warm-up rounds, then K rounds each bracketed by CUDA events on the launching
+stream with an (untimed) L2 flush in between, barrier + synchronize on both sides of the region,
+MAX over ranks.  ``e2e`` re-measures through the same public API (``FederatedEngine.run_rounds``)
+with, every round, the H2D copy of the round's shard from pinned host memory and a D2H read of
+the round's loss, timed by the host clock.  ``--impl reference`` reports that the reference
+cannot be installed offline; ``--impl torch_nccl`` runs the stock-PyTorch + NCCL
+comparator from ``baseline/`` for the same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PUBLISHED_ROUNDS_PER_S = 0.1133  # 12 rounds x 1000 it, 2x RPi 3B+ (best published rounds/s)
+
+CONFIGS = {
+    # name: (model, total_samples, batch, local_epochs, select_k, description)
+    "cfg2": ("mlp", 8192, 1, 1, None, "3-layer MLP 10-64-64-2, 1 local epoch, all workers (BASELINE config 2)"),
+    "cfg3": ("mlp", 8192, 1, 5, 4, "same MLP, 5 local epochs, temporal window selects 4 of 8 (BASELINE config 3)"),
+    "ffnn": ("ffnn", 8192, 1, 1, None, "reference FFNN 10-50-30-10-1, BCE, 1 local epoch"),
+    "cfg4": ("resnet18", 2048, 128, 1, None, "ResNet-18 bf16 on synthetic 32x32 images (BASELINE config 4)"),
+    "cfg5": ("wide_mlp", 8192, 1024, 1, None, "wide MLP 10-4096x4-2 bandwidth sweep (BASELINE config 5)"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_nccl"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--samples", type=int, default=None, help="total samples across all workers (strong scaling)")
+    ap.add_argument("--batch-size", type=int, default=None)
+    ap.add_argument("--local-epochs", type=int, default=None)
+    ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    return ap.parse_args()
+
+
+def reference_unavailable() -> None:
+    why = ("reference is a flat script tree without setup.py/pyproject (pip: 'not installable') and needs "
+           "syft==0.2.x + torch 1.4 + paho-mqtt, none of which are in the offline wheelhouse")
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+
+
+def make_data(model: str, total: int, rank: int, world: int, seed: int = 0):
+    import torch
+    from colearn_federated_learning_b200.data import shard_bounds, synthetic_images, synthetic_unsw
+
+    if model == "resnet18":
+        x, y = synthetic_images(total, seed=seed)
+        y = y.float().view(-1, 1)
+    else:
+        x, y = synthetic_unsw(total, seed=seed)
+    lo, hi = shard_bounds(total, world)[rank]
+    return x[lo:hi].contiguous(), y[lo:hi].contiguous()
+
+
+def main() -> None:
+    args = parse_args()
+    if args.impl == "reference":
+        reference_unavailable()
+        return
+
+    import torch
+    import torch.distributed as dist
+    from colearn_federated_learning_b200.parallel import init_distributed, shutdown
+    from colearn_federated_learning_b200.utils.monitors import NvmlSampler
+
+    rank, world, device = init_distributed()
+    if world != args.gpus and rank == 0:
+        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    if device.type != "cuda":
+        print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device on this box"}))
+        return
+
+    model, total, bsz, epochs, select_k, desc = CONFIGS[args.config]
+    total = args.samples or total
+    bsz = args.batch_size or bsz
+    epochs = args.local_epochs or epochs
+    K, W = args.steps, max(3, args.warmup)
+    x, y = make_data(model, total, rank, world)
+    n_local = x.shape[0]
+    mask = None
+    if select_k is not None and select_k < world:
+        mask = (1 << select_k) - 1  # registration order = rank order ("first" policy)
+
+    flush_buf = None
+    if not args.no_flush:
+        flush_buf = torch.empty(160 * 1024 * 1024 // 4, device=device)  # 160 MB > 126 MB L2
+
+    def max_over_ranks(v: float) -> float:
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = NvmlSampler(index=device.index or 0, period_s=0.02)
+    launches = 0
+    extra = {}
+
+    if args.impl == "ours":
+        from colearn_federated_learning_b200 import ops
+        from colearn_federated_learning_b200.parallel import FederatedEngine
+
+        engine = FederatedEngine(model, backend="fused", device=device, batch_size=bsz, lr=args.lr, local_epochs=epochs,
+                                 weighted=True, seed=1, bf16_shadow=(model == "wide_mlp"))
+        engine.set_local_data(x, y)
+        for _ in range(W):
+            engine.run_rounds(1, masks=mask)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler.start()
+        dev_ms = 0.0
+        for _ in range(K):
+            if flush_buf is not None:
+                ops.l2_flush(flush_buf)
+            rep = engine.run_rounds(1, masks=mask)
+            dev_ms += rep.device_ms
+            launches += rep.launches
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop()
+        dev_ms = max_over_ranks(dev_ms)
+        extra = dict(rep.extra)
+        # pipelined variant: K rounds enqueued in one call, no host in the loop, no flush
+        rep_p = engine.run_rounds(K, masks=mask)
+        extra["pipelined_rounds_per_s"] = K / (max_over_ranks(rep_p.device_ms) * 1e-3)
+        extra["final_mean_loss"] = float(rep_p.losses[-1, :, 1].mean()) if rep_p.losses is not None else None
+
+        e2e = None
+        if not args.no_e2e:
+            hx, hy = x.pin_memory(), y.pin_memory()
+            for _ in range(2):
+                engine.run_rounds(1, masks=mask, host_inputs=[(hx, hy)], read_back=True, barrier=False)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                engine.run_rounds(1, masks=mask, host_inputs=[(hx, hy)], read_back=True, barrier=False)
+            torch.cuda.synchronize()
+            wall = max_over_ranks(time.perf_counter() - t0)
+            e2e = {"value": K / wall, "unit": "rounds/s",
+                   "h2d_bytes_per_step": int(hx.numel() * hx.element_size() + hy.numel() * hy.element_size()),
+                   "d2h_bytes_per_step": int(engine.loss_host.numel() * 4) if rank == 0 else 8,
+                   "timing": "host clock, max over ranks, sync both sides"}
+        impl = "ours"
+    else:  # torch_nccl comparator
+        from baseline.torch_nccl_fedavg import TorchNcclFedAvg
+        from colearn_federated_learning_b200.models import build_model, DEFAULT_LOSS
+
+        torch.manual_seed(1)
+        eng = TorchNcclFedAvg(build_model(model), device, loss=DEFAULT_LOSS[model], batch_size=bsz, lr=args.lr,
+                              epochs=epochs, weighted=True, bf16_autocast=(model in ("resnet18", "wide_mlp")))
+        eng.set_local_data(x, y)
+        hx, hy = x.pin_memory(), y.pin_memory()
+        for _ in range(W):
+            eng.run_round(mask)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler.start()
+        dev_ms = 0.0
+        for _ in range(K):
+            if flush_buf is not None:
+                flush_buf.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.run_round(mask)
+            e1.record()
+            torch.cuda.synchronize()
+            dev_ms += e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop()
+        dev_ms = max_over_ranks(dev_ms)
+        e2e = None
+        if not args.no_e2e:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                eng.run_round(mask, host_inputs=(hx, hy))
+            torch.cuda.synchronize()
+            wall = max_over_ranks(time.perf_counter() - t0)
+            e2e = {"value": K / wall, "unit": "rounds/s",
+                   "h2d_bytes_per_step": int(hx.numel() * hx.element_size() + hy.numel() * hy.element_size()),
+                   "d2h_bytes_per_step": 4, "timing": "host clock, max over ranks, sync both sides"}
+        impl = "torch_nccl_comparator"
+
+    value = K / (dev_ms * 1e-3)
+    if rank == 0:
+        steps_per_round = epochs * ((n_local + bsz - 1) // bsz)
+        out = {
+            "metric": "FL rounds/sec (whole box, device-timed, max over ranks)",
+            "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": value / PUBLISHED_ROUNDS_PER_S,
+            "dtype": "bf16" if model in ("resnet18", "wide_mlp") else "fp32",
+            "data": "synthetic UNSW-IoT-shaped features / random-init weights" if model != "resnet18"
+                    else "synthetic 32x32 images / random-init weights",
+            "impl": impl,
+            "config": {"name": args.config, "model": model, "description": desc, "global_batch": bsz * world,
+                       "batch_size_per_worker": bsz, "seq_len": None, "parallelism": f"fedavg-dp{world}",
+                       "total_samples": total, "samples_per_worker": n_local, "local_epochs": epochs,
+                       "local_sgd_steps_per_round": steps_per_round, "selected_workers": select_k or world,
+                       "fedavg": "sample-count weighted", "l2": "flushed between timed rounds (160 MB write)" if flush_buf is not None else "not flushed",
+                       "baseline_ref": "0.1133 rounds/s = 12 rounds x 1000 it on 2x RPi 3B+ (BASELINE.md)", **extra},
+            "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []),
+                       "power_w_max": clocks.get("power_w_max"), "samples": clocks.get("samples")},
+            "e2e": e2e,
+            "gpu_launches": launches,
+        }
+        print(json.dumps(out))
+    shutdown()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,250 @@
+"""Worker handles and the device-side worker runtime.
+
+Replaces PySyft's ``VirtualWorker`` / ``WebsocketClientWorker`` / ``WebsocketServerWorker``
+(instantiated at ``federated_coordinator.py:149,167`` and ``remote_worker.py:95``).
+
+* :class:`VirtualWorker` — in-process worker object (local mode, fc.py:139-149).
+* :class:`WorkerServer` — device-side runtime (``remote_worker.py`` hosts one): owns the private
+  dataset under key ``"training"`` (rw.py:108) and tagged inference tensors (rw.py:102-104) and
+  serves ``fit`` / ``search`` / ``predict`` / ``ping`` RPCs.
+* :class:`RemoteWorkerClient` — coordinator-side handle with the same verbs.
+
+Wire format: 4-byte big-endian length + msgpack map; tensors travel as raw little-endian fp32
+bytes of the **flat arena** (9.6 kB for FFNN instead of ≈36 kB of TorchScript+msgpack per leg,
+SURVEY §2.5).  Workers never execute code received from the wire: the model is chosen by name
+from the registry and the loss by name — unlike the reference, which ships TorchScript.
+"""
+from __future__ import annotations
+
+import logging
+import socket
+import socketserver
+import struct
+import threading
+from typing import Any, Dict, List, Optional, Tuple
+
+import msgpack
+import numpy as np
+import torch
+
+from ..data import dataset_tensors
+from ..fl.trainer import FitConfig, local_fit
+from ..fl.evaluate import predict as predict_fn
+from ..models import build_model, flatten_params, num_params
+
+log = logging.getLogger(__name__)
+
+
+class VirtualWorker:
+    """In-process worker.  Data arrives via ``federate()`` at training time (reference local mode)
+    or can be attached up-front with :meth:`add_dataset`."""
+
+    def __init__(self, worker_id: str, device: Optional[torch.device] = None) -> None:
+        self.id = worker_id
+        self.device = device
+        self.datasets: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.tagged: Dict[str, List[torch.Tensor]] = {}
+
+    def add_dataset(self, dataset, key: str = "training") -> None:
+        self.datasets[key] = dataset_tensors(dataset, self.device)
+
+    def load_data(self, tensors: List[torch.Tensor], tag: str = "inference") -> None:
+        self.tagged.setdefault(tag, []).extend(tensors)
+
+    def search(self, tag: str) -> List[torch.Tensor]:
+        return list(self.tagged.get(tag, []))
+
+    def close(self) -> None:
+        pass
+
+    def __repr__(self) -> str:
+        return f"<VirtualWorker id:{self.id}>"
+
+
+# ---------------------------------------------------------------------------------------------
+# framing
+# ---------------------------------------------------------------------------------------------
+def _send_msg(sock: socket.socket, obj: Dict[str, Any]) -> None:
+    data = msgpack.packb(obj, use_bin_type=True)
+    sock.sendall(struct.pack(">I", len(data)) + data)
+
+
+def _recv_exact(sock: socket.socket, n: int) -> bytes:
+    buf = bytearray()
+    while len(buf) < n:
+        chunk = sock.recv(n - len(buf))
+        if not chunk:
+            raise ConnectionError("peer closed the connection")
+        buf.extend(chunk)
+    return bytes(buf)
+
+
+def _recv_msg(sock: socket.socket) -> Dict[str, Any]:
+    (n,) = struct.unpack(">I", _recv_exact(sock, 4))
+    return msgpack.unpackb(_recv_exact(sock, n), raw=False)
+
+
+def _to_bytes(t: torch.Tensor) -> bytes:
+    return t.detach().to("cpu", torch.float32).contiguous().numpy().tobytes()
+
+
+def _from_bytes(b: bytes, device=None) -> torch.Tensor:
+    t = torch.from_numpy(np.frombuffer(b, dtype=np.float32).copy())
+    return t.to(device) if device is not None else t
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side runtime
+# ---------------------------------------------------------------------------------------------
+class WorkerServer:
+    def __init__(self, worker_id: str, host: str, port: int, device: Optional[torch.device] = None,
+                 verbose: bool = False) -> None:
+        self.id = worker_id
+        self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.verbose = verbose
+        self.datasets: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.tagged: Dict[str, List[torch.Tensor]] = {}
+        self.fits_served = 0
+        self._round = 0
+        outer = self
+
+        class Handler(socketserver.BaseRequestHandler):
+            def handle(self) -> None:
+                while True:
+                    try:
+                        req = _recv_msg(self.request)
+                    except (ConnectionError, OSError, struct.error):
+                        return
+                    try:
+                        resp = outer._dispatch(req)
+                    except Exception as e:  # noqa: BLE001 - report to the coordinator, keep serving
+                        log.exception("worker RPC failed")
+                        resp = {"ok": False, "error": repr(e)}
+                    try:
+                        _send_msg(self.request, resp)
+                    except OSError:
+                        return
+                    if req.get("op") == "close":
+                        return
+
+        class Server(socketserver.ThreadingMixIn, socketserver.TCPServer):
+            allow_reuse_address = True
+            daemon_threads = True
+
+        self._server = Server((host, port), Handler)
+        self.host, self.port = self._server.server_address[:2]
+        self._thread: Optional[threading.Thread] = None
+
+    # -- data hosting (rw.py:97-108) -------------------------------------------------------
+    def add_dataset(self, dataset, key: str = "training") -> None:
+        self.datasets[key] = dataset_tensors(dataset, self.device)
+
+    def load_data(self, tensors: List[torch.Tensor], tag: str = "inference") -> None:
+        self.tagged.setdefault(tag, []).extend(t.to(self.device) for t in tensors)
+
+    # -- RPC -----------------------------------------------------------------------------------
+    def _dispatch(self, req: Dict[str, Any]) -> Dict[str, Any]:
+        op = req.get("op")
+        if self.verbose:
+            log.info("worker %s <- %s", self.id, op)
+        if op == "ping":
+            return {"ok": True, "id": self.id}
+        if op == "close":
+            return {"ok": True}
+        if op == "search":
+            return {"ok": True, "count": len(self.tagged.get(req["tag"], []))}
+        if op == "fit":
+            cfg = FitConfig.from_dict(req["config"])
+            x, y = self.datasets[req.get("dataset_key", "training")]
+            model = build_model(cfg.model)
+            flat = _from_bytes(req["params"], self.device)
+            if flat.numel() != num_params(model):
+                return {"ok": False, "error": f"param count {flat.numel()} != {num_params(model)} for {cfg.model}"}
+            spec = getattr(model, "spec", None)
+            if spec is not None and not spec.flatten_input and x.shape[1] != spec.dims[0]:
+                return {"ok": False, "error": f"dataset has {x.shape[1]} features, {cfg.model} wants {spec.dims[0]}"}
+            model.to(self.device)
+            loss, path = local_fit(flat, model, x, y, cfg, round_idx=self._round)
+            self._round += 1
+            self.fits_served += 1
+            return {"ok": True, "params": _to_bytes(flat), "loss": float(loss), "n": int(x.shape[0]), "path": path}
+        if op == "predict":
+            cfg_model = req["model"]
+            model = build_model(cfg_model).to(self.device)
+            flat = _from_bytes(req["params"], self.device)
+            data = self.tagged.get(req.get("tag", "inference"), [])
+            if not data:
+                return {"ok": True, "pred": [], "count": 0}
+            x = torch.stack([d.reshape(-1) for d in data]).float()
+            pred = predict_fn(model, x, flat)
+            return {"ok": True, "pred": pred.reshape(-1).tolist(), "count": len(data)}
+        return {"ok": False, "error": f"unknown op {op!r}"}
+
+    def start(self, block: bool = True) -> None:
+        if block:
+            self._server.serve_forever()
+        else:
+            self._thread = threading.Thread(target=self._server.serve_forever, name=f"worker-{self.id}", daemon=True)
+            self._thread.start()
+
+    def stop(self) -> None:
+        self._server.shutdown()
+        self._server.server_close()
+
+
+# ---------------------------------------------------------------------------------------------
+# coordinator-side handle
+# ---------------------------------------------------------------------------------------------
+class RemoteWorkerClient:
+    def __init__(self, worker_id: str, host: str, port: int, timeout: Optional[float] = 10.0,
+                 verbose: bool = False) -> None:
+        self.id = worker_id
+        self.host, self.port = host, port
+        self.verbose = verbose
+        self._lock = threading.Lock()
+        self._sock: Optional[socket.socket] = socket.create_connection((host, port), timeout=timeout)
+        self._sock.settimeout(None)
+
+    def _call(self, req: Dict[str, Any], timeout: Optional[float] = None) -> Dict[str, Any]:
+        with self._lock:
+            if self._sock is None:
+                raise ConnectionError(f"worker {self.id} is closed")
+            self._sock.settimeout(timeout)
+            _send_msg(self._sock, req)
+            resp = _recv_msg(self._sock)
+        if not resp.get("ok", False):
+            raise RuntimeError(f"worker {self.id}: {resp.get('error')}")
+        return resp
+
+    def ping(self) -> bool:
+        return bool(self._call({"op": "ping"}, timeout=5.0).get("ok"))
+
+    def fit(self, flat: torch.Tensor, cfg: FitConfig, dataset_key: str = "training",
+            timeout: Optional[float] = None) -> Tuple[torch.Tensor, float, int]:
+        """Broadcast leg + remote local-SGD + gather leg (cf.py:209-211) in one RPC."""
+        resp = self._call({"op": "fit", "config": cfg.to_dict(), "params": _to_bytes(flat),
+                           "dataset_key": dataset_key}, timeout=timeout)
+        return _from_bytes(resp["params"]), float(resp["loss"]), int(resp["n"])
+
+    def search(self, tag: str) -> int:
+        return int(self._call({"op": "search", "tag": tag}).get("count", 0))
+
+    def predict(self, flat: torch.Tensor, model_name: str, tag: str = "inference") -> List[int]:
+        return list(self._call({"op": "predict", "params": _to_bytes(flat), "model": model_name, "tag": tag})["pred"])
+
+    def close(self) -> None:
+        with self._lock:
+            if self._sock is None:
+                return
+            try:
+                _send_msg(self._sock, {"op": "close"})
+                _recv_msg(self._sock)
+            except (OSError, ConnectionError, struct.error):
+                pass
+            try:
+                self._sock.close()
+            finally:
+                self._sock = None
+
+    def __repr__(self) -> str:
+        return f"<RemoteWorkerClient id:{self.id}>"

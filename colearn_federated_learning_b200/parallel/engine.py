@@ -1,0 +1,389 @@
+"""FederatedEngine — the round loop of the reference mapped onto the GPUs of one box.
+
+One process per GPU.  Rank ``coordinator_rank`` (0) hosts the coordinator role *and* is a worker
+(co-located); every rank holds a private shard.  One **round** is what the
+reference's ``training_remote`` loop body does (``federated_coordinator.py:540-568``):
+
+    broadcast θ to the selected workers      train_config.send(worker)      cf.py:209   (K1)
+    each worker: local SGD on its shard      worker.async_fit(...)          cf.py:210   (K12)
+    gather the trained models                model_ptr.get()                cf.py:211   (K2)
+    θ ← FedAvg (uniform or n_k-weighted)     utils.federated_avg(models)    fc.py:568   (K3)
+
+Backends
+  ``fused``  hand-written kernels over symmetric memory, **no NCCL on the round path**:
+             * ``star``    (persistent-MLP models): the worker kernel waits for the broadcast flag,
+               trains, writes ``w_k·θ_k`` straight into the coordinator's slot over NVLink and
+               raises an arrive flag; ONE coordinator kernel then reduces + applies + pushes the
+               next round's θ into every selected inbox.  2 launches/round on rank 0, 1 elsewhere.
+             * ``twoshot`` (large models): in-place symmetric all-reduce-with-apply on the work
+               arenas (``twoshot_fedavg_kernel``), dual fp32 + bf16 write, per-chunk ready flags.
+  ``cpu``    gloo + ``ops.reference`` — same semantics, for tests on a GPU-less box.
+The ``nccl`` comparator lives in ``baseline/`` and shares none of this code.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+import time
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import ops
+from ..fl.fedavg import normalized_weights
+from ..fl.trainer import FitConfig, local_fit, resolve_loss
+from ..models import MLPNet, build_model, flatten_params, num_params, unflatten_params, state_dict_from_flat
+from ..ops import reference
+from ..utils.checkpoint import save_state_dict
+
+log = logging.getLogger(__name__)
+
+
+def _dist_ready() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+@dataclass
+class RoundReport:
+    rounds: int
+    world: int
+    backend: str
+    algo: str
+    device_ms: float                      # CUDA-event time of the whole call on this rank
+    losses: Optional[torch.Tensor] = None  # [rounds, world, 2] (coordinator) last/mean loss per worker
+    launches: int = 0                      # kernels of this repo launched inside the timed region
+    bytes_bcast: int = 0
+    bytes_reduce: int = 0
+    extra: Dict[str, Any] = field(default_factory=dict)
+
+
+class FederatedEngine:
+    def __init__(self, model: str = "mlp", *, backend: str = "auto", device: Optional[torch.device] = None,
+                 group: Optional[dist.ProcessGroup] = None, batch_size: int = 1, lr: float = 0.01,
+                 local_epochs: int = 1, max_batches: int = -1, loss: str = "auto", weighted: bool = True,
+                 server_lr: float = 1.0, coordinator_rank: int = 0, algo: str = "auto", seed: int = 1,
+                 shuffle: bool = True, chunk_elems: int = 65536, bf16_shadow: bool = False,
+                 model_kwargs: Optional[Dict[str, Any]] = None) -> None:
+        self.rank = dist.get_rank(group) if _dist_ready() else 0
+        self.world = dist.get_world_size(group) if _dist_ready() else 1
+        self.group = group
+        self.coord = coordinator_rank
+        if device is None:
+            if torch.cuda.is_available():
+                device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", self.rank % max(1, torch.cuda.device_count()))))
+            else:
+                device = torch.device("cpu")
+        self.device = torch.device(device)
+        if backend == "auto":
+            backend = "fused" if self.device.type == "cuda" else "cpu"
+        if backend == "fused" and self.device.type != "cuda":
+            raise RuntimeError("backend 'fused' needs a CUDA device")
+        self.backend = backend
+        self.model_name = model
+        torch.manual_seed(seed)  # identical init on every rank (only the coordinator's copy matters)
+        self.model: nn.Module = build_model(model, **(model_kwargs or {}))
+        self.spec = self.model.spec if isinstance(self.model, MLPNet) else None
+        self.P = num_params(self.model)
+        self.P4 = (self.P + 3) // 4 * 4
+        self.cfg = FitConfig(model=model, loss=resolve_loss(model, loss), batch_size=batch_size, epochs=local_epochs,
+                             max_nr_batches=max_batches, lr=lr, shuffle=shuffle, seed=seed)
+        self.weighted = weighted
+        self.server_lr = server_lr
+        self.seed = seed
+        persistent = self.spec is not None and ops.net_kind_for(self.spec.dims, self.spec.out_activation) is not None
+        if algo == "auto":
+            algo = "star" if persistent else "twoshot"
+        if algo == "star" and backend == "fused" and not persistent:
+            raise ValueError(f"algo 'star' needs a persistent-kernel model, got {model}")
+        self.algo = algo
+        self.chunk_elems = int(chunk_elems)
+        self.bf16_shadow = bf16_shadow
+        self.epoch = 0          # monotonically increasing flag epoch (never reset)
+        self.rounds_done = 0
+        self.x: Optional[torch.Tensor] = None
+        self.y: Optional[torch.Tensor] = None
+        self.n_local = 0
+        self.counts: List[int] = [0] * self.world
+        self._stream_inputs: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+        if backend == "fused":
+            self._init_fused()
+        else:
+            self.theta = flatten_params(self.model).to(self.device)
+        self.model.to(self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def _init_fused(self) -> None:
+        from .symm import SymmetricArena
+
+        torch.cuda.set_device(self.device)
+        W, P4 = self.world, self.P4
+        if self.algo == "star":
+            layout = {"inbox": (P4, torch.float32), "slots": (W * P4, torch.float32), "flags": (64, torch.int32),
+                      "losses": (2 * W, torch.float32)}
+        else:
+            self.n_chunks = (P4 + self.chunk_elems - 1) // self.chunk_elems
+            layout = {"work": (P4, torch.float32), "chunk_flags": (self.n_chunks, torch.int32),
+                      "flags": (64, torch.int32), "losses": (2 * W, torch.float32)}
+            if self.bf16_shadow:
+                layout["shadow"] = (P4, torch.bfloat16)
+        self.arena = SymmetricArena(layout, self.device, self.group)
+        self.ext = ops._ext.require()
+        self.grid_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
+        flat = flatten_params(self.model).to(self.device)
+        if self.algo == "star":
+            self.theta = torch.zeros(P4, device=self.device)
+            self.theta[: self.P].copy_(flat)
+        else:
+            self.theta = self.arena.tensor("work")
+            self.theta[: self.P].copy_(flat)
+            self.weights_dev = torch.zeros(16, device=self.device)
+            if self.world > 1:
+                # initial model sync: every rank pulls the coordinator's arena over NVLink
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)
+                if self.rank != self.coord:
+                    self.ext.p2p_copy(self.arena.ptr("work"), self.arena.ptr("work", self.coord), P4, 0, 0, 296)
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)
+        self.loss_host = torch.zeros(2 * W, dtype=torch.float32).pin_memory()
+
+    # ------------------------------------------------------------------------------------------
+    def set_local_data(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Attach this rank's private shard (device-resident from here on)."""
+        self.x = x.to(self.device).float().contiguous()
+        yy = y.to(self.device).float()
+        self.y = (yy.view(-1, 1) if yy.dim() == 1 else yy).contiguous()
+        self.n_local = int(self.x.shape[0])
+        if _dist_ready() and self.world > 1:
+            gathered = [0] * self.world
+            dist.all_gather_object(gathered, self.n_local, group=self.group)
+            self.counts = [int(c) for c in gathered]
+        else:
+            self.counts = [self.n_local]
+
+    def load_global(self, flat: torch.Tensor) -> None:
+        self.theta[: self.P].copy_(flat.to(self.device).float().reshape(-1)[: self.P])
+
+    def global_flat(self) -> torch.Tensor:
+        return self.theta[: self.P]
+
+    def global_state_dict(self):
+        return state_dict_from_flat(self.model, self.global_flat())
+
+    def save_checkpoint(self, path: str) -> Optional[str]:
+        if self.rank != self.coord:
+            return None
+        return save_state_dict(self.global_state_dict(), path,
+                               meta={"rounds": self.rounds_done, "world": self.world, "model": self.model_name,
+                                     "backend": self.backend, "algo": self.algo, "sample_counts": self.counts})
+
+    # ------------------------------------------------------------------------------------------
+    def _round_weights(self, mask: int) -> List[float]:
+        sel = [k for k in range(self.world) if (mask >> k) & 1]
+        if not sel:
+            return [0.0] * self.world
+        w = normalized_weights([self.counts[k] for k in sel] if self.weighted else None, len(sel))
+        out = [0.0] * self.world
+        for k, v in zip(sel, w.tolist()):
+            out[k] = v
+        return out
+
+    def _masks(self, rounds: int, masks) -> List[int]:
+        full = (1 << self.world) - 1
+        if masks is None:
+            return [full] * rounds
+        if isinstance(masks, int):
+            return [masks & full] * rounds
+        assert len(masks) == rounds
+        return [int(m) & full for m in masks]
+
+    def run_rounds(self, rounds: int, masks=None, host_inputs: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
+                   read_back: bool = False, barrier: bool = True) -> RoundReport:
+        """Run ``rounds`` federated rounds.  ``masks``: selection bitmask(s) (bit k = rank k
+        trains).  ``host_inputs``: per-round pinned-host ``(x, y)`` for this rank, copied H2D
+        inside the round (end-to-end mode); ``read_back`` additionally copies each round's losses
+        D2H and synchronises per round.  ``barrier=False`` skips the host-side process-group
+        barriers around the timed region (rounds are self-synchronising through device flags)."""
+        self._barrier = barrier
+        if self.x is None and host_inputs is None:
+            raise RuntimeError("set_local_data() first")
+        ms = self._masks(rounds, masks)
+        if self.backend == "cpu":
+            return self._run_cpu(rounds, ms)
+        if self.algo == "star":
+            return self._run_star(rounds, ms, host_inputs, read_back)
+        return self._run_twoshot(rounds, ms, host_inputs, read_back)
+
+    # ------------------------------------------------------------------------------------------ star
+    def _run_star(self, rounds: int, masks: List[int], host_inputs, read_back: bool) -> RoundReport:
+        ext, arena, W, P4, r = self.ext, self.arena, self.world, self.P4, self.rank
+        dev = self.device
+        cfg = self.cfg
+        n = self.n_local if host_inputs is None else int(host_inputs[0][0].shape[0])
+        if host_inputs is not None and (self.x is None or self.x.shape[0] != n):
+            self.x = torch.empty(n, host_inputs[0][0].shape[1], device=dev)
+            self.y = torch.empty(n, 1, device=dev)
+            self.set_local_data(self.x, self.y)
+        e0 = self.epoch
+        perm = ops.device_permutation(n, cfg.epochs * rounds, self.seed * 1000003 + self.rounds_done + 17 * r, dev) \
+            if cfg.shuffle else None
+        coord_slots = arena.ptr("slots", self.coord, r * P4)
+        coord_loss = arena.ptr("losses", self.coord, 2 * r)
+        coord_arrive = arena.ptr("flags", self.coord, 1 + r)
+        tasks = []
+        for i in range(rounds):
+            w = self._round_weights(masks[i])[r]
+            p = perm[i * cfg.epochs:(i + 1) * cfg.epochs] if perm is not None else None
+            tasks.append(ops.ClientTask(x=self.x, y=self.y, theta_in=arena.ptr("inbox"), theta_out=coord_slots, perm=p,
+                                        loss_out=coord_loss, wait_flag=arena.ptr("flags"), wait_value=e0 + i + 1,
+                                        signal_flag=coord_arrive, signal_value=e0 + i + 1, out_scale=w))
+        descs = ops.build_client_descs(tasks, dev)
+        inbox_ptrs = arena.peer_ptrs("inbox")
+        bflag_ptrs = arena.peer_ptrs("flags")
+        n_blocks = max(1, min(148, (P4 // 4 + 255) // 256))
+        is_coord = r == self.coord
+        losses_log = torch.zeros(rounds, W, 2, device=dev) if is_coord else None
+        launches = 0
+        if _dist_ready() and W > 1 and self._barrier:
+            dist.barrier(group=self.group)
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+
+        def star(do_reduce: bool, do_bcast: bool, mask_reduce: int, mask_bcast: int, arrive_epoch: int, bcast_epoch: int):
+            # reduce over the workers of the finished round, broadcast to those of the next one
+            if do_reduce and do_bcast and mask_reduce != mask_bcast:
+                ext.star_round(self.theta.data_ptr(), arena.ptr("slots"), P4, arena.ptr("flags", None, 1), arrive_epoch,
+                               inbox_ptrs, bflag_ptrs, bcast_epoch, 0, mask_reduce, self.server_lr, P4, True, False,
+                               self.grid_counter.data_ptr(), n_blocks)
+                ext.star_round(self.theta.data_ptr(), arena.ptr("slots"), P4, arena.ptr("flags", None, 1), arrive_epoch,
+                               inbox_ptrs, bflag_ptrs, bcast_epoch, arena.mc_ptr("inbox") if mask_bcast == (1 << W) - 1 else 0,
+                               mask_bcast, self.server_lr, P4, False, True, self.grid_counter.data_ptr(), n_blocks)
+                return 2
+            mask = mask_reduce if do_reduce else mask_bcast
+            mc = arena.mc_ptr("inbox") if (do_bcast and mask == (1 << W) - 1) else 0
+            ext.star_round(self.theta.data_ptr(), arena.ptr("slots"), P4, arena.ptr("flags", None, 1), arrive_epoch,
+                           inbox_ptrs, bflag_ptrs, bcast_epoch, mc, mask, self.server_lr, P4, do_reduce, do_bcast,
+                           self.grid_counter.data_ptr(), n_blocks)
+            return 1
+
+        if is_coord:
+            launches += star(False, True, 0, masks[0], 0, e0 + 1)
+        for i in range(rounds):
+            if host_inputs is not None:
+                hx, hy = host_inputs[i]
+                self.x.copy_(hx, non_blocking=True)
+                self.y.copy_(hy.view(-1, 1), non_blocking=True)
+            if (masks[i] >> r) & 1:
+                ops.mlp_local_sgd_multi(self.spec.dims, self.spec.out_activation, descs, 1, cfg.batch_size, cfg.lr,
+                                        cfg.epochs, cfg.max_nr_batches, cfg.loss, desc_offset=i)
+                launches += 1
+            if is_coord:
+                last = i == rounds - 1
+                launches += star(True, not last, masks[i], masks[i + 1] if not last else 0, e0 + i + 1, e0 + i + 2)
+                losses_log[i].copy_(arena.tensor("losses").view(W, 2), non_blocking=True)
+                if read_back:
+                    self.loss_host.copy_(arena.tensor("losses"), non_blocking=True)
+                    torch.cuda.current_stream(dev).synchronize()
+            elif read_back:
+                torch.cuda.current_stream(dev).synchronize()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        self.epoch = e0 + rounds + 1
+        self.rounds_done += rounds
+        if _dist_ready() and W > 1 and self._barrier:
+            dist.barrier(group=self.group)
+        nsel = [bin(m).count("1") for m in masks]
+        return RoundReport(rounds, W, "fused", "star", ev0.elapsed_time(ev1), losses_log, launches,
+                           bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel),
+                           extra={"provider": arena.provider, "multicast": arena.has_multicast})
+
+    # ------------------------------------------------------------------------------------------ twoshot
+    def _local_train_inplace(self, round_idx: int) -> torch.Tensor:
+        """Local fit in place on the work arena (layer-wise tcgen05 trainer or torch autograd)."""
+        flat = self.theta[: self.P]
+        last, path = local_fit(flat, self.model, self.x, self.y, FitConfig(**{**self.cfg.to_dict()}), round_idx)
+        self._last_path = path
+        return last
+
+    def _run_twoshot(self, rounds: int, masks: List[int], host_inputs, read_back: bool) -> RoundReport:
+        ext, arena, W, P4, r = self.ext, self.arena, self.world, self.P4, self.rank
+        dev = self.device
+        if abs(self.server_lr - 1.0) > 1e-12:
+            raise NotImplementedError("twoshot supports server_lr == 1 (plain FedAvg) in this version")
+        work_ptrs = arena.peer_ptrs("work")
+        shadow_ptrs = arena.peer_ptrs("shadow") if self.bf16_shadow else []
+        cflag_ptrs = arena.peer_ptrs("chunk_flags")
+        arrive_ptrs = [arena.ptr("flags", k, 1 + r) for k in range(W)]  # my arrive slot on every rank
+        n_blocks = max(1, min(148 * 2, (self.n_chunks + W - 1) // W))
+        losses_log = torch.zeros(rounds, W, 2, device=dev)
+        launches = 0
+        e0 = self.epoch
+        if _dist_ready() and W > 1 and self._barrier:
+            dist.barrier(group=self.group)
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(rounds):
+            e = e0 + i + 1
+            if host_inputs is not None:
+                hx, hy = host_inputs[i]
+                if self.x is None or self.x.shape != hx.shape:
+                    self.x = torch.empty(hx.shape, device=dev, dtype=torch.float32)
+                    self.y = torch.empty(hy.shape[0], 1, device=dev)
+                    self.set_local_data(self.x, self.y)
+                self.x.copy_(hx, non_blocking=True)
+                self.y.copy_(hy.view(-1, 1), non_blocking=True)
+            if (masks[i] >> r) & 1:
+                last = self._local_train_inplace(self.rounds_done + i)
+                losses_log[i, r, 0] = last
+            wts = self._round_weights(masks[i])
+            self.weights_dev[:W].copy_(torch.tensor(wts, dtype=torch.float32), non_blocking=True)
+            ext.signal_peers(arrive_ptrs, e)
+            ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
+                               0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, n_blocks)
+            ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e)
+            launches += 3
+            if read_back:
+                self.loss_host[:2].copy_(losses_log[i, r], non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        self.epoch = e0 + rounds
+        self.rounds_done += rounds
+        if _dist_ready() and W > 1 and self._barrier:
+            dist.barrier(group=self.group)
+        nsel = [bin(m).count("1") for m in masks]
+        return RoundReport(rounds, W, "fused", "twoshot", ev0.elapsed_time(ev1), losses_log, launches,
+                           bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel),
+                           extra={"provider": arena.provider, "train_path": getattr(self, "_last_path", None),
+                                  "n_chunks": self.n_chunks})
+
+    # ------------------------------------------------------------------------------------------ cpu / gloo
+    def _run_cpu(self, rounds: int, masks: List[int]) -> RoundReport:
+        W, r = self.world, self.rank
+        t0 = time.perf_counter()
+        losses_log = torch.zeros(rounds, W, 2)
+        for i in range(rounds):
+            if _dist_ready() and W > 1:
+                dist.broadcast(self.theta, src=self.coord, group=self.group)          # K1
+            local = self.theta.clone()
+            loss = torch.zeros(())
+            if (masks[i] >> r) & 1:
+                loss, _ = local_fit(local, self.model, self.x, self.y, self.cfg, self.rounds_done + i)
+            w = self._round_weights(masks[i])[r]
+            contrib = local * w
+            lvec = torch.zeros(W, 2)
+            lvec[r, 0] = float(loss)
+            if _dist_ready() and W > 1:
+                dist.reduce(contrib, dst=self.coord, group=self.group)                 # K2 + K3
+                dist.reduce(lvec, dst=self.coord, group=self.group)
+            if r == self.coord:
+                self.theta.add_(self.server_lr * (contrib - self.theta))
+                losses_log[i] = lvec
+        self.rounds_done += rounds
+        return RoundReport(rounds, W, "cpu", "gloo", (time.perf_counter() - t0) * 1e3, losses_log, 0)

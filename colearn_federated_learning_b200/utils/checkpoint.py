@@ -27,7 +27,7 @@ def save_state_dict(state: Dict[str, torch.Tensor], path: str = DEFAULT_PATH,
                     meta: Optional[Dict[str, Any]] = None) -> str:
     d = os.path.dirname(os.path.abspath(path))
     os.makedirs(d, exist_ok=True)
-    fd, tmp = tempfile.mkstemp(prefix=".ckpt-", dir=d)
+    fd, tmp = tempfile.mkstemp(prefix="ckpt-tmp-", suffix=".pth", dir=d)
     os.close(fd)
     try:
         torch.save({k: v.detach().cpu() for k, v in state.items()}, tmp)

@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""CoLearn coordinator CLI (flag-compatible with the reference ``federated_coordinator.py:64-90``).
+
+    python federated_coordinator.py -t "topic/state"          # local (VirtualWorker) case
+    python federated_coordinator.py -t "topic/state" -r       # remote case
+
+Events are published to the bus as ``"(192.168.1.7, TRAINING)"`` (local) or
+``"(127.0.0.1, 8777, TRAINING)"`` (remote) — e.g. with ``python -m
+colearn_federated_learning_b200.tools.bus_pub -t topic/state -m "(192.168.1.7, TRAINING)"``, the
+stand-in for ``mosquitto_pub``.  ``--host embedded`` (default when ``--host localhost`` has no
+broker listening) starts the TCP bus broker inside this process.
+
+On a multi-GPU box launch it under torchrun with ``--box``: rank 0 hosts the coordinator role,
+every rank is a worker, and the broadcast / FedAvg legs run as fused NVLink kernels
+(``colearn_federated_learning_b200.parallel``).
+"""
+import argparse
+import logging
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from colearn_federated_learning_b200.control.arguments import Arguments  # noqa: E402
+from colearn_federated_learning_b200.models import MODEL_REGISTRY  # noqa: E402
+
+
+def build_parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(description="Run Federated coordinator")
+    # --- reference flags (fc.py:64-90) ---------------------------------------------------------
+    parser.add_argument("--port", "-p", type=int, default=1883, help="port number of the where the broker is listining (default 1883)")
+    parser.add_argument("--host", type=str, default="localhost", help="broker ip address (default localhost)")
+    parser.add_argument("--topic", "-t", type=str, required=True, help="topic where the event must be published")
+    parser.add_argument("--remote", "-r", action="store_true", help="Remote learning activation")
+    parser.add_argument("--window", "-w", type=int, default=1, help="temporal window size (default 1)")
+    parser.add_argument("--encryption", "-e", action="store_true", help="Simulates the encryption on two virtual workes")
+    parser.add_argument("--federated_round", "-f", type=int, default=1, help="number of federated rounds (round > 1 trains 1000 batches per round)")
+    parser.add_argument("--iot", "-i", action="store_true", help="enable iot validation (IP allow-list)")
+    # --- everything the reference hard-codes in Arguments / Coordinator.__init__ ------------------
+    d = Arguments()
+    parser.add_argument("--model", choices=sorted(MODEL_REGISTRY), default=d.model)
+    parser.add_argument("--loss", default=d.loss, choices=["auto", "bce", "sse", "xent", "mse"])
+    parser.add_argument("--batch-size", type=int, default=d.batch_size)
+    parser.add_argument("--local-epochs", type=int, default=d.epochs)
+    parser.add_argument("--max-batches", type=int, default=d.federate_after_n_batches, help="local SGD steps per round (-1 = full epoch; rounds>1 default to 1000)")
+    parser.add_argument("--lr", type=float, default=d.lr)
+    parser.add_argument("--server-lr", type=float, default=d.server_lr)
+    parser.add_argument("--seed", type=int, default=d.seed)
+    parser.add_argument("--log-interval", type=int, default=d.log_interval)
+    parser.add_argument("--test-path", type=str, default=d.test_path, help="CSV used by local/encrypted mode and evaluation")
+    parser.add_argument("--synthetic", type=int, default=0, help="use N synthetic UNSW-shaped rows instead of --test-path")
+    parser.add_argument("--weighted", action="store_true", help="sample-count weighted FedAvg (default: uniform, like the reference)")
+    parser.add_argument("--select", type=int, default=None, help="train at most k of the collected workers")
+    parser.add_argument("--selection", choices=["all", "first", "random"], default="all")
+    parser.add_argument("--checkpoint", type=str, default="./test.pth")
+    parser.add_argument("--no-cuda", action="store_true")
+    parser.add_argument("--strict-events", action="store_true", help="validate IPv4 octets / full match (reference is lax)")
+    parser.add_argument("--fit-timeout", type=float, default=None, help="seconds before a silent remote worker is dropped from a round")
+    parser.add_argument("--filter-file", type=str, default=None)
+    parser.add_argument("--metrics", type=str, default=None, help="write per-round JSONL here")
+    parser.add_argument("--round-log", type=str, default=None, help="write the reference-format round log here")
+    parser.add_argument("--evaluate", action="store_true", help="evaluate the global model on --test-path after training")
+    parser.add_argument("--embedded-broker", action="store_true", help="start the TCP bus broker inside this process")
+    parser.add_argument("--exit-after", type=int, default=0, help="exit after N completed trainings (0 = run forever)")
+    parser.add_argument("--box", action="store_true", help="multi-GPU box mode under torchrun (rank 0 = coordinator)")
+    parser.add_argument("--backend", choices=["auto", "fused", "nccl", "cpu"], default="auto")
+    return parser
+
+
+def arguments_from_cli(ns: argparse.Namespace) -> Arguments:
+    a = Arguments()
+    a.model, a.loss, a.batch_size, a.epochs = ns.model, ns.loss, ns.batch_size, ns.local_epochs
+    a.federate_after_n_batches, a.lr, a.server_lr, a.seed = ns.max_batches, ns.lr, ns.server_lr, ns.seed
+    a.log_interval, a.test_path, a.synthetic, a.weighted = ns.log_interval, ns.test_path, ns.synthetic, ns.weighted
+    a.no_cuda, a.backend = ns.no_cuda, ns.backend
+    return a
+
+
+def main(args: argparse.Namespace) -> None:
+    logging.basicConfig(format="%(asctime)s: %(message)s", level=logging.INFO, datefmt="%H:%M:%S")
+    logging.info(os.getpid())
+    if args.box:
+        from colearn_federated_learning_b200.parallel.box import run_box_coordinator
+        run_box_coordinator(args, arguments_from_cli(args))
+        return
+
+    from colearn_federated_learning_b200.control.bus import TcpBroker
+    from colearn_federated_learning_b200.control.coordinator import Coordinator
+    from colearn_federated_learning_b200.utils.metrics import RoundLogger
+    import socket
+    import time
+
+    broker = None
+    if args.embedded_broker:
+        broker = TcpBroker("127.0.0.1" if args.host == "localhost" else args.host, args.port).start()
+        logging.info("embedded bus broker listening on %s:%d", broker.host, broker.port)
+    coordinator = Coordinator(args.window, args.remote, args.federated_round, args.encryption, args.iot,
+                              args=arguments_from_cli(args), transport="tcp", path=args.checkpoint,
+                              strict_events=args.strict_events, select_k=args.select, selection=args.selection,
+                              fit_timeout=args.fit_timeout, filter_file=args.filter_file,
+                              metrics=RoundLogger(args.metrics, args.round_log), evaluate_after=args.evaluate)
+    try:
+        if args.exit_after > 0:
+            coordinator.run(args.host, args.port, args.topic, forever=False)
+            while coordinator.trainings_done < args.exit_after:
+                time.sleep(0.05)
+            coordinator.shutdown()
+        else:
+            coordinator.run(args.host, args.port, args.topic)
+    except (ConnectionRefusedError, socket.gaierror) as e:
+        logging.error("cannot reach the bus broker at %s:%d (%r); start one with --embedded-broker", args.host, args.port, e)
+        sys.exit(2)
+    finally:
+        if broker is not None:
+            broker.stop()
+
+
+if __name__ == "__main__":
+    main(build_parser().parse_args())

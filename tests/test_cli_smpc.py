@@ -1,0 +1,120 @@
+"""CLI flag parity + an end-to-end run of the real CLIs over the TCP bus; SMPC numerics."""
+import os
+import socket
+import subprocess
+import sys
+import time
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_coordinator_cli_flags_match_reference():
+    import federated_coordinator as fc
+    ns = fc.build_parser().parse_args(["-t", "topic/state"])
+    assert (ns.port, ns.host, ns.window, ns.federated_round, ns.remote, ns.encryption, ns.iot) == \
+        (1883, "localhost", 1, 1, False, False, False)
+    ns = fc.build_parser().parse_args(["-p", "1999", "--host", "h", "-t", "x", "-r", "-w", "3", "-e", "-f", "6", "-i"])
+    assert (ns.port, ns.host, ns.topic, ns.remote, ns.window, ns.encryption, ns.federated_round, ns.iot) == \
+        (1999, "h", "x", True, 3, True, 6, True)
+    with pytest.raises(SystemExit):
+        fc.build_parser().parse_args([])                # --topic is required
+
+
+def test_worker_cli_flags_match_reference():
+    import remote_worker as rw
+    ns = rw.build_parser().parse_args(["--host", "127.0.0.1", "-b", "localhost", "-t", "topic/state"])
+    assert (ns.port, ns.wait, ns.event, ns.training, ns.inference, ns.verbose) == (8777, 5, "TRAINING", None, None, False)
+    ns = rw.build_parser().parse_args(["--host", "1.2.3.4", "-p", "8778", "-b", "b", "-t", "t", "-w", "1", "-e", "INFERENCE",
+                                       "-dt", "a.csv", "-di", "b.csv", "-v"])
+    assert (ns.port, ns.event, ns.training, ns.inference, ns.verbose) == (8778, "INFERENCE", "a.csv", "b.csv", True)
+    for missing in (["-b", "b", "-t", "t"], ["--host", "h", "-t", "t"], ["--host", "h", "-b", "b"]):
+        with pytest.raises(SystemExit):
+            rw.build_parser().parse_args(missing)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_real_clis_remote_training_end_to_end(tmp_path):
+    """README flow: coordinator -r, two remote_worker.py processes on 127.0.0.1, 2 rounds → test.pth."""
+    bport, w1, w2 = _free_port(), _free_port(), _free_port()
+    ckpt = str(tmp_path / "test.pth")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    coord = subprocess.Popen([sys.executable, os.path.join(ROOT, "federated_coordinator.py"), "-t", "topic/state", "-r",
+                              "-w", "2", "-f", "2", "-p", str(bport), "--embedded-broker", "--checkpoint", ckpt,
+                              "--max-batches", "20", "--exit-after", "1", "--no-cuda",
+                              "--round-log", str(tmp_path / "round.txt")],
+                             env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    workers = []
+    try:
+        time.sleep(4.0)
+        for port in (w1, w2):
+            workers.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "remote_worker.py"), "--host", "127.0.0.1",
+                                             "-p", str(port), "-b", "127.0.0.1", "--broker-port", str(bport), "-t", "topic/state",
+                                             "-w", "1", "--synthetic", "64", "--no-cuda"], env=env,
+                                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        out, _ = coord.communicate(timeout=120)
+        assert coord.returncode == 0, out[-2000:]
+        assert os.path.exists(ckpt)
+        state = torch.load(ckpt, weights_only=True)
+        assert state["fc4.weight"].shape == (1, 10)
+        log = open(tmp_path / "round.txt").read()
+        assert "Testing round on: 20" in log and "Time round 1 :" in log and "Total training time:" in log
+        assert log.count("Loss for worker id: 127.0.0.1:") == 4
+    finally:
+        for w in workers:
+            w.kill()
+        if coord.poll() is None:
+            coord.kill()
+
+
+# ---- SMPC -------------------------------------------------------------------------------------------------------
+def test_fixed_point_and_sharing_roundtrip():
+    from colearn_federated_learning_b200.smpc import CryptoProvider, fix_precision, float_precision, share
+    x = torch.tensor([[0.1234, -5.5], [3.0, 0.0004]])
+    fx = fix_precision(x)
+    assert fx.dtype == torch.int64 and fx.tolist() == [[123, -5500], [3000, 0]]          # round(x * 10^3)
+    s = share(fx, CryptoProvider(1))
+    assert not torch.equal(s.shares[0], fx) and torch.equal(s.get(), fx)
+    assert torch.equal(s.refresh().get(), fx)
+    assert torch.allclose(float_precision(s.get()), torch.round(x * 1000) / 1000)
+
+
+def test_beaver_matmul_and_mul_are_correct():
+    from colearn_federated_learning_b200.smpc import CryptoProvider, fix_precision, float_precision, share
+    p = CryptoProvider(2)
+    a, b = torch.randn(4, 6), torch.randn(6, 3)
+    c = float_precision(share(fix_precision(a), p).matmul(share(fix_precision(b), p)).truncate().get())
+    assert (c - a @ b).abs().max() < 0.02
+    u, v = torch.randn(5), torch.randn(5)
+    w = float_precision(share(fix_precision(u), p).mul(share(fix_precision(v), p)).truncate().get())
+    assert (w - u * v).abs().max() < 0.01
+    bits = share(fix_precision(u), p).positive_bit().get()
+    assert bits.tolist() == (fix_precision(u) > 0).long().tolist()
+    assert p.triples_dealt == 2 and p.comparisons == 1
+
+
+def test_encrypted_training_tracks_plaintext_training():
+    from colearn_federated_learning_b200.models import FFNN
+    from colearn_federated_learning_b200.smpc import CryptoProvider, SharedMLP, fix_precision, float_precision, share
+    torch.manual_seed(0)
+    m = FFNN()
+    p = CryptoProvider(3)
+    sm = SharedMLP.from_module(m, p)
+    x, y = torch.rand(1, 10), torch.ones(1, 1)
+    losses = [float(float_precision(sm.step(share(fix_precision(x), p), share(fix_precision(y), p), 0.1).get()))
+              for _ in range(25)]
+    assert losses[-1] < losses[0] * 0.7
+    before = torch.cat([q.detach().reshape(-1) for q in m.parameters()]).clone()
+    sm.reveal_into(m)
+    after = torch.cat([q.detach().reshape(-1) for q in m.parameters()])
+    assert not torch.equal(before, after) and (m(x) > 0.5).all()
