@@ -1,0 +1,179 @@
+"""Layer-wise local training of wide MLPs on tcgen05 GEMMs (BASELINE config 5).
+
+Every Linear of the wide MLP (10 → 4096×4 → 2) runs on ``ops.gemm_bf16`` — the hand-written
+tcgen05/TMEM/TMA kernel — in three roles that all reduce to ``C = A·Bᵀ`` with K-major operands:
+
+    forward   H_l  = relu(H_{l-1} · W_lᵀ + b_l)       A = H_{l-1}[B,in]   B = W_l[out,in]   (+bias, relu)
+    dgrad     dZ_{l-1} = (dZ_l · W_l) ⊙ relu'          A = dZ_l[B,out]     B = W_lᵀ[in,out]  (+mask, +colsum = db)
+    wgrad     W_l ← W_l − lr · dZ_lᵀ · H_{l-1}         A = dZ_lᵀ[out,B]    B = H_{l-1}ᵀ[in,B] (+fused SGD on the
+                                                        fp32 master, bf16 shadows W / Wᵀ refreshed in the epilogue)
+
+The transposed activations / gradients the wgrad needs are written by the producing epilogues
+(``out_bf16_t``), the bias gradient is the post-mask column sum of the dgrad epilogue, the SGD
+step never materialises dW.  fp32 master weights live in the flat arena (what FedAvg
+averages); bf16 shadows of the three 4096×4096 layers are *views into the bf16 shadow arena* that
+the two-shot FedAvg kernel fills over NVLink, so the first forward GEMM of a round can poll the
+per-chunk ready flags and start on the rows that have landed (fused broadcast → GEMM).
+The 10-wide input and 2-wide head are zero-padded to tile multiples (128).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import ops
+from ..models import MLPSpec
+
+PAD = 128
+
+
+def _pad_to(n: int, m: int = PAD) -> int:
+    return (n + m - 1) // m * m
+
+
+class LayerwiseMLPTrainer:
+    _cache: Dict[Tuple, "LayerwiseMLPTrainer"] = {}
+
+    @staticmethod
+    def supports(spec: MLPSpec, cfg) -> bool:
+        hidden = spec.dims[1:-1]
+        return (len(hidden) >= 1 and all(h % 128 == 0 for h in hidden) and cfg.batch_size % 128 == 0
+                and cfg.loss == "xent" and spec.out_activation == "none")
+
+    @classmethod
+    def cached(cls, spec: MLPSpec, flat: torch.Tensor, batch_size: int) -> "LayerwiseMLPTrainer":
+        key = (spec.dims, flat.data_ptr(), batch_size)
+        tr = cls._cache.get(key)
+        if tr is None:
+            if len(cls._cache) > 4:
+                cls._cache.clear()
+            tr = cls._cache[key] = cls(spec, flat, batch_size)
+        return tr
+
+    def __init__(self, spec: MLPSpec, flat: torch.Tensor, batch_size: int, shadow: Optional[torch.Tensor] = None) -> None:
+        self.spec, self.B, self.dev = spec, batch_size, flat.device
+        self.dims = list(spec.dims)
+        self.L = spec.n_layers
+        self.offsets = spec.offsets()
+        self.kp = [_pad_to(d) for d in self.dims]          # padded widths
+        dev, bf = self.dev, torch.bfloat16
+        B = batch_size
+        self.shadow_arena = shadow                           # bf16 arena written by the two-shot broadcast (or None)
+        # bf16 shadows W_l [out_p, in_p] and W_l^T [in_p, out_p]
+        self.Ws: List[torch.Tensor] = []
+        self.WsT: List[torch.Tensor] = []
+        self.exact: List[bool] = []                          # layer needs no padding → fused SGD epilogue allowed
+        for l in range(self.L):
+            k, n = self.dims[l], self.dims[l + 1]
+            exact = (k == self.kp[l] and n == self.kp[l + 1])
+            self.exact.append(exact)
+            if exact and shadow is not None:
+                off = self.offsets[l][0]
+                self.Ws.append(shadow[off:off + n * k].view(n, k))   # zero-copy view of the broadcast payload
+            else:
+                self.Ws.append(torch.zeros(self.kp[l + 1], self.kp[l], device=dev, dtype=bf))
+            self.WsT.append(torch.zeros(self.kp[l], self.kp[l + 1], device=dev, dtype=bf))
+        self.bias_p = [torch.zeros(self.kp[l + 1], device=dev) for l in range(self.L)]
+        # activations (a[0] = padded input) and their transposes, gradients and their transposes
+        self.a = [torch.zeros(B, self.kp[l], device=dev, dtype=bf) for l in range(self.L)]
+        self.aT = [torch.zeros(self.kp[l], B, device=dev, dtype=bf) for l in range(self.L)]
+        self.dz = [torch.zeros(B, self.kp[l + 1], device=dev, dtype=bf) for l in range(self.L)]
+        self.dzT = [torch.zeros(self.kp[l + 1], B, device=dev, dtype=bf) for l in range(self.L)]
+        self.logits = torch.zeros(B, self.kp[self.L], device=dev)
+        self.db = [torch.zeros(self.kp[l + 1], device=dev) for l in range(self.L)]
+        self.dw_edge = {l: torch.zeros(self.kp[l + 1], self.kp[l], device=dev) for l in range(self.L) if not self.exact[l]}
+        self.launches = 0
+
+    # -- parameter views -----------------------------------------------------------------------------
+    def _w(self, flat: torch.Tensor, l: int) -> torch.Tensor:
+        off = self.offsets[l][0]
+        return flat[off:off + self.dims[l] * self.dims[l + 1]].view(self.dims[l + 1], self.dims[l])
+
+    def _b(self, flat: torch.Tensor, l: int) -> torch.Tensor:
+        off = self.offsets[l][1]
+        return flat[off:off + self.dims[l + 1]]
+
+    def refresh_shadows(self, flat: torch.Tensor, from_broadcast: bool = False) -> None:
+        """fp32 master → bf16 shadows (+ transposes).  With ``from_broadcast`` the exact layers' W
+        shadows were already written by the two-shot kernel; only the transposes are rebuilt."""
+        for l in range(self.L):
+            w = self._w(flat, l)
+            if self.exact[l]:
+                if not (from_broadcast and self.shadow_arena is not None):
+                    self.Ws[l].copy_(ops.fp32_to_bf16(w.contiguous().view(-1)).view_as(self.Ws[l]))
+                ops.transpose_bf16(self.Ws[l], self.WsT[l])
+            else:
+                self.Ws[l].zero_()
+                self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
+                ops.transpose_bf16(self.Ws[l], self.WsT[l])
+            self.bias_p[l].zero_()
+            self.bias_p[l][: self.dims[l + 1]].copy_(self._b(flat, l))
+
+    # -- one SGD step -------------------------------------------------------------------------------------
+    def step(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor, lr: float,
+             ready: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+        """``ready = (chunk_flags_ptr, epoch, chunk_elems)`` makes the forward GEMMs of the exact
+        layers poll the broadcast's per-chunk flags (first step of a round only)."""
+        L, B = self.L, self.B
+        self.a[0].zero_()
+        self.a[0][:, : self.dims[0]].copy_(x)
+        ops.transpose_bf16(self.a[0], self.aT[0])
+        # forward
+        for l in range(L):
+            kw = {}
+            if ready is not None and self.exact[l] and self.shadow_arena is not None:
+                kw = dict(ready_flags=ready[0], ready_epoch=ready[1], ready_chunk_elems=ready[2],
+                          ready_elem_offset=self.offsets[l][0])
+            if l < L - 1:
+                ops.gemm_bf16(self.a[l], self.Ws[l], bias=self.bias_p[l], relu=True, out_bf16=self.a[l + 1],
+                              out_bf16_t=self.aT[l + 1], **kw)
+            else:
+                ops.gemm_bf16(self.a[l], self.Ws[l], bias=self.bias_p[l], out_f32=self.logits, **kw)
+        nc = self.dims[-1]
+        loss, dlog = ops.softmax_xent(self.logits[:, :nc].contiguous(), labels)
+        self.dz[L - 1].zero_()
+        self.dz[L - 1][:, :nc].copy_(dlog)
+        ops.transpose_bf16(self.dz[L - 1], self.dzT[L - 1])
+        self.db[L - 1].zero_()
+        self.db[L - 1][:nc].copy_(dlog.sum(0))
+        # backward: dgrad with the old weights first, then the (fused) update of layer l
+        for l in range(L - 1, -1, -1):
+            if l > 0:
+                self.db[l - 1].zero_()
+                ops.gemm_bf16(self.dz[l], self.WsT[l], relu_mask=self.a[l], out_bf16=self.dz[l - 1],
+                              out_bf16_t=self.dzT[l - 1], colsum=self.db[l - 1])
+            if self.exact[l]:
+                ops.gemm_bf16(self.dzT[l], self.aT[l], sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l],
+                              sgd_shadow_t=self.WsT[l])
+            else:
+                ops.gemm_bf16(self.dzT[l], self.aT[l], out_f32=self.dw_edge[l])
+                w = self._w(flat, l)
+                w.sub_(self.dw_edge[l][: w.shape[0], : w.shape[1]], alpha=lr)
+                self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
+                ops.transpose_bf16(self.Ws[l], self.WsT[l])
+            b = self._b(flat, l)
+            b.sub_(self.db[l][: b.shape[0]], alpha=lr)
+            self.bias_p[l][: b.shape[0]].copy_(b)
+        self.launches += 3 * L + 8
+        return loss
+
+    def fit(self, flat: torch.Tensor, x: torch.Tensor, y: torch.Tensor, cfg, perm: Optional[torch.Tensor],
+            ready: Optional[Tuple[int, int, int]] = None, wait_all=None) -> torch.Tensor:
+        """Local SGD in place on ``flat`` (full batches only; the tail < batch_size is dropped)."""
+        n = x.shape[0]
+        B = self.B
+        self.refresh_shadows(flat, from_broadcast=ready is not None)
+        labels_all = y.reshape(-1).long()
+        it = 0
+        limit = cfg.max_nr_batches if cfg.max_nr_batches and cfg.max_nr_batches > 0 else None
+        last = torch.zeros((), device=flat.device)
+        for e in range(cfg.epochs):
+            order = perm[e % perm.shape[0]].long() if perm is not None else torch.arange(n, device=flat.device)
+            for lo in range(0, n - B + 1, B):
+                idx = order[lo:lo + B]
+                last = self.step(flat, x[idx], labels_all[idx], cfg.lr, ready if it == 0 else None)
+                it += 1
+                if limit is not None and it >= limit:
+                    return last
+        return last

@@ -177,6 +177,14 @@ torch::Tensor fp32_to_bf16(torch::Tensor x) {
 void fp32_to_bf16_into(int64_t src, int64_t dst, int64_t n) {
   check(launch_fp32_to_bf16(ptr_of<const float>(src), ptr_of<void>(dst), n, cur_stream()), "fp32_to_bf16");
 }
+torch::Tensor transpose_bf16(torch::Tensor x, c10::optional<torch::Tensor> out) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous(), "x must be contiguous CUDA bf16 [R,C]");
+  c10::cuda::CUDAGuard guard(x.device());
+  torch::Tensor o = out.has_value() ? *out : torch::empty({x.size(1), x.size(0)}, x.options());
+  TORCH_CHECK(o.is_contiguous() && o.numel() == x.numel() && o.scalar_type() == at::kBFloat16, "out");
+  check(launch_transpose_bf16(x.data_ptr(), o.data_ptr(), (int)x.size(0), (int)x.size(1), cur_stream()), "transpose_bf16");
+  return o;
+}
 void l2_flush(torch::Tensor buf) {
   CHECK_CUDA_F32(buf);
   c10::cuda::CUDAGuard guard(buf.device());
@@ -295,7 +303,7 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                   c10::optional<torch::Tensor> out_f32, c10::optional<torch::Tensor> out_bf16_t,
                   c10::optional<torch::Tensor> sgd_master, double sgd_lr, c10::optional<torch::Tensor> sgd_shadow,
                   c10::optional<torch::Tensor> sgd_shadow_t, c10::optional<torch::Tensor> colsum,
-                  int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_rows) {
+                  int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "A,B must be CUDA bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous() && A.size(1) == B.size(1), "A[M,K], B[N,K]");
   c10::cuda::CUDAGuard guard(A.device());
@@ -321,7 +329,8 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.colsum = (float*)chk(colsum, at::kFloat, 1, N, "colsum");
   ep.ready_flags = ptr_of<const uint32_t>(ready_flags);
   ep.ready_epoch = (uint32_t)ready_epoch;
-  ep.ready_chunk_rows = ready_chunk_rows;
+  ep.ready_chunk_elems = ready_chunk_elems > 0 ? ready_chunk_elems : 1;
+  ep.ready_elem_offset = ready_elem_offset;
   cudaError_t e = launch_gemm_tcgen05(A.data_ptr(), B.data_ptr(), M, N, K, ep, cur_stream());
   TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05: ", cudaGetErrorString(e), " (", gemm_tcgen05_last_error(), ")");
 }
@@ -349,6 +358,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fp32_to_bf16", &fp32_to_bf16);
   m.def("fp32_to_bf16_into", &fp32_to_bf16_into);
   m.def("l2_flush", &l2_flush);
+  m.def("transpose_bf16", &transpose_bf16);
   m.def("star_round", &star_round);
   m.def("twoshot_fedavg", &twoshot_fedavg);
   m.def("set_flag", &set_flag);

@@ -86,6 +86,8 @@ cudaError_t launch_minmax_scale(const float* x, float* out, int rows, int cols, 
 cudaError_t launch_feistel_permutation(int* out, int n, int rows, uint64_t seed, cudaStream_t s);
 cudaError_t launch_fp32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t s);
 cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s);
+// out[C,R] = in[R,C]^T (bf16), 32x32 smem tiles
+cudaError_t launch_transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // Cross-GPU collectives over NVLink peer memory (comm.cu)
@@ -165,11 +167,14 @@ struct GemmEpilogue {
   void* sgd_shadow;         // bf16 [M,N]
   void* sgd_shadow_t;       // bf16 [N,M]
   float* colsum;            // [N] += column sums of acc (bias gradient), atomicAdd; or nullptr
-  // fused broadcast consumption: before loading B rows [n0, n0+BN) the TMA producer waits until
-  // ready_flags[(n0*K*elem)/chunk] >= ready_epoch  (peer-written weights)
+  // fused broadcast consumption: B is a view at element offset ready_elem_offset of a flat arena
+  // whose chunk c (ready_chunk_elems elements each) is published by a peer GPU raising
+  // ready_flags[c] >= ready_epoch.  Before loading B rows [n0, n0+BN) the TMA producer waits for
+  // every chunk overlapping those rows.
   const uint32_t* ready_flags;
   uint32_t ready_epoch;
-  int64_t ready_chunk_rows;  // rows of B per flag
+  int64_t ready_chunk_elems;
+  int64_t ready_elem_offset;
 };
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,

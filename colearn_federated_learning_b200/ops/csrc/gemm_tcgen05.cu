@@ -175,7 +175,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (ep.ready_flags != nullptr) {
           // wait for the peer-written weight rows [n0, n0+BN) of this round, then make them
           // visible to the async proxy before TMA touches them
-          const int64_t c_lo = n0 / ep.ready_chunk_rows, c_hi = (n0 + BN - 1) / ep.ready_chunk_rows;
+          const int64_t c_lo = (ep.ready_elem_offset + (int64_t)n0 * K) / ep.ready_chunk_elems;
+          const int64_t c_hi = (ep.ready_elem_offset + (int64_t)(n0 + BN) * K - 1) / ep.ready_chunk_elems;
           for (int64_t c = c_lo; c <= c_hi; ++c)
             while (ld_acquire_sys(ep.ready_flags + c) < ep.ready_epoch) __nanosleep(64);
           asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -238,15 +239,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (ep.colsum != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float s = f[j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == (j & 31)) atomicAdd(ep.colsum + col + j, s);
-          }
-        }
         if (ep.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += __ldg(ep.bias + col + j);
@@ -268,6 +260,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if (!(lo != 0 && !(lo & 0x8000u))) f[g * 8 + h * 2] = 0.f;
               if (!(hi != 0 && !(hi & 0x8000u))) f[g * 8 + h * 2 + 1] = 0.f;
             }
+          }
+        }
+        if (ep.colsum != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float s = f[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == (j & 31)) atomicAdd(ep.colsum + col + j, s);
           }
         }
         if (ep.sgd_master != nullptr) {

@@ -20,18 +20,18 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
               sgd_master: Optional[torch.Tensor] = None, sgd_lr: float = 0.0,
               sgd_shadow: Optional[torch.Tensor] = None, sgd_shadow_t: Optional[torch.Tensor] = None,
               colsum: Optional[torch.Tensor] = None, ready_flags: int = 0, ready_epoch: int = 0,
-              ready_chunk_rows: int = 1) -> None:
+              ready_chunk_elems: int = 1, ready_elem_offset: int = 0) -> None:
     """Launch the tcgen05 GEMM; results land in the provided output tensors."""
     if not a.is_cuda:
         acc = a.float() @ b.float().t()
-        if colsum is not None:
-            colsum += acc.sum(0)
         if bias is not None:
             acc = acc + bias
         if relu:
             acc = torch.relu(acc)
         if relu_mask is not None:
             acc = acc * (relu_mask.float() > 0)
+        if colsum is not None:
+            colsum += acc.sum(0)
         if sgd_master is not None:
             sgd_master.sub_(sgd_lr * acc)
             if sgd_shadow is not None:
@@ -48,7 +48,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
         return
     _ext.require().gemm_tcgen05(a, b, bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
                                 float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(ready_flags), int(ready_epoch),
-                                int(ready_chunk_rows))
+                                int(ready_chunk_elems), int(ready_elem_offset))
 
 
 def linear_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
@@ -61,3 +61,14 @@ def linear_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor
     else:
         gemm_bf16(x, w, bias=bias, relu=relu, out_f32=out)
     return out
+
+
+def transpose_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[C,R] = x[R,C]^T`` for bf16 (smem-tiled kernel on CUDA)."""
+    if not x.is_cuda:
+        res = x.t().contiguous()
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    return _ext.require().transpose_bf16(x.contiguous(), out)

@@ -175,7 +175,7 @@ def test_gemm_tcgen05_epilogues():
     cs = torch.zeros(n, device=dev)
     ops.gemm_bf16(a, b, relu_mask=mask, out_f32=of, colsum=cs)
     assert torch.allclose(of, ref * (mask.float() > 0), atol=1e-2, rtol=1e-2)
-    assert torch.allclose(cs, ref.sum(0), atol=5e-2, rtol=1e-2)
+    assert torch.allclose(cs, (ref * (mask.float() > 0)).sum(0), atol=5e-2, rtol=1e-2)   # bias-grad = post-mask column sums
     # fused SGD on the fp32 master + shadow refresh
     master = torch.randn(m, n, device=dev)
     want_master = master - 0.1 * ref
