@@ -52,13 +52,13 @@ py::bytes make_client_desc(int64_t x, int64_t y, int64_t perm, int64_t theta_in,
 int64_t client_desc_size() { return (int64_t)sizeof(ClientDesc); }
 
 void mlp_local_sgd(int64_t net_kind, torch::Tensor descs, int64_t desc_offset, int64_t n_clients,
-                   int64_t batch_size, int64_t epochs, int64_t max_steps, int64_t loss, double lr) {
+                   int64_t batch_size, int64_t epochs, int64_t max_steps, int64_t loss, double lr, int64_t variant) {
   TORCH_CHECK(descs.is_cuda() && descs.scalar_type() == at::kByte && descs.is_contiguous(), "descs must be CUDA uint8");
   TORCH_CHECK((desc_offset + n_clients) * (int64_t)sizeof(ClientDesc) <= descs.numel(), "descs too small");
   c10::cuda::CUDAGuard guard(descs.device());
   SgdHyper hp;
   hp.batch_size = (int)batch_size; hp.epochs = (int)epochs; hp.max_steps = (int)max_steps;
-  hp.loss = (int)loss; hp.lr = (float)lr;
+  hp.loss = (int)loss; hp.lr = (float)lr; hp.variant = (int)variant;
   const ClientDesc* d = reinterpret_cast<const ClientDesc*>(descs.data_ptr<uint8_t>()) + desc_offset;
   check(launch_mlp_local_sgd((int)net_kind, d, (int)n_clients, hp, cur_stream()), "mlp_local_sgd launch");
 }

@@ -22,6 +22,8 @@ NET_KINDS = {
     ((2, 50, 10, 1), "none"): 2,
 }
 LOSS_CODES = {"bce": 0, "sse": 1, "xent": 2, "mse": 3}
+# 2 = register-resident weights (default), 1 = smem-resident weights (first version, kept for A/B runs)
+KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "2"))
 
 PtrLike = Union[torch.Tensor, int, None]
 
@@ -86,7 +88,7 @@ def _prep_xy(x: torch.Tensor, y: torch.Tensor, loss: str) -> Tuple[torch.Tensor,
 
 def mlp_local_sgd_multi(dims: Sequence[int], out_activation: str, descs: torch.Tensor, n_clients: int,
                         batch_size: int = 1, lr: float = 0.01, epochs: int = 1, max_nr_batches: int = -1,
-                        loss: str = "xent", desc_offset: int = 0) -> None:
+                        loss: str = "xent", desc_offset: int = 0, variant: Optional[int] = None) -> None:
     """Launch ``n_clients`` CTAs from a packed descriptor tensor (see :func:`build_client_descs`)."""
     kind = net_kind_for(dims, out_activation)
     if kind is None:
@@ -94,13 +96,14 @@ def mlp_local_sgd_multi(dims: Sequence[int], out_activation: str, descs: torch.T
     if loss == "bce" and out_activation != "sigmoid":
         raise ValueError("bce needs a sigmoid head")
     _ext.require().mlp_local_sgd(kind, descs, int(desc_offset), int(n_clients), int(batch_size), int(epochs),
-                                 int(max_nr_batches if max_nr_batches is not None else -1), LOSS_CODES[loss], float(lr))
+                                 int(max_nr_batches if max_nr_batches is not None else -1), LOSS_CODES[loss], float(lr),
+                                 int(KERNEL_VARIANT if variant is None else variant))
 
 
 def mlp_local_sgd(flat: torch.Tensor, dims: Sequence[int], x: torch.Tensor, y: torch.Tensor,
                   perm: Optional[torch.Tensor], batch_size: int = 1, lr: float = 0.01, epochs: int = 1,
                   max_nr_batches: int = -1, loss: str = "xent", out_activation: str = "none",
-                  return_mean: bool = False) -> torch.Tensor:
+                  return_mean: bool = False, variant: Optional[int] = None) -> torch.Tensor:
     """Single-client in-place local SGD on ``flat``; returns the last batch loss (0-dim tensor).
 
     CPU tensors run ``reference.mlp_local_sgd`` (identical semantics); CUDA tensors run the
@@ -115,7 +118,7 @@ def mlp_local_sgd(flat: torch.Tensor, dims: Sequence[int], x: torch.Tensor, y: t
         perm = perm.to(flat.device, torch.int32).contiguous()
     task = ClientTask(x=x, y=y, theta_in=flat, theta_out=flat, perm=perm, loss_out=loss_out)
     descs = build_client_descs([task], flat.device)
-    mlp_local_sgd_multi(dims, out_activation, descs, 1, batch_size, lr, epochs, max_nr_batches, loss)
+    mlp_local_sgd_multi(dims, out_activation, descs, 1, batch_size, lr, epochs, max_nr_batches, loss, variant=variant)
     return loss_out[1 if return_mean else 0]
 
 

@@ -38,7 +38,7 @@ def bench_mlp(results, quick):
         model = ctor()
         spec = model.spec
         theta = flatten_params(model).to(dev)
-        for bsz, n in ((1, 1024), (1, 8192), (32, 8192), (128, 32768)):
+        for variant, bsz, n in ((2, 1, 1024), (2, 1, 8192), (1, 1, 8192), (2, 32, 8192), (1, 32, 8192)):
             x = torch.rand(n, spec.dims[0], device=dev)
             y = (torch.rand(n, 1, device=dev) > 0.5).float()
             perm = ops.device_permutation(n, 1, 0, dev)
@@ -46,10 +46,10 @@ def bench_mlp(results, quick):
             loss_out = torch.zeros(2, device=dev)
             task = ops.ClientTask(x=x, y=y, theta_in=theta, theta_out=out, perm=perm, loss_out=loss_out)
             descs = ops.build_client_descs([task], dev)
-            fn = lambda: ops.mlp_local_sgd_multi(spec.dims, spec.out_activation, descs, 1, bsz, 0.01, 1, -1, loss)
+            fn = lambda: ops.mlp_local_sgd_multi(spec.dims, spec.out_activation, descs, 1, bsz, 0.01, 1, -1, loss, variant=variant)
             med, best = time_cuda(fn)
             steps = (n + bsz - 1) // bsz
-            results.append({"kernel": "mlp_local_sgd_persistent", "net": name, "batch": bsz, "samples": n,
+            results.append({"kernel": "mlp_local_sgd_persistent", "variant": variant, "net": name, "batch": bsz, "samples": n,
                             "ms": med, "ms_best": best, "us_per_step": 1e3 * med / steps,
                             "samples_per_s": n / (med * 1e-3)})
             print(results[-1], flush=True)

@@ -21,7 +21,8 @@ def test_extension_loaded():
 
 @pytest.mark.parametrize("ctor,loss", [(FFNN, "bce"), (FFNN, "sse"), (MLP, "xent"), (TestingRemote, "sse"), (TestingRemote, "mse")])
 @pytest.mark.parametrize("bsz,n,epochs,max_b", [(1, 97, 1, -1), (1, 200, 2, 150), (8, 203, 2, -1), (32, 64, 3, 5)])
-def test_persistent_mlp_matches_reference(ctor, loss, bsz, n, epochs, max_b):
+@pytest.mark.parametrize("variant", [2, 1])
+def test_persistent_mlp_matches_reference(ctor, loss, bsz, n, epochs, max_b, variant):
     torch.manual_seed(0)
     model = ctor()
     spec = model.spec
@@ -36,7 +37,7 @@ def test_persistent_mlp_matches_reference(ctor, loss, bsz, n, epochs, max_b):
     ref_last = R.mlp_local_sgd(ref, spec.dims, x, y, perm, bsz, 0.05, epochs, max_b, loss, spec.out_activation)
     got = flat0.clone().to(_dev())
     last = ops.mlp_local_sgd(got, spec.dims, x.to(_dev()), y.to(_dev()), perm.to(_dev()), bsz, 0.05, epochs, max_b,
-                             loss, spec.out_activation)
+                             loss, spec.out_activation, variant=variant)
     torch.cuda.synchronize()
     assert torch.allclose(got.cpu(), ref, atol=2e-4, rtol=2e-3), (got.cpu() - ref).abs().max()
     assert torch.allclose(last.cpu(), ref_last, atol=1e-3, rtol=1e-2)
@@ -183,3 +184,39 @@ def test_gemm_tcgen05_epilogues():
     ops.gemm_bf16(a, b, sgd_master=master, sgd_lr=0.1, sgd_shadow=sh, sgd_shadow_t=sht)
     assert torch.allclose(master, want_master, atol=1e-2, rtol=1e-2)
     assert torch.equal(sh, master.to(torch.bfloat16)) and torch.equal(sht, master.t().contiguous().to(torch.bfloat16))
+
+
+def test_layerwise_tcgen05_trainer_matches_autograd():
+    """Wide-MLP local SGD on tcgen05 GEMMs (fwd / dgrad / wgrad + fused SGD) vs fp32 autograd."""
+    from colearn_federated_learning_b200.fl import FitConfig
+    from colearn_federated_learning_b200.fl.layerwise import LayerwiseMLPTrainer
+    from colearn_federated_learning_b200.models import MLPNet, MLPSpec
+    dev = _dev()
+    torch.manual_seed(0)
+    spec = MLPSpec((10, 256, 256, 2), "none", "xent")
+    m = MLPNet(spec)
+    flat = flatten_params(m).clone().to(dev)
+    x, y = torch.rand(384, 10), torch.randint(0, 2, (384, 1)).float()
+    cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
+    assert LayerwiseMLPTrainer.supports(spec, cfg)
+    tr = LayerwiseMLPTrainer(spec, flat, 128)
+    last = tr.fit(flat, x.to(dev), y.to(dev), cfg, None)
+    torch.cuda.synchronize()
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    for lo in (0, 128, 256):
+        opt.zero_grad()
+        l = torch.nn.functional.cross_entropy(m(x[lo:lo + 128]), y[lo:lo + 128].view(-1).long())
+        l.backward()
+        opt.step()
+    ref = flatten_params(m)
+    assert abs(float(last) - float(l)) < 2e-2
+    assert (flat.cpu() - ref).abs().max() < 5e-3, (flat.cpu() - ref).abs().max()
+    # shadows are consistent with the fp32 master after the fused-SGD epilogue
+    w2 = flat[spec.offsets()[1][0]: spec.offsets()[1][0] + 256 * 256].view(256, 256)
+    assert torch.equal(tr.Ws[1], w2.to(torch.bfloat16)) and torch.equal(tr.WsT[1], w2.t().contiguous().to(torch.bfloat16))
+
+
+def test_transpose_bf16():
+    dev = _dev()
+    x = torch.randn(300, 70, device=dev).to(torch.bfloat16)
+    assert torch.equal(ops.transpose_bf16(x), x.t().contiguous())
