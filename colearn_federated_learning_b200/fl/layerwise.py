@@ -94,42 +94,60 @@ class LayerwiseMLPTrainer:
         off = self.offsets[l][1]
         return flat[off:off + self.dims[l + 1]]
 
-    def refresh_shadows(self, flat: torch.Tensor, from_broadcast: bool = False) -> None:
-        """fp32 master → bf16 shadows (+ transposes).  With ``from_broadcast`` the exact layers' W
-        shadows were already written by the two-shot kernel; only the transposes are rebuilt."""
+    def chunk_range(self, l: int, chunk_elems: int) -> Tuple[int, int]:
+        """[first, last] flag indices covering layer ``l``'s weight + bias in the flat arena."""
+        lo = self.offsets[l][0]
+        hi = self.offsets[l][1] + self.dims[l + 1] - 1
+        return lo // chunk_elems, hi // chunk_elems
+
+    def refresh_edge(self, flat: torch.Tensor) -> None:
+        """Padded bf16 shadows (+ transposes, padded biases) of the layers that need padding."""
         for l in range(self.L):
-            w = self._w(flat, l)
             if self.exact[l]:
-                if not (from_broadcast and self.shadow_arena is not None):
-                    self.Ws[l].copy_(ops.fp32_to_bf16(w.contiguous().view(-1)).view_as(self.Ws[l]))
-                ops.transpose_bf16(self.Ws[l], self.WsT[l])
-            else:
-                self.Ws[l].zero_()
-                self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
-                ops.transpose_bf16(self.Ws[l], self.WsT[l])
+                continue
+            w = self._w(flat, l)
+            self.Ws[l].zero_()
+            self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
+            ops.transpose_bf16(self.Ws[l], self.WsT[l])
             self.bias_p[l].zero_()
             self.bias_p[l][: self.dims[l + 1]].copy_(self._b(flat, l))
 
-    # -- one SGD step -------------------------------------------------------------------------------------
-    def step(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor, lr: float,
-             ready: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
-        """``ready = (chunk_flags_ptr, epoch, chunk_elems)`` makes the forward GEMMs of the exact
-        layers poll the broadcast's per-chunk flags (first step of a round only)."""
-        L, B = self.L, self.B
+    def refresh_exact(self, flat: torch.Tensor, from_broadcast: bool) -> None:
+        """bf16 shadow W (skipped when the two-shot broadcast already wrote it) and W^T."""
+        for l in range(self.L):
+            if not self.exact[l]:
+                continue
+            if not (from_broadcast and self.shadow_arena is not None):
+                self.Ws[l].copy_(ops.fp32_to_bf16(self._w(flat, l).contiguous().view(-1)).view_as(self.Ws[l]))
+            ops.transpose_bf16(self.Ws[l], self.WsT[l])
+
+    def refresh_shadows(self, flat: torch.Tensor, from_broadcast: bool = False) -> None:
+        self.refresh_edge(flat)
+        self.refresh_exact(flat, from_broadcast)
+
+    def _bias(self, flat: torch.Tensor, l: int) -> torch.Tensor:
+        # exact layers read the fp32 master bias straight from the arena (no copy to keep in sync)
+        return self._b(flat, l) if self.exact[l] else self.bias_p[l]
+
+    # -- one SGD step = forward() + backward() ------------------------------------------------------------
+    def forward(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor,
+                ready: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+        """``ready = (chunk_flags_ptr, epoch, chunk_elems)``: the GEMMs of the exact layers poll the
+        two-shot broadcast's per-chunk flags from their TMA producer warp (first step of a round)."""
+        L = self.L
         self.a[0].zero_()
         self.a[0][:, : self.dims[0]].copy_(x)
         ops.transpose_bf16(self.a[0], self.aT[0])
-        # forward
         for l in range(L):
             kw = {}
             if ready is not None and self.exact[l] and self.shadow_arena is not None:
                 kw = dict(ready_flags=ready[0], ready_epoch=ready[1], ready_chunk_elems=ready[2],
                           ready_elem_offset=self.offsets[l][0])
             if l < L - 1:
-                ops.gemm_bf16(self.a[l], self.Ws[l], bias=self.bias_p[l], relu=True, out_bf16=self.a[l + 1],
+                ops.gemm_bf16(self.a[l], self.Ws[l], bias=self._bias(flat, l), relu=True, out_bf16=self.a[l + 1],
                               out_bf16_t=self.aT[l + 1], **kw)
             else:
-                ops.gemm_bf16(self.a[l], self.Ws[l], bias=self.bias_p[l], out_f32=self.logits, **kw)
+                ops.gemm_bf16(self.a[l], self.Ws[l], bias=self._bias(flat, l), out_f32=self.logits, **kw)
         nc = self.dims[-1]
         loss, dlog = ops.softmax_xent(self.logits[:, :nc].contiguous(), labels)
         self.dz[L - 1].zero_()
@@ -137,7 +155,12 @@ class LayerwiseMLPTrainer:
         ops.transpose_bf16(self.dz[L - 1], self.dzT[L - 1])
         self.db[L - 1].zero_()
         self.db[L - 1][:nc].copy_(dlog.sum(0))
-        # backward: dgrad with the old weights first, then the (fused) update of layer l
+        self.launches += L + 4
+        return loss
+
+    def backward(self, flat: torch.Tensor, lr: float) -> None:
+        """dgrad with the old weights first, then the (fused) update of layer l."""
+        L = self.L
         for l in range(L - 1, -1, -1):
             if l > 0:
                 self.db[l - 1].zero_()
@@ -154,16 +177,31 @@ class LayerwiseMLPTrainer:
                 ops.transpose_bf16(self.Ws[l], self.WsT[l])
             b = self._b(flat, l)
             b.sub_(self.db[l][: b.shape[0]], alpha=lr)
-            self.bias_p[l][: b.shape[0]].copy_(b)
-        self.launches += 3 * L + 8
+            if not self.exact[l]:
+                self.bias_p[l][: b.shape[0]].copy_(b)
+        self.launches += 2 * L + 4
+
+    def step(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
+        loss = self.forward(flat, x, labels)
+        self.backward(flat, lr)
         return loss
 
     def fit(self, flat: torch.Tensor, x: torch.Tensor, y: torch.Tensor, cfg, perm: Optional[torch.Tensor],
-            ready: Optional[Tuple[int, int, int]] = None, wait_all=None) -> torch.Tensor:
-        """Local SGD in place on ``flat`` (full batches only; the tail < batch_size is dropped)."""
-        n = x.shape[0]
-        B = self.B
-        self.refresh_shadows(flat, from_broadcast=ready is not None)
+            ready: Optional[Tuple[int, int, int]] = None, wait_chunks=None) -> torch.Tensor:
+        """Local SGD in place on ``flat`` (full batches only; a tail < batch_size is dropped).
+
+        With ``ready`` (fused broadcast consumption) the order is: wait only for the chunks of the
+        padded edge layers → first forward, whose GEMMs poll the per-chunk flags of the big layers
+        while the rest of the broadcast is still in flight → ``wait_chunks(None)`` for everything
+        (peers must be done reading this rank's arena before SGD writes it) → W^T + backward."""
+        n, B = x.shape[0], self.B
+        if ready is not None and wait_chunks is not None:
+            for l in range(self.L):
+                if not self.exact[l]:
+                    wait_chunks(self.chunk_range(l, ready[2]))
+        self.refresh_edge(flat)
+        if ready is None:
+            self.refresh_exact(flat, from_broadcast=False)
         labels_all = y.reshape(-1).long()
         it = 0
         limit = cfg.max_nr_batches if cfg.max_nr_batches and cfg.max_nr_batches > 0 else None
@@ -172,8 +210,16 @@ class LayerwiseMLPTrainer:
             order = perm[e % perm.shape[0]].long() if perm is not None else torch.arange(n, device=flat.device)
             for lo in range(0, n - B + 1, B):
                 idx = order[lo:lo + B]
-                last = self.step(flat, x[idx], labels_all[idx], cfg.lr, ready if it == 0 else None)
+                first = it == 0 and ready is not None
+                last = self.forward(flat, x[idx], labels_all[idx], ready if first else None)
+                if first:
+                    if wait_chunks is not None:
+                        wait_chunks(None)
+                    self.refresh_exact(flat, from_broadcast=True)
+                self.backward(flat, cfg.lr)
                 it += 1
                 if limit is not None and it >= limit:
                     return last
+        if it == 0 and ready is not None and wait_chunks is not None:
+            wait_chunks(None)
         return last

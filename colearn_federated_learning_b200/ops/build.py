@@ -44,8 +44,9 @@ def _stamp(src: str, flags: List[str]) -> str:
     h = hashlib.sha1()
     with open(src, "rb") as f:
         h.update(f.read())
-    with open(os.path.join(CSRC, "colearn_kernels.h"), "rb") as f:
-        h.update(f.read())
+    for dep in ("colearn_kernels.h", "mlp_v2.inc"):
+        with open(os.path.join(CSRC, dep), "rb") as f:
+            h.update(f.read())
     h.update(" ".join(flags).encode())
     return h.hexdigest()[:16]
 

@@ -421,388 +421,16 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
 // pure register FFMA, the barrier between dgrad and update disappears (weights are thread-private)
 // and only activations / dz vectors travel through shared memory.  128 threads = one warp per SMSP.
 // =====================================================================================================
-namespace v2 {
-
-constexpr int NT2 = 128;
-
-__host__ __device__ constexpr int gsize(int n_out, int k_in) {
-  int t = pow2_floor(NT2 / n_out);
-  if (t > 32) t = 32;
-  while (t > 1 && t > k_in) t /= 2;
-  return t;
-}
-__host__ __device__ constexpr int align4(int x) { return (x + 3) / 4 * 4; }
-
-template <class N, int LI>
-struct RL {
-  static constexpr int K = N::template dim<LI>();
-  static constexpr int NO = N::template dim<LI + 1>();
-  static constexpr int T = gsize(NO, K);
-  static constexpr int KC = (K + T - 1) / T;
-  static constexpr int TB = gsize(K, NO);
-  static constexpr int NC = (NO + TB - 1) / TB;
-  static constexpr int FW = Offs<N, LI>::flat;            // arena offset of W
-  static constexpr int FB = Offs<N, LI>::flat + NO * K;   // arena offset of bias
-};
-// activation offsets padded to 16 bytes (a_{LI+1} lives at AOff<LI>)
-template <class N, int LI> struct AOff { static constexpr int v = AOff<N, LI - 1>::v + align4(N::template dim<LI>()); };
-template <class N> struct AOff<N, 0> { static constexpr int v = 0; };
-template <class N> struct ATot { static constexpr int v = AOff<N, N::L>::v; };
-
-template <class N, int LI, bool ACC>
-struct LayerRegs {
-  float wr[RL<N, LI>::KC];
-  float wt[RL<N, LI>::NC];
-  float av[RL<N, LI>::KC];   // inputs of this thread's row slice, kept from forward to update
-  float gr[ACC ? RL<N, LI>::KC : 1];
-  float gt[ACC ? RL<N, LI>::NC : 1];
-  float br, gb;
-};
-template <class N, int LI, bool ACC>
-struct AllRegs : AllRegs<N, LI + 1, ACC> { LayerRegs<N, LI, ACC> r; };
-template <class N, bool ACC>
-struct AllRegs<N, N::L, ACC> {};
-template <int LI, class N, bool ACC>
-__device__ __forceinline__ LayerRegs<N, LI, ACC>& regs_of(AllRegs<N, 0, ACC>& all) {
-  return static_cast<AllRegs<N, LI, ACC>&>(all).r;
-}
-
-template <class N, int LI, bool ACC>
-__device__ __forceinline__ void load_regs(AllRegs<N, 0, ACC>& all, const float* __restrict__ theta, int tid) {
-  using R = RL<N, LI>;
-  auto& r = regs_of<LI>(all);
-  {
-    const int n = (tid < R::NO * R::T) ? tid / R::T : R::NO - 1, t = tid % R::T;
-#pragma unroll
-    for (int i = 0; i < R::KC; ++i) {
-      const int k = t * R::KC + i;
-      r.wr[i] = (k < R::K) ? __ldcg(theta + R::FW + n * R::K + k) : 0.f;
-      if (ACC) r.gr[i] = 0.f;
-    }
-    r.br = __ldcg(theta + R::FB + n);
-    r.gb = 0.f;
-  }
-  {
-    const int k = (tid < R::K * R::TB) ? tid / R::TB : R::K - 1, t = tid % R::TB;
-#pragma unroll
-    for (int i = 0; i < R::NC; ++i) {
-      const int n = t * R::NC + i;
-      r.wt[i] = (n < R::NO) ? __ldcg(theta + R::FW + n * R::K + k) : 0.f;
-      if (ACC) r.gt[i] = 0.f;
-    }
-  }
-  if constexpr (LI + 1 < N::L) load_regs<N, LI + 1, ACC>(all, theta, tid);
-}
-
-template <class N, int LI, bool ACC>
-__device__ __forceinline__ void store_regs(AllRegs<N, 0, ACC>& all, const float* __restrict__ theta_in,
-                                           float* __restrict__ theta_out, float w, int delta_mode, int tid) {
-  using R = RL<N, LI>;
-  auto& r = regs_of<LI>(all);
-  if (tid < R::NO * R::T) {
-    const int n = tid / R::T, t = tid % R::T;
-#pragma unroll
-    for (int i = 0; i < R::KC; ++i) {
-      const int k = t * R::KC + i;
-      if (k < R::K) {
-        float v = r.wr[i];
-        if (delta_mode) v -= __ldcg(theta_in + R::FW + n * R::K + k);
-        theta_out[R::FW + n * R::K + k] = w * v;
-      }
-    }
-    if (t == 0) {
-      float v = r.br;
-      if (delta_mode) v -= __ldcg(theta_in + R::FB + n);
-      theta_out[R::FB + n] = w * v;
-    }
-  }
-  if constexpr (LI + 1 < N::L) store_regs<N, LI + 1, ACC>(all, theta_in, theta_out, w, delta_mode, tid);
-}
-
-template <class N, int LI, bool ACC>
-__device__ __forceinline__ void fwd(AllRegs<N, 0, ACC>& all, const float* __restrict__ a_in, float* __restrict__ a_out, int tid) {
-  using R = RL<N, LI>;
-  constexpr bool RELU = (LI != N::L - 1);
-  auto& r = regs_of<LI>(all);
-  const bool valid = tid < R::NO * R::T;
-  const int n = valid ? tid / R::T : R::NO - 1, t = tid % R::T;
-  float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < R::KC; ++i) {
-    const int k = t * R::KC + i;
-    r.av[i] = (R::T * R::KC == R::K || k < R::K) ? a_in[k] : 0.f;
-    if (i & 1) acc1 = fmaf(r.wr[i], r.av[i], acc1);
-    else acc0 = fmaf(r.wr[i], r.av[i], acc0);
-  }
-  float acc = acc0 + acc1;
-#pragma unroll
-  for (int o = R::T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (valid && t == 0) {
-    const float z = acc + r.br;
-    a_out[n] = RELU ? fmaxf(z, 0.f) : z;
-  }
-}
-
-// backward of layer LI: dgrad (LI >= 1) from the thread-private column slices, then the rank-1 update of
-// both register copies.  No barrier between the two: the weights are private to the thread.
-template <class N, int LI, bool ACC>
-__device__ __forceinline__ void bwd(AllRegs<N, 0, ACC>& all, const float* __restrict__ dz_out, const float* __restrict__ a_in,
-                                    float* __restrict__ dz_in, float scale, int tid) {
-  using R = RL<N, LI>;
-  auto& r = regs_of<LI>(all);
-  if constexpr (LI > 0) {
-    const bool valid = tid < R::K * R::TB;
-    const int k = valid ? tid / R::TB : R::K - 1, t = tid % R::TB;
-    float dzv[R::NC];
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < R::NC; ++i) {
-      const int n = t * R::NC + i;
-      dzv[i] = (R::TB * R::NC == R::NO || n < R::NO) ? dz_out[n] : 0.f;
-      if (i & 1) acc1 = fmaf(r.wt[i], dzv[i], acc1);
-      else acc0 = fmaf(r.wt[i], dzv[i], acc0);
-    }
-    float acc = acc0 + acc1;
-#pragma unroll
-    for (int o = R::TB / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    const float ak = a_in[k];
-    if (valid && t == 0) dz_in[k] = ak > 0.f ? acc : 0.f;
-    // column-copy update (same products, same order as the row copy below)
-#pragma unroll
-    for (int i = 0; i < R::NC; ++i) {
-      if (ACC) r.gt[i] = fmaf(dzv[i], ak, r.gt[i]);
-      else r.wt[i] = fmaf(scale * dzv[i], ak, r.wt[i]);
-    }
-  }
-  {
-    const int n = (tid < R::NO * R::T) ? tid / R::T : R::NO - 1;
-    const float d = dz_out[n];
-    const float g = ACC ? d : scale * d;
-#pragma unroll
-    for (int i = 0; i < R::KC; ++i) {
-      if (ACC) r.gr[i] = fmaf(g, r.av[i], r.gr[i]);
-      else r.wr[i] = fmaf(g, r.av[i], r.wr[i]);
-    }
-    if (ACC) r.gb += g; else r.br += g;
-  }
-}
-
-template <class N, int LI, bool ACC>
-__device__ __forceinline__ void apply_grads(AllRegs<N, 0, ACC>& all, float neg_lr) {
-  using R = RL<N, LI>;
-  auto& r = regs_of<LI>(all);
-#pragma unroll
-  for (int i = 0; i < R::KC; ++i) { r.wr[i] = fmaf(neg_lr, r.gr[i], r.wr[i]); r.gr[i] = 0.f; }
-#pragma unroll
-  for (int i = 0; i < R::NC; ++i) { r.wt[i] = fmaf(neg_lr, r.gt[i], r.wt[i]); r.gt[i] = 0.f; }
-  r.br = fmaf(neg_lr, r.gb, r.br);
-  r.gb = 0.f;
-  if constexpr (LI + 1 < N::L) apply_grads<N, LI + 1, ACC>(all, neg_lr);
-}
-
-template <class N, int LI, bool ACC>
-struct Fwd2 {
-  static __device__ __forceinline__ void run(AllRegs<N, 0, ACC>& all, const float* a0, float* acts, int tid) {
-    const float* a_in = (LI == 0) ? a0 : acts + AOff<N, LI - (LI > 0)>::v;
-    fwd<N, LI, ACC>(all, a_in, acts + AOff<N, LI>::v, tid);
-    __syncthreads();
-    if constexpr (LI + 1 < N::L) Fwd2<N, LI + 1, ACC>::run(all, a0, acts, tid);
-  }
-};
-template <class N, int LI, bool ACC>
-struct Bwd2 {
-  static __device__ __forceinline__ void run(AllRegs<N, 0, ACC>& all, const float* a0, const float* acts, float* dzs,
-                                             float scale, int tid) {
-    const float* a_in = (LI == 0) ? a0 : acts + AOff<N, LI - (LI > 0)>::v;
-    float* dz_in = dzs + AOff<N, LI - (LI > 0)>::v;   // dz_{LI} (unused for LI == 0)
-    bwd<N, LI, ACC>(all, dzs + AOff<N, LI>::v, a_in, dz_in, scale, tid);
-    if constexpr (LI > 0) {
-      __syncthreads();   // dz_{LI} visible to the next layer's threads
-      Bwd2<N, LI - 1, ACC>::run(all, a0, acts, dzs, scale, tid);
-    }
-  }
-};
-
-// single-thread loss for tiny heads (DOUT <= 2): no shuffles on the critical path
-template <class N>
-__device__ __forceinline__ float loss_small(float* aL, float* dzL, const float* yrow, int loss, float inv_b) {
-  constexpr int DO = N::DOUT;
-  if (loss == LOSS_XENT) {
-    const int label = (int)yrow[0];
-    float m = aL[0];
-#pragma unroll
-    for (int j = 1; j < DO; ++j) m = fmaxf(m, aL[j]);
-    float e[DO], s = 0.f;
-#pragma unroll
-    for (int j = 0; j < DO; ++j) { e[j] = __expf(aL[j] - m); s += e[j]; }
-    const float inv_s = 1.f / s;
-    float zl = 0.f;
-#pragma unroll
-    for (int j = 0; j < DO; ++j) {
-      dzL[j] = (e[j] * inv_s - (j == label ? 1.f : 0.f)) * inv_b;
-      if (j == label) zl = aL[j];
-    }
-    return (__logf(s) + m) - zl;
-  }
-  float value = 0.f;
-#pragma unroll
-  for (int j = 0; j < DO; ++j) {
-    const float z = aL[j], y = yrow[j];
-    float out = z, dact = 1.f;
-    if (N::kSigmoid) { out = 1.f / (1.f + __expf(-z)); dact = out * (1.f - out); }
-    if (loss == LOSS_BCE) {
-      const float lp = fmaxf(__logf(out), -100.f), l1p = fmaxf(log1pf(-out), -100.f);
-      value -= (y * lp + (1.f - y) * l1p) * (1.f / DO);
-      dzL[j] = (out - y) * inv_b * (1.f / DO);
-    } else {
-      const float d = out - y;
-      value += d * d;
-      dzL[j] = 2.f * d * dact * ((loss == LOSS_MSE) ? inv_b : 1.f);
-    }
-  }
-  return value;
-}
-
-template <class N, bool ACC>
-__global__ void __launch_bounds__(NT2, 1)
-mlp_local_sgd_kernel_v2(const ClientDesc* __restrict__ descs, SgdHyper hp) {
-  using Tot = Totals<N>;
-  constexpr int DIN = N::DIN, ROWM = Tot::ROW_MAX;
-  constexpr int EPT2 = (CHUNK * ROWM + NT2 - 1) / NT2;
-  constexpr int ACTS = ATot<N>::v;
-  extern __shared__ __align__(16) float smem[];
-  const ClientDesc d = descs[blockIdx.x];
-  const int tid = threadIdx.x;
-  const int B = hp.batch_size < 1 ? 1 : hp.batch_size;
-
-  float* sAct = smem;                       // 2 x ACTS (double buffered by step parity)
-  float* sDz = sAct + 2 * ACTS;             // ACTS
-  float* sData = sDz + ACTS;                // 2 x CHUNK x ROWM
-  float* sMisc = sData + 2 * CHUNK * ROWM;  // [0] last loss, [1] loss sum
-
-  if (d.wait_flag != nullptr) {
-    if (tid == 0) while (ld_acquire_sys(d.wait_flag) < d.wait_value) __nanosleep(32);
-    __syncthreads();
-  }
-  AllRegs<N, 0, ACC> W;
-  load_regs<N, 0, ACC>(W, d.theta_in, tid);
-  if (tid < 2) sMisc[tid] = 0.f;
-
-  const int n = d.n, ydim = d.y_dim, row = DIN + ydim;
-  const int spe = (n + B - 1) / B;
-  long long total_steps = (long long)hp.epochs * spe;
-  if (hp.max_steps > 0 && hp.max_steps < total_steps) total_steps = hp.max_steps;
-  long long Q;
-  {
-    const long long full_epochs = total_steps / spe;
-    long long rem_samples = (total_steps - full_epochs * spe) * B;
-    if (rem_samples > n) rem_samples = n;
-    Q = full_epochs * (long long)n + rem_samples;
-  }
-  const int n_chunks = (int)((Q + CHUNK - 1) / CHUNK);
-
-  float pre[EPT2];
-  auto issue_loads = [&](int chunk) {
-#pragma unroll
-    for (int j = 0; j < EPT2; ++j) {
-      const int e = tid + j * NT2;
-      pre[j] = 0.f;
-      if (e < CHUNK * row) {
-        const int i = e / row, c = e - i * row;
-        const long long q = (long long)chunk * CHUNK + i;
-        if (q < Q) {
-          const int ep = (int)(q / n);
-          const int pos = (int)(q - (long long)ep * n);
-          const int idx = d.perm ? __ldg(d.perm + (size_t)(ep % d.perm_rows) * n + pos) : pos;
-          pre[j] = (c < DIN) ? __ldg(d.x + (size_t)idx * DIN + c) : __ldg(d.y + (size_t)idx * ydim + (c - DIN));
-        }
-      }
-    }
-  };
-  auto store_loads = [&](int buf) {
-    float* dst = sData + buf * (CHUNK * ROWM);
-#pragma unroll
-    for (int j = 0; j < EPT2; ++j) {
-      const int e = tid + j * NT2;
-      if (e < CHUNK * row) dst[e] = pre[j];
-    }
-  };
-  if (n_chunks > 0) { issue_loads(0); store_loads(0); }
-  __syncthreads();
-
-  long long step = 0;
-  int pos_in_epoch = 0, in_batch = 0;
-  int cur_batch = (n < B) ? n : B;
-  float batch_loss = 0.f;
-  int parity = 0;
-  const float neg_lr = -hp.lr;
-
-  for (int c = 0; c < n_chunks; ++c) {
-    if (c + 1 < n_chunks) issue_loads(c + 1);
-    const float* chunk = sData + (c & 1) * (CHUNK * ROWM);
-    const long long q0 = (long long)c * CHUNK;
-    const int cnt = (int)((Q - q0) < CHUNK ? (Q - q0) : CHUNK);
-    for (int i = 0; i < cnt; ++i) {
-      const float* a0 = chunk + i * row;
-      float* acts = sAct + parity * ACTS;
-      const float inv_b = 1.f / (float)cur_batch;
-
-      Fwd2<N, 0, ACC>::run(W, a0, acts, tid);
-      if (N::DOUT <= 2) {
-        if (tid == 0) {
-          const float v = loss_small<N>(acts + AOff<N, N::L - 1>::v, sDz + AOff<N, N::L - 1>::v, a0 + DIN, hp.loss, inv_b);
-          batch_loss += (hp.loss == LOSS_SSE) ? v : v * inv_b;
-        }
-      } else if (tid < 32) {
-        const float v = loss_and_dz<N>(acts + AOff<N, N::L - 1>::v, sDz + AOff<N, N::L - 1>::v, a0 + DIN, hp.loss, inv_b, tid);
-        if (tid == 0) batch_loss += (hp.loss == LOSS_SSE) ? v : v * inv_b;
-      }
-      __syncthreads();
-      Bwd2<N, N::L - 1, ACC>::run(W, a0, acts, sDz, neg_lr, tid);
-      parity ^= 1;
-
-      ++in_batch;
-      ++pos_in_epoch;
-      if (in_batch == cur_batch) {
-        if (ACC) apply_grads<N, 0, ACC>(W, neg_lr);
-        if (tid == 0) { sMisc[0] = batch_loss; sMisc[1] += batch_loss; batch_loss = 0.f; }
-        ++step;
-        in_batch = 0;
-        if (pos_in_epoch >= n) pos_in_epoch = 0;
-        const int left = n - pos_in_epoch;
-        cur_batch = left < B ? left : B;
-      }
-    }
-    __syncthreads();
-    if (c + 1 < n_chunks) store_loads((c + 1) & 1);
-    __syncthreads();
-  }
-  __syncthreads();
-  store_regs<N, 0, ACC>(W, d.theta_in, d.theta_out, d.out_scale, d.delta_mode, tid);
-  if (tid == 0 && d.loss_out != nullptr) {
-    d.loss_out[0] = sMisc[0];
-    d.loss_out[1] = step > 0 ? sMisc[1] / (float)step : 0.f;
-  }
-  __syncthreads();
-  if (tid == 0 && d.signal_flag != nullptr) {
-    __threadfence_system();
-    st_release_sys(d.signal_flag, d.signal_value);
-  }
-}
-
-template <class N>
-int smem_bytes2() {
-  return (3 * ATot<N>::v + 2 * CHUNK * Totals<N>::ROW_MAX + 8) * (int)sizeof(float);
-}
-template <class N>
-cudaError_t launch2(const ClientDesc* descs, int n_clients, SgdHyper hp, cudaStream_t stream) {
-  const int bytes = smem_bytes2<N>();
-  if (hp.batch_size > 1) mlp_local_sgd_kernel_v2<N, true><<<n_clients, NT2, bytes, stream>>>(descs, hp);
-  else mlp_local_sgd_kernel_v2<N, false><<<n_clients, NT2, bytes, stream>>>(descs, hp);
-  return cudaGetLastError();
-}
-
-}  // namespace v2
+#define V2_NS v2_128
+#define V2_NT 128
+#include "mlp_v2.inc"
+#undef V2_NS
+#undef V2_NT
+#define V2_NS v2_256
+#define V2_NT 256
+#include "mlp_v2.inc"
+#undef V2_NS
+#undef V2_NT
 
 // ---- batched forward (inference / evaluation) --------------------------------------------------------
 template <class N>
@@ -879,11 +507,21 @@ cudaError_t forward_t(const float* theta, const float* x, float* out, int n, cud
 
 cudaError_t launch_mlp_local_sgd(int net_kind, const ClientDesc* descs, int n_clients, SgdHyper hp,
                                  cudaStream_t stream) {
-  if (hp.variant != 1) {  // default: v2 (register-resident weights); variant 1 keeps the smem-weight kernel
+  // variant 2 (default): register-resident weights, 256-thread CTA; 3: same with 128 threads;
+  // 1: first version with smem-resident weights (kept for A/B measurements)
+  if (hp.variant == 3) {
     switch (net_kind) {
-      case NET_FFNN: return v2::launch2<FFNNNet>(descs, n_clients, hp, stream);
-      case NET_MLP64: return v2::launch2<MLP64Net>(descs, n_clients, hp, stream);
-      case NET_TESTING_REMOTE: return v2::launch2<TestingRemoteNet>(descs, n_clients, hp, stream);
+      case NET_FFNN: return v2_128::launch2<FFNNNet>(descs, n_clients, hp, stream);
+      case NET_MLP64: return v2_128::launch2<MLP64Net>(descs, n_clients, hp, stream);
+      case NET_TESTING_REMOTE: return v2_128::launch2<TestingRemoteNet>(descs, n_clients, hp, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  if (hp.variant != 1) {
+    switch (net_kind) {
+      case NET_FFNN: return v2_256::launch2<FFNNNet>(descs, n_clients, hp, stream);
+      case NET_MLP64: return v2_256::launch2<MLP64Net>(descs, n_clients, hp, stream);
+      case NET_TESTING_REMOTE: return v2_256::launch2<TestingRemoteNet>(descs, n_clients, hp, stream);
       default: return cudaErrorInvalidValue;
     }
   }

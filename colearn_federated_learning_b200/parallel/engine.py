@@ -303,11 +303,48 @@ class FederatedEngine:
                            extra={"provider": arena.provider, "multicast": arena.has_multicast})
 
     # ------------------------------------------------------------------------------------------ twoshot
-    def _local_train_inplace(self, round_idx: int) -> torch.Tensor:
-        """Local fit in place on the work arena (layer-wise tcgen05 trainer or torch autograd)."""
+    def _layerwise_trainer(self):
+        """tcgen05 layer-wise trainer bound to the work arena (+ bf16 shadow arena), or None."""
+        if getattr(self, "_lw_checked", False):
+            return self._lw
+        self._lw_checked, self._lw = True, None
+        if self.spec is not None:
+            from ..fl.layerwise import LayerwiseMLPTrainer
+            if LayerwiseMLPTrainer.supports(self.spec, self.cfg):
+                shadow = self.arena.tensor("shadow") if self.bf16_shadow else None
+                self._lw = LayerwiseMLPTrainer(self.spec, self.theta[: self.P], self.cfg.batch_size, shadow=shadow)
+        return self._lw
+
+    def _local_train_inplace(self, round_idx: int, epoch: int) -> torch.Tensor:
+        """Local fit in place on the work arena.  Wide MLPs: tcgen05 layer-wise trainer whose first
+        forward GEMMs consume the previous round's broadcast chunk by chunk (flags of ``epoch-1``);
+        everything else: torch autograd (cuDNN convs) + this repo's loss / SGD kernels."""
         flat = self.theta[: self.P]
-        last, path = local_fit(flat, self.model, self.x, self.y, FitConfig(**{**self.cfg.to_dict()}), round_idx)
-        self._last_path = path
+        lw = self._layerwise_trainer()
+        if lw is None:
+            if epoch > 1:
+                self.ext.wait_flags(self.arena.ptr("chunk_flags"), self.n_chunks, epoch - 1)
+            last, path = local_fit(flat, self.model, self.x, self.y, FitConfig(**{**self.cfg.to_dict()}), round_idx)
+            self._last_path = path
+            return last
+        from ..fl.trainer import make_perm
+        perm = make_perm(self.x.shape[0], self.cfg, self.device, round_idx)
+        cf_ptr = self.arena.ptr("chunk_flags")
+        fused = epoch > 1 and self.bf16_shadow
+        ready = (cf_ptr, epoch - 1, self.chunk_elems) if fused else None
+
+        def wait_chunks(rng):
+            if epoch <= 1:
+                return
+            if rng is None:
+                self.ext.wait_flags(cf_ptr, self.n_chunks, epoch - 1)
+            else:
+                self.ext.wait_flags(cf_ptr + 4 * rng[0], rng[1] - rng[0] + 1, epoch - 1)
+
+        if not fused:
+            wait_chunks(None)
+        last = lw.fit(flat, self.x.view(self.x.shape[0], -1), self.y, self.cfg, perm, ready, wait_chunks)
+        self._last_path = "layerwise+fused_bcast" if fused else "layerwise"
         return last
 
     def _run_twoshot(self, rounds: int, masks: List[int], host_inputs, read_back: bool) -> RoundReport:
@@ -339,15 +376,20 @@ class FederatedEngine:
                 self.x.copy_(hx, non_blocking=True)
                 self.y.copy_(hy.view(-1, 1), non_blocking=True)
             if (masks[i] >> r) & 1:
-                last = self._local_train_inplace(self.rounds_done + i)
+                last = self._local_train_inplace(self.rounds_done + i, e)
                 losses_log[i, r, 0] = last
+            elif e > 1:
+                ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e - 1)
             wts = self._round_weights(masks[i])
             self.weights_dev[:W].copy_(torch.tensor(wts, dtype=torch.float32), non_blocking=True)
             ext.signal_peers(arrive_ptrs, e)
             ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
                                0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, n_blocks)
-            ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e)
-            launches += 3
+            launches += 2
+            if read_back or i == rounds - 1:
+                # arena must be complete before the host reads the loss / the call returns
+                ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e)
+                launches += 1
             if read_back:
                 self.loss_host[:2].copy_(losses_log[i, r], non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()

@@ -257,3 +257,23 @@ def test_monitors(tmp_path):
     assert open(temp).read().count("Monitoring: ") == 2
     s = monitors.NvmlSampler().start()
     assert "reasons" in s.stop()
+
+
+def test_reference_shaped_client_federated_api(tmp_path):
+    import asyncio
+    from colearn_federated_learning_b200 import client_federated as cf
+    from colearn_federated_learning_b200.data import BaseDataset
+    pred, tgt = torch.tensor([[0.8], [0.3]]), torch.tensor([[1.0], [0.0]])
+    assert torch.allclose(cf.loss_fn(target=tgt, pred=pred), torch.nn.functional.binary_cross_entropy(pred, tgt))
+    x, y = synthetic_unsw(40, seed=0)
+    fed = federate(BaseDataset(x, y), ["a", "b"])
+    loader = FederatedDataLoader(fed, batch_size=1, shuffle=True)
+    a = Arguments()
+    m = cf.FFNN()
+    before = flatten_params(m).clone()
+    m2, loss = cf.train_local("a", m, torch.optim.SGD(m.parameters(), lr=0.05), 1, loader, a)
+    assert m2 is m and not torch.equal(flatten_params(m), before) and loss.ndim == 0
+    res = cf.evaluate(cf.FFNN(), [(x[i:i + 8], y[i:i + 8]) for i in range(0, 40, 8)], torch.device("cpu"))
+    assert res["n"] == 40 and 0 <= res["accuracy"] <= 1
+    shared = cf.get_private_data_loaders(["a", "b"], a, n_train_items=5, dataset=BaseDataset(x, y))
+    assert len(shared) == 5
