@@ -1,0 +1,97 @@
+"""Broadcast + FedAvg-reduce bandwidth sweep (BASELINE.json: "broadcast+FedAvg-reduce GB/s vs 900 GB/s/dir").
+
+Run under torchrun on N GPUs.  For each message size P (fp32 elements) it times, with CUDA events and
+max over ranks:
+  * ours   — ``twoshot_fedavg_kernel`` (reduce + weight + apply + re-broadcast, fp32 [+ bf16 shadow]) and,
+             for small P, the coordinator-centric ``star_round_kernel`` path;
+  * nccl   — ``dist.all_reduce`` (the library collective the comparator would use for the same job).
+Reported bandwidth is algorithmic per-GPU traffic: every rank must receive (W-1)/W·P (reduce leg) and
+(W-1)/W·P (broadcast leg) fp32 → bus_bytes = 2·(W-1)/W·4P, the same convention as nccl-tests' busbw.
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from colearn_federated_learning_b200 import ops
+from colearn_federated_learning_b200.parallel import init_distributed, shutdown
+from colearn_federated_learning_b200.parallel.symm import SymmetricArena
+
+
+def timed(fn, iters, world, device):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/comm_sweep.json")
+    ap.add_argument("--sizes", default="4994,109386,1048576,11181644,50397188")
+    ap.add_argument("--chunk-elems", type=int, default=65536)
+    ap.add_argument("--shadow", action="store_true")
+    args = ap.parse_args()
+    rank, world, device = init_distributed()
+    ext = ops._ext.require()
+    results = []
+    for P in [int(s) for s in args.sizes.split(",")]:
+        P4 = (P + 3) // 4 * 4
+        n_chunks = (P4 + args.chunk_elems - 1) // args.chunk_elems
+        layout = {"work": (P4, torch.float32), "chunk_flags": (n_chunks, torch.int32), "flags": (64, torch.int32)}
+        if args.shadow:
+            layout["shadow"] = (P4, torch.bfloat16)
+        arena = SymmetricArena(layout, device)
+        arena.tensor("work").normal_()
+        weights = torch.full((16,), 1.0 / world, device=device)
+        arrive = [arena.ptr("flags", k, 1 + rank) for k in range(world)]
+        state = {"e": 0}
+        n_blocks = max(1, min(148 * 2, (n_chunks + world - 1) // world))
+
+        def ours():
+            state["e"] += 1
+            e = state["e"]
+            ext.signal_peers(arrive, e)
+            ext.twoshot_fedavg(arena.peer_ptrs("work"), arena.peer_ptrs("shadow") if args.shadow else [],
+                               arena.peer_ptrs("chunk_flags"), arena.ptr("flags", None, 1), weights.data_ptr(), 0, e,
+                               (1 << world) - 1, 1.0, P4, args.chunk_elems, rank, n_blocks)
+            ext.wait_flags(arena.ptr("chunk_flags"), n_chunks, e)
+
+        iters = 20 if P4 < (1 << 22) else 8
+        ms = timed(ours, iters, world, device)
+        buf = torch.randn(P4, device=device)
+        ms_nccl = timed(lambda: dist.all_reduce(buf), iters, world, device) if world > 1 else float("nan")
+        bus = 2.0 * (world - 1) / world * 4.0 * P4
+        rec = {"P": P, "bytes": 4 * P4, "world": world, "provider": arena.provider, "multicast": arena.has_multicast,
+               "twoshot_ms": ms, "twoshot_busbw_GBps": bus / ms / 1e6 if world > 1 else None,
+               "nccl_allreduce_ms": ms_nccl, "nccl_busbw_GBps": bus / ms_nccl / 1e6 if world > 1 else None,
+               "shadow_bf16": args.shadow, "chunk_elems": args.chunk_elems}
+        results.append(rec)
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
+        arena.close()
+        del arena
+    if rank == 0:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        with open(args.out, "w") as f:
+            json.dump(results, f, indent=1)
+    shutdown()
+
+
+if __name__ == "__main__":
+    main()
