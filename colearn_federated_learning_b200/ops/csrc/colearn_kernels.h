@@ -176,6 +176,7 @@ struct GemmEpilogue {
   uint32_t ready_epoch;
   int64_t ready_chunk_elems;
   int64_t ready_elem_offset;
+  int tile_n;               // 0 = auto, 128 or 256 = force the N tile width
 };
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,

@@ -30,15 +30,22 @@
 namespace colearn {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128, BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int kStages = 6;
 constexpr int kAccStages = 2;
-constexpr int kTmemCols = kAccStages * BN;  // 256
 constexpr int kThreads = 192;
-constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
-constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kMaxStages = 6;
+// Tile config.  BN = 256 halves the B-operand smem traffic per FLOP (128x128x16 UMMAs sit exactly at the
+// 128 B/clk smem limit: 8 KB of operands per 64-cycle instruction; 128x256x16 needs 12 KB per 128 cycles).
+template <int BN_>
+struct Cfg {
+  static constexpr int BN = BN_;
+  static constexpr int kStages = BN_ == 256 ? 4 : 6;
+  static constexpr int kTmemCols = kAccStages * BN_;  // 256 or 512 (all of TMEM)
+  static constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN_ * BK * 2;
+  static constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 std::string g_last_error;
 
@@ -126,8 +133,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 struct SharedBarriers {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t tmem_full[kAccStages];
   uint64_t tmem_empty[kAccStages];
   uint32_t tmem_base;
@@ -138,9 +145,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     int M, int N, int K, GemmEpilogue ep) {
+  using C = Cfg<BN>;
+  constexpr int kStages = C::kStages, kTmemCols = C::kTmemCols;
+  constexpr uint32_t kStageBytesA = C::kStageBytesA, kStageBytesB = C::kStageBytesB, kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -352,28 +363,29 @@ PFN_encodeTiled get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols; }
+  const void* ptr; int rows, cols, box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 1000003u) ^ (std::hash<int>()(k.cols) * 10007u);
+    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 1000003u) ^ (std::hash<int>()(k.cols) * 10007u) ^
+           (std::hash<int>()(k.box_rows) * 131u);
   }
 };
 
-bool make_tmap(const void* ptr, int rows, int cols, CUtensorMap* out) {
-  // row-major [rows, cols] bf16; box = [128 rows, 64 cols] (64 bf16 = one 128-byte swizzle row)
+bool make_tmap(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
+  // row-major [rows, cols] bf16; box = [box_rows rows, 64 cols] (64 bf16 = one 128-byte swizzle row)
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
-  MapKey key{ptr, rows, cols};
+  MapKey key{ptr, rows, cols, box_rows};
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
   PFN_encodeTiled enc = get_encode();
   if (enc == nullptr) { g_last_error = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -386,24 +398,17 @@ bool make_tmap(const void* ptr, int rows, int cols, CUtensorMap* out) {
   return true;
 }
 
-}  // namespace
-
-const char* gemm_tcgen05_last_error() { return g_last_error.c_str(); }
-
-cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
-  if (M <= 0 || N <= 0 || K <= 0 || (M % BM) || (N % BN) || (K % BK)) {
-    g_last_error = "shape must satisfy M%128==0, N%128==0, K%64==0";
-    return cudaErrorInvalidValue;
-  }
-  if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
+template <int BN>
+cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+  using C = Cfg<BN>;
   CUtensorMap ta, tb;
-  if (!make_tmap(A, M, K, &ta) || !make_tmap(B, N, K, &tb)) return cudaErrorInvalidValue;
+  if (!make_tmap(A, M, K, BM, &ta) || !make_tmap(B, N, K, BN, &tb)) return cudaErrorInvalidValue;
   static bool configured[64] = {false};
   static int num_sms[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem) failed"; return e; }
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
@@ -411,8 +416,27 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
   const int tiles = (M / BM) * (N / BN);
   int grid = tiles < num_sms[dev & 63] ? tiles : num_sms[dev & 63];
   if (grid < 1) grid = 1;
-  gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+  gemm_tcgen05_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
   return cudaGetLastError();
+}
+
+}  // namespace
+
+const char* gemm_tcgen05_last_error() { return g_last_error.c_str(); }
+
+cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0 || (M % BM) || (N % 128) || (K % BK)) {
+    g_last_error = "shape must satisfy M%128==0, N%128==0, K%64==0";
+    return cudaErrorInvalidValue;
+  }
+  if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
+  // BN=256 when it divides N and leaves enough tiles to fill the machine; BN=128 otherwise
+  const bool wide = (N % 256 == 0) && ((int64_t)(M / BM) * (N / 256) >= 120) && ep.tile_n != 128;
+  if (wide || ep.tile_n == 256) {
+    if (N % 256) { g_last_error = "tile_n=256 needs N%256==0"; return cudaErrorInvalidValue; }
+    return launch_t<256>(A, B, M, N, K, ep, s);
+  }
+  return launch_t<128>(A, B, M, N, K, ep, s);
 }
 
 }  // namespace colearn

@@ -95,14 +95,16 @@ def bench_gemm(results, quick):
         a = (torch.randn(m, k, device=dev) * 0.1).to(torch.bfloat16)
         b = (torch.randn(n, k, device=dev) * 0.1).to(torch.bfloat16)
         out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
-        fn = lambda: ops.gemm_bf16(a, b, out_bf16=out)
-        med, best = time_cuda(fn)
         ref = lambda: torch.matmul(a, b.t())
         rmed, rbest = time_cuda(ref)
         fl = 2.0 * m * n * k
-        results.append({"kernel": "gemm_tcgen05", "m": m, "n": n, "k": k, "ms": med, "tflops": fl / med / 1e9,
-                        "tflops_best": fl / best / 1e9, "cublas_ms": rmed, "cublas_tflops": fl / rmed / 1e9})
-        print(results[-1], flush=True)
+        for tile_n in (128, 256):
+            fn = lambda: ops.gemm_bf16(a, b, out_bf16=out, tile_n=tile_n)
+            med, best = time_cuda(fn)
+            results.append({"kernel": "gemm_tcgen05", "tile_n": tile_n, "m": m, "n": n, "k": k, "ms": med,
+                            "tflops": fl / med / 1e9, "tflops_best": fl / best / 1e9, "cublas_ms": rmed,
+                            "cublas_tflops": fl / rmed / 1e9})
+            print(results[-1], flush=True)
 
 
 def bench_elementwise(results, quick):
