@@ -139,6 +139,9 @@ struct TwoShotArgs {
   int64_t chunk_elems;          // flag granularity (multiple of 4)
   int world;
   int rank;
+  uint32_t* peer_arrive[16];    // if signal_arrive: my arrive slot on every rank (raised at kernel start)
+  int signal_arrive;            // fold the "local training done" signal into this kernel
+  int wait_all;                 // spin at the end until every chunk of MY arena carries `epoch`
 };
 cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s);
 

@@ -133,6 +133,11 @@ __global__ void __launch_bounds__(512)
 twoshot_fedavg_kernel(TwoShotArgs a) {
   const int tid = threadIdx.x;
   __shared__ float sw[16];
+  // (0) announce "my local training of this round is done" to every rank (stream order guarantees it is)
+  if (a.signal_arrive && blockIdx.x == 0 && tid < a.world) {
+    __threadfence_system();
+    st_release_sys(a.peer_arrive[tid], a.epoch);
+  }
   if (tid < a.world) {
     sw[tid] = a.weights[tid];
     if ((a.select_mask >> tid) & 1u)
@@ -147,29 +152,58 @@ twoshot_fedavg_kernel(TwoShotArgs a) {
     const int64_t lo = c * a.chunk_elems;
     const int64_t hi = (lo + a.chunk_elems < a.n) ? lo + a.chunk_elems : a.n;
     const int64_t len4 = (hi - lo) >> 2;  // n and chunk_elems are multiples of 4
-    for (int64_t j = tid; j < len4; j += blockDim.x) {
-      const int64_t e4 = (lo >> 2) + j;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int k = 0; k < a.world; ++k) {
-        if (!((a.select_mask >> k) & 1u)) continue;
-        const float4 v = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4);
-        const float w = sw[k];
-        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+    // two float4 per thread per iteration: 2 x (#selected peers) 16-byte peer loads in flight per thread
+    for (int64_t j = tid; j < len4; j += 2 * blockDim.x) {
+      const int64_t e4a = (lo >> 2) + j;
+      const int64_t jb = j + blockDim.x;
+      const bool has_b = jb < len4;
+      const int64_t e4b = (lo >> 2) + jb;
+      float4 va[8], vb[8];   // world <= 8 on an HGX box (checked by the launcher)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < a.world && ((a.select_mask >> k) & 1u)) {
+          va[k] = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4a);
+          if (has_b) vb[k] = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4b);
+        }
+      }
+      float4 acca = make_float4(0.f, 0.f, 0.f, 0.f), accb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < a.world && ((a.select_mask >> k) & 1u)) {
+          const float w = sw[k];
+          acca.x = fmaf(w, va[k].x, acca.x); acca.y = fmaf(w, va[k].y, acca.y);
+          acca.z = fmaf(w, va[k].z, acca.z); acca.w = fmaf(w, va[k].w, acca.w);
+          if (has_b) {
+            accb.x = fmaf(w, vb[k].x, accb.x); accb.y = fmaf(w, vb[k].y, accb.y);
+            accb.z = fmaf(w, vb[k].z, accb.z); accb.w = fmaf(w, vb[k].w, accb.w);
+          }
+        }
       }
       if (a.theta_prev != nullptr) {
-        float4 t = reinterpret_cast<float4*>(a.theta_prev)[e4];
-        t.x = fmaf(a.server_lr, acc.x - t.x, t.x); t.y = fmaf(a.server_lr, acc.y - t.y, t.y);
-        t.z = fmaf(a.server_lr, acc.z - t.z, t.z); t.w = fmaf(a.server_lr, acc.w - t.w, t.w);
-        reinterpret_cast<float4*>(a.theta_prev)[e4] = t;
-        acc = t;
+        float4 t = reinterpret_cast<float4*>(a.theta_prev)[e4a];
+        t.x = fmaf(a.server_lr, acca.x - t.x, t.x); t.y = fmaf(a.server_lr, acca.y - t.y, t.y);
+        t.z = fmaf(a.server_lr, acca.z - t.z, t.z); t.w = fmaf(a.server_lr, acca.w - t.w, t.w);
+        reinterpret_cast<float4*>(a.theta_prev)[e4a] = t;
+        acca = t;
+        if (has_b) {
+          float4 u = reinterpret_cast<float4*>(a.theta_prev)[e4b];
+          u.x = fmaf(a.server_lr, accb.x - u.x, u.x); u.y = fmaf(a.server_lr, accb.y - u.y, u.y);
+          u.z = fmaf(a.server_lr, accb.z - u.z, u.z); u.w = fmaf(a.server_lr, accb.w - u.w, u.w);
+          reinterpret_cast<float4*>(a.theta_prev)[e4b] = u;
+          accb = u;
+        }
       }
-      const uint2 packed = pack_bf16x4(acc);
-#pragma unroll 4
-      for (int k = 0; k < a.world; ++k) {
-        st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4, acc);
-        if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4] = packed;
+      const uint2 pa = pack_bf16x4(acca), pb = pack_bf16x4(accb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < a.world) {
+          st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4a, acca);
+          if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4a] = pa;
+          if (has_b) {
+            st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4b, accb);
+            if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4b] = pb;
+          }
+        }
       }
     }
     __threadfence_system();
@@ -179,6 +213,11 @@ twoshot_fedavg_kernel(TwoShotArgs a) {
       st_release_sys(a.chunk_flags[tid] + c, a.epoch);
     }
     __syncthreads();
+  }
+  // (3) optionally hold the stream until the whole arena of THIS rank has been refreshed by its owners
+  if (a.wait_all) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < n_chunks; c += (int64_t)gridDim.x * blockDim.x)
+      while (ld_acquire_sys(a.chunk_flags[a.rank] + c) < a.epoch) __nanosleep(40);
   }
 }
 
@@ -234,7 +273,7 @@ cudaError_t launch_star_round(const StarRoundArgs& a, int n_blocks, cudaStream_t
 }
 
 cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s) {
-  if (a.world > 16 || (a.n & 3) || (a.chunk_elems & 3)) return cudaErrorInvalidValue;
+  if (a.world > 8 || (a.n & 3) || (a.chunk_elems & 3)) return cudaErrorInvalidValue;
   if (n_blocks < 1) n_blocks = 1;
   twoshot_fedavg_kernel<<<n_blocks, 512, 0, s>>>(a);
   return cudaGetLastError();

@@ -22,8 +22,9 @@ NET_KINDS = {
     ((2, 50, 10, 1), "none"): 2,
 }
 LOSS_CODES = {"bce": 0, "sse": 1, "xent": 2, "mse": 3}
-# 2 = register-resident weights (default), 1 = smem-resident weights (first version, kept for A/B runs)
-KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "2"))
+# 3 = register-resident weights, 128-thread CTA (default: fastest measured, profiles/r1_call4_*), 2 = same with
+# 256 threads, 1 = smem-resident weights (first version, kept for A/B runs)
+KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "3"))
 
 PtrLike = Union[torch.Tensor, int, None]
 

@@ -66,7 +66,7 @@ class FederatedEngine:
                  group: Optional[dist.ProcessGroup] = None, batch_size: int = 1, lr: float = 0.01,
                  local_epochs: int = 1, max_batches: int = -1, loss: str = "auto", weighted: bool = True,
                  server_lr: float = 1.0, coordinator_rank: int = 0, algo: str = "auto", seed: int = 1,
-                 shuffle: bool = True, chunk_elems: int = 65536, bf16_shadow: bool = False,
+                 shuffle: bool = True, chunk_elems: int = 0, bf16_shadow: bool = False,
                  model_kwargs: Optional[Dict[str, Any]] = None) -> None:
         self.rank = dist.get_rank(group) if _dist_ready() else 0
         self.world = dist.get_world_size(group) if _dist_ready() else 1
@@ -100,6 +100,12 @@ class FederatedEngine:
         if algo == "star" and backend == "fused" and not persistent:
             raise ValueError(f"algo 'star' needs a persistent-kernel model, got {model}")
         self.algo = algo
+        if not chunk_elems:
+            # flag/work granularity of the two-shot kernel: >= ~2 CTAs per SM worth of chunks per rank
+            target = max(1, self.P4 // (self.world * 296))
+            chunk_elems = 2048
+            while chunk_elems < target and chunk_elems < 65536:
+                chunk_elems *= 2
         self.chunk_elems = int(chunk_elems)
         self.bf16_shadow = bf16_shadow
         self.epoch = 0          # monotonically increasing flag epoch (never reset)
@@ -382,14 +388,10 @@ class FederatedEngine:
                 ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e - 1)
             wts = self._round_weights(masks[i])
             self.weights_dev[:W].copy_(torch.tensor(wts, dtype=torch.float32), non_blocking=True)
-            ext.signal_peers(arrive_ptrs, e)
+            need_wait = read_back or i == rounds - 1   # otherwise the next round's consumer polls the flags
             ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
-                               0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, n_blocks)
-            launches += 2
-            if read_back or i == rounds - 1:
-                # arena must be complete before the host reads the loss / the call returns
-                ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e)
-                launches += 1
+                               0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, n_blocks, arrive_ptrs, need_wait)
+            launches += 1
             if read_back:
                 self.loss_host[:2].copy_(losses_log[i, r], non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()

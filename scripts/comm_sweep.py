@@ -44,7 +44,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/comm_sweep.json")
     ap.add_argument("--sizes", default="4994,109386,1048576,11181644,50397188")
-    ap.add_argument("--chunk-elems", type=int, default=65536)
+    ap.add_argument("--chunk-elems", type=int, default=0, help="0 = adaptive")
     ap.add_argument("--shadow", action="store_true")
     args = ap.parse_args()
     rank, world, device = init_distributed()
@@ -52,7 +52,12 @@ def main():
     results = []
     for P in [int(s) for s in args.sizes.split(",")]:
         P4 = (P + 3) // 4 * 4
-        n_chunks = (P4 + args.chunk_elems - 1) // args.chunk_elems
+        chunk = args.chunk_elems
+        if not chunk:
+            chunk, target = 2048, max(1, P4 // (world * 296))
+            while chunk < target and chunk < 65536:
+                chunk *= 2
+        n_chunks = (P4 + chunk - 1) // chunk
         layout = {"work": (P4, torch.float32), "chunk_flags": (n_chunks, torch.int32), "flags": (64, torch.int32)}
         if args.shadow:
             layout["shadow"] = (P4, torch.bfloat16)
@@ -66,11 +71,9 @@ def main():
         def ours():
             state["e"] += 1
             e = state["e"]
-            ext.signal_peers(arrive, e)
             ext.twoshot_fedavg(arena.peer_ptrs("work"), arena.peer_ptrs("shadow") if args.shadow else [],
                                arena.peer_ptrs("chunk_flags"), arena.ptr("flags", None, 1), weights.data_ptr(), 0, e,
-                               (1 << world) - 1, 1.0, P4, args.chunk_elems, rank, n_blocks)
-            ext.wait_flags(arena.ptr("chunk_flags"), n_chunks, e)
+                               (1 << world) - 1, 1.0, P4, chunk, rank, n_blocks, arrive, True)
 
         iters = 20 if P4 < (1 << 22) else 8
         ms = timed(ours, iters, world, device)
@@ -80,7 +83,7 @@ def main():
         rec = {"P": P, "bytes": 4 * P4, "world": world, "provider": arena.provider, "multicast": arena.has_multicast,
                "twoshot_ms": ms, "twoshot_busbw_GBps": bus / ms / 1e6 if world > 1 else None,
                "nccl_allreduce_ms": ms_nccl, "nccl_busbw_GBps": bus / ms_nccl / 1e6 if world > 1 else None,
-               "shadow_bf16": args.shadow, "chunk_elems": args.chunk_elems}
+               "shadow_bf16": args.shadow, "chunk_elems": chunk}
         results.append(rec)
         if rank == 0:
             print(json.dumps(rec), flush=True)
