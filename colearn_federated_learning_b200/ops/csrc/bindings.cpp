@@ -185,6 +185,29 @@ torch::Tensor transpose_bf16(torch::Tensor x, c10::optional<torch::Tensor> out) 
   check(launch_transpose_bf16(x.data_ptr(), o.data_ptr(), (int)x.size(0), (int)x.size(1), cur_stream()), "transpose_bf16");
   return o;
 }
+torch::Tensor fix_precision(torch::Tensor x, double base) {
+  CHECK_CUDA_F32(x);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto out = torch::empty(x.sizes(), x.options().dtype(at::kLong));
+  check(launch_fix_precision(x.data_ptr<float>(), reinterpret_cast<long long*>(out.data_ptr<int64_t>()), x.numel(), base, cur_stream()), "fix_precision");
+  return out;
+}
+torch::Tensor float_precision(torch::Tensor x, double base) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kLong && x.is_contiguous(), "x must be contiguous CUDA int64");
+  c10::cuda::CUDAGuard guard(x.device());
+  auto out = torch::empty(x.sizes(), x.options().dtype(at::kFloat));
+  check(launch_float_precision(reinterpret_cast<const long long*>(x.data_ptr<int64_t>()), out.data_ptr<float>(), x.numel(), 1.0 / base, cur_stream()), "float_precision");
+  return out;
+}
+torch::Tensor ring_matmul(torch::Tensor a, torch::Tensor b) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.scalar_type() == at::kLong && b.scalar_type() == at::kLong, "int64 CUDA tensors");
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(0) && a.is_contiguous() && b.is_contiguous(), "A[M,K] B[K,N] contiguous");
+  c10::cuda::CUDAGuard guard(a.device());
+  auto out = torch::empty({a.size(0), b.size(1)}, a.options());
+  check(launch_ring_matmul(reinterpret_cast<const long long*>(a.data_ptr<int64_t>()), reinterpret_cast<const long long*>(b.data_ptr<int64_t>()),
+                           reinterpret_cast<long long*>(out.data_ptr<int64_t>()), (int)a.size(0), (int)a.size(1), (int)b.size(1), cur_stream()), "ring_matmul");
+  return out;
+}
 void l2_flush(torch::Tensor buf) {
   CHECK_CUDA_F32(buf);
   c10::cuda::CUDAGuard guard(buf.device());
@@ -363,6 +386,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fp32_to_bf16", &fp32_to_bf16);
   m.def("fp32_to_bf16_into", &fp32_to_bf16_into);
   m.def("l2_flush", &l2_flush);
+  m.def("fix_precision", &fix_precision);
+  m.def("float_precision", &float_precision);
+  m.def("ring_matmul", &ring_matmul);
   m.def("transpose_bf16", &transpose_bf16);
   m.def("star_round", &star_round);
   m.def("twoshot_fedavg", &twoshot_fedavg);

@@ -87,6 +87,10 @@ cudaError_t launch_minmax_scale(const float* x, float* out, int rows, int cols, 
 cudaError_t launch_feistel_permutation(int* out, int n, int rows, uint64_t seed, cudaStream_t s);
 cudaError_t launch_fp32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t s);
 cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s);
+// SMPC ring ops (int64, arithmetic mod 2^64)
+cudaError_t launch_fix_precision(const float* x, long long* out, int64_t n, double base, cudaStream_t s);
+cudaError_t launch_float_precision(const long long* x, float* out, int64_t n, double inv_base, cudaStream_t s);
+cudaError_t launch_ring_matmul(const long long* A, const long long* B, long long* C, int M, int K, int N, cudaStream_t s);
 // out[C,R] = in[R,C]^T (bf16), 32x32 smem tiles
 cudaError_t launch_transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t s);
 

@@ -311,6 +311,35 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv
   }
 }
 
+// ---- int64 ring ops for the SMPC path: Z_{2^64} arithmetic on CUDA cores ---------------------
+__global__ void fix_precision_kernel(const float* __restrict__ x, long long* __restrict__ out, int64_t n, double base) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (long long)rint((double)x[i] * base);   // round-half-even, same as torch.round
+}
+__global__ void float_precision_kernel(const long long* __restrict__ x, float* __restrict__ out, int64_t n, double inv_base) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (float)((double)x[i] * inv_base);
+}
+// C[m,n] = sum_k A[m,k] * B[k,n]  (mod 2^64; unsigned wrap-around == two's complement ring arithmetic)
+__global__ void ring_matmul_kernel(const unsigned long long* __restrict__ A, const unsigned long long* __restrict__ B,
+                                   unsigned long long* __restrict__ C, int M, int K, int N) {
+  __shared__ unsigned long long sa[16][17], sb[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  unsigned long long acc = 0ull;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    sa[ty][tx] = (row < M && k0 + tx < K) ? A[(size_t)row * K + k0 + tx] : 0ull;
+    sb[ty][tx] = (k0 + ty < K && col < N) ? B[(size_t)(k0 + ty) * N + col] : 0ull;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[k][tx];
+    __syncthreads();
+  }
+  if (row < M && col < N) C[(size_t)row * N + col] = acc;
+}
+
 __global__ void l2_flush_kernel(float* __restrict__ buf, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = (float)i;
@@ -395,6 +424,20 @@ cudaError_t launch_fp32_to_bf16(const float* in, void* out, int64_t n, cudaStrea
 cudaError_t launch_transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t s) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   transpose_bf16_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), rows, cols);
+  return cudaGetLastError();
+}
+cudaError_t launch_fix_precision(const float* x, long long* out, int64_t n, double base, cudaStream_t s) {
+  fix_precision_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(x, out, n, base);
+  return cudaGetLastError();
+}
+cudaError_t launch_float_precision(const long long* x, float* out, int64_t n, double inv_base, cudaStream_t s) {
+  float_precision_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(x, out, n, inv_base);
+  return cudaGetLastError();
+}
+cudaError_t launch_ring_matmul(const long long* A, const long long* B, long long* C, int M, int K, int N, cudaStream_t s) {
+  dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
+  ring_matmul_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const unsigned long long*>(A), reinterpret_cast<const unsigned long long*>(B),
+                                            reinterpret_cast<unsigned long long*>(C), M, K, N);
   return cudaGetLastError();
 }
 cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s) {

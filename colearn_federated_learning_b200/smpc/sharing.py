@@ -11,20 +11,32 @@ BASE = 10 ** PRECISION_FRACTIONAL
 
 
 def fix_precision(x: torch.Tensor, precision_fractional: int = PRECISION_FRACTIONAL) -> torch.Tensor:
-    """``round(x * 10**p)`` as int64 (reference ``cf.py:265``, ``fc.py:438,444``)."""
+    """``round(x * 10**p)`` as int64 (reference ``cf.py:265``, ``fc.py:438,444``).  CUDA tensors use the
+    ``fix_precision_kernel`` of ``csrc/elementwise.cu``."""
+    if x.is_cuda:
+        from ..ops import _ext
+        return _ext.require().fix_precision(x.contiguous().float(), float(10 ** precision_fractional))
     return torch.round(x.double() * (10 ** precision_fractional)).to(torch.int64)
 
 
 def float_precision(x: torch.Tensor, precision_fractional: int = PRECISION_FRACTIONAL) -> torch.Tensor:
+    if x.is_cuda:
+        from ..ops import _ext
+        return _ext.require().float_precision(x.contiguous(), float(10 ** precision_fractional))
     return x.to(torch.float64).div(10 ** precision_fractional).float()
 
 
-def _rand_ring(shape, gen: torch.Generator) -> torch.Tensor:
-    return torch.randint(-(2 ** 62), 2 ** 62, tuple(shape), dtype=torch.int64, generator=gen)
+def _rand_ring(shape, gen: torch.Generator, device=None) -> torch.Tensor:
+    r = torch.randint(-(2 ** 62), 2 ** 62, tuple(shape), dtype=torch.int64, generator=gen)
+    return r.to(device) if device is not None else r
 
 
 def ring_matmul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """int64 matmul with wrap-around (== arithmetic mod 2^64)."""
+    """int64 matmul with wrap-around (== arithmetic mod 2^64).  torch has no integer GEMM on CUDA; CUDA
+    tensors use the tiled ``ring_matmul_kernel``."""
+    if a.is_cuda and a.dim() == 2 and b.dim() == 2:
+        from ..ops import _ext
+        return _ext.require().ring_matmul(a.contiguous(), b.contiguous())
     return (a.unsqueeze(-1) * b.unsqueeze(-3)).sum(-2) if a.dim() > 1 else a @ b
 
 
@@ -37,14 +49,14 @@ class CryptoProvider:
         self.triples_dealt = 0
         self.comparisons = 0
 
-    def matmul_triple(self, a_shape, b_shape) -> Tuple["SharedTensor", "SharedTensor", "SharedTensor"]:
-        a, b = _rand_ring(a_shape, self.gen), _rand_ring(b_shape, self.gen)
+    def matmul_triple(self, a_shape, b_shape, device=None) -> Tuple["SharedTensor", "SharedTensor", "SharedTensor"]:
+        a, b = _rand_ring(a_shape, self.gen, device), _rand_ring(b_shape, self.gen, device)
         c = ring_matmul(a, b)
         self.triples_dealt += 1
         return share(a, self), share(b, self), share(c, self)
 
-    def mul_triple(self, shape) -> Tuple["SharedTensor", "SharedTensor", "SharedTensor"]:
-        a, b = _rand_ring(shape, self.gen), _rand_ring(shape, self.gen)
+    def mul_triple(self, shape, device=None) -> Tuple["SharedTensor", "SharedTensor", "SharedTensor"]:
+        a, b = _rand_ring(shape, self.gen, device), _rand_ring(shape, self.gen, device)
         self.triples_dealt += 1
         return share(a, self), share(b, self), share(a * b, self)
 
@@ -71,7 +83,7 @@ class SharedTensor:
         return self.shares[0] + self.shares[1]
 
     def refresh(self) -> "SharedTensor":
-        r = _rand_ring(self.shape, self.provider.gen)
+        r = _rand_ring(self.shape, self.provider.gen, self.shares[0].device)
         return SharedTensor([self.shares[0] + r, self.shares[1] - r], self.provider)
 
     # -- linear ops are local -----------------------------------------------------------------
@@ -106,7 +118,7 @@ class SharedTensor:
 
     # -- Beaver multiplication --------------------------------------------------------------------
     def matmul(self, other: "SharedTensor") -> "SharedTensor":
-        a, b, c = self.provider.matmul_triple(self.shape, other.shape)
+        a, b, c = self.provider.matmul_triple(self.shape, other.shape, self.shares[0].device)
         d = (self - a).get()   # opened
         e = (other - b).get()  # opened
         z0 = c.shares[0] + ring_matmul(d, b.shares[0]) + ring_matmul(a.shares[0], e) + ring_matmul(d, e)
@@ -114,7 +126,7 @@ class SharedTensor:
         return SharedTensor([z0, z1], self.provider)
 
     def mul(self, other: "SharedTensor") -> "SharedTensor":
-        a, b, c = self.provider.mul_triple(self.shape)
+        a, b, c = self.provider.mul_triple(self.shape, self.shares[0].device)
         d, e = (self - a).get(), (other - b).get()
         z0 = c.shares[0] + d * b.shares[0] + a.shares[0] * e + d * e
         z1 = c.shares[1] + d * b.shares[1] + a.shares[1] * e
@@ -127,5 +139,5 @@ class SharedTensor:
 
 
 def share(secret: torch.Tensor, provider: CryptoProvider) -> SharedTensor:
-    r = _rand_ring(secret.shape, provider.gen)
+    r = _rand_ring(secret.shape, provider.gen, secret.device)
     return SharedTensor([r, secret - r], provider)

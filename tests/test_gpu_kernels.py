@@ -221,3 +221,22 @@ def test_transpose_bf16():
     dev = _dev()
     x = torch.randn(300, 70, device=dev).to(torch.bfloat16)
     assert torch.equal(ops.transpose_bf16(x), x.t().contiguous())
+
+
+def test_smpc_ring_kernels_match_cpu():
+    """int64 ring ops on CUDA cores (fix-precision encode/decode, wrap-around matmul, Beaver matmul)."""
+    from colearn_federated_learning_b200.smpc import CryptoProvider, fix_precision, float_precision, share
+    from colearn_federated_learning_b200.smpc.sharing import ring_matmul
+    dev = _dev()
+    torch.manual_seed(8)
+    x = torch.randn(37, 19) * 5
+    assert torch.equal(fix_precision(x.to(dev)).cpu(), fix_precision(x))
+    assert torch.allclose(float_precision(fix_precision(x.to(dev))).cpu(), float_precision(fix_precision(x)))
+    a = torch.randint(-(2 ** 62), 2 ** 62, (33, 21), dtype=torch.int64)
+    b = torch.randint(-(2 ** 62), 2 ** 62, (21, 18), dtype=torch.int64)
+    assert torch.equal(ring_matmul(a.to(dev), b.to(dev)).cpu(), ring_matmul(a, b))      # exact, incl. wrap-around
+    p = CryptoProvider(4)
+    u, v = torch.randn(6, 9), torch.randn(9, 5)
+    su, sv = share(fix_precision(u.to(dev)), p), share(fix_precision(v.to(dev)), p)
+    got = float_precision(su.matmul(sv).truncate().get()).cpu()
+    assert (got - u @ v).abs().max() < 0.03
