@@ -218,7 +218,7 @@ void l2_flush(torch::Tensor buf) {
 void star_round(int64_t theta, int64_t slots, int64_t slot_stride, int64_t arrive_flags, int64_t arrive_epoch,
                 std::vector<int64_t> peer_inbox, std::vector<int64_t> peer_bcast_flag, int64_t bcast_epoch,
                 int64_t mc_inbox, int64_t select_mask, double server_lr, int64_t n, bool do_reduce, bool do_bcast,
-                int64_t grid_counter, int64_t n_blocks) {
+                int64_t grid_counter, int64_t n_blocks, double timeout_ms, std::vector<double> weights, int64_t decision) {
   StarRoundArgs a;
   std::memset(&a, 0, sizeof(a));
   a.theta = ptr_of<float>(theta);
@@ -240,6 +240,10 @@ void star_round(int64_t theta, int64_t slots, int64_t slot_stride, int64_t arriv
   a.do_reduce = do_reduce ? 1 : 0;
   a.do_bcast = do_bcast ? 1 : 0;
   a.grid_counter = ptr_of<uint32_t>(grid_counter);
+  a.timeout_ns = timeout_ms > 0 ? (unsigned long long)(timeout_ms * 1e6) : 0ull;
+  for (size_t k = 0; k < weights.size() && k < 16; ++k) a.weights[k] = (float)weights[k];
+  a.decision = ptr_of<uint32_t>(decision);
+  TORCH_CHECK(a.timeout_ns == 0 || a.decision != nullptr, "a deadline needs the decision scratch buffer");
   check(launch_star_round(a, (int)n_blocks, cur_stream()), "star_round");
 }
 

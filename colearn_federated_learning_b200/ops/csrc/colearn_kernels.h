@@ -119,6 +119,12 @@ struct StarRoundArgs {
   int do_reduce;                // 0: broadcast only (round 0)
   int do_bcast;                 // 0: reduce/apply only (last round)
   uint32_t* grid_counter;       // device scratch for the in-kernel grid barrier
+  // failure detection: give up on a silent worker after timeout_ns (0 = wait forever).  weights[k]
+  // are the FedAvg weights the producers pre-applied, so the sum can be renormalised over the
+  // workers that actually arrived.  decision[0] = epoch flag, decision[1] = arrived mask (device).
+  unsigned long long timeout_ns;
+  float weights[16];
+  uint32_t* decision;
 };
 cudaError_t launch_star_round(const StarRoundArgs& a, int n_blocks, cudaStream_t s);
 

@@ -60,12 +60,54 @@ __device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
 __global__ void __launch_bounds__(256)
 star_round_kernel(StarRoundArgs a) {
   const int tid = threadIdx.x;
-  // (1) wait for every selected worker's contribution of this round
+  // (1) wait for every selected worker's contribution of this round.  With a deadline (failure
+  //     detection): block 0 decides who made it, publishes the arrived mask, and every block
+  //     reduces over exactly that set, renormalising by the weight that actually arrived.
+  uint32_t mask = a.select_mask;
+  float renorm = 1.f;
   if (a.do_reduce) {
-    if (tid < a.world && ((a.select_mask >> tid) & 1u)) {
-      while (ld_acquire_sys(a.arrive_flags + tid) < a.arrive_epoch) __nanosleep(20);
+    if (a.timeout_ns == 0) {
+      if (tid < a.world && ((mask >> tid) & 1u))
+        while (ld_acquire_sys(a.arrive_flags + tid) < a.arrive_epoch) __nanosleep(20);
+      __syncthreads();
+    } else {
+      __shared__ uint32_t s_mask;
+      if (blockIdx.x == 0) {
+        if (tid == 0) s_mask = 0u;
+        __syncthreads();
+        if (tid < a.world && ((mask >> tid) & 1u)) {
+          unsigned long long t0, t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          bool ok = false;
+          do {
+            ok = ld_acquire_sys(a.arrive_flags + tid) >= a.arrive_epoch;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          } while (!ok && (t1 - t0) < a.timeout_ns);
+          if (ok) atomicOr(&s_mask, 1u << tid);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          a.decision[1] = s_mask;
+          __threadfence();
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.decision), "r"(a.arrive_epoch) : "memory");
+        }
+      } else {
+        if (tid == 0) {
+          uint32_t v;
+          do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.decision) : "memory"); } while (v < a.arrive_epoch);
+          s_mask = a.decision[1];
+        }
+      }
+      __syncthreads();
+      mask = s_mask;
+      float wsum = 0.f, wall = 0.f;
+      for (int k = 0; k < a.world; ++k) {
+        if ((a.select_mask >> k) & 1u) wall += a.weights[k];
+        if ((mask >> k) & 1u) wsum += a.weights[k];
+      }
+      renorm = wsum > 0.f ? wall / wsum : 0.f;
+      if (mask == 0u) renorm = 0.f;
     }
-    __syncthreads();
   }
   const int64_t n4 = a.n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -75,10 +117,12 @@ star_round_kernel(StarRoundArgs a) {
     if (a.do_reduce) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = 0; k < a.world; ++k) {
-        if (!((a.select_mask >> k) & 1u)) continue;
+        if (!((mask >> k) & 1u)) continue;
         const float4 v = __ldcg(reinterpret_cast<const float4*>(a.slots + k * a.slot_stride) + j);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
+      if (mask == 0u) acc = t;   // nobody arrived: keep theta
+      else if (renorm != 1.f) { acc.x *= renorm; acc.y *= renorm; acc.z *= renorm; acc.w *= renorm; }
       t.x = fmaf(a.server_lr, acc.x - t.x, t.x); t.y = fmaf(a.server_lr, acc.y - t.y, t.y);
       t.z = fmaf(a.server_lr, acc.z - t.z, t.z); t.w = fmaf(a.server_lr, acc.w - t.w, t.w);
       theta4[j] = t;
@@ -98,7 +142,8 @@ star_round_kernel(StarRoundArgs a) {
     if (a.do_reduce) {
       float acc = 0.f;
       for (int k = 0; k < a.world; ++k)
-        if ((a.select_mask >> k) & 1u) acc += __ldcg(a.slots + k * a.slot_stride + j);
+        if ((mask >> k) & 1u) acc += __ldcg(a.slots + k * a.slot_stride + j);
+      acc = (mask == 0u) ? t : acc * renorm;
       t = fmaf(a.server_lr, acc - t, t);
       a.theta[j] = t;
     }

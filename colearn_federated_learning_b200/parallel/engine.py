@@ -67,6 +67,7 @@ class FederatedEngine:
                  local_epochs: int = 1, max_batches: int = -1, loss: str = "auto", weighted: bool = True,
                  server_lr: float = 1.0, coordinator_rank: int = 0, algo: str = "auto", seed: int = 1,
                  shuffle: bool = True, chunk_elems: int = 0, bf16_shadow: bool = False,
+                 round_deadline_ms: float = 0.0,
                  model_kwargs: Optional[Dict[str, Any]] = None) -> None:
         self.rank = dist.get_rank(group) if _dist_ready() else 0
         self.world = dist.get_world_size(group) if _dist_ready() else 1
@@ -108,6 +109,9 @@ class FederatedEngine:
                 chunk_elems *= 2
         self.chunk_elems = int(chunk_elems)
         self.bf16_shadow = bf16_shadow
+        # failure detection: a selected worker that has not delivered within this many ms of the coordinator
+        # starting its reduce is dropped from that round (its weight is renormalised away); 0 = wait forever
+        self.round_deadline_ms = float(round_deadline_ms)
         self.epoch = 0          # monotonically increasing flag epoch (never reset)
         self.rounds_done = 0
         self.x: Optional[torch.Tensor] = None
@@ -139,6 +143,7 @@ class FederatedEngine:
         self.arena = SymmetricArena(layout, self.device, self.group)
         self.ext = ops._ext.require()
         self.grid_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.decision = torch.zeros(2, dtype=torch.int32, device=self.device)
         flat = flatten_params(self.model).to(self.device)
         if self.algo == "star":
             self.theta = torch.zeros(P4, device=self.device)
@@ -253,6 +258,7 @@ class FederatedEngine:
         n_blocks = max(1, min(148, (P4 // 4 + 255) // 256))
         is_coord = r == self.coord
         losses_log = torch.zeros(rounds, W, 2, device=dev) if is_coord else None
+        arrived_log = torch.zeros(rounds, dtype=torch.int32, device=dev)
         launches = 0
         if _dist_ready() and W > 1 and self._barrier:
             dist.barrier(group=self.group)
@@ -261,20 +267,22 @@ class FederatedEngine:
         ev0.record()
 
         def star(do_reduce: bool, do_bcast: bool, mask_reduce: int, mask_bcast: int, arrive_epoch: int, bcast_epoch: int):
+            wts = [float(v) for v in self._round_weights(mask_reduce)] if do_reduce else [0.0] * W
             # reduce over the workers of the finished round, broadcast to those of the next one
             if do_reduce and do_bcast and mask_reduce != mask_bcast:
                 ext.star_round(self.theta.data_ptr(), arena.ptr("slots"), P4, arena.ptr("flags", None, 1), arrive_epoch,
                                inbox_ptrs, bflag_ptrs, bcast_epoch, 0, mask_reduce, self.server_lr, P4, True, False,
-                               self.grid_counter.data_ptr(), n_blocks)
+                               self.grid_counter.data_ptr(), n_blocks, self.round_deadline_ms, wts, self.decision.data_ptr())
                 ext.star_round(self.theta.data_ptr(), arena.ptr("slots"), P4, arena.ptr("flags", None, 1), arrive_epoch,
                                inbox_ptrs, bflag_ptrs, bcast_epoch, arena.mc_ptr("inbox") if mask_bcast == (1 << W) - 1 else 0,
-                               mask_bcast, self.server_lr, P4, False, True, self.grid_counter.data_ptr(), n_blocks)
+                               mask_bcast, self.server_lr, P4, False, True, self.grid_counter.data_ptr(), n_blocks, 0.0, wts, 0)
                 return 2
             mask = mask_reduce if do_reduce else mask_bcast
             mc = arena.mc_ptr("inbox") if (do_bcast and mask == (1 << W) - 1) else 0
             ext.star_round(self.theta.data_ptr(), arena.ptr("slots"), P4, arena.ptr("flags", None, 1), arrive_epoch,
                            inbox_ptrs, bflag_ptrs, bcast_epoch, mc, mask, self.server_lr, P4, do_reduce, do_bcast,
-                           self.grid_counter.data_ptr(), n_blocks)
+                           self.grid_counter.data_ptr(), n_blocks, self.round_deadline_ms if do_reduce else 0.0, wts,
+                           self.decision.data_ptr())
             return 1
 
         if is_coord:
@@ -292,6 +300,8 @@ class FederatedEngine:
                 last = i == rounds - 1
                 launches += star(True, not last, masks[i], masks[i + 1] if not last else 0, e0 + i + 1, e0 + i + 2)
                 losses_log[i].copy_(arena.tensor("losses").view(W, 2), non_blocking=True)
+                if self.round_deadline_ms > 0:
+                    arrived_log[i].copy_(self.decision[1], non_blocking=True)
                 if read_back:
                     self.loss_host.copy_(arena.tensor("losses"), non_blocking=True)
                     torch.cuda.current_stream(dev).synchronize()
@@ -306,7 +316,8 @@ class FederatedEngine:
         nsel = [bin(m).count("1") for m in masks]
         return RoundReport(rounds, W, "fused", "star", ev0.elapsed_time(ev1), losses_log, launches,
                            bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel),
-                           extra={"provider": arena.provider, "multicast": arena.has_multicast})
+                           extra={"provider": arena.provider, "multicast": arena.has_multicast,
+                                  "arrived_masks": arrived_log.tolist() if (is_coord and self.round_deadline_ms > 0) else None})
 
     # ------------------------------------------------------------------------------------------ twoshot
     def _layerwise_trainer(self):
