@@ -118,3 +118,20 @@ def test_encrypted_training_tracks_plaintext_training():
     sm.reveal_into(m)
     after = torch.cat([q.detach().reshape(-1) for q in m.parameters()])
     assert not torch.equal(before, after) and (m(x) > 0.5).all()
+
+
+def test_box_mode_cli_two_ranks_gloo(tmp_path):
+    """``federated_coordinator.py --box`` under torchrun: rank 0 runs parser/window/selection on the in-process bus,
+    both ranks train, rank 0 writes the reference-format checkpoint (CPU/gloo stand-in for the fused GPU path)."""
+    ckpt = str(tmp_path / "test.pth")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "federated_coordinator.py"),
+                          "-t", "topic/state", "--box", "--model", "mlp", "--synthetic", "128", "-f", "2", "--weighted",
+                          "-w", "1", "--checkpoint", ckpt, "--batch-size", "4"], env=env, capture_output=True, text=True,
+                         timeout=240, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "window closed: members=['10.0.0.1:8777', '10.0.0.2:8778']" in out.stderr
+    assert out.stderr.count("Loss for worker id: 10.0.0.") == 4
+    state = torch.load(ckpt, weights_only=True)
+    assert state["fc1.weight"].shape == (64, 10) and state["fc3.weight"].shape == (2, 64)
