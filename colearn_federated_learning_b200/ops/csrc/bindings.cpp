@@ -250,7 +250,7 @@ void star_round(int64_t theta, int64_t slots, int64_t slot_stride, int64_t arriv
 void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std::vector<int64_t> chunk_flags,
                     int64_t arrive_flags, int64_t weights, int64_t theta_prev, int64_t epoch, int64_t select_mask,
                     double server_lr, int64_t n, int64_t chunk_elems, int64_t rank, int64_t n_blocks,
-                    std::vector<int64_t> peer_arrive, bool wait_all) {
+                    std::vector<int64_t> peer_arrive, bool wait_all, int64_t mc_work, int64_t mc_shadow) {
   TwoShotArgs a;
   std::memset(&a, 0, sizeof(a));
   a.world = (int)work.size();
@@ -272,6 +272,8 @@ void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std:
   a.signal_arrive = peer_arrive.empty() ? 0 : 1;
   for (size_t k = 0; k < peer_arrive.size() && k < 16; ++k) a.peer_arrive[k] = ptr_of<uint32_t>(peer_arrive[k]);
   a.wait_all = wait_all ? 1 : 0;
+  a.mc_work = ptr_of<float>(mc_work);
+  a.mc_shadow = ptr_of<void>(mc_shadow);
   check(launch_twoshot_fedavg(a, (int)n_blocks, cur_stream()), "twoshot_fedavg");
 }
 

@@ -150,6 +150,8 @@ struct TwoShotArgs {
   int world;
   int rank;
   uint32_t* peer_arrive[16];    // if signal_arrive: my arrive slot on every rank (raised at kernel start)
+  float* mc_work;               // NVLS multicast alias of the work arena: enables multimem.ld_reduce / multimem.st
+  void* mc_shadow;              // multicast alias of the bf16 shadow arena (or nullptr)
   int signal_arrive;            // fold the "local training done" signal into this kernel
   int wait_all;                 // spin at the end until every chunk of MY arena carries `epoch`
 };

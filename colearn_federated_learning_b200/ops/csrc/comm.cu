@@ -48,6 +48,16 @@ __device__ __forceinline__ void st_peer_f4(float4* p, const float4& v) {
 __device__ __forceinline__ void multimem_st_f4(float4* p, const float4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float4* p) {
+  // in-switch (NVLS) sum over every member of the multicast group: one 16-byte response per request
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_b64(uint2* p, const uint2& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
+}
 __device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   uint2 r;
@@ -197,6 +207,28 @@ twoshot_fedavg_kernel(TwoShotArgs a) {
     const int64_t lo = c * a.chunk_elems;
     const int64_t hi = (lo + a.chunk_elems < a.n) ? lo + a.chunk_elems : a.n;
     const int64_t len4 = (hi - lo) >> 2;  // n and chunk_elems are multiples of 4
+    if (a.mc_work != nullptr) {
+      // NVLS path (all ranks selected, uniform weights): the switch sums the W copies on the way in
+      // (ingress P/W instead of (W-1)P/W) and replicates the result on the way out (egress P/W).
+      const float w = sw[0];
+      const float4* src = reinterpret_cast<const float4*>(a.mc_work) + (lo >> 2);
+      float4* dst = reinterpret_cast<float4*>(a.mc_work) + (lo >> 2);
+      uint2* dsh = a.mc_shadow ? reinterpret_cast<uint2*>(a.mc_shadow) + (lo >> 2) : nullptr;
+      for (int64_t j = tid; j < len4; j += 4 * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j + u * blockDim.x < len4) v[u] = multimem_ld_reduce_f4(src + j + u * blockDim.x);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j + u * blockDim.x < len4) {
+            v[u].x *= w; v[u].y *= w; v[u].z *= w; v[u].w *= w;
+            multimem_st_f4(dst + j + u * blockDim.x, v[u]);
+            if (dsh) multimem_st_b64(dsh + j + u * blockDim.x, pack_bf16x4(v[u]));
+          }
+        }
+      }
+    } else
     // two float4 per thread per iteration: 2 x (#selected peers) 16-byte peer loads in flight per thread
     for (int64_t j = tid; j < len4; j += 2 * blockDim.x) {
       const int64_t e4a = (lo >> 2) + j;

@@ -112,6 +112,7 @@ class FederatedEngine:
         # failure detection: a selected worker that has not delivered within this many ms of the coordinator
         # starting its reduce is dropped from that round (its weight is renormalised away); 0 = wait forever
         self.round_deadline_ms = float(round_deadline_ms)
+        self.use_nvls = os.environ.get("COLEARN_NVLS", "1") != "0"   # multimem.ld_reduce / multimem.st in the two-shot kernel
         self.epoch = 0          # monotonically increasing flag epoch (never reset)
         self.rounds_done = 0
         self.x: Optional[torch.Tensor] = None
@@ -400,8 +401,14 @@ class FederatedEngine:
             wts = self._round_weights(masks[i])
             self.weights_dev[:W].copy_(torch.tensor(wts, dtype=torch.float32), non_blocking=True)
             need_wait = read_back or i == rounds - 1   # otherwise the next round's consumer polls the flags
+            sel_w = [w for k, w in enumerate(wts) if (masks[i] >> k) & 1]
+            nvls = (self.use_nvls and arena.has_multicast and masks[i] == (1 << W) - 1 and W > 1
+                    and max(sel_w) - min(sel_w) < 1e-7)
             ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
-                               0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, n_blocks, arrive_ptrs, need_wait)
+                               0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, n_blocks, arrive_ptrs, need_wait,
+                               arena.mc_ptr("work") if nvls else 0,
+                               arena.mc_ptr("shadow") if (nvls and self.bf16_shadow) else 0)
+            self._last_nvls = bool(nvls)
             launches += 1
             if read_back:
                 self.loss_host[:2].copy_(losses_log[i, r], non_blocking=True)
@@ -416,7 +423,7 @@ class FederatedEngine:
         return RoundReport(rounds, W, "fused", "twoshot", ev0.elapsed_time(ev1), losses_log, launches,
                            bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel),
                            extra={"provider": arena.provider, "train_path": getattr(self, "_last_path", None),
-                                  "n_chunks": self.n_chunks})
+                                  "n_chunks": self.n_chunks, "nvls": getattr(self, "_last_nvls", False)})
 
     # ------------------------------------------------------------------------------------------ cpu / gloo
     def _run_cpu(self, rounds: int, masks: List[int]) -> RoundReport:

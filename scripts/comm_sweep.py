@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--sizes", default="4994,109386,1048576,11181644,50397188")
     ap.add_argument("--chunk-elems", type=int, default=0, help="0 = adaptive")
     ap.add_argument("--shadow", action="store_true")
+    ap.add_argument("--nvls", type=int, default=1, help="use multimem.ld_reduce/st when a multicast mapping exists")
     args = ap.parse_args()
     rank, world, device = init_distributed()
     ext = ops._ext.require()
@@ -64,6 +65,7 @@ def main():
         arena = SymmetricArena(layout, device)
         arena.tensor("work").normal_()
         weights = torch.full((16,), 1.0 / world, device=device)
+        use_nvls = bool(args.nvls and arena.has_multicast and world > 1)
         arrive = [arena.ptr("flags", k, 1 + rank) for k in range(world)]
         state = {"e": 0}
         n_blocks = max(1, min(148 * 2, (n_chunks + world - 1) // world))
@@ -73,7 +75,9 @@ def main():
             e = state["e"]
             ext.twoshot_fedavg(arena.peer_ptrs("work"), arena.peer_ptrs("shadow") if args.shadow else [],
                                arena.peer_ptrs("chunk_flags"), arena.ptr("flags", None, 1), weights.data_ptr(), 0, e,
-                               (1 << world) - 1, 1.0, P4, chunk, rank, n_blocks, arrive, True)
+                               (1 << world) - 1, 1.0, P4, chunk, rank, n_blocks, arrive, True,
+                               arena.mc_ptr("work") if use_nvls else 0,
+                               arena.mc_ptr("shadow") if (use_nvls and args.shadow) else 0)
 
         iters = 20 if P4 < (1 << 22) else 8
         ms = timed(ours, iters, world, device)
@@ -83,7 +87,7 @@ def main():
         rec = {"P": P, "bytes": 4 * P4, "world": world, "provider": arena.provider, "multicast": arena.has_multicast,
                "twoshot_ms": ms, "twoshot_busbw_GBps": bus / ms / 1e6 if world > 1 else None,
                "nccl_allreduce_ms": ms_nccl, "nccl_busbw_GBps": bus / ms_nccl / 1e6 if world > 1 else None,
-               "shadow_bf16": args.shadow, "chunk_elems": chunk}
+               "shadow_bf16": args.shadow, "chunk_elems": chunk, "nvls": use_nvls}
         results.append(rec)
         if rank == 0:
             print(json.dumps(rec), flush=True)

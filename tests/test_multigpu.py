@@ -115,6 +115,49 @@ def _rank_main(rank, world, port, out_path, case):
             if rank == 0:
                 torch.save({"same": same, "shadow_ok": bool(shadow_ok), "moved": not torch.equal(flat, theta0),
                             "finite": bool(torch.isfinite(flat).all()), "n_chunks": rep.extra["n_chunks"]}, out_path)
+        elif case == "twoshot_kernel":
+            # direct numerics of twoshot_fedavg_kernel: P2P path (non-uniform weights, subset mask) and NVLS path
+            from colearn_federated_learning_b200.parallel.symm import SymmetricArena
+            ext = ops._ext.require()
+            P4, chunk = 40000, 2048
+            n_chunks = (P4 + chunk - 1) // chunk
+            arena = SymmetricArena({"work": (P4, torch.float32), "shadow": (P4, torch.bfloat16),
+                                    "chunk_flags": (n_chunks, torch.int32), "flags": (64, torch.int32)}, dev)
+            base = torch.arange(P4, dtype=torch.float32, device=dev) * 1e-3
+            arrive = [arena.ptr("flags", k, 1 + rank) for k in range(world)]
+            results = {}
+            epoch = 0
+            for name, mask, wts, nvls in (("p2p_weighted", (1 << world) - 1, [float(k + 1) for k in range(world)], False),
+                                          ("p2p_subset", 0b01 if world == 2 else 0b0110, None, False),
+                                          ("nvls_uniform", (1 << world) - 1, None, True)):
+                epoch += 1
+                sel = [k for k in range(world) if (mask >> k) & 1]
+                w = torch.zeros(16)
+                if wts is None:
+                    for k in sel:
+                        w[k] = 1.0 / len(sel)
+                else:
+                    tot = sum(wts[k] for k in sel)
+                    for k in sel:
+                        w[k] = wts[k] / tot
+                arena.tensor("work").copy_(base * (rank + 1) + rank)
+                torch.cuda.synchronize()
+                dist.barrier()
+                use_nvls = nvls and arena.has_multicast
+                ext.twoshot_fedavg(arena.peer_ptrs("work"), arena.peer_ptrs("shadow"), arena.peer_ptrs("chunk_flags"),
+                                   arena.ptr("flags", None, 1), w.to(dev).data_ptr(), 0, epoch, mask, 1.0, P4, chunk, rank,
+                                   8, arrive, True, arena.mc_ptr("work") if use_nvls else 0,
+                                   arena.mc_ptr("shadow") if use_nvls else 0)
+                torch.cuda.synchronize()
+                dist.barrier()
+                want = sum(float(w[k]) * (base * (k + 1) + k) for k in sel)
+                got = arena.tensor("work")
+                results[name] = {"err": float((got - want).abs().max() / want.abs().max()), "nvls": bool(use_nvls),
+                                 "shadow_ok": bool(torch.equal(arena.tensor("shadow"), got.to(torch.bfloat16)))}
+            allr = [None] * world
+            dist.all_gather_object(allr, results)
+            if rank == 0:
+                torch.save(allr, out_path)
         elif case == "deadline":
             # failure detection: rank 1 is ~60x slower than the coordinator's deadline allows -> dropped from the
             # round, its weight renormalised away, the round completes with the workers that did arrive
@@ -162,7 +205,7 @@ def _rank_main(rank, world, port, out_path, case):
 
 
 @pytest.mark.multigpu
-@pytest.mark.parametrize("case", ["star", "twoshot", "wide", "deadline"])
+@pytest.mark.parametrize("case", ["star", "twoshot", "twoshot_kernel", "wide", "deadline"])
 def test_fused_collectives_multi_rank(tmp_path, case):
     world = min(torch.cuda.device_count(), 8)
     out = str(tmp_path / "out.pt")
@@ -171,6 +214,10 @@ def test_fused_collectives_multi_rank(tmp_path, case):
     if case == "star":
         assert res["err"] < 2e-3, res
         assert torch.isfinite(res["losses"]).all()
+    elif case == "twoshot_kernel":
+        for per_rank in res:
+            for name, r in per_rank.items():
+                assert r["err"] < 1e-5 and r["shadow_ok"], (name, r)
     elif case == "deadline":
         assert (res["arrived"] >> 1) & 1 == 0 and res["arrived"] & 1 == 1, res     # slow rank 1 dropped, rank 0 kept
         assert res["err"] < 2e-3, res
