@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--sizes", default="4994,109386,1048576,11181644,50397188")
     ap.add_argument("--chunk-elems", type=int, default=0, help="0 = adaptive")
     ap.add_argument("--shadow", action="store_true")
+    ap.add_argument("--blocks", type=int, default=0, help="CTAs for the two-shot kernel (0 = auto)")
+    ap.add_argument("--tag", default="")
     ap.add_argument("--nvls", type=int, default=1, help="use multimem.ld_reduce/st when a multicast mapping exists")
     args = ap.parse_args()
     rank, world, device = init_distributed()
@@ -68,7 +70,7 @@ def main():
         use_nvls = bool(args.nvls and arena.has_multicast and world > 1)
         arrive = [arena.ptr("flags", k, 1 + rank) for k in range(world)]
         state = {"e": 0}
-        n_blocks = max(1, min(148 * 2, (n_chunks + world - 1) // world))
+        n_blocks = args.blocks or max(1, min(148 * 2, (n_chunks + world - 1) // world))
 
         def ours():
             state["e"] += 1
@@ -87,7 +89,7 @@ def main():
         rec = {"P": P, "bytes": 4 * P4, "world": world, "provider": arena.provider, "multicast": arena.has_multicast,
                "twoshot_ms": ms, "twoshot_busbw_GBps": bus / ms / 1e6 if world > 1 else None,
                "nccl_allreduce_ms": ms_nccl, "nccl_busbw_GBps": bus / ms_nccl / 1e6 if world > 1 else None,
-               "shadow_bf16": args.shadow, "chunk_elems": chunk, "nvls": use_nvls}
+               "shadow_bf16": args.shadow, "chunk_elems": chunk, "nvls": use_nvls, "blocks": n_blocks, "tag": args.tag}
         results.append(rec)
         if rank == 0:
             print(json.dumps(rec), flush=True)
