@@ -28,6 +28,15 @@ from ..models import MLPSpec
 PAD = 128
 
 
+class ReadySpec:
+    """Where the two-shot broadcast publishes per-chunk readiness (fused broadcast -> GEMM).
+    ``epoch_ptr`` (device uint32) takes precedence over ``epoch`` so a captured CUDA graph can be replayed
+    every round with a new epoch."""
+
+    def __init__(self, flags_ptr: int, chunk_elems: int, epoch: int = 0, epoch_ptr: int = 0) -> None:
+        self.flags_ptr, self.chunk_elems, self.epoch, self.epoch_ptr = int(flags_ptr), int(chunk_elems), int(epoch), int(epoch_ptr)
+
+
 def _pad_to(n: int, m: int = PAD) -> int:
     return (n + m - 1) // m * m
 
@@ -131,8 +140,8 @@ class LayerwiseMLPTrainer:
 
     # -- one SGD step = forward() + backward() ------------------------------------------------------------
     def forward(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor,
-                ready: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
-        """``ready = (chunk_flags_ptr, epoch, chunk_elems)``: the GEMMs of the exact layers poll the
+                ready: Optional[ReadySpec] = None) -> torch.Tensor:
+        """``ready`` (:class:`ReadySpec`): the GEMMs of the exact layers poll the
         two-shot broadcast's per-chunk flags from their TMA producer warp (first step of a round)."""
         L = self.L
         self.a[0].zero_()
@@ -141,8 +150,8 @@ class LayerwiseMLPTrainer:
         for l in range(L):
             kw = {}
             if ready is not None and self.exact[l] and self.shadow_arena is not None:
-                kw = dict(ready_flags=ready[0], ready_epoch=ready[1], ready_chunk_elems=ready[2],
-                          ready_elem_offset=self.offsets[l][0])
+                kw = dict(ready_flags=ready.flags_ptr, ready_epoch=ready.epoch, ready_chunk_elems=ready.chunk_elems,
+                          ready_elem_offset=self.offsets[l][0], ready_epoch_ptr=ready.epoch_ptr)
             if l < L - 1:
                 ops.gemm_bf16(self.a[l], self.Ws[l], bias=self._bias(flat, l), relu=True, out_bf16=self.a[l + 1],
                               out_bf16_t=self.aT[l + 1], **kw)
@@ -187,7 +196,7 @@ class LayerwiseMLPTrainer:
         return loss
 
     def fit(self, flat: torch.Tensor, x: torch.Tensor, y: torch.Tensor, cfg, perm: Optional[torch.Tensor],
-            ready: Optional[Tuple[int, int, int]] = None, wait_chunks=None) -> torch.Tensor:
+            ready: Optional[ReadySpec] = None, wait_chunks=None) -> torch.Tensor:
         """Local SGD in place on ``flat`` (full batches only; a tail < batch_size is dropped).
 
         With ``ready`` (fused broadcast consumption) the order is: wait only for the chunks of the
@@ -198,7 +207,7 @@ class LayerwiseMLPTrainer:
         if ready is not None and wait_chunks is not None:
             for l in range(self.L):
                 if not self.exact[l]:
-                    wait_chunks(self.chunk_range(l, ready[2]))
+                    wait_chunks(self.chunk_range(l, ready.chunk_elems))
         self.refresh_edge(flat)
         if ready is None:
             self.refresh_exact(flat, from_broadcast=False)
@@ -223,3 +232,63 @@ class LayerwiseMLPTrainer:
         if it == 0 and ready is not None and wait_chunks is not None:
             wait_chunks(None)
         return last
+
+    # -- CUDA graph of a whole local fit (launch-bound inner loop -> one replay per round) -----------------
+    def build_round_graph(self, flat: torch.Tensor, x: torch.Tensor, y: torch.Tensor, lr: float, n_steps: int,
+                          ready: ReadySpec, n_chunks: int) -> None:
+        """Capture ``n_steps`` SGD steps of a *fused-broadcast* round into one CUDA graph:
+
+            wait(edge-layer chunks) -> edge shadows -> [gather batch -> forward (GEMMs poll the broadcast
+            flags on step 0) -> wait(all chunks) + W^T on step 0 -> backward] x n_steps
+
+        Everything round-specific is device-resident: the epoch the flag waits compare against lives in
+        ``ready.epoch_ptr``, the sample order in ``self.g_idx``.  ~45 launches + Python per step collapse
+        into one ``replay()``."""
+        ext = ops._ext.require()
+        dev = flat.device
+        self.g_idx = torch.zeros(n_steps, self.B, dtype=torch.long, device=dev)
+        self.g_labels = y.reshape(-1).long().contiguous()
+        self.g_loss = torch.zeros((), device=dev)
+        self.g_steps = n_steps
+
+        def wait(rng):
+            if rng is None:
+                ext.wait_flags_dev(ready.flags_ptr, n_chunks, ready.epoch_ptr)
+            else:
+                ext.wait_flags_dev(ready.flags_ptr + 4 * rng[0], rng[1] - rng[0] + 1, ready.epoch_ptr)
+
+        def body():
+            for l in range(self.L):
+                if not self.exact[l]:
+                    wait(self.chunk_range(l, ready.chunk_elems))
+            self.refresh_edge(flat)
+            loss = None
+            for s_i in range(n_steps):
+                idx = self.g_idx[s_i]
+                loss = self.forward(flat, x.index_select(0, idx), self.g_labels.index_select(0, idx),
+                                    ready if s_i == 0 else None)
+                if s_i == 0:
+                    wait(None)
+                    self.refresh_exact(flat, from_broadcast=True)
+                self.backward(flat, lr)
+            self.g_loss.copy_(loss)
+
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    def run_round_graph(self, perm: Optional[torch.Tensor], n: int) -> torch.Tensor:
+        """Replay the captured round on the sample order ``perm`` (int32 ``[epochs, n]`` or None)."""
+        need = self.g_steps * self.B
+        if perm is None:
+            order = torch.arange(need, device=self.g_idx.device) % n
+        else:
+            flat_perm = perm.reshape(-1)
+            if flat_perm.numel() < need:  # several epochs of full batches: drop each epoch's tail like fit()
+                per = (n // self.B) * self.B
+                flat_perm = perm[:, :per].reshape(-1)
+            order = flat_perm[:need]
+        self.g_idx.copy_(order.view(self.g_steps, self.B))
+        self.graph.replay()
+        return self.g_loss

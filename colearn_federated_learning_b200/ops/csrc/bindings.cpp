@@ -280,6 +280,7 @@ void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std:
 void set_flag(int64_t flag, int64_t value) { check(launch_set_flag(ptr_of<uint32_t>(flag), (uint32_t)value, cur_stream()), "set_flag"); }
 void wait_flag(int64_t flag, int64_t value) { check(launch_wait_flag(ptr_of<const uint32_t>(flag), (uint32_t)value, cur_stream()), "wait_flag"); }
 void wait_flags(int64_t flags, int64_t count, int64_t value) { check(launch_wait_flags(ptr_of<const uint32_t>(flags), (int)count, (uint32_t)value, cur_stream()), "wait_flags"); }
+void wait_flags_dev(int64_t flags, int64_t count, int64_t value_ptr) { check(launch_wait_flags_dev(ptr_of<const uint32_t>(flags), (int)count, ptr_of<const uint32_t>(value_ptr), cur_stream()), "wait_flags_dev"); }
 void signal_peers(std::vector<int64_t> flags, int64_t value) {
   PeerFlags f;
   std::memset(&f, 0, sizeof(f));
@@ -336,7 +337,8 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                   c10::optional<torch::Tensor> out_f32, c10::optional<torch::Tensor> out_bf16_t,
                   c10::optional<torch::Tensor> sgd_master, double sgd_lr, c10::optional<torch::Tensor> sgd_shadow,
                   c10::optional<torch::Tensor> sgd_shadow_t, c10::optional<torch::Tensor> colsum,
-                  int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset, int64_t tile_n) {
+                  int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset, int64_t tile_n,
+                  int64_t ready_epoch_ptr) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "A,B must be CUDA bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous() && A.size(1) == B.size(1), "A[M,K], B[N,K]");
   c10::cuda::CUDAGuard guard(A.device());
@@ -362,6 +364,7 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.colsum = (float*)chk(colsum, at::kFloat, 1, N, "colsum");
   ep.ready_flags = ptr_of<const uint32_t>(ready_flags);
   ep.ready_epoch = (uint32_t)ready_epoch;
+  ep.ready_epoch_ptr = ptr_of<const uint32_t>(ready_epoch_ptr);
   ep.ready_chunk_elems = ready_chunk_elems > 0 ? ready_chunk_elems : 1;
   ep.ready_elem_offset = ready_elem_offset;
   ep.tile_n = (int)tile_n;
@@ -401,6 +404,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_flag", &set_flag);
   m.def("wait_flag", &wait_flag);
   m.def("wait_flags", &wait_flags);
+  m.def("wait_flags_dev", &wait_flags_dev);
   m.def("signal_peers", &signal_peers);
   m.def("p2p_copy", &p2p_copy);
   m.def("ipc_alloc", &ipc_alloc);

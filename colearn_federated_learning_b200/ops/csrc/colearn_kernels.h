@@ -161,6 +161,8 @@ cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream
 cudaError_t launch_set_flag(uint32_t* flag, uint32_t value, cudaStream_t s);
 cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t s);
 cudaError_t launch_wait_flags(const uint32_t* flags, int count, uint32_t value, cudaStream_t s);
+// same, but the value to wait for is read from device memory at kernel start (CUDA-graph friendly)
+cudaError_t launch_wait_flags_dev(const uint32_t* flags, int count, const uint32_t* value_ptr, cudaStream_t s);
 // raise flag_ptrs[k][0] = value on every rank k < world (release, system scope)
 struct PeerFlags { uint32_t* ptr[16]; };
 cudaError_t launch_signal_peers(const PeerFlags& flags, int world, uint32_t value, cudaStream_t s);
@@ -189,6 +191,7 @@ struct GemmEpilogue {
   // every chunk overlapping those rows.
   const uint32_t* ready_flags;
   uint32_t ready_epoch;
+  const uint32_t* ready_epoch_ptr;  // if set, the epoch is read from device memory (CUDA-graph replays)
   int64_t ready_chunk_elems;
   int64_t ready_elem_offset;
   int tile_n;               // 0 = auto, 128 or 256 = force the N tile width

@@ -315,6 +315,12 @@ __global__ void wait_flags_kernel(const uint32_t* flags, int count, uint32_t val
     while (ld_acquire_sys(flags + i) < value) __nanosleep(50);
 }
 
+__global__ void wait_flags_dev_kernel(const uint32_t* flags, int count, const uint32_t* value_ptr) {
+  const uint32_t value = ld_acquire_sys(value_ptr);
+  for (int i = threadIdx.x; i < count; i += blockDim.x)
+    while (ld_acquire_sys(flags + i) < value) __nanosleep(50);
+}
+
 __global__ void __launch_bounds__(512)
 p2p_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, uint32_t* flag,
                 uint32_t flag_value, uint32_t* counter) {
@@ -372,6 +378,10 @@ cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t 
 }
 cudaError_t launch_wait_flags(const uint32_t* flags, int count, uint32_t value, cudaStream_t s) {
   wait_flags_kernel<<<1, 128, 0, s>>>(flags, count, value);
+  return cudaGetLastError();
+}
+cudaError_t launch_wait_flags_dev(const uint32_t* flags, int count, const uint32_t* value_ptr, cudaStream_t s) {
+  wait_flags_dev_kernel<<<1, 128, 0, s>>>(flags, count, value_ptr);
   return cudaGetLastError();
 }
 cudaError_t launch_p2p_copy(float* dst, const float* src, int64_t n, uint32_t* flag, uint32_t flag_value,

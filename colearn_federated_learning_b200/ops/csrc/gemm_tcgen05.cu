@@ -184,17 +184,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
         if (ep.ready_flags != nullptr) {
+          const uint32_t want = ep.ready_epoch_ptr ? ld_acquire_sys(ep.ready_epoch_ptr) : ep.ready_epoch;
           // wait for the peer-written weight rows [n0, n0+BN) of this round, then make them
           // visible to the async proxy before TMA touches them
           const int64_t c_lo = (ep.ready_elem_offset + (int64_t)n0 * K) / ep.ready_chunk_elems;
           const int64_t c_hi = (ep.ready_elem_offset + (int64_t)(n0 + BN) * K - 1) / ep.ready_chunk_elems;
           for (int64_t c = c_lo; c <= c_hi; ++c)
-            while (ld_acquire_sys(ep.ready_flags + c) < ep.ready_epoch) __nanosleep(64);
+            while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
           if (ep.bias != nullptr) {  // the layer's fp32 bias directly follows its weight in the flat arena
             const int64_t b_lo = (ep.ready_elem_offset + (int64_t)N * K + n0) / ep.ready_chunk_elems;
             const int64_t b_hi = (ep.ready_elem_offset + (int64_t)N * K + n0 + BN - 1) / ep.ready_chunk_elems;
             for (int64_t c = b_lo; c <= b_hi; ++c)
-              while (ld_acquire_sys(ep.ready_flags + c) < ep.ready_epoch) __nanosleep(64);
+              while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");
         }

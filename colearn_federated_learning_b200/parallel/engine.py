@@ -112,6 +112,7 @@ class FederatedEngine:
         # failure detection: a selected worker that has not delivered within this many ms of the coordinator
         # starting its reduce is dropped from that round (its weight is renormalised away); 0 = wait forever
         self.round_deadline_ms = float(round_deadline_ms)
+        self.use_graphs = os.environ.get("COLEARN_CUDA_GRAPHS", "1") != "0"
         self.use_nvls = os.environ.get("COLEARN_NVLS", "1") != "0"   # multimem.ld_reduce / multimem.st in the two-shot kernel
         self.epoch = 0          # monotonically increasing flag epoch (never reset)
         self.rounds_done = 0
@@ -145,6 +146,7 @@ class FederatedEngine:
         self.ext = ops._ext.require()
         self.grid_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.decision = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         flat = flatten_params(self.model).to(self.device)
         if self.algo == "star":
             self.theta = torch.zeros(P4, device=self.device)
@@ -345,11 +347,27 @@ class FederatedEngine:
             last, path = local_fit(flat, self.model, self.x, self.y, FitConfig(**{**self.cfg.to_dict()}), round_idx)
             self._last_path = path
             return last
+        from ..fl.layerwise import ReadySpec
         from ..fl.trainer import make_perm
-        perm = make_perm(self.x.shape[0], self.cfg, self.device, round_idx)
+        n = self.x.shape[0]
+        perm = make_perm(n, self.cfg, self.device, round_idx)
         cf_ptr = self.arena.ptr("chunk_flags")
         fused = epoch > 1 and self.bf16_shadow
-        ready = (cf_ptr, epoch - 1, self.chunk_elems) if fused else None
+        xs = self.x.view(n, -1)
+        if fused and self.use_graphs:
+            # launch-bound inner loop -> ONE CUDA-graph replay per round (flag epoch + sample order are device-side)
+            if getattr(lw, "graph", None) is None:
+                steps = (n // self.cfg.batch_size) * self.cfg.epochs
+                if self.cfg.max_nr_batches and self.cfg.max_nr_batches > 0:
+                    steps = min(steps, self.cfg.max_nr_batches)
+                self.ext.set_flag(self.epoch_dev.data_ptr(), epoch - 1)
+                lw.build_round_graph(flat, xs, self.y, self.cfg.lr, steps,
+                                     ReadySpec(cf_ptr, self.chunk_elems, 0, self.epoch_dev.data_ptr()), self.n_chunks)
+            self.ext.set_flag(self.epoch_dev.data_ptr(), epoch - 1)
+            last = lw.run_round_graph(perm, n)
+            self._last_path = "layerwise+fused_bcast+cuda_graph"
+            return last
+        ready = ReadySpec(cf_ptr, self.chunk_elems, epoch - 1) if fused else None
 
         def wait_chunks(rng):
             if epoch <= 1:
@@ -361,7 +379,7 @@ class FederatedEngine:
 
         if not fused:
             wait_chunks(None)
-        last = lw.fit(flat, self.x.view(self.x.shape[0], -1), self.y, self.cfg, perm, ready, wait_chunks)
+        last = lw.fit(flat, xs, self.y, self.cfg, perm, ready, wait_chunks)
         self._last_path = "layerwise+fused_bcast" if fused else "layerwise"
         return last
 

@@ -225,4 +225,4 @@ def test_fused_collectives_multi_rank(tmp_path, case):
         assert res["same"] and res["shadow_ok"] and res["moved"] and res["finite"], res
     else:
         assert res["same"] and res["shadow_ok"] and res["finite"], res
-        assert res["path"] == "layerwise+fused_bcast" and res["loss_last"] < res["loss_first"], res
+        assert res["path"].startswith("layerwise+fused_bcast") and res["loss_last"] < res["loss_first"], res
