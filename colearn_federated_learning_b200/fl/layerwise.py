@@ -91,6 +91,8 @@ class LayerwiseMLPTrainer:
         self.dzT = [torch.zeros(self.kp[l + 1], B, device=dev, dtype=bf) for l in range(self.L)]
         self.logits = torch.zeros(B, self.kp[self.L], device=dev)
         self.db = [torch.zeros(self.kp[l + 1], device=dev) for l in range(self.L)]
+        # bias-gradient partials written by the dgrad epilogue: one row per 32 batch rows (no atomics)
+        self.dbp = [torch.zeros(B // 32, self.kp[l + 1], device=dev) for l in range(self.L)]
         self.dw_edge = {l: torch.zeros(self.kp[l + 1], self.kp[l], device=dev) for l in range(self.L) if not self.exact[l]}
         self.launches = 0
 
@@ -172,12 +174,13 @@ class LayerwiseMLPTrainer:
         L = self.L
         for l in range(L - 1, -1, -1):
             if l > 0:
-                self.db[l - 1].zero_()
                 ops.gemm_bf16(self.dz[l], self.WsT[l], relu_mask=self.a[l], out_bf16=self.dz[l - 1],
-                              out_bf16_t=self.dzT[l - 1], colsum=self.db[l - 1])
+                              out_bf16_t=self.dzT[l - 1], colsum=self.dbp[l - 1])
             if self.exact[l]:
-                ops.gemm_bf16(self.dzT[l], self.aT[l], sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l],
-                              sgd_shadow_t=self.WsT[l])
+                # fused SGD on the fp32 master + bf16 shadow; W^T is rebuilt by the coalesced transpose kernel
+                # (2-byte transposed stores from the epilogue cost more than a separate 64 MB pass)
+                ops.gemm_bf16(self.dzT[l], self.aT[l], sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l])
+                ops.transpose_bf16(self.Ws[l], self.WsT[l])
             else:
                 ops.gemm_bf16(self.dzT[l], self.aT[l], out_f32=self.dw_edge[l])
                 w = self._w(flat, l)
@@ -185,7 +188,10 @@ class LayerwiseMLPTrainer:
                 self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
                 ops.transpose_bf16(self.Ws[l], self.WsT[l])
             b = self._b(flat, l)
-            b.sub_(self.db[l][: b.shape[0]], alpha=lr)
+            if l == L - 1:
+                b.sub_(self.db[l][: b.shape[0]], alpha=lr)          # head: gradient came from the loss kernel
+            else:
+                ops.bias_sgd_from_partials(b, self.dbp[l], lr)       # hidden: reduce the epilogue partials + SGD
             if not self.exact[l]:
                 self.bias_p[l][: b.shape[0]].copy_(b)
         self.launches += 2 * L + 4

@@ -208,6 +208,22 @@ torch::Tensor ring_matmul(torch::Tensor a, torch::Tensor b) {
                            reinterpret_cast<long long*>(out.data_ptr<int64_t>()), (int)a.size(0), (int)a.size(1), (int)b.size(1), cur_stream()), "ring_matmul");
   return out;
 }
+torch::Tensor bias_sgd_from_partials(c10::optional<torch::Tensor> bias, torch::Tensor partials, double lr) {
+  CHECK_CUDA_F32(partials);
+  TORCH_CHECK(partials.dim() == 2, "partials [rows, n]");
+  c10::cuda::CUDAGuard guard(partials.device());
+  const int rows = (int)partials.size(0), n = (int)partials.size(1);
+  auto grad = torch::empty({n}, partials.options());
+  float* b = nullptr;
+  int nb = n;
+  if (bias.has_value()) {
+    TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == at::kFloat && bias->is_contiguous() && bias->numel() <= n, "bias");
+    b = bias->data_ptr<float>();
+    nb = (int)bias->numel();
+  }
+  check(launch_bias_sgd_from_partials(b, partials.data_ptr<float>(), rows, nb, partials.stride(0), (float)lr, grad.data_ptr<float>(), cur_stream()), "bias_sgd_from_partials");
+  return grad;
+}
 void l2_flush(torch::Tensor buf) {
   CHECK_CUDA_F32(buf);
   c10::cuda::CUDAGuard guard(buf.device());
@@ -361,7 +377,7 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.sgd_lr = (float)sgd_lr;
   ep.sgd_shadow = chk(sgd_shadow, at::kBFloat16, M, N, "sgd_shadow");
   ep.sgd_shadow_t = chk(sgd_shadow_t, at::kBFloat16, N, M, "sgd_shadow_t");
-  ep.colsum = (float*)chk(colsum, at::kFloat, 1, N, "colsum");
+  ep.colsum = (float*)chk(colsum, at::kFloat, M / 32, N, "colsum (partials [M/32, N])");
   ep.ready_flags = ptr_of<const uint32_t>(ready_flags);
   ep.ready_epoch = (uint32_t)ready_epoch;
   ep.ready_epoch_ptr = ptr_of<const uint32_t>(ready_epoch_ptr);
@@ -395,6 +411,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fp32_to_bf16", &fp32_to_bf16);
   m.def("fp32_to_bf16_into", &fp32_to_bf16_into);
   m.def("l2_flush", &l2_flush);
+  m.def("bias_sgd_from_partials", &bias_sgd_from_partials);
   m.def("fix_precision", &fix_precision);
   m.def("float_precision", &float_precision);
   m.def("ring_matmul", &ring_matmul);

@@ -87,6 +87,9 @@ cudaError_t launch_minmax_scale(const float* x, float* out, int rows, int cols, 
 cudaError_t launch_feistel_permutation(int* out, int n, int rows, uint64_t seed, cudaStream_t s);
 cudaError_t launch_fp32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t s);
 cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s);
+// bias[n] -= lr * sum_r partials[r, n]   (also writes the summed gradient to grad_out if non-null)
+cudaError_t launch_bias_sgd_from_partials(float* bias, const float* partials, int rows, int n, int64_t row_stride,
+                                          float lr, float* grad_out, cudaStream_t s);
 // SMPC ring ops (int64, arithmetic mod 2^64)
 cudaError_t launch_fix_precision(const float* x, long long* out, int64_t n, double base, cudaStream_t s);
 cudaError_t launch_float_precision(const long long* x, float* out, int64_t n, double inv_base, cudaStream_t s);
@@ -184,7 +187,8 @@ struct GemmEpilogue {
   float sgd_lr;
   void* sgd_shadow;         // bf16 [M,N]
   void* sgd_shadow_t;       // bf16 [N,M]
-  float* colsum;            // [N] += column sums of acc (bias gradient), atomicAdd; or nullptr
+  float* colsum;            // [M/32, N] per-32-row-block column sums of the epilogue output (bias gradient
+                            // partials, reduced by launch_bias_sgd_from_partials); or nullptr
   // fused broadcast consumption: B is a view at element offset ready_elem_offset of a flat arena
   // whose chunk c (ready_chunk_elems elements each) is published by a peer GPU raising
   // ready_flags[c] >= ready_epoch.  Before loading B rows [n0, n0+BN) the TMA producer waits for

@@ -340,6 +340,16 @@ __global__ void ring_matmul_kernel(const unsigned long long* __restrict__ A, con
   if (row < M && col < N) C[(size_t)row * N + col] = acc;
 }
 
+__global__ void bias_sgd_from_partials_kernel(float* __restrict__ bias, const float* __restrict__ partials, int rows, int n,
+                                              int64_t row_stride, float lr, float* __restrict__ grad_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float g = 0.f;
+  for (int r = 0; r < rows; ++r) g += partials[(size_t)r * row_stride + c];
+  if (grad_out) grad_out[c] = g;
+  if (bias) bias[c] = fmaf(-lr, g, bias[c]);
+}
+
 __global__ void l2_flush_kernel(float* __restrict__ buf, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = (float)i;
@@ -438,6 +448,11 @@ cudaError_t launch_ring_matmul(const long long* A, const long long* B, long long
   dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
   ring_matmul_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const unsigned long long*>(A), reinterpret_cast<const unsigned long long*>(B),
                                             reinterpret_cast<unsigned long long*>(C), M, K, N);
+  return cudaGetLastError();
+}
+cudaError_t launch_bias_sgd_from_partials(float* bias, const float* partials, int rows, int n, int64_t row_stride, float lr,
+                                          float* grad_out, cudaStream_t s) {
+  bias_sgd_from_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(bias, partials, rows, n, row_stride, lr, grad_out);
   return cudaGetLastError();
 }
 cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s) {

@@ -16,7 +16,7 @@
 // Structure (persistent, 1 CTA / SM, 192 threads):
 //   warp 0   : TMA producer  (1 elected lane)     smem ring of kStages x {A 128x64, B 128x64} bf16, SW128
 //   warp 1   : TMEM alloc + MMA issuer (1 lane)   tcgen05.mma.cta_group::1.kind::f16, UMMA 128x128x16
-//   warps 2-5: epilogue                           tcgen05.ld 32x32b.x32 -> regs -> fused epilogue -> global
+//   warps 2-9: epilogue (2 per TMEM lane quarter)  tcgen05.ld 32x32b.x32 -> regs -> fused epilogue -> global
 //   TMEM     : 2 accumulator stages x 128 columns (epilogue of tile i overlaps mainloop of tile i+1)
 #include "colearn_kernels.h"
 
@@ -33,7 +33,8 @@ namespace {
 constexpr int BM = 128, BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int kAccStages = 2;
-constexpr int kThreads = 192;
+constexpr int kEpilogueWarps = 8;                 // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kThreads = 64 + 32 * kEpilogueWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kMaxStages = 6;
 // Tile config.  BN = 256 halves the B-operand smem traffic per FLOP (128x128x16 UMMAs sit exactly at the
 // 128 B/clk smem limit: 8 KB of operands per 64-cycle instruction; 128x256x16 needs 12 KB per 128 cycles).
@@ -167,7 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], kEpilogueWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -240,6 +241,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;          // 0: columns [0, BN/2), 1: [BN/2, BN)
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
@@ -249,7 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
         tmem_ld_wait();
@@ -281,13 +283,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         if (ep.colsum != nullptr) {
+          // bias gradient: per-(32-row block) partial column sums, plain coalesced stores (no atomics);
+          // the consumer (bias_sgd_from_partials) adds the M/32 partial rows
+          float mine = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float s = f[j];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == (j & 31)) atomicAdd(ep.colsum + col + j, s);
+            if (lane == j) mine = s;
           }
+          ep.colsum[(size_t)((m0 >> 5) + q) * N + col + lane] = mine;
         }
         if (ep.sgd_master != nullptr) {
           float4* mp = reinterpret_cast<float4*>(ep.sgd_master + (size_t)row * N + col);

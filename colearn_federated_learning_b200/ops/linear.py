@@ -31,8 +31,8 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
             acc = torch.relu(acc)
         if relu_mask is not None:
             acc = acc * (relu_mask.float() > 0)
-        if colsum is not None:
-            colsum += acc.sum(0)
+        if colsum is not None:   # [M/32, N] per-32-row-block partial column sums
+            colsum.copy_(acc.view(acc.shape[0] // 32, 32, acc.shape[1]).sum(1))
         if sgd_master is not None:
             sgd_master.sub_(sgd_lr * acc)
             if sgd_shadow is not None:
@@ -73,3 +73,14 @@ def transpose_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
             return out
         return res
     return _ext.require().transpose_bf16(x.contiguous(), out)
+
+
+def bias_sgd_from_partials(bias: Optional[torch.Tensor], partials: torch.Tensor, lr: float) -> torch.Tensor:
+    """``bias[:] -= lr * partials.sum(0)[:len(bias)]`` (partials = the GEMM epilogue's bias-gradient partial
+    sums); returns the summed gradient."""
+    if not partials.is_cuda:
+        g = partials.sum(0)
+        if bias is not None:
+            bias.sub_(g[: bias.numel()], alpha=lr)
+        return g
+    return _ext.require().bias_sgd_from_partials(bias, partials.contiguous(), float(lr))

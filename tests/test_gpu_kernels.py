@@ -174,10 +174,15 @@ def test_gemm_tcgen05_epilogues():
     # relu mask (dgrad) + column sums (bias grad)
     mask = (torch.randn(m, n, device=dev)).to(torch.bfloat16)
     of = torch.empty(m, n, device=dev)
-    cs = torch.zeros(n, device=dev)
+    cs = torch.zeros(m // 32, n, device=dev)
     ops.gemm_bf16(a, b, relu_mask=mask, out_f32=of, colsum=cs)
     assert torch.allclose(of, ref * (mask.float() > 0), atol=1e-2, rtol=1e-2)
-    assert torch.allclose(cs, (ref * (mask.float() > 0)).sum(0), atol=5e-2, rtol=1e-2)   # bias-grad = post-mask column sums
+    want_cs = (ref * (mask.float() > 0)).view(m // 32, 32, n).sum(1)                      # per-32-row-block partials
+    assert torch.allclose(cs, want_cs, atol=5e-2, rtol=1e-2)
+    bias_t = torch.randn(n - 3, device=dev)
+    before = bias_t.clone()
+    g = ops.bias_sgd_from_partials(bias_t, cs, 0.1)
+    assert torch.allclose(g, want_cs.sum(0), atol=5e-2, rtol=1e-2) and torch.allclose(bias_t, before - 0.1 * g[: n - 3], atol=1e-5)
     # fused SGD on the fp32 master + shadow refresh
     master = torch.randn(m, n, device=dev)
     want_master = master - 0.1 * ref
