@@ -221,7 +221,7 @@ torch::Tensor bias_sgd_from_partials(c10::optional<torch::Tensor> bias, torch::T
     b = bias->data_ptr<float>();
     nb = (int)bias->numel();
   }
-  check(launch_bias_sgd_from_partials(b, partials.data_ptr<float>(), rows, nb, partials.stride(0), (float)lr, grad.data_ptr<float>(), cur_stream()), "bias_sgd_from_partials");
+  check(launch_bias_sgd_from_partials(b, partials.data_ptr<float>(), rows, n, partials.stride(0), (float)lr, grad.data_ptr<float>(), nb, cur_stream()), "bias_sgd_from_partials");
   return grad;
 }
 void l2_flush(torch::Tensor buf) {

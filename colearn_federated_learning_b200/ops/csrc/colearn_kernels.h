@@ -89,7 +89,7 @@ cudaError_t launch_fp32_to_bf16(const float* in, void* out, int64_t n, cudaStrea
 cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s);
 // bias[n] -= lr * sum_r partials[r, n]   (also writes the summed gradient to grad_out if non-null)
 cudaError_t launch_bias_sgd_from_partials(float* bias, const float* partials, int rows, int n, int64_t row_stride,
-                                          float lr, float* grad_out, cudaStream_t s);
+                                          float lr, float* grad_out, int n_bias, cudaStream_t s);
 // SMPC ring ops (int64, arithmetic mod 2^64)
 cudaError_t launch_fix_precision(const float* x, long long* out, int64_t n, double base, cudaStream_t s);
 cudaError_t launch_float_precision(const long long* x, float* out, int64_t n, double inv_base, cudaStream_t s);

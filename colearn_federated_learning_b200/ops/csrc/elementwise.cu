@@ -341,13 +341,13 @@ __global__ void ring_matmul_kernel(const unsigned long long* __restrict__ A, con
 }
 
 __global__ void bias_sgd_from_partials_kernel(float* __restrict__ bias, const float* __restrict__ partials, int rows, int n,
-                                              int64_t row_stride, float lr, float* __restrict__ grad_out) {
+                                              int64_t row_stride, float lr, float* __restrict__ grad_out, int n_bias) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   float g = 0.f;
   for (int r = 0; r < rows; ++r) g += partials[(size_t)r * row_stride + c];
   if (grad_out) grad_out[c] = g;
-  if (bias) bias[c] = fmaf(-lr, g, bias[c]);
+  if (bias && c < n_bias) bias[c] = fmaf(-lr, g, bias[c]);
 }
 
 __global__ void l2_flush_kernel(float* __restrict__ buf, int64_t n) {
@@ -451,8 +451,8 @@ cudaError_t launch_ring_matmul(const long long* A, const long long* B, long long
   return cudaGetLastError();
 }
 cudaError_t launch_bias_sgd_from_partials(float* bias, const float* partials, int rows, int n, int64_t row_stride, float lr,
-                                          float* grad_out, cudaStream_t s) {
-  bias_sgd_from_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(bias, partials, rows, n, row_stride, lr, grad_out);
+                                          float* grad_out, int n_bias, cudaStream_t s) {
+  bias_sgd_from_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(bias, partials, rows, n, row_stride, lr, grad_out, n_bias);
   return cudaGetLastError();
 }
 cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s) {
