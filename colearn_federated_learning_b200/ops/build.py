@@ -102,6 +102,11 @@ def build_all(force: bool = False, verbose: bool = True) -> str:
         _run(link, "link")
         if verbose:
             print(f"[colearn build] linked {out}", file=sys.stderr)
+    # drop stale cached objects (every source edit leaves one behind)
+    keep = {os.path.basename(o) for o in objs}
+    for name in os.listdir(OBJ):
+        if name.endswith(".o") and name not in keep:
+            os.remove(os.path.join(OBJ, name))
     return out
 
 
