@@ -19,7 +19,6 @@ from __future__ import annotations
 import asyncio
 import logging
 import os
-import sys
 import time
 from collections import OrderedDict
 from typing import Any, Dict, List, Optional

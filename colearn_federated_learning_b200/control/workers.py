@@ -30,7 +30,7 @@ import torch
 from ..data import dataset_tensors
 from ..fl.trainer import FitConfig, local_fit
 from ..fl.evaluate import predict as predict_fn
-from ..models import build_model, flatten_params, num_params
+from ..models import build_model, num_params
 
 log = logging.getLogger(__name__)
 

@@ -11,7 +11,7 @@ The module-level API below works on ``nn.Module`` dicts for CLI/CPU use; the dat
 """
 from __future__ import annotations
 
-from typing import Dict, Mapping, Optional, Sequence
+from typing import Mapping, Optional, Sequence
 
 import torch
 import torch.nn as nn

@@ -18,7 +18,7 @@ The 10-wide input and 2-wide head are zero-padded to tile multiples (128).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 

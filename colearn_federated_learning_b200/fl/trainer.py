@@ -14,7 +14,6 @@ Three execution paths, chosen by :func:`local_fit`:
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass, asdict
 from typing import Any, Dict, Optional, Tuple
 
@@ -23,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..models import MLPNet, build_model, flatten_params, unflatten_params, DEFAULT_LOSS
+from ..models import MLPNet, flatten_params, unflatten_params, DEFAULT_LOSS
 from ..ops import reference
 
 

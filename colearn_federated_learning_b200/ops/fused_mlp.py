@@ -10,7 +10,7 @@ layer-wise trainer (``fl/layerwise.py``).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import Optional, Sequence, Tuple, Union
 
 import torch
 

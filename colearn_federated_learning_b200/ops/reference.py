@@ -12,7 +12,7 @@ backward; SGD step; if ++it >= max_nr_batches >= 0: stop`` and return the last l
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 

@@ -16,7 +16,6 @@ import threading
 import time
 from typing import Any, Dict, List, Optional
 
-import torch
 import torch.distributed as dist
 
 from ..control.arguments import Arguments, ROUND_MODE_BATCHES
@@ -24,7 +23,7 @@ from ..control.bus import BusClient, InProcessBroker
 from ..control.event_parser import EventParser, format_event
 from ..control.selection import SelectionPolicy, LOWER_BOUND, UPPER_BOUND
 from ..control.window import TemporalWindow
-from ..data import synthetic_unsw, NetworkTrafficDataset, federate
+from ..data import synthetic_unsw, NetworkTrafficDataset
 from ..settings import DeviceRegistry
 from ..utils.checkpoint import load_or_init, checkpoint_compatible
 from ..models import flatten_params

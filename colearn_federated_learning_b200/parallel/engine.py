@@ -23,7 +23,6 @@ The ``nccl`` comparator lives in ``baseline/`` and shares none of this code.
 from __future__ import annotations
 
 import logging
-import math
 import os
 import time
 from dataclasses import dataclass, field
@@ -36,8 +35,7 @@ import torch.nn as nn
 from .. import ops
 from ..fl.fedavg import normalized_weights
 from ..fl.trainer import FitConfig, local_fit, resolve_loss
-from ..models import MLPNet, build_model, flatten_params, num_params, unflatten_params, state_dict_from_flat
-from ..ops import reference
+from ..models import MLPNet, build_model, flatten_params, num_params, state_dict_from_flat
 from ..utils.checkpoint import save_state_dict
 
 log = logging.getLogger(__name__)

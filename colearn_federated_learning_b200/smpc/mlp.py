@@ -8,7 +8,7 @@ learning rate (``optimizer.fix_precision()``, fc.py:443-444).
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Sequence
 
 import torch
 

@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import argparse
 
-import numpy as np
 import pandas as pd
 
 RENAME = {"srcaddr": "saddr", "dstaddr": "daddr", "srcbytes": "sbytes", "dstbytes": "dbytes", "srcpkts": "spkts",
