@@ -293,6 +293,12 @@ void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std:
   check(launch_twoshot_fedavg(a, (int)n_blocks, cur_stream()), "twoshot_fedavg");
 }
 
+void reduce_push(int64_t slots, int64_t k, int64_t stride, int64_t n, int64_t dst, int64_t losses, int64_t loss_dst,
+                 int64_t flag, int64_t value, int64_t counter, int64_t n_blocks) {
+  check(launch_reduce_push(ptr_of<const float>(slots), (int)k, stride, n, ptr_of<float>(dst), ptr_of<const float>(losses),
+                           ptr_of<float>(loss_dst), ptr_of<uint32_t>(flag), (uint32_t)value, ptr_of<uint32_t>(counter),
+                           (int)n_blocks, cur_stream()), "reduce_push");
+}
 void set_flag(int64_t flag, int64_t value) { check(launch_set_flag(ptr_of<uint32_t>(flag), (uint32_t)value, cur_stream()), "set_flag"); }
 void wait_flag(int64_t flag, int64_t value) { check(launch_wait_flag(ptr_of<const uint32_t>(flag), (uint32_t)value, cur_stream()), "wait_flag"); }
 void wait_flags(int64_t flags, int64_t count, int64_t value) { check(launch_wait_flags(ptr_of<const uint32_t>(flags), (int)count, (uint32_t)value, cur_stream()), "wait_flags"); }
@@ -418,6 +424,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("transpose_bf16", &transpose_bf16);
   m.def("star_round", &star_round);
   m.def("twoshot_fedavg", &twoshot_fedavg);
+  m.def("reduce_push", &reduce_push);
   m.def("set_flag", &set_flag);
   m.def("wait_flag", &wait_flag);
   m.def("wait_flags", &wait_flags);

@@ -160,6 +160,12 @@ struct TwoShotArgs {
 };
 cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s);
 
+// Many virtual clients per GPU: dst[j] = sum_c slots[c*stride + j] pushed to (peer) dst, mean losses to loss_dst,
+// then flag <- value (release) by the last CTA.  counter: zero-initialised device scratch.
+cudaError_t launch_reduce_push(const float* slots, int k, int64_t stride, int64_t n, float* dst, const float* losses,
+                               float* loss_dst, uint32_t* flag, uint32_t value, uint32_t* counter, int n_blocks,
+                               cudaStream_t s);
+
 // Tiny helpers used by the host engine / tests.
 cudaError_t launch_set_flag(uint32_t* flag, uint32_t value, cudaStream_t s);
 cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t s);

@@ -298,6 +298,45 @@ twoshot_fedavg_kernel(TwoShotArgs a) {
   }
 }
 
+// Many clients per GPU: sum the C locally trained (already weight-scaled) client models and push the
+// result into the coordinator's slot on a peer GPU, then raise this rank's arrive flag (last CTA).
+__global__ void __launch_bounds__(256)
+reduce_push_kernel(const float* __restrict__ slots, int k, int64_t stride, int64_t n, float* __restrict__ dst,
+                   const float* __restrict__ losses, float* __restrict__ loss_dst, uint32_t* flag, uint32_t value,
+                   uint32_t* counter) {
+  const int64_t n4 = n >> 2;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += gstride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < k; ++c) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(slots + c * stride) + j);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    st_peer_f4(reinterpret_cast<float4*>(dst) + j, acc);
+  }
+  for (int64_t j = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gstride) {
+    float acc = 0.f;
+    for (int c = 0; c < k; ++c) acc += __ldcg(slots + c * stride + j);
+    dst[j] = acc;
+  }
+  __shared__ bool is_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    *counter = 0u;
+    if (loss_dst != nullptr && losses != nullptr) {  // mean of the clients' {last, mean} losses
+      float l0 = 0.f, l1 = 0.f;
+      for (int c = 0; c < k; ++c) { l0 += __ldcg(losses + 2 * c); l1 += __ldcg(losses + 2 * c + 1); }
+      loss_dst[0] = l0 / k;
+      loss_dst[1] = l1 / k;
+    }
+    __threadfence_system();
+    if (flag != nullptr) st_release_sys(flag, value);
+  }
+}
+
 __global__ void set_flag_kernel(uint32_t* flag, uint32_t value) {
   __threadfence_system();
   st_release_sys(flag, value);
@@ -368,6 +407,13 @@ cudaError_t launch_signal_peers(const PeerFlags& flags, int world, uint32_t valu
   return cudaGetLastError();
 }
 
+cudaError_t launch_reduce_push(const float* slots, int k, int64_t stride, int64_t n, float* dst, const float* losses,
+                               float* loss_dst, uint32_t* flag, uint32_t value, uint32_t* counter, int n_blocks,
+                               cudaStream_t s) {
+  if (n_blocks < 1) n_blocks = 1;
+  reduce_push_kernel<<<n_blocks, 256, 0, s>>>(slots, k, stride, n, dst, losses, loss_dst, flag, value, counter);
+  return cudaGetLastError();
+}
 cudaError_t launch_set_flag(uint32_t* flag, uint32_t value, cudaStream_t s) {
   set_flag_kernel<<<1, 1, 0, s>>>(flag, value);
   return cudaGetLastError();

@@ -120,7 +120,8 @@ def run_box_coordinator(cli, args: Arguments) -> None:
     backend = "auto" if args.backend in ("auto", "nccl") else args.backend
     engine = FederatedEngine(args.model, backend=backend, device=device, batch_size=args.batch_size, lr=args.lr,
                              local_epochs=args.epochs, max_batches=max_batches, loss=args.loss, weighted=args.weighted,
-                             server_lr=args.server_lr, seed=args.seed)
+                             server_lr=args.server_lr, seed=args.seed,
+                             clients_per_rank=getattr(cli, "clients_per_gpu", 1) if backend != "cpu" and device.type == "cuda" else 1)
     if rank == 0:
         import os
         if os.path.exists(cli.checkpoint) and checkpoint_compatible(engine.model, cli.checkpoint):

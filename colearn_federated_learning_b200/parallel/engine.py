@@ -65,7 +65,7 @@ class FederatedEngine:
                  local_epochs: int = 1, max_batches: int = -1, loss: str = "auto", weighted: bool = True,
                  server_lr: float = 1.0, coordinator_rank: int = 0, algo: str = "auto", seed: int = 1,
                  shuffle: bool = True, chunk_elems: int = 0, bf16_shadow: bool = False,
-                 round_deadline_ms: float = 0.0,
+                 round_deadline_ms: float = 0.0, clients_per_rank: int = 1,
                  model_kwargs: Optional[Dict[str, Any]] = None) -> None:
         self.rank = dist.get_rank(group) if _dist_ready() else 0
         self.world = dist.get_world_size(group) if _dist_ready() else 1
@@ -110,6 +110,8 @@ class FederatedEngine:
         # failure detection: a selected worker that has not delivered within this many ms of the coordinator
         # starting its reduce is dropped from that round (its weight is renormalised away); 0 = wait forever
         self.round_deadline_ms = float(round_deadline_ms)
+        # many virtual clients (federated devices) per GPU: one CTA each, summed locally before the NVLink push
+        self.clients_per_rank = max(1, int(clients_per_rank))
         self.use_graphs = os.environ.get("COLEARN_CUDA_GRAPHS", "1") != "0"
         self.use_nvls = os.environ.get("COLEARN_NVLS", "1") != "0"   # multimem.ld_reduce / multimem.st in the two-shot kernel
         self.epoch = 0          # monotonically increasing flag epoch (never reset)
@@ -162,6 +164,11 @@ class FederatedEngine:
                 torch.cuda.synchronize(self.device)
                 dist.barrier(group=self.group)
         self.loss_host = torch.zeros(2 * W, dtype=torch.float32).pin_memory()
+        if self.algo == "star" and self.clients_per_rank > 1:
+            C = self.clients_per_rank
+            self.client_slots = torch.zeros(C, P4, device=self.device)
+            self.client_losses = torch.zeros(C, 2, device=self.device)
+            self.push_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     # ------------------------------------------------------------------------------------------
     def set_local_data(self, x: torch.Tensor, y: torch.Tensor) -> None:
@@ -247,12 +254,29 @@ class FederatedEngine:
         coord_loss = arena.ptr("losses", self.coord, 2 * r)
         coord_arrive = arena.ptr("flags", self.coord, 1 + r)
         tasks = []
+        C = self.clients_per_rank
+        if C > 1:
+            from ..data import shard_bounds
+            cb = [b for b in shard_bounds(n, C)]
+            cperm = [ops.device_permutation(hi - lo, cfg.epochs * rounds, self.seed * 7919 + self.rounds_done + 131 * c + 17 * r, dev)
+                     if (cfg.shuffle and hi > lo) else None for c, (lo, hi) in enumerate(cb)]
         for i in range(rounds):
             w = self._round_weights(masks[i])[r]
             p = perm[i * cfg.epochs:(i + 1) * cfg.epochs] if perm is not None else None
-            tasks.append(ops.ClientTask(x=self.x, y=self.y, theta_in=arena.ptr("inbox"), theta_out=coord_slots, perm=p,
-                                        loss_out=coord_loss, wait_flag=arena.ptr("flags"), wait_value=e0 + i + 1,
-                                        signal_flag=coord_arrive, signal_value=e0 + i + 1, out_scale=w))
+            if C == 1:
+                tasks.append(ops.ClientTask(x=self.x, y=self.y, theta_in=arena.ptr("inbox"), theta_out=coord_slots, perm=p,
+                                            loss_out=coord_loss, wait_flag=arena.ptr("flags"), wait_value=e0 + i + 1,
+                                            signal_flag=coord_arrive, signal_value=e0 + i + 1, out_scale=w))
+            else:
+                # C virtual clients on this GPU (one CTA each); each starts from the broadcast theta, trains on its
+                # contiguous sub-shard and leaves w_rank * (n_c / n_rank) * theta_c in a local slot
+                for c, (lo, hi) in enumerate(cb):
+                    share = ((hi - lo) / max(1, n)) if self.weighted else 1.0 / C
+                    tasks.append(ops.ClientTask(x=self.x[lo:hi], y=self.y[lo:hi], theta_in=arena.ptr("inbox"),
+                                                theta_out=self.client_slots[c],
+                                                perm=(cperm[c][i * cfg.epochs:(i + 1) * cfg.epochs] if cperm[c] is not None else None),
+                                                loss_out=self.client_losses[c],
+                                                wait_flag=arena.ptr("flags"), wait_value=e0 + i + 1, out_scale=w * share))
         descs = ops.build_client_descs(tasks, dev)
         inbox_ptrs = arena.peer_ptrs("inbox")
         bflag_ptrs = arena.peer_ptrs("flags")
@@ -294,9 +318,13 @@ class FederatedEngine:
                 self.x.copy_(hx, non_blocking=True)
                 self.y.copy_(hy.view(-1, 1), non_blocking=True)
             if (masks[i] >> r) & 1:
-                ops.mlp_local_sgd_multi(self.spec.dims, self.spec.out_activation, descs, 1, cfg.batch_size, cfg.lr,
-                                        cfg.epochs, cfg.max_nr_batches, cfg.loss, desc_offset=i)
+                ops.mlp_local_sgd_multi(self.spec.dims, self.spec.out_activation, descs, C, cfg.batch_size, cfg.lr,
+                                        cfg.epochs, cfg.max_nr_batches, cfg.loss, desc_offset=i * C)
                 launches += 1
+                if C > 1:
+                    ext.reduce_push(self.client_slots.data_ptr(), C, P4, P4, coord_slots, self.client_losses.data_ptr(),
+                                    coord_loss, coord_arrive, e0 + i + 1, self.push_counter.data_ptr(), n_blocks)
+                    launches += 1
             if is_coord:
                 last = i == rounds - 1
                 launches += star(True, not last, masks[i], masks[i + 1] if not last else 0, e0 + i + 1, e0 + i + 2)

@@ -66,6 +66,7 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--exit-after", type=int, default=0, help="exit after N completed trainings (0 = run forever)")
     parser.add_argument("--box", action="store_true", help="multi-GPU box mode under torchrun (rank 0 = coordinator)")
     parser.add_argument("--backend", choices=["auto", "fused", "nccl", "cpu"], default="auto")
+    parser.add_argument("--clients-per-gpu", type=int, default=1, help="--box: virtual federated devices hosted by each GPU (one CTA each)")
     return parser
 
 

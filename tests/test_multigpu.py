@@ -46,6 +46,32 @@ def test_engine_star_single_gpu_matches_reference_round():
     assert abs(float(eng.loss_host[0]) - float(rep2.losses[-1, 0, 0])) < 1e-6
 
 
+def test_engine_many_clients_per_gpu():
+    """100 federated devices do not need 100 GPUs: C virtual clients per rank, one CTA each, summed on-GPU."""
+    from colearn_federated_learning_b200.data import shard_bounds, synthetic_unsw
+    from colearn_federated_learning_b200.ops import reference as R
+    from colearn_federated_learning_b200.parallel import FederatedEngine
+    dev = torch.device("cuda", 0)
+    C, n = 13, 650
+    eng = FederatedEngine("ffnn", backend="fused", device=dev, batch_size=1, lr=0.05, seed=2, shuffle=False, weighted=True,
+                          clients_per_rank=C)
+    x, y = synthetic_unsw(n, seed=4)
+    eng.set_local_data(x, y)
+    theta0 = eng.global_flat().cpu().clone()
+    rep = eng.run_rounds(2)
+    ref = theta0.clone()
+    for _ in range(2):
+        acc = torch.zeros_like(ref)
+        for lo, hi in shard_bounds(n, C):
+            loc = ref.clone()
+            R.mlp_local_sgd(loc, eng.spec.dims, x[lo:hi], y[lo:hi], R.make_permutation(hi - lo, 1, 0, shuffle=False), 1, 0.05, 1,
+                            -1, "bce", "sigmoid")
+            acc += loc * ((hi - lo) / n)
+        ref = acc
+    assert torch.allclose(eng.global_flat().cpu(), ref, atol=5e-4, rtol=5e-3), (eng.global_flat().cpu() - ref).abs().max()
+    assert rep.launches == 2 * 3 + 1 and torch.isfinite(rep.losses).all()
+
+
 def test_engine_twoshot_single_gpu_resnet_round():
     from colearn_federated_learning_b200.data import synthetic_images
     from colearn_federated_learning_b200.parallel import FederatedEngine
