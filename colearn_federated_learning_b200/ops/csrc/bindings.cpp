@@ -360,7 +360,7 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                   c10::optional<torch::Tensor> sgd_master, double sgd_lr, c10::optional<torch::Tensor> sgd_shadow,
                   c10::optional<torch::Tensor> sgd_shadow_t, c10::optional<torch::Tensor> colsum,
                   int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset, int64_t tile_n,
-                  int64_t ready_epoch_ptr) {
+                  int64_t ready_epoch_ptr, int64_t cluster) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "A,B must be CUDA bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous() && A.size(1) == B.size(1), "A[M,K], B[N,K]");
   c10::cuda::CUDAGuard guard(A.device());
@@ -390,6 +390,7 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.ready_chunk_elems = ready_chunk_elems > 0 ? ready_chunk_elems : 1;
   ep.ready_elem_offset = ready_elem_offset;
   ep.tile_n = (int)tile_n;
+  ep.cluster = (int)cluster;
   cudaError_t e = launch_gemm_tcgen05(A.data_ptr(), B.data_ptr(), M, N, K, ep, cur_stream());
   TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05: ", cudaGetErrorString(e), " (", gemm_tcgen05_last_error(), ")");
 }

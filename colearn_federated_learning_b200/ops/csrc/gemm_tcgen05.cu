@@ -78,6 +78,26 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
+  // the tile lands at the same CTA-relative smem offset in every CTA of cta_mask and completes tx bytes on the
+  // mbarrier at the same offset in each of them
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -146,11 +166,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN>
+// CL = 2: thread-block cluster of two CTAs working on vertically adjacent tiles (same n-block).  Each CTA fetches
+// its own A tile and HALF of the shared B tile, multicasting that half into both CTAs' shared memory, which cuts
+// the L2->SM operand traffic per CTA from 48 KB to 32 KB per k-block (the 128x256 tile is L2-bandwidth bound).
+template <int BN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     int M, int N, int K, GemmEpilogue ep) {
   using C = Cfg<BN>;
+  const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
   constexpr int kStages = C::kStages, kTmemCols = C::kTmemCols;
   constexpr uint32_t kStageBytesA = C::kStageBytesA, kStageBytesB = C::kStageBytesB, kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -162,18 +186,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = M / BM, n_tiles = N / BN, num_kb = K / BK;
-  const int total_tiles = m_tiles * n_tiles;
+  // work unit = one tile (CL == 1) or a vertical pair of tiles handled by the two CTAs of a cluster (CL == 2)
+  const int m_units = m_tiles / CL;
+  const int total_work = m_units * n_tiles;
+  const int work0 = blockIdx.x / CL, work_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], CL); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], kEpilogueWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // the peer may multicast into my smem / arrive on my barriers from now on
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -182,8 +210,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+      for (int tile = work0; tile < total_work; tile += work_stride) {
+        const int m0 = ((tile % m_units) * CL + (int)crank) * BM, n0 = (tile / m_units) * BN;
         if (ep.ready_flags != nullptr) {
           const uint32_t want = ep.ready_epoch_ptr ? ld_acquire_sys(ep.ready_epoch_ptr) : ep.ready_epoch;
           // wait for the peer-written weight rows [n0, n0+BN) of this round, then make them
@@ -204,7 +232,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
           tma_load_2d(smem_a + stage * kStageBytesA, &tmap_a, kb * BK, m0, &bars->full[stage]);
-          tma_load_2d(smem_b + stage * kStageBytesB, &tmap_b, kb * BK, n0, &bars->full[stage]);
+          if (CL == 2) {
+            // my half of the shared B tile -> both CTAs (tmap_b's box is BN/2 rows in this mode)
+            tma_load_2d_mcast(smem_b + stage * kStageBytesB + crank * (kStageBytesB / 2), &tmap_b, kb * BK,
+                              n0 + (int)crank * (BN / 2), &bars->full[stage], (uint16_t)0x3);
+          } else {
+            tma_load_2d(smem_b + stage * kStageBytesB, &tmap_b, kb * BK, n0, &bars->full[stage]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -216,7 +250,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int tile = work0; tile < total_work; tile += work_stride, ++local) {
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
@@ -232,7 +266,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in (addr>>4) units
             umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&bars->empty[stage]);
+          if (CL == 2) umma_commit_mcast(&bars->empty[stage], (uint16_t)0x3);  // both producers write into this stage
+          else umma_commit(&bars->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bars->tmem_full[as]);
@@ -243,8 +278,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;          // 0: columns [0, BN/2), 1: [BN/2, BN)
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+    for (int tile = work0; tile < total_work; tile += work_stride, ++local) {
+      const int m0 = ((tile % m_units) * CL + (int)crank) * BM, n0 = (tile / m_units) * BN;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&bars->tmem_full[as], aphase);
@@ -345,6 +380,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // nobody may still multicast into / arrive on a CTA that exits
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -405,26 +441,38 @@ bool make_tmap(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* o
   return true;
 }
 
-template <int BN>
+template <int BN, int CL>
 cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
   using C = Cfg<BN>;
   CUtensorMap ta, tb;
-  if (!make_tmap(A, M, K, BM, &ta) || !make_tmap(B, N, K, BN, &tb)) return cudaErrorInvalidValue;
+  if (!make_tmap(A, M, K, BM, &ta) || !make_tmap(B, N, K, BN / CL, &tb)) return cudaErrorInvalidValue;
   static bool configured[64] = {false};
   static int num_sms[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem) failed"; return e; }
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
-  const int tiles = (M / BM) * (N / BN);
-  int grid = tiles < num_sms[dev & 63] ? tiles : num_sms[dev & 63];
-  if (grid < 1) grid = 1;
-  gemm_tcgen05_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
-  return cudaGetLastError();
+  const int work = (M / BM / CL) * (N / BN);
+  int units = num_sms[dev & 63] / CL;          // persistent: one CTA (or CTA pair) per SM (pair)
+  if (work < units) units = work;
+  if (units < 1) units = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * CL);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CL > 1) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CL>, ta, tb, M, N, K, ep);
 }
 
 }  // namespace
@@ -441,9 +489,13 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
   const bool wide = (N % 256 == 0) && ((int64_t)(M / BM) * (N / 256) >= 120) && ep.tile_n != 128;
   if (wide || ep.tile_n == 256) {
     if (N % 256) { g_last_error = "tile_n=256 needs N%256==0"; return cudaErrorInvalidValue; }
-    return launch_t<256>(A, B, M, N, K, ep, s);
+    // cluster of 2 with TMA multicast of the shared B tile when the m-tiles pair up (ep.cluster: 0 auto, 1 off, 2 force)
+    const bool pair = (M % (2 * BM) == 0) && ep.cluster != 1;
+    if (ep.cluster == 2 && !pair) { g_last_error = "cluster=2 needs M%256==0"; return cudaErrorInvalidValue; }
+    if (pair) return launch_t<256, 2>(A, B, M, N, K, ep, s);
+    return launch_t<256, 1>(A, B, M, N, K, ep, s);
   }
-  return launch_t<128>(A, B, M, N, K, ep, s);
+  return launch_t<128, 1>(A, B, M, N, K, ep, s);
 }
 
 }  // namespace colearn

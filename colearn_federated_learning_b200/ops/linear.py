@@ -21,7 +21,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
               sgd_shadow: Optional[torch.Tensor] = None, sgd_shadow_t: Optional[torch.Tensor] = None,
               colsum: Optional[torch.Tensor] = None, ready_flags: int = 0, ready_epoch: int = 0,
               ready_chunk_elems: int = 1, ready_elem_offset: int = 0, tile_n: int = 0,
-              ready_epoch_ptr: int = 0) -> None:
+              ready_epoch_ptr: int = 0, cluster: int = 0) -> None:
     """Launch the tcgen05 GEMM; results land in the provided output tensors."""
     if not a.is_cuda:
         acc = a.float() @ b.float().t()
@@ -49,7 +49,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
         return
     _ext.require().gemm_tcgen05(a, b, bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
                                 float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(ready_flags), int(ready_epoch),
-                                int(ready_chunk_elems), int(ready_elem_offset), int(tile_n), int(ready_epoch_ptr))
+                                int(ready_chunk_elems), int(ready_elem_offset), int(tile_n), int(ready_epoch_ptr), int(cluster))
 
 
 def linear_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,

@@ -98,10 +98,10 @@ def bench_gemm(results, quick):
         ref = lambda: torch.matmul(a, b.t())
         rmed, rbest = time_cuda(ref)
         fl = 2.0 * m * n * k
-        for tile_n in (128, 256):
-            fn = lambda: ops.gemm_bf16(a, b, out_bf16=out, tile_n=tile_n)
+        for tile_n, cluster in ((128, 1), (256, 1), (256, 2)):
+            fn = lambda: ops.gemm_bf16(a, b, out_bf16=out, tile_n=tile_n, cluster=cluster)
             med, best = time_cuda(fn)
-            results.append({"kernel": "gemm_tcgen05", "tile_n": tile_n, "m": m, "n": n, "k": k, "ms": med,
+            results.append({"kernel": "gemm_tcgen05", "tile_n": tile_n, "cluster": cluster, "m": m, "n": n, "k": k, "ms": med,
                             "tflops": fl / med / 1e9, "tflops_best": fl / best / 1e9, "cublas_ms": rmed,
                             "cublas_tflops": fl / rmed / 1e9})
             print(results[-1], flush=True)

@@ -142,15 +142,17 @@ def test_eval_argmax_minmax_perm_convert():
     assert torch.equal(ops.fp32_to_bf16(v), v.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("m,n,k,tile_n", [(128, 128, 64, 0), (256, 384, 512, 0), (1024, 4096, 4096, 0), (128, 256, 128, 256),
-                                          (384, 512, 320, 256), (1024, 4096, 4096, 128)])
-def test_gemm_tcgen05_plain(m, n, k, tile_n):
+@pytest.mark.parametrize("m,n,k,tile_n,cluster", [(128, 128, 64, 0, 0), (256, 384, 512, 0, 0), (1024, 4096, 4096, 0, 0),
+                                                  (128, 256, 128, 256, 1), (384, 512, 320, 256, 1), (1024, 4096, 4096, 128, 0),
+                                                  (256, 256, 64, 256, 2), (512, 768, 448, 256, 2), (2048, 4096, 1024, 256, 2),
+                                                  (1024, 4096, 4096, 256, 1)])
+def test_gemm_tcgen05_plain(m, n, k, tile_n, cluster):
     dev = _dev()
     torch.manual_seed(6)
     a = (torch.randn(m, k, device=dev) * 0.5).to(torch.bfloat16)
     b = (torch.randn(n, k, device=dev) * 0.5).to(torch.bfloat16)
     out = torch.empty(m, n, device=dev, dtype=torch.float32)
-    ops.gemm_bf16(a, b, out_f32=out, tile_n=tile_n)
+    ops.gemm_bf16(a, b, out_f32=out, tile_n=tile_n, cluster=cluster)
     torch.cuda.synchronize()
     ref = a.float() @ b.float().t()
     err = (out - ref).abs().max().item()
