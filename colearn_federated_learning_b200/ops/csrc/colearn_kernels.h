@@ -205,7 +205,7 @@ struct GemmEpilogue {
   int64_t ready_chunk_elems;
   int64_t ready_elem_offset;
   int tile_n;               // 0 = auto, 128 or 256 = force the N tile width
-  int cluster;              // 0 = auto (pairs of CTAs + TMA multicast when M%256==0 and tile 256), 1 = off, 2 = force
+  int cluster;              // 2 = pairs of CTAs + TMA multicast of the shared B tile (needs M%256==0, tile 256); else off
 };
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,

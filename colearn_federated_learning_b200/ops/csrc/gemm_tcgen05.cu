@@ -489,8 +489,10 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
   const bool wide = (N % 256 == 0) && ((int64_t)(M / BM) * (N / 256) >= 120) && ep.tile_n != 128;
   if (wide || ep.tile_n == 256) {
     if (N % 256) { g_last_error = "tile_n=256 needs N%256==0"; return cudaErrorInvalidValue; }
-    // cluster of 2 with TMA multicast of the shared B tile when the m-tiles pair up (ep.cluster: 0 auto, 1 off, 2 force)
-    const bool pair = (M % (2 * BM) == 0) && ep.cluster != 1;
+    // cluster of 2 with TMA multicast of the shared B tile (ep.cluster == 2).  Measured (profiles/README.md §3): it cuts
+    // L2->SM traffic by a third but not the per-SM smem traffic (TMA writes 94 B/clk + UMMA reads 96 B/clk against a
+    // 128 B/clk port), so it is not faster than independent CTAs; it stays opt-in until the cta_group::2 MMA lands.
+    const bool pair = (M % (2 * BM) == 0) && ep.cluster == 2;
     if (ep.cluster == 2 && !pair) { g_last_error = "cluster=2 needs M%256==0"; return cudaErrorInvalidValue; }
     if (pair) return launch_t<256, 2>(A, B, M, N, K, ep, s);
     return launch_t<256, 1>(A, B, M, N, K, ep, s);
