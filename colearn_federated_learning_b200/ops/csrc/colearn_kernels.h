@@ -205,7 +205,8 @@ struct GemmEpilogue {
   int64_t ready_chunk_elems;
   int64_t ready_elem_offset;
   int tile_n;               // 0 = auto, 128 or 256 = force the N tile width
-  int cluster;              // 2 = pairs of CTAs + TMA multicast of the shared B tile (needs M%256==0, tile 256); else off
+  int cluster;              // 3 = cta_group::2 (two SMs per 256x256 tile, UMMA M=256; needs M%256==0, N%256==0);
+                            // 2 = pairs of CTAs + TMA multicast of the shared B tile (M%256==0, tile 256); else off
 };
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,

@@ -136,6 +136,42 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
+
+// ---- cta_group::2 (two SMs on one 256-row tile) ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t mbar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // K-major, 128B-swizzled smem operand descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, ignored for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
 //   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
@@ -165,6 +201,91 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// Fused epilogue for one 32-column chunk of one accumulator row per thread (row = m0 + 32*q + lane).
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const GemmEpilogue& ep, int row, int col, int lane,
+                                               int q, int m0, int M, int N) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (ep.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] += __ldg(ep.bias + col + j);
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (ep.relu_mask != nullptr) {
+    const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.relu_mask) + (size_t)row * N + col);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 mv = __ldg(mp + g);
+      const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+        const uint32_t lo = w[h] & 0xFFFFu, hi = w[h] >> 16;
+        if (!(lo != 0 && !(lo & 0x8000u))) f[g * 8 + h * 2] = 0.f;
+        if (!(hi != 0 && !(hi & 0x8000u))) f[g * 8 + h * 2 + 1] = 0.f;
+      }
+    }
+  }
+  if (ep.colsum != nullptr) {
+    // bias gradient: per-(32-row block) partial column sums, plain coalesced stores (no atomics);
+    // the consumer (bias_sgd_from_partials) adds the M/32 partial rows
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float s = f[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == j) mine = s;
+    }
+    ep.colsum[(size_t)((m0 >> 5) + q) * N + col + lane] = mine;
+  }
+  if (ep.sgd_master != nullptr) {
+    float4* mp = reinterpret_cast<float4*>(ep.sgd_master + (size_t)row * N + col);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float4 w = mp[g];
+      w.x = fmaf(-ep.sgd_lr, f[g * 4 + 0], w.x); w.y = fmaf(-ep.sgd_lr, f[g * 4 + 1], w.y);
+      w.z = fmaf(-ep.sgd_lr, f[g * 4 + 2], w.z); w.w = fmaf(-ep.sgd_lr, f[g * 4 + 3], w.w);
+      mp[g] = w;
+      f[g * 4 + 0] = w.x; f[g * 4 + 1] = w.y; f[g * 4 + 2] = w.z; f[g * 4 + 3] = w.w;  // f now holds the new weights
+    }
+    if (ep.sgd_shadow != nullptr) {
+      uint4* sp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.sgd_shadow) + (size_t)row * N + col);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        sp[g] = make_uint4(pack2(f[g * 8], f[g * 8 + 1]), pack2(f[g * 8 + 2], f[g * 8 + 3]),
+                           pack2(f[g * 8 + 4], f[g * 8 + 5]), pack2(f[g * 8 + 6], f[g * 8 + 7]));
+    }
+    if (ep.sgd_shadow_t != nullptr) {
+      __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(ep.sgd_shadow_t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tp[(size_t)(col + j) * M + row] = __float2bfloat16(f[j]);
+    }
+  } else {
+    if (ep.out_f32 != nullptr) {
+      float4* op = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * N + col);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) op[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+    }
+    if (ep.out_bf16 != nullptr) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + (size_t)row * N + col);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        op[g] = make_uint4(pack2(f[g * 8], f[g * 8 + 1]), pack2(f[g * 8 + 2], f[g * 8 + 3]),
+                           pack2(f[g * 8 + 4], f[g * 8 + 5]), pack2(f[g * 8 + 6], f[g * 8 + 7]));
+    }
+    if (ep.out_bf16_t != nullptr) {
+      __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(ep.out_bf16_t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tp[(size_t)(col + j) * M + row] = __float2bfloat16(f[j]);
+    }
+  }
+      }
 
 // CL = 2: thread-block cluster of two CTAs working on vertically adjacent tiles (same n-block).  Each CTA fetches
 // its own A tile and HALF of the shared B tile, multicasting that half into both CTAs' shared memory, which cuts
@@ -290,87 +411,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
         tmem_ld_wait();
-        const int col = n0 + c0;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (ep.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(ep.bias + col + j);
-        }
-        if (ep.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (ep.relu_mask != nullptr) {
-          const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.relu_mask) + (size_t)row * N + col);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint4 mv = __ldg(mp + g);
-            const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-              const uint32_t lo = w[h] & 0xFFFFu, hi = w[h] >> 16;
-              if (!(lo != 0 && !(lo & 0x8000u))) f[g * 8 + h * 2] = 0.f;
-              if (!(hi != 0 && !(hi & 0x8000u))) f[g * 8 + h * 2 + 1] = 0.f;
-            }
-          }
-        }
-        if (ep.colsum != nullptr) {
-          // bias gradient: per-(32-row block) partial column sums, plain coalesced stores (no atomics);
-          // the consumer (bias_sgd_from_partials) adds the M/32 partial rows
-          float mine = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float s = f[j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == j) mine = s;
-          }
-          ep.colsum[(size_t)((m0 >> 5) + q) * N + col + lane] = mine;
-        }
-        if (ep.sgd_master != nullptr) {
-          float4* mp = reinterpret_cast<float4*>(ep.sgd_master + (size_t)row * N + col);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 w = mp[g];
-            w.x = fmaf(-ep.sgd_lr, f[g * 4 + 0], w.x); w.y = fmaf(-ep.sgd_lr, f[g * 4 + 1], w.y);
-            w.z = fmaf(-ep.sgd_lr, f[g * 4 + 2], w.z); w.w = fmaf(-ep.sgd_lr, f[g * 4 + 3], w.w);
-            mp[g] = w;
-            f[g * 4 + 0] = w.x; f[g * 4 + 1] = w.y; f[g * 4 + 2] = w.z; f[g * 4 + 3] = w.w;  // f now holds the new weights
-          }
-          if (ep.sgd_shadow != nullptr) {
-            uint4* sp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.sgd_shadow) + (size_t)row * N + col);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              sp[g] = make_uint4(pack2(f[g * 8], f[g * 8 + 1]), pack2(f[g * 8 + 2], f[g * 8 + 3]),
-                                 pack2(f[g * 8 + 4], f[g * 8 + 5]), pack2(f[g * 8 + 6], f[g * 8 + 7]));
-          }
-          if (ep.sgd_shadow_t != nullptr) {
-            __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(ep.sgd_shadow_t);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tp[(size_t)(col + j) * M + row] = __float2bfloat16(f[j]);
-          }
-        } else {
-          if (ep.out_f32 != nullptr) {
-            float4* op = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * N + col);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) op[g] = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-          }
-          if (ep.out_bf16 != nullptr) {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + (size_t)row * N + col);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              op[g] = make_uint4(pack2(f[g * 8], f[g * 8 + 1]), pack2(f[g * 8 + 2], f[g * 8 + 3]),
-                                 pack2(f[g * 8 + 4], f[g * 8 + 5]), pack2(f[g * 8 + 6], f[g * 8 + 7]));
-          }
-          if (ep.out_bf16_t != nullptr) {
-            __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(ep.out_bf16_t);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tp[(size_t)(col + j) * M + row] = __float2bfloat16(f[j]);
-          }
-        }
+        epilogue_chunk(v, ep, row, n0 + c0, lane, q, m0, M, N);
       }
       tc_fence_before();
       __syncwarp();
@@ -475,6 +516,196 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CL>, ta, tb, M, N, K, ep);
 }
 
+
+// =====================================================================================================================
+// cta_group::2 variant: a cluster of two CTAs (= two SMs) computes one 256 x 256 tile with UMMA M = 256.
+//   * each CTA stages ITS 128 rows of A and ITS 128 of the 256 B rows (32 KB / stage instead of 48 KB): the tensor
+//     cores of both SMs read both halves, so per-SM shared-memory traffic drops from ~190 B/clk (TMA fill 94 + UMMA
+//     reads 96, over the 128 B/clk port) to ~126 B/clk — the bound the single-CTA kernel sits on (profiles/README §3);
+//   * only the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2; both CTAs' TMA loads credit the LEADER's
+//     full barrier (.cta_group::2 TMA + mapa'd barrier address), tcgen05.commit multicasts the "stage free" and
+//     "accumulator ready" arrivals to both CTAs, and the peer's epilogue warps release the accumulator stage with
+//     remote mbarrier arrives;
+//   * every CTA's 8 epilogue warps drain its own 128 TMEM lanes (its 128 output rows).
+// =====================================================================================================================
+struct Cfg2SM {
+  static constexpr int BN = 256;
+  static constexpr int kStages = 6;
+  static constexpr int kTmemCols = kAccStages * BN;   // 512
+  static constexpr uint32_t kStageBytesA = BM * BK * 2;         // 16 KB: my 128 rows of A
+  static constexpr uint32_t kStageBytesB = (BN / 2) * BK * 2;   // 16 KB: my 128 rows of B
+  static constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        int M, int N, int K, GemmEpilogue ep) {
+  using C = Cfg2SM;
+  constexpr int BN = C::BN, kStages = C::kStages, kTmemCols = C::kTmemCols;
+  constexpr uint32_t kStageBytesA = C::kStageBytesA, kStageBytesB = C::kStageBytesB, kStageBytes = C::kStageBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kStageBytesA;
+  SharedBarriers* bars = reinterpret_cast<SharedBarriers*>(smem + kStages * kStageBytes);
+
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_units = M / (2 * BM), n_tiles = N / BN, num_kb = K / BK;
+  const int total_work = m_units * n_tiles;
+  const int work0 = blockIdx.x >> 1, work_stride = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars->full[i], 2);                  // (leader only is waited on) both producers arrive
+      mbar_init(&bars->empty[i], 1);                 // leader's commit, multicast to both CTAs
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);             // leader's commit, multicast to both CTAs
+      mbar_init(&bars->tmem_empty[i], 2 * kEpilogueWarps);   // (leader's is waited on) both CTAs' epilogue warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): my A rows + my half of the B rows, bytes credited to the leader's barrier =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = work0; tile < total_work; tile += work_stride) {
+        const int m0 = ((tile % m_units) * 2 + (int)crank) * BM, n0 = (tile / m_units) * BN;
+        const int nb0 = n0 + (int)crank * (BN / 2);
+        if (ep.ready_flags != nullptr) {
+          const uint32_t want = ep.ready_epoch_ptr ? ld_acquire_sys(ep.ready_epoch_ptr) : ep.ready_epoch;
+          const int64_t c_lo = (ep.ready_elem_offset + (int64_t)nb0 * K) / ep.ready_chunk_elems;
+          const int64_t c_hi = (ep.ready_elem_offset + (int64_t)(nb0 + BN / 2) * K - 1) / ep.ready_chunk_elems;
+          for (int64_t c = c_lo; c <= c_hi; ++c)
+            while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
+          if (ep.bias != nullptr) {
+            const int64_t b_lo = (ep.ready_elem_offset + (int64_t)N * K + n0) / ep.ready_chunk_elems;
+            const int64_t b_hi = (ep.ready_elem_offset + (int64_t)N * K + n0 + BN - 1) / ep.ready_chunk_elems;
+            for (int64_t c = b_lo; c <= b_hi; ++c)
+              while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
+          }
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          const uint32_t lead_full = mapa_shared(smem_u32(&bars->full[stage]), 0u);
+          if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * kStageBytes);   // bytes of BOTH CTAs
+          else mbar_arrive_remote(lead_full);
+          tma_load_2d_2sm(smem_a + stage * kStageBytesA, &tmap_a, kb * BK, m0, lead_full);
+          tma_load_2d_2sm(smem_b + stage * kStageBytesB, &tmap_b, kb * BK, nb0, lead_full);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only, one lane =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = work0; tile < total_work; tile += work_stride, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * kStageBytesA));
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * kStageBytesB));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2sm(&bars->empty[stage], (uint16_t)0x3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&bars->tmem_full[as], (uint16_t)0x3);
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..9 (both CTAs): my 128 rows of the 256-row tile =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int local = 0;
+    for (int tile = work0; tile < total_work; tile += work_stride, ++local) {
+      const int m0 = ((tile % m_units) * 2 + (int)crank) * BM, n0 = (tile / m_units) * BN;
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        tmem_ld_wait();
+        epilogue_chunk(v, ep, row, n0 + c0, lane, q, m0, M, N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&bars->tmem_empty[as]);
+        else mbar_arrive_remote(mapa_shared(smem_u32(&bars->tmem_empty[as]), 0u));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+  using C = Cfg2SM;
+  CUtensorMap ta, tb;
+  if (!make_tmap(A, M, K, BM, &ta) || !make_tmap(B, N, K, C::BN / 2, &tb)) return cudaErrorInvalidValue;
+  static bool configured[64] = {false};
+  static int num_sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem, 2sm) failed"; return e; }
+    cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    configured[dev & 63] = true;
+  }
+  const int work = (M / (2 * BM)) * (N / C::BN);
+  int units = num_sms[dev & 63] / 2;
+  if (work < units) units = work;
+  if (units < 1) units = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * 2);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel, ta, tb, M, N, K, ep);
+}
+
 }  // namespace
 
 const char* gemm_tcgen05_last_error() { return g_last_error.c_str(); }
@@ -486,6 +717,10 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
   }
   if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
   // BN=256 when it divides N and leaves enough tiles to fill the machine; BN=128 otherwise
+  if (ep.cluster == 3) {   // cta_group::2: two SMs per 256x256 tile
+    if ((M % 256) || (N % 256)) { g_last_error = "cta_group::2 needs M%256==0 and N%256==0"; return cudaErrorInvalidValue; }
+    return launch_2sm(A, B, M, N, K, ep, s);
+  }
   const bool wide = (N % 256 == 0) && ((int64_t)(M / BM) * (N / 256) >= 120) && ep.tile_n != 128;
   if (wide || ep.tile_n == 256) {
     if (N % 256) { g_last_error = "tile_n=256 needs N%256==0"; return cudaErrorInvalidValue; }

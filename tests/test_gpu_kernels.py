@@ -145,7 +145,8 @@ def test_eval_argmax_minmax_perm_convert():
 @pytest.mark.parametrize("m,n,k,tile_n,cluster", [(128, 128, 64, 0, 0), (256, 384, 512, 0, 0), (1024, 4096, 4096, 0, 0),
                                                   (128, 256, 128, 256, 1), (384, 512, 320, 256, 1), (1024, 4096, 4096, 128, 0),
                                                   (256, 256, 64, 256, 2), (512, 768, 448, 256, 2), (2048, 4096, 1024, 256, 2),
-                                                  (1024, 4096, 4096, 256, 1)])
+                                                  (1024, 4096, 4096, 256, 1),
+                                                  (256, 256, 64, 256, 3), (512, 768, 448, 256, 3), (1024, 4096, 4096, 256, 3)])
 def test_gemm_tcgen05_plain(m, n, k, tile_n, cluster):
     dev = _dev()
     torch.manual_seed(6)
@@ -159,7 +160,8 @@ def test_gemm_tcgen05_plain(m, n, k, tile_n, cluster):
     assert err < 1e-2 * max(1.0, ref.abs().max().item()), err
 
 
-def test_gemm_tcgen05_epilogues():
+@pytest.mark.parametrize("cluster", [0, 3])
+def test_gemm_tcgen05_epilogues(cluster):
     dev = _dev()
     torch.manual_seed(7)
     m, n, k = 256, 256, 192
@@ -169,7 +171,7 @@ def test_gemm_tcgen05_epilogues():
     ref = a.float() @ b.float().t()
     # bias + relu, bf16 + transposed outputs
     o, ot = torch.empty(m, n, device=dev, dtype=torch.bfloat16), torch.empty(n, m, device=dev, dtype=torch.bfloat16)
-    ops.gemm_bf16(a, b, bias=bias, relu=True, out_bf16=o, out_bf16_t=ot)
+    ops.gemm_bf16(a, b, bias=bias, relu=True, out_bf16=o, out_bf16_t=ot, cluster=cluster)
     want = torch.relu(ref + bias)
     assert torch.allclose(o.float(), want, atol=5e-2, rtol=2e-2)
     assert torch.equal(ot, o.t().contiguous())
@@ -177,7 +179,7 @@ def test_gemm_tcgen05_epilogues():
     mask = (torch.randn(m, n, device=dev)).to(torch.bfloat16)
     of = torch.empty(m, n, device=dev)
     cs = torch.zeros(m // 32, n, device=dev)
-    ops.gemm_bf16(a, b, relu_mask=mask, out_f32=of, colsum=cs)
+    ops.gemm_bf16(a, b, relu_mask=mask, out_f32=of, colsum=cs, cluster=cluster)
     assert torch.allclose(of, ref * (mask.float() > 0), atol=1e-2, rtol=1e-2)
     want_cs = (ref * (mask.float() > 0)).view(m // 32, 32, n).sum(1)                      # per-32-row-block partials
     assert torch.allclose(cs, want_cs, atol=5e-2, rtol=1e-2)
@@ -189,7 +191,7 @@ def test_gemm_tcgen05_epilogues():
     master = torch.randn(m, n, device=dev)
     want_master = master - 0.1 * ref
     sh, sht = torch.empty(m, n, device=dev, dtype=torch.bfloat16), torch.empty(n, m, device=dev, dtype=torch.bfloat16)
-    ops.gemm_bf16(a, b, sgd_master=master, sgd_lr=0.1, sgd_shadow=sh, sgd_shadow_t=sht)
+    ops.gemm_bf16(a, b, sgd_master=master, sgd_lr=0.1, sgd_shadow=sh, sgd_shadow_t=sht, cluster=cluster)
     assert torch.allclose(master, want_master, atol=1e-2, rtol=1e-2)
     assert torch.equal(sh, master.to(torch.bfloat16)) and torch.equal(sht, master.t().contiguous().to(torch.bfloat16))
 
