@@ -248,36 +248,55 @@ class FederatedEngine:
             self.y = torch.empty(n, 1, device=dev)
             self.set_local_data(self.x, self.y)
         e0 = self.epoch
-        perm = ops.device_permutation(n, cfg.epochs * rounds, self.seed * 1000003 + self.rounds_done + 17 * r, dev) \
-            if cfg.shuffle else None
         coord_slots = arena.ptr("slots", self.coord, r * P4)
         coord_loss = arena.ptr("losses", self.coord, 2 * r)
         coord_arrive = arena.ptr("flags", self.coord, 1 + r)
-        tasks = []
         C = self.clients_per_rank
-        if C > 1:
-            from ..data import shard_bounds
-            cb = [b for b in shard_bounds(n, C)]
-            cperm = [ops.device_permutation(hi - lo, cfg.epochs * rounds, self.seed * 7919 + self.rounds_done + 131 * c + 17 * r, dev)
-                     if (cfg.shuffle and hi > lo) else None for c, (lo, hi) in enumerate(cb)]
-        for i in range(rounds):
-            w = self._round_weights(masks[i])[r]
-            p = perm[i * cfg.epochs:(i + 1) * cfg.epochs] if perm is not None else None
-            if C == 1:
-                tasks.append(ops.ClientTask(x=self.x, y=self.y, theta_in=arena.ptr("inbox"), theta_out=coord_slots, perm=p,
-                                            loss_out=coord_loss, wait_flag=arena.ptr("flags"), wait_value=e0 + i + 1,
-                                            signal_flag=coord_arrive, signal_value=e0 + i + 1, out_scale=w))
-            else:
-                # C virtual clients on this GPU (one CTA each); each starts from the broadcast theta, trains on its
-                # contiguous sub-shard and leaves w_rank * (n_c / n_rank) * theta_c in a local slot
-                for c, (lo, hi) in enumerate(cb):
-                    share = ((hi - lo) / max(1, n)) if self.weighted else 1.0 / C
-                    tasks.append(ops.ClientTask(x=self.x[lo:hi], y=self.y[lo:hi], theta_in=arena.ptr("inbox"),
-                                                theta_out=self.client_slots[c],
-                                                perm=(cperm[c][i * cfg.epochs:(i + 1) * cfg.epochs] if cperm[c] is not None else None),
-                                                loss_out=self.client_losses[c],
-                                                wait_flag=arena.ptr("flags"), wait_value=e0 + i + 1, out_scale=w * share))
-        descs = ops.build_client_descs(tasks, dev)
+        # Single-round calls (the e2e / per-step usage) reuse a cached plan: descriptors + sample orders for the next
+        # kPlanRounds rounds are built once; a call then costs no descriptor packing, no H2D of descriptors and no
+        # permutation launch.  Epochs advance by 2 per single-round call (broadcast, then reduce without broadcast).
+        kPlanRounds = 256
+        plan_key = (masks[0], n, self.x.data_ptr(), cfg.batch_size, cfg.epochs, cfg.max_nr_batches, cfg.lr, C)
+        plan = getattr(self, "_star_plan", None)
+        cached = (rounds == 1 and plan is not None and plan["key"] == plan_key and plan["used"] < plan["cap"]
+                  and plan["e0"] + 2 * plan["used"] == e0)
+        if cached:
+            descs, desc_base = plan["descs"], plan["used"] * C
+            plan["used"] += 1
+        else:
+            cap = kPlanRounds if rounds == 1 else rounds
+            stride = 2 if rounds == 1 else 1
+            perm = ops.device_permutation(n, cfg.epochs * cap, self.seed * 1000003 + self.rounds_done + 17 * r, dev) \
+                if cfg.shuffle else None
+            tasks = []
+            if C > 1:
+                from ..data import shard_bounds
+                cb = [b for b in shard_bounds(n, C)]
+                cperm = [ops.device_permutation(hi - lo, cfg.epochs * cap, self.seed * 7919 + self.rounds_done + 131 * c + 17 * r, dev)
+                         if (cfg.shuffle and hi > lo) else None for c, (lo, hi) in enumerate(cb)]
+            for i in range(cap):
+                w = self._round_weights(masks[i] if rounds > 1 else masks[0])[r]
+                p = perm[i * cfg.epochs:(i + 1) * cfg.epochs] if perm is not None else None
+                ev = e0 + stride * i + 1
+                if C == 1:
+                    tasks.append(ops.ClientTask(x=self.x, y=self.y, theta_in=arena.ptr("inbox"), theta_out=coord_slots, perm=p,
+                                                loss_out=coord_loss, wait_flag=arena.ptr("flags"), wait_value=ev,
+                                                signal_flag=coord_arrive, signal_value=ev, out_scale=w))
+                else:
+                    # C virtual clients on this GPU (one CTA each); each starts from the broadcast theta, trains on its
+                    # contiguous sub-shard and leaves w_rank * (n_c / n_rank) * theta_c in a local slot
+                    for c, (lo, hi) in enumerate(cb):
+                        share = ((hi - lo) / max(1, n)) if self.weighted else 1.0 / C
+                        tasks.append(ops.ClientTask(x=self.x[lo:hi], y=self.y[lo:hi], theta_in=arena.ptr("inbox"),
+                                                    theta_out=self.client_slots[c],
+                                                    perm=(cperm[c][i * cfg.epochs:(i + 1) * cfg.epochs] if cperm[c] is not None else None),
+                                                    loss_out=self.client_losses[c],
+                                                    wait_flag=arena.ptr("flags"), wait_value=ev, out_scale=w * share))
+            descs = ops.build_client_descs(tasks, dev)
+            desc_base = 0
+            if rounds == 1:
+                self._star_plan = {"key": plan_key, "descs": descs, "perm": perm, "cperm": cperm if C > 1 else None,
+                                   "cap": cap, "used": 1, "e0": e0}
         inbox_ptrs = arena.peer_ptrs("inbox")
         bflag_ptrs = arena.peer_ptrs("flags")
         n_blocks = max(1, min(148, (P4 // 4 + 255) // 256))
@@ -319,7 +338,7 @@ class FederatedEngine:
                 self.y.copy_(hy.view(-1, 1), non_blocking=True)
             if (masks[i] >> r) & 1:
                 ops.mlp_local_sgd_multi(self.spec.dims, self.spec.out_activation, descs, C, cfg.batch_size, cfg.lr,
-                                        cfg.epochs, cfg.max_nr_batches, cfg.loss, desc_offset=i * C)
+                                        cfg.epochs, cfg.max_nr_batches, cfg.loss, desc_offset=desc_base + i * C)
                 launches += 1
                 if C > 1:
                     ext.reduce_push(self.client_slots.data_ptr(), C, P4, P4, coord_slots, self.client_losses.data_ptr(),

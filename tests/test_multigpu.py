@@ -46,6 +46,26 @@ def test_engine_star_single_gpu_matches_reference_round():
     assert abs(float(eng.loss_host[0]) - float(rep2.losses[-1, 0, 0])) < 1e-6
 
 
+def test_engine_single_round_calls_use_cached_plan_and_match_multi_round():
+    from colearn_federated_learning_b200.data import synthetic_unsw
+    from colearn_federated_learning_b200.parallel import FederatedEngine
+    dev = torch.device("cuda", 0)
+    x, y = synthetic_unsw(200, seed=5)
+    a = FederatedEngine("mlp", backend="fused", device=dev, batch_size=1, lr=0.05, seed=9, shuffle=False)
+    b = FederatedEngine("mlp", backend="fused", device=dev, batch_size=1, lr=0.05, seed=9, shuffle=False)
+    a.set_local_data(x, y)
+    b.set_local_data(x, y)
+    for _ in range(4):
+        a.run_rounds(1)
+    assert a._star_plan["used"] == 4                      # one plan, four single-round calls
+    b.run_rounds(4)
+    assert torch.allclose(a.global_flat(), b.global_flat(), atol=1e-6)
+    a.run_rounds(2)                                       # a multi-round call in between invalidates nothing it should not
+    a.run_rounds(1)
+    b.run_rounds(3)
+    assert torch.allclose(a.global_flat(), b.global_flat(), atol=1e-6)
+
+
 def test_engine_many_clients_per_gpu():
     """100 federated devices do not need 100 GPUs: C virtual clients per rank, one CTA each, summed on-GPU."""
     from colearn_federated_learning_b200.data import shard_bounds, synthetic_unsw
