@@ -98,6 +98,22 @@ class InProcessBroker:
     def inject_duplicate(self, predicate: Callable[[Message], bool]) -> None:
         self.add_fault_hook(lambda m: [(0.0, m), (0.0, m)] if predicate(m) else [(0.0, m)])
 
+    def inject_from_spec(self, spec: str) -> None:
+        """Install a fault hook from a CLI string (``federated_coordinator.py --inject``):
+        ``drop:<regex>`` | ``dup:<regex>`` | ``delay:<seconds>:<regex>`` — the regex is searched in the utf-8 payload."""
+        import re
+        kind, _, rest = spec.partition(":")
+        if kind == "delay":
+            secs, _, pattern = rest.partition(":")
+            rx = re.compile(pattern or ".")
+            self.inject_delay(lambda m: bool(rx.search(m.payload.decode("utf-8", "replace"))), float(secs))
+        elif kind in ("drop", "dup"):
+            rx = re.compile(rest or ".")
+            pred = lambda m: bool(rx.search(m.payload.decode("utf-8", "replace")))  # noqa: E731
+            (self.inject_drop if kind == "drop" else self.inject_duplicate)(pred)
+        else:
+            raise ValueError(f"unknown fault spec {spec!r} (use drop:<re>, dup:<re> or delay:<s>:<re>)")
+
     # -- publish -------------------------------------------------------------------------
     def publish(self, topic: str, payload, qos: int = 0) -> int:
         if isinstance(payload, str):

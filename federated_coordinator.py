@@ -63,6 +63,8 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--round-log", type=str, default=None, help="write the reference-format round log here")
     parser.add_argument("--evaluate", action="store_true", help="evaluate the global model on --test-path after training")
     parser.add_argument("--embedded-broker", action="store_true", help="start the TCP bus broker inside this process")
+    parser.add_argument("--inject", action="append", default=[], metavar="SPEC",
+                        help="fault injection on the embedded broker: drop:<regex> | dup:<regex> | delay:<seconds>:<regex> (repeatable)")
     parser.add_argument("--exit-after", type=int, default=0, help="exit after N completed trainings (0 = run forever)")
     parser.add_argument("--box", action="store_true", help="multi-GPU box mode under torchrun (rank 0 = coordinator)")
     parser.add_argument("--backend", choices=["auto", "fused", "nccl", "cpu"], default="auto")
@@ -97,6 +99,9 @@ def main(args: argparse.Namespace) -> None:
     if args.embedded_broker:
         broker = TcpBroker("127.0.0.1" if args.host == "localhost" else args.host, args.port).start()
         logging.info("embedded bus broker listening on %s:%d", broker.host, broker.port)
+        for spec in args.inject:
+            broker.broker.inject_from_spec(spec)
+            logging.info("fault injection active: %s", spec)
     coordinator = Coordinator(args.window, args.remote, args.federated_round, args.encryption, args.iot,
                               args=arguments_from_cli(args), transport="tcp", path=args.checkpoint,
                               strict_events=args.strict_events, select_k=args.select, selection=args.selection,

@@ -57,6 +57,22 @@ def test_fault_injection_drop_duplicate_delay():
     assert c.drain() == 1 and got[-1] == b"late"
 
 
+def test_fault_injection_from_cli_spec():
+    b = InProcessBroker()
+    c, got = _collector(b)
+    p = BusClient("pub", broker=b)
+    p.connect()
+    b.inject_from_spec(r"drop:192\.168\.1\.66")
+    b.inject_from_spec("dup:NOT_READY")
+    p.publish("topic/state", "(192.168.1.66, TRAINING)")
+    p.publish("topic/state", "(192.168.1.7, NOT_READY)")
+    p.publish("topic/state", "(192.168.1.8, TRAINING)")
+    c.drain()
+    assert got == [b"(192.168.1.7, NOT_READY)"] * 2 + [b"(192.168.1.8, TRAINING)"]
+    with pytest.raises(ValueError):
+        b.inject_from_spec("explode:everything")
+
+
 def test_tcp_transport_roundtrip():
     with TcpBroker("127.0.0.1", 0) as broker:
         got = []
