@@ -158,11 +158,40 @@ class NvmlSampler:
                 "bad": sorted(BAD_REASONS & set(reasons))}
 
 
+def monitor_gpu(index: int = 0, path: str = "monitoring_gpu.txt", samples: int = 3000, interval: float = 1.0,
+                stop: Optional[threading.Event] = None) -> None:
+    """GPU analogue of :func:`monitor_cpu`: one ``Monitoring: <i> <timestamp>`` block per sample with SM clock,
+    power, temperature and the active throttle reasons (NVML)."""
+    sampler = NvmlSampler(index, period_s=interval)
+    with open(path, "w+") as f:
+        if not sampler._ok:
+            f.write("nvml unavailable\n")
+            return
+        nv, h = sampler._nv, sampler._h
+        for i in range(samples):
+            if stop is not None and stop.is_set():
+                break
+            try:
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                names = sorted(n for b, n in THROTTLE_BITS.items() if int(reasons) & b)
+                f.write("Monitoring: " + str(i) + " " + str(datetime.now()) + "\n")
+                f.write("    sm_mhz=%s power_w=%.1f temp_c=%s reasons=%s\n" % (
+                    nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                    nv.nvmlDeviceGetTemperature(h, nv.NVML_TEMPERATURE_GPU), ",".join(names) or "none"))
+                f.flush()
+            except Exception as e:  # noqa: BLE001
+                f.write("nvml error: %r\n" % (e,))
+                break
+            time.sleep(interval)
+
+
 def build_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser(description="Process monitoring")
     parser.add_argument("--pid", "-p", type=int, default=None, help="process pid to monitor")
     parser.add_argument("--network", "-n", type=str, default=None, help="Start monitor a network interface")
     parser.add_argument("--temperature", "-T", action="store_true", help="also sample temperatures")
+    parser.add_argument("--gpu", "-g", type=int, default=None, help="also sample this GPU through NVML")
     parser.add_argument("--samples", type=int, default=3000)
     return parser
 
@@ -179,6 +208,8 @@ def main(argv=None) -> None:
         threads.append(threading.Thread(target=monitor_network, args=(args.network,), kwargs={"samples": args.samples}))
     if args.temperature:
         threads.append(threading.Thread(target=monitor_temperature, kwargs={"samples": args.samples}))
+    if args.gpu is not None:
+        threads.append(threading.Thread(target=monitor_gpu, args=(args.gpu,), kwargs={"samples": args.samples}))
     for t in threads:
         t.start()
     logging.info("Waiting for the threads ending")

@@ -257,6 +257,11 @@ def test_monitors(tmp_path):
     assert open(temp).read().count("Monitoring: ") == 2
     s = monitors.NvmlSampler().start()
     assert "reasons" in s.stop()
+    gpu = str(tmp_path / "gpu.txt")
+    monitors.monitor_gpu(0, gpu, samples=1, interval=0.01)      # no NVML on the CPU box -> says so, never raises
+    assert os.path.getsize(gpu) > 0
+    ns = monitors.build_parser().parse_args(["-p", "1", "-n", "eth0", "--gpu", "0"])
+    assert (ns.pid, ns.network, ns.gpu) == (1, "eth0", 0)
 
 
 def test_reference_shaped_client_federated_api(tmp_path):
