@@ -1,0 +1,346 @@
+"""Local training of ResNet-18 on this repo's own kernels (BASELINE config 4).
+
+Every convolution is ``im2col`` + the tcgen05 GEMM (``ops.gemm_bf16``) in its three roles,
+
+    forward   z[M, Cout]      = col[M, K]      · Wp[Cout, K]ᵀ                      (M = N·OH·OW, k = (kh, kw, c))
+    dgrad     dcol[M, K]      = dz[M, Cout]    · (Wpᵀ)[K, Cout]ᵀ   → col2im gather → dx
+    wgrad     Wp[Cout, K]    -= lr · dzᵀ[Cout, M] · colᵀ[K, M]ᵀ    (SGD fused in the GEMM epilogue: fp32 master +
+                                                                    bf16 shadow refreshed, dW never materialised)
+
+with NHWC bf16 activations, so the GEMM output *is* the next layer's activation matrix.  BatchNorm (training
+statistics, apply + residual + ReLU, backward with the ReLU mask folded in), max / average pooling and the
+weight (un)packing are the kernels of ``ops/csrc/convnet.cu``; the loss is ``ops.softmax_xent`` and the small
+parameters (γ, β, fc bias) take one flat ``ops.sgd_step``.  During a fit the *packed* fp32 weights
+(``[Cout_pad, K_pad]``, what the wgrad epilogue updates) are the master copy; ``load`` packs them from the flat
+arena FedAvg averages and ``store`` unpacks them back, once per fit each.
+
+Numerics follow the autocast-bf16 torch path this replaces (bf16 operands / activations, fp32 accumulation,
+fp32 statistics and parameters).  No reference counterpart: the reference has no conv nets.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..models.registry import param_layout
+from ..models.resnet import BasicBlock, ResNet18
+from ..ops import conv as C
+
+BF = torch.bfloat16
+PAD = 128
+
+
+def _pad(n: int, m: int = PAD) -> int:
+    return (n + m - 1) // m * m
+
+
+class _Conv:
+    """Geometry + buffers of one convolution (+ the BatchNorm that follows it)."""
+
+    def __init__(self, name: str, mod: nn.Conv2d, bn_name: str, bn: nn.BatchNorm2d, n: int, h: int, w: int) -> None:
+        self.name, self.bn_name = name, bn_name
+        self.cin, self.cout = mod.in_channels, mod.out_channels
+        self.k, self.stride, self.pad = mod.kernel_size[0], mod.stride[0], mod.padding[0]
+        self.n, self.h, self.w = n, h, w
+        self.oh, self.ow = C.out_size(h, self.k, self.stride, self.pad), C.out_size(w, self.k, self.stride, self.pad)
+        self.m_in, self.m = n * h * w, n * self.oh * self.ow
+        self.K = self.k * self.k * self.cin
+        self.K_pad, self.cout_pad = _pad(self.K), _pad(self.cout)
+        self.eps, self.momentum = bn.eps, (0.1 if bn.momentum is None else bn.momentum)
+        self.entry: Optional[C.PackEntry] = None
+
+    def alloc(self, dev, act_dtype: torch.dtype = BF) -> None:
+        z = lambda *s, dt=act_dtype: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
+        self.col = z(self.m, self.K_pad)              # saved for the wgrad
+        self.z = z(self.m, self.cout_pad)             # conv output (pre-BN), pitch cout_pad
+        self.out = z(self.m, self.cout)               # post BN (+res) (+ReLU) activation
+        self.mean = z(self.cout, dt=torch.float32)
+        self.invstd = z(self.cout, dt=torch.float32)
+        self.rm = z(self.cout, dt=torch.float32)      # running statistics (module buffers, kept on the device)
+        self.rv = torch.ones(self.cout, device=dev)
+        self.wT = z(self.K_pad, self.cout)            # bf16 Wpᵀ (valid rows only) for the dgrad
+        self.dz = z(self.m, self.cout)                # gradient w.r.t. the conv output
+
+
+class _Block:
+    def __init__(self, c1: _Conv, c2: _Conv, ds: Optional[_Conv]) -> None:
+        self.c1, self.c2, self.ds = c1, c2, ds
+
+
+class ConvNetTrainer:
+    """SGD steps of :class:`~colearn_federated_learning_b200.models.resnet.ResNet18` on a flat fp32 arena."""
+
+    _cache: Dict[Tuple, "ConvNetTrainer"] = {}
+
+    # -- construction --------------------------------------------------------------------------------------
+    @staticmethod
+    def supports(model: nn.Module, cfg, x: torch.Tensor) -> bool:
+        return (isinstance(model, ResNet18) and cfg.loss == "xent" and cfg.batch_size % 128 == 0 and x.dim() == 4
+                and x.shape[1] == model.conv1.in_channels and x.shape[0] >= cfg.batch_size
+                and x.shape[0] % cfg.batch_size == 0          # a ragged last batch stays on the autograd path
+                and x.shape[2] >= 32 and x.shape[3] >= 32)
+
+    @classmethod
+    def cached(cls, model: ResNet18, flat: torch.Tensor, batch_size: int, hw: Tuple[int, int]) -> "ConvNetTrainer":
+        key = (id(model), flat.data_ptr(), str(flat.device), batch_size, tuple(hw))
+        tr = cls._cache.get(key)
+        if tr is None:
+            if len(cls._cache) > 2:
+                cls._cache.clear()
+            tr = cls._cache[key] = cls(model, flat.device, batch_size, hw)
+        return tr
+
+    def __init__(self, model: ResNet18, device, batch_size: int, hw: Tuple[int, int] = (32, 32),
+                 act_dtype: torch.dtype = BF) -> None:
+        """``act_dtype=torch.float32`` (CPU only) keeps every buffer in fp32: the PyTorch definitions of the ops then
+        make the whole step an exact oracle for the orchestration (tests compare it with autograd)."""
+        assert batch_size % 128 == 0, "the GEMM tiles need batch_size % 128 == 0"
+        assert act_dtype == BF or torch.device(device).type == "cpu", "the kernels are bf16"
+        self.dev, self.B, self.dt = torch.device(device), batch_size, act_dtype
+        self.num_classes = model.fc.out_features
+        dev, B = self.dev, batch_size
+        layout = {name: (off, shape) for name, shape, off, _ in param_layout(model)}
+        self.n_params = sum(n for _, _, _, n in param_layout(model))
+
+        # ---- geometry -------------------------------------------------------------------------------------
+        h, w = hw
+        self.stem = _Conv("conv1", model.conv1, "bn1", model.bn1, B, h, w)
+        h, w = self.stem.oh, self.stem.ow
+        self.pool_in = (h, w)
+        self.pool_k, self.pool_s, self.pool_p = 3, 2, 1
+        h, w = C.out_size(h, 3, 2, 1), C.out_size(w, 3, 2, 1)
+        self.pool_out = (h, w)
+        self.blocks: List[_Block] = []
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(model, f"layer{li}")):
+                assert isinstance(blk, BasicBlock)
+                p = f"layer{li}.{bi}"
+                c1 = _Conv(f"{p}.conv1", blk.conv1, f"{p}.bn1", blk.bn1, B, h, w)
+                c2 = _Conv(f"{p}.conv2", blk.conv2, f"{p}.bn2", blk.bn2, B, c1.oh, c1.ow)
+                ds = None
+                if blk.downsample is not None:
+                    ds = _Conv(f"{p}.downsample.0", blk.downsample[0], f"{p}.downsample.1", blk.downsample[1], B, h, w)
+                self.blocks.append(_Block(c1, c2, ds))
+                h, w = c2.oh, c2.ow
+        self.final_hw = h * w
+        self.feat_dim = self.blocks[-1].c2.cout
+        self.convs: List[_Conv] = [self.stem] + [c for b in self.blocks for c in ((b.c1, b.c2, b.ds) if b.ds else (b.c1, b.c2))]
+
+        # ---- packed big parameters: conv weights + fc weight ([rows_pad, cols_pad], GEMM layout) ---------------
+        entries = []
+        for cv in self.convs:
+            off, _ = layout[cv.name + ".weight"]
+            cv.entry = C.PackEntry(cv.name + ".weight", off, cv.cout, cv.K, cv.cout_pad, cv.K_pad, cv.cin, cv.k * cv.k)
+            entries.append(cv.entry)
+        off, _ = layout["fc.weight"]
+        self.nc_pad = _pad(self.num_classes)
+        self.fc_entry = C.PackEntry("fc.weight", off, self.num_classes, self.feat_dim, self.nc_pad, _pad(self.feat_dim))
+        entries.append(self.fc_entry)
+        self.big = C.PackPlan(entries, dev)
+        self.mpk = torch.zeros(self.big.total, device=dev)                       # fp32 master (during a fit)
+        self.wpk = torch.zeros(self.big.total, device=dev, dtype=act_dtype)      # bf16 shadow (GEMM operand)
+
+        # ---- packed small parameters: gamma / beta of every BatchNorm, fc bias (padded) -----------------------
+        small = []
+        for cv in self.convs:
+            for leaf in ("weight", "bias"):
+                off, _ = layout[f"{cv.bn_name}.{leaf}"]
+                small.append(C.PackEntry(f"{cv.bn_name}.{leaf}", off, 1, cv.cout, 1, cv.cout))
+        off, _ = layout["fc.bias"]
+        small.append(C.PackEntry("fc.bias", off, 1, self.num_classes, 1, self.nc_pad))
+        self.small = C.PackPlan(small, dev)
+        self.spk = torch.zeros(self.small.total, device=dev)
+        self.gsp = torch.zeros(self.small.total, device=dev)
+        self._small_by_name = {e.name: e for e in self.small.entries}
+
+        # ---- buffers ------------------------------------------------------------------------------------------
+        for cv in self.convs:
+            cv.alloc(dev, act_dtype)
+        z = lambda *s, dt=act_dtype: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
+        max_colT = max(cv.m * cv.K_pad for cv in self.convs)
+        max_dzT = max(cv.m * cv.cout_pad for cv in self.convs)
+        self.colT = z(max_colT)                        # scratch: colᵀ of the layer whose wgrad runs
+        self.dcol = z(max_colT)                        # scratch: dgrad GEMM output
+        self.dzT = z(max_dzT)                          # scratch: dzᵀ padded to cout_pad rows
+        self.partial = z(max(C.bn_partial_numel(cv.m, cv.cout) for cv in self.convs), dt=torch.float32)
+        m_pool = B * self.pool_out[0] * self.pool_out[1]
+        self.pool_y = z(m_pool, self.stem.cout)
+        self.pool_idx = torch.zeros(m_pool, self.stem.cout, device=dev, dtype=torch.uint8)
+        self.d_pool = z(m_pool, self.stem.cout)        # gradient w.r.t. the pooled stem output
+        self.d_stem = z(self.stem.m, self.stem.cout)   # gradient w.r.t. the stem activation
+        for b in self.blocks:
+            b.g = z(b.c2.m, b.c2.cout)                 # masked gradient at the block output (identity branch)
+            b.d_mid = z(b.c1.m, b.c1.cout)             # gradient w.r.t. relu(bn1(conv1))
+            b.d_in = z(b.c1.m_in, b.c1.cin)            # gradient w.r.t. the block input
+            b.d_skip = z(b.c1.m_in, b.c1.cin) if b.ds else None
+        self.feat = z(B, self.feat_dim)
+        self.featT = z(self.feat_dim, B)
+        self.d_feat = z(B, self.feat_dim)
+        self.d_last = z(self.blocks[-1].c2.m, self.feat_dim)
+        self.logits = z(B, self.nc_pad, dt=torch.float32)
+        self.dlog = z(B, self.nc_pad)
+        self.dlogT = z(self.nc_pad, B)
+        self.fc_wT = z(self.feat_dim, self.nc_pad)
+        self.launches = 0
+        self.steps_done = 0
+
+    # -- parameter views ------------------------------------------------------------------------------------------
+    def _w(self, e: C.PackEntry) -> torch.Tensor:
+        return self.big.view(self.wpk, e)
+
+    def _m(self, e: C.PackEntry) -> torch.Tensor:
+        return self.big.view(self.mpk, e)
+
+    def _s(self, name: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        e = self._small_by_name[name]
+        return (self.spk if buf is None else buf)[e.dst_off:e.dst_off + e.numel_pad]
+
+    def load(self, flat: torch.Tensor, model: Optional[ResNet18] = None) -> None:
+        """Flat arena (and the module's BatchNorm buffers) → packed device state."""
+        C.pack_params(flat, self.mpk, self.wpk, self.big)
+        C.pack_params(flat, self.spk, None, self.small)
+        for cv in self.convs:
+            ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
+        ops.transpose_bf16(self._w(self.fc_entry), self.fc_wT)
+        if model is not None:
+            mods = dict(model.named_modules())
+            for cv in self.convs:
+                bn = mods[cv.bn_name]
+                cv.rm.copy_(bn.running_mean)
+                cv.rv.copy_(bn.running_var)
+        self.launches += 3 + len(self.convs)
+
+    def store(self, flat: torch.Tensor, model: Optional[ResNet18] = None) -> None:
+        """Packed device state → flat arena (and the module's BatchNorm buffers)."""
+        C.pack_params(flat, self.mpk, None, self.big, unpack=True)
+        C.pack_params(flat, self.spk, None, self.small, unpack=True)
+        if model is not None:
+            mods = dict(model.named_modules())
+            with torch.no_grad():
+                for cv in self.convs:
+                    bn = mods[cv.bn_name]
+                    bn.running_mean.copy_(cv.rm)
+                    bn.running_var.copy_(cv.rv)
+                    bn.num_batches_tracked += self.steps_done
+        self.steps_done = 0
+        self.launches += 2
+
+    # -- forward ------------------------------------------------------------------------------------------------------
+    def _conv_bn(self, cv: _Conv, x4: torch.Tensor, res: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+        C.im2col(x4, cv.col, cv.k, cv.k, cv.stride, cv.pad)
+        ops.gemm_bf16(cv.col, self._w(cv.entry), out_bf16=cv.z)
+        C.bn_stats(cv.z, cv.cout, self.partial, cv.mean, cv.invstd, cv.rm, cv.rv, cv.eps, cv.momentum)
+        C.bn_apply(cv.z, cv.cout, cv.mean, cv.invstd, self._s(cv.bn_name + ".weight"), self._s(cv.bn_name + ".bias"),
+                   res, relu, cv.out)
+        self.launches += 5
+        return cv.out
+
+    def forward(self, xb: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """Training-mode forward of one batch (``xb``: ``[B, Cin, H, W]`` fp32 or bf16); returns the mean loss."""
+        B = self.B
+        st = self.stem
+        a = self._conv_bn(st, xb, None, True)
+        C.maxpool_fwd(a, self.pool_y, self.pool_idx, B, st.oh, st.ow, st.cout, self.pool_k, self.pool_k, self.pool_s, self.pool_p)
+        a = self.pool_y
+        for b in self.blocks:
+            c1, c2 = b.c1, b.c2
+            x4 = C.nhwc_view(a, B, c1.h, c1.w, c1.cin)
+            identity = a if b.ds is None else self._conv_bn(b.ds, x4, None, False)
+            mid = self._conv_bn(c1, x4, None, True)
+            a = self._conv_bn(c2, C.nhwc_view(mid, B, c2.h, c2.w, c2.cin), identity, True)
+        C.avgpool_fwd(a, self.feat, B, self.final_hw, self.feat_dim)
+        ops.gemm_bf16(self.feat, self._w(self.fc_entry), bias=self._s("fc.bias"), out_f32=self.logits)
+        loss, dlog = ops.softmax_xent(self.logits[:, : self.num_classes].contiguous(), labels)
+        self.dlog[:, : self.num_classes].copy_(dlog)
+        self._s("fc.bias", self.gsp)[: self.num_classes].copy_(dlog.sum(0))
+        self.launches += 8
+        return loss
+
+    # -- backward (+ SGD) ---------------------------------------------------------------------------------------------------
+    def _bn_bwd(self, cv: _Conv, dy: torch.Tensor, masked: bool, g_out: Optional[torch.Tensor]) -> None:
+        C.bn_backward(cv.z, cv.cout, dy, cv.out if masked else None, cv.mean, cv.invstd, self._s(cv.bn_name + ".weight"),
+                      self.partial, self._s(cv.bn_name + ".weight", self.gsp), self._s(cv.bn_name + ".bias", self.gsp),
+                      cv.dz, g_out)
+        self.launches += 3
+
+    def _conv_bwd(self, cv: _Conv, lr: float, dx: Optional[torch.Tensor], add: Optional[torch.Tensor]) -> None:
+        """dgrad with the old weights (→ ``dx`` through the col2im gather), then the fused wgrad + SGD."""
+        if dx is not None:
+            dcol = self.dcol[: cv.m * cv.K_pad].view(cv.m, cv.K_pad)
+            ops.gemm_bf16(cv.dz, cv.wT, out_bf16=dcol)
+            C.col2im(dcol, dx, add, cv.n, cv.h, cv.w, cv.cin, cv.k, cv.k, cv.stride, cv.pad)
+            self.launches += 2
+        dzT = self.dzT[: cv.cout_pad * cv.m].view(cv.cout_pad, cv.m)
+        if cv.cout_pad != cv.cout:
+            dzT[cv.cout:].zero_()
+        ops.transpose_bf16(cv.dz, dzT[: cv.cout])
+        colT = self.colT[: cv.K_pad * cv.m].view(cv.K_pad, cv.m)
+        ops.transpose_bf16(cv.col, colT)
+        ops.gemm_bf16(dzT, colT, sgd_master=self._m(cv.entry), sgd_lr=lr, sgd_shadow=self._w(cv.entry))
+        ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
+        self.launches += 4
+
+    def backward(self, lr: float) -> None:
+        B = self.B
+        # classifier: dgrad first (old weights), then the fused update
+        ops.gemm_bf16(self.dlog, self.fc_wT, out_bf16=self.d_feat)
+        ops.transpose_bf16(self.dlog, self.dlogT)
+        ops.transpose_bf16(self.feat, self.featT)
+        e = self.fc_entry
+        ops.gemm_bf16(self.dlogT, self.featT, sgd_master=self._m(e), sgd_lr=lr, sgd_shadow=self._w(e))
+        ops.transpose_bf16(self._w(e), self.fc_wT)
+        C.avgpool_bwd(self.d_feat, self.d_last, B, self.final_hw, self.feat_dim)
+        self.launches += 6
+        d_out = self.d_last
+        for b in reversed(self.blocks):
+            c1, c2, ds = b.c1, b.c2, b.ds
+            self._bn_bwd(c2, d_out, True, b.g)                       # through relu(bn2(.) + identity)
+            self._conv_bwd(c2, lr, b.d_mid, None)
+            self._bn_bwd(c1, b.d_mid, True, None)                    # through relu(bn1(.))
+            if ds is None:
+                self._conv_bwd(c1, lr, b.d_in, b.g)                  # + identity branch
+            else:
+                self._bn_bwd(ds, b.g, False, None)
+                self._conv_bwd(ds, lr, b.d_skip, None)
+                self._conv_bwd(c1, lr, b.d_in, b.d_skip)
+            d_out = b.d_in
+        st = self.stem
+        C.maxpool_bwd(d_out, self.pool_idx, self.d_stem, B, st.oh, st.ow, st.cout, self.pool_k, self.pool_k, self.pool_s, self.pool_p)
+        self._bn_bwd(st, self.d_stem, True, None)
+        self._conv_bwd(st, lr, None, None)
+        ops.sgd_step(self.spk, self.gsp, lr)                         # every gamma / beta / fc bias in one launch
+        self.launches += 2
+        self.steps_done += 1
+
+    def step(self, xb: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
+        loss = self.forward(xb, labels)
+        self.backward(lr)
+        return loss
+
+    # -- a whole local fit -------------------------------------------------------------------------------------------------------
+    def fit(self, flat: torch.Tensor, model: ResNet18, x: torch.Tensor, y: torch.Tensor, cfg, perm: Optional[torch.Tensor]) -> torch.Tensor:
+        """Local SGD in place on ``flat`` (full batches only; a tail < batch_size is dropped, like the layer-wise
+        MLP trainer)."""
+        n, B = x.shape[0], self.B
+        self.load(flat, model)
+        labels_all = y.reshape(-1).long()
+        limit = cfg.max_nr_batches if cfg.max_nr_batches and cfg.max_nr_batches > 0 else None
+        last = torch.zeros((), device=flat.device)
+        it = 0
+        done = False
+        for e in range(cfg.epochs):
+            order = perm[e % perm.shape[0]].long() if perm is not None else torch.arange(n, device=flat.device)
+            for lo in range(0, n - B + 1, B):
+                idx = order[lo:lo + B]
+                last = self.step(x.index_select(0, idx), labels_all.index_select(0, idx), cfg.lr)
+                it += 1
+                if limit is not None and it >= limit:
+                    done = True
+                    break
+            if done:
+                break
+        self.store(flat, model)
+        return last

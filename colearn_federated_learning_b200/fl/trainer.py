@@ -9,11 +9,14 @@ small MLP family on a GPU, as ONE persistent-kernel launch (``ops.mlp_local_sgd`
 Three execution paths, chosen by :func:`local_fit`:
   * ``persistent``  FFNN / MLP / TestingRemote on CUDA → csrc/mlp_persistent.cu
   * ``layerwise``   wide MLPs on CUDA → tcgen05 GEMMs + fused loss/SGD kernels (fl/layerwise.py)
-  * ``torch``       anything else (ResNet-18 via cuDNN; every model on CPU) → autograd loop that
-                    still uses this repo's fused loss + flat SGD kernels where they apply.
+  * ``convnet``     ResNet-18 on CUDA → im2col + tcgen05 GEMMs + this repo's BatchNorm / pooling kernels
+                    (fl/convnet.py); ``COLEARN_CONV_PATH=torch`` selects the library path instead
+  * ``torch``       anything else (every model on CPU; conv nets with a ragged last batch) → autograd loop
+                    that still uses this repo's fused loss + flat SGD kernels where they apply.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, asdict
 from typing import Any, Dict, Optional, Tuple
 
@@ -46,6 +49,19 @@ class FitConfig:
     @classmethod
     def from_dict(cls, d: Dict[str, Any]) -> "FitConfig":
         return cls(**{k: v for k, v in d.items() if k in cls.__dataclass_fields__})
+
+
+# Which executor trains conv nets on a GPU: "native" = fl/convnet.py (this repo's kernels), "torch" = autograd over
+# cuDNN/ATen.  ``COLEARN_CONV_PATH`` overrides; on CPU tensors the native path (PyTorch definitions of the same ops)
+# only runs when asked for explicitly.
+CONV_PATH_DEFAULT = "torch"
+
+
+def conv_path(device) -> str:
+    env = os.environ.get("COLEARN_CONV_PATH", "").strip().lower()
+    if env in ("native", "torch"):
+        return env
+    return CONV_PATH_DEFAULT if torch.device(device).type == "cuda" else "torch"
 
 
 def resolve_loss(model_name: str, loss: str) -> str:
@@ -126,6 +142,11 @@ def local_fit(flat: torch.Tensor, model: nn.Module, x: torch.Tensor, y: torch.Te
             if LayerwiseMLPTrainer.supports(spec, cfg):
                 tr = LayerwiseMLPTrainer.cached(spec, flat, cfg.batch_size)
                 return tr.fit(flat, xx, y, cfg, perm), "layerwise"
+    if conv_path(flat.device) == "native":
+        from .convnet import ConvNetTrainer
+        if ConvNetTrainer.supports(model, cfg, x):
+            tr = ConvNetTrainer.cached(model, flat, cfg.batch_size, tuple(x.shape[2:]))
+            return tr.fit(flat, model, x, y, cfg, perm), "convnet"
     unflatten_params(model, flat)
     last = torch_fit(model, x, y, cfg, perm, autocast_bf16=flat.is_cuda)
     flatten_params(model, out=flat)

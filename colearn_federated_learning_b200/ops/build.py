@@ -20,8 +20,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 EXT_NAME = "_colearn_C"
+EMUL_NAME = "_colearn_emul"     # CPU emulator of the conv kernels (tests on boxes without a GPU)
 
-CU_SOURCES = ["mlp_persistent.cu", "elementwise.cu", "comm.cu", "gemm_tcgen05.cu"]
+CU_SOURCES = ["mlp_persistent.cu", "elementwise.cu", "comm.cu", "gemm_tcgen05.cu", "convnet.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
@@ -44,7 +45,7 @@ def _stamp(src: str, flags: List[str]) -> str:
     h = hashlib.sha1()
     with open(src, "rb") as f:
         h.update(f.read())
-    for dep in ("colearn_kernels.h", "mlp_v2.inc"):
+    for dep in ("colearn_kernels.h", "mlp_v2.inc", "conv_ops.cuh", "conv_bindings.inc"):
         with open(os.path.join(CSRC, dep), "rb") as f:
             h.update(f.read())
     h.update(" ".join(flags).encode())
@@ -59,15 +60,52 @@ def _run(cmd: List[str], log_name: str) -> None:
         raise RuntimeError(f"build step failed: {' '.join(cmd)}\n{proc.stdout}")
 
 
-def build_all(force: bool = False, verbose: bool = True) -> str:
+def _cxx_setup():
     import torch
     from torch.utils import cpp_extension as ce
+
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    inc = [f"-I{p}" for p in ce.include_paths(device_type="cuda")] + [f"-I{sysconfig.get_paths()['include']}", f"-I{CSRC}",
+                                                                       f"-I{os.path.join(cuda_home, 'include')}"]
+    flags = ["-O2", "-std=c++17", "-fPIC", "-DTORCH_API_INCLUDE_EXTENSION_H",
+             f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-Wno-deprecated-declarations"]
+    return ce, cuda_home, inc, flags
+
+
+def emul_path() -> str:
+    suffix = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+    return os.path.join(HERE, EMUL_NAME + suffix)
+
+
+def build_emul(force: bool = False) -> str:
+    """g++-only build of ``csrc/conv_emul.cpp`` (the conv kernels' bodies run on the CPU).  Links against the CPU
+    libtorch only, so it loads on a box without a CUDA driver."""
+    ce, _, inc, flags = _cxx_setup()
+    os.makedirs(OBJ, exist_ok=True)
+    out = emul_path()
+    src = os.path.join(CSRC, "conv_emul.cpp")
+    cxx_flags = flags + [f"-DTORCH_EXTENSION_NAME={EMUL_NAME}"]
+    obj = os.path.join(OBJ, f"conv_emul.cpp.{_stamp(src, cxx_flags)}.o")
+    if force or not os.path.exists(obj) or not os.path.exists(out):
+        for name in os.listdir(OBJ):
+            if name.startswith("conv_emul.cpp.") and name.endswith(".o"):
+                os.remove(os.path.join(OBJ, name))
+        _run(["g++", *cxx_flags, *inc, "-c", src, "-o", obj], "conv_emul.cpp")
+        link = ["g++", "-shared", obj, "-o", out]
+        for d in ce.library_paths(device_type="cpu"):
+            link += [f"-L{d}", f"-Wl,-rpath,{d}"]
+        link += ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python"]
+        _run(link, "link_emul")
+    return out
+
+
+def build_all(force: bool = False, verbose: bool = True) -> str:
+    ce, cuda_home, inc, base_cxx = _cxx_setup()
 
     os.makedirs(OBJ, exist_ok=True)
     out = ext_path()
     objs, jobs = [], []
 
-    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     for src in CU_SOURCES:
         path = os.path.join(CSRC, src)
         obj = os.path.join(OBJ, f"{src}.{_stamp(path, NVCC_FLAGS)}.o")
@@ -75,10 +113,7 @@ def build_all(force: bool = False, verbose: bool = True) -> str:
         if force or not os.path.exists(obj):
             jobs.append(([_nvcc(), *NVCC_FLAGS, "-I", CSRC, "-c", path, "-o", obj], src))
 
-    inc = [f"-I{p}" for p in ce.include_paths(device_type="cuda")] + [f"-I{sysconfig.get_paths()['include']}", f"-I{CSRC}"]
-    cxx_flags = ["-O2", "-std=c++17", "-fPIC", f"-DTORCH_EXTENSION_NAME={EXT_NAME}",
-                 "-DTORCH_API_INCLUDE_EXTENSION_H", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
-                 "-Wno-deprecated-declarations"]
+    cxx_flags = base_cxx + [f"-DTORCH_EXTENSION_NAME={EXT_NAME}"]
     for src in CPP_SOURCES:
         path = os.path.join(CSRC, src)
         obj = os.path.join(OBJ, f"{src}.{_stamp(path, cxx_flags)}.o")
@@ -105,10 +140,13 @@ def build_all(force: bool = False, verbose: bool = True) -> str:
     # drop stale cached objects (every source edit leaves one behind)
     keep = {os.path.basename(o) for o in objs}
     for name in os.listdir(OBJ):
-        if name.endswith(".o") and name not in keep:
+        if name.endswith(".o") and name not in keep and not name.startswith("conv_emul.cpp."):
             os.remove(os.path.join(OBJ, name))
     return out
 
 
 if __name__ == "__main__":
-    print(build_all(force="--force" in sys.argv))
+    if "--emul" in sys.argv:
+        print(build_emul(force="--force" in sys.argv))
+    else:
+        print(build_all(force="--force" in sys.argv))

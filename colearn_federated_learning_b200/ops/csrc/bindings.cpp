@@ -395,7 +395,25 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05: ", cudaGetErrorString(e), " (", gemm_tcgen05_last_error(), ")");
 }
 
+// ---- NHWC conv / BatchNorm / pooling (convnet.cu); wrappers shared with the host emulator ------------------
+struct ConvCudaExec {
+  static constexpr bool kCuda = true;
+  static void im2col(const convops::Im2colArgs& a) { check(launch_im2col(a, cur_stream()), "im2col"); }
+  static void col2im(const convops::Col2imArgs& a) { check(launch_col2im(a, cur_stream()), "col2im"); }
+  static void bn_reduce(const convops::BnReduceArgs& a) { check(launch_bn_reduce(a, cur_stream()), "bn_reduce"); }
+  static void bn_finalize(const convops::BnFinalizeArgs& a) { check(launch_bn_finalize(a, cur_stream()), "bn_finalize"); }
+  static void bn_apply(const convops::BnApplyArgs& a) { check(launch_bn_apply(a, cur_stream()), "bn_apply"); }
+  static void bn_bwd(const convops::BnBwdArgs& a) { check(launch_bn_bwd(a, cur_stream()), "bn_bwd"); }
+  static void maxpool_fwd(const convops::PoolArgs& a) { check(launch_maxpool_fwd(a, cur_stream()), "maxpool_fwd"); }
+  static void maxpool_bwd(const convops::PoolArgs& a) { check(launch_maxpool_bwd(a, cur_stream()), "maxpool_bwd"); }
+  static void avgpool_fwd(const convops::AvgPoolArgs& a) { check(launch_avgpool_fwd(a, cur_stream()), "avgpool_fwd"); }
+  static void avgpool_bwd(const convops::AvgPoolArgs& a) { check(launch_avgpool_bwd(a, cur_stream()), "avgpool_bwd"); }
+  static void pack(const convops::PackArgs& a) { check(launch_pack(a, cur_stream()), "pack"); }
+};
+
 }  // namespace
+
+#include "conv_bindings.inc"
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "colearn_federated_learning_b200 sm_100a kernels";
@@ -441,4 +459,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("enable_peer_access", &enable_peer_access);
   m.def("tensor_from_ptr", &tensor_from_ptr);
   m.def("gemm_tcgen05", &gemm_tcgen05);
+  convbind::register_ops<ConvCudaExec>(m);
 }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "conv_ops.cuh"
+
 namespace colearn {
 
 // ---------------------------------------------------------------------------------------------
@@ -212,5 +214,20 @@ struct GemmEpilogue {
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,
                                 const GemmEpilogue& ep, cudaStream_t s);
 const char* gemm_tcgen05_last_error();
+
+// ---------------------------------------------------------------------------------------------
+// NHWC convolution / BatchNorm / pooling kernels (convnet.cu; bodies + argument structs in conv_ops.cuh)
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_im2col(const convops::Im2colArgs& a, cudaStream_t s);
+cudaError_t launch_col2im(const convops::Col2imArgs& a, cudaStream_t s);
+cudaError_t launch_bn_reduce(const convops::BnReduceArgs& a, cudaStream_t s);
+cudaError_t launch_bn_finalize(const convops::BnFinalizeArgs& a, cudaStream_t s);
+cudaError_t launch_bn_apply(const convops::BnApplyArgs& a, cudaStream_t s);
+cudaError_t launch_bn_bwd(const convops::BnBwdArgs& a, cudaStream_t s);
+cudaError_t launch_maxpool_fwd(const convops::PoolArgs& a, cudaStream_t s);
+cudaError_t launch_maxpool_bwd(const convops::PoolArgs& a, cudaStream_t s);
+cudaError_t launch_avgpool_fwd(const convops::AvgPoolArgs& a, cudaStream_t s);
+cudaError_t launch_avgpool_bwd(const convops::AvgPoolArgs& a, cudaStream_t s);
+cudaError_t launch_pack(const convops::PackArgs& a, cudaStream_t s);
 
 }  // namespace colearn

@@ -1,0 +1,98 @@
+// NHWC convolution / BatchNorm / pooling kernels around the tcgen05 GEMM (ResNet-18 ops).
+// The arithmetic of every kernel is the host+device body in conv_ops.cuh; this file only maps bodies onto
+// grids: grid-stride maps (128-bit loads/stores, one work item = 8 channels) and two-phase block reductions.
+#include "colearn_kernels.h"
+
+namespace colearn {
+using namespace convops;
+
+namespace {
+constexpr int kMapThreads = 256;
+inline int map_grid(long long items) {
+  long long b = (items + kMapThreads - 1) / kMapThreads;
+  const long long cap = 148LL * 16;            // 16 resident 256-thread CTAs per SM is already more than enough
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define COLEARN_MAP_KERNEL(NAME, ARGS, ITEMS, BODY)                                              \
+  __global__ void __launch_bounds__(kMapThreads) NAME(const ARGS a) {                           \
+    const long long total = ITEMS(a);                                                            \
+    const long long stride = (long long)gridDim.x * blockDim.x;                                  \
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) \
+      BODY(a, i);                                                                                \
+  }
+
+COLEARN_MAP_KERNEL(im2col_kernel, Im2colArgs, im2col_items, im2col_body)
+COLEARN_MAP_KERNEL(col2im_kernel, Col2imArgs, col2im_items, col2im_body)
+COLEARN_MAP_KERNEL(bn_apply_kernel, BnApplyArgs, bn_apply_items, bn_apply_body)
+COLEARN_MAP_KERNEL(bn_bwd_kernel, BnBwdArgs, bn_bwd_items, bn_bwd_body)
+COLEARN_MAP_KERNEL(maxpool_fwd_kernel, PoolArgs, maxpool_fwd_items, maxpool_fwd_body)
+COLEARN_MAP_KERNEL(maxpool_bwd_kernel, PoolArgs, maxpool_bwd_items, maxpool_bwd_body)
+COLEARN_MAP_KERNEL(avgpool_fwd_kernel, AvgPoolArgs, avgpool_fwd_items, avgpool_fwd_body)
+COLEARN_MAP_KERNEL(avgpool_bwd_kernel, AvgPoolArgs, avgpool_bwd_items, avgpool_bwd_body)
+
+__device__ __forceinline__ long long pack_items(const PackArgs& a) { return a.total; }
+COLEARN_MAP_KERNEL(pack_kernel, PackArgs, pack_items, pack_body)
+
+// grid = (C/64, nseg), 256 threads
+__global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const BnReduceArgs a) {
+  __shared__ float smem[kBnSmemFloats];
+  bn_reduce_phase1(a, blockIdx.x, blockIdx.y, threadIdx.x, smem);
+  __syncthreads();
+  bn_reduce_phase2(a, blockIdx.x, blockIdx.y, threadIdx.x, smem);
+}
+__global__ void bn_finalize_kernel(const BnFinalizeArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < a.C) bn_finalize_body(a, c);
+}
+}  // namespace
+
+cudaError_t launch_im2col(const Im2colArgs& a, cudaStream_t s) {
+  im2col_kernel<<<map_grid(im2col_items(a)), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_col2im(const Col2imArgs& a, cudaStream_t s) {
+  col2im_kernel<<<map_grid(col2im_items(a)), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_reduce(const BnReduceArgs& a, cudaStream_t s) {
+  dim3 grid(a.C / kBnCols, bn_nseg(a));
+  bn_reduce_kernel<<<grid, kBnThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t s) {
+  bn_finalize_kernel<<<(a.C + 63) / 64, 64, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s) {
+  bn_apply_kernel<<<map_grid(bn_apply_items(a)), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s) {
+  bn_bwd_kernel<<<map_grid(bn_bwd_items(a)), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_maxpool_fwd(const PoolArgs& a, cudaStream_t s) {
+  maxpool_fwd_kernel<<<map_grid(maxpool_fwd_items(a)), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_maxpool_bwd(const PoolArgs& a, cudaStream_t s) {
+  maxpool_bwd_kernel<<<map_grid(maxpool_bwd_items(a)), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_avgpool_fwd(const AvgPoolArgs& a, cudaStream_t s) {
+  avgpool_fwd_kernel<<<map_grid(avgpool_fwd_items(a)), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_avgpool_bwd(const AvgPoolArgs& a, cudaStream_t s) {
+  avgpool_bwd_kernel<<<map_grid(avgpool_bwd_items(a)), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack(const PackArgs& a, cudaStream_t s) {
+  pack_kernel<<<map_grid(a.total), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace colearn

@@ -36,16 +36,16 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
         if sgd_master is not None:
             sgd_master.sub_(sgd_lr * acc)
             if sgd_shadow is not None:
-                sgd_shadow.copy_(sgd_master.to(torch.bfloat16))
+                sgd_shadow.copy_(sgd_master)
             if sgd_shadow_t is not None:
-                sgd_shadow_t.copy_(sgd_master.t().to(torch.bfloat16))
+                sgd_shadow_t.copy_(sgd_master.t())
             return
         if out_f32 is not None:
             out_f32.copy_(acc)
         if out_bf16 is not None:
-            out_bf16.copy_(acc.to(torch.bfloat16))
+            out_bf16.copy_(acc)
         if out_bf16_t is not None:
-            out_bf16_t.copy_(acc.t().to(torch.bfloat16))
+            out_bf16_t.copy_(acc.t())
         return
     _ext.require().gemm_tcgen05(a, b, bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
                                 float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(ready_flags), int(ready_epoch),
