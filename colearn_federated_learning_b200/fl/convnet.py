@@ -59,8 +59,7 @@ class _Conv:
         self.out = z(self.m, self.cout)               # post BN (+res) (+ReLU) activation
         self.mean = z(self.cout, dt=torch.float32)
         self.invstd = z(self.cout, dt=torch.float32)
-        self.rm = z(self.cout, dt=torch.float32)      # running statistics (module buffers, kept on the device)
-        self.rv = torch.ones(self.cout, device=dev)
+        self.rm = self.rv = None                      # running statistics: views handed out by the trainer
         self.wT = z(self.K_pad, self.cout)            # bf16 Wpᵀ (valid rows only) for the dgrad
         self.dz = z(self.m, self.cout)                # gradient w.r.t. the conv output
 
@@ -91,6 +90,7 @@ class ConvNetTrainer:
             if len(cls._cache) > 2:
                 cls._cache.clear()
             tr = cls._cache[key] = cls(model, flat.device, batch_size, hw)
+            tr.bind_buffers(model)
         return tr
 
     def __init__(self, model: ResNet18, device, batch_size: int, hw: Tuple[int, int] = (32, 32),
@@ -159,6 +159,19 @@ class ConvNetTrainer:
         # ---- buffers ------------------------------------------------------------------------------------------
         for cv in self.convs:
             cv.alloc(dev, act_dtype)
+        # BatchNorm buffers of every layer in three flat tensors; bind_buffers() can alias the module's buffers onto
+        # them so the kernels update the module in place and a fit needs no buffer copies
+        tot_c = sum(cv.cout for cv in self.convs)
+        self.running_mean = torch.zeros(tot_c, device=dev)
+        self.running_var = torch.ones(tot_c, device=dev)
+        self.batches_tracked = torch.zeros(len(self.convs), device=dev, dtype=torch.long)
+        off = 0
+        for cv in self.convs:
+            cv.rm, cv.rv = self.running_mean[off:off + cv.cout], self.running_var[off:off + cv.cout]
+            off += cv.cout
+        self._bound: Optional[nn.Module] = None
+        self._graph = None
+        self._graph_key = None
         z = lambda *s, dt=act_dtype: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
         max_colT = max(cv.m * cv.K_pad for cv in self.convs)
         max_dzT = max(cv.m * cv.cout_pad for cv in self.convs)
@@ -185,7 +198,8 @@ class ConvNetTrainer:
         self.dlogT = z(self.nc_pad, B)
         self.fc_wT = z(self.feat_dim, self.nc_pad)
         self.launches = 0
-        self.steps_done = 0
+        self.steps_done = 0                            # since the last store() (BatchNorm num_batches_tracked)
+        self.steps_total = 0
 
     # -- parameter views ------------------------------------------------------------------------------------------
     def _w(self, e: C.PackEntry) -> torch.Tensor:
@@ -198,14 +212,31 @@ class ConvNetTrainer:
         e = self._small_by_name[name]
         return (self.spk if buf is None else buf)[e.dst_off:e.dst_off + e.numel_pad]
 
+    def bind_buffers(self, model: ResNet18) -> bool:
+        """Alias the module's BatchNorm buffers onto this trainer's flat statistics tensors (zero-copy, like
+        ``alias_params_to_arena`` for parameters).  Only possible when the module lives on the trainer's device."""
+        mods = dict(model.named_modules())
+        if any(mods[cv.bn_name].running_mean.device != self.running_mean.device for cv in self.convs):
+            return False
+        with torch.no_grad():
+            for i, cv in enumerate(self.convs):
+                bn = mods[cv.bn_name]
+                cv.rm.copy_(bn.running_mean)
+                cv.rv.copy_(bn.running_var)
+                self.batches_tracked[i] = bn.num_batches_tracked
+                bn.running_mean.data, bn.running_var.data = cv.rm, cv.rv
+                bn.num_batches_tracked.data = self.batches_tracked[i]
+        self._bound = model
+        return True
+
     def load(self, flat: torch.Tensor, model: Optional[ResNet18] = None) -> None:
-        """Flat arena (and the module's BatchNorm buffers) → packed device state."""
+        """Flat arena (and the module's BatchNorm buffers, unless bound) → packed device state."""
         C.pack_params(flat, self.mpk, self.wpk, self.big)
         C.pack_params(flat, self.spk, None, self.small)
         for cv in self.convs:
             ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
         ops.transpose_bf16(self._w(self.fc_entry), self.fc_wT)
-        if model is not None:
+        if model is not None and model is not self._bound:
             mods = dict(model.named_modules())
             for cv in self.convs:
                 bn = mods[cv.bn_name]
@@ -214,10 +245,12 @@ class ConvNetTrainer:
         self.launches += 3 + len(self.convs)
 
     def store(self, flat: torch.Tensor, model: Optional[ResNet18] = None) -> None:
-        """Packed device state → flat arena (and the module's BatchNorm buffers)."""
+        """Packed device state → flat arena (and the module's BatchNorm buffers, unless bound)."""
         C.pack_params(flat, self.mpk, None, self.big, unpack=True)
         C.pack_params(flat, self.spk, None, self.small, unpack=True)
-        if model is not None:
+        if model is not None and model is self._bound:
+            self.batches_tracked += self.steps_done
+        elif model is not None:
             mods = dict(model.named_modules())
             with torch.no_grad():
                 for cv in self.convs:
@@ -226,7 +259,7 @@ class ConvNetTrainer:
                     bn.running_var.copy_(cv.rv)
                     bn.num_batches_tracked += self.steps_done
         self.steps_done = 0
-        self.launches += 2
+        self.launches += 3
 
     # -- forward ------------------------------------------------------------------------------------------------------
     def _conv_bn(self, cv: _Conv, x4: torch.Tensor, res: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
@@ -314,6 +347,7 @@ class ConvNetTrainer:
         ops.sgd_step(self.spk, self.gsp, lr)                         # every gamma / beta / fc bias in one launch
         self.launches += 2
         self.steps_done += 1
+        self.steps_total += 1
 
     def step(self, xb: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
         loss = self.forward(xb, labels)
@@ -321,10 +355,40 @@ class ConvNetTrainer:
         return loss
 
     # -- a whole local fit -------------------------------------------------------------------------------------------------------
-    def fit(self, flat: torch.Tensor, model: ResNet18, x: torch.Tensor, y: torch.Tensor, cfg, perm: Optional[torch.Tensor]) -> torch.Tensor:
-        """Local SGD in place on ``flat`` (full batches only; a tail < batch_size is dropped, like the layer-wise
-        MLP trainer)."""
+    # -- CUDA graph of one SGD step (~320 launches -> one replay) ------------------------------------------------------------
+    def _graph_step(self, xb: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
+        """Replay the captured step on a new batch.  The first step of a trainer's life runs eagerly (driver entry
+        points, allocator pools), the second one is captured; a different lr or input dtype re-captures."""
+        key = (float(lr), xb.dtype, tuple(xb.shape))
+        if self._graph is None or self._graph_key != key:
+            if self.steps_total == 0:
+                return self.step(xb, labels, lr)
+            self.g_x, self.g_y = torch.zeros_like(xb), torch.zeros_like(labels)
+            self.g_loss = torch.zeros((), device=self.dev)
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            launches, steps = self.launches, self.steps_done
+            with torch.cuda.graph(graph):
+                self.g_loss.copy_(self.step(self.g_x, self.g_y, lr))
+            self.launches, self.steps_done = launches, steps           # capture executed nothing
+            self.steps_total -= 1
+            self._graph, self._graph_key = graph, key
+        self.g_x.copy_(xb)
+        self.g_y.copy_(labels)
+        self._graph.replay()
+        self.launches += 3
+        self.steps_done += 1
+        self.steps_total += 1
+        return self.g_loss
+
+    def fit(self, flat: torch.Tensor, model: ResNet18, x: torch.Tensor, y: torch.Tensor, cfg, perm: Optional[torch.Tensor],
+            use_graph: Optional[bool] = None) -> torch.Tensor:
+        """Local SGD in place on ``flat`` (full batches; ``supports`` rejects ragged shards).  On a GPU every step
+        after the trainer's first is one CUDA-graph replay."""
         n, B = x.shape[0], self.B
+        if use_graph is None:
+            use_graph = flat.is_cuda
+        step = self._graph_step if use_graph else self.step
         self.load(flat, model)
         labels_all = y.reshape(-1).long()
         limit = cfg.max_nr_batches if cfg.max_nr_batches and cfg.max_nr_batches > 0 else None
@@ -335,7 +399,7 @@ class ConvNetTrainer:
             order = perm[e % perm.shape[0]].long() if perm is not None else torch.arange(n, device=flat.device)
             for lo in range(0, n - B + 1, B):
                 idx = order[lo:lo + B]
-                last = self.step(x.index_select(0, idx), labels_all.index_select(0, idx), cfg.lr)
+                last = step(x.index_select(0, idx), labels_all.index_select(0, idx), cfg.lr)
                 it += 1
                 if limit is not None and it >= limit:
                     done = True

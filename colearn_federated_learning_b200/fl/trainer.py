@@ -56,6 +56,10 @@ class FitConfig:
 # only runs when asked for explicitly.
 CONV_PATH_DEFAULT = "torch"
 
+# kernels of THIS repo launched by the most recent local_fit (library kernels of the torch path are not counted);
+# the engine adds it to RoundReport.launches
+LAST_FIT_LAUNCHES = 0
+
 
 def conv_path(device) -> str:
     env = os.environ.get("COLEARN_CONV_PATH", "").strip().lower()
@@ -125,6 +129,8 @@ def torch_fit(model: nn.Module, x: torch.Tensor, y: torch.Tensor, cfg: FitConfig
 def local_fit(flat: torch.Tensor, model: nn.Module, x: torch.Tensor, y: torch.Tensor, cfg: FitConfig,
               round_idx: int = 0, perm: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, str]:
     """Run the local fit **in place on ``flat``**; returns (last loss, path used)."""
+    global LAST_FIT_LAUNCHES
+    LAST_FIT_LAUNCHES = 0
     loss = resolve_loss(cfg.model, cfg.loss)
     cfg = FitConfig(**{**cfg.to_dict(), "loss": loss})
     if perm is None:
@@ -136,17 +142,24 @@ def local_fit(flat: torch.Tensor, model: nn.Module, x: torch.Tensor, y: torch.Te
         if not flat.is_cuda or has_kernel:
             last = ops.mlp_local_sgd(flat, spec.dims, xx, y, perm, cfg.batch_size, cfg.lr, cfg.epochs,
                                      cfg.max_nr_batches, loss, spec.out_activation)
+            LAST_FIT_LAUNCHES = 1 if flat.is_cuda else 0
             return last, ("persistent" if flat.is_cuda else "reference")
         if flat.is_cuda:
             from .layerwise import LayerwiseMLPTrainer
             if LayerwiseMLPTrainer.supports(spec, cfg):
                 tr = LayerwiseMLPTrainer.cached(spec, flat, cfg.batch_size)
-                return tr.fit(flat, xx, y, cfg, perm), "layerwise"
+                before = tr.launches
+                last = tr.fit(flat, xx, y, cfg, perm)
+                LAST_FIT_LAUNCHES = tr.launches - before
+                return last, "layerwise"
     if conv_path(flat.device) == "native":
         from .convnet import ConvNetTrainer
         if ConvNetTrainer.supports(model, cfg, x):
             tr = ConvNetTrainer.cached(model, flat, cfg.batch_size, tuple(x.shape[2:]))
-            return tr.fit(flat, model, x, y, cfg, perm), "convnet"
+            before = tr.launches
+            last = tr.fit(flat, model, x, y, cfg, perm)
+            LAST_FIT_LAUNCHES = tr.launches - before
+            return last, "convnet"
     unflatten_params(model, flat)
     last = torch_fit(model, x, y, cfg, perm, autocast_bf16=flat.is_cuda)
     flatten_params(model, out=flat)

@@ -390,7 +390,8 @@ class FederatedEngine:
             if epoch > 1:
                 self.ext.wait_flags(self.arena.ptr("chunk_flags"), self.n_chunks, epoch - 1)
             last, path = local_fit(flat, self.model, self.x, self.y, FitConfig(**{**self.cfg.to_dict()}), round_idx)
-            self._last_path = path
+            from ..fl import trainer as _trainer
+            self._last_path, self._train_launches = path, _trainer.LAST_FIT_LAUNCHES
             return last
         from ..fl.layerwise import ReadySpec
         from ..fl.trainer import make_perm
@@ -411,6 +412,7 @@ class FederatedEngine:
             self.ext.set_flag(self.epoch_dev.data_ptr(), epoch - 1)
             last = lw.run_round_graph(perm, n)
             self._last_path = "layerwise+fused_bcast+cuda_graph"
+            self._train_launches = 3                     # epoch flag, sample order copy, graph replay
             return last
         ready = ReadySpec(cf_ptr, self.chunk_elems, epoch - 1) if fused else None
 
@@ -424,8 +426,10 @@ class FederatedEngine:
 
         if not fused:
             wait_chunks(None)
+        before = lw.launches
         last = lw.fit(flat, xs, self.y, self.cfg, perm, ready, wait_chunks)
         self._last_path = "layerwise+fused_bcast" if fused else "layerwise"
+        self._train_launches = lw.launches - before
         return last
 
     def _run_twoshot(self, rounds: int, masks: List[int], host_inputs, read_back: bool) -> RoundReport:
@@ -457,8 +461,11 @@ class FederatedEngine:
                 self.x.copy_(hx, non_blocking=True)
                 self.y.copy_(hy.view(-1, 1), non_blocking=True)
             if (masks[i] >> r) & 1:
+                self._train_launches = 0
                 last = self._local_train_inplace(self.rounds_done + i, e)
                 losses_log[i, r, 0] = last
+                losses_log[i, r, 1] = last
+                launches += self._train_launches
             elif e > 1:
                 ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e - 1)
             wts = self._round_weights(masks[i])

@@ -146,7 +146,10 @@ def test_eval_argmax_minmax_perm_convert():
                                                   (128, 256, 128, 256, 1), (384, 512, 320, 256, 1), (1024, 4096, 4096, 128, 0),
                                                   (256, 256, 64, 256, 2), (512, 768, 448, 256, 2), (2048, 4096, 1024, 256, 2),
                                                   (1024, 4096, 4096, 256, 1),
-                                                  (256, 256, 64, 256, 3), (512, 768, 448, 256, 3), (1024, 4096, 4096, 256, 3)])
+                                                  (256, 256, 64, 256, 3), (512, 768, 448, 256, 3), (1024, 4096, 4096, 256, 3),
+                                                  # the ResNet-18 conv shapes (fl/convnet.py): stem fwd / wgrad, layer1 dgrad / wgrad
+                                                  (32768, 128, 256, 0, 0), (128, 256, 32768, 0, 0), (8192, 640, 64, 0, 0),
+                                                  (128, 640, 8192, 0, 0), (128, 4608, 128, 0, 0)])
 def test_gemm_tcgen05_plain(m, n, k, tile_n, cluster):
     dev = _dev()
     torch.manual_seed(6)
