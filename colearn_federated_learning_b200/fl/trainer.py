@@ -54,7 +54,7 @@ class FitConfig:
 # Which executor trains conv nets on a GPU: "native" = fl/convnet.py (this repo's kernels), "torch" = autograd over
 # cuDNN/ATen.  ``COLEARN_CONV_PATH`` overrides; on CPU tensors the native path (PyTorch definitions of the same ops)
 # only runs when asked for explicitly.
-CONV_PATH_DEFAULT = "torch"
+CONV_PATH_DEFAULT = "native"
 
 # kernels of THIS repo launched by the most recent local_fit (library kernels of the torch path are not counted);
 # the engine adds it to RoundReport.launches

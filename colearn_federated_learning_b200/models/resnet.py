@@ -3,11 +3,12 @@
 Not present in the reference.  Structure and state-dict keys follow the
 canonical ImageNet ResNet-18 (7x7 stem, max-pool, 4 stages of 2 BasicBlocks, global avg-pool,
 fc) so that with ``num_classes=10`` the parameter count is the 11 181 642 (+9 620 BN buffers)
-quoted in SURVEY §2.5.  Convolutions / BatchNorm run through cuDNN/ATen (library code); the
-federated part — flat-arena broadcast, FedAvg reduce/apply, SGD, loss — runs through this
-repo's kernels.  BN running statistics are buffers and are *not* averaged by default, which is
-the reference FedAvg semantics (parameters only); ``average_buffers=True`` on the
-engine opts in.
+quoted in SURVEY §2.5.  This module is the architecture + state-dict definition (and the CPU /
+eval path); local training on a GPU runs through ``fl/convnet.py`` — im2col + tcgen05 GEMMs +
+this repo's BatchNorm / pooling kernels — and the federated part (flat-arena broadcast, FedAvg
+reduce/apply, SGD, loss) through the comm / elementwise kernels.  BN running statistics are
+buffers and are *not* averaged by default, which is the reference FedAvg semantics (parameters
+only); ``average_buffers=True`` on the engine opts in.
 """
 from __future__ import annotations
 

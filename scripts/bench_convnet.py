@@ -58,7 +58,9 @@ def main():
         ms = timed(fn)
         out[name] = {"ms_per_fit": ms, "ms_per_step": ms / steps}
         if env == "native":
-            out[name]["launches_per_step_eager"] = 330
+            before = tr.launches
+            fn()
+            out[name]["launches_per_fit"] = tr.launches - before
         loss, _ = (fn() if env == "torch" else (fn(), None))
         out[name]["last_loss"] = float(loss)
     print(json.dumps(out))
