@@ -292,6 +292,47 @@ class ConvNetTrainer:
         self.launches += 8
         return loss
 
+    # -- inference (eval mode: BatchNorm uses the running statistics) -------------------------------------------------------
+    @torch.no_grad()
+    def infer(self, x: torch.Tensor) -> torch.Tensor:
+        """Eval-mode logits ``[n, num_classes]`` (fp32) for ``x`` ``[n, Cin, H, W]`` with the currently loaded
+        parameters (call :meth:`load` first).  Runs in chunks of the trainer's batch size; the last chunk is zero
+        padded (eval-mode BatchNorm has no cross-sample coupling, so padding rows do not disturb real rows)."""
+        B, n = self.B, x.shape[0]
+        inv_all = torch.rsqrt(self.running_var + self.stem.eps)
+        out = torch.empty(n, self.num_classes, device=self.dev)
+        off, invs = 0, {}
+        for cv in self.convs:
+            invs[cv.name] = inv_all[off:off + cv.cout]
+            off += cv.cout
+
+        def conv_bn(cv: _Conv, x4, res, relu):
+            C.im2col(x4, cv.col, cv.k, cv.k, cv.stride, cv.pad)
+            ops.gemm_bf16(cv.col, self._w(cv.entry), out_bf16=cv.z)
+            C.bn_apply(cv.z, cv.cout, cv.rm, invs[cv.name], self._s(cv.bn_name + ".weight"), self._s(cv.bn_name + ".bias"),
+                       res, relu, cv.out)
+            return cv.out
+
+        for lo in range(0, n, B):
+            xb = x[lo:lo + B]
+            if xb.shape[0] < B:
+                xb = torch.cat([xb, xb.new_zeros(B - xb.shape[0], *xb.shape[1:])])
+            st = self.stem
+            a = conv_bn(st, xb.contiguous(), None, True)
+            C.maxpool_fwd(a, self.pool_y, self.pool_idx, B, st.oh, st.ow, st.cout, self.pool_k, self.pool_k, self.pool_s, self.pool_p)
+            a = self.pool_y
+            for b in self.blocks:
+                c1, c2 = b.c1, b.c2
+                x4 = C.nhwc_view(a, B, c1.h, c1.w, c1.cin)
+                identity = a if b.ds is None else conv_bn(b.ds, x4, None, False)
+                mid = conv_bn(c1, x4, None, True)
+                a = conv_bn(c2, C.nhwc_view(mid, B, c2.h, c2.w, c2.cin), identity, True)
+            C.avgpool_fwd(a, self.feat, B, self.final_hw, self.feat_dim)
+            ops.gemm_bf16(self.feat, self._w(self.fc_entry), bias=self._s("fc.bias"), out_f32=self.logits)
+            k = min(B, n - lo)
+            out[lo:lo + k].copy_(self.logits[:k, : self.num_classes])
+        return out
+
     # -- backward (+ SGD) ---------------------------------------------------------------------------------------------------
     def _bn_bwd(self, cv: _Conv, dy: torch.Tensor, masked: bool, g_out: Optional[torch.Tensor]) -> None:
         C.bn_backward(cv.z, cv.cout, dy, cv.out if masked else None, cv.mean, cv.invstd, self._s(cv.bn_name + ".weight"),

@@ -23,6 +23,15 @@ def forward_flat(model: nn.Module, flat: Optional[torch.Tensor], x: torch.Tensor
         xx = x.view(x.shape[0], -1) if spec.flatten_input else x
         if not flat.is_cuda or ops.net_kind_for(spec.dims, spec.out_activation) is not None:
             return ops.mlp_forward(flat, spec.dims, xx.to(flat.device), spec.out_activation)
+    if flat is not None and flat.is_cuda and x.dim() == 4:
+        # conv nets on a GPU: eval-mode forward on this repo's kernels (fl/convnet.py), batch 128 chunks
+        from .convnet import ConvNetTrainer
+        from .trainer import conv_path
+        from ..models.resnet import ResNet18
+        if isinstance(model, ResNet18) and conv_path(flat.device) == "native" and x.shape[2] >= 32 and x.shape[3] >= 32:
+            tr = ConvNetTrainer.cached(model, flat, 128, tuple(x.shape[2:]))
+            tr.load(flat, model)
+            return tr.infer(x.to(flat.device))
     model.eval()
     return model(x)
 

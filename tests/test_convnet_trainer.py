@@ -62,6 +62,33 @@ def test_fp32_oracle_step_equals_autograd():
             assert int(m.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("mode", ["fp32", "definitions", "emulated"])
+def test_eval_mode_inference_matches_module_eval(mode):
+    """``infer``: eval-mode forward (running statistics) in chunks of 128 with a zero-padded last chunk."""
+    torch.manual_seed(3)
+    model = ResNet18(10)
+    with torch.no_grad():                                 # non-trivial running statistics
+        for m in model.modules():
+            if hasattr(m, "running_mean"):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(B + 37, 3, 32, 32)
+    model.eval()
+    with torch.no_grad():
+        want = model(x)
+    flat = flatten_params(model).clone()
+    tr = ConvNetTrainer(model, "cpu", B, (32, 32), act_dtype=torch.float32 if mode == "fp32" else torch.bfloat16)
+    with (conv.emulated() if mode == "emulated" else contextlib.nullcontext()):
+        tr.load(flat, model)
+        got = tr.infer(x)
+    assert got.shape == want.shape
+    if mode == "fp32":
+        torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-3)
+    else:
+        assert float((got - want).abs().max()) < 0.15 * float(want.abs().max()) + 0.05
+        assert float((got.argmax(1) == want.argmax(1)).float().mean()) > 0.9
+
+
 @pytest.mark.parametrize("mode", ["definitions", "emulated"])
 def test_bf16_step_is_as_close_to_fp32_autograd_as_autocast_is(mode):
     """bf16 activations on a random-init ResNet-18 with 1x1 final feature maps are noisy (torch's own autocast path
