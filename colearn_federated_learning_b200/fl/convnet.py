@@ -19,6 +19,7 @@ fp32 statistics and parameters).  No reference counterpart: the reference has no
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -170,6 +171,12 @@ class ConvNetTrainer:
             cv.rm, cv.rv = self.running_mean[off:off + cv.cout], self.running_var[off:off + cv.cout]
             off += cv.cout
         self._bound: Optional[nn.Module] = None
+        # opt-in (not yet measured on a B200): wgrad chains on a second stream, see _conv_bwd
+        self._side = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and os.environ.get("COLEARN_CONV_STREAMS") == "1") else None
+        self._fuse_shadow_t = os.environ.get("COLEARN_CONV_SHADOW_T") == "1"
+        # opt-in: BatchNorm reduction + finalize in one launch (ticket counter, last block finalises)
+        self.bn_counters = (torch.zeros(max(cv.cout for cv in self.convs) // 64, device=dev, dtype=torch.int32)
+                            if os.environ.get("COLEARN_CONV_FUSED_BN") == "1" and act_dtype == BF else None)
         self._graph = None
         self._graph_key = None
         z = lambda *s, dt=act_dtype: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
@@ -265,7 +272,7 @@ class ConvNetTrainer:
     def _conv_bn(self, cv: _Conv, x4: torch.Tensor, res: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
         C.im2col(x4, cv.col, cv.k, cv.k, cv.stride, cv.pad)
         ops.gemm_bf16(cv.col, self._w(cv.entry), out_bf16=cv.z)
-        C.bn_stats(cv.z, cv.cout, self.partial, cv.mean, cv.invstd, cv.rm, cv.rv, cv.eps, cv.momentum)
+        C.bn_stats(cv.z, cv.cout, self.partial, cv.mean, cv.invstd, cv.rm, cv.rv, cv.eps, cv.momentum, self.bn_counters)
         C.bn_apply(cv.z, cv.cout, cv.mean, cv.invstd, self._s(cv.bn_name + ".weight"), self._s(cv.bn_name + ".bias"),
                    res, relu, cv.out)
         self.launches += 5
@@ -337,28 +344,68 @@ class ConvNetTrainer:
     def _bn_bwd(self, cv: _Conv, dy: torch.Tensor, masked: bool, g_out: Optional[torch.Tensor]) -> None:
         C.bn_backward(cv.z, cv.cout, dy, cv.out if masked else None, cv.mean, cv.invstd, self._s(cv.bn_name + ".weight"),
                       self.partial, self._s(cv.bn_name + ".weight", self.gsp), self._s(cv.bn_name + ".bias", self.gsp),
-                      cv.dz, g_out)
+                      cv.dz, g_out, self.bn_counters)
         self.launches += 3
 
-    def _conv_bwd(self, cv: _Conv, lr: float, dx: Optional[torch.Tensor], add: Optional[torch.Tensor]) -> None:
-        """dgrad with the old weights (→ ``dx`` through the col2im gather), then the fused wgrad + SGD."""
-        if dx is not None:
-            dcol = self.dcol[: cv.m * cv.K_pad].view(cv.m, cv.K_pad)
-            ops.gemm_bf16(cv.dz, cv.wT, out_bf16=dcol)
-            C.col2im(dcol, dx, add, cv.n, cv.h, cv.w, cv.cin, cv.k, cv.k, cv.stride, cv.pad)
-            self.launches += 2
+    def _dgrad(self, cv: _Conv, dx: torch.Tensor, add: Optional[torch.Tensor]) -> None:
+        dcol = self.dcol[: cv.m * cv.K_pad].view(cv.m, cv.K_pad)
+        ops.gemm_bf16(cv.dz, cv.wT, out_bf16=dcol)
+        C.col2im(dcol, dx, add, cv.n, cv.h, cv.w, cv.cin, cv.k, cv.k, cv.stride, cv.pad)
+        self.launches += 2
+
+    def _wgrad(self, cv: _Conv, lr: float, shadow_t: bool = False) -> None:
         dzT = self.dzT[: cv.cout_pad * cv.m].view(cv.cout_pad, cv.m)
         if cv.cout_pad != cv.cout:
             dzT[cv.cout:].zero_()
         ops.transpose_bf16(cv.dz, dzT[: cv.cout])
         colT = self.colT[: cv.K_pad * cv.m].view(cv.K_pad, cv.m)
         ops.transpose_bf16(cv.col, colT)
-        ops.gemm_bf16(dzT, colT, sgd_master=self._m(cv.entry), sgd_lr=lr, sgd_shadow=self._w(cv.entry))
-        ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
-        self.launches += 4
+        ops.gemm_bf16(dzT, colT, sgd_master=self._m(cv.entry), sgd_lr=lr, sgd_shadow=self._w(cv.entry),
+                      sgd_shadow_t=cv.wT if shadow_t else None)
+        self.launches += 3
+
+    def _conv_bwd(self, cv: _Conv, lr: float, dx: Optional[torch.Tensor], add: Optional[torch.Tensor]) -> None:
+        """dgrad with the old weights (→ ``dx`` through the col2im gather), then the fused wgrad + SGD.
+
+        With a side stream (``COLEARN_CONV_STREAMS=1``) the wgrad chain (two transposes, GEMM + fused SGD, Wᵀ
+        refresh) leaves the critical path: it only needs ``dz`` (event after the BatchNorm backward) and may
+        overwrite ``wT`` only once the dgrad GEMM that reads the old weights is done (second event); its scratch
+        (``dzT`` / ``colT``) is touched by the side stream alone, ``dcol`` / ``partial`` by the main stream alone."""
+        side = self._side
+        # Wᵀ straight from the wgrad epilogue (``sgd_shadow_t``) when the layer needs no row padding
+        fuse_t = self._fuse_shadow_t and cv.cout_pad == cv.cout
+        if side is None:
+            if dx is not None:
+                self._dgrad(cv, dx, add)
+            self._wgrad(cv, lr, fuse_t)
+            if not fuse_t:
+                ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
+                self.launches += 1
+            return
+        main = torch.cuda.current_stream(self.dev)
+        ev_dz = torch.cuda.Event()
+        ev_dz.record(main)
+        ev_dgrad = None
+        if dx is not None:
+            self._dgrad(cv, dx, add)
+            ev_dgrad = torch.cuda.Event()
+            ev_dgrad.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_dz)
+            if fuse_t and ev_dgrad is not None:
+                side.wait_event(ev_dgrad)                # the epilogue itself overwrites wT
+            self._wgrad(cv, lr, fuse_t)
+            if not fuse_t:
+                if ev_dgrad is not None:
+                    side.wait_event(ev_dgrad)
+                ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
+                self.launches += 1
 
     def backward(self, lr: float) -> None:
         B = self.B
+        side = self._side
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(self.dev))    # fork (also what makes it capturable)
         # classifier: dgrad first (old weights), then the fused update
         ops.gemm_bf16(self.dlog, self.fc_wT, out_bf16=self.d_feat)
         ops.transpose_bf16(self.dlog, self.dlogT)
@@ -385,6 +432,8 @@ class ConvNetTrainer:
         C.maxpool_bwd(d_out, self.pool_idx, self.d_stem, B, st.oh, st.ow, st.cout, self.pool_k, self.pool_k, self.pool_s, self.pool_p)
         self._bn_bwd(st, self.d_stem, True, None)
         self._conv_bwd(st, lr, None, None)
+        if side is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(side)    # join: the next forward reads the new shadows
         ops.sgd_step(self.spk, self.gsp, lr)                         # every gamma / beta / fc bias in one launch
         self.launches += 2
         self.steps_done += 1

@@ -124,12 +124,14 @@ def bn_partial_numel(m: int, c: int) -> int:
 
 def bn_stats(x: torch.Tensor, c: int, partial: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor,
              running_mean: Optional[torch.Tensor] = None, running_var: Optional[torch.Tensor] = None,
-             eps: float = 1e-5, momentum: float = 0.1) -> None:
+             eps: float = 1e-5, momentum: float = 0.1, counters: Optional[torch.Tensor] = None) -> None:
     """Per-channel batch mean and ``1/sqrt(var + eps)`` (biased variance) of ``x[:, :c]`` (bf16 ``[M, ldx]``);
-    running statistics updated in place with torch semantics (unbiased variance, ``momentum``)."""
+    running statistics updated in place with torch semantics (unbiased variance, ``momentum``).  ``counters``
+    (int32 ``[c/64]``, zero before the first use, self-resetting) selects the single-launch reduction whose last
+    block finalises."""
     mod = _native(x)
     if mod is not None:
-        mod.bn_stats(x, c, partial, mean, invstd, running_mean, running_var, float(eps), float(momentum))
+        mod.bn_stats(x, c, partial, mean, invstd, running_mean, running_var, float(eps), float(momentum), counters)
         return
     xf = x[:, :c].float()
     m = xf.shape[0]
@@ -161,14 +163,14 @@ def bn_apply(x: torch.Tensor, c: int, mean: torch.Tensor, invstd: torch.Tensor, 
 
 def bn_backward(x: torch.Tensor, c: int, dy: torch.Tensor, out: Optional[torch.Tensor], mean: torch.Tensor,
                 invstd: torch.Tensor, gamma: torch.Tensor, partial: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
-                dx: torch.Tensor, g_out: Optional[torch.Tensor] = None) -> None:
+                dx: torch.Tensor, g_out: Optional[torch.Tensor] = None, counters: Optional[torch.Tensor] = None) -> None:
     """BatchNorm backward.  With ``out`` (the layer's post-ReLU output) the upstream gradient is masked first
     (``g = dy * (out > 0)``; optionally written to ``g_out`` for the identity branch of a residual block).
 
     ``dbeta = Σ g``, ``dgamma = Σ g·x̂``, ``dx = γ·invstd·(g − dbeta/M − x̂·dgamma/M)``."""
     mod = _native(x)
     if mod is not None:
-        mod.bn_backward(x, c, dy, out, mean, invstd, gamma, partial, dgamma, dbeta, dx, g_out)
+        mod.bn_backward(x, c, dy, out, mean, invstd, gamma, partial, dgamma, dbeta, dx, g_out, counters)
         return
     m = x.shape[0]
     g = dy[:m].float()

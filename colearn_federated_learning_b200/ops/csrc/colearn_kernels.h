@@ -222,6 +222,7 @@ cudaError_t launch_im2col(const convops::Im2colArgs& a, cudaStream_t s);
 cudaError_t launch_col2im(const convops::Col2imArgs& a, cudaStream_t s);
 cudaError_t launch_bn_reduce(const convops::BnReduceArgs& a, cudaStream_t s);
 cudaError_t launch_bn_finalize(const convops::BnFinalizeArgs& a, cudaStream_t s);
+cudaError_t launch_bn_reduce_finalize(const convops::BnFusedArgs& a, cudaStream_t s);
 cudaError_t launch_bn_apply(const convops::BnApplyArgs& a, cudaStream_t s);
 cudaError_t launch_bn_bwd(const convops::BnBwdArgs& a, cudaStream_t s);
 cudaError_t launch_maxpool_fwd(const convops::PoolArgs& a, cudaStream_t s);

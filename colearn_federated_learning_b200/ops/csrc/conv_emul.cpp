@@ -34,7 +34,21 @@ struct ConvHostExec {
       }
   }
   static void bn_finalize(const BnFinalizeArgs& a) {
-    for (int c = 0; c < a.C; ++c) bn_finalize_body(a, c);
+    for (int c = 0; c < a.C; ++c) bn_finalize_body<false>(a, c);
+  }
+  // blocks run one after the other here, so "the last ticket" is simply the last block of each column group
+  static void bn_reduce_finalize(const BnFusedArgs& a) {
+    std::vector<float> smem(kBnSmemFloats);
+    const int nseg = bn_nseg(a.r);
+    for (int by = 0; by < nseg; ++by)
+      for (int bx = 0; bx < a.r.C / kBnCols; ++bx) {
+        for (int tid = 0; tid < kBnThreads; ++tid) bn_reduce_phase1(a.r, bx, by, tid, smem.data());
+        for (int tid = 0; tid < kBnThreads; ++tid) bn_reduce_phase2(a.r, bx, by, tid, smem.data());
+        if (++a.counters[bx] == (unsigned)nseg) {
+          for (int tid = 0; tid < kBnThreads; ++tid) bn_fused_phase3(a, bx, tid);
+          a.counters[bx] = 0;
+        }
+      }
   }
   static void bn_apply(const BnApplyArgs& a) { run_map(a, bn_apply_items, bn_apply_body); }
   static void bn_bwd(const BnBwdArgs& a) { run_map(a, bn_bwd_items, bn_bwd_body); }

@@ -21,6 +21,12 @@
 #else
 #define CL_HD inline
 #endif
+// L2-coherent load (skips L1): used where one CTA reads what other CTAs of the same launch just wrote
+#if defined(__CUDA_ARCH__)
+#define CL_LD_CG(p) __ldcg(p)
+#else
+#define CL_LD_CG(p) (*(p))
+#endif
 
 namespace colearn {
 namespace convops {
@@ -216,11 +222,14 @@ struct BnFinalizeArgs {
   float* dgamma;                // mode 1 outputs
   float* dbeta;
 };
+template <bool kCoherent = false>
 CL_HD void bn_finalize_body(const BnFinalizeArgs& a, int c) {
   double s1 = 0.0, s2 = 0.0;
   for (int s = 0; s < a.nseg; ++s) {
-    s1 += (double)a.partial[((long long)s * 2 + 0) * a.C + c];
-    s2 += (double)a.partial[((long long)s * 2 + 1) * a.C + c];
+    const float* p1 = a.partial + ((long long)s * 2 + 0) * a.C + c;
+    const float* p2 = a.partial + ((long long)s * 2 + 1) * a.C + c;
+    s1 += (double)(kCoherent ? CL_LD_CG(p1) : *p1);
+    s2 += (double)(kCoherent ? CL_LD_CG(p2) : *p2);
   }
   if (a.mode == 0) {
     const double mean = s1 / a.M;
@@ -237,6 +246,18 @@ CL_HD void bn_finalize_body(const BnFinalizeArgs& a, int c) {
     a.dbeta[c] = (float)s1;
     a.dgamma[c] = (float)s2;
   }
+}
+
+// Reduction + finalize in ONE launch: every block bumps a per-column-group counter after publishing its partial;
+// the block that observes the last ticket finalises that group's 64 channels (threadfence-reduction pattern) and
+// resets the counter, so the buffer is reusable without a memset.
+struct BnFusedArgs {
+  BnReduceArgs r;
+  BnFinalizeArgs f;
+  unsigned int* counters;       // [C / 64], zero before the first use
+};
+CL_HD void bn_fused_phase3(const BnFusedArgs& a, int bx, int tid) {
+  if (tid < kBnCols) bn_finalize_body<true>(a.f, bx * kBnCols + tid);
 }
 
 // out = relu?( (x - mean) * invstd * gamma + beta (+ res) )

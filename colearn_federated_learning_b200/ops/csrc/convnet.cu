@@ -45,7 +45,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const BnReduceArg
 }
 __global__ void bn_finalize_kernel(const BnFinalizeArgs a) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < a.C) bn_finalize_body(a, c);
+  if (c < a.C) bn_finalize_body<false>(a, c);
+}
+// reduction + finalize fused: the last block of each column group (ticket counter) finalises it
+__global__ void __launch_bounds__(kBnThreads) bn_reduce_finalize_kernel(const BnFusedArgs a) {
+  __shared__ float smem[kBnSmemFloats];
+  __shared__ int s_last;
+  bn_reduce_phase1(a.r, blockIdx.x, blockIdx.y, threadIdx.x, smem);
+  __syncthreads();
+  bn_reduce_phase2(a.r, blockIdx.x, blockIdx.y, threadIdx.x, smem);
+  __threadfence();                 // partials of this block visible device-wide before the ticket
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&a.counters[blockIdx.x], 1u) == gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    bn_fused_phase3(a, blockIdx.x, threadIdx.x);
+    if (threadIdx.x == 0) a.counters[blockIdx.x] = 0;
+  }
 }
 }  // namespace
 
@@ -60,6 +77,11 @@ cudaError_t launch_col2im(const Col2imArgs& a, cudaStream_t s) {
 cudaError_t launch_bn_reduce(const BnReduceArgs& a, cudaStream_t s) {
   dim3 grid(a.C / kBnCols, bn_nseg(a));
   bn_reduce_kernel<<<grid, kBnThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_reduce_finalize(const BnFusedArgs& a, cudaStream_t s) {
+  dim3 grid(a.r.C / kBnCols, bn_nseg(a.r));
+  bn_reduce_finalize_kernel<<<grid, kBnThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t s) {

@@ -194,24 +194,36 @@ def test_im2col_stem_reads_the_user_batch_directly(backend, src):
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("m,c,ldx", [(128, 64, 128), (8192, 64, 128), (2048, 128, 128), (512, 256, 256), (100, 64, 64), (4100, 512, 512)])
 def test_batchnorm_kernels(backend, m, c, ldx):
+    _batchnorm_case(backend, m, c, ldx, fused=False)
+
+
+def _batchnorm_case(backend, m, c, ldx, fused):
     torch.manual_seed(5)
     x = (torch.randn(m, ldx) * 1.5 + 0.3).to(BF)
     res = torch.randn(m, c).to(BF)
     dy = torch.randn(m, c).to(BF)
     gamma, beta = torch.rand(c) + 0.5, torch.randn(c)
 
+    counters = {}
+
     def run(dev, masked, with_res):
         xd = x.to(dev)
         mean, invstd = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
         rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
         partial = torch.zeros(conv.bn_partial_numel(m, c), device=dev)
-        conv.bn_stats(xd, c, partial, mean, invstd, rm, rv, 1e-5, 0.1)
+        # single-launch reduction: the ticket counters are shared by all calls and must come back to zero each time
+        cnt = counters.setdefault(str(dev), torch.zeros(c // 64, dtype=torch.int32, device=dev)) if fused else None
+        conv.bn_stats(xd, c, partial, mean, invstd, rm, rv, 1e-5, 0.1, cnt)
+        if fused:
+            assert int(cnt.abs().sum()) == 0
         out = torch.zeros(m, c, dtype=BF, device=dev)
         conv.bn_apply(xd, c, mean, invstd, gamma.to(dev), beta.to(dev), res.to(dev) if with_res else None, masked, out)
         dg, db = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
         dx, g = torch.zeros(m, c, dtype=BF, device=dev), torch.zeros(m, c, dtype=BF, device=dev)
         conv.bn_backward(xd, c, dy.to(dev), out if masked else None, mean, invstd, gamma.to(dev), partial, dg, db, dx,
-                         g if masked else None)
+                         g if masked else None, cnt)
+        if fused:
+            assert int(cnt.abs().sum()) == 0
         return [t.cpu() for t in (mean, invstd, rm, rv, out, dg, db, dx, g)]
 
     for masked, with_res in ((True, True), (False, False), (True, False)):
@@ -295,3 +307,10 @@ def test_pack_and_unpack_params(backend):
     assert torch.equal(pf, pf_ref) and torch.equal(pb, pb_ref) and torch.equal(back, back_ref)
     touched = back_ref != -1.0
     assert torch.equal(back_ref[touched], (arena * 2)[touched]) and int(touched.sum()) == sum(e.rows * e.cols for e in entries)
+
+
+@pytest.mark.parametrize("m,c,ldx", [(128, 64, 128), (8192, 64, 128), (512, 256, 256), (4100, 512, 512)])
+def test_fused_batchnorm_reduction_kernel_bodies_on_host(m, c, ldx):
+    """Single-launch BatchNorm reduction (the last block of a column group finalises, the ticket counter resets
+    itself): the host build of the bodies against the definitions.  The sm_100a run lives in test_zz_round2_gpu."""
+    _batchnorm_case("emul", m, c, ldx, fused=True)

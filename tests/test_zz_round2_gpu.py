@@ -2,6 +2,8 @@
 already validated on a B200 (tests/test_conv_ops.py, tests/test_convnet_trainer.py) but has not itself run on one
 yet.  The file sorts last on purpose, so that under ``pytest -x`` a surprise here cannot mask the validated suites.
 """
+import os
+
 import pytest
 import torch
 
@@ -44,3 +46,46 @@ def test_resnet_eval_mode_inference_on_own_kernels():
     assert float((pred == want.argmax(1)).float().mean()) > 0.9
     res = evaluate(model, x.to(dev), want.argmax(1).to(dev), flat, verbose=False)
     assert res["accuracy"] > 0.9 and res["n"] == x.shape[0]
+
+
+@pytest.mark.parametrize("m,c,ldx", [(128, 64, 128), (8192, 64, 128), (512, 256, 256), (4100, 512, 512)])
+def test_fused_batchnorm_reduction_kernel(m, c, ldx):
+    """``bn_reduce_finalize_kernel`` (ticket counter, last block finalises) against the two-kernel definitions."""
+    _dev()
+    from test_conv_ops import _batchnorm_case
+    _batchnorm_case("cuda", m, c, ldx, fused=True)
+
+
+@pytest.mark.parametrize("flags", [{"COLEARN_CONV_STREAMS": "1"}, {"COLEARN_CONV_SHADOW_T": "1"}, {"COLEARN_CONV_FUSED_BN": "1"},
+                                   {"COLEARN_CONV_STREAMS": "1", "COLEARN_CONV_SHADOW_T": "1", "COLEARN_CONV_FUSED_BN": "1"}])
+def test_optional_step_optimisations_do_not_change_the_result(flags, monkeypatch):
+    """Second stream for the wgrad chains / W^T from the wgrad epilogue / single-launch BatchNorm reductions are
+    re-schedulings of the same kernels on the same data: the parameters after two steps (one eager, one through the
+    CUDA graph) must match the default schedule (bitwise for the stream and W^T variants)."""
+    dev = _dev()
+    torch.manual_seed(0)
+    x = torch.randn(256, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (256,), device=dev)
+
+    def run():
+        torch.manual_seed(1)
+        model = ResNet18(10).to(dev)
+        flat = flatten_params(model)
+        tr = ConvNetTrainer(model, dev, 128, (32, 32))
+        tr.load(flat, model)
+        for lo in (0, 128):
+            tr._graph_step(x[lo:lo + 128], y[lo:lo + 128], 0.05)
+        tr.store(flat, model)
+        torch.cuda.synchronize()
+        return flat.clone()
+
+    for k in ("COLEARN_CONV_STREAMS", "COLEARN_CONV_SHADOW_T", "COLEARN_CONV_FUSED_BN"):
+        monkeypatch.delenv(k, raising=False)
+    base = run()
+    for k, v in flags.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    if "COLEARN_CONV_FUSED_BN" in flags:
+        torch.testing.assert_close(got, base, rtol=1e-2, atol=1e-3)
+    else:
+        assert torch.equal(got, base)
