@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import base64
 import json
+import logging
 import queue
 import socket
 import socketserver
@@ -27,6 +28,9 @@ import threading
 import time
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Tuple
+
+
+log = logging.getLogger("colearn.bus")
 
 
 @dataclass
@@ -137,6 +141,7 @@ class InProcessBroker:
                 t = threading.Timer(delay, self._deliver, args=(msg,))
                 t.daemon = True
                 with self._lock:
+                    self._timers = [x for x in self._timers if x.is_alive()]   # fired timers are not kept around
                     self._timers.append(t)
                 t.start()
             else:
@@ -214,14 +219,19 @@ class _TcpHandler(socketserver.StreamRequestHandler):
                     frame = json.loads(raw.decode("utf-8"))
                 except ValueError:
                     continue
+                if not isinstance(frame, dict) or not isinstance(frame.get("topic", ""), str):
+                    continue
                 op = frame.get("op")
-                if op == "sub":
-                    broker.add_subscription(frame["topic"], proxy)  # type: ignore[arg-type]
-                elif op == "pub":
-                    broker.publish(frame["topic"], base64.b64decode(frame.get("payload", "")),
-                                   int(frame.get("qos", 0)))
-                elif op == "ping":
-                    proxy._enqueue(Message("$SYS/pong", b""))
+                try:
+                    if op == "sub" and "topic" in frame:
+                        broker.add_subscription(frame["topic"], proxy)  # type: ignore[arg-type]
+                    elif op == "pub" and "topic" in frame:
+                        broker.publish(frame["topic"], base64.b64decode(frame.get("payload", "")),
+                                       int(frame.get("qos", 0)))
+                    elif op == "ping":
+                        proxy._enqueue(Message("$SYS/pong", b""))
+                except (ValueError, TypeError):        # bad base64 / qos: drop the frame, keep the connection
+                    continue
         finally:
             proxy.alive = False
             broker.remove_client(proxy)  # type: ignore[arg-type]
@@ -278,6 +288,9 @@ class BusClient:
         self._reader: Optional[threading.Thread] = None
         self._connected = False
         self._mid = 0
+        # loop_start()/loop_forever() survive a raising callback (logged); drain()/loop() called directly from
+        # tests re-raise unless this is set
+        self.suppress_callback_errors = False
 
     # Default callbacks (paho signatures) — overridable --------------------------------
     def on_connect(self, client, userdata, flags, rc) -> None:  # noqa: D401
@@ -359,8 +372,19 @@ class BusClient:
             return 0
         if msg is None:
             return 0
-        self.on_message(self, None, msg)
+        self._dispatch(msg)
         return 1
+
+    def _dispatch(self, msg: Message) -> None:
+        """A callback that raises must not take the network loop (and with it the whole control plane) down:
+        log it and keep serving, like a broker connection would."""
+        try:
+            self.on_message(self, None, msg)
+        except Exception:  # noqa: BLE001
+            if self.suppress_callback_errors:
+                log.exception("on_message raised for topic %r (client %r); message dropped", msg.topic, self.client_id)
+            else:
+                raise
 
     def drain(self) -> int:
         """Synchronously deliver everything currently queued (handy in tests)."""
@@ -371,13 +395,17 @@ class BusClient:
             except queue.Empty:
                 return n
             if msg is not None:
-                self.on_message(self, None, msg)
+                self._dispatch(msg)
                 n += 1
 
     def loop_forever(self) -> None:
         self._running.set()
-        while self._running.is_set():
-            self.loop(timeout=0.1)
+        prev, self.suppress_callback_errors = self.suppress_callback_errors, True
+        try:
+            while self._running.is_set():
+                self.loop(timeout=0.1)
+        finally:
+            self.suppress_callback_errors = prev
 
     def loop_start(self) -> None:
         if self._loop_thread is None or not self._loop_thread.is_alive():

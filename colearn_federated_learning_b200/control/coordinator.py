@@ -83,6 +83,7 @@ class Coordinator(BusClient):
         self.evaluate_after = evaluate_after
         self.last_predictions: Optional[List[int]] = None
         self.trainings_done = 0
+        self._in_flight: Dict[str, Any] = {}      # id -> handle of the devices a running training is using
 
         self.windower = TemporalWindow(self.registry, window, self._start_training, timer_factory,
                                        lower_bound=0, rearm_if_pending=rearm_if_pending)
@@ -137,6 +138,14 @@ class Coordinator(BusClient):
 
         if worker is not None or (state == "NOT_READY" and ip_address != -1):
             if state == "TRAINING":
+                # a device that announces twice (duplicate delivery, reconnect) replaces its handle; the old
+                # connection is closed unless a training in flight is still using it (that one closes it itself)
+                old = self.known_workers.get(worker.id)
+                if old is not None and old is not worker and worker.id not in self._in_flight:
+                    try:
+                        old.close()
+                    except Exception:  # noqa: BLE001
+                        pass
                 self.known_workers[worker.id] = worker
                 armed = self.windower.on_training(worker.id, worker)
                 log.info(worker)
@@ -190,15 +199,19 @@ class Coordinator(BusClient):
 
     # ------------------------------------------------------------------ training dispatch
     def _start_training(self, snapshot: "OrderedDict[str, Any]") -> Any:
-        if self.remote:
-            loop = asyncio.new_event_loop()  # fresh loop inside the timer thread (fc.py:194-203)
-            try:
-                return loop.run_until_complete(self.training_remote(snapshot))
-            finally:
-                loop.close()
-        if self.encryption:
-            return self.starting_training_enc(snapshot)
-        return self.starting_training_local(snapshot)
+        self._in_flight = dict(snapshot)
+        try:
+            if self.remote:
+                loop = asyncio.new_event_loop()  # fresh loop inside the timer thread (fc.py:194-203)
+                try:
+                    return loop.run_until_complete(self.training_remote(snapshot))
+                finally:
+                    loop.close()
+            if self.encryption:
+                return self.starting_training_enc(snapshot)
+            return self.starting_training_local(snapshot)
+        finally:
+            self._in_flight = {}
 
     def _policy(self, lower: int, upper: int, policy: Optional[str] = None) -> SelectionPolicy:
         return SelectionPolicy(lower_bound=lower, upper_bound=upper, policy=policy or self.selection,
@@ -229,8 +242,15 @@ class Coordinator(BusClient):
                          max_nr_batches=self.args.federate_after_n_batches, lr=self.args.lr, shuffle=True,
                          seed=self.args.seed)
 
-    def _deregister(self, ids) -> None:
-        for wid in ids:
+    def _deregister(self, trained) -> None:
+        """Forget the devices that just trained (fc.py:376-379, 571-577) — unless the device re-announced itself
+        while its training was running: that newer registration is a late joiner and rides the next window."""
+        for wid in trained:
+            used = self._in_flight.get(wid)
+            current = self.registry.get(wid)
+            if used is not None and current is not None and current is not used:
+                log.info("Keeping " + str(wid) + ": it registered again during the training")
+                continue
             log.info("Removing: " + str(wid) + " from training devices")
             self.registry.remove(wid)
             self.known_workers.pop(wid, None)

@@ -79,8 +79,13 @@ def _recv_exact(sock: socket.socket, n: int) -> bytes:
     return bytes(buf)
 
 
+MAX_FRAME = 1 << 30   # 1 GiB: five times the largest arena in the model zoo (wide MLP, 201.6 MB)
+
+
 def _recv_msg(sock: socket.socket) -> Dict[str, Any]:
     (n,) = struct.unpack(">I", _recv_exact(sock, 4))
+    if n > MAX_FRAME:
+        raise ConnectionError(f"frame of {n} bytes exceeds the {MAX_FRAME}-byte limit")
     return msgpack.unpackb(_recv_exact(sock, n), raw=False)
 
 
@@ -106,6 +111,10 @@ class WorkerServer:
         self.tagged: Dict[str, List[torch.Tensor]] = {}
         self.fits_served = 0
         self._round = 0
+        # one model instance + one flat arena per architecture, reused across fits: the trainers behind local_fit
+        # (layer-wise MLP, conv net) cache their buffers / CUDA graphs per (model, arena)
+        self._models: Dict[str, Tuple[torch.nn.Module, torch.Tensor]] = {}
+        self._work_lock = threading.Lock()   # fits / predictions share those buffers: one at a time
         outer = self
 
         class Handler(socketserver.BaseRequestHandler):
@@ -156,29 +165,43 @@ class WorkerServer:
         if op == "fit":
             cfg = FitConfig.from_dict(req["config"])
             x, y = self.datasets[req.get("dataset_key", "training")]
-            model = build_model(cfg.model)
-            flat = _from_bytes(req["params"], self.device)
-            if flat.numel() != num_params(model):
-                return {"ok": False, "error": f"param count {flat.numel()} != {num_params(model)} for {cfg.model}"}
-            spec = getattr(model, "spec", None)
-            if spec is not None and not spec.flatten_input and x.shape[1] != spec.dims[0]:
-                return {"ok": False, "error": f"dataset has {x.shape[1]} features, {cfg.model} wants {spec.dims[0]}"}
-            model.to(self.device)
-            loss, path = local_fit(flat, model, x, y, cfg, round_idx=self._round)
-            self._round += 1
-            self.fits_served += 1
-            return {"ok": True, "params": _to_bytes(flat), "loss": float(loss), "n": int(x.shape[0]), "path": path}
+            with self._work_lock:
+                model, flat, err = self._model_and_arena(cfg.model, req["params"])
+                if err:
+                    return {"ok": False, "error": err}
+                spec = getattr(model, "spec", None)
+                if spec is not None and not spec.flatten_input and x.shape[1] != spec.dims[0]:
+                    return {"ok": False, "error": f"dataset has {x.shape[1]} features, {cfg.model} wants {spec.dims[0]}"}
+                loss, path = local_fit(flat, model, x, y, cfg, round_idx=self._round)
+                self._round += 1
+                self.fits_served += 1
+                return {"ok": True, "params": _to_bytes(flat), "loss": float(loss), "n": int(x.shape[0]), "path": path}
         if op == "predict":
-            cfg_model = req["model"]
-            model = build_model(cfg_model).to(self.device)
-            flat = _from_bytes(req["params"], self.device)
             data = self.tagged.get(req.get("tag", "inference"), [])
             if not data:
                 return {"ok": True, "pred": [], "count": 0}
-            x = torch.stack([d.reshape(-1) for d in data]).float()
-            pred = predict_fn(model, x, flat)
-            return {"ok": True, "pred": pred.reshape(-1).tolist(), "count": len(data)}
+            with self._work_lock:
+                model, flat, err = self._model_and_arena(req["model"], req["params"])
+                if err:
+                    return {"ok": False, "error": err}
+                spec = getattr(model, "spec", None)
+                keep_shape = spec is None                       # conv nets take [C, H, W] samples as they are
+                x = torch.stack([d if keep_shape else d.reshape(-1) for d in data]).float()
+                pred = predict_fn(model, x, flat)
+                return {"ok": True, "pred": pred.reshape(-1).tolist(), "count": len(data)}
         return {"ok": False, "error": f"unknown op {op!r}"}
+
+    def _model_and_arena(self, name: str, params: bytes):
+        """(model, arena holding ``params``, error) — instances are created once per architecture."""
+        if name not in self._models:
+            model = build_model(name).to(self.device)
+            self._models[name] = (model, torch.empty(num_params(model), device=self.device))
+        model, flat = self._models[name]
+        incoming = _from_bytes(params)
+        if incoming.numel() != flat.numel():
+            return None, None, f"param count {incoming.numel()} != {flat.numel()} for {name}"
+        flat.copy_(incoming)
+        return model, flat, None
 
     def start(self, block: bool = True) -> None:
         if block:
@@ -209,9 +232,18 @@ class RemoteWorkerClient:
         with self._lock:
             if self._sock is None:
                 raise ConnectionError(f"worker {self.id} is closed")
-            self._sock.settimeout(timeout)
-            _send_msg(self._sock, req)
-            resp = _recv_msg(self._sock)
+            try:
+                self._sock.settimeout(timeout)
+                _send_msg(self._sock, req)
+                resp = _recv_msg(self._sock)
+            except (OSError, ConnectionError, struct.error):
+                # a timed-out / broken exchange leaves the stream out of step (the late reply would be read as the
+                # answer to the next request): the handle is dead from here on
+                try:
+                    self._sock.close()
+                finally:
+                    self._sock = None
+                raise
         if not resp.get("ok", False):
             raise RuntimeError(f"worker {self.id}: {resp.get('error')}")
         return resp

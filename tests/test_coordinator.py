@@ -227,3 +227,99 @@ def test_worker_rpc_direct():
         cl.close()
     finally:
         w.stop()
+
+
+def test_worker_runtime_reuses_model_and_arena_and_guards_the_wire():
+    """Robustness of the RPC runtime: one model/arena per architecture across fits (trainer caches key on them),
+    a handle that timed out is dead (no desynchronised replies), oversized frames are refused."""
+    import socket
+    import struct
+
+    from colearn_federated_learning_b200.control import workers as W
+
+    w, p = _worker(seed=5)
+    try:
+        cl = RemoteWorkerClient("x", "127.0.0.1", p)
+        flat = flatten_params(FFNN())
+        cfg = FitConfig(model="ffnn", loss="bce", max_nr_batches=5, lr=0.1)
+        a, _, _ = cl.fit(flat, cfg)
+        model0, arena0 = w._models["ffnn"]
+        b, _, _ = cl.fit(flat, cfg)
+        assert w._models["ffnn"][0] is model0 and w._models["ffnn"][1].data_ptr() == arena0.data_ptr()
+        assert w.fits_served == 2 and a.shape == b.shape
+        # the arena is overwritten by every request: fit #2 started from `flat`, not from fit #1's result
+        c, _, _ = cl.fit(a, cfg)
+        assert not torch.equal(c, b)
+        # timeout -> the handle closes itself
+        with pytest.raises(OSError):
+            cl._call({"op": "fit", "config": FitConfig(model="ffnn", loss="bce", epochs=3).to_dict(),
+                      "params": W._to_bytes(flat), "dataset_key": "training"}, timeout=1e-4)
+        with pytest.raises(ConnectionError):
+            cl.ping()
+        deadline = time.time() + 20                          # let the orphaned fit finish before tearing down
+        while w.fits_served < 4 and time.time() < deadline:
+            time.sleep(0.01)
+        assert w.fits_served == 4
+        # a frame header announcing more than MAX_FRAME bytes is refused and the connection dropped
+        s = socket.create_connection(("127.0.0.1", p), timeout=5)
+        s.sendall(struct.pack(">I", W.MAX_FRAME + 1))
+        s.settimeout(5)
+        assert s.recv(1) == b""
+        s.close()
+        cl2 = RemoteWorkerClient("y", "127.0.0.1", p)       # the server itself is still fine
+        assert cl2.ping()
+        cl2.close()
+    finally:
+        w.stop()
+
+
+def test_duplicate_and_mid_training_announcements(tmp_path):
+    """A duplicated TRAINING event must not leak the first connection; a device that announces itself again while
+    its own training is running is a late joiner for the *next* window, not wiped by the end-of-training cleanup."""
+    w1, p1 = _worker(seed=1)
+    w2, p2 = _worker(seed=2)
+    try:
+        c, pub, clock = make(tmp_path, remote=True, rounds=1, args=Arguments(lr=0.05))
+        ident = f"127.0.0.1:{p1}"
+        pub.publish(TOPIC, f"(127.0.0.1, {p1}, TRAINING)")
+        c.drain()
+        first = c.known_workers[ident]
+        pub.publish(TOPIC, f"(127.0.0.1, {p1}, TRAINING)")      # duplicate delivery
+        pub.publish(TOPIC, f"(127.0.0.1, {p2}, TRAINING)")
+        c.drain()
+        second = c.known_workers[ident]
+        assert second is not first and first._sock is None and second._sock is not None
+        assert len(settings.training_devices) == 2
+
+        # re-announce from inside the training (the fit RPC of worker 2 triggers it)
+        orig_fit = RemoteWorkerClient.fit
+        fired = []
+
+        def fit_and_reannounce(self, *a, **k):
+            if not fired and self.id == ident:
+                fired.append(1)
+                pub.publish(TOPIC, f"(127.0.0.1, {p1}, TRAINING)")
+                c.drain()
+            return orig_fit(self, *a, **k)
+
+        RemoteWorkerClient.fit = fit_and_reannounce
+        try:
+            clock.advance(1.0)
+        finally:
+            RemoteWorkerClient.fit = orig_fit
+        res = c.windower.last_result
+        assert sorted(res["workers"]) == sorted([ident, f"127.0.0.1:{p2}"]) and res["dropped"] == []
+        # worker 2 is forgotten, worker 1's newer registration survived and armed the next window
+        assert list(settings.training_devices) == [ident] and ident in c.known_workers
+        assert c.known_workers[ident] is not second and second._sock is None
+        # reference semantics: the late joiner waits for the next event to arm a window (fc.py:187-191)
+        assert c.windower.state == "IDLE" and c.trainings_done == 1
+        pub.publish(TOPIC, f"(127.0.0.1, {p2}, TRAINING)")
+        c.drain()
+        assert c.windower.state == "COLLECTING"
+        clock.advance(1.0)
+        assert c.trainings_done == 2 and sorted(c.windower.last_result["workers"]) == sorted([ident, f"127.0.0.1:{p2}"])
+        assert len(settings.training_devices) == 0
+        c.shutdown()
+    finally:
+        w1.stop(); w2.stop()
