@@ -2,5 +2,5 @@
 from .datasets import (NetworkTrafficDataset, BaseDataset, ToTensor, ToTensorLong, Normalize,  # noqa: F401
                        FEATURE_COLUMNS, LABEL_COLUMN, CSV_HEADER, minmax_scale, xor_toy_dataset,
                        dataset_tensors)
-from .synthetic import synthetic_unsw, synthetic_images, write_synthetic_csv  # noqa: F401
+from .synthetic import synthetic_unsw, synthetic_images, synthetic_for_model, write_synthetic_csv  # noqa: F401
 from .federate import federate, FederatedDataset, FederatedDataLoader, Shard, shard_bounds  # noqa: F401

@@ -42,6 +42,27 @@ def synthetic_images(n: int, seed: int = 0, size: int = 32, classes: int = 10,
     return x, y
 
 
+def synthetic_for_model(model: str, n: int, seed: int = 0,
+                        device: Optional[torch.device] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Synthetic data of the shape ``model`` consumes (``--synthetic N`` on the CLIs): 32x32 images with 10 classes
+    for ``resnet18``, 28x28 single-channel digits-shaped inputs for ``net`` (784-128-64-10), two XOR-like features
+    for ``testing_remote``, the ten UNSW-IoT features otherwise.  Labels are ``[n, 1]`` floats (class index for the
+    cross-entropy models), which is what every fit executor accepts."""
+    if model == "resnet18":
+        x, y = synthetic_images(n, seed=seed)
+        y = y.float().view(n, 1)
+    elif model == "net":
+        x, y = synthetic_images(n, seed=seed, size=28)
+        x, y = x[:, :1].contiguous(), y.float().view(n, 1)
+    elif model == "testing_remote":
+        x, y = synthetic_unsw(n, seed=seed, n_features=2)
+    else:
+        x, y = synthetic_unsw(n, seed=seed)
+    if device is not None:
+        x, y = x.to(device), y.to(device)
+    return x, y
+
+
 def write_synthetic_csv(path: str, n: int, seed: int = 0, attack_fraction: Optional[float] = None) -> str:
     """Write a Bot-IoT-shaped CSV (19 columns, header identical to the reference example)."""
     import pandas as pd

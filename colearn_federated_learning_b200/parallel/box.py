@@ -23,7 +23,7 @@ from ..control.bus import BusClient, InProcessBroker
 from ..control.event_parser import EventParser, format_event
 from ..control.selection import SelectionPolicy, LOWER_BOUND, UPPER_BOUND
 from ..control.window import TemporalWindow
-from ..data import synthetic_unsw, NetworkTrafficDataset
+from ..data import synthetic_for_model, NetworkTrafficDataset
 from ..settings import DeviceRegistry
 from ..utils.checkpoint import load_or_init, checkpoint_compatible
 from ..models import flatten_params
@@ -129,7 +129,7 @@ def run_box_coordinator(cli, args: Arguments) -> None:
             engine.load_global(flatten_params(engine.model))
     # private shards: contiguous ceil(N/world) split of the dataset, like dataset.federate(workers)
     if args.synthetic and args.synthetic > 0:
-        x, y = synthetic_unsw(args.synthetic, seed=args.seed)
+        x, y = synthetic_for_model(args.model, args.synthetic, seed=args.seed)
     else:
         x, y = NetworkTrafficDataset(args.test_path).tensors()
     from ..data import shard_bounds

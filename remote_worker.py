@@ -33,7 +33,10 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--verbose", "-v", action="store_true", help="verbose worker")
     # extensions
     parser.add_argument("--broker-port", type=int, default=1883)
-    parser.add_argument("--synthetic", type=int, default=0, help="host N synthetic UNSW-shaped rows instead of --training")
+    parser.add_argument("--synthetic", type=int, default=0, help="host N synthetic rows instead of --training")
+    parser.add_argument("--data-model", default="ffnn",
+                        help="architecture the synthetic data is shaped for (resnet18: 32x32 images, net: 28x28, "
+                             "testing_remote: 2 features, otherwise the ten UNSW-IoT features)")
     parser.add_argument("--seed", type=int, default=0)
     parser.add_argument("--no-cuda", action="store_true")
     return parser
@@ -45,7 +48,7 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
     from colearn_federated_learning_b200.control.bus import BusClient
     from colearn_federated_learning_b200.control.event_parser import format_event
     from colearn_federated_learning_b200.control.workers import WorkerServer
-    from colearn_federated_learning_b200.data import (BaseDataset, NetworkTrafficDataset, synthetic_unsw,
+    from colearn_federated_learning_b200.data import (BaseDataset, NetworkTrafficDataset, synthetic_for_model,
                                                       xor_toy_dataset)
 
     logging.basicConfig(format="%(asctime)s: %(message)s", level=logging.INFO, datefmt="%H:%M:%S")
@@ -58,7 +61,7 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
     to_publish = format_event(args.host, args.event, args.port)
 
     if args.synthetic > 0:
-        dataset = BaseDataset(*synthetic_unsw(args.synthetic, seed=args.seed))
+        dataset = BaseDataset(*synthetic_for_model(args.data_model, args.synthetic, seed=args.seed))
     elif args.training is None:
         dataset = xor_toy_dataset()  # rw.py:75-80
     else:

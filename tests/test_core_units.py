@@ -282,3 +282,19 @@ def test_reference_shaped_client_federated_api(tmp_path):
     assert res["n"] == 40 and 0 <= res["accuracy"] <= 1
     shared = cf.get_private_data_loaders(["a", "b"], a, n_train_items=5, dataset=BaseDataset(x, y))
     assert len(shared) == 5
+
+
+@pytest.mark.parametrize("name", ["ffnn", "testing_remote", "net", "mlp", "resnet18"])
+def test_synthetic_data_matches_every_architecture(name):
+    """``--synthetic N`` must produce data the chosen ``--model`` can train on (box mode / local mode / workers)."""
+    from colearn_federated_learning_b200.data import synthetic_for_model
+    from colearn_federated_learning_b200.fl.trainer import FitConfig, local_fit
+    from colearn_federated_learning_b200.models import build_model, flatten_params
+
+    x, y = synthetic_for_model(name, 24, seed=2)
+    assert x.shape[0] == 24 and y.shape == (24, 1)
+    model = build_model(name)
+    flat = flatten_params(model).clone()
+    before = flat.clone()
+    loss, _ = local_fit(flat, model, x, y, FitConfig(model=name, loss="auto", batch_size=8, lr=0.05))
+    assert torch.isfinite(loss) and torch.isfinite(flat).all() and not torch.equal(flat, before)
