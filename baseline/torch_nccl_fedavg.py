@@ -12,7 +12,6 @@ runs ``epochs`` of shuffled mini-batch SGD on its shard â†’ ``dist.reduce(w_kÂ·Î
 """
 from __future__ import annotations
 
-import math
 from typing import List, Optional, Tuple
 
 import torch

@@ -22,7 +22,7 @@ import contextlib
 import glob
 import importlib.util
 import os
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import torch
 import torch.nn.functional as F

@@ -13,7 +13,6 @@ import torch
 
 from colearn_federated_learning_b200 import ops
 from colearn_federated_learning_b200.models import FFNN, MLP, flatten_params
-from colearn_federated_learning_b200.ops import reference as R
 
 
 def time_cuda(fn, warmup=3, iters=10):

@@ -2,7 +2,6 @@
 worker servers, encrypted mode, inference, fault injection — all through the in-process bus + fake clock."""
 import os
 import socket
-import threading
 import time
 
 import pytest
@@ -16,7 +15,7 @@ from colearn_federated_learning_b200.control.window import FakeClock
 from colearn_federated_learning_b200.control.workers import RemoteWorkerClient, WorkerServer
 from colearn_federated_learning_b200.data import BaseDataset, synthetic_unsw, write_synthetic_csv, xor_toy_dataset
 from colearn_federated_learning_b200.fl import FitConfig
-from colearn_federated_learning_b200.models import FFNN, MLP, TestingRemote, flatten_params
+from colearn_federated_learning_b200.models import FFNN, flatten_params
 from colearn_federated_learning_b200.utils.checkpoint import load_meta, save_model
 
 TOPIC = "topic/state"

@@ -1,7 +1,6 @@
 """Selection bounds, FedAvg, checkpoint, data layer, models, tooling (all CPU)."""
 import os
 import subprocess
-import sys
 
 import numpy as np
 import pytest
@@ -243,7 +242,6 @@ def test_feature_generator(tmp_path):
 
 
 def test_monitors(tmp_path):
-    import threading
     from colearn_federated_learning_b200.utils import monitors
     cpu, net, temp = (str(tmp_path / n) for n in ("cpu.txt", "net.txt", "temp.txt"))
     monitors.monitor_cpu(os.getpid(), cpu, samples=2, interval=0.01)
@@ -265,7 +263,6 @@ def test_monitors(tmp_path):
 
 
 def test_reference_shaped_client_federated_api(tmp_path):
-    import asyncio
     from colearn_federated_learning_b200 import client_federated as cf
     from colearn_federated_learning_b200.data import BaseDataset
     pred, tgt = torch.tensor([[0.8], [0.3]]), torch.tensor([[1.0], [0.0]])

@@ -3,14 +3,12 @@ the multi-GPU path), plus the box-mode control plane."""
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from colearn_federated_learning_b200.data import shard_bounds, synthetic_unsw
+from colearn_federated_learning_b200.data import synthetic_unsw
 from colearn_federated_learning_b200.models import MLP, flatten_params
-from colearn_federated_learning_b200.ops import reference as R
 from colearn_federated_learning_b200.parallel import FederatedEngine
 from colearn_federated_learning_b200.parallel.box import collect_plan, rank_identity, worker_id_to_rank
 from colearn_federated_learning_b200.control.event_parser import format_event

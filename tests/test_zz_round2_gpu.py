@@ -2,8 +2,6 @@
 already validated on a B200 (tests/test_conv_ops.py, tests/test_convnet_trainer.py) but has not itself run on one
 yet.  The file sorts last on purpose, so that under ``pytest -x`` a surprise here cannot mask the validated suites.
 """
-import os
-
 import pytest
 import torch
 
