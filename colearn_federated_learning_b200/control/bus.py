@@ -7,9 +7,10 @@ box there is no broker to talk to, so the bus is:
 * :class:`InProcessBroker` — topic → subscribers in one process.  This *is* the multi-node fake
   used by the tests (it mirrors the reference's VirtualWorker idea) and carries the fault-
   injection hooks (drop / delay / duplicate / rewrite) required by SURVEY §5.
-* :class:`TcpBroker` / ``BusClient(transport="tcp")`` — the same protocol over a localhost TCP
-  socket (newline-delimited JSON frames) so that ``remote_worker.py`` processes and
-  ``federated_coordinator.py`` can find each other exactly like they do through mosquitto.
+* :class:`TcpBroker` / ``BusClient(transport="tcp")`` — the same bus over TCP speaking **MQTT 3.1.1**
+  (``control/mqtt.py``): ``remote_worker.py`` processes and ``federated_coordinator.py`` find each other exactly
+  like they do through mosquitto, ``mosquitto_pub`` / paho clients can publish to the embedded broker, and the
+  clients can equally connect to a real mosquitto.  Retained messages, last-will and keep-alive are honoured.
 * :class:`BusClient` — a paho-shaped client (``connect / subscribe / publish / loop_forever /
   loop_start / loop_stop / disconnect`` and the ``on_connect / on_message / on_publish``
   callbacks with the paho signatures) so the Coordinator reads like the reference's.
@@ -18,8 +19,6 @@ MQTT topic filters ``+`` (one level) and ``#`` (rest) are honoured.
 """
 from __future__ import annotations
 
-import base64
-import json
 import logging
 import queue
 import socket
@@ -28,6 +27,8 @@ import threading
 import time
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Tuple
+
+from . import mqtt
 
 
 log = logging.getLogger("colearn.bus")
@@ -74,11 +75,20 @@ class InProcessBroker:
         self.delivered = 0
         self.dropped = 0
         self._timers: List[threading.Timer] = []
+        self._retained: dict = {}     # topic -> Message (MQTT retained messages)
 
     # -- subscription management -----------------------------------------------------
     def add_subscription(self, pattern: str, client: "BusClient") -> None:
         with self._lock:
-            self._subs.append((pattern, client))
+            if (pattern, client) not in self._subs:
+                self._subs.append((pattern, client))
+            retained = [m for t, m in self._retained.items() if topic_matches(pattern, t)]
+        for m in retained:                      # a new subscriber gets the last retained message per topic
+            client._enqueue(m)
+
+    def remove_subscription(self, pattern: str, client: "BusClient") -> None:
+        with self._lock:
+            self._subs = [(p, c) for (p, c) in self._subs if not (p == pattern and c is client)]
 
     def remove_client(self, client: "BusClient") -> None:
         with self._lock:
@@ -119,14 +129,20 @@ class InProcessBroker:
             raise ValueError(f"unknown fault spec {spec!r} (use drop:<re>, dup:<re> or delay:<s>:<re>)")
 
     # -- publish -------------------------------------------------------------------------
-    def publish(self, topic: str, payload, qos: int = 0) -> int:
+    def publish(self, topic: str, payload, qos: int = 0, retain: bool = False) -> int:
         if isinstance(payload, str):
             payload = payload.encode("utf-8")
+        payload = bytes(payload if payload is not None else b"")
         with self._lock:
             self._mid += 1
             mid = self._mid
             hooks = list(self._hooks)
-        deliveries: List[Tuple[float, Message]] = [(0.0, Message(topic, bytes(payload), qos, mid=mid))]
+            if retain:                          # empty retained payload clears the topic (MQTT-3.3.1-10)
+                if payload:
+                    self._retained[topic] = Message(topic, payload, qos, retain=True, mid=mid)
+                else:
+                    self._retained.pop(topic, None)
+        deliveries: List[Tuple[float, Message]] = [(0.0, Message(topic, payload, qos, mid=mid))]
         for hook in hooks:
             nxt: List[Tuple[float, Message]] = []
             for delay, msg in deliveries:
@@ -184,57 +200,104 @@ def reset_default_broker() -> InProcessBroker:
 
 
 # ---------------------------------------------------------------------------------------------
-# TCP transport (cross-process, localhost) — newline-delimited JSON frames:
-#   {"op":"sub","topic":...} / {"op":"pub","topic":...,"payload":<b64>,"qos":0}
-#   broker -> client: {"op":"msg","topic":...,"payload":<b64>,"qos":0,"mid":n}
+# TCP transport = MQTT 3.1.1 on the wire (control/mqtt.py): mosquitto_pub / mosquitto_sub / paho clients can talk
+# to TcpBroker, and BusClient(transport="tcp") can talk to a real mosquitto.
 # ---------------------------------------------------------------------------------------------
-class _TcpBridgeClient:
-    """Broker-side proxy for one TCP connection; quacks like a BusClient for ``_enqueue``."""
+class _MqttBridgeClient:
+    """Broker-side proxy for one MQTT connection; quacks like a BusClient for ``_enqueue``."""
 
-    def __init__(self, wfile, lock: threading.Lock) -> None:
+    def __init__(self, wfile, client_id: str) -> None:
         self._wfile = wfile
-        self._lock = lock
+        self._lock = threading.Lock()
+        self.client_id = client_id
         self.alive = True
+        self.taken_over = False
 
-    def _enqueue(self, msg: Message) -> None:
+    def send(self, data: bytes) -> None:
         if not self.alive:
             return
-        frame = json.dumps({"op": "msg", "topic": msg.topic, "qos": msg.qos, "mid": msg.mid,
-                            "payload": base64.b64encode(msg.payload).decode("ascii")}) + "\n"
         try:
             with self._lock:
-                self._wfile.write(frame.encode("utf-8"))
+                self._wfile.write(data)
                 self._wfile.flush()
-        except OSError:
+        except (OSError, ValueError):
             self.alive = False
 
+    def _enqueue(self, msg: Message) -> None:
+        # every subscription is granted qos 0, so deliveries never carry a packet id
+        self.send(mqtt.publish(msg.topic, msg.payload, qos=0, retain=msg.retain))
 
-class _TcpHandler(socketserver.StreamRequestHandler):
+
+class _MqttHandler(socketserver.StreamRequestHandler):
+    CONNECT_TIMEOUT = 10.0
+
     def handle(self) -> None:  # one thread per connection
-        broker: InProcessBroker = self.server.broker  # type: ignore[attr-defined]
-        proxy = _TcpBridgeClient(self.wfile, threading.Lock())
+        owner: "TcpBroker" = self.server.owner  # type: ignore[attr-defined]
+        broker = owner.broker
+        self.request.settimeout(self.CONNECT_TIMEOUT)
         try:
-            for raw in self.rfile:
-                try:
-                    frame = json.loads(raw.decode("utf-8"))
-                except ValueError:
-                    continue
-                if not isinstance(frame, dict) or not isinstance(frame.get("topic", ""), str):
-                    continue
-                op = frame.get("op")
-                try:
-                    if op == "sub" and "topic" in frame:
-                        broker.add_subscription(frame["topic"], proxy)  # type: ignore[arg-type]
-                    elif op == "pub" and "topic" in frame:
-                        broker.publish(frame["topic"], base64.b64decode(frame.get("payload", "")),
-                                       int(frame.get("qos", 0)))
-                    elif op == "ping":
-                        proxy._enqueue(Message("$SYS/pong", b""))
-                except (ValueError, TypeError):        # bad base64 / qos: drop the frame, keep the connection
-                    continue
+            pkt = mqtt.read_packet(self.rfile)
+            if pkt is None or pkt[0] != mqtt.CONNECT:
+                return                                   # first packet must be CONNECT (MQTT-3.1.0-1)
+            info = mqtt.parse_connect(pkt[2])
+        except mqtt.ProtocolError:
+            try:
+                self.wfile.write(mqtt.connack(mqtt.CONNACK_BAD_PROTOCOL))
+            except OSError:
+                pass
+            return
+        except OSError:
+            return
+        client_id = info.client_id or owner.auto_client_id()
+        proxy = _MqttBridgeClient(self.wfile, client_id)
+        owner.register(client_id, proxy, self.request)
+        proxy.send(mqtt.connack(mqtt.CONNACK_ACCEPTED))
+        # a client that stays silent for 1.5 keep-alive periods is dead (MQTT-3.1.2-24) -> its will fires
+        self.request.settimeout(1.5 * info.keepalive if info.keepalive else None)
+        graceful = False
+        try:
+            while True:
+                pkt = mqtt.read_packet(self.rfile)
+                if pkt is None:
+                    break
+                ptype, flags, body = pkt
+                if ptype == mqtt.PUBLISH:
+                    topic, payload, qos, retain, pid = mqtt.parse_publish(flags, body)
+                    broker.publish(topic, payload, qos, retain=retain)
+                    if qos == 1:
+                        proxy.send(mqtt.puback(pid))
+                    elif qos == 2:
+                        proxy.send(mqtt.pubrec(pid))
+                elif ptype == mqtt.PUBREL:
+                    proxy.send(mqtt.pubcomp(mqtt.parse_packet_id(body)))
+                elif ptype == mqtt.SUBSCRIBE:
+                    pid, filters = mqtt.parse_subscribe(body)
+                    proxy.send(mqtt.suback(pid, [0] * len(filters)))
+                    for pattern, _qos in filters:
+                        broker.add_subscription(pattern, proxy)  # type: ignore[arg-type]
+                elif ptype == mqtt.UNSUBSCRIBE:
+                    pid, filters = mqtt.parse_unsubscribe(body)
+                    for pattern in filters:
+                        broker.remove_subscription(pattern, proxy)  # type: ignore[arg-type]
+                    proxy.send(mqtt.unsuback(pid))
+                elif ptype == mqtt.PINGREQ:
+                    proxy.send(mqtt.pingresp())
+                elif ptype == mqtt.DISCONNECT:
+                    graceful = True
+                    break
+                elif ptype in (mqtt.PUBACK, mqtt.PUBREC, mqtt.PUBCOMP):
+                    pass
+                else:
+                    raise mqtt.ProtocolError(f"unexpected packet type {ptype}")
+        except (OSError, mqtt.ProtocolError, ValueError):
+            pass
         finally:
             proxy.alive = False
             broker.remove_client(proxy)  # type: ignore[arg-type]
+            owner.unregister(client_id, proxy)
+            if not graceful and not proxy.taken_over and info.will is not None:
+                log.info("client %r vanished: publishing its will on %r", client_id, info.will.topic)
+                broker.publish(info.will.topic, info.will.payload, info.will.qos, retain=info.will.retain)
 
 
 class _ThreadedTCPServer(socketserver.ThreadingMixIn, socketserver.TCPServer):
@@ -243,15 +306,48 @@ class _ThreadedTCPServer(socketserver.ThreadingMixIn, socketserver.TCPServer):
 
 
 class TcpBroker:
-    """A tiny stand-in for mosquitto on 127.0.0.1 (default port 1883 like MQTT)."""
+    """A small MQTT 3.1.1 broker on 127.0.0.1 (default port 1883) in front of an :class:`InProcessBroker` — the
+    stand-in for mosquitto: qos-0 delivery, retained messages, last-will, keep-alive supervision, client-id
+    take-over (a second connection with the same id closes the first, which is why workers use unique ids)."""
 
     def __init__(self, host: str = "127.0.0.1", port: int = 1883,
                  broker: Optional[InProcessBroker] = None) -> None:
         self.broker = broker or InProcessBroker()
-        self._server = _ThreadedTCPServer((host, port), _TcpHandler)
-        self._server.broker = self.broker  # type: ignore[attr-defined]
+        self._server = _ThreadedTCPServer((host, port), _MqttHandler)
+        self._server.owner = self  # type: ignore[attr-defined]
         self.host, self.port = self._server.server_address[:2]
         self._thread: Optional[threading.Thread] = None
+        self._lock = threading.Lock()
+        self._sessions: dict = {}     # client id -> (proxy, socket)
+        self._auto = 0
+
+    def auto_client_id(self) -> str:
+        with self._lock:
+            self._auto += 1
+            return f"auto-{self._auto}"
+
+    def register(self, client_id: str, proxy: _MqttBridgeClient, sock) -> None:
+        with self._lock:
+            old = self._sessions.get(client_id)
+            self._sessions[client_id] = (proxy, sock)
+        if old is not None:
+            old[0].taken_over = True
+            old[0].alive = False
+            try:
+                old[1].shutdown(socket.SHUT_RDWR)
+            except OSError:
+                pass
+
+    def unregister(self, client_id: str, proxy: _MqttBridgeClient) -> None:
+        with self._lock:
+            cur = self._sessions.get(client_id)
+            if cur is not None and cur[0] is proxy:
+                del self._sessions[client_id]
+
+    @property
+    def clients(self) -> List[str]:
+        with self._lock:
+            return sorted(self._sessions)
 
     def start(self) -> "TcpBroker":
         self._thread = threading.Thread(target=self._server.serve_forever, name="bus-broker", daemon=True)
@@ -261,6 +357,14 @@ class TcpBroker:
     def stop(self) -> None:
         self._server.shutdown()
         self._server.server_close()
+        with self._lock:
+            sessions = list(self._sessions.values())
+        for proxy, sock in sessions:
+            proxy.taken_over = True          # a broker going down is not a client failure: no wills
+            try:
+                sock.shutdown(socket.SHUT_RDWR)
+            except OSError:
+                pass
         self.broker.shutdown()
 
     def __enter__(self) -> "TcpBroker":
@@ -288,6 +392,16 @@ class BusClient:
         self._reader: Optional[threading.Thread] = None
         self._connected = False
         self._mid = 0
+        self._will: Optional[mqtt.Will] = None
+        self._username: Optional[str] = None
+        self._password: Optional[bytes] = None
+        self._rfile = None
+        self._keepalive = 0
+        self._pinger: Optional[threading.Thread] = None
+        self._closing = threading.Event()
+        self._ack_cond = threading.Condition()
+        self._acked: set = set()
+        self._last_pong = 0.0
         # loop_start()/loop_forever() survive a raising callback (logged); drain()/loop() called directly from
         # tests re-raise unless this is set
         self.suppress_callback_errors = False
@@ -302,14 +416,45 @@ class BusClient:
     def on_publish(self, client, userdata, mid) -> None:
         pass
 
+    def on_disconnect(self, client, userdata, rc) -> None:
+        pass
+
+    # paho-compatible session options (set before connect) -----------------------------------
+    def will_set(self, topic: str, payload=None, qos: int = 0, retain: bool = False) -> None:
+        """Last-will: published by the broker if this client vanishes without DISCONNECT (e.g. a worker that dies
+        announces ``NOT_READY`` through its will)."""
+        if isinstance(payload, str):
+            payload = payload.encode("utf-8")
+        self._will = mqtt.Will(topic, bytes(payload or b""), qos, retain)
+
+    def username_pw_set(self, username: Optional[str], password: Optional[str] = None) -> None:
+        self._username = username
+        self._password = password.encode("utf-8") if isinstance(password, str) else password
+
     # Connection ---------------------------------------------------------------------------
     def connect(self, host: str = "localhost", port: int = 1883, keepalive: int = 60) -> int:
         if self._transport == "tcp":
             addr = "127.0.0.1" if host in ("localhost", "") else host
-            self._sock = socket.create_connection((addr, port), timeout=10)
-            self._sock.settimeout(None)
+            sock = socket.create_connection((addr, port), timeout=10)
+            cid = self.client_id or f"colearn-{id(self):x}"
+            sock.sendall(mqtt.connect(cid, keepalive, True, self._will, self._username, self._password))
+            rfile = sock.makefile("rb")
+            pkt = mqtt.read_packet(rfile)
+            if pkt is None or pkt[0] != mqtt.CONNACK:
+                sock.close()
+                raise ConnectionError("broker closed the connection during the MQTT handshake")
+            _, rc = mqtt.parse_connack(pkt[2])
+            if rc != mqtt.CONNACK_ACCEPTED:
+                sock.close()
+                raise ConnectionRefusedError(f"MQTT broker refused the connection (return code {rc})")
+            sock.settimeout(None)
+            self._sock, self._rfile, self._keepalive = sock, rfile, keepalive
+            self._closing.clear()
             self._reader = threading.Thread(target=self._tcp_reader, name="bus-reader", daemon=True)
             self._reader.start()
+            if keepalive > 0:
+                self._pinger = threading.Thread(target=self._ping_loop, name="bus-ping", daemon=True)
+                self._pinger.start()
         else:
             if self._broker is None:
                 self._broker = default_broker()
@@ -318,45 +463,103 @@ class BusClient:
         return 0
 
     def _tcp_reader(self) -> None:
-        assert self._sock is not None
-        f = self._sock.makefile("rb")
+        rc = 1
         try:
-            for raw in f:
-                try:
-                    frame = json.loads(raw.decode("utf-8"))
-                except ValueError:
-                    continue
-                if frame.get("op") == "msg":
-                    self._enqueue(Message(frame["topic"], base64.b64decode(frame.get("payload", "")),
-                                          int(frame.get("qos", 0)), mid=int(frame.get("mid", 0))))
-        except OSError:
+            while True:
+                pkt = mqtt.read_packet(self._rfile)
+                if pkt is None:
+                    break
+                ptype, flags, body = pkt
+                if ptype == mqtt.PUBLISH:
+                    topic, payload, qos, retain, pid = mqtt.parse_publish(flags, body)
+                    if qos == 1:
+                        self._send(mqtt.puback(pid))
+                    elif qos == 2:
+                        self._send(mqtt.pubrec(pid))
+                    self._enqueue(Message(topic, payload, qos, retain=retain, mid=pid))
+                elif ptype == mqtt.PUBREL:
+                    self._send(mqtt.pubcomp(mqtt.parse_packet_id(body)))
+                elif ptype == mqtt.PUBREC:
+                    self._send(mqtt.pubrel(mqtt.parse_packet_id(body)))
+                elif ptype in (mqtt.SUBACK, mqtt.UNSUBACK, mqtt.PUBACK, mqtt.PUBCOMP):
+                    with self._ack_cond:
+                        self._acked.add((ptype, mqtt.parse_packet_id(body)))
+                        self._ack_cond.notify_all()
+                elif ptype == mqtt.PINGRESP:
+                    self._last_pong = time.time()
+        except (OSError, ValueError):
             pass
+        finally:
+            if self._closing.is_set():
+                rc = 0
+            self._connected = False
+            try:
+                self.on_disconnect(self, None, rc)
+            except Exception:  # noqa: BLE001
+                log.exception("on_disconnect raised")
 
-    def _send(self, frame: dict) -> None:
-        assert self._sock is not None
-        data = (json.dumps(frame) + "\n").encode("utf-8")
+    def _ping_loop(self) -> None:
+        period = max(0.05, self._keepalive / 2.0)
+        while not self._closing.wait(period):
+            try:
+                self._send(mqtt.pingreq())
+            except (OSError, AssertionError):
+                return
+
+    def _send(self, data: bytes) -> None:
+        sock = self._sock
+        if sock is None:
+            raise OSError("not connected")
         with self._sock_lock:
-            self._sock.sendall(data)
+            sock.sendall(data)
+
+    def _next_pid(self) -> int:
+        with self._sock_lock:
+            self._mid = self._mid % 0xFFFF + 1
+            return self._mid
+
+    def wait_for_ack(self, ptype: int, pid: int, timeout: float = 5.0) -> bool:
+        """Block until the broker acknowledged packet ``pid`` (SUBACK / UNSUBACK / PUBACK / PUBCOMP)."""
+        deadline = time.time() + timeout
+        with self._ack_cond:
+            while (ptype, pid) not in self._acked:
+                left = deadline - time.time()
+                if left <= 0 or not self._connected:
+                    return (ptype, pid) in self._acked
+                self._ack_cond.wait(min(left, 0.1))
+            self._acked.discard((ptype, pid))
+            return True
 
     def subscribe(self, topic: str, qos: int = 0):
         if self._transport == "tcp":
-            self._send({"op": "sub", "topic": topic, "qos": qos})
-        else:
-            assert self._broker is not None, "connect() first"
-            self._broker.add_subscription(topic, self)
+            pid = self._next_pid()
+            self._send(mqtt.subscribe(pid, [(topic, qos)]))
+            self.wait_for_ack(mqtt.SUBACK, pid)       # like mosquitto_sub: return once the subscription is live
+            return (0, pid)
+        assert self._broker is not None, "connect() first"
+        self._broker.add_subscription(topic, self)
+        return (0, 0)
+
+    def unsubscribe(self, topic: str):
+        if self._transport == "tcp":
+            pid = self._next_pid()
+            self._send(mqtt.unsubscribe(pid, [topic]))
+            self.wait_for_ack(mqtt.UNSUBACK, pid)
+            return (0, pid)
+        assert self._broker is not None, "connect() first"
+        self._broker.remove_subscription(topic, self)
         return (0, 0)
 
     def publish(self, topic: str, payload=b"", qos: int = 0, retain: bool = False):
         if isinstance(payload, str):
             payload = payload.encode("utf-8")
+        payload = bytes(payload if payload is not None else b"")
         if self._transport == "tcp":
-            self._send({"op": "pub", "topic": topic, "qos": qos,
-                        "payload": base64.b64encode(payload).decode("ascii")})
-            self._mid += 1
-            mid = self._mid
+            mid = self._next_pid()
+            self._send(mqtt.publish(topic, payload, qos, retain, packet_id=mid if qos else 0))
         else:
             assert self._broker is not None, "connect() first"
-            mid = self._broker.publish(topic, payload, qos)
+            mid = self._broker.publish(topic, payload, qos, retain=retain)
         self.on_publish(self, None, mid)
         return mid
 
@@ -425,6 +628,11 @@ class BusClient:
     def disconnect(self) -> None:
         self.loop_stop()
         if self._transport == "tcp" and self._sock is not None:
+            self._closing.set()
+            try:
+                self._send(mqtt.disconnect())            # graceful: the broker discards the will
+            except OSError:
+                pass
             try:
                 self._sock.shutdown(socket.SHUT_RDWR)
             except OSError:

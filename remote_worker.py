@@ -57,6 +57,8 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
 
     # unique client id per worker (the reference's literal "woker" gets duplicates kicked)
     client = BusClient(client_id="worker-" + identifier, transport="tcp")
+    # last will: if this process dies without a DISCONNECT the broker withdraws the device for us
+    client.will_set(args.topic, format_event(args.host, "NOT_READY", args.port))
     client.connect(args.broker, args.broker_port)
     to_publish = format_event(args.host, args.event, args.port)
 

@@ -77,6 +77,47 @@ def test_real_clis_remote_training_end_to_end(tmp_path):
             coord.kill()
 
 
+def test_killed_worker_is_withdrawn_through_its_mqtt_last_will(tmp_path):
+    """Failure detection on the control plane: ``remote_worker.py`` registers a NOT_READY last-will with the broker;
+    SIGKILL-ing it after it announced TRAINING makes the (in-test) MQTT broker publish the will, and a Coordinator
+    listening through the same broker drops the device before the window closes."""
+    from colearn_federated_learning_b200 import settings
+    from colearn_federated_learning_b200.control.bus import TcpBroker
+    from colearn_federated_learning_b200.control.coordinator import Coordinator
+    from colearn_federated_learning_b200.control.window import FakeClock
+
+    wport = _free_port()
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    with TcpBroker(port=0) as tb:
+        clock = FakeClock()
+        c = Coordinator(30, True, 1, False, False, transport="tcp", timer_factory=clock, path=str(tmp_path / "t.pth"),
+                        device=torch.device("cpu"))
+        c.connect(tb.host, tb.port)
+        c.subscribe("topic/state")
+        c.loop_start()
+        w = subprocess.Popen([sys.executable, os.path.join(ROOT, "remote_worker.py"), "--host", "127.0.0.1", "-p", str(wport),
+                              "-b", "127.0.0.1", "--broker-port", str(tb.port), "-t", "topic/state", "-w", "1",
+                              "--synthetic", "16", "--no-cuda"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        try:
+            ident = f"127.0.0.1:{wport}"
+            deadline = time.time() + 60
+            while ident not in settings.training_devices and time.time() < deadline:
+                time.sleep(0.05)
+            assert ident in settings.training_devices and c.windower.state == "COLLECTING"
+            w.kill()                                             # no DISCONNECT: the broker fires the will
+            deadline = time.time() + 20
+            while ident in settings.training_devices and time.time() < deadline:
+                time.sleep(0.05)
+            assert ident not in settings.training_devices and ident not in c.known_workers
+            clock.advance(30.0)                                  # window closes with nobody left: no training
+            assert c.trainings_done == 0
+        finally:
+            if w.poll() is None:
+                w.kill()
+            c.shutdown()
+            c.disconnect()
+
+
 # ---- SMPC -------------------------------------------------------------------------------------------------------
 def test_fixed_point_and_sharing_roundtrip():
     from colearn_federated_learning_b200.smpc import CryptoProvider, fix_precision, float_precision, share
