@@ -126,7 +126,7 @@ def test_will_retained_takeover_and_keepalive():
         watcher.loop_start()
 
         def wait_for(n):
-            deadline = time.time() + 5
+            deadline = time.time() + 10
             while len(events) < n and time.time() < deadline:
                 time.sleep(0.01)
             return len(events) >= n
@@ -151,13 +151,13 @@ def test_will_retained_takeover_and_keepalive():
         silent.sendall(mqtt.connect("silent", 1, True, mqtt.Will("topic/state", b"silent-died")))
         assert _recv(silent, 4) == CONNACK_OK
         t0 = time.time()
-        assert wait_for(3) and events[2][1] == b"silent-died" and 1.0 < time.time() - t0 < 4.0
+        assert wait_for(3) and events[2][1] == b"silent-died" and 1.0 < time.time() - t0 < 5.0
         silent.close()
         # ... while a BusClient keeps itself alive with PINGREQs
         alive = BusClient("alive", transport="tcp")
         alive.will_set("topic/state", "alive-died")
-        alive.connect(tb.host, tb.port, keepalive=1)
-        time.sleep(2.2)
+        alive.connect(tb.host, tb.port, keepalive=2)     # pings every second, the broker would give up after 3 s
+        time.sleep(3.5)
         assert len(events) == 3 and "alive" in tb.clients
         # 4. take-over: a second connection with the same client id closes the first, without firing its will
         dis = []
