@@ -295,3 +295,15 @@ def test_synthetic_data_matches_every_architecture(name):
     before = flat.clone()
     loss, _ = local_fit(flat, model, x, y, FitConfig(model=name, loss="auto", batch_size=8, lr=0.05))
     assert torch.isfinite(loss) and torch.isfinite(flat).all() and not torch.equal(flat, before)
+
+
+def test_osmud_probe_dry_run(tmp_path):
+    """``data/osmud_test.sh`` (router-side osMUD probe): named options, the reference's positional form, dry-run."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(["sh", os.path.join(root, "data", "osmud_test.sh"), "-d", "-n", "2", "-t", "3", "-o", str(tmp_path / "r")],
+                         capture_output=True, text=True, check=True).stdout
+    assert out.count("/etc/init.d/firewall restart") == 2 and "+ sleep 3" in out and f"{tmp_path}/r/test_2.txt" in out
+    assert not (tmp_path / "r").exists()
+    out = subprocess.run(["sh", os.path.join(root, "data", "osmud_test.sh"), "-d", "1", "7"], capture_output=True, text=True,
+                         check=True, cwd=str(tmp_path)).stdout
+    assert "+ sleep 7" in out and "run 1/1" in out
