@@ -20,70 +20,79 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# (flags, kwargs): the nine reference options first (same spellings and defaults), then the extensions
+_OPTIONS = (
+    (("--port", "-p"), dict(type=int, default=8777, help="TCP port the worker's RPC server listens on")),
+    (("--host",), dict(type=str, required=True, help="IPv4 address of this device (it is what the coordinator parses out of the event)")),
+    (("--broker", "-b"), dict(type=str, required=True, help="MQTT broker to announce to")),
+    (("--topic", "-t"), dict(type=str, required=True, help="topic the coordinator listens on")),
+    (("--wait", "-w"), dict(type=float, default=5, help="delay in seconds between start-up and the announcement")),
+    (("--event", "-e"), dict(type=str, default="TRAINING", help="what to announce: TRAINING, INFERENCE or NOT_READY")),
+    (("--training", "-dt"), dict(type=str, default=None, help="Bot-IoT CSV hosted as the private training set")),
+    (("--inference", "-di"), dict(type=str, default=None, help="Bot-IoT CSV whose rows are hosted as inference tensors")),
+    (("--verbose", "-v"), dict(action="store_true", help="log every RPC")),
+    (("--broker-port",), dict(type=int, default=1883)),
+    (("--synthetic",), dict(type=int, default=0, help="host N synthetic rows instead of --training")),
+    (("--data-model",), dict(default="ffnn", help="architecture the synthetic data is shaped for (resnet18: 32x32 images, net: "
+                                                  "28x28, testing_remote: 2 features, otherwise the ten UNSW-IoT features)")),
+    (("--seed",), dict(type=int, default=0)),
+    (("--no-cuda",), dict(action="store_true", help="serve fits on the CPU even if a GPU is present")),
+    (("--no-will",), dict(action="store_true", help="do not register the NOT_READY last-will with the broker")),
+)
+
+
 def build_parser() -> argparse.ArgumentParser:
-    parser = argparse.ArgumentParser(description="Run a federated worker (RPC server).")
-    parser.add_argument("--port", "-p", type=int, default=8777, help="port number of the worker server, e.g. --port 8777")
-    parser.add_argument("--host", type=str, required=True, help="ip address of the interface the worker listens on")
-    parser.add_argument("--broker", "-b", type=str, required=True, help="bus broker host")
-    parser.add_argument("--topic", "-t", type=str, required=True, help="topic where the event must be published")
-    parser.add_argument("--wait", "-w", type=int, default=5, help="seconds to wait before sending the event")
-    parser.add_argument("--event", "-e", type=str, default="TRAINING", help="state of the client (TRAINING, INFERENCE, NOT_READY)")
-    parser.add_argument("--training", "-dt", type=str, default=None, help="training data csv")
-    parser.add_argument("--inference", "-di", type=str, default=None, help="inference data csv")
-    parser.add_argument("--verbose", "-v", action="store_true", help="verbose worker")
-    # extensions
-    parser.add_argument("--broker-port", type=int, default=1883)
-    parser.add_argument("--synthetic", type=int, default=0, help="host N synthetic rows instead of --training")
-    parser.add_argument("--data-model", default="ffnn",
-                        help="architecture the synthetic data is shaped for (resnet18: 32x32 images, net: 28x28, "
-                             "testing_remote: 2 features, otherwise the ten UNSW-IoT features)")
-    parser.add_argument("--seed", type=int, default=0)
-    parser.add_argument("--no-cuda", action="store_true")
+    parser = argparse.ArgumentParser(description="CoLearn device: hosts a private dataset and serves fit / search / predict RPCs.")
+    for flags, kwargs in _OPTIONS:
+        parser.add_argument(*flags, **kwargs)
     return parser
 
 
-def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by the CLI integration test
+def pick_dataset(args):
+    """--synthetic N > the CSV given with -dt > the reference's XOR toy set (rw.py:75-80)."""
+    from colearn_federated_learning_b200.data import BaseDataset, NetworkTrafficDataset, synthetic_for_model, xor_toy_dataset
+
+    if args.synthetic > 0:
+        return BaseDataset(*synthetic_for_model(args.data_model, args.synthetic, seed=args.seed))
+    if args.training:
+        logging.info("training data: %s", args.training)
+        return NetworkTrafficDataset(args.training)
+    return xor_toy_dataset()
+
+
+def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by the CLI integration tests
     import torch
 
     from colearn_federated_learning_b200.control.bus import BusClient
     from colearn_federated_learning_b200.control.event_parser import format_event
     from colearn_federated_learning_b200.control.workers import WorkerServer
-    from colearn_federated_learning_b200.data import (BaseDataset, NetworkTrafficDataset, synthetic_for_model,
-                                                      xor_toy_dataset)
+    from colearn_federated_learning_b200.data import NetworkTrafficDataset
 
     logging.basicConfig(format="%(asctime)s: %(message)s", level=logging.INFO, datefmt="%H:%M:%S")
-    identifier = args.host + ":" + str(args.port)
-    device = torch.device("cpu" if args.no_cuda or not torch.cuda.is_available() else "cuda")
+    identity = f"{args.host}:{args.port}"
+    on_gpu = torch.cuda.is_available() and not args.no_cuda
+    server = WorkerServer(identity, args.host, args.port, device=torch.device("cuda" if on_gpu else "cpu"), verbose=args.verbose)
+    server.add_dataset(pick_dataset(args), key="training")                       # rw.py:108
+    if args.inference:
+        logging.info("inference data: %s", args.inference)
+        rows = NetworkTrafficDataset(args.inference).data
+        server.load_data([torch.tensor(r).float() for r in rows], tag="inference")   # rw.py:102-104
 
-    # unique client id per worker (the reference's literal "woker" gets duplicates kicked)
-    client = BusClient(client_id="worker-" + identifier, transport="tcp")
-    # last will: if this process dies without a DISCONNECT the broker withdraws the device for us
-    client.will_set(args.topic, format_event(args.host, "NOT_READY", args.port))
-    client.connect(args.broker, args.broker_port)
-    to_publish = format_event(args.host, args.event, args.port)
-
-    if args.synthetic > 0:
-        dataset = BaseDataset(*synthetic_for_model(args.data_model, args.synthetic, seed=args.seed))
-    elif args.training is None:
-        dataset = xor_toy_dataset()  # rw.py:75-80
-    else:
-        print(args.training)
-        dataset = NetworkTrafficDataset(args.training)
-
-    worker = WorkerServer(identifier, args.host, args.port, device=device, verbose=args.verbose)
-    if args.inference is not None:
-        print(args.inference)
-        dataset_inf = NetworkTrafficDataset(args.inference)
-        worker.load_data([torch.tensor(row).float() for row in dataset_inf.data], tag="inference")
-    worker.add_dataset(dataset, key="training")
-
-    t = Timer(args.wait, lambda: client.publish(args.topic, to_publish))
-    t.daemon = True
-    t.start()
+    # one bus identity per device (the reference's shared literal id gets duplicates kicked, SURVEY §2.8-12)
+    bus = BusClient(client_id="worker-" + identity, transport="tcp")
+    if not args.no_will:
+        # if this process dies without a DISCONNECT the broker withdraws the device on our behalf
+        bus.will_set(args.topic, format_event(args.host, "NOT_READY", args.port))
+    bus.connect(args.broker, args.broker_port)
+    announcement = format_event(args.host, args.event, args.port)
+    delayed = Timer(args.wait, bus.publish, args=(args.topic, announcement))     # rw.py:110-114
+    delayed.daemon = True
+    delayed.start()
     try:
-        worker.start()  # blocks forever
+        server.start()                                                            # serve forever (rw.py:117)
     except KeyboardInterrupt:
-        worker.stop()
+        server.stop()
+        bus.disconnect()
 
 
 if __name__ == "__main__":
