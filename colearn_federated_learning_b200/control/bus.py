@@ -230,13 +230,14 @@ class _MqttBridgeClient:
 
 class _MqttHandler(socketserver.StreamRequestHandler):
     CONNECT_TIMEOUT = 10.0
+    MAX_PACKET = 1 << 20          # control-plane messages are tens of bytes; refuse to buffer more than 1 MiB
 
     def handle(self) -> None:  # one thread per connection
         owner: "TcpBroker" = self.server.owner  # type: ignore[attr-defined]
         broker = owner.broker
         self.request.settimeout(self.CONNECT_TIMEOUT)
         try:
-            pkt = mqtt.read_packet(self.rfile)
+            pkt = mqtt.read_packet(self.rfile, self.MAX_PACKET)
             if pkt is None or pkt[0] != mqtt.CONNECT:
                 return                                   # first packet must be CONNECT (MQTT-3.1.0-1)
             info = mqtt.parse_connect(pkt[2])
@@ -257,7 +258,7 @@ class _MqttHandler(socketserver.StreamRequestHandler):
         graceful = False
         try:
             while True:
-                pkt = mqtt.read_packet(self.rfile)
+                pkt = mqtt.read_packet(self.rfile, self.MAX_PACKET)
                 if pkt is None:
                     break
                 ptype, flags, body = pkt

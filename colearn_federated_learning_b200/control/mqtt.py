@@ -95,8 +95,9 @@ def _read_exact(f: BinaryIO, n: int) -> Optional[bytes]:
     return bytes(buf)
 
 
-def read_packet(f: BinaryIO) -> Optional[Tuple[int, int, bytes]]:
-    """Read one control packet from a blocking binary stream: ``(type, flags, body)``; None on a clean EOF."""
+def read_packet(f: BinaryIO, max_size: int = MAX_PACKET) -> Optional[Tuple[int, int, bytes]]:
+    """Read one control packet from a blocking binary stream: ``(type, flags, body)``; None on a clean EOF.
+    ``max_size`` bounds the body a peer can make us allocate (the broker uses 1 MiB: events are tens of bytes)."""
     first = f.read(1)
     if not first:
         return None
@@ -111,6 +112,8 @@ def read_packet(f: BinaryIO) -> Optional[Tuple[int, int, bytes]]:
         mult *= 128
     else:
         raise ProtocolError("malformed remaining length")
+    if length > max_size:
+        raise ProtocolError(f"packet of {length} bytes exceeds the {max_size}-byte limit")
     body = _read_exact(f, length) if length else b""
     if body is None:
         return None

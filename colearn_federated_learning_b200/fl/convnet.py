@@ -20,6 +20,7 @@ fp32 statistics and parameters).  No reference counterpart: the reference has no
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -87,10 +88,13 @@ class ConvNetTrainer:
     def cached(cls, model: ResNet18, flat: torch.Tensor, batch_size: int, hw: Tuple[int, int]) -> "ConvNetTrainer":
         key = (id(model), flat.data_ptr(), str(flat.device), batch_size, tuple(hw))
         tr = cls._cache.get(key)
+        if tr is not None and tr._model_ref() is not model:      # id() of a collected module got recycled
+            tr = None
         if tr is None:
             if len(cls._cache) > 2:
                 cls._cache.clear()
             tr = cls._cache[key] = cls(model, flat.device, batch_size, hw)
+            tr._model_ref = weakref.ref(model)
             tr.bind_buffers(model)
         return tr
 
@@ -171,6 +175,7 @@ class ConvNetTrainer:
             cv.rm, cv.rv = self.running_mean[off:off + cv.cout], self.running_var[off:off + cv.cout]
             off += cv.cout
         self._bound: Optional[nn.Module] = None
+        self._model_ref = weakref.ref(model)
         # opt-in (not yet measured on a B200): wgrad chains on a second stream, see _conv_bwd
         self._side = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and os.environ.get("COLEARN_CONV_STREAMS") == "1") else None
         self._fuse_shadow_t = os.environ.get("COLEARN_CONV_SHADOW_T") == "1"

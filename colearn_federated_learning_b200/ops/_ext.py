@@ -16,7 +16,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lock = threading.Lock()
 _mod = None
-_err: Optional[BaseException] = None
+_err: Optional[Exception] = None
 _tried = False
 
 
@@ -45,7 +45,7 @@ def load(build_if_missing: bool = False):
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)  # type: ignore[union-attr]
             _mod = mod
-        except BaseException as e:  # noqa: BLE001
+        except Exception as e:  # noqa: BLE001 - ImportError / OSError (missing libtorch symbols, wrong arch, ...)
             _err = e
         _tried = True
         return _mod
