@@ -34,7 +34,8 @@ class Arguments:
     weighted: bool = False         # False = uniform FedAvg (reference), True = n_k / sum(n)
     server_lr: float = 1.0         # theta <- theta + server_lr * avg_delta (1.0 = plain FedAvg)
     backend: str = "auto"          # auto | fused | nccl | cpu
-    dtype: str = "fp32"
+    dtype: str = "fp32"            # fp32 | bf16 (box mode: bf16 shadow of the broadcast for the tcgen05 consumers)
+    save_every: int = 0            # >0: checkpoint every N rounds, not only after the last one
     synthetic: int = 0             # >0: generate this many synthetic UNSW-shaped rows
     n_train_items_enc: int = 1000  # fc.py:432
     precision_fractional: int = 3  # fc.py:433

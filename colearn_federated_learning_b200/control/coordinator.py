@@ -242,6 +242,16 @@ class Coordinator(BusClient):
                          max_nr_batches=self.args.federate_after_n_batches, lr=self.args.lr, shuffle=True,
                          seed=self.args.seed)
 
+    def _maybe_checkpoint(self, model, theta: torch.Tensor, round_idx: int, meta: Dict[str, Any]) -> None:
+        """``--save-every N``: durable progress inside a long training (the reference only saves after the last
+        round, fc.py:381,585).  Atomic like every checkpoint write; the final save still happens."""
+        n = getattr(self.args, "save_every", 0)
+        if n and (round_idx + 1) % n == 0 and round_idx + 1 < self.enabled_round:
+            from ..models import state_dict_from_flat
+            from ..utils.checkpoint import save_state_dict
+            save_state_dict(state_dict_from_flat(model, theta), self.path, meta={**meta, "rounds": round_idx + 1, "partial": True})
+            log.info("checkpoint after round %d written to %s", round_idx + 1, self.path)
+
     def _deregister(self, trained) -> None:
         """Forget the devices that just trained (fc.py:376-379, 571-577) — unless the device re-announced itself
         while its training was running: that newer registration is a late joiner and rides the next window."""
@@ -284,6 +294,7 @@ class Coordinator(BusClient):
                 self.metrics.worker_loss(wid, l)
                 result["losses"][wid] = l
             self.metrics.end_round(r, time.time() - t0, selected=fed.workers, n_k=counts, loss_k=losses)
+            self._maybe_checkpoint(model, theta, r, {"workers": fed.workers, "mode": "local"})
         log.info("End training")
         unflatten_params(model, theta)
         save_model(model.cpu(), self.path, meta={"rounds": self.enabled_round, "workers": fed.workers, "mode": "local"})
@@ -360,6 +371,7 @@ class Coordinator(BusClient):
                 ops.fedavg_apply(th, stacked, w, self.args.server_lr)
                 theta = th.cpu()
             self.metrics.end_round(r, time.time() - t0, selected=ids, n_k=counts)
+            self._maybe_checkpoint(model, theta, r, {"workers": list(to_train.keys()), "mode": "remote"})
             if not alive:
                 break
         for wid, worker in to_train.items():

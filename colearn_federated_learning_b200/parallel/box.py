@@ -118,10 +118,12 @@ def run_box_coordinator(cli, args: Arguments) -> None:
     if rounds > 1 and max_batches < 0:
         max_batches = ROUND_MODE_BATCHES
     backend = "auto" if args.backend in ("auto", "nccl") else args.backend
+    on_gpu = backend != "cpu" and device.type == "cuda"
     engine = FederatedEngine(args.model, backend=backend, device=device, batch_size=args.batch_size, lr=args.lr,
                              local_epochs=args.epochs, max_batches=max_batches, loss=args.loss, weighted=args.weighted,
                              server_lr=args.server_lr, seed=args.seed,
-                             clients_per_rank=getattr(cli, "clients_per_gpu", 1) if backend != "cpu" and device.type == "cuda" else 1)
+                             bf16_shadow=on_gpu and getattr(args, "dtype", "fp32") == "bf16",
+                             clients_per_rank=getattr(cli, "clients_per_gpu", 1) if on_gpu else 1)
     if rank == 0:
         import os
         if os.path.exists(cli.checkpoint) and checkpoint_compatible(engine.model, cli.checkpoint):
@@ -136,12 +138,70 @@ def run_box_coordinator(cli, args: Arguments) -> None:
     lo, hi = shard_bounds(len(x), world)[rank]
     engine.set_local_data(x[lo:hi], y[lo:hi])
     t0 = time.time()
-    rep = engine.run_rounds(rounds, masks=plan["mask"])
+    save_every = max(0, getattr(args, "save_every", 0))
+    metrics_path = getattr(cli, "metrics", None)
+    if metrics_path or save_every:
+        # observable mode: one engine call per round, so every round gets its own device time (max over ranks),
+        # traffic / link-roofline figures and, if asked for, a checkpoint.  Without these flags all rounds are
+        # enqueued in one call and the host never enters the loop.
+        _run_rounds_observed(engine, plan["mask"], rounds, rank, world, metrics_path, save_every, cli.checkpoint)
+    else:
+        rep = engine.run_rounds(rounds, masks=plan["mask"])
+        if rank == 0:
+            for i in range(rounds):
+                for k in range(world):
+                    if (plan["mask"] >> k) & 1:
+                        log.info("Loss for worker id: %s tensor(%.4f)", "%s:%d" % rank_identity(k), float(rep.losses[i, k, 0]))
+            log.info("Total training time: %s (device %.3f ms for %d rounds)", time.time() - t0, rep.device_ms, rounds)
     if rank == 0:
-        for i in range(rounds):
-            for k in range(world):
-                if (plan["mask"] >> k) & 1:
-                    log.info("Loss for worker id: %s tensor(%.4f)", "%s:%d" % rank_identity(k), float(rep.losses[i, k, 0]))
-        log.info("Total training time: %s (device %.3f ms for %d rounds)", time.time() - t0, rep.device_ms, rounds)
         engine.save_checkpoint(cli.checkpoint)
     shutdown()
+
+
+NVLINK_GBPS_PER_DIR = 900.0     # NVLink 5 per GPU and direction (the roofline the box-mode metrics refer to)
+
+
+def round_record(round_idx: int, mask: int, world: int, counts: List[int], losses, device_ms: float, bytes_bcast: int,
+                 bytes_reduce: int, launches: int, algo: str) -> Dict[str, Any]:
+    """One JSONL record per round (SURVEY §5 metrics): who trained, on how many samples, the losses, the device time
+    (already the max over ranks), the model bytes moved by the two collective legs and how far the round is from the
+    time the slower leg would take at NVLink line rate."""
+    sel = [k for k in range(world) if (mask >> k) & 1]
+    t = max(device_ms, 1e-6) * 1e-3
+    link_s = max(bytes_bcast, bytes_reduce) / (NVLINK_GBPS_PER_DIR * 1e9)
+    return {"round": round_idx, "selected": ["%s:%d" % rank_identity(k) for k in sel], "n_k": [counts[k] for k in sel],
+            "loss_k": [float(losses[k]) for k in sel], "t_round_max_over_ranks_ms": device_ms, "algo": algo,
+            "bytes_bcast": bytes_bcast, "bytes_reduce": bytes_reduce, "launches": launches,
+            "GBps": (bytes_bcast + bytes_reduce) / t / 1e9, "link_time_lower_bound_ms": link_s * 1e3,
+            "roofline_frac": link_s / t}
+
+
+def _run_rounds_observed(engine: FederatedEngine, mask: int, rounds: int, rank: int, world: int, metrics_path: Optional[str],
+                         save_every: int, checkpoint: str) -> None:
+    import json
+
+    import torch
+
+    t0 = time.time()
+    total_ms = 0.0
+    for i in range(rounds):
+        rep = engine.run_rounds(1, masks=mask)
+        ms = torch.tensor([rep.device_ms], dtype=torch.float64, device=engine.device if engine.backend != "cpu" else "cpu")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        total_ms += float(ms)
+        if rank == 0:
+            losses = rep.losses[0, :, 0].tolist() if rep.losses is not None else [0.0] * world
+            rec = round_record(i, mask, world, engine.counts, losses, float(ms), rep.bytes_bcast, rep.bytes_reduce,
+                               rep.launches, rep.algo)
+            for k, l in zip([k for k in range(world) if (mask >> k) & 1], rec["loss_k"]):
+                log.info("Loss for worker id: %s tensor(%.4f)", "%s:%d" % rank_identity(k), l)
+            log.info("Time round %d : %s", i, rec["t_round_max_over_ranks_ms"] * 1e-3)
+            if metrics_path:
+                with open(metrics_path, "a") as f:
+                    f.write(json.dumps(rec) + "\n")
+            if save_every and (i + 1) % save_every == 0 and i + 1 < rounds:
+                engine.save_checkpoint(checkpoint)
+                log.info("checkpoint after round %d written to %s", i + 1, checkpoint)
+    if rank == 0:
+        log.info("Total training time: %s (device %.3f ms for %d rounds)", time.time() - t0, total_ms, rounds)

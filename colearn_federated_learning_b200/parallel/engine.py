@@ -518,4 +518,6 @@ class FederatedEngine:
                 self.theta.add_(self.server_lr * (contrib - self.theta))
                 losses_log[i] = lvec
         self.rounds_done += rounds
-        return RoundReport(rounds, W, "cpu", "gloo", (time.perf_counter() - t0) * 1e3, losses_log, 0)
+        nsel = [bin(m).count("1") for m in masks]
+        return RoundReport(rounds, W, "cpu", "gloo", (time.perf_counter() - t0) * 1e3, losses_log, 0,
+                           bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel))

@@ -55,6 +55,10 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--select", type=int, default=None, help="train at most k of the collected workers")
     parser.add_argument("--selection", choices=["all", "first", "random"], default="all")
     parser.add_argument("--checkpoint", type=str, default="./test.pth")
+    parser.add_argument("--save-every", type=int, default=0, help="also write the checkpoint every N rounds (0 = only after the last round, like the reference)")
+    parser.add_argument("--dtype", choices=["fp32", "bf16"], default=d.dtype,
+                        help="--box: bf16 makes the FedAvg broadcast carry a bf16 copy of the model next to the fp32 master "
+                             "(consumed directly by the tcgen05 GEMMs of the wide / conv models)")
     parser.add_argument("--no-cuda", action="store_true")
     parser.add_argument("--strict-events", action="store_true", help="validate IPv4 octets / full match (reference is lax)")
     parser.add_argument("--fit-timeout", type=float, default=None, help="seconds before a silent remote worker is dropped from a round")
@@ -78,6 +82,7 @@ def arguments_from_cli(ns: argparse.Namespace) -> Arguments:
     a.federate_after_n_batches, a.lr, a.server_lr, a.seed = ns.max_batches, ns.lr, ns.server_lr, ns.seed
     a.log_interval, a.test_path, a.synthetic, a.weighted = ns.log_interval, ns.test_path, ns.synthetic, ns.weighted
     a.no_cuda, a.backend = ns.no_cuda, ns.backend
+    a.dtype, a.save_every = ns.dtype, max(0, ns.save_every)
     return a
 
 

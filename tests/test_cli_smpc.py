@@ -176,3 +176,61 @@ def test_box_mode_cli_two_ranks_gloo(tmp_path):
     assert out.stderr.count("Loss for worker id: 10.0.0.") == 4
     state = torch.load(ckpt, weights_only=True)
     assert state["fc1.weight"].shape == (64, 10) and state["fc3.weight"].shape == (2, 64)
+
+
+def test_box_mode_metrics_jsonl_and_periodic_checkpoints(tmp_path):
+    """``--metrics`` / ``--save-every`` in box mode: one JSONL record per round with the fields SURVEY §5 lists
+    (selection, n_k, loss_k, device time as max over ranks, bytes of both collective legs, GB/s, link-roofline
+    fraction) and a checkpoint that exists before the last round finishes."""
+    import json
+    ckpt, metrics = str(tmp_path / "test.pth"), str(tmp_path / "rounds.jsonl")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "federated_coordinator.py"),
+                          "-t", "topic/state", "--box", "--model", "mlp", "--synthetic", "96", "-f", "3", "-w", "1",
+                          "--checkpoint", ckpt, "--batch-size", "8", "--metrics", metrics, "--save-every", "1", "--dtype", "bf16"],
+                         env=env, capture_output=True, text=True, timeout=240, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    recs = [json.loads(l) for l in open(metrics)]
+    assert [r["round"] for r in recs] == [0, 1, 2]
+    for r in recs:
+        assert r["selected"] == ["10.0.0.1:8777", "10.0.0.2:8778"] and r["n_k"] == [48, 48] and len(r["loss_k"]) == 2
+        assert r["t_round_max_over_ranks_ms"] > 0 and r["bytes_bcast"] == r["bytes_reduce"] == 2 * 4 * 4994
+        assert 0 < r["roofline_frac"] < 1 and r["GBps"] > 0 and r["link_time_lower_bound_ms"] > 0
+    assert out.stderr.count("checkpoint after round") == 2 and out.stderr.count("Time round") == 3
+    assert torch.load(ckpt, weights_only=True)["fc1.weight"].shape == (64, 10)
+
+
+def test_save_every_in_remote_mode(tmp_path):
+    """``--save-every`` on the classic coordinator: the checkpoint (marked partial in its sidecar) exists while
+    later rounds are still running."""
+    from colearn_federated_learning_b200.control.arguments import Arguments
+    from colearn_federated_learning_b200.control.bus import BusClient, InProcessBroker
+    from colearn_federated_learning_b200.control.coordinator import Coordinator
+    from colearn_federated_learning_b200.control.window import FakeClock
+    from colearn_federated_learning_b200.utils.checkpoint import load_meta
+
+    broker, clock = InProcessBroker(), FakeClock()
+    a = Arguments()
+    a.synthetic, a.save_every, a.model, a.batch_size = 48, 1, "mlp", 8
+    seen = []
+
+    class Spy(Coordinator):
+        def _maybe_checkpoint(self, model, theta, r, meta):
+            super()._maybe_checkpoint(model, theta, r, meta)
+            if os.path.exists(self.path):
+                seen.append((r, load_meta(self.path).get("partial", False), load_meta(self.path).get("rounds")))
+
+    c = Spy(1, False, 3, False, False, args=a, broker=broker, timer_factory=clock, path=str(tmp_path / "t.pth"),
+            device=torch.device("cpu"))
+    c.connect()
+    c.subscribe("topic/state")
+    pub = BusClient("pub", broker=broker)
+    pub.connect()
+    pub.publish("topic/state", "(192.168.1.7, TRAINING)")
+    pub.publish("topic/state", "(192.168.1.8, TRAINING)")
+    c.drain()
+    clock.advance(1.0)
+    assert seen[:2] == [(0, True, 1), (1, True, 2)]            # rounds 1 and 2 left partial checkpoints behind
+    meta = load_meta(c.path)
+    assert meta["rounds"] == 3 and not meta.get("partial", False)
