@@ -1,0 +1,26 @@
+#!/bin/sh
+# First GPU call of the next round (ONE box, one call: a call costs ~1.5 GPU-minutes before the command even starts).
+#   1. the GPU tests written after round 1's budget ran out (incl. the opt-in kernels / schedules)
+#   2. the ResNet step with each opt-in re-scheduling, against the default and the cuDNN path
+#   3. per-kernel durations of one eager ResNet step (where do the 1.77 ms go?) + ncu --set full of the conv kernels
+#   4. compute-sanitizer memcheck over the conv ops
+#   5. cfg4 at N=1 with the winners
+# Everything lands in gpurun_out/r2_*; copy the summaries into profiles/.
+mkdir -p gpurun_out
+COLEARN_RUN_UNVALIDATED=1 timeout 150 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu > gpurun_out/r2_unvalidated_tests.log 2>&1
+tail -n 3 gpurun_out/r2_unvalidated_tests.log
+for flags in "" "COLEARN_CONV_FUSED_BN=1" "COLEARN_CONV_STREAMS=1" "COLEARN_CONV_SHADOW_T=1" \
+             "COLEARN_CONV_FUSED_BN=1 COLEARN_CONV_STREAMS=1 COLEARN_CONV_SHADOW_T=1"; do
+  tag=$(echo "${flags:-default}" | tr ' =' '__' | sed 's/COLEARN_CONV_//g')
+  env $flags timeout 60 python scripts/bench_convnet.py --reps 3 > "gpurun_out/r2_convnet_${tag}.json" 2> "gpurun_out/r2_convnet_${tag}.err"
+  echo "== $tag"; cut -c1-400 "gpurun_out/r2_convnet_${tag}.json"
+done
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_convnet_launch_times.csv \
+    python scripts/prof_convnet_only.py 2 > gpurun_out/r2_convnet_launch_times.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"im2col_kernel|col2im_kernel|bn_reduce_kernel|bn_apply_kernel|bn_bwd_kernel" \
+    -s 10 -c 10 -o gpurun_out/r2_prof_conv python scripts/prof_convnet_only.py 2 > gpurun_out/r2_prof_conv.log 2>&1
+timeout 200 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/r2_sanitizer_memcheck_conv.log \
+    python -m pytest tests/test_conv_ops.py -q -m gpu -x > gpurun_out/r2_sanitizer_memcheck_conv.out 2>&1
+echo "memcheck rc=$?"; tail -n 3 gpurun_out/r2_sanitizer_memcheck_conv.log
+timeout 80 python bench.py --config cfg4 --steps 5 --warmup 3 > gpurun_out/r2_bench_cfg4_n1.json 2> gpurun_out/r2_bench_cfg4_n1.err
+cut -c1-300 gpurun_out/r2_bench_cfg4_n1.json
