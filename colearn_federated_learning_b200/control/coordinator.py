@@ -335,6 +335,10 @@ class Coordinator(BusClient):
         cfg = self._fit_config("remote")
         theta = flatten_params(model).cpu()
         loop = asyncio.get_running_loop()
+        # one thread per selected device: every fit RPC of a round is in flight at the same time (the default
+        # executor would cap the fan-out at min(32, cpu_count + 4) and serialise a 100-device round)
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=max(1, len(to_train)), thread_name_prefix="fit-rpc")
         self.metrics.start_training(cfg.max_nr_batches)
         result: Dict[str, Any] = {"workers": list(to_train.keys()), "losses": {}, "rounds": self.enabled_round, "dropped": []}
         alive = OrderedDict(to_train)
@@ -345,7 +349,7 @@ class Coordinator(BusClient):
 
             async def one(wid: str, worker: RemoteWorkerClient):
                 try:
-                    fut = loop.run_in_executor(None, lambda: worker.fit(theta, rcfg, timeout=self.fit_timeout))
+                    fut = loop.run_in_executor(pool, lambda: worker.fit(theta, rcfg, timeout=self.fit_timeout))
                     flat, loss, n = await fut
                     return wid, flat, loss, n
                 except Exception as e:  # noqa: BLE001 - a failing worker must not sink the round
@@ -374,6 +378,7 @@ class Coordinator(BusClient):
             self._maybe_checkpoint(model, theta, r, {"workers": list(to_train.keys()), "mode": "remote"})
             if not alive:
                 break
+        pool.shutdown(wait=False)
         for wid, worker in to_train.items():
             log.info("Closing socket for " + str(wid))
             worker.close()

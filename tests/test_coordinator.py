@@ -322,3 +322,31 @@ def test_duplicate_and_mid_training_announcements(tmp_path):
         c.shutdown()
     finally:
         w1.stop(); w2.stop()
+
+
+def test_remote_round_fans_out_to_all_devices_at_once(tmp_path):
+    """40 devices whose fit takes 0.25 s each: the round must take about one fit, not 40 / (cpu_count + 4) of them
+    (the default asyncio executor would serialise the upper-bound-100 case the reference advertises)."""
+    from collections import OrderedDict
+
+    class SlowWorker:
+        def __init__(self, wid):
+            self.id, self.closed = wid, False
+
+        def fit(self, flat, cfg, dataset_key="training", timeout=None):
+            time.sleep(0.25)
+            return flat.clone() + 0.01, 0.5, 10
+
+        def close(self):
+            self.closed = True
+
+    c, pub, clock = make(tmp_path, remote=True, rounds=2)
+    snapshot = OrderedDict((f"10.0.0.{i}:8777", SlowWorker(f"10.0.0.{i}:8777")) for i in range(1, 41))
+    for wid, w in snapshot.items():
+        c.registry.register(wid, w)
+    t0 = time.time()
+    res = c._start_training(snapshot)
+    dt = time.time() - t0
+    assert len(res["losses"]) == 40 and res["dropped"] == [] and all(w.closed for w in snapshot.values())
+    assert dt < 1.5, dt      # 2 rounds x 0.25 s + overhead; behind the default executor (cpu_count + 4 threads): >= 2 s here
+    assert len(settings.training_devices) == 0
