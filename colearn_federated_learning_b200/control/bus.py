@@ -232,7 +232,22 @@ class _MqttHandler(socketserver.StreamRequestHandler):
     CONNECT_TIMEOUT = 10.0
     MAX_PACKET = 1 << 20          # control-plane messages are tens of bytes; refuse to buffer more than 1 MiB
 
+    def setup(self) -> None:
+        # TLS handshake in the connection's own thread (a slow or hostile peer cannot stall the accept loop)
+        ctx = self.server.owner.ssl_context  # type: ignore[attr-defined]
+        self.tls_failed = False
+        if ctx is not None:
+            self.request.settimeout(self.CONNECT_TIMEOUT)
+            try:
+                self.request = ctx.wrap_socket(self.request, server_side=True)
+            except (OSError, ValueError) as e:          # ssl.SSLError is an OSError
+                log.info("TLS handshake with %s failed: %r", self.client_address, e)
+                self.tls_failed = True
+        super().setup()
+
     def handle(self) -> None:  # one thread per connection
+        if self.tls_failed:
+            return
         owner: "TcpBroker" = self.server.owner  # type: ignore[attr-defined]
         broker = owner.broker
         self.request.settimeout(self.CONNECT_TIMEOUT)
@@ -312,8 +327,9 @@ class TcpBroker:
     take-over (a second connection with the same id closes the first, which is why workers use unique ids)."""
 
     def __init__(self, host: str = "127.0.0.1", port: int = 1883,
-                 broker: Optional[InProcessBroker] = None) -> None:
+                 broker: Optional[InProcessBroker] = None, ssl_context=None) -> None:
         self.broker = broker or InProcessBroker()
+        self.ssl_context = ssl_context            # control/tls.py::server_context(...) -> MQTT over TLS (port 8883 by convention)
         self._server = _ThreadedTCPServer((host, port), _MqttHandler)
         self._server.owner = self  # type: ignore[attr-defined]
         self.host, self.port = self._server.server_address[:2]
@@ -394,6 +410,7 @@ class BusClient:
         self._connected = False
         self._mid = 0
         self._will: Optional[mqtt.Will] = None
+        self._ssl_context = None
         self._username: Optional[str] = None
         self._password: Optional[bytes] = None
         self._rfile = None
@@ -428,6 +445,12 @@ class BusClient:
             payload = payload.encode("utf-8")
         self._will = mqtt.Will(topic, bytes(payload or b""), qos, retain)
 
+    def tls_set(self, ca_certs: Optional[str] = None, certfile: Optional[str] = None, keyfile: Optional[str] = None,
+                check_hostname: bool = False, context=None) -> None:
+        """paho's ``tls_set``: MQTT over TLS (optionally with a client certificate for mutual TLS)."""
+        from .tls import client_context
+        self._ssl_context = context or client_context(ca_certs, certfile, keyfile, check_hostname=check_hostname)
+
     def username_pw_set(self, username: Optional[str], password: Optional[str] = None) -> None:
         self._username = username
         self._password = password.encode("utf-8") if isinstance(password, str) else password
@@ -437,6 +460,8 @@ class BusClient:
         if self._transport == "tcp":
             addr = "127.0.0.1" if host in ("localhost", "") else host
             sock = socket.create_connection((addr, port), timeout=10)
+            if self._ssl_context is not None:
+                sock = self._ssl_context.wrap_socket(sock, server_hostname=addr)
             cid = self.client_id or f"colearn-{id(self):x}"
             sock.sendall(mqtt.connect(cid, keepalive, True, self._will, self._username, self._password))
             rfile = sock.makefile("rb")

@@ -54,8 +54,9 @@ class Coordinator(BusClient):
                  strict_events: bool = False, device: Optional[torch.device] = None,
                  select_k: Optional[int] = None, selection: str = "all", fit_timeout: Optional[float] = None,
                  filter_file: Optional[str] = None, metrics: Optional[RoundLogger] = None,
-                 rearm_if_pending: bool = False, evaluate_after: bool = False) -> None:
+                 rearm_if_pending: bool = False, evaluate_after: bool = False, worker_ssl_context=None) -> None:
         super().__init__(client_id="coordinator", broker=broker, transport=transport)
+        self.worker_ssl_context = worker_ssl_context     # TLS towards the devices' RPC servers (control/tls.py)
         self.registry = settings.init()
 
         # Command parameters (fc.py:105-109)
@@ -125,7 +126,8 @@ class Coordinator(BusClient):
                     identifier = str(ip_address) + ":" + str(port)
                     log.info("Remote worker idetifier: " + identifier)
                     try:
-                        worker = RemoteWorkerClient(identifier, str(ip_address), port, verbose=True)
+                        worker = RemoteWorkerClient(identifier, str(ip_address), port, verbose=True,
+                                                    ssl_context=self.worker_ssl_context)
                     except OSError as e:  # connection refused etc. → device skipped (fc.py:166-170)
                         log.info("Error " + repr(e))
                 elif state == "NOT_READY":

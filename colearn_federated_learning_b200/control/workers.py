@@ -103,8 +103,9 @@ def _from_bytes(b: bytes, device=None) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 class WorkerServer:
     def __init__(self, worker_id: str, host: str, port: int, device: Optional[torch.device] = None,
-                 verbose: bool = False) -> None:
+                 verbose: bool = False, ssl_context=None) -> None:
         self.id = worker_id
+        self.ssl_context = ssl_context          # control/tls.py::server_context(...): the reference's cert_path / key_path stub
         self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.verbose = verbose
         self.datasets: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -118,8 +119,19 @@ class WorkerServer:
         outer = self
 
         class Handler(socketserver.BaseRequestHandler):
+            def setup(self) -> None:
+                self.tls_failed = False
+                if outer.ssl_context is not None:
+                    self.request.settimeout(10.0)
+                    try:
+                        self.request = outer.ssl_context.wrap_socket(self.request, server_side=True)
+                        self.request.settimeout(None)
+                    except (OSError, ValueError) as e:
+                        log.info("TLS handshake with %s failed: %r", self.client_address, e)
+                        self.tls_failed = True
+
             def handle(self) -> None:
-                while True:
+                while not self.tls_failed:
                     try:
                         req = _recv_msg(self.request)
                     except (ConnectionError, OSError, struct.error):
@@ -220,12 +232,15 @@ class WorkerServer:
 # ---------------------------------------------------------------------------------------------
 class RemoteWorkerClient:
     def __init__(self, worker_id: str, host: str, port: int, timeout: Optional[float] = 10.0,
-                 verbose: bool = False) -> None:
+                 verbose: bool = False, ssl_context=None) -> None:
         self.id = worker_id
         self.host, self.port = host, port
         self.verbose = verbose
         self._lock = threading.Lock()
-        self._sock: Optional[socket.socket] = socket.create_connection((host, port), timeout=timeout)
+        sock = socket.create_connection((host, port), timeout=timeout)
+        if ssl_context is not None:
+            sock = ssl_context.wrap_socket(sock, server_hostname=host)
+        self._sock: Optional[socket.socket] = sock
         self._sock.settimeout(None)
 
     def _call(self, req: Dict[str, Any], timeout: Optional[float] = None) -> Dict[str, Any]:

@@ -67,6 +67,9 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--round-log", type=str, default=None, help="write the reference-format round log here")
     parser.add_argument("--evaluate", action="store_true", help="evaluate the global model on --test-path after training")
     parser.add_argument("--embedded-broker", action="store_true", help="start the TCP bus broker inside this process")
+    parser.add_argument("--tls-ca", default=None, help="CA bundle: verify the broker / the devices (and, with --tls-cert on the embedded broker, demand client certificates)")
+    parser.add_argument("--tls-cert", default=None, help="certificate for the embedded broker / client certificate towards broker and devices")
+    parser.add_argument("--tls-key", default=None, help="private key belonging to --tls-cert")
     parser.add_argument("--inject", action="append", default=[], metavar="SPEC",
                         help="fault injection on the embedded broker: drop:<regex> | dup:<regex> | delay:<seconds>:<regex> (repeatable)")
     parser.add_argument("--exit-after", type=int, default=0, help="exit after N completed trainings (0 = run forever)")
@@ -100,9 +103,14 @@ def main(args: argparse.Namespace) -> None:
     import socket
     import time
 
+    from colearn_federated_learning_b200.control.tls import contexts_from_cli
+
     broker = None
+    client_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=False)
     if args.embedded_broker:
-        broker = TcpBroker("127.0.0.1" if args.host == "localhost" else args.host, args.port).start()
+        server_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=True,
+                                       require_client_cert=bool(args.tls_ca)) if args.tls_cert else None
+        broker = TcpBroker("127.0.0.1" if args.host == "localhost" else args.host, args.port, ssl_context=server_tls).start()
         logging.info("embedded bus broker listening on %s:%d", broker.host, broker.port)
         for spec in args.inject:
             broker.broker.inject_from_spec(spec)
@@ -111,7 +119,10 @@ def main(args: argparse.Namespace) -> None:
                               args=arguments_from_cli(args), transport="tcp", path=args.checkpoint,
                               strict_events=args.strict_events, select_k=args.select, selection=args.selection,
                               fit_timeout=args.fit_timeout, filter_file=args.filter_file,
-                              metrics=RoundLogger(args.metrics, args.round_log), evaluate_after=args.evaluate)
+                              metrics=RoundLogger(args.metrics, args.round_log), evaluate_after=args.evaluate,
+                              worker_ssl_context=client_tls)
+    if client_tls is not None:
+        coordinator.tls_set(context=client_tls)
     try:
         if args.exit_after > 0:
             coordinator.run(args.host, args.port, args.topic, forever=False)

@@ -38,6 +38,9 @@ _OPTIONS = (
     (("--seed",), dict(type=int, default=0)),
     (("--no-cuda",), dict(action="store_true", help="serve fits on the CPU even if a GPU is present")),
     (("--no-will",), dict(action="store_true", help="do not register the NOT_READY last-will with the broker")),
+    (("--tls-ca",), dict(default=None, help="CA bundle: verify the broker; with --tls-cert also demand a client certificate from the coordinator")),
+    (("--tls-cert",), dict(default=None, help="this device's certificate (RPC server side and client certificate towards the broker)")),
+    (("--tls-key",), dict(default=None, help="private key belonging to --tls-cert")),
 )
 
 
@@ -71,7 +74,11 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
     logging.basicConfig(format="%(asctime)s: %(message)s", level=logging.INFO, datefmt="%H:%M:%S")
     identity = f"{args.host}:{args.port}"
     on_gpu = torch.cuda.is_available() and not args.no_cuda
-    server = WorkerServer(identity, args.host, args.port, device=torch.device("cuda" if on_gpu else "cpu"), verbose=args.verbose)
+    from colearn_federated_learning_b200.control.tls import contexts_from_cli
+    rpc_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=True,
+                                require_client_cert=bool(args.tls_ca)) if args.tls_cert else None   # rw.py:60-61
+    server = WorkerServer(identity, args.host, args.port, device=torch.device("cuda" if on_gpu else "cpu"), verbose=args.verbose,
+                          ssl_context=rpc_tls)
     server.add_dataset(pick_dataset(args), key="training")                       # rw.py:108
     if args.inference:
         logging.info("inference data: %s", args.inference)
@@ -80,6 +87,9 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
 
     # one bus identity per device (the reference's shared literal id gets duplicates kicked)
     bus = BusClient(client_id="worker-" + identity, transport="tcp")
+    bus_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=False)
+    if bus_tls is not None:
+        bus.tls_set(context=bus_tls)
     if not args.no_will:
         # if this process dies without a DISCONNECT the broker withdraws the device on our behalf
         bus.will_set(args.topic, format_event(args.host, "NOT_READY", args.port))
