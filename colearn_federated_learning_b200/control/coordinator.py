@@ -251,7 +251,7 @@ class Coordinator(BusClient):
         if n and (round_idx + 1) % n == 0 and round_idx + 1 < self.enabled_round:
             from ..models import state_dict_from_flat
             from ..utils.checkpoint import save_state_dict
-            save_state_dict(state_dict_from_flat(model, theta), self.path, meta={**meta, "rounds": round_idx + 1, "partial": True})
+            save_state_dict(state_dict_from_flat(model, theta), self.path, meta={**meta, "model": self.args.model, "rounds": round_idx + 1, "partial": True})
             log.info("checkpoint after round %d written to %s", round_idx + 1, self.path)
 
     def _deregister(self, trained) -> None:
@@ -299,7 +299,7 @@ class Coordinator(BusClient):
             self._maybe_checkpoint(model, theta, r, {"workers": fed.workers, "mode": "local"})
         log.info("End training")
         unflatten_params(model, theta)
-        save_model(model.cpu(), self.path, meta={"rounds": self.enabled_round, "workers": fed.workers, "mode": "local"})
+        save_model(model.cpu(), self.path, meta={"model": self.args.model, "rounds": self.enabled_round, "workers": fed.workers, "mode": "local"})
         self._deregister(to_train.keys())
         self.metrics.end_training()
         self.trainings_done += 1
@@ -317,7 +317,7 @@ class Coordinator(BusClient):
         model = self._load_model()
         log.info("Distribute the data among the virtual workers...")
         result = train_encrypted(model, self._dataset(), list(to_train.keys()), self.args)
-        save_model(model, self.path, meta={"mode": "encrypted", "workers": list(to_train.keys())})
+        save_model(model, self.path, meta={"model": self.args.model, "mode": "encrypted", "workers": list(to_train.keys())})
         self._deregister(to_train.keys())
         self.trainings_done += 1
         log.info("End encryption")
@@ -386,7 +386,7 @@ class Coordinator(BusClient):
             worker.close()
         self._deregister(to_train.keys())
         unflatten_params(model, theta)
-        save_model(model, self.path, meta={"rounds": self.enabled_round, "workers": list(to_train.keys()), "mode": "remote"})
+        save_model(model, self.path, meta={"model": self.args.model, "rounds": self.enabled_round, "workers": list(to_train.keys()), "mode": "remote"})
         eval_loss = None
         if self.evaluate_after:
             ds = self._dataset()

@@ -307,3 +307,24 @@ def test_osmud_probe_dry_run(tmp_path):
     out = subprocess.run(["sh", os.path.join(root, "data", "osmud_test.sh"), "-d", "1", "7"], capture_output=True, text=True,
                          check=True, cwd=str(tmp_path)).stdout
     assert "+ sleep 7" in out and "run 1/1" in out
+
+
+def test_evaluate_model_tool(tmp_path, capsys):
+    """``tools/evaluate_model``: the reference's (unused) evaluate() as a CLI over a saved checkpoint."""
+    import json
+
+    from colearn_federated_learning_b200.models import MLP, FFNN
+    from colearn_federated_learning_b200.tools import evaluate_model
+    from colearn_federated_learning_b200.utils.checkpoint import save_model
+
+    ck = str(tmp_path / "m.pth")
+    save_model(MLP(), ck, meta={"model": "mlp", "rounds": 1})
+    assert evaluate_model.main(["--checkpoint", ck, "--synthetic", "64", "--json", "--no-cuda"]) == 0
+    res = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert res["model"] == "mlp" and res["n"] == 64 and 0 <= res["accuracy"] <= 1 and res["loss"] > 0
+    # text mode prints the reference's line; a mismatching architecture is refused
+    save_model(FFNN(), ck)
+    assert evaluate_model.main(["--checkpoint", ck, "--model", "ffnn", "--synthetic", "32", "--no-cuda"]) == 0
+    assert "Test set: Average loss:" in capsys.readouterr().out
+    assert evaluate_model.main(["--checkpoint", ck, "--model", "mlp", "--no-cuda"]) == 2
+    assert evaluate_model.main(["--checkpoint", str(tmp_path / "missing.pth"), "--no-cuda"]) == 2
