@@ -24,3 +24,5 @@ timeout 200 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpur
 echo "memcheck rc=$?"; tail -n 3 gpurun_out/r2_sanitizer_memcheck_conv.log
 timeout 80 python bench.py --config cfg4 --steps 5 --warmup 3 > gpurun_out/r2_bench_cfg4_n1.json 2> gpurun_out/r2_bench_cfg4_n1.err
 cut -c1-300 gpurun_out/r2_bench_cfg4_n1.json
+timeout 60 python bench.py --config cfg1 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg1.json 2> gpurun_out/r2_bench_cfg1.err
+cut -c1-200 gpurun_out/r2_bench_cfg1.json
