@@ -145,8 +145,13 @@ def build_all(force: bool = False, verbose: bool = True) -> str:
     return out
 
 
+def main(argv=None) -> int:
+    """``python -m colearn_federated_learning_b200.ops.build [--emul] [--force]`` / ``colearn-build-kernels``."""
+    argv = sys.argv[1:] if argv is None else argv
+    force = "--force" in argv
+    print(build_emul(force=force) if "--emul" in argv else build_all(force=force))
+    return 0
+
+
 if __name__ == "__main__":
-    if "--emul" in sys.argv:
-        print(build_emul(force="--force" in sys.argv))
-    else:
-        print(build_all(force="--force" in sys.argv))
+    sys.exit(main())
