@@ -99,9 +99,12 @@ class ConvNetTrainer:
         return tr
 
     def __init__(self, model: ResNet18, device, batch_size: int, hw: Tuple[int, int] = (32, 32),
-                 act_dtype: torch.dtype = BF) -> None:
+                 act_dtype: torch.dtype = BF, split_k: Optional[bool] = None) -> None:
         """``act_dtype=torch.float32`` (CPU only) keeps every buffer in fp32: the PyTorch definitions of the ops then
-        make the whole step an exact oracle for the orchestration (tests compare it with autograd)."""
+        make the whole step an exact oracle for the orchestration (tests compare it with autograd).  ``split_k``
+        (default: ``COLEARN_CONV_SPLITK=1``) runs the skinny GEMMs — the wgrads of the stem / layer1 / layer2 (1-5 output
+        tiles, reductions over up to 32 768 pixels) and the forwards of layer3 / layer4 — in split-K mode, see
+        :meth:`_pick_split` (``1`` / ``True``: wgrads only, ``2``: forwards too)."""
         assert batch_size % 128 == 0, "the GEMM tiles need batch_size % 128 == 0"
         assert act_dtype == BF or torch.device(device).type == "cpu", "the kernels are bf16"
         self.dev, self.B, self.dt = torch.device(device), batch_size, act_dtype
@@ -185,6 +188,15 @@ class ConvNetTrainer:
         self._graph = None
         self._graph_key = None
         z = lambda *s, dt=act_dtype: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
+        # opt-in (not yet measured on a B200): split-K for the GEMMs with too few output tiles to fill 148 SMs
+        # COLEARN_CONV_SPLITK=1: wgrads only; =2: forwards too
+        self._splitk = int(os.environ.get("COLEARN_CONV_SPLITK", "0") or 0) if split_k is None else int(split_k)
+        for cv in self.convs:
+            cv.s_fwd = self._pick_split(cv.m, cv.cout_pad, cv.K_pad, min_slices=8) if self._splitk >= 2 else 1
+            cv.s_wgrad = self._pick_split(cv.cout_pad, cv.K_pad, cv.m, min_slices=4) if self._splitk >= 1 else 1
+        # fp32 partial accumulators [S, M, N]; forward and wgrad have their own (the wgrad chains may run on a side stream)
+        self.kpart_f = z(max([cv.s_fwd * cv.m * cv.cout_pad for cv in self.convs if cv.s_fwd > 1] or [4]), dt=torch.float32)
+        self.kpart_w = z(max([cv.s_wgrad * cv.cout_pad * cv.K_pad for cv in self.convs if cv.s_wgrad > 1] or [4]), dt=torch.float32)
         max_colT = max(cv.m * cv.K_pad for cv in self.convs)
         max_dzT = max(cv.m * cv.cout_pad for cv in self.convs)
         self.colT = z(max_colT)                        # scratch: colᵀ of the layer whose wgrad runs
@@ -212,6 +224,28 @@ class ConvNetTrainer:
         self.launches = 0
         self.steps_done = 0                            # since the last store() (BatchNorm num_batches_tracked)
         self.steps_total = 0
+
+    @staticmethod
+    def _pick_split(m: int, n: int, k: int, min_slices: int = 2, sms: int = 148) -> int:
+        """Number of K slices for a ``[m, n] = [m, k]·[n, k]ᵀ`` GEMM: 1 when the output already has enough tiles
+        (128 x 256 when ``n % 256 == 0``, else 128 x 128) to occupy the machine, otherwise as many slices as it takes to
+        give every SM a work unit while each slice keeps >= 8 k-blocks of 64 (a pipeline's worth); fewer than
+        ``min_slices`` slices are not worth the extra reduction launch.  E.g. batch 128, 32x32 images: stem wgrad
+        128x256x32768 -> 1 tile x 64 slices; layer1 wgrad 128x640x8192 -> 5 tiles x 16."""
+        tiles = (m // 128) * (n // (256 if n % 256 == 0 else 128))
+        if tiles >= sms // 2:
+            return 1
+        s = min((k // 64) // 8, -(-sms // tiles))
+        return s if s >= max(2, min_slices) else 1
+
+    def _gemm_fwd(self, cv: _Conv) -> None:
+        """``cv.z = cv.col · Wpᵀ`` (bf16), split-K when the layer has few output tiles."""
+        if cv.s_fwd > 1:
+            ops.gemm_bf16(cv.col, self._w(cv.entry), split_k=cv.s_fwd, split_out=self.kpart_f)
+            C.splitk_reduce(self.kpart_f, cv.s_fwd, cv.m * cv.cout_pad, out_bf16=cv.z)
+            self.launches += 1
+        else:
+            ops.gemm_bf16(cv.col, self._w(cv.entry), out_bf16=cv.z)
 
     # -- parameter views ------------------------------------------------------------------------------------------
     def _w(self, e: C.PackEntry) -> torch.Tensor:
@@ -276,7 +310,7 @@ class ConvNetTrainer:
     # -- forward ------------------------------------------------------------------------------------------------------
     def _conv_bn(self, cv: _Conv, x4: torch.Tensor, res: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
         C.im2col(x4, cv.col, cv.k, cv.k, cv.stride, cv.pad)
-        ops.gemm_bf16(cv.col, self._w(cv.entry), out_bf16=cv.z)
+        self._gemm_fwd(cv)
         C.bn_stats(cv.z, cv.cout, self.partial, cv.mean, cv.invstd, cv.rm, cv.rv, cv.eps, cv.momentum, self.bn_counters)
         C.bn_apply(cv.z, cv.cout, cv.mean, cv.invstd, self._s(cv.bn_name + ".weight"), self._s(cv.bn_name + ".bias"),
                    res, relu, cv.out)
@@ -320,7 +354,7 @@ class ConvNetTrainer:
 
         def conv_bn(cv: _Conv, x4, res, relu):
             C.im2col(x4, cv.col, cv.k, cv.k, cv.stride, cv.pad)
-            ops.gemm_bf16(cv.col, self._w(cv.entry), out_bf16=cv.z)
+            self._gemm_fwd(cv)
             C.bn_apply(cv.z, cv.cout, cv.rm, invs[cv.name], self._s(cv.bn_name + ".weight"), self._s(cv.bn_name + ".bias"),
                        res, relu, cv.out)
             return cv.out
@@ -365,8 +399,14 @@ class ConvNetTrainer:
         ops.transpose_bf16(cv.dz, dzT[: cv.cout])
         colT = self.colT[: cv.K_pad * cv.m].view(cv.K_pad, cv.m)
         ops.transpose_bf16(cv.col, colT)
-        ops.gemm_bf16(dzT, colT, sgd_master=self._m(cv.entry), sgd_lr=lr, sgd_shadow=self._w(cv.entry),
-                      sgd_shadow_t=cv.wT if shadow_t else None)
+        if cv.s_wgrad > 1:   # partial sums over pixel slices, then one pass: sum + SGD on the master + bf16 shadow
+            ops.gemm_bf16(dzT, colT, split_k=cv.s_wgrad, split_out=self.kpart_w)
+            C.splitk_reduce(self.kpart_w, cv.s_wgrad, cv.cout_pad * cv.K_pad, master=self._m(cv.entry), lr=lr,
+                            shadow=self._w(cv.entry))
+            self.launches += 1
+        else:
+            ops.gemm_bf16(dzT, colT, sgd_master=self._m(cv.entry), sgd_lr=lr, sgd_shadow=self._w(cv.entry),
+                          sgd_shadow_t=cv.wT if shadow_t else None)
         self.launches += 3
 
     def _conv_bwd(self, cv: _Conv, lr: float, dx: Optional[torch.Tensor], add: Optional[torch.Tensor]) -> None:
@@ -378,7 +418,7 @@ class ConvNetTrainer:
         (``dzT`` / ``colT``) is touched by the side stream alone, ``dcol`` / ``partial`` by the main stream alone."""
         side = self._side
         # Wᵀ straight from the wgrad epilogue (``sgd_shadow_t``) when the layer needs no row padding
-        fuse_t = self._fuse_shadow_t and cv.cout_pad == cv.cout
+        fuse_t = self._fuse_shadow_t and cv.cout_pad == cv.cout and cv.s_wgrad == 1
         if side is None:
             if dx is not None:
                 self._dgrad(cv, dx, add)

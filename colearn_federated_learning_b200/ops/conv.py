@@ -308,3 +308,29 @@ def pack_params(arena: torch.Tensor, packed_f32: torch.Tensor, packed_bf16: Opti
                 dst[: e.rows, : e.cols].copy_(src)
     if not unpack and packed_bf16 is not None:
         packed_bf16.copy_(packed_f32)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# split-K GEMM: reduction of the partial accumulators + the epilogue the un-split GEMM would have fused
+# ----------------------------------------------------------------------------------------------------------
+def splitk_reduce(part: torch.Tensor, splits: int, numel: int, *, master: Optional[torch.Tensor] = None, lr: float = 0.0,
+                  shadow: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None) -> None:
+    """Sum the ``splits`` fp32 partials ``part[s, numel]`` a split-K ``ops.gemm_bf16`` left behind (in slice order)
+    and finish the GEMM: with ``master`` the fused SGD step of a wgrad (``master -= lr·Σ``, ``shadow`` = the bf16
+    copy the next forward reads), otherwise ``out_bf16 = Σ`` rounded to the buffer's dtype."""
+    assert (master is None) != (out_bf16 is None)
+    mod = _native(part)
+    if mod is not None:
+        mod.splitk_reduce(part, int(splits), int(numel), master, float(lr), shadow, out_bf16)
+        return
+    p = part[: splits * numel].view(splits, numel)
+    acc = p[0].clone()
+    for s in range(1, splits):
+        acc += p[s]
+    if master is not None:
+        m = master.view(-1)[:numel]
+        m.sub_(lr * acc)
+        if shadow is not None:
+            shadow.view(-1)[:numel].copy_(m)
+    else:
+        out_bf16.view(-1)[:numel].copy_(acc)

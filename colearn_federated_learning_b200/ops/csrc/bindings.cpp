@@ -360,7 +360,7 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                   c10::optional<torch::Tensor> sgd_master, double sgd_lr, c10::optional<torch::Tensor> sgd_shadow,
                   c10::optional<torch::Tensor> sgd_shadow_t, c10::optional<torch::Tensor> colsum,
                   int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset, int64_t tile_n,
-                  int64_t ready_epoch_ptr, int64_t cluster) {
+                  int64_t ready_epoch_ptr, int64_t cluster, int64_t split_k, c10::optional<torch::Tensor> split_out) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "A,B must be CUDA bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous() && A.size(1) == B.size(1), "A[M,K], B[N,K]");
   c10::cuda::CUDAGuard guard(A.device());
@@ -391,6 +391,12 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.ready_elem_offset = ready_elem_offset;
   ep.tile_n = (int)tile_n;
   ep.cluster = (int)cluster;
+  if (split_k > 1) {
+    TORCH_CHECK(split_out.has_value() && split_out->is_cuda() && split_out->scalar_type() == at::kFloat && split_out->is_contiguous() &&
+                split_out->numel() >= split_k * (int64_t)M * N, "split_out must be a contiguous CUDA fp32 tensor with >= split_k*M*N elements");
+    ep.split_k = (int)split_k;
+    ep.split_out = split_out->data_ptr<float>();
+  }
   cudaError_t e = launch_gemm_tcgen05(A.data_ptr(), B.data_ptr(), M, N, K, ep, cur_stream());
   TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05: ", cudaGetErrorString(e), " (", gemm_tcgen05_last_error(), ")");
 }
@@ -410,6 +416,7 @@ struct ConvCudaExec {
   static void avgpool_fwd(const convops::AvgPoolArgs& a) { check(launch_avgpool_fwd(a, cur_stream()), "avgpool_fwd"); }
   static void avgpool_bwd(const convops::AvgPoolArgs& a) { check(launch_avgpool_bwd(a, cur_stream()), "avgpool_bwd"); }
   static void pack(const convops::PackArgs& a) { check(launch_pack(a, cur_stream()), "pack"); }
+  static void splitk_reduce(const convops::SplitKReduceArgs& a) { check(launch_splitk_reduce(a, cur_stream()), "splitk_reduce"); }
 };
 
 }  // namespace

@@ -209,6 +209,12 @@ struct GemmEpilogue {
   int tile_n;               // 0 = auto, 128 or 256 = force the N tile width
   int cluster;              // 3 = cta_group::2 (two SMs per 256x256 tile, UMMA M=256; needs M%256==0, N%256==0);
                             // 2 = pairs of CTAs + TMA multicast of the shared B tile (M%256==0, tile 256); else off
+  // split-K (skinny problems: few output tiles, long reduction — the conv wgrads): the K range of every output tile
+  // is cut into split_k slices that run as independent work units; slice s stores its raw fp32 accumulator to
+  // split_out[s, M, N] and NO other epilogue op runs (launch_splitk_reduce sums the slices and applies the epilogue:
+  // fused SGD or bf16 output).  split_k <= 1: off.  1-CTA kernel only; needs K/64 >= split_k.
+  int split_k;
+  float* split_out;         // fp32 [split_k, M, N]
 };
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,
@@ -230,5 +236,6 @@ cudaError_t launch_maxpool_bwd(const convops::PoolArgs& a, cudaStream_t s);
 cudaError_t launch_avgpool_fwd(const convops::AvgPoolArgs& a, cudaStream_t s);
 cudaError_t launch_avgpool_bwd(const convops::AvgPoolArgs& a, cudaStream_t s);
 cudaError_t launch_pack(const convops::PackArgs& a, cudaStream_t s);
+cudaError_t launch_splitk_reduce(const convops::SplitKReduceArgs& a, cudaStream_t s);
 
 }  // namespace colearn

@@ -59,6 +59,7 @@ struct ConvHostExec {
   static void pack(const PackArgs& a) {
     for (long long e = 0; e < a.total; ++e) pack_body(a, e);
   }
+  static void splitk_reduce(const SplitKReduceArgs& a) { run_map(a, splitk_reduce_items, splitk_reduce_body); }
 };
 }  // namespace
 

@@ -494,5 +494,50 @@ CL_HD void pack_body(const PackArgs& a, long long e) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Split-K reduction: the tcgen05 GEMM in split-K mode leaves S raw fp32 partial accumulators part[s, rows, cols]
+// (gemm_tcgen05.cu, GemmEpilogue::split_k); this map sums them in slice order (deterministic) and applies the
+// epilogue the un-split GEMM would have fused:
+//   master != null : fused SGD of the wgrad GEMMs  master -= lr * sum ; shadow = bf16(master)
+//   else           : out_bf16 = bf16(sum)          (conv forward: the next activation matrix)
+// One work item = 4 consecutive elements (float4 loads, one 8-byte bf16x4 store).
+// ------------------------------------------------------------------------------------------------------
+struct alignas(8) BF4 {
+  __nv_bfloat16 v[4];
+};
+struct alignas(16) F4 {
+  float v[4];
+};
+struct SplitKReduceArgs {
+  const float* part;            // [S, numel]
+  int S;
+  long long numel;              // rows * cols of one slice (multiple of 4)
+  float* master;                // [numel] fp32 master weights, updated in place; or null
+  float lr;
+  __nv_bfloat16* shadow;        // [numel] bf16 copy of the updated master; or null
+  __nv_bfloat16* out_bf16;      // [numel] bf16(sum) when master == null
+};
+CL_HD long long splitk_reduce_items(const SplitKReduceArgs& a) { return a.numel / 4; }
+CL_HD void splitk_reduce_body(const SplitKReduceArgs& a, long long item) {
+  const long long e = item * 4;
+  F4 acc = *reinterpret_cast<const F4*>(a.part + e);
+  for (int s = 1; s < a.S; ++s) {
+    const F4 t = *reinterpret_cast<const F4*>(a.part + (long long)s * a.numel + e);
+    for (int j = 0; j < 4; ++j) acc.v[j] += t.v[j];
+  }
+  BF4 o;
+  if (a.master) {
+    F4 w = *reinterpret_cast<const F4*>(a.master + e);
+    for (int j = 0; j < 4; ++j) w.v[j] = fmaf(-a.lr, acc.v[j], w.v[j]);   // same expression as the fused GEMM epilogue
+    *reinterpret_cast<F4*>(a.master + e) = w;
+    if (!a.shadow) return;
+    for (int j = 0; j < 4; ++j) o.v[j] = f2bf(w.v[j]);
+    *reinterpret_cast<BF4*>(a.shadow + e) = o;
+  } else {
+    for (int j = 0; j < 4; ++j) o.v[j] = f2bf(acc.v[j]);
+    *reinterpret_cast<BF4*>(a.out_bf16 + e) = o;
+  }
+}
+
 }  // namespace convops
 }  // namespace colearn

@@ -35,6 +35,7 @@ COLEARN_MAP_KERNEL(avgpool_bwd_kernel, AvgPoolArgs, avgpool_bwd_items, avgpool_b
 
 __device__ __forceinline__ long long pack_items(const PackArgs& a) { return a.total; }
 COLEARN_MAP_KERNEL(pack_kernel, PackArgs, pack_items, pack_body)
+COLEARN_MAP_KERNEL(splitk_reduce_kernel, SplitKReduceArgs, splitk_reduce_items, splitk_reduce_body)
 
 // grid = (C/64, nseg), 256 threads
 __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const BnReduceArgs a) {
@@ -114,6 +115,10 @@ cudaError_t launch_avgpool_bwd(const AvgPoolArgs& a, cudaStream_t s) {
 }
 cudaError_t launch_pack(const PackArgs& a, cudaStream_t s) {
   pack_kernel<<<map_grid(a.total), kMapThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_splitk_reduce(const SplitKReduceArgs& a, cudaStream_t s) {
+  splitk_reduce_kernel<<<map_grid(splitk_reduce_items(a)), kMapThreads, 0, s>>>(a);
   return cudaGetLastError();
 }
 

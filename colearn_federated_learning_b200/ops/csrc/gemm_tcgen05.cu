@@ -203,6 +203,9 @@ __device__ __forceinline__ void work_to_tile(int w, int m_units, int n_tiles, in
   n_blk = r / gsz;
 }
 
+// k-block range of K slice s of S: [split_kb(s), split_kb(s + 1)); non-empty for every s when num_kb >= S
+__host__ __device__ __forceinline__ int split_kb(int num_kb, int s, int S) { return (int)(((long long)num_kb * s) / S); }
+
 struct SharedBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -323,7 +326,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int m_tiles = M / BM, n_tiles = N / BN, num_kb = K / BK;
   // work unit = one tile (CL == 1) or a vertical pair of tiles handled by the two CTAs of a cluster (CL == 2)
   const int m_units = m_tiles / CL;
-  const int total_work = m_units * n_tiles;
+  // split-K (CL == 1 only): work unit = (output tile, K slice); slices of one tile are adjacent work units, so they
+  // run concurrently on different SMs and each stores a raw fp32 partial (see GemmEpilogue::split_k)
+  const int S = (CL == 1 && ep.split_k > 1) ? ep.split_k : 1;
+  const int total_work = m_units * n_tiles * S;
   const int work0 = blockIdx.x / CL, work_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
@@ -347,7 +353,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       for (int tile = work0; tile < total_work; tile += work_stride) {
         int mu, nb;
-        work_to_tile(tile, m_units, n_tiles, mu, nb);
+        work_to_tile(tile / S, m_units, n_tiles, mu, nb);
+        const int ks = tile % S;
+        const int kb_lo = split_kb(num_kb, ks, S), kb_hi = split_kb(num_kb, ks + 1, S);
         const int m0 = (mu * CL + (int)crank) * BM, n0 = nb * BN;
         if (ep.ready_flags != nullptr) {
           const uint32_t want = ep.ready_epoch_ptr ? ld_acquire_sys(ep.ready_epoch_ptr) : ep.ready_epoch;
@@ -365,7 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
           tma_load_2d(smem_a + stage * kStageBytesA, &tmap_a, kb * BK, m0, &bars->full[stage]);
@@ -393,7 +401,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int ks = tile % S;
+        const int kb_lo = split_kb(num_kb, ks, S), kb_hi = split_kb(num_kb, ks + 1, S);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * kStageBytesA));
@@ -401,7 +411,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in (addr>>4) units
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
           }
           if (CL == 2) umma_commit_mcast(&bars->empty[stage], (uint16_t)0x3);  // both producers write into this stage
           else umma_commit(&bars->empty[stage]);
@@ -417,19 +427,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int local = 0;
     for (int tile = work0; tile < total_work; tile += work_stride, ++local) {
       int mu, nb;
-        work_to_tile(tile, m_units, n_tiles, mu, nb);
-        const int m0 = (mu * CL + (int)crank) * BM, n0 = nb * BN;
+      work_to_tile(tile / S, m_units, n_tiles, mu, nb);
+      const int m0 = (mu * CL + (int)crank) * BM, n0 = nb * BN;
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
+      // split-K: this work unit's raw accumulator goes to slice (tile % S) of the fp32 partial buffer
+      float* part = (S > 1) ? ep.split_out + ((size_t)(tile % S) * M + row) * N + n0 : nullptr;
 #pragma unroll 1
       for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
         tmem_ld_wait();
-        epilogue_chunk(v, ep, row, n0 + c0, lane, q, m0, M, N);
+        if (S > 1) {
+          float4* op = reinterpret_cast<float4*>(part + c0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            op[g] = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                                __uint_as_float(v[g * 4 + 3]));
+        } else {
+          epilogue_chunk(v, ep, row, n0 + c0, lane, q, m0, M, N);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -515,7 +535,7 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
-  const int work = (M / BM / CL) * (N / BN);
+  const int work = (M / BM / CL) * (N / BN) * ((CL == 1 && ep.split_k > 1) ? ep.split_k : 1);
   int units = num_sms[dev & 63] / CL;          // persistent: one CTA (or CTA pair) per SM (pair)
   if (work < units) units = work;
   if (units < 1) units = 1;
@@ -738,6 +758,20 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
     return cudaErrorInvalidValue;
   }
   if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
+  if (ep.split_k > 1) {
+    // split-K: raw fp32 partials only, 1-CTA kernel; 128x256 tiles whenever N allows (half the B smem traffic per FLOP)
+    if (ep.split_out == nullptr) { g_last_error = "split_k needs split_out"; return cudaErrorInvalidValue; }
+    if (K / BK < ep.split_k) { g_last_error = "split_k must not exceed K/64"; return cudaErrorInvalidValue; }
+    if (ep.cluster != 0 || ep.ready_flags != nullptr || ep.bias || ep.relu || ep.relu_mask || ep.out_bf16 || ep.out_f32 ||
+        ep.out_bf16_t || ep.sgd_master || ep.colsum) {
+      g_last_error = "split_k stores raw partials: no other epilogue / cluster / ready-flag option may be set";
+      return cudaErrorInvalidValue;
+    }
+    if (((uintptr_t)ep.split_out) & 15) { g_last_error = "split_out must be 16-byte aligned"; return cudaErrorInvalidValue; }
+    if (ep.tile_n == 256 && (N % 256)) { g_last_error = "tile_n=256 needs N%256==0"; return cudaErrorInvalidValue; }
+    if (ep.tile_n == 256 || (ep.tile_n == 0 && N % 256 == 0)) return launch_t<256, 1>(A, B, M, N, K, ep, s);
+    return launch_t<128, 1>(A, B, M, N, K, ep, s);
+  }
   // BN=256 when it divides N and leaves enough tiles to fill the machine; BN=128 otherwise
   // cta_group::2 (two SMs per 256x256 tile): forced with cluster == 3, automatic when the shape allows it and there
   // are enough tile pairs to fill the machine (measured: 1 485 vs 1 263 TFLOP/s at 4096^3, equal at 1024x4096x4096)

@@ -21,9 +21,26 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
               sgd_shadow: Optional[torch.Tensor] = None, sgd_shadow_t: Optional[torch.Tensor] = None,
               colsum: Optional[torch.Tensor] = None, ready_flags: int = 0, ready_epoch: int = 0,
               ready_chunk_elems: int = 1, ready_elem_offset: int = 0, tile_n: int = 0,
-              ready_epoch_ptr: int = 0, cluster: int = 0) -> None:
-    """Launch the tcgen05 GEMM; results land in the provided output tensors."""
+              ready_epoch_ptr: int = 0, cluster: int = 0, split_k: int = 0,
+              split_out: Optional[torch.Tensor] = None) -> None:
+    """Launch the tcgen05 GEMM; results land in the provided output tensors.
+
+    ``split_k = S > 1`` (skinny problems: few output tiles, long reduction): the K range is cut into S slices that
+    run as independent work units; slice ``s`` stores its raw fp32 accumulator to ``split_out[s]`` (``[S, M, N]``)
+    and no other epilogue option may be given — ``ops.conv.splitk_reduce`` sums the slices and applies the epilogue."""
+    if split_k and split_k > 1:
+        assert split_out is not None and split_out.numel() >= split_k * a.shape[0] * b.shape[0]
+        assert (bias is None and not relu and relu_mask is None and out_bf16 is None and out_f32 is None and out_bf16_t is None
+                and sgd_master is None and colsum is None and not ready_flags), "split-K stores raw partials only"
+        assert a.shape[1] // 64 >= split_k, "split_k must not exceed K/64"
     if not a.is_cuda:
+        if split_k and split_k > 1:   # same slice boundaries as the kernel: k-blocks of 64, slice s = [nkb*s/S, nkb*(s+1)/S)
+            nkb = a.shape[1] // 64
+            part = split_out[: split_k * a.shape[0] * b.shape[0]].view(split_k, a.shape[0], b.shape[0])
+            for s_ in range(split_k):
+                lo, hi = nkb * s_ // split_k * 64, nkb * (s_ + 1) // split_k * 64
+                part[s_].copy_(a[:, lo:hi].float() @ b[:, lo:hi].float().t())
+            return
         acc = a.float() @ b.float().t()
         if bias is not None:
             acc = acc + bias
@@ -49,7 +66,8 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
         return
     _ext.require().gemm_tcgen05(a, b, bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
                                 float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(ready_flags), int(ready_epoch),
-                                int(ready_chunk_elems), int(ready_elem_offset), int(tile_n), int(ready_epoch_ptr), int(cluster))
+                                int(ready_chunk_elems), int(ready_elem_offset), int(tile_n), int(ready_epoch_ptr), int(cluster),
+                                int(split_k or 0), split_out)
 
 
 def linear_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,

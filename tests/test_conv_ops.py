@@ -314,3 +314,71 @@ def test_fused_batchnorm_reduction_kernel_bodies_on_host(m, c, ldx):
     """Single-launch BatchNorm reduction (the last block of a column group finalises, the ticket counter resets
     itself): the host build of the bodies against the definitions.  The sm_100a run lives in test_zz_round2_gpu."""
     _batchnorm_case("emul", m, c, ldx, fused=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# split-K GEMM: partial accumulators + the reduction that applies the epilogue
+# ---------------------------------------------------------------------------------------------------------------------
+def test_splitk_reference_slices_add_up_to_the_plain_gemm():
+    """``gemm_bf16(split_k=S)`` on the CPU defines the slice boundaries the kernel uses (k-blocks of 64, slice s =
+    [nkb·s/S, nkb·(s+1)/S)); the slices must partition K for every S <= nkb, including S that do not divide nkb."""
+    from colearn_federated_learning_b200 import ops
+    torch.manual_seed(0)
+    a, b = torch.randn(128, 64 * 7).to(BF), torch.randn(256, 64 * 7).to(BF)
+    want = a.float() @ b.float().t()
+    for s in (2, 3, 7):
+        part = torch.full((s * 128 * 256 + 5,), 7.0)
+        ops.gemm_bf16(a, b, split_k=s, split_out=part)
+        torch.testing.assert_close(part[: s * 128 * 256].view(s, 128, 256).sum(0), want, rtol=1e-5, atol=1e-4)
+        assert float(part[s * 128 * 256:].min()) == 7.0
+    with pytest.raises(AssertionError):
+        ops.gemm_bf16(a, b, split_k=8, split_out=torch.zeros(8 * 128 * 256))          # more slices than k-blocks
+    with pytest.raises(AssertionError):
+        ops.gemm_bf16(a, b, split_k=2, split_out=torch.zeros(2 * 128 * 256), out_f32=torch.zeros(128, 256))
+
+
+@pytest.mark.parametrize("splits,rows,cols", [(2, 128, 128), (16, 128, 640), (64, 128, 256), (5, 4, 12)])
+def test_splitk_reduce_kernel_body_on_host(splits, rows, cols):
+    _splitk_reduce_case("emul", splits, rows, cols)
+
+
+def _splitk_reduce_case(backend, splits, rows, cols):
+    """Sum of the slices in slice order, then either the fused SGD step (fp32 master in place + bf16 shadow) or the
+    bf16 output — bit-exact against the same expressions in PyTorch (fmaf for the SGD update)."""
+    torch.manual_seed(splits)
+    n = rows * cols
+    part = torch.randn(splits, n)
+    master0 = torch.randn(n)
+    acc = part[0].clone()
+    for s in range(1, splits):
+        acc += part[s]
+    lr = 0.05
+    want_master = torch.addcmul(master0.double(), torch.tensor(-lr, dtype=torch.float32).double(), acc.double()).float()
+    with backend_ctx(backend) as dev:
+        p = torch.cat([part.reshape(-1), torch.full((8,), float("nan"))]).to(dev)     # slack must not be read
+        master, shadow = master0.clone().to(dev), torch.zeros(n, dtype=BF, device=dev)
+        conv.splitk_reduce(p, splits, n, master=master, lr=lr, shadow=shadow)
+        out = torch.zeros(n + 4, dtype=BF, device=dev)
+        conv.splitk_reduce(p, splits, n, out_bf16=out)
+        only_master = master0.clone().to(dev)
+        conv.splitk_reduce(p, splits, n, master=only_master, lr=lr)
+    # fmaf(-lr, acc, w) rounds once: the double-precision product + sum rounded to fp32 is the same number
+    torch.testing.assert_close(master.cpu(), want_master, rtol=0, atol=0)
+    assert torch.equal(only_master.cpu(), master.cpu())
+    assert torch.equal(shadow.cpu(), want_master.to(BF))
+    assert torch.equal(out[:n].cpu(), acc.to(BF)) and float(out[n:].float().abs().max()) == 0
+    # the definitions agree with the kernel bodies up to the non-fused multiply-add
+    m2, s2 = master0.clone(), torch.zeros(n, dtype=BF)
+    conv.splitk_reduce(part.reshape(-1).clone(), splits, n, master=m2, lr=lr, shadow=s2)
+    torch.testing.assert_close(m2, want_master, rtol=1e-6, atol=1e-6)
+
+
+def test_splitk_reduce_rejects_bad_arguments():
+    with conv.emulated():
+        p = torch.zeros(2 * 8)
+        with pytest.raises(RuntimeError):
+            conv.splitk_reduce(p, 2, 6, out_bf16=torch.zeros(6, dtype=BF))             # numel % 4
+        with pytest.raises(RuntimeError):
+            conv.splitk_reduce(p, 3, 8, out_bf16=torch.zeros(8, dtype=BF))             # part too small
+        with pytest.raises(RuntimeError):
+            conv.splitk_reduce(p, 2, 8, out_bf16=torch.zeros(4, dtype=BF))             # output too small

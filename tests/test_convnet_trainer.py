@@ -62,6 +62,53 @@ def test_fp32_oracle_step_equals_autograd():
             assert int(m.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("level", [1, 2])
+def test_split_k_schedule_is_the_same_step(level):
+    """Split-K (wgrads of the stem / layer1 / layer2 cut over pixel slices, level 2: the layer4 forwards too) only
+    changes the fp32 summation order: in fp32-oracle mode the step must agree with the un-split step to rounding,
+    and with bf16 buffers through the host build of the kernel bodies it must stay in the same class."""
+    torch.manual_seed(0)
+    model = ResNet18(10)
+    flat0 = flatten_params(model).clone()
+    x, y = torch.randn(B, 3, 32, 32), torch.randint(0, 10, (B,))
+
+    def run(split, dtype, emul=False):
+        flat = flat0.clone()
+        tr = ConvNetTrainer(model, "cpu", B, (32, 32), act_dtype=dtype, split_k=split)
+        with (conv.emulated() if emul else contextlib.nullcontext()):
+            tr.load(flat, None)
+            loss = float(tr.step(x, y, 0.05))
+            tr.store(flat, None)
+        return flat, loss, tr
+
+    base, loss0, tr0 = run(0, torch.float32)
+    got, loss1, tr1 = run(level, torch.float32)
+    assert all(cv.s_wgrad == 1 and cv.s_fwd == 1 for cv in tr0.convs)
+    assert tr1.stem.s_wgrad == 64 and tr1.blocks[0].c1.s_wgrad == 16 and tr1.blocks[2].c1.s_wgrad == 4
+    assert (max(cv.s_fwd for cv in tr1.convs) > 1) == (level == 2)
+    assert tr1.launches > tr0.launches                      # one reduction launch per split GEMM
+    assert abs(loss0 - loss1) < 1e-4
+    rel = float((got - base).norm() / (base - flat0).norm())
+    assert rel < 1e-4, rel
+    # bf16 buffers, host build of the kernel bodies (splitk_reduce_body): same class as the un-split bf16 step
+    b16, _, _ = run(0, torch.bfloat16, emul=True)
+    s16, _, _ = run(level, torch.bfloat16, emul=True)
+    d0, d1 = b16 - flat0, s16 - flat0
+    assert float((d0 * d1).sum() / (d0.norm() * d1.norm())) > (0.999 if level == 1 else 0.95)
+
+
+def test_pick_split_heuristic():
+    pick = ConvNetTrainer._pick_split
+    assert pick(128, 256, 32768) == 64          # stem wgrad: 1 tile of 128x256, 512 k-blocks -> 64 slices of 8
+    assert pick(128, 640, 8192) == 16           # layer1 wgrad: 5 tiles of 128x128, 128 k-blocks
+    assert pick(128, 640, 8192, min_slices=32) == 1
+    assert pick(32768, 128, 256) == 1           # plenty of tiles
+    assert pick(128, 128, 64) == 1              # nothing to split
+    for m, n, k in [(128, 256, 32768), (128, 640, 8192), (128, 1152, 2048), (128, 512, 4608)]:
+        s = pick(m, n, k)
+        assert s == 1 or (k // 64) // s >= 8    # every slice keeps a pipeline's worth of k-blocks
+
+
 @pytest.mark.parametrize("mode", ["fp32", "definitions", "emulated"])
 def test_eval_mode_inference_matches_module_eval(mode):
     """``infer``: eval-mode forward (running statistics) in chunks of 128 with a zero-padded last chunk."""

@@ -96,3 +96,74 @@ def test_optional_step_optimisations_do_not_change_the_result(flags, monkeypatch
         torch.testing.assert_close(got, base, rtol=1e-2, atol=1e-3)
     else:
         assert torch.equal(got, base)
+
+
+@unvalidated
+@pytest.mark.parametrize("splits,rows,cols", [(2, 128, 128), (16, 128, 640), (64, 128, 256), (5, 4, 12)])
+def test_splitk_reduce_kernel(splits, rows, cols):
+    _dev()
+    from test_conv_ops import _splitk_reduce_case
+    _splitk_reduce_case("cuda", splits, rows, cols)
+
+
+@unvalidated
+@pytest.mark.parametrize("m,n,k,s,tile_n", [(128, 256, 32768, 64, 0), (128, 640, 8192, 16, 0), (256, 128, 4096, 3, 0),
+                                            (512, 512, 1024, 4, 128), (128, 512, 4608, 9, 256), (1024, 256, 512, 8, 0)])
+def test_gemm_split_k_partials(m, n, k, s, tile_n):
+    """Split-K mode of the 1-CTA tcgen05 GEMM: every slice's raw accumulator against the fp32 product of the same
+    K range (slice boundaries = the CPU definition's), their sum against the un-split kernel, untouched slack."""
+    dev = _dev()
+    from colearn_federated_learning_b200 import ops
+    torch.manual_seed(m + n + s)
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16)
+    b = torch.randn(n, k, device=dev).to(torch.bfloat16)
+    part = torch.full((s * m * n + 64,), 7.0, device=dev)
+    ops.gemm_bf16(a, b, split_k=s, split_out=part, tile_n=tile_n)
+    plain = torch.empty(m, n, device=dev)
+    ops.gemm_bf16(a, b, out_f32=plain)
+    torch.cuda.synchronize()
+    assert float(part[s * m * n:].min()) == 7.0 and float(part[s * m * n:].max()) == 7.0
+    want = torch.zeros(s * m * n + 64)
+    ops.gemm_bf16(a.cpu(), b.cpu(), split_k=s, split_out=want)
+    got = part[: s * m * n].view(s, m, n).cpu()
+    torch.testing.assert_close(got, want[: s * m * n].view(s, m, n), rtol=2e-3, atol=2e-2 * (k / s / 512) ** 0.5)
+    torch.testing.assert_close(got.sum(0), plain.cpu(), rtol=2e-3, atol=5e-2)
+    # and through the reduction: the bf16 result of the un-split kernel
+    out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    ref = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    from colearn_federated_learning_b200.ops import conv as C
+    C.splitk_reduce(part, s, m * n, out_bf16=out)
+    ops.gemm_bf16(a, b, out_bf16=ref)
+    torch.testing.assert_close(out.float().cpu(), ref.float().cpu(), rtol=1.6e-2, atol=0.5)
+
+
+@unvalidated
+@pytest.mark.parametrize("level", ["1", "2"])
+def test_split_k_step_matches_default_schedule(level, monkeypatch):
+    """COLEARN_CONV_SPLITK: two ResNet-18 steps (one eager, one through the CUDA graph) against the default schedule —
+    the split only changes the fp32 summation order of the affected GEMMs."""
+    dev = _dev()
+    torch.manual_seed(0)
+    x = torch.randn(256, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (256,), device=dev)
+
+    def run():
+        torch.manual_seed(1)
+        model = ResNet18(10).to(dev)
+        flat = flatten_params(model)
+        flat0 = flat.clone()
+        tr = ConvNetTrainer(model, dev, 128, (32, 32))
+        tr.load(flat, model)
+        for lo in (0, 128):
+            tr._graph_step(x[lo:lo + 128], y[lo:lo + 128], 0.05)
+        tr.store(flat, model)
+        torch.cuda.synchronize()
+        return flat.clone() - flat0
+
+    monkeypatch.delenv("COLEARN_CONV_SPLITK", raising=False)
+    base = run()
+    monkeypatch.setenv("COLEARN_CONV_SPLITK", level)
+    got = run()
+    cos = float((got * base).sum() / (got.norm() * base.norm()))
+    assert cos > 0.98, cos
+    assert torch.isfinite(got).all()
