@@ -99,12 +99,14 @@ class ConvNetTrainer:
         return tr
 
     def __init__(self, model: ResNet18, device, batch_size: int, hw: Tuple[int, int] = (32, 32),
-                 act_dtype: torch.dtype = BF, split_k: Optional[bool] = None) -> None:
+                 act_dtype: torch.dtype = BF, split_k: Optional[bool] = None, wgrad_mn: Optional[bool] = None) -> None:
         """``act_dtype=torch.float32`` (CPU only) keeps every buffer in fp32: the PyTorch definitions of the ops then
         make the whole step an exact oracle for the orchestration (tests compare it with autograd).  ``split_k``
         (default: ``COLEARN_CONV_SPLITK=1``) runs the skinny GEMMs — the wgrads of the stem / layer1 / layer2 (1-5 output
         tiles, reductions over up to 32 768 pixels) and the forwards of layer3 / layer4 — in split-K mode, see
-        :meth:`_pick_split` (``1`` / ``True``: wgrads only, ``2``: forwards too)."""
+        :meth:`_pick_split` (``1`` / ``True``: wgrads only, ``2``: forwards too).  ``wgrad_mn`` (default:
+        ``COLEARN_CONV_WGRAD_MN=1``) feeds the wgrad GEMMs ``dz`` and ``col`` as they are (MN-major UMMA operands,
+        reduction over rows) instead of transposing both first."""
         assert batch_size % 128 == 0, "the GEMM tiles need batch_size % 128 == 0"
         assert act_dtype == BF or torch.device(device).type == "cpu", "the kernels are bf16"
         self.dev, self.B, self.dt = torch.device(device), batch_size, act_dtype
@@ -189,6 +191,8 @@ class ConvNetTrainer:
         self._graph_key = None
         z = lambda *s, dt=act_dtype: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
         # opt-in (not yet measured on a B200): split-K for the GEMMs with too few output tiles to fill 148 SMs
+        # opt-in (not yet measured on a B200): wgrad GEMMs on MN-major operands — no dz^T / col^T transposes
+        self._wgrad_mn = (os.environ.get("COLEARN_CONV_WGRAD_MN") == "1") if wgrad_mn is None else bool(wgrad_mn)
         # COLEARN_CONV_SPLITK=1: wgrads only; =2: forwards too
         self._splitk = int(os.environ.get("COLEARN_CONV_SPLITK", "0") or 0) if split_k is None else int(split_k)
         for cv in self.convs:
@@ -393,6 +397,19 @@ class ConvNetTrainer:
         self.launches += 2
 
     def _wgrad(self, cv: _Conv, lr: float, shadow_t: bool = False) -> None:
+        if self._wgrad_mn:
+            # dW[Cout, k] = Σ_pixels dz[pixel, Cout]·col[pixel, k]: both operands are read in place (rows = the
+            # reduction index); the Cout padding rows of the tile are TMA zero fill
+            if cv.s_wgrad > 1:
+                ops.gemm_bf16(cv.dz, cv.col, mn_m=cv.cout_pad, split_k=cv.s_wgrad, split_out=self.kpart_w)
+                C.splitk_reduce(self.kpart_w, cv.s_wgrad, cv.cout_pad * cv.K_pad, master=self._m(cv.entry), lr=lr,
+                                shadow=self._w(cv.entry))
+                self.launches += 1
+            else:
+                ops.gemm_bf16(cv.dz, cv.col, mn_m=cv.cout_pad, sgd_master=self._m(cv.entry), sgd_lr=lr,
+                              sgd_shadow=self._w(cv.entry), sgd_shadow_t=cv.wT if shadow_t else None)
+            self.launches += 1
+            return
         dzT = self.dzT[: cv.cout_pad * cv.m].view(cv.cout_pad, cv.m)
         if cv.cout_pad != cv.cout:
             dzT[cv.cout:].zero_()

@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -360,11 +361,15 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                   c10::optional<torch::Tensor> sgd_master, double sgd_lr, c10::optional<torch::Tensor> sgd_shadow,
                   c10::optional<torch::Tensor> sgd_shadow_t, c10::optional<torch::Tensor> colsum,
                   int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset, int64_t tile_n,
-                  int64_t ready_epoch_ptr, int64_t cluster, int64_t split_k, c10::optional<torch::Tensor> split_out) {
+                  int64_t ready_epoch_ptr, int64_t cluster, int64_t split_k, c10::optional<torch::Tensor> split_out,
+                  int64_t mn_m) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "A,B must be CUDA bf16");
-  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous() && A.size(1) == B.size(1), "A[M,K], B[N,K]");
+  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous(), "A, B must be contiguous matrices");
+  // mn_m > 0: "MN-major" operands A[K, a_cols], B[K, N] (C = A^T B, M = mn_m >= a_cols); else A[M, K], B[N, K]
+  const bool mn = mn_m > 0;
+  TORCH_CHECK(mn ? A.size(0) == B.size(0) : A.size(1) == B.size(1), mn ? "A[K,a_cols], B[K,N]" : "A[M,K], B[N,K]");
   c10::cuda::CUDAGuard guard(A.device());
-  const int M = (int)A.size(0), N = (int)B.size(0), K = (int)A.size(1);
+  const int M = mn ? (int)mn_m : (int)A.size(0), N = mn ? (int)B.size(1) : (int)B.size(0), K = mn ? (int)A.size(0) : (int)A.size(1);
   GemmEpilogue ep;
   std::memset(&ep, 0, sizeof(ep));
   auto chk = [&](const c10::optional<torch::Tensor>& t, at::ScalarType st, int64_t r, int64_t c, const char* name) -> void* {
@@ -396,6 +401,15 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                 split_out->numel() >= split_k * (int64_t)M * N, "split_out must be a contiguous CUDA fp32 tensor with >= split_k*M*N elements");
     ep.split_k = (int)split_k;
     ep.split_out = split_out->data_ptr<float>();
+  }
+  if (mn) {
+    static const int dbg_lbo = std::getenv("COLEARN_UMMA_MN_LBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_LBO")) : 0;
+    static const int dbg_sbo = std::getenv("COLEARN_UMMA_MN_SBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_SBO")) : 0;
+    ep.mn_lbo = dbg_lbo;
+    ep.mn_sbo = dbg_sbo;
+    cudaError_t e = launch_gemm_tcgen05_mn(A.data_ptr(), (int)A.size(1), B.data_ptr(), M, N, K, ep, cur_stream());
+    TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05 (mn-major): ", cudaGetErrorString(e), " (", gemm_tcgen05_last_error(), ")");
+    return;
   }
   cudaError_t e = launch_gemm_tcgen05(A.data_ptr(), B.data_ptr(), M, N, K, ep, cur_stream());
   TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05: ", cudaGetErrorString(e), " (", gemm_tcgen05_last_error(), ")");

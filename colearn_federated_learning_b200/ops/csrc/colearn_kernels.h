@@ -215,10 +215,16 @@ struct GemmEpilogue {
   // fused SGD or bf16 output).  split_k <= 1: off.  1-CTA kernel only; needs K/64 >= split_k.
   int split_k;
   float* split_out;         // fp32 [split_k, M, N]
+  // debug overrides of the MN-major shared-memory descriptor fields (bytes; 0 = the kernel's layout: LBO 8192, SBO 1024)
+  int mn_lbo, mn_sbo;
 };
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,
                                 const GemmEpilogue& ep, cudaStream_t s);
+// "MN-major" variant: C[M, N] = A^T * B with A [K, a_cols] and B [K, N] row-major bf16 (the reduction runs over rows);
+// a_cols <= M, the missing columns are zero-filled by TMA.  M%128==0, N%128==0, K%64==0, a_cols%8==0.
+cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_cols, const void* B, int M, int N, int K,
+                                   const GemmEpilogue& ep, cudaStream_t s);
 const char* gemm_tcgen05_last_error();
 
 // ---------------------------------------------------------------------------------------------

@@ -184,6 +184,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major, 128B-swizzled operand (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): the
+// operand sits in shared memory the way a row-major [K rows, MN columns] global matrix lands through TMA boxes of
+// [64 rows x 64 columns]: inside a box, reduction row r is the 128-byte line r (8-line groups = one 1024-byte swizzle
+// atom, SBO = 1024 between groups); consecutive 64-column blocks are consecutive boxes (LBO = box size = 8192).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t kIdescMnMajorAB = (1u << 15) | (1u << 16);   // a_major = b_major = MN
+constexpr uint32_t kMnBoxBytes = 64 * 64 * 2;                   // one [64 x 64] bf16 TMA box
+
 // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -307,7 +323,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
 // CL = 2: thread-block cluster of two CTAs working on vertically adjacent tiles (same n-block).  Each CTA fetches
 // its own A tile and HALF of the shared B tile, multicasting that half into both CTAs' shared memory, which cuts
 // the L2->SM operand traffic per CTA from 48 KB to 32 KB per k-block (the 128x256 tile is L2-bandwidth bound).
-template <int BN, int CL>
+// MN = true ("both operands MN-major"): A is [K, M] and B is [K, N] row-major, i.e. C = A^T B with the reduction
+// running over ROWS — the conv wgrad dW[Cout, k] = sum_pixels dz[pixel, Cout] * col[pixel, k] reads dz and col as they
+// are, without the two transposes a K-major kernel needs.  A stage holds 64 reduction rows; every 64-column block of
+// the tile is one [64 x 64] TMA box (columns past the matrix edge are zero-filled by TMA = the Cout padding).
+template <int BN, int CL, bool MN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     int M, int N, int K, GemmEpilogue ep) {
@@ -376,6 +396,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+          if (MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(smem_a + stage * kStageBytesA + j * kMnBoxBytes, &tmap_a, m0 + j * 64, kb * BK, &bars->full[stage]);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(smem_b + stage * kStageBytesB + j * kMnBoxBytes, &tmap_b, n0 + j * 64, kb * BK, &bars->full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           tma_load_2d(smem_a + stage * kStageBytesA, &tmap_a, kb * BK, m0, &bars->full[stage]);
           if (CL == 2) {
             // my half of the shared B tile -> both CTAs (tmap_b's box is BN/2 rows in this mode)
@@ -391,7 +421,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = make_idesc(BM, BN) | (MN ? kIdescMnMajorAB : 0u);
+      const uint32_t mn_lbo = ep.mn_lbo ? (uint32_t)ep.mn_lbo : kMnBoxBytes, mn_sbo = ep.mn_sbo ? (uint32_t)ep.mn_sbo : 1024u;
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -406,12 +437,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * kStageBytesA));
-          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * kStageBytesB));
+          if (MN) {
+            const uint64_t da = make_smem_desc_mn(smem_u32(smem_a + stage * kStageBytesA), mn_lbo, mn_sbo);
+            const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + stage * kStageBytesB), mn_lbo, mn_sbo);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in (addr>>4) units
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 reduction rows = 16 lines of 128 bytes = two whole swizzle atoms: +128 in (addr>>4) units
+              umma_bf16(tmem_d, da + 128 * k, db + 128 * k, idesc, ((kb - kb_lo) | k) != 0);
+            }
+          } else {
+            const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * kStageBytesA));
+            const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * kStageBytesB));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in (addr>>4) units
+              umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
+            }
           }
           if (CL == 2) umma_commit_mcast(&bars->empty[stage], (uint16_t)0x3);  // both producers write into this stage
           else umma_commit(&bars->empty[stage]);
@@ -552,6 +593,31 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
   cfg.attrs = attr;
   cfg.numAttrs = (CL > 1) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CL>, ta, tb, M, N, K, ep);
+}
+
+
+// MN-major operands: A [K, a_cols] and B [K, N] row-major bf16, boxes of [64 rows x 64 columns]
+template <int BN>
+cudaError_t launch_mn(const void* A, int a_cols, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+  using C = Cfg<BN>;
+  CUtensorMap ta, tb;
+  if (!make_tmap(A, K, a_cols, 64, &ta) || !make_tmap(B, K, N, 64, &tb)) return cudaErrorInvalidValue;
+  static bool configured[64] = {false};
+  static int num_sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem, mn) failed"; return e; }
+    cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    configured[dev & 63] = true;
+  }
+  const int work = (M / BM) * (N / BN) * (ep.split_k > 1 ? ep.split_k : 1);
+  int units = num_sms[dev & 63];
+  if (work < units) units = work;
+  if (units < 1) units = 1;
+  gemm_tcgen05_kernel<BN, 1, true><<<units, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+  return cudaGetLastError();
 }
 
 
@@ -751,6 +817,32 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
 }  // namespace
 
 const char* gemm_tcgen05_last_error() { return g_last_error.c_str(); }
+
+// C[M, N] = A^T B for A [K, a_cols] (a_cols <= M; the missing columns count as zeros) and B [K, N], both row-major
+cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_cols, const void* B, int M, int N, int K, const GemmEpilogue& ep,
+                                   cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0 || (M % BM) || (N % 128) || (K % BK) || a_cols <= 0 || a_cols > M || (a_cols % 8)) {
+    g_last_error = "mn-major shape must satisfy M%128==0, N%128==0, K%64==0, 0 < a_cols <= M, a_cols%8==0";
+    return cudaErrorInvalidValue;
+  }
+  if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
+  if (ep.cluster != 0 || ep.ready_flags != nullptr) { g_last_error = "mn-major mode has no cluster / ready-flag variant"; return cudaErrorInvalidValue; }
+  if (ep.split_k > 1) {
+    if (ep.split_out == nullptr || K / BK < ep.split_k || (((uintptr_t)ep.split_out) & 15)) {
+      g_last_error = "split_k needs a 16-byte aligned split_out and K/64 >= split_k";
+      return cudaErrorInvalidValue;
+    }
+    if (ep.bias || ep.relu || ep.relu_mask || ep.out_bf16 || ep.out_f32 || ep.out_bf16_t || ep.sgd_master || ep.colsum) {
+      g_last_error = "split_k stores raw partials: no other epilogue option may be set";
+      return cudaErrorInvalidValue;
+    }
+  }
+  if (ep.tile_n == 256 && (N % 256)) { g_last_error = "tile_n=256 needs N%256==0"; return cudaErrorInvalidValue; }
+  const bool wide = (N % 256 == 0) && ep.tile_n != 128 &&
+                    (ep.tile_n == 256 || ep.split_k > 1 || (int64_t)(M / BM) * (N / 256) >= 120);
+  if (wide) return launch_mn<256>(A, a_cols, B, M, N, K, ep, s);
+  return launch_mn<128>(A, a_cols, B, M, N, K, ep, s);
+}
 
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0 || (M % BM) || (N % 128) || (K % BK)) {

@@ -97,6 +97,57 @@ def test_split_k_schedule_is_the_same_step(level):
     assert float((d0 * d1).sum() / (d0.norm() * d1.norm())) > (0.999 if level == 1 else 0.95)
 
 
+@pytest.mark.parametrize("split", [0, 1])
+def test_mn_major_wgrad_schedule_is_the_same_step(split):
+    """``wgrad_mn``: the wgrad GEMMs read ``dz`` / ``col`` in place (reduction over rows) instead of transposed copies —
+    the same products, so the fp32-oracle step must agree with the default schedule to rounding; fewer launches."""
+    torch.manual_seed(0)
+    model = ResNet18(10)
+    flat0 = flatten_params(model).clone()
+    x, y = torch.randn(B, 3, 32, 32), torch.randint(0, 10, (B,))
+
+    def run(mn, dtype):
+        flat = flat0.clone()
+        tr = ConvNetTrainer(model, "cpu", B, (32, 32), act_dtype=dtype, split_k=split, wgrad_mn=mn)
+        tr.load(flat, None)
+        loss = float(tr.step(x, y, 0.05))
+        tr.store(flat, None)
+        return flat, loss, tr.launches
+
+    base, loss0, n0 = run(False, torch.float32)
+    got, loss1, n1 = run(True, torch.float32)
+    assert n0 - n1 == 2 * 20                                 # two transposes per convolution are gone
+    assert abs(loss0 - loss1) < 1e-5
+    assert float((got - base).norm() / (base - flat0).norm()) < 1e-4
+    b16, _, _ = run(False, torch.bfloat16)
+    m16, _, _ = run(True, torch.bfloat16)
+    d0, d1 = b16 - flat0, m16 - flat0
+    assert float((d0 * d1).sum() / (d0.norm() * d1.norm())) > 0.9999
+
+
+def test_mn_major_gemm_reference_definition():
+    """``gemm_bf16(a[K, a_cols], b[K, N], mn_m=M)`` = ``aᵀ·b`` zero-extended to M rows, with every epilogue of the
+    K-major form (here: fused SGD + both shadows, and split-K partials)."""
+    from colearn_federated_learning_b200 import ops
+    torch.manual_seed(1)
+    a, b = torch.randn(256, 64).to(torch.bfloat16), torch.randn(256, 384).to(torch.bfloat16)
+    want = torch.zeros(128, 384)
+    want[:64] = a.float().t() @ b.float()
+    out = torch.empty(128, 384)
+    ops.gemm_bf16(a, b, mn_m=128, out_f32=out)
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-4)
+    master, shadow, shadow_t = torch.ones(128, 384), torch.zeros(128, 384, dtype=torch.bfloat16), torch.zeros(384, 128, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, b, mn_m=128, sgd_master=master, sgd_lr=0.5, sgd_shadow=shadow, sgd_shadow_t=shadow_t)
+    torch.testing.assert_close(master, 1 - 0.5 * want, rtol=1e-5, atol=1e-4)
+    assert torch.equal(shadow, master.to(torch.bfloat16)) and torch.equal(shadow_t, shadow.t())
+    part = torch.zeros(4 * 128 * 384)
+    ops.gemm_bf16(a, b, mn_m=128, split_k=4, split_out=part)
+    torch.testing.assert_close(part.view(4, 128, 384).sum(0), want, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(part.view(4, 128, 384)[1, :64], a[64:128].float().t() @ b[64:128].float(), rtol=1e-5, atol=1e-4)
+    with pytest.raises(AssertionError):
+        ops.gemm_bf16(a, b, mn_m=64, out_f32=out)            # M must be a multiple of 128
+
+
 def test_pick_split_heuristic():
     pick = ConvNetTrainer._pick_split
     assert pick(128, 256, 32768) == 64          # stem wgrad: 1 tile of 128x256, 512 k-blocks -> 64 slices of 8

@@ -167,3 +167,87 @@ def test_split_k_step_matches_default_schedule(level, monkeypatch):
     cos = float((got * base).sum() / (got.norm() * base.norm()))
     assert cos > 0.98, cos
     assert torch.isfinite(got).all()
+
+
+def _mn_case(dev, kdim, a_cols, m, n, split=0):
+    from colearn_federated_learning_b200 import ops
+    torch.manual_seed(kdim + n)
+    a = torch.randn(kdim, a_cols, device=dev).to(torch.bfloat16)
+    b = torch.randn(kdim, n, device=dev).to(torch.bfloat16)
+    want = torch.zeros(m, n)
+    want[:a_cols] = a.float().cpu().t() @ b.float().cpu()
+    tol = dict(rtol=2e-3, atol=2e-2 * (kdim / 512) ** 0.5)
+    if split:
+        part = torch.full((split * m * n + 64,), 7.0, device=dev)
+        ops.gemm_bf16(a, b, mn_m=m, split_k=split, split_out=part)
+        torch.cuda.synchronize()
+        assert float(part[split * m * n:].min()) == 7.0
+        got = part[: split * m * n].view(split, m, n).sum(0).cpu()
+    else:
+        out = torch.full((m, n), 7.0, device=dev)
+        ops.gemm_bf16(a, b, mn_m=m, out_f32=out)
+        torch.cuda.synchronize()
+        got = out.cpu()
+    return got, want, tol
+
+
+@unvalidated
+@pytest.mark.parametrize("kdim,a_cols,m,n,split", [(64, 128, 128, 128, 0), (128, 64, 128, 128, 0), (8192, 64, 128, 640, 0),
+                                                   (32768, 64, 128, 256, 64), (512, 256, 256, 2304, 0), (128, 512, 512, 4608, 0),
+                                                   (8192, 64, 128, 640, 16), (2048, 128, 128, 1152, 4)])
+def test_gemm_mn_major_operands(kdim, a_cols, m, n, split):
+    """C = AᵀB with A [K, a_cols], B [K, N] row-major (MN-major UMMA descriptors, boxes of 64 rows x 64 columns; the
+    rows of C past a_cols are TMA zero fill) against the fp32 product."""
+    got, want, tol = _mn_case(_dev(), kdim, a_cols, m, n, split)
+    torch.testing.assert_close(got, want, **tol)
+
+
+@unvalidated
+def test_gemm_mn_major_fused_sgd_epilogue():
+    dev = _dev()
+    from colearn_federated_learning_b200 import ops
+    torch.manual_seed(5)
+    a = torch.randn(2048, 128, device=dev).to(torch.bfloat16)
+    b = torch.randn(2048, 1152, device=dev).to(torch.bfloat16)
+    master = torch.randn(128, 1152, device=dev)
+    m0 = master.clone()
+    shadow = torch.zeros(128, 1152, device=dev, dtype=torch.bfloat16)
+    shadow_t = torch.zeros(1152, 128, device=dev, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, b, mn_m=128, sgd_master=master, sgd_lr=0.01, sgd_shadow=shadow, sgd_shadow_t=shadow_t)
+    torch.cuda.synchronize()
+    want = m0 - 0.01 * (a.float().t() @ b.float())
+    torch.testing.assert_close(master, want, rtol=1e-3, atol=1e-2)
+    assert torch.equal(shadow, master.to(torch.bfloat16)) and torch.equal(shadow_t, shadow.t().contiguous())
+
+
+@unvalidated
+@pytest.mark.parametrize("flags", [{"COLEARN_CONV_WGRAD_MN": "1"}, {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_SPLITK": "1"},
+                                   {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_SPLITK": "2", "COLEARN_CONV_STREAMS": "1",
+                                    "COLEARN_CONV_FUSED_BN": "1"}])
+def test_mn_major_wgrad_step_matches_default_schedule(flags, monkeypatch):
+    dev = _dev()
+    torch.manual_seed(0)
+    x = torch.randn(256, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (256,), device=dev)
+
+    def run():
+        torch.manual_seed(1)
+        model = ResNet18(10).to(dev)
+        flat = flatten_params(model)
+        flat0 = flat.clone()
+        tr = ConvNetTrainer(model, dev, 128, (32, 32))
+        tr.load(flat, model)
+        for lo in (0, 128):
+            tr._graph_step(x[lo:lo + 128], y[lo:lo + 128], 0.05)
+        tr.store(flat, model)
+        torch.cuda.synchronize()
+        return flat.clone() - flat0
+
+    for k in ("COLEARN_CONV_WGRAD_MN", "COLEARN_CONV_SPLITK", "COLEARN_CONV_STREAMS", "COLEARN_CONV_FUSED_BN", "COLEARN_CONV_SHADOW_T"):
+        monkeypatch.delenv(k, raising=False)
+    base = run()
+    for k, v in flags.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    cos = float((got * base).sum() / (got.norm() * base.norm()))
+    assert cos > 0.98 and torch.isfinite(got).all(), cos
