@@ -99,14 +99,16 @@ class ConvNetTrainer:
         return tr
 
     def __init__(self, model: ResNet18, device, batch_size: int, hw: Tuple[int, int] = (32, 32),
-                 act_dtype: torch.dtype = BF, split_k: Optional[bool] = None, wgrad_mn: Optional[bool] = None) -> None:
+                 act_dtype: torch.dtype = BF, split_k: Optional[bool] = None, wgrad_mn: Optional[bool] = None,
+                 dgrad_kn: Optional[bool] = None) -> None:
         """``act_dtype=torch.float32`` (CPU only) keeps every buffer in fp32: the PyTorch definitions of the ops then
         make the whole step an exact oracle for the orchestration (tests compare it with autograd).  ``split_k``
         (default: ``COLEARN_CONV_SPLITK=1``) runs the skinny GEMMs — the wgrads of the stem / layer1 / layer2 (1-5 output
         tiles, reductions over up to 32 768 pixels) and the forwards of layer3 / layer4 — in split-K mode, see
         :meth:`_pick_split` (``1`` / ``True``: wgrads only, ``2``: forwards too).  ``wgrad_mn`` (default:
         ``COLEARN_CONV_WGRAD_MN=1``) feeds the wgrad GEMMs ``dz`` and ``col`` as they are (MN-major UMMA operands,
-        reduction over rows) instead of transposing both first."""
+        reduction over rows) instead of transposing both first; ``dgrad_kn`` (``COLEARN_CONV_DGRAD_KN=1``) lets the
+        dgrad GEMMs read the packed weights ``Wp[Cout, K]`` as an MN-major B operand, so no ``Wᵀ`` copy is kept."""
         assert batch_size % 128 == 0, "the GEMM tiles need batch_size % 128 == 0"
         assert act_dtype == BF or torch.device(device).type == "cpu", "the kernels are bf16"
         self.dev, self.B, self.dt = torch.device(device), batch_size, act_dtype
@@ -193,6 +195,8 @@ class ConvNetTrainer:
         # opt-in (not yet measured on a B200): split-K for the GEMMs with too few output tiles to fill 148 SMs
         # opt-in (not yet measured on a B200): wgrad GEMMs on MN-major operands — no dz^T / col^T transposes
         self._wgrad_mn = (os.environ.get("COLEARN_CONV_WGRAD_MN") == "1") if wgrad_mn is None else bool(wgrad_mn)
+        # opt-in: dgrad GEMMs against the packed weights themselves (MN-major B operand) — no W^T copies to refresh
+        self._dgrad_kn = (os.environ.get("COLEARN_CONV_DGRAD_KN") == "1") if dgrad_kn is None else bool(dgrad_kn)
         # COLEARN_CONV_SPLITK=1: wgrads only; =2: forwards too
         self._splitk = int(os.environ.get("COLEARN_CONV_SPLITK", "0") or 0) if split_k is None else int(split_k)
         for cv in self.convs:
@@ -283,8 +287,9 @@ class ConvNetTrainer:
         """Flat arena (and the module's BatchNorm buffers, unless bound) → packed device state."""
         C.pack_params(flat, self.mpk, self.wpk, self.big)
         C.pack_params(flat, self.spk, None, self.small)
-        for cv in self.convs:
-            ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
+        if not self._dgrad_kn:
+            for cv in self.convs:
+                ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
         ops.transpose_bf16(self._w(self.fc_entry), self.fc_wT)
         if model is not None and model is not self._bound:
             mods = dict(model.named_modules())
@@ -292,7 +297,7 @@ class ConvNetTrainer:
                 bn = mods[cv.bn_name]
                 cv.rm.copy_(bn.running_mean)
                 cv.rv.copy_(bn.running_var)
-        self.launches += 3 + len(self.convs)
+        self.launches += 3 + (0 if self._dgrad_kn else len(self.convs))
 
     def store(self, flat: torch.Tensor, model: Optional[ResNet18] = None) -> None:
         """Packed device state → flat arena (and the module's BatchNorm buffers, unless bound)."""
@@ -392,7 +397,10 @@ class ConvNetTrainer:
 
     def _dgrad(self, cv: _Conv, dx: torch.Tensor, add: Optional[torch.Tensor]) -> None:
         dcol = self.dcol[: cv.m * cv.K_pad].view(cv.m, cv.K_pad)
-        ops.gemm_bf16(cv.dz, cv.wT, out_bf16=dcol)
+        if self._dgrad_kn:   # dcol[pixel, k] = Σ_co dz[pixel, co]·Wp[co, k]: B is the packed weight matrix itself
+            ops.gemm_bf16(cv.dz, self._w(cv.entry), b_kn=True, out_bf16=dcol)
+        else:
+            ops.gemm_bf16(cv.dz, cv.wT, out_bf16=dcol)
         C.col2im(dcol, dx, add, cv.n, cv.h, cv.w, cv.cin, cv.k, cv.k, cv.stride, cv.pad)
         self.launches += 2
 
@@ -435,12 +443,12 @@ class ConvNetTrainer:
         (``dzT`` / ``colT``) is touched by the side stream alone, ``dcol`` / ``partial`` by the main stream alone."""
         side = self._side
         # Wᵀ straight from the wgrad epilogue (``sgd_shadow_t``) when the layer needs no row padding
-        fuse_t = self._fuse_shadow_t and cv.cout_pad == cv.cout and cv.s_wgrad == 1
+        fuse_t = self._fuse_shadow_t and cv.cout_pad == cv.cout and cv.s_wgrad == 1 and not self._dgrad_kn
         if side is None:
             if dx is not None:
                 self._dgrad(cv, dx, add)
             self._wgrad(cv, lr, fuse_t)
-            if not fuse_t:
+            if not fuse_t and not self._dgrad_kn:
                 ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
                 self.launches += 1
             return
@@ -454,10 +462,10 @@ class ConvNetTrainer:
             ev_dgrad.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ev_dz)
-            if fuse_t and ev_dgrad is not None:
-                side.wait_event(ev_dgrad)                # the epilogue itself overwrites wT
+            if (fuse_t or self._dgrad_kn) and ev_dgrad is not None:
+                side.wait_event(ev_dgrad)                # the epilogue itself overwrites wT (or the W the dgrad reads)
             self._wgrad(cv, lr, fuse_t)
-            if not fuse_t:
+            if not fuse_t and not self._dgrad_kn:
                 if ev_dgrad is not None:
                     side.wait_event(ev_dgrad)
                 ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)

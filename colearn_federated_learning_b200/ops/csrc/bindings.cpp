@@ -362,14 +362,17 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                   c10::optional<torch::Tensor> sgd_shadow_t, c10::optional<torch::Tensor> colsum,
                   int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset, int64_t tile_n,
                   int64_t ready_epoch_ptr, int64_t cluster, int64_t split_k, c10::optional<torch::Tensor> split_out,
-                  int64_t mn_m) {
+                  int64_t mn_m, bool b_kn) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "A,B must be CUDA bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous(), "A, B must be contiguous matrices");
-  // mn_m > 0: "MN-major" operands A[K, a_cols], B[K, N] (C = A^T B, M = mn_m >= a_cols); else A[M, K], B[N, K]
+  // mn_m > 0: "MN-major" operands A[K, a_cols], B[K, N] (C = A^T B, M = mn_m >= a_cols);
+  // b_kn:     A[M, K] K-major, B[b_rows >= K, N] (C = A B[:K]);   else A[M, K], B[N, K] (C = A B^T)
   const bool mn = mn_m > 0;
-  TORCH_CHECK(mn ? A.size(0) == B.size(0) : A.size(1) == B.size(1), mn ? "A[K,a_cols], B[K,N]" : "A[M,K], B[N,K]");
+  TORCH_CHECK(!(mn && b_kn), "mn_m and b_kn are exclusive");
+  TORCH_CHECK(mn ? A.size(0) == B.size(0) : (b_kn ? A.size(1) <= B.size(0) : A.size(1) == B.size(1)),
+              mn ? "A[K,a_cols], B[K,N]" : (b_kn ? "A[M,K], B[>=K,N]" : "A[M,K], B[N,K]"));
   c10::cuda::CUDAGuard guard(A.device());
-  const int M = mn ? (int)mn_m : (int)A.size(0), N = mn ? (int)B.size(1) : (int)B.size(0), K = mn ? (int)A.size(0) : (int)A.size(1);
+  const int M = mn ? (int)mn_m : (int)A.size(0), N = (mn || b_kn) ? (int)B.size(1) : (int)B.size(0), K = mn ? (int)A.size(0) : (int)A.size(1);
   GemmEpilogue ep;
   std::memset(&ep, 0, sizeof(ep));
   auto chk = [&](const c10::optional<torch::Tensor>& t, at::ScalarType st, int64_t r, int64_t c, const char* name) -> void* {
@@ -402,12 +405,12 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
     ep.split_k = (int)split_k;
     ep.split_out = split_out->data_ptr<float>();
   }
-  if (mn) {
+  if (mn || b_kn) {
     static const int dbg_lbo = std::getenv("COLEARN_UMMA_MN_LBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_LBO")) : 0;
     static const int dbg_sbo = std::getenv("COLEARN_UMMA_MN_SBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_SBO")) : 0;
     ep.mn_lbo = dbg_lbo;
     ep.mn_sbo = dbg_sbo;
-    cudaError_t e = launch_gemm_tcgen05_mn(A.data_ptr(), (int)A.size(1), B.data_ptr(), M, N, K, ep, cur_stream());
+    cudaError_t e = launch_gemm_tcgen05_mn(A.data_ptr(), mn ? 1 : 0, (int)A.size(1), B.data_ptr(), (int)B.size(0), M, N, K, ep, cur_stream());
     TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05 (mn-major): ", cudaGetErrorString(e), " (", gemm_tcgen05_last_error(), ")");
     return;
   }

@@ -221,9 +221,11 @@ struct GemmEpilogue {
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,
                                 const GemmEpilogue& ep, cudaStream_t s);
-// "MN-major" variant: C[M, N] = A^T * B with A [K, a_cols] and B [K, N] row-major bf16 (the reduction runs over rows);
-// a_cols <= M, the missing columns are zero-filled by TMA.  M%128==0, N%128==0, K%64==0, a_cols%8==0.
-cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_cols, const void* B, int M, int N, int K,
+// "MN-major" variants (operands whose reduction index runs over ROWS are read in place, no transposed copies):
+//   a_mn = 1: C[M, N] = A^T * B  with A [K, a_cols], B [K, N]   (conv wgrad; a_cols <= M, missing columns = TMA zero fill)
+//   a_mn = 0: C[M, N] = A * B    with A [M, K], B [b_rows >= K, N] (conv dgrad against the packed weights)
+// M%128==0, N%128==0, K%64==0, a_cols%8==0.
+cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_mn, int a_cols, const void* B, int b_rows, int M, int N, int K,
                                    const GemmEpilogue& ep, cudaStream_t s);
 const char* gemm_tcgen05_last_error();
 

@@ -197,7 +197,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
   d |= (uint64_t)2 << 61;
   return d;
 }
-constexpr uint32_t kIdescMnMajorAB = (1u << 15) | (1u << 16);   // a_major = b_major = MN
+constexpr uint32_t kIdescMnMajorA = 1u << 15, kIdescMnMajorB = 1u << 16;   // a_major / b_major = MN
 constexpr uint32_t kMnBoxBytes = 64 * 64 * 2;                   // one [64 x 64] bf16 TMA box
 
 // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
@@ -327,7 +327,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
 // running over ROWS — the conv wgrad dW[Cout, k] = sum_pixels dz[pixel, Cout] * col[pixel, k] reads dz and col as they
 // are, without the two transposes a K-major kernel needs.  A stage holds 64 reduction rows; every 64-column block of
 // the tile is one [64 x 64] TMA box (columns past the matrix edge are zero-filled by TMA = the Cout padding).
-template <int BN, int CL, bool MN = false>
+// BMN alone (A K-major [M, K], B [K, N] row-major): the conv dgrad dcol[pixel, k] = sum_co dz[pixel, co] * Wp[co, k]
+// reads the packed weights Wp[Cout, K] as they are, so no W^T copy has to be kept in step with the SGD updates.
+template <int BN, int CL, bool MN = false, bool BMN = MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     int M, int N, int K, GemmEpilogue ep) {
@@ -400,14 +402,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
               tma_load_2d(smem_a + stage * kStageBytesA + j * kMnBoxBytes, &tmap_a, m0 + j * 64, kb * BK, &bars->full[stage]);
+          } else {
+            tma_load_2d(smem_a + stage * kStageBytesA, &tmap_a, kb * BK, m0, &bars->full[stage]);
+          }
+          if (BMN) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d(smem_b + stage * kStageBytesB + j * kMnBoxBytes, &tmap_b, n0 + j * 64, kb * BK, &bars->full[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          tma_load_2d(smem_a + stage * kStageBytesA, &tmap_a, kb * BK, m0, &bars->full[stage]);
-          if (CL == 2) {
+          } else if (CL == 2) {
             // my half of the shared B tile -> both CTAs (tmap_b's box is BN/2 rows in this mode)
             tma_load_2d_mcast(smem_b + stage * kStageBytesB + crank * (kStageBytesB / 2), &tmap_b, kb * BK,
                               n0 + (int)crank * (BN / 2), &bars->full[stage], (uint16_t)0x3);
@@ -421,7 +423,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN) | (MN ? kIdescMnMajorAB : 0u);
+      constexpr uint32_t idesc = make_idesc(BM, BN) | (MN ? kIdescMnMajorA : 0u) | (BMN ? kIdescMnMajorB : 0u);
       const uint32_t mn_lbo = ep.mn_lbo ? (uint32_t)ep.mn_lbo : kMnBoxBytes, mn_sbo = ep.mn_sbo ? (uint32_t)ep.mn_sbo : 1024u;
       int stage = 0;
       uint32_t phase = 0;
@@ -437,23 +439,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
-          if (MN) {
-            const uint64_t da = make_smem_desc_mn(smem_u32(smem_a + stage * kStageBytesA), mn_lbo, mn_sbo);
-            const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + stage * kStageBytesB), mn_lbo, mn_sbo);
+          // K-major operand: +16 bf16 = 32 bytes inside the 128B swizzle atom per UMMA_K (+2 in addr>>4 units);
+          // MN-major operand: +16 reduction rows = 16 lines of 128 bytes = two whole swizzle atoms (+128)
+          const uint64_t da = MN ? make_smem_desc_mn(smem_u32(smem_a + stage * kStageBytesA), mn_lbo, mn_sbo)
+                                 : make_smem_desc(smem_u32(smem_a + stage * kStageBytesA));
+          const uint64_t db = BMN ? make_smem_desc_mn(smem_u32(smem_b + stage * kStageBytesB), mn_lbo, mn_sbo)
+                                  : make_smem_desc(smem_u32(smem_b + stage * kStageBytesB));
+          constexpr uint32_t kStepA = MN ? 128 : 2, kStepB = BMN ? 128 : 2;
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 16 reduction rows = 16 lines of 128 bytes = two whole swizzle atoms: +128 in (addr>>4) units
-              umma_bf16(tmem_d, da + 128 * k, db + 128 * k, idesc, ((kb - kb_lo) | k) != 0);
-            }
-          } else {
-            const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * kStageBytesA));
-            const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * kStageBytesB));
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in (addr>>4) units
-              umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb_lo) | k) != 0);
-            }
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_d, da + kStepA * k, db + kStepB * k, idesc, ((kb - kb_lo) | k) != 0);
           if (CL == 2) umma_commit_mcast(&bars->empty[stage], (uint16_t)0x3);  // both producers write into this stage
           else umma_commit(&bars->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -596,18 +591,19 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
 }
 
 
-// MN-major operands: A [K, a_cols] and B [K, N] row-major bf16, boxes of [64 rows x 64 columns]
-template <int BN>
-cudaError_t launch_mn(const void* A, int a_cols, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+// MN-major operands: A [K, a_cols] (AMN) or [M, K]; B [b_rows >= K, N] row-major bf16, boxes of [64 rows x 64 columns]
+template <int BN, bool AMN>
+cudaError_t launch_mn(const void* A, int a_cols, const void* B, int b_rows, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
   using C = Cfg<BN>;
   CUtensorMap ta, tb;
-  if (!make_tmap(A, K, a_cols, 64, &ta) || !make_tmap(B, K, N, 64, &tb)) return cudaErrorInvalidValue;
+  if (!(AMN ? make_tmap(A, K, a_cols, 64, &ta) : make_tmap(A, M, K, BM, &ta)) || !make_tmap(B, b_rows, N, 64, &tb))
+    return cudaErrorInvalidValue;
   static bool configured[64] = {false};
   static int num_sms[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, AMN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem, mn) failed"; return e; }
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
@@ -616,7 +612,7 @@ cudaError_t launch_mn(const void* A, int a_cols, const void* B, int M, int N, in
   int units = num_sms[dev & 63];
   if (work < units) units = work;
   if (units < 1) units = 1;
-  gemm_tcgen05_kernel<BN, 1, true><<<units, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+  gemm_tcgen05_kernel<BN, 1, AMN, true><<<units, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
   return cudaGetLastError();
 }
 
@@ -818,11 +814,16 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
 
 const char* gemm_tcgen05_last_error() { return g_last_error.c_str(); }
 
-// C[M, N] = A^T B for A [K, a_cols] (a_cols <= M; the missing columns count as zeros) and B [K, N], both row-major
-cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_cols, const void* B, int M, int N, int K, const GemmEpilogue& ep,
-                                   cudaStream_t s) {
-  if (M <= 0 || N <= 0 || K <= 0 || (M % BM) || (N % 128) || (K % BK) || a_cols <= 0 || a_cols > M || (a_cols % 8)) {
-    g_last_error = "mn-major shape must satisfy M%128==0, N%128==0, K%64==0, 0 < a_cols <= M, a_cols%8==0";
+// a_mn = 1: C[M, N] = A^T B for A [K, a_cols] (a_cols <= M; the missing columns count as zeros) and B [K, N];
+// a_mn = 0: C[M, N] = A B   for A [M, K] and B [b_rows >= K, N] (only the first K rows are read).  All row-major bf16.
+cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_mn, int a_cols, const void* B, int b_rows, int M, int N, int K,
+                                   const GemmEpilogue& ep, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0 || (M % BM) || (N % 128) || (K % BK) || b_rows < K) {
+    g_last_error = "mn-major shape must satisfy M%128==0, N%128==0, K%64==0, b_rows >= K";
+    return cudaErrorInvalidValue;
+  }
+  if (a_mn && (a_cols <= 0 || a_cols > M || (a_cols % 8))) {
+    g_last_error = "mn-major A needs 0 < a_cols <= M, a_cols%8==0";
     return cudaErrorInvalidValue;
   }
   if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
@@ -840,8 +841,12 @@ cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_cols, const void* B, int
   if (ep.tile_n == 256 && (N % 256)) { g_last_error = "tile_n=256 needs N%256==0"; return cudaErrorInvalidValue; }
   const bool wide = (N % 256 == 0) && ep.tile_n != 128 &&
                     (ep.tile_n == 256 || ep.split_k > 1 || (int64_t)(M / BM) * (N / 256) >= 120);
-  if (wide) return launch_mn<256>(A, a_cols, B, M, N, K, ep, s);
-  return launch_mn<128>(A, a_cols, B, M, N, K, ep, s);
+  if (a_mn) {
+    if (wide) return launch_mn<256, true>(A, a_cols, B, b_rows, M, N, K, ep, s);
+    return launch_mn<128, true>(A, a_cols, B, b_rows, M, N, K, ep, s);
+  }
+  if (wide) return launch_mn<256, false>(A, a_cols, B, b_rows, M, N, K, ep, s);
+  return launch_mn<128, false>(A, a_cols, B, b_rows, M, N, K, ep, s);
 }
 
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {

@@ -22,12 +22,14 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
               colsum: Optional[torch.Tensor] = None, ready_flags: int = 0, ready_epoch: int = 0,
               ready_chunk_elems: int = 1, ready_elem_offset: int = 0, tile_n: int = 0,
               ready_epoch_ptr: int = 0, cluster: int = 0, split_k: int = 0,
-              split_out: Optional[torch.Tensor] = None, mn_m: int = 0) -> None:
+              split_out: Optional[torch.Tensor] = None, mn_m: int = 0, b_kn: bool = False) -> None:
     """Launch the tcgen05 GEMM; results land in the provided output tensors.
 
     ``mn_m = M > 0`` selects the "MN-major" form ``C[M, N] = Aᵀ·B`` for ``a[K, a_cols]`` (``a_cols <= M``, the missing
     columns count as zeros) and ``b[K, N]``, both row-major: the reduction runs over *rows*, which is how the conv
     wgrad ``dW[Cout, k] = Σ_pixels dz[pixel, Cout]·col[pixel, k]`` finds its operands in memory (no transposes).
+    ``b_kn=True`` keeps ``a[M, K]`` K-major and takes ``b[rows >= K, N]`` row-major (``C = A·B[:K]``) — the conv dgrad
+    against the packed weights ``Wp[Cout, K]``, so no ``Wᵀ`` copy is needed.
 
     ``split_k = S > 1`` (skinny problems: few output tiles, long reduction): the K range is cut into S slices that
     run as independent work units; slice ``s`` stores its raw fp32 accumulator to ``split_out[s]`` (``[S, M, N]``)
@@ -39,7 +41,11 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
             at = a.new_zeros(mn_m, a.shape[0])
             at[: a.shape[1]].copy_(a.t())
             a, b, mn_m = at, b.t().contiguous(), 0
-    m_out, n_out = (mn_m, b.shape[1]) if mn_m else (a.shape[0], b.shape[0])
+    if b_kn:
+        assert not mn_m and a.shape[1] <= b.shape[0] and not ready_flags and not cluster
+        if not a.is_cuda:
+            b, b_kn = b[: a.shape[1]].t().contiguous(), False
+    m_out, n_out = (mn_m, b.shape[1]) if mn_m else (a.shape[0], b.shape[1] if b_kn else b.shape[0])
     k_red = a.shape[0] if mn_m else a.shape[1]
     if split_k and split_k > 1:
         assert split_out is not None and split_out.numel() >= split_k * m_out * n_out
@@ -80,7 +86,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
     _ext.require().gemm_tcgen05(a, b, bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
                                 float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(ready_flags), int(ready_epoch),
                                 int(ready_chunk_elems), int(ready_elem_offset), int(tile_n), int(ready_epoch_ptr), int(cluster),
-                                int(split_k or 0), split_out, int(mn_m or 0))
+                                int(split_k or 0), split_out, int(mn_m or 0), bool(b_kn))
 
 
 def linear_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,

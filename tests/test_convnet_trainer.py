@@ -106,9 +106,9 @@ def test_mn_major_wgrad_schedule_is_the_same_step(split):
     flat0 = flatten_params(model).clone()
     x, y = torch.randn(B, 3, 32, 32), torch.randint(0, 10, (B,))
 
-    def run(mn, dtype):
+    def run(mn, dtype, kn=False):
         flat = flat0.clone()
-        tr = ConvNetTrainer(model, "cpu", B, (32, 32), act_dtype=dtype, split_k=split, wgrad_mn=mn)
+        tr = ConvNetTrainer(model, "cpu", B, (32, 32), act_dtype=dtype, split_k=split, wgrad_mn=mn, dgrad_kn=kn)
         tr.load(flat, None)
         loss = float(tr.step(x, y, 0.05))
         tr.store(flat, None)
@@ -117,6 +117,10 @@ def test_mn_major_wgrad_schedule_is_the_same_step(split):
     base, loss0, n0 = run(False, torch.float32)
     got, loss1, n1 = run(True, torch.float32)
     assert n0 - n1 == 2 * 20                                 # two transposes per convolution are gone
+    # ... and with the dgrads reading the packed weights in place, the W^T copies (load + refresh per step) too
+    got_kn, loss2, n2 = run(True, torch.float32, kn=True)
+    assert n1 - n2 == 2 * 20 and abs(loss0 - loss2) < 1e-5
+    assert float((got_kn - base).norm() / (base - flat0).norm()) < 1e-4
     assert abs(loss0 - loss1) < 1e-5
     assert float((got - base).norm() / (base - flat0).norm()) < 1e-4
     b16, _, _ = run(False, torch.bfloat16)

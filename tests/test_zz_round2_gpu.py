@@ -203,6 +203,24 @@ def test_gemm_mn_major_operands(kdim, a_cols, m, n, split):
 
 
 @unvalidated
+@pytest.mark.parametrize("m,kdim,b_rows,n", [(128, 64, 64, 128), (8192, 64, 128, 640), (2048, 128, 128, 1152), (512, 256, 256, 2304),
+                                             (128, 512, 512, 4608), (32768, 64, 128, 256)])
+def test_gemm_mn_major_b_operand(m, kdim, b_rows, n):
+    """C = A·B[:K] with A [M, K] K-major and B [b_rows >= K, N] row-major (MN-major B descriptor): the conv dgrad
+    against the packed weights."""
+    dev = _dev()
+    from colearn_federated_learning_b200 import ops
+    torch.manual_seed(m + n)
+    a = torch.randn(m, kdim, device=dev).to(torch.bfloat16)
+    b = torch.randn(b_rows, n, device=dev).to(torch.bfloat16)
+    out = torch.full((m, n), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, b, b_kn=True, out_bf16=out)
+    torch.cuda.synchronize()
+    want = a.float() @ b[:kdim].float()
+    torch.testing.assert_close(out.float(), want, rtol=1.6e-2, atol=2e-2 * (kdim / 64) ** 0.5)
+
+
+@unvalidated
 def test_gemm_mn_major_fused_sgd_epilogue():
     dev = _dev()
     from colearn_federated_learning_b200 import ops
@@ -221,9 +239,12 @@ def test_gemm_mn_major_fused_sgd_epilogue():
 
 
 @unvalidated
-@pytest.mark.parametrize("flags", [{"COLEARN_CONV_WGRAD_MN": "1"}, {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_SPLITK": "1"},
-                                   {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_SPLITK": "2", "COLEARN_CONV_STREAMS": "1",
-                                    "COLEARN_CONV_FUSED_BN": "1"}])
+@pytest.mark.parametrize("flags", [{"COLEARN_CONV_WGRAD_MN": "1"}, {"COLEARN_CONV_DGRAD_KN": "1"},
+                                   {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_SPLITK": "1"},
+                                   {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_DGRAD_KN": "1", "COLEARN_CONV_SPLITK": "1",
+                                    "COLEARN_CONV_FUSED_BN": "1"},
+                                   {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_DGRAD_KN": "1", "COLEARN_CONV_SPLITK": "2",
+                                    "COLEARN_CONV_STREAMS": "1", "COLEARN_CONV_FUSED_BN": "1"}])
 def test_mn_major_wgrad_step_matches_default_schedule(flags, monkeypatch):
     dev = _dev()
     torch.manual_seed(0)
@@ -243,7 +264,8 @@ def test_mn_major_wgrad_step_matches_default_schedule(flags, monkeypatch):
         torch.cuda.synchronize()
         return flat.clone() - flat0
 
-    for k in ("COLEARN_CONV_WGRAD_MN", "COLEARN_CONV_SPLITK", "COLEARN_CONV_STREAMS", "COLEARN_CONV_FUSED_BN", "COLEARN_CONV_SHADOW_T"):
+    for k in ("COLEARN_CONV_WGRAD_MN", "COLEARN_CONV_DGRAD_KN", "COLEARN_CONV_SPLITK", "COLEARN_CONV_STREAMS", "COLEARN_CONV_FUSED_BN",
+              "COLEARN_CONV_SHADOW_T"):
         monkeypatch.delenv(k, raising=False)
     base = run()
     for k, v in flags.items():
