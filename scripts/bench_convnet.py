@@ -23,14 +23,17 @@ def main():
     ap.add_argument("--samples", type=int, default=2048)
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--only", default="", help="comma-separated subset of torch_cudnn_autocast,native_eager,native_graph")
     args = ap.parse_args()
+    only = {t for t in args.only.split(",") if t}
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     x = torch.randn(args.samples, 3, 32, 32, device=dev)
     y = torch.randint(0, 10, (args.samples, 1), device=dev).float()
     cfg = FitConfig(model="resnet18", loss="xent", batch_size=args.batch, epochs=1, lr=0.01, shuffle=True, seed=1)
     steps = args.samples // args.batch
-    out = {"steps_per_fit": steps, "batch": args.batch}
+    out = {"steps_per_fit": steps, "batch": args.batch,
+           "flags": {k: v for k, v in os.environ.items() if k.startswith("COLEARN_CONV_")}}
 
     def timed(fn):
         for _ in range(2):
@@ -47,6 +50,8 @@ def main():
         return best
 
     for name, env, graph in (("torch_cudnn_autocast", "torch", None), ("native_eager", "native", False), ("native_graph", "native", True)):
+        if only and name not in only:
+            continue
         os.environ["COLEARN_CONV_PATH"] = env
         model = ResNet18(10).to(dev)
         flat = flatten_params(model)

@@ -1,22 +1,37 @@
 #!/bin/sh
 # First GPU call of the next round (ONE box, one call: a call costs ~1.5 GPU-minutes before the command even starts).
-#   1. the GPU tests written after round 1's budget ran out (incl. the opt-in kernels / schedules)
+#   1. the GPU tests written after round 1's budget ran out (incl. the opt-in kernels / schedules); if the MN-major
+#      GEMM tests fail, the descriptor sweep (scripts/debug_umma_mn.py) runs right away
 #   2. the ResNet step with each opt-in re-scheduling, against the default and the cuDNN path
 #   3. per-kernel durations of one eager ResNet step (where do the 1.77 ms go?) + ncu --set full of the conv kernels
 #   4. compute-sanitizer memcheck over the conv ops
-#   5. cfg4 at N=1 with the winners
+#   5. cfg4 at N=1 with the default path, cfg1 on a GPU
 # Everything lands in gpurun_out/r2_*; copy the summaries into profiles/.
 mkdir -p gpurun_out
-COLEARN_RUN_UNVALIDATED=1 timeout 150 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu > gpurun_out/r2_unvalidated_tests.log 2>&1
-tail -n 3 gpurun_out/r2_unvalidated_tests.log
-for flags in "" "COLEARN_CONV_FUSED_BN=1" "COLEARN_CONV_STREAMS=1" "COLEARN_CONV_SHADOW_T=1" \
-             "COLEARN_CONV_FUSED_BN=1 COLEARN_CONV_STREAMS=1 COLEARN_CONV_SHADOW_T=1"; do
-  tag=$(echo "${flags:-default}" | tr ' =' '__' | sed 's/COLEARN_CONV_//g')
-  env $flags timeout 60 python scripts/bench_convnet.py --reps 3 > "gpurun_out/r2_convnet_${tag}.json" 2> "gpurun_out/r2_convnet_${tag}.err"
-  echo "== $tag"; cut -c1-400 "gpurun_out/r2_convnet_${tag}.json"
+COLEARN_RUN_UNVALIDATED=1 timeout 420 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider \
+    > gpurun_out/r2_unvalidated_tests.log 2>&1
+grep -E "passed|failed|error" gpurun_out/r2_unvalidated_tests.log | tail -n 3
+grep -E "^FAILED|^ERROR" gpurun_out/r2_unvalidated_tests.log | cut -c1-160 | head -n 40
+if grep -E "^FAILED.*(mn_major|b_operand)" gpurun_out/r2_unvalidated_tests.log > /dev/null; then
+  timeout 300 python scripts/debug_umma_mn.py > gpurun_out/r2_umma_mn_sweep.log 2>&1
+  cat gpurun_out/r2_umma_mn_sweep.log
+fi
+timeout 90 python scripts/bench_convnet.py --reps 3 > gpurun_out/r2_convnet_default.json 2> gpurun_out/r2_convnet_default.err
+echo "== default"; cut -c1-600 gpurun_out/r2_convnet_default.json
+ALL="COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_DGRAD_KN=1 COLEARN_CONV_SPLITK=1 COLEARN_CONV_FUSED_BN=1"
+for flags in "COLEARN_CONV_FUSED_BN=1" "COLEARN_CONV_STREAMS=1" "COLEARN_CONV_SHADOW_T=1" "COLEARN_CONV_SPLITK=1" "COLEARN_CONV_SPLITK=2" \
+             "COLEARN_CONV_WGRAD_MN=1" "COLEARN_CONV_DGRAD_KN=1" "COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_SPLITK=1" \
+             "COLEARN_CONV_FUSED_BN=1 COLEARN_CONV_STREAMS=1 COLEARN_CONV_SHADOW_T=1" \
+             "$ALL" "$ALL COLEARN_CONV_STREAMS=1" "COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_DGRAD_KN=1 COLEARN_CONV_SPLITK=2 COLEARN_CONV_FUSED_BN=1"; do
+  tag=$(echo "$flags" | tr ' =' '__' | sed 's/COLEARN_CONV_//g')
+  env $flags timeout 60 python scripts/bench_convnet.py --reps 3 --only native_eager,native_graph \
+      > "gpurun_out/r2_convnet_${tag}.json" 2> "gpurun_out/r2_convnet_${tag}.err"
+  echo "== $tag rc=$?"; cut -c1-500 "gpurun_out/r2_convnet_${tag}.json"
 done
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_convnet_launch_times.csv \
     python scripts/prof_convnet_only.py 2 > gpurun_out/r2_convnet_launch_times.log 2>&1
+env $ALL timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_convnet_launch_times_allflags.csv \
+    python scripts/prof_convnet_only.py 2 > gpurun_out/r2_convnet_launch_times_allflags.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"im2col_kernel|col2im_kernel|bn_reduce_kernel|bn_apply_kernel|bn_bwd_kernel" \
     -s 10 -c 10 -o gpurun_out/r2_prof_conv python scripts/prof_convnet_only.py 2 > gpurun_out/r2_prof_conv.log 2>&1
 timeout 200 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/r2_sanitizer_memcheck_conv.log \
