@@ -451,6 +451,19 @@ def train_virtual_workers(theta: torch.Tensor, model, fed, cfg: FitConfig, round
             for i in idx:
                 losses[i] = vals[i]
         return flats, losses, counts
+    if spec is not None and device.type == "cpu" and ops.host.available() and spec.out_activation in ("none", "sigmoid"):
+        # CPU box: the native host executor trains the K workers concurrently on K threads (ops/csrc/mlp_host.cpp)
+        idx = [i for i, wid in enumerate(fed.workers) if len(fed[wid]) > 0]
+        if idx:
+            shards = [fed[fed.workers[i]] for i in idx]
+            perms = [make_perm(len(sh), FitConfig(**{**cfg.to_dict(), "seed": cfg.seed + 31 * i}), device, round_idx)
+                     for i, sh in zip(idx, shards)]
+            res = ops.host.mlp_local_sgd_multi(spec.dims, spec.out_activation, [flats[i] for i in idx], [sh.x for sh in shards],
+                                               [sh.y for sh in shards], perms, cfg.batch_size, cfg.lr, cfg.epochs,
+                                               cfg.max_nr_batches, resolve_loss(cfg.model, cfg.loss))
+            for j, i in enumerate(idx):
+                losses[i] = float(res[j, 0])
+        return flats, losses, counts
     for i, wid in enumerate(fed.workers):
         sh = fed[wid]
         if len(sh) == 0:

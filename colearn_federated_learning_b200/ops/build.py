@@ -21,6 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 EXT_NAME = "_colearn_C"
 EMUL_NAME = "_colearn_emul"     # CPU emulator of the conv kernels (tests on boxes without a GPU)
+HOST_NAME = "_colearn_host"     # native CPU executor of the MLP local fit (devices / boxes without a GPU)
 
 CU_SOURCES = ["mlp_persistent.cu", "elementwise.cu", "comm.cu", "gemm_tcgen05.cu", "convnet.cu"]
 CPP_SOURCES = ["bindings.cpp"]
@@ -99,6 +100,34 @@ def build_emul(force: bool = False) -> str:
     return out
 
 
+def host_path() -> str:
+    suffix = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+    return os.path.join(HERE, HOST_NAME + suffix)
+
+
+def build_host(force: bool = False) -> str:
+    """g++-only build of ``csrc/mlp_host.cpp`` (worker-side local SGD for devices without a GPU).  No CUDA headers or
+    libraries are involved; portable ``-O3`` (no ``-march=native``: the in-tree ``.so`` travels between boxes)."""
+    ce, _, inc, flags = _cxx_setup()
+    os.makedirs(OBJ, exist_ok=True)
+    out = host_path()
+    src = os.path.join(CSRC, "mlp_host.cpp")
+    cxx_flags = [f for f in flags if f != "-O2"] + ["-O3", "-fno-math-errno", f"-DTORCH_EXTENSION_NAME={HOST_NAME}"]
+    h = hashlib.sha1(open(src, "rb").read() + " ".join(cxx_flags).encode()).hexdigest()[:16]
+    obj = os.path.join(OBJ, f"mlp_host.cpp.{h}.o")
+    if force or not os.path.exists(obj) or not os.path.exists(out):
+        for name in os.listdir(OBJ):
+            if name.startswith("mlp_host.cpp.") and name.endswith(".o"):
+                os.remove(os.path.join(OBJ, name))
+        _run(["g++", *cxx_flags, *[i for i in inc if "cuda" not in i.lower() or "torch" in i.lower()], "-c", src, "-o", obj], "mlp_host.cpp")
+        link = ["g++", "-shared", obj, "-o", out, "-pthread"]
+        for d in ce.library_paths(device_type="cpu"):
+            link += [f"-L{d}", f"-Wl,-rpath,{d}"]
+        link += ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python"]
+        _run(link, "link_host")
+    return out
+
+
 def build_all(force: bool = False, verbose: bool = True) -> str:
     ce, cuda_home, inc, base_cxx = _cxx_setup()
 
@@ -140,16 +169,24 @@ def build_all(force: bool = False, verbose: bool = True) -> str:
     # drop stale cached objects (every source edit leaves one behind)
     keep = {os.path.basename(o) for o in objs}
     for name in os.listdir(OBJ):
-        if name.endswith(".o") and name not in keep and not name.startswith("conv_emul.cpp."):
+        if name.endswith(".o") and name not in keep and not name.startswith(("conv_emul.cpp.", "mlp_host.cpp.")):
             os.remove(os.path.join(OBJ, name))
+    build_host(force=force)      # the CPU executor ships with every build (CPU-only boxes: `--host` builds it alone)
     return out
 
 
 def main(argv=None) -> int:
-    """``python -m colearn_federated_learning_b200.ops.build [--emul] [--force]`` / ``colearn-build-kernels``."""
+    """``python -m colearn_federated_learning_b200.ops.build [--emul | --host] [--force]`` / ``colearn-build-kernels``.
+
+    ``--host`` builds only the CPU executor (no nvcc needed: edge devices), ``--emul`` only the conv-kernel emulator."""
     argv = sys.argv[1:] if argv is None else argv
     force = "--force" in argv
-    print(build_emul(force=force) if "--emul" in argv else build_all(force=force))
+    if "--emul" in argv:
+        print(build_emul(force=force))
+    elif "--host" in argv:
+        print(build_host(force=force))
+    else:
+        print(build_all(force=force))
     return 0
 
 

@@ -14,7 +14,7 @@ from typing import Optional, Sequence, Tuple, Union
 
 import torch
 
-from . import _ext, reference
+from . import _ext, host, reference
 
 NET_KINDS = {
     ((10, 50, 30, 10, 1), "sigmoid"): 0,
@@ -110,6 +110,13 @@ def mlp_local_sgd(flat: torch.Tensor, dims: Sequence[int], x: torch.Tensor, y: t
     CPU tensors run ``reference.mlp_local_sgd`` (identical semantics); CUDA tensors run the
     persistent kernel — there is no silent fallback on CUDA."""
     if not flat.is_cuda:
+        # CPU devices: the native host executor (csrc/mlp_host.cpp) when it is built and the arena can be trained in
+        # place, else the PyTorch definitions (identical semantics; the executor is tested against them)
+        if (host.available() and flat.dtype == torch.float32 and flat.is_contiguous() and not flat.requires_grad
+                and out_activation in ("none", "sigmoid")):
+            res = host.mlp_local_sgd_multi(dims, out_activation, [flat], [x], [y], [perm], batch_size, lr, epochs,
+                                           max_nr_batches, loss, threads=1)
+            return res[0, 1 if return_mean else 0].clone()
         if perm is None:
             perm = reference.make_permutation(x.shape[0], epochs, 0, shuffle=False)
         return reference.mlp_local_sgd(flat, dims, x, y, perm, batch_size, lr, epochs, max_nr_batches, loss, out_activation)

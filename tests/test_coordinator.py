@@ -251,8 +251,9 @@ def test_worker_runtime_reuses_model_and_arena_and_guards_the_wire():
         assert not torch.equal(c, b)
         # timeout -> the handle closes itself
         with pytest.raises(OSError):
-            cl._call({"op": "fit", "config": FitConfig(model="ffnn", loss="bce", epochs=3).to_dict(),
-                      "params": W._to_bytes(flat), "dataset_key": "training"}, timeout=1e-4)
+            # 2 000 epochs x 64 batch-1 steps: ~0.3 s even through the native host executor (~2 us / step)
+            cl._call({"op": "fit", "config": FitConfig(model="ffnn", loss="bce", epochs=2000).to_dict(),
+                      "params": W._to_bytes(flat), "dataset_key": "training"}, timeout=1e-3)
         with pytest.raises(ConnectionError):
             cl.ping()
         deadline = time.time() + 20                          # let the orphaned fit finish before tearing down
