@@ -53,6 +53,8 @@ class _Conv:
         self.K_pad, self.cout_pad = _pad(self.K), _pad(self.cout)
         self.eps, self.momentum = bn.eps, (0.1 if bn.momentum is None else bn.momentum)
         self.entry: Optional[C.PackEntry] = None
+        self.implicit = False                          # implicit-GEMM schedule (4-D TMA boxes instead of im2col / col2im)
+        self.x_in: Optional[torch.Tensor] = None       # the layer's input activation matrix [m_in, cin] (implicit wgrad)
 
     def alloc(self, dev, act_dtype: torch.dtype = BF) -> None:
         z = lambda *s, dt=act_dtype: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
@@ -100,7 +102,7 @@ class ConvNetTrainer:
 
     def __init__(self, model: ResNet18, device, batch_size: int, hw: Tuple[int, int] = (32, 32),
                  act_dtype: torch.dtype = BF, split_k: Optional[bool] = None, wgrad_mn: Optional[bool] = None,
-                 dgrad_kn: Optional[bool] = None) -> None:
+                 dgrad_kn: Optional[bool] = None, implicit: Optional[int] = None) -> None:
         """``act_dtype=torch.float32`` (CPU only) keeps every buffer in fp32: the PyTorch definitions of the ops then
         make the whole step an exact oracle for the orchestration (tests compare it with autograd).  ``split_k``
         (default: ``COLEARN_CONV_SPLITK=1``) runs the skinny GEMMs — the wgrads of the stem / layer1 / layer2 (1-5 output
@@ -108,7 +110,10 @@ class ConvNetTrainer:
         :meth:`_pick_split` (``1`` / ``True``: wgrads only, ``2``: forwards too).  ``wgrad_mn`` (default:
         ``COLEARN_CONV_WGRAD_MN=1``) feeds the wgrad GEMMs ``dz`` and ``col`` as they are (MN-major UMMA operands,
         reduction over rows) instead of transposing both first; ``dgrad_kn`` (``COLEARN_CONV_DGRAD_KN=1``) lets the
-        dgrad GEMMs read the packed weights ``Wp[Cout, K]`` as an MN-major B operand, so no ``Wᵀ`` copy is kept."""
+        dgrad GEMMs read the packed weights ``Wp[Cout, K]`` as an MN-major B operand, so no ``Wᵀ`` copy is kept.
+        ``implicit`` (``COLEARN_CONV_IMPLICIT=1|2``): the stride-1 3x3 convolutions whose images have 1-64 pixels (13 of
+        the 20) run as implicit GEMMs — forward and dgrad read x / dz through 4-D TMA boxes (``ops.conv.conv_gemm``;
+        level 2: the wgrad too, which needs the MN-major path), so ``col`` / ``dcol`` / ``col2im`` disappear."""
         assert batch_size % 128 == 0, "the GEMM tiles need batch_size % 128 == 0"
         assert act_dtype == BF or torch.device(device).type == "cpu", "the kernels are bf16"
         self.dev, self.B, self.dt = torch.device(device), batch_size, act_dtype
@@ -197,6 +202,11 @@ class ConvNetTrainer:
         self._wgrad_mn = (os.environ.get("COLEARN_CONV_WGRAD_MN") == "1") if wgrad_mn is None else bool(wgrad_mn)
         # opt-in: dgrad GEMMs against the packed weights themselves (MN-major B operand) — no W^T copies to refresh
         self._dgrad_kn = (os.environ.get("COLEARN_CONV_DGRAD_KN") == "1") if dgrad_kn is None else bool(dgrad_kn)
+        # opt-in: implicit GEMM for the stride-1 3x3 convolutions (1: forward + dgrad, 2: wgrad too)
+        self._implicit = int(os.environ.get("COLEARN_CONV_IMPLICIT", "0") or 0) if implicit is None else int(implicit)
+        for cv in self.convs:
+            cv.implicit = (self._implicit > 0 and cv.k == 3 and cv.pad == 1 and cv.cout % 64 == 0
+                           and C.implicit_ok(cv.h, cv.w, cv.cin, cv.stride, B))
         # COLEARN_CONV_SPLITK=1: wgrads only; =2: forwards too
         self._splitk = int(os.environ.get("COLEARN_CONV_SPLITK", "0") or 0) if split_k is None else int(split_k)
         for cv in self.convs:
@@ -246,6 +256,11 @@ class ConvNetTrainer:
         s = min((k // 64) // 8, -(-sms // tiles))
         return s if s >= max(2, min_slices) else 1
 
+    def _needs_wT(self, cv: _Conv) -> bool:
+        """A bf16 ``Wᵀ`` copy is the dgrad's K-major B operand — explicit schedule without ``dgrad_kn``, and every
+        implicit dgrad (rows ``(tap, ci)``, columns ``co``)."""
+        return cv.implicit or not self._dgrad_kn
+
     def _gemm_fwd(self, cv: _Conv) -> None:
         """``cv.z = cv.col · Wpᵀ`` (bf16), split-K when the layer has few output tiles."""
         if cv.s_fwd > 1:
@@ -287,8 +302,8 @@ class ConvNetTrainer:
         """Flat arena (and the module's BatchNorm buffers, unless bound) → packed device state."""
         C.pack_params(flat, self.mpk, self.wpk, self.big)
         C.pack_params(flat, self.spk, None, self.small)
-        if not self._dgrad_kn:
-            for cv in self.convs:
+        for cv in self.convs:
+            if self._needs_wT(cv):
                 ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
         ops.transpose_bf16(self._w(self.fc_entry), self.fc_wT)
         if model is not None and model is not self._bound:
@@ -297,7 +312,7 @@ class ConvNetTrainer:
                 bn = mods[cv.bn_name]
                 cv.rm.copy_(bn.running_mean)
                 cv.rv.copy_(bn.running_var)
-        self.launches += 3 + (0 if self._dgrad_kn else len(self.convs))
+        self.launches += 3 + sum(1 for cv in self.convs if self._needs_wT(cv))
 
     def store(self, flat: torch.Tensor, model: Optional[ResNet18] = None) -> None:
         """Packed device state → flat arena (and the module's BatchNorm buffers, unless bound)."""
@@ -317,9 +332,26 @@ class ConvNetTrainer:
         self.launches += 3
 
     # -- forward ------------------------------------------------------------------------------------------------------
-    def _conv_bn(self, cv: _Conv, x4: torch.Tensor, res: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+    def _conv_fwd(self, cv: _Conv, x4: torch.Tensor, xmat: Optional[torch.Tensor]) -> None:
+        """``cv.z`` = the convolution of the layer input (``x4``: strided NCHW view; ``xmat``: the same data as the NHWC
+        matrix ``[m_in, cin]`` when the producer was one of this trainer's kernels)."""
+        if cv.implicit and xmat is not None:
+            cv.x_in = xmat
+            if cv.s_fwd > 1:
+                C.conv_gemm("fwd", xmat, self._w(cv.entry), cv.n, cv.h, cv.w, cv.cin, cv.k, cv.k, cv.pad, split_k=cv.s_fwd,
+                            split_out=self.kpart_f)
+                C.splitk_reduce(self.kpart_f, cv.s_fwd, cv.m * cv.cout_pad, out_bf16=cv.z)
+                self.launches += 1
+            else:
+                C.conv_gemm("fwd", xmat, self._w(cv.entry), cv.n, cv.h, cv.w, cv.cin, cv.k, cv.k, cv.pad, out_bf16=cv.z)
+            self.launches -= 1                         # no im2col launch on this path (callers count 5 per conv)
+            return
         C.im2col(x4, cv.col, cv.k, cv.k, cv.stride, cv.pad)
         self._gemm_fwd(cv)
+
+    def _conv_bn(self, cv: _Conv, x4: torch.Tensor, res: Optional[torch.Tensor], relu: bool,
+                 xmat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self._conv_fwd(cv, x4, xmat)
         C.bn_stats(cv.z, cv.cout, self.partial, cv.mean, cv.invstd, cv.rm, cv.rv, cv.eps, cv.momentum, self.bn_counters)
         C.bn_apply(cv.z, cv.cout, cv.mean, cv.invstd, self._s(cv.bn_name + ".weight"), self._s(cv.bn_name + ".bias"),
                    res, relu, cv.out)
@@ -337,8 +369,8 @@ class ConvNetTrainer:
             c1, c2 = b.c1, b.c2
             x4 = C.nhwc_view(a, B, c1.h, c1.w, c1.cin)
             identity = a if b.ds is None else self._conv_bn(b.ds, x4, None, False)
-            mid = self._conv_bn(c1, x4, None, True)
-            a = self._conv_bn(c2, C.nhwc_view(mid, B, c2.h, c2.w, c2.cin), identity, True)
+            mid = self._conv_bn(c1, x4, None, True, xmat=a)
+            a = self._conv_bn(c2, C.nhwc_view(mid, B, c2.h, c2.w, c2.cin), identity, True, xmat=mid)
         C.avgpool_fwd(a, self.feat, B, self.final_hw, self.feat_dim)
         ops.gemm_bf16(self.feat, self._w(self.fc_entry), bias=self._s("fc.bias"), out_f32=self.logits)
         loss, dlog = ops.softmax_xent(self.logits[:, : self.num_classes].contiguous(), labels)
@@ -361,9 +393,8 @@ class ConvNetTrainer:
             invs[cv.name] = inv_all[off:off + cv.cout]
             off += cv.cout
 
-        def conv_bn(cv: _Conv, x4, res, relu):
-            C.im2col(x4, cv.col, cv.k, cv.k, cv.stride, cv.pad)
-            self._gemm_fwd(cv)
+        def conv_bn(cv: _Conv, x4, res, relu, xmat=None):
+            self._conv_fwd(cv, x4, xmat)
             C.bn_apply(cv.z, cv.cout, cv.rm, invs[cv.name], self._s(cv.bn_name + ".weight"), self._s(cv.bn_name + ".bias"),
                        res, relu, cv.out)
             return cv.out
@@ -380,8 +411,8 @@ class ConvNetTrainer:
                 c1, c2 = b.c1, b.c2
                 x4 = C.nhwc_view(a, B, c1.h, c1.w, c1.cin)
                 identity = a if b.ds is None else conv_bn(b.ds, x4, None, False)
-                mid = conv_bn(c1, x4, None, True)
-                a = conv_bn(c2, C.nhwc_view(mid, B, c2.h, c2.w, c2.cin), identity, True)
+                mid = conv_bn(c1, x4, None, True, xmat=a)
+                a = conv_bn(c2, C.nhwc_view(mid, B, c2.h, c2.w, c2.cin), identity, True, xmat=mid)
             C.avgpool_fwd(a, self.feat, B, self.final_hw, self.feat_dim)
             ops.gemm_bf16(self.feat, self._w(self.fc_entry), bias=self._s("fc.bias"), out_f32=self.logits)
             k = min(B, n - lo)
@@ -396,6 +427,13 @@ class ConvNetTrainer:
         self.launches += 3
 
     def _dgrad(self, cv: _Conv, dx: torch.Tensor, add: Optional[torch.Tensor]) -> None:
+        if cv.implicit and cv.x_in is not None:
+            # dx[p, ci] = Σ_(tap, co) dz[p + pad − tap, co]·Wᵀ[(tap, ci), co] (+ the identity branch's gradient): dz boxes
+            # through the 4-D map, no dcol, no col2im
+            C.conv_gemm("dgrad", cv.dz, cv.wT, cv.n, cv.oh, cv.ow, cv.cout, cv.k, cv.k, cv.pad, out_bf16=dx, addend=add,
+                        rows_per_tap=cv.cin)
+            self.launches += 1
+            return
         dcol = self.dcol[: cv.m * cv.K_pad].view(cv.m, cv.K_pad)
         if self._dgrad_kn:   # dcol[pixel, k] = Σ_co dz[pixel, co]·Wp[co, k]: B is the packed weight matrix itself
             ops.gemm_bf16(cv.dz, self._w(cv.entry), b_kn=True, out_bf16=dcol)
@@ -405,6 +443,23 @@ class ConvNetTrainer:
         self.launches += 2
 
     def _wgrad(self, cv: _Conv, lr: float, shadow_t: bool = False) -> None:
+        if cv.implicit and cv.x_in is not None:
+            if self._implicit >= 2:
+                # dW[co, (tap, c)] = Σ_p dz[p, co]·x[p + tap − pad, c]: dz MN-major, x through 64-pixel boxes — no col at all
+                if cv.s_wgrad > 1:
+                    C.conv_gemm("wgrad", cv.x_in, cv.dz, cv.n, cv.h, cv.w, cv.cin, cv.k, cv.k, cv.pad, m_pad=cv.cout_pad,
+                                k_pad=cv.K_pad, split_k=cv.s_wgrad, split_out=self.kpart_w)
+                    C.splitk_reduce(self.kpart_w, cv.s_wgrad, cv.cout_pad * cv.K_pad, master=self._m(cv.entry), lr=lr,
+                                    shadow=self._w(cv.entry))
+                    self.launches += 1
+                else:
+                    C.conv_gemm("wgrad", cv.x_in, cv.dz, cv.n, cv.h, cv.w, cv.cin, cv.k, cv.k, cv.pad, m_pad=cv.cout_pad,
+                                k_pad=cv.K_pad, sgd_master=self._m(cv.entry), sgd_lr=lr, sgd_shadow=self._w(cv.entry))
+                self.launches += 1
+                return
+            # level 1: the forward ran without a col matrix; build it now, off the forward's critical path
+            C.im2col(C.nhwc_view(cv.x_in, cv.n, cv.h, cv.w, cv.cin), cv.col, cv.k, cv.k, cv.stride, cv.pad)
+            self.launches += 1
         if self._wgrad_mn:
             # dW[Cout, k] = Σ_pixels dz[pixel, Cout]·col[pixel, k]: both operands are read in place (rows = the
             # reduction index); the Cout padding rows of the tile are TMA zero fill
@@ -443,12 +498,15 @@ class ConvNetTrainer:
         (``dzT`` / ``colT``) is touched by the side stream alone, ``dcol`` / ``partial`` by the main stream alone."""
         side = self._side
         # Wᵀ straight from the wgrad epilogue (``sgd_shadow_t``) when the layer needs no row padding
-        fuse_t = self._fuse_shadow_t and cv.cout_pad == cv.cout and cv.s_wgrad == 1 and not self._dgrad_kn
+        keep_t = self._needs_wT(cv)                      # a W^T copy exists and must follow the update
+        in_place = not keep_t                            # the dgrad reads the packed weights the wgrad overwrites
+        fuse_t = (self._fuse_shadow_t and cv.cout_pad == cv.cout and cv.s_wgrad == 1 and keep_t
+                  and not (cv.implicit and self._implicit >= 2))
         if side is None:
             if dx is not None:
                 self._dgrad(cv, dx, add)
             self._wgrad(cv, lr, fuse_t)
-            if not fuse_t and not self._dgrad_kn:
+            if not fuse_t and keep_t:
                 ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)
                 self.launches += 1
             return
@@ -462,10 +520,10 @@ class ConvNetTrainer:
             ev_dgrad.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ev_dz)
-            if (fuse_t or self._dgrad_kn) and ev_dgrad is not None:
+            if (fuse_t or in_place) and ev_dgrad is not None:
                 side.wait_event(ev_dgrad)                # the epilogue itself overwrites wT (or the W the dgrad reads)
             self._wgrad(cv, lr, fuse_t)
-            if not fuse_t and not self._dgrad_kn:
+            if not fuse_t and keep_t:
                 if ev_dgrad is not None:
                     side.wait_event(ev_dgrad)
                 ops.transpose_bf16(self._w(cv.entry)[: cv.cout], cv.wT)

@@ -334,3 +334,76 @@ def splitk_reduce(part: torch.Tensor, splits: int, numel: int, *, master: Option
             shadow.view(-1)[:numel].copy_(m)
     else:
         out_bf16.view(-1)[:numel].copy_(acc)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# implicit-GEMM convolution (stride 1): the activation is read through a 4-D TMA tensor map, no col matrix
+# ----------------------------------------------------------------------------------------------------------
+def implicit_ok(h: int, w: int, c: int, stride: int, n: int = 128) -> bool:
+    """Geometries the implicit path covers: stride 1, 64-channel blocks, images of 1 / 4 / 16 / 64 pixels (a GEMM tile
+    of 128 pixels — 64 for the wgrad's reduction blocks — is then a box of whole images)."""
+    return stride == 1 and c % 64 == 0 and h * w in (1, 4, 16, 64) and (n * h * w) % 128 == 0
+
+
+def conv_gemm(kind: str, act: torch.Tensor, other: torch.Tensor, n: int, h: int, w: int, c: int, kh: int, kw: int, pad: int, *,
+              out_bf16: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None, rows_per_tap: int = 0,
+              m_pad: int = 0, k_pad: int = 0, sgd_master: Optional[torch.Tensor] = None, sgd_lr: float = 0.0,
+              sgd_shadow: Optional[torch.Tensor] = None, split_k: int = 0, split_out: Optional[torch.Tensor] = None) -> None:
+    """The three GEMMs of a stride-1 convolution with the NHWC activation ``act`` (``[n*h*w, c]`` bf16) as an implicit
+    operand (``csrc/conv_ops.cuh``: ``ConvAddr``; boxes of whole images through a 4-D tensor map, TMA zero fill = the
+    padding).  ``kind``:
+
+    * ``"fwd"``   ``out[p, co] = Σ act[p + tap − pad, ·]·other[co, tap·c + ·]`` — ``other`` = packed weights ``[Cout_pad, K_pad]``
+    * ``"dgrad"`` ``out[p, ci] = Σ act[p + pad − tap, ·]·other[tap·rows_per_tap + ci, ·] (+ addend)`` — ``act`` = dz
+      ``[pixels, c = Cout]``, ``other`` = ``Wᵀ`` ``[K_pad, Cout]``, ``rows_per_tap`` = Cin
+    * ``"wgrad"`` ``dW[co, tap·c + ·] = Σ_p other[p, co]·act[p + tap − pad, ·]`` — ``other`` = dz ``[pixels, Cout]``; the
+      result (``[m_pad, k_pad]``, K padding = zeros) goes through the fused SGD epilogue or the split-K partials.
+
+    CPU tensors use the PyTorch definitions (``im2col`` / ``col2im`` + the reference GEMM), CUDA the tcgen05 kernel."""
+    from .linear import gemm_bf16
+    m = n * h * w
+    taps = kh * kw
+    if act.is_cuda:
+        mod = _ext.require()
+        if kind == "wgrad":
+            assert m_pad > 0 and k_pad >= taps * c
+            geom = [2, 0, c, kh, kw, pad, h, w, n, 0, m_pad, k_pad, m]
+        elif kind == "fwd":
+            geom = [1, 0, c, kh, kw, pad, h, w, n, 0, m, out_bf16.shape[1] if out_bf16 is not None else other.shape[0], taps * c]
+        else:
+            geom = [1, 1, c, kh, kw, pad, h, w, n, rows_per_tap, m, rows_per_tap, taps * c]
+        mod.gemm_tcgen05(act, other, None, False, None, out_bf16, None, None, sgd_master, float(sgd_lr), sgd_shadow, None, None,
+                         0, 0, 1, 0, 0, 0, 0, int(split_k or 0), split_out, 0, False, addend, geom)
+        return
+    # --- definitions --------------------------------------------------------------------------------------------
+    x4 = nhwc_view(act, n, h, w, c)
+    k = taps * c
+    if kind == "fwd":
+        col = torch.zeros(m, k, dtype=act.dtype)
+        im2col(x4, col, kh, kw, 1, pad)
+        if split_k and split_k > 1:     # slices of the implicit K loop: k-blocks of 64 over (tap, c)
+            nn_ = other.shape[0]
+            part = split_out[: split_k * m * nn_].view(split_k, m, nn_)
+            nkb = k // 64
+            for s_ in range(split_k):
+                lo, hi = nkb * s_ // split_k * 64, nkb * (s_ + 1) // split_k * 64
+                part[s_].copy_(col[:, lo:hi].float() @ other[:, lo:hi].float().t())
+            return
+        out_bf16.copy_(col.float() @ other[:, :k].float().t())
+    elif kind == "dgrad":
+        cin = rows_per_tap
+        wt = other[: taps * cin].float()                                    # [taps*cin, cout]
+        dcol = act[:m].float() @ wt.t()                                     # [m, taps*cin], k = (tap, ci)
+        dx = torch.zeros(m, cin, dtype=out_bf16.dtype)
+        col2im(dcol.to(out_bf16.dtype), dx, addend, n, h, w, cin, kh, kw, 1, pad)
+        out_bf16[:m].copy_(dx)
+    elif kind == "wgrad":
+        col = torch.zeros(m, k, dtype=act.dtype)
+        im2col(x4, col, kh, kw, 1, pad)
+        assert m_pad > 0 and k_pad >= k
+        colp = torch.zeros(m, k_pad, dtype=act.dtype)
+        colp[:, :k] = col
+        gemm_bf16(other, colp, mn_m=m_pad, sgd_master=sgd_master, sgd_lr=sgd_lr, sgd_shadow=sgd_shadow, split_k=split_k,
+                  split_out=split_out)
+    else:
+        raise ValueError(kind)

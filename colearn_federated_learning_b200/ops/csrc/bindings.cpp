@@ -362,17 +362,23 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                   c10::optional<torch::Tensor> sgd_shadow_t, c10::optional<torch::Tensor> colsum,
                   int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset, int64_t tile_n,
                   int64_t ready_epoch_ptr, int64_t cluster, int64_t split_k, c10::optional<torch::Tensor> split_out,
-                  int64_t mn_m, bool b_kn) {
+                  int64_t mn_m, bool b_kn, c10::optional<torch::Tensor> addend, std::vector<int64_t> conv) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "A,B must be CUDA bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous(), "A, B must be contiguous matrices");
   // mn_m > 0: "MN-major" operands A[K, a_cols], B[K, N] (C = A^T B, M = mn_m >= a_cols);
   // b_kn:     A[M, K] K-major, B[b_rows >= K, N] (C = A B[:K]);   else A[M, K], B[N, K] (C = A B^T)
   const bool mn = mn_m > 0;
   TORCH_CHECK(!(mn && b_kn), "mn_m and b_kn are exclusive");
-  TORCH_CHECK(mn ? A.size(0) == B.size(0) : (b_kn ? A.size(1) <= B.size(0) : A.size(1) == B.size(1)),
+  TORCH_CHECK(!conv.empty() || (mn ? A.size(0) == B.size(0) : (b_kn ? A.size(1) <= B.size(0) : A.size(1) == B.size(1))),
               mn ? "A[K,a_cols], B[K,N]" : (b_kn ? "A[M,K], B[>=K,N]" : "A[M,K], B[N,K]"));
   c10::cuda::CUDAGuard guard(A.device());
-  const int M = mn ? (int)mn_m : (int)A.size(0), N = (mn || b_kn) ? (int)B.size(1) : (int)B.size(0), K = mn ? (int)A.size(0) : (int)A.size(1);
+  // conv (implicit GEMM) = [mode, flip, C, KH, KW, pad, H, W, n_images, b_rows_per_tap, M, N, K]: A is the NHWC activation
+  // [n_images*H*W, C] read through a 4-D tensor map, B the other operand (mode 1: K-major weights; mode 2: dz [pixels, a_cols])
+  const bool is_conv = !conv.empty();
+  TORCH_CHECK(!is_conv || (conv.size() == 13 && !mn && !b_kn), "conv = 13 ints, exclusive with mn_m / b_kn");
+  const int M = is_conv ? (int)conv[10] : (mn ? (int)mn_m : (int)A.size(0));
+  const int N = is_conv ? (int)conv[11] : ((mn || b_kn) ? (int)B.size(1) : (int)B.size(0));
+  const int K = is_conv ? (int)conv[12] : (mn ? (int)A.size(0) : (int)A.size(1));
   GemmEpilogue ep;
   std::memset(&ep, 0, sizeof(ep));
   auto chk = [&](const c10::optional<torch::Tensor>& t, at::ScalarType st, int64_t r, int64_t c, const char* name) -> void* {
@@ -404,6 +410,21 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                 split_out->numel() >= split_k * (int64_t)M * N, "split_out must be a contiguous CUDA fp32 tensor with >= split_k*M*N elements");
     ep.split_k = (int)split_k;
     ep.split_out = split_out->data_ptr<float>();
+  }
+  ep.addend = chk(addend, at::kBFloat16, M, N, "addend");
+  if (is_conv) {
+    convops::ConvAddr& g = ep.conv;
+    g.mode = (int)conv[0]; g.flip = (int)conv[1]; g.C = (int)conv[2]; g.KH = (int)conv[3]; g.KW = (int)conv[4]; g.pad = (int)conv[5];
+    const int H = (int)conv[6], W = (int)conv[7];
+    g.HW = H * W; g.n_images = (int)conv[8]; g.b_rows_per_tap = (int)conv[9];
+    TORCH_CHECK(A.numel() == (int64_t)g.n_images * H * W * g.C, "activation must be [n_images*H*W, C]");
+    static const int dbg_lbo = std::getenv("COLEARN_UMMA_MN_LBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_LBO")) : 0;
+    static const int dbg_sbo = std::getenv("COLEARN_UMMA_MN_SBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_SBO")) : 0;
+    ep.mn_lbo = dbg_lbo;
+    ep.mn_sbo = dbg_sbo;
+    cudaError_t e = launch_gemm_tcgen05_conv(A.data_ptr(), g.n_images, H, W, B.data_ptr(), (int)B.size(0), (int)B.size(1), M, N, K, ep, cur_stream());
+    TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05 (implicit conv): ", cudaGetErrorString(e), " (", gemm_tcgen05_last_error(), ")");
+    return;
   }
   if (mn || b_kn) {
     static const int dbg_lbo = std::getenv("COLEARN_UMMA_MN_LBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_LBO")) : 0;

@@ -217,6 +217,9 @@ struct GemmEpilogue {
   float* split_out;         // fp32 [split_k, M, N]
   // debug overrides of the MN-major shared-memory descriptor fields (bytes; 0 = the kernel's layout: LBO 8192, SBO 1024)
   int mn_lbo, mn_sbo;
+  // implicit-GEMM convolution: one operand is an NHWC activation read through a 4-D tensor map (conv_ops.cuh)
+  convops::ConvAddr conv;
+  const void* addend;       // bf16 [M,N] added to the accumulator before the bf16/fp32 outputs (residual gradient), or nullptr
 };
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,
@@ -227,6 +230,11 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
 // M%128==0, N%128==0, K%64==0, a_cols%8==0.
 cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_mn, int a_cols, const void* B, int b_rows, int M, int N, int K,
                                    const GemmEpilogue& ep, cudaStream_t s);
+// Implicit-GEMM convolution (stride 1, NHWC activation `act` [n_images, H, W, C] bf16, H*W in {1, 4, 16, 64}, C % 64 == 0).
+//   ep.conv.mode = 1: C[M = n_images*H*W, N] = conv operand (A, K-major boxes) x `other` [N or rows, K] K-major weights
+//   ep.conv.mode = 2: C[M, N] = other^T (A = dz [K = pixels, a_cols] MN-major) x conv operand (B, MN-major boxes)
+cudaError_t launch_gemm_tcgen05_conv(const void* act, int n_images, int H, int W, const void* other, int other_rows, int other_cols,
+                                     int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s);
 const char* gemm_tcgen05_last_error();
 
 // ---------------------------------------------------------------------------------------------

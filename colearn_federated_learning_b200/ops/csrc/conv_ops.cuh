@@ -495,6 +495,66 @@ CL_HD void pack_body(const PackArgs& a, long long e) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Implicit GEMM addressing (stride-1 convolutions on NHWC activations whose images are <= 128 pixels).
+// The activation [N, H, W, C] is described to TMA as a 4-D tensor (c, w, h, n); a GEMM tile of 128 (or 64) pixels is a
+// box of whole images (c: 64, w: W, h: H, n: pixels / (H*W)), and tap (kh, kw) of the filter is the same box moved by
+// (kw - pad, kh - pad): what falls outside the image is zero-filled by TMA — the convolution's padding.  The box lands
+// in shared memory as [pixels x 64 channels] lines of 128 bytes, i.e. exactly the operand tile the explicit im2col
+// GEMM reads, so no col matrix exists.  One decode serves the three GEMMs of a convolution:
+//   forward (mode 1, flip 0):  A = x boxes,  K = (tap, c):   z[p, co]  = sum x[p + tap - pad, c]  * Wp[co, tap*C + c]
+//   dgrad   (mode 1, flip 1):  A = dz boxes, K = (tap, co):  dx[p, c]  = sum dz[p + pad - tap, co] * Wt[tap*Cin + c, co]
+//   wgrad   (mode 2):          B = x boxes (MN-major), reduction over pixels:
+//                                                           dW[co, tap*C + c] = sum_p dz[p, co] * x[p + tap - pad, c]
+// ------------------------------------------------------------------------------------------------------
+struct ConvAddr {
+  int mode;        // 0: off   1: the A operand is an activation (K-major boxes of 128 pixels)   2: the B operand is (MN-major, 64 pixels)
+  int flip;        // mode 1: 0 = forward (coordinate tap - pad), 1 = dgrad (pad - tap)
+  int C;           // channels of the activation behind the 4-D map (multiple of 64)
+  int KH, KW, pad;
+  int HW;          // H*W of the activation: 1, 4, 16 or 64 (whole images per box)
+  int n_images;    // N (a fully padded K/N block is pushed out of bounds with this)
+  int b_rows_per_tap;  // mode 1 / flip 1: rows of W^T per tap (= Cin of the convolution = N of the GEMM)
+};
+struct ConvBox {
+  int c, w, h, n;  // 4-D TMA coordinates of the activation box
+  int b_col, b_row;  // mode 1: 2-D coordinates of the weight box (column = k offset, row = first output column)
+};
+// mode 1: k-block kb (64 channels of one tap) of the output tile starting at pixel m0 / output column n0
+CL_HD ConvBox conv_kblock(const ConvAddr& g, int kb, int m0, int n0) {
+  const int cblocks = g.C / 64;
+  const int tap = kb / cblocks, cb = kb % cblocks;
+  const int kh = tap / g.KW, kw = tap % g.KW;
+  ConvBox b;
+  b.c = cb * 64;
+  b.w = g.flip ? g.pad - kw : kw - g.pad;
+  b.h = g.flip ? g.pad - kh : kh - g.pad;
+  b.n = m0 / g.HW;
+  if (g.flip) {
+    b.b_col = cb * 64;                          // K index inside W^T's row = output channel of the convolution
+    b.b_row = tap * g.b_rows_per_tap + n0;
+  } else {
+    b.b_col = kb * 64;                          // k = tap*C + c, the packed weights' own column order
+    b.b_row = n0;
+  }
+  return b;
+}
+// mode 2: the 64-column block `blk` (= k / 64, k = tap*C + c) of the B operand for the reduction block kb (64 pixels);
+// blocks past the last tap (the K padding of the packed weights) are placed out of bounds = zeros
+CL_HD ConvBox conv_nblock(const ConvAddr& g, int blk, int kb) {
+  const int cblocks = g.C / 64;
+  const int tap = blk / cblocks, cb = blk % cblocks;
+  const int kh = tap / g.KW, kw = tap % g.KW;
+  ConvBox b;
+  b.c = cb * 64;
+  b.w = kw - g.pad;
+  b.h = kh - g.pad;
+  b.n = tap < g.KH * g.KW ? (kb * 64) / g.HW : g.n_images;
+  b.b_col = 0;
+  b.b_row = 0;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Split-K reduction: the tcgen05 GEMM in split-K mode leaves S raw fp32 partial accumulators part[s, rows, cols]
 // (gemm_tcgen05.cu, GemmEpilogue::split_k); this map sums them in slice order (deterministic) and applies the
 // epilogue the un-split GEMM would have fused:

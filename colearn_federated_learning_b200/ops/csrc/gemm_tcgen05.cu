@@ -78,6 +78,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  // 4-D tiled box (implicit-GEMM convolution: (channel, w, h, image) of an NHWC activation); coordinates may be
+  // negative / past the edge, those elements are zero-filled
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
   // the tile lands at the same CTA-relative smem offset in every CTA of cta_mask and completes tx bytes on the
   // mbarrier at the same offset in each of them
@@ -264,6 +271,19 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       }
     }
   }
+  if (ep.addend != nullptr) {
+    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.addend) + (size_t)row * N + col);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 av = __ldg(ap + g);
+      const uint32_t w[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        f[g * 8 + h * 2] += __uint_as_float(w[h] << 16);              // bf16 -> fp32: the bits are the high half
+        f[g * 8 + h * 2 + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
+      }
+    }
+  }
   if (ep.colsum != nullptr) {
     // bias gradient: per-(32-row block) partial column sums, plain coalesced stores (no atomics);
     // the consumer (bias_sgd_from_partials) adds the M/32 partial rows
@@ -398,6 +418,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+          if (CL == 1 && !MN && !BMN && ep.conv.mode == 1) {
+            // implicit-GEMM convolution, forward / dgrad: the A tile is the activation box of this tap (conv_ops.cuh)
+            const convops::ConvBox bx = convops::conv_kblock(ep.conv, kb, m0, n0);
+            tma_load_4d(smem_a + stage * kStageBytesA, &tmap_a, bx.c, bx.w, bx.h, bx.n, &bars->full[stage]);
+            tma_load_2d(smem_b + stage * kStageBytesB, &tmap_b, bx.b_col, bx.b_row, &bars->full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
@@ -405,7 +433,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
             tma_load_2d(smem_a + stage * kStageBytesA, &tmap_a, kb * BK, m0, &bars->full[stage]);
           }
-          if (BMN) {
+          if (BMN && ep.conv.mode == 2) {
+            // implicit-GEMM convolution, wgrad: every 64-column block (tap, 64 channels) of the B tile is an activation box
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              const convops::ConvBox bx = convops::conv_nblock(ep.conv, n0 / 64 + j, kb);
+              tma_load_4d(smem_b + stage * kStageBytesB + j * kMnBoxBytes, &tmap_b, bx.c, bx.w, bx.h, bx.n, &bars->full[stage]);
+            }
+          } else if (BMN) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d(smem_b + stage * kStageBytesB + j * kMnBoxBytes, &tmap_b, n0 + j * 64, kb * BK, &bars->full[stage]);
@@ -550,6 +585,34 @@ bool make_tmap(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* o
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { g_last_error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return false; }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
+
+bool make_tmap_4d(const void* ptr, int n_images, int H, int W, int C, int box_images, CUtensorMap* out) {
+  // NHWC bf16 activation as (c, w, h, n); box = 64 channels x whole images (SW128: one box line = 64 channels = 128 bytes)
+  struct Key { const void* p; int n, h, w, c, b; bool operator==(const Key& o) const { return p == o.p && n == o.n && h == o.h && w == o.w && c == o.c && b == o.b; } };
+  struct KeyHash { size_t operator()(const Key& k) const {
+    return std::hash<const void*>()(k.p) ^ (size_t)k.n * 1000003u ^ (size_t)k.h * 10007u ^ (size_t)k.w * 131u ^ (size_t)k.c * 31u ^ (size_t)k.b * 7u; } };
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Key key{ptr, n_images, H, W, C, box_images};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) { g_last_error = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_images};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)W, (cuuint32_t)H, (cuuint32_t)box_images};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_error = "cuTensorMapEncodeTiled (4-d) failed with CUresult " + std::to_string((int)r); return false; }
   if (cache.size() > 4096) cache.clear();
   cache[key] = m;
   *out = m;
@@ -814,6 +877,90 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
 
 const char* gemm_tcgen05_last_error() { return g_last_error.c_str(); }
 
+template <int BN, bool WGRAD>
+cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const void* other, int other_rows, int other_cols,
+                          int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+  using C = Cfg<BN>;
+  CUtensorMap ta, tb;
+  const int HW = H * W;
+  if (WGRAD) {   // A = dz [K pixels, a_cols] MN-major boxes, B = activation boxes of 64 pixels
+    if (!make_tmap(other, other_rows, other_cols, 64, &ta) || !make_tmap_4d(act, n_images, H, W, ep.conv.C, 64 / HW, &tb))
+      return cudaErrorInvalidValue;
+  } else {       // A = activation boxes of 128 pixels, B = K-major weights [other_rows, other_cols]
+    if (!make_tmap_4d(act, n_images, H, W, ep.conv.C, 128 / HW, &ta) || !make_tmap(other, other_rows, other_cols, BN, &tb))
+      return cudaErrorInvalidValue;
+  }
+  static bool configured[64] = {false};
+  static int num_sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, WGRAD, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem, conv) failed"; return e; }
+    cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    configured[dev & 63] = true;
+  }
+  const int work = (M / BM) * (N / BN) * (ep.split_k > 1 ? ep.split_k : 1);
+  int units = num_sms[dev & 63];
+  if (work < units) units = work;
+  if (units < 1) units = 1;
+  gemm_tcgen05_kernel<BN, 1, WGRAD, WGRAD><<<units, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tcgen05_conv(const void* act, int n_images, int H, int W, const void* other, int other_rows, int other_cols,
+                                     int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+  const convops::ConvAddr& g = ep.conv;
+  const int HW = H * W;
+  if ((g.mode != 1 && g.mode != 2) || g.C <= 0 || (g.C % 64) || g.KH <= 0 || g.KW <= 0 || g.pad < 0 || g.HW != HW ||
+      !(HW == 1 || HW == 4 || HW == 16 || HW == 64) || W > 256 || H > 256 || g.n_images != n_images) {
+    g_last_error = "implicit conv GEMM: mode 1|2, C%64==0, H*W in {1,4,16,64}, consistent geometry";
+    return cudaErrorInvalidValue;
+  }
+  // N % 64 for the A-operand modes: a 64-channel layer's dgrad has only 64 output columns (UMMA 128x64x16 tile)
+  if (M <= 0 || N <= 0 || K <= 0 || (M % BM) || (N % (g.mode == 1 ? 64 : 128)) || (K % BK)) {
+    g_last_error = "shape must satisfy M%128==0, N%128==0 (N%64==0 with a conv A operand), K%64==0";
+    return cudaErrorInvalidValue;
+  }
+  if ((((uintptr_t)act) | ((uintptr_t)other)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
+  if (ep.cluster != 0 || ep.ready_flags != nullptr) { g_last_error = "implicit conv GEMM has no cluster / ready-flag variant"; return cudaErrorInvalidValue; }
+  if (g.mode == 1) {
+    // M = pixels (whole images per 128-row tile), K = taps * C
+    if (M != n_images * HW || K != g.KH * g.KW * g.C) { g_last_error = "implicit conv GEMM (A): M = N*H*W, K = KH*KW*C"; return cudaErrorInvalidValue; }
+    if (g.flip ? (other_rows < (g.KH * g.KW - 1) * g.b_rows_per_tap + N || other_cols < g.C || g.b_rows_per_tap <= 0)
+               : (other_rows < N || other_cols < K)) {
+      g_last_error = "implicit conv GEMM (A): weight matrix too small";
+      return cudaErrorInvalidValue;
+    }
+  } else {
+    // K = pixels, N = padded taps * C
+    if (K != n_images * HW || N < g.KH * g.KW * g.C || other_rows != K || other_cols > M || (other_cols % 8)) {
+      g_last_error = "implicit conv GEMM (B): K = N*H*W, N >= KH*KW*C, dz [K, a_cols <= M]";
+      return cudaErrorInvalidValue;
+    }
+  }
+  if (ep.split_k > 1) {
+    if (ep.split_out == nullptr || K / BK < ep.split_k || (((uintptr_t)ep.split_out) & 15)) {
+      g_last_error = "split_k needs a 16-byte aligned split_out and K/64 >= split_k";
+      return cudaErrorInvalidValue;
+    }
+    if (ep.bias || ep.relu || ep.relu_mask || ep.out_bf16 || ep.out_f32 || ep.out_bf16_t || ep.sgd_master || ep.colsum || ep.addend) {
+      g_last_error = "split_k stores raw partials: no other epilogue option may be set";
+      return cudaErrorInvalidValue;
+    }
+  }
+  if (ep.tile_n == 256 && (N % 256)) { g_last_error = "tile_n=256 needs N%256==0"; return cudaErrorInvalidValue; }
+  const bool wide = (N % 256 == 0) && ep.tile_n != 128 &&
+                    (ep.tile_n == 256 || ep.split_k > 1 || (int64_t)(M / BM) * (N / 256) >= 120);
+  if (g.mode == 2) {
+    if (wide) return launch_conv_t<256, true>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
+    return launch_conv_t<128, true>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
+  }
+  if (wide) return launch_conv_t<256, false>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
+  if (N % 128) return launch_conv_t<64, false>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
+  return launch_conv_t<128, false>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
+}
+
 // a_mn = 1: C[M, N] = A^T B for A [K, a_cols] (a_cols <= M; the missing columns count as zeros) and B [K, N];
 // a_mn = 0: C[M, N] = A B   for A [M, K] and B [b_rows >= K, N] (only the first K rows are read).  All row-major bf16.
 cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_mn, int a_cols, const void* B, int b_rows, int M, int N, int K,
@@ -833,7 +980,7 @@ cudaError_t launch_gemm_tcgen05_mn(const void* A, int a_mn, int a_cols, const vo
       g_last_error = "split_k needs a 16-byte aligned split_out and K/64 >= split_k";
       return cudaErrorInvalidValue;
     }
-    if (ep.bias || ep.relu || ep.relu_mask || ep.out_bf16 || ep.out_f32 || ep.out_bf16_t || ep.sgd_master || ep.colsum) {
+    if (ep.bias || ep.relu || ep.relu_mask || ep.out_bf16 || ep.out_f32 || ep.out_bf16_t || ep.sgd_master || ep.colsum || ep.addend) {
       g_last_error = "split_k stores raw partials: no other epilogue option may be set";
       return cudaErrorInvalidValue;
     }
@@ -860,7 +1007,7 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
     if (ep.split_out == nullptr) { g_last_error = "split_k needs split_out"; return cudaErrorInvalidValue; }
     if (K / BK < ep.split_k) { g_last_error = "split_k must not exceed K/64"; return cudaErrorInvalidValue; }
     if (ep.cluster != 0 || ep.ready_flags != nullptr || ep.bias || ep.relu || ep.relu_mask || ep.out_bf16 || ep.out_f32 ||
-        ep.out_bf16_t || ep.sgd_master || ep.colsum) {
+        ep.out_bf16_t || ep.sgd_master || ep.colsum || ep.addend) {
       g_last_error = "split_k stores raw partials: no other epilogue / cluster / ready-flag option may be set";
       return cudaErrorInvalidValue;
     }

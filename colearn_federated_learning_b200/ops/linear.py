@@ -22,7 +22,8 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
               colsum: Optional[torch.Tensor] = None, ready_flags: int = 0, ready_epoch: int = 0,
               ready_chunk_elems: int = 1, ready_elem_offset: int = 0, tile_n: int = 0,
               ready_epoch_ptr: int = 0, cluster: int = 0, split_k: int = 0,
-              split_out: Optional[torch.Tensor] = None, mn_m: int = 0, b_kn: bool = False) -> None:
+              split_out: Optional[torch.Tensor] = None, mn_m: int = 0, b_kn: bool = False,
+              addend: Optional[torch.Tensor] = None) -> None:
     """Launch the tcgen05 GEMM; results land in the provided output tensors.
 
     ``mn_m = M > 0`` selects the "MN-major" form ``C[M, N] = Aᵀ·B`` for ``a[K, a_cols]`` (``a_cols <= M``, the missing
@@ -30,6 +31,9 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
     wgrad ``dW[Cout, k] = Σ_pixels dz[pixel, Cout]·col[pixel, k]`` finds its operands in memory (no transposes).
     ``b_kn=True`` keeps ``a[M, K]`` K-major and takes ``b[rows >= K, N]`` row-major (``C = A·B[:K]``) — the conv dgrad
     against the packed weights ``Wp[Cout, K]``, so no ``Wᵀ`` copy is needed.
+
+    ``addend`` (bf16 ``[M, N]``) is added to the accumulator before the bf16 / fp32 outputs are written (the residual
+    gradient joining a dgrad).
 
     ``split_k = S > 1`` (skinny problems: few output tiles, long reduction): the K range is cut into S slices that
     run as independent work units; slice ``s`` stores its raw fp32 accumulator to ``split_out[s]`` (``[S, M, N]``)
@@ -50,7 +54,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
     if split_k and split_k > 1:
         assert split_out is not None and split_out.numel() >= split_k * m_out * n_out
         assert (bias is None and not relu and relu_mask is None and out_bf16 is None and out_f32 is None and out_bf16_t is None
-                and sgd_master is None and colsum is None and not ready_flags), "split-K stores raw partials only"
+                and sgd_master is None and colsum is None and not ready_flags and addend is None), "split-K stores raw partials only"
         assert k_red // 64 >= split_k, "split_k must not exceed K/64"
     if not a.is_cuda:
         if split_k and split_k > 1:   # same slice boundaries as the kernel: k-blocks of 64, slice s = [nkb*s/S, nkb*(s+1)/S)
@@ -67,6 +71,8 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
             acc = torch.relu(acc)
         if relu_mask is not None:
             acc = acc * (relu_mask.float() > 0)
+        if addend is not None:
+            acc = acc + addend.float()
         if colsum is not None:   # [M/32, N] per-32-row-block partial column sums
             colsum.copy_(acc.view(acc.shape[0] // 32, 32, acc.shape[1]).sum(1))
         if sgd_master is not None:
@@ -86,7 +92,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
     _ext.require().gemm_tcgen05(a, b, bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
                                 float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(ready_flags), int(ready_epoch),
                                 int(ready_chunk_elems), int(ready_elem_offset), int(tile_n), int(ready_epoch_ptr), int(cluster),
-                                int(split_k or 0), split_out, int(mn_m or 0), bool(b_kn))
+                                int(split_k or 0), split_out, int(mn_m or 0), bool(b_kn), addend, [])
 
 
 def linear_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,

@@ -8,7 +8,7 @@
 #   5. cfg4 at N=1 with the default path, cfg1 on a GPU
 # Everything lands in gpurun_out/r2_*; copy the summaries into profiles/.
 mkdir -p gpurun_out
-COLEARN_RUN_UNVALIDATED=1 timeout 420 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider \
+COLEARN_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider \
     > gpurun_out/r2_unvalidated_tests.log 2>&1
 grep -E "passed|failed|error" gpurun_out/r2_unvalidated_tests.log | tail -n 3
 grep -E "^FAILED|^ERROR" gpurun_out/r2_unvalidated_tests.log | cut -c1-160 | head -n 40
@@ -19,9 +19,11 @@ fi
 timeout 90 python scripts/bench_convnet.py --reps 3 > gpurun_out/r2_convnet_default.json 2> gpurun_out/r2_convnet_default.err
 echo "== default"; cut -c1-600 gpurun_out/r2_convnet_default.json
 ALL="COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_DGRAD_KN=1 COLEARN_CONV_SPLITK=1 COLEARN_CONV_FUSED_BN=1"
+IMP="$ALL COLEARN_CONV_IMPLICIT=2"
 for flags in "COLEARN_CONV_FUSED_BN=1" "COLEARN_CONV_STREAMS=1" "COLEARN_CONV_SHADOW_T=1" "COLEARN_CONV_SPLITK=1" "COLEARN_CONV_SPLITK=2" \
              "COLEARN_CONV_WGRAD_MN=1" "COLEARN_CONV_DGRAD_KN=1" "COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_SPLITK=1" \
              "COLEARN_CONV_FUSED_BN=1 COLEARN_CONV_STREAMS=1 COLEARN_CONV_SHADOW_T=1" \
+             "COLEARN_CONV_IMPLICIT=1" "COLEARN_CONV_IMPLICIT=2" "$IMP" "$IMP COLEARN_CONV_STREAMS=1" \
              "$ALL" "$ALL COLEARN_CONV_STREAMS=1" "COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_DGRAD_KN=1 COLEARN_CONV_SPLITK=2 COLEARN_CONV_FUSED_BN=1"; do
   tag=$(echo "$flags" | tr ' =' '__' | sed 's/COLEARN_CONV_//g')
   env $flags timeout 60 python scripts/bench_convnet.py --reps 3 --only native_eager,native_graph \
@@ -30,7 +32,7 @@ for flags in "COLEARN_CONV_FUSED_BN=1" "COLEARN_CONV_STREAMS=1" "COLEARN_CONV_SH
 done
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_convnet_launch_times.csv \
     python scripts/prof_convnet_only.py 2 > gpurun_out/r2_convnet_launch_times.log 2>&1
-env $ALL timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_convnet_launch_times_allflags.csv \
+env $IMP timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_convnet_launch_times_allflags.csv \
     python scripts/prof_convnet_only.py 2 > gpurun_out/r2_convnet_launch_times_allflags.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"im2col_kernel|col2im_kernel|bn_reduce_kernel|bn_apply_kernel|bn_bwd_kernel" \
     -s 10 -c 10 -o gpurun_out/r2_prof_conv python scripts/prof_convnet_only.py 2 > gpurun_out/r2_prof_conv.log 2>&1

@@ -273,3 +273,109 @@ def test_mn_major_wgrad_step_matches_default_schedule(flags, monkeypatch):
     got = run()
     cos = float((got * base).sum() / (got.norm() * base.norm()))
     assert cos > 0.98 and torch.isfinite(got).all(), cos
+
+
+# ---- implicit-GEMM convolution (4-D TMA boxes): tests/test_implicit_conv.py has the host-side evidence -----------------
+IMPLICIT_GEOMS = [(128, 8, 8, 64, 64), (128, 4, 4, 128, 128), (128, 2, 2, 256, 256), (128, 1, 1, 512, 512), (128, 4, 4, 64, 128)]
+
+
+def _implicit_case(n, h, w, cin, cout):
+    import torch.nn.functional as F
+    torch.manual_seed(n + h + cin)
+    x = torch.randn(n, cin, h, w).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, 3, 3) * (2.0 / (9 * cin)) ** 0.5).to(torch.bfloat16)
+    xr, wr = x.float().requires_grad_(True), wt.float().requires_grad_(True)
+    z = F.conv2d(xr, wr, padding=1)
+    dz4 = torch.randn_like(z).to(torch.bfloat16)
+    z.backward(dz4.float())
+    m = n * h * w
+    nhwc = lambda t, c: t.permute(0, 2, 3, 1).reshape(m, c).contiguous()      # noqa: E731
+    cout_pad, k_pad = (cout + 127) // 128 * 128, (9 * cin + 127) // 128 * 128
+    wp = torch.zeros(cout_pad, k_pad, dtype=torch.bfloat16)
+    wp[:cout, :9 * cin] = wt.permute(0, 2, 3, 1).reshape(cout, -1)
+    return dict(m=m, act=nhwc(x, cin), dz=nhwc(dz4, cout), wp=wp, cout_pad=cout_pad, k_pad=k_pad,
+                z=nhwc(z.detach(), cout), dx=nhwc(xr.grad, cin), dw=wr.grad.permute(0, 2, 3, 1).reshape(cout, -1))
+
+
+@unvalidated
+@pytest.mark.parametrize("n,h,w,cin,cout", IMPLICIT_GEOMS)
+def test_implicit_conv_forward_and_dgrad(n, h, w, cin, cout):
+    dev = _dev()
+    from colearn_federated_learning_b200.ops import conv as C
+    d = _implicit_case(n, h, w, cin, cout)
+    m = d["m"]
+    out = torch.full((m, d["cout_pad"]), 7.0, device=dev, dtype=torch.bfloat16)
+    C.conv_gemm("fwd", d["act"].to(dev), d["wp"].to(dev), n, h, w, cin, 3, 3, 1, out_bf16=out)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out[:, :cout].float().cpu(), d["z"], rtol=2e-2, atol=3e-2)
+    assert float(out[:, cout:].float().abs().max() if d["cout_pad"] > cout else 0.0) == 0.0
+    # split-K over the (tap, channel-block) loop
+    s = 3
+    part = torch.zeros(s * m * d["cout_pad"], device=dev)
+    C.conv_gemm("fwd", d["act"].to(dev), d["wp"].to(dev), n, h, w, cin, 3, 3, 1, split_k=s, split_out=part)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(part.view(s, m, d["cout_pad"]).sum(0)[:, :cout].cpu(), d["z"], rtol=2e-2, atol=3e-2)
+    # dgrad (+ residual gradient); cin = 64 exercises the 128x64 tile
+    wT = d["wp"][:cout].t().contiguous().to(dev)
+    add = torch.randn(m, cin).to(torch.bfloat16)
+    dx = torch.full((m, cin), 7.0, device=dev, dtype=torch.bfloat16)
+    C.conv_gemm("dgrad", d["dz"].to(dev), wT, n, h, w, cout, 3, 3, 1, out_bf16=dx, addend=add.to(dev), rows_per_tap=cin)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dx.float().cpu(), d["dx"] + add.float(), rtol=2e-2, atol=5e-2)
+
+
+@unvalidated
+@pytest.mark.parametrize("n,h,w,cin,cout", IMPLICIT_GEOMS)
+def test_implicit_conv_wgrad(n, h, w, cin, cout):
+    dev = _dev()
+    from colearn_federated_learning_b200.ops import conv as C
+    d = _implicit_case(n, h, w, cin, cout)
+    cp, kp = d["cout_pad"], d["k_pad"]
+    master = torch.zeros(cp, kp, device=dev)
+    shadow = torch.zeros(cp, kp, device=dev, dtype=torch.bfloat16)
+    C.conv_gemm("wgrad", d["act"].to(dev), d["dz"].to(dev), n, h, w, cin, 3, 3, 1, m_pad=cp, k_pad=kp, sgd_master=master,
+                sgd_lr=-1.0, sgd_shadow=shadow)                                  # lr = -1: master = +dW
+    torch.cuda.synchronize()
+    scale = float(d["dw"].abs().max())
+    torch.testing.assert_close(master[:cout, :9 * cin].cpu(), d["dw"], rtol=2e-2, atol=2e-2 * scale)
+    assert float(master[cout:].abs().max() if cp > cout else 0.0) == 0.0 and float(master[:, 9 * cin:].abs().max() if kp > 9 * cin else 0.0) == 0.0
+    assert torch.equal(shadow, master.to(torch.bfloat16))
+    s = 4
+    part = torch.zeros(s * cp * kp + 64, device=dev)
+    C.conv_gemm("wgrad", d["act"].to(dev), d["dz"].to(dev), n, h, w, cin, 3, 3, 1, m_pad=cp, k_pad=kp, split_k=s, split_out=part)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(part[: s * cp * kp].view(s, cp, kp).sum(0), master, rtol=1e-3, atol=1e-3 * scale)
+
+
+@unvalidated
+@pytest.mark.parametrize("flags", [{"COLEARN_CONV_IMPLICIT": "1"}, {"COLEARN_CONV_IMPLICIT": "2"},
+                                   {"COLEARN_CONV_IMPLICIT": "2", "COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_DGRAD_KN": "1",
+                                    "COLEARN_CONV_SPLITK": "1", "COLEARN_CONV_FUSED_BN": "1"}])
+def test_implicit_step_matches_default_schedule(flags, monkeypatch):
+    dev = _dev()
+    torch.manual_seed(0)
+    x = torch.randn(256, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (256,), device=dev)
+
+    def run():
+        torch.manual_seed(1)
+        model = ResNet18(10).to(dev)
+        flat = flatten_params(model)
+        flat0 = flat.clone()
+        tr = ConvNetTrainer(model, dev, 128, (32, 32))
+        tr.load(flat, model)
+        for lo in (0, 128):
+            tr._graph_step(x[lo:lo + 128], y[lo:lo + 128], 0.05)
+        tr.store(flat, model)
+        torch.cuda.synchronize()
+        return flat.clone() - flat0
+
+    for k in ("COLEARN_CONV_IMPLICIT", "COLEARN_CONV_WGRAD_MN", "COLEARN_CONV_DGRAD_KN", "COLEARN_CONV_SPLITK", "COLEARN_CONV_STREAMS",
+              "COLEARN_CONV_FUSED_BN", "COLEARN_CONV_SHADOW_T"):
+        monkeypatch.delenv(k, raising=False)
+    base = run()
+    for k, v in flags.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    cos = float((got * base).sum() / (got.norm() * base.norm()))
+    assert cos > 0.9 and torch.isfinite(got).all(), cos
