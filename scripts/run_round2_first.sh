@@ -8,9 +8,17 @@
 #   5. cfg4 at N=1 with the default path, cfg1 on a GPU
 # Everything lands in gpurun_out/r2_*; copy the summaries into profiles/.
 mkdir -p gpurun_out
-COLEARN_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider \
-    > gpurun_out/r2_unvalidated_tests.log 2>&1
-grep -E "passed|failed|error" gpurun_out/r2_unvalidated_tests.log | tail -n 3
+# one pytest process per group: a kernel that hangs only takes its own group down (timeout kills the process + context)
+: > gpurun_out/r2_unvalidated_tests.log
+for grp in "resnet_eval" "fused_batchnorm or optional_step" "splitk_reduce or gemm_split_k or split_k_step" \
+           "mn_major_operands or mn_major_b_operand or mn_major_fused" "mn_major_wgrad_step" \
+           "implicit_conv_forward" "implicit_conv_wgrad" "implicit_step"; do
+  echo "=== group: $grp" >> gpurun_out/r2_unvalidated_tests.log
+  COLEARN_RUN_UNVALIDATED=1 timeout 240 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider -k "$grp" \
+      >> gpurun_out/r2_unvalidated_tests.log 2>&1
+  echo "rc=$? ($grp)" | tee -a gpurun_out/r2_unvalidated_tests.log
+done
+grep -E "passed|failed|error" gpurun_out/r2_unvalidated_tests.log | tail -n 12
 grep -E "^FAILED|^ERROR" gpurun_out/r2_unvalidated_tests.log | cut -c1-160 | head -n 40
 if grep -E "^FAILED.*(mn_major|b_operand)" gpurun_out/r2_unvalidated_tests.log > /dev/null; then
   timeout 300 python scripts/debug_umma_mn.py > gpurun_out/r2_umma_mn_sweep.log 2>&1
