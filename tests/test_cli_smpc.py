@@ -234,3 +234,22 @@ def test_save_every_in_remote_mode(tmp_path):
     assert seen[:2] == [(0, True, 1), (1, True, 2)]            # rounds 1 and 2 left partial checkpoints behind
     meta = load_meta(c.path)
     assert meta["rounds"] == 3 and not meta.get("partial", False)
+
+
+def test_bench_paper_experiment_runs_end_to_end():
+    """``bench.py --config paper``: the reference's published experiment (12 rounds x 1000 it, 2 remote worker
+    processes over TCP, FFNN + BCE) through the real coordinator and ``remote_worker.py`` — one JSON line, rounds/s
+    far above the published 0.1133 (2 x RPi 3B+)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--config", "paper", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["config"]["name"] == "paper" and out["config"]["rounds_per_training"] == 12 and out["config"]["workers"] == 2
+    assert out["unit"] == "rounds/s" and out["value"] > 1.0 and out["vs_baseline"] > 8
+    assert len(out["config"]["final_losses"]) == 2
