@@ -112,7 +112,7 @@ def build_host(force: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     out = host_path()
     src = os.path.join(CSRC, "mlp_host.cpp")
-    cxx_flags = [f for f in flags if f != "-O2"] + ["-O3", "-fno-math-errno", f"-DTORCH_EXTENSION_NAME={HOST_NAME}"]
+    cxx_flags = [f for f in flags if f != "-O2"] + ["-O3", "-fno-math-errno", "-fopenmp-simd", f"-DTORCH_EXTENSION_NAME={HOST_NAME}"]
     h = hashlib.sha1(open(src, "rb").read() + " ".join(cxx_flags).encode()).hexdigest()[:16]
     obj = os.path.join(OBJ, f"mlp_host.cpp.{h}.o")
     if force or not os.path.exists(obj) or not os.path.exists(out):

@@ -83,8 +83,10 @@ __attribute__((always_inline)) inline void forward_one(const Net& net, const flo
     float* out = acts + (int64_t)(l + 1) * stride_l;
     for (int j = 0; j < n; ++j) {
       const float* wr = w + (int64_t)j * k;
-      float s = b[j];
+      float s = 0.f;
+#pragma omp simd reduction(+ : s)
       for (int i = 0; i < k; ++i) s += wr[i] * in[i];
+      s += b[j];
       if (l < L - 1) s = s > 0.f ? s : 0.f;
       else if (net.sigmoid_out) s = 1.f / (1.f + std::exp(-s));
       out[j] = s;
