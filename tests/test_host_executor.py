@@ -130,3 +130,32 @@ def test_host_executor_is_orders_of_magnitude_faster_than_eager_definitions():
     reference.mlp_local_sgd(flat.clone(), dims, x, y, reference.make_permutation(400, 1, 0, shuffle=False), 1, 0.01, 1, -1, "xent")
     t_ref = time.perf_counter() - t0
     assert t_host * 5 < t_ref, (t_host, t_ref)
+
+
+def test_host_fit_matches_reference_on_random_architectures():
+    """Property test: any MLP shape / batch size / loss / step limit — the executor tracks the PyTorch definitions."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(hidden=st.lists(st.integers(1, 24), min_size=0, max_size=3), d_in=st.integers(1, 12), d_out=st.integers(1, 5),
+           batch=st.integers(1, 9), n=st.integers(1, 23), loss=st.sampled_from(["xent", "sse", "mse", "bce"]),
+           epochs=st.integers(1, 3), limit=st.sampled_from([-1, 1, 4]), seed=st.integers(0, 10_000))
+    def prop(hidden, d_in, d_out, batch, n, loss, epochs, limit, seed):
+        dims = (d_in, *hidden, d_out)
+        act = "sigmoid" if loss == "bce" else ("sigmoid" if seed % 3 == 0 and loss != "xent" else "none")
+        if loss == "xent" and d_out < 2:
+            dims = (d_in, *hidden, 2)
+        g = torch.Generator().manual_seed(seed)
+        x = torch.rand(n, dims[0], generator=g)
+        y = (torch.randint(0, dims[-1], (n, 1), generator=g).float() if loss == "xent"
+             else (torch.rand(n, dims[-1], generator=g) > 0.5).float())
+        p = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1))
+        flat0 = (torch.rand(p, generator=g) - 0.5) * 0.8
+        perm = reference.make_permutation(n, epochs, seed)
+        want, got = flat0.clone(), flat0.clone()
+        last = reference.mlp_local_sgd(want, dims, x, y, perm, batch, 0.05, epochs, limit, loss, act)
+        res = host.mlp_local_sgd_multi(dims, act, [got], [x], [y], [perm], batch, 0.05, epochs, limit, loss)
+        torch.testing.assert_close(got, want, rtol=5e-4, atol=5e-5)
+        assert abs(float(res[0, 0]) - float(last)) <= 2e-4 * max(1.0, abs(float(last)))
+
+    prop()
