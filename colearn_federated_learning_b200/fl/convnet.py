@@ -34,6 +34,24 @@ from ..ops import conv as C
 BF = torch.bfloat16
 PAD = 128
 
+# Step schedule (docs/ROUND2_NOTES.md).  Every entry is a re-scheduling / operand-layout choice with the same
+# mathematical result; an entry goes to its non-zero value here once its row has been measured on a B200.  The
+# environment (COLEARN_CONV_<NAME>=<int>) overrides in both directions, constructor arguments override the environment.
+SCHEDULE_DEFAULTS = {
+    "STREAMS": 0,     # 1: wgrad chains on a second stream inside the step graph
+    "SHADOW_T": 0,    # 1: W^T written by the wgrad epilogue instead of a transpose launch
+    "FUSED_BN": 0,    # 1: BatchNorm reduction + finalize in one launch
+    "SPLITK": 0,      # 1: split-K for the skinny wgrad GEMMs, 2: also the layer4 forwards
+    "WGRAD_MN": 0,    # 1: wgrad GEMMs read dz / col in place (MN-major operands)
+    "DGRAD_KN": 0,    # 1: dgrad GEMMs read the packed weights (MN-major B), no W^T copies
+    "IMPLICIT": 0,    # 1: implicit-GEMM forward + dgrad for the stride-1 3x3 convs, 2: wgrad too
+}
+
+
+def schedule_flag(name: str) -> int:
+    v = os.environ.get("COLEARN_CONV_" + name, "").strip()
+    return int(v) if v else SCHEDULE_DEFAULTS[name]
+
 
 def _pad(n: int, m: int = PAD) -> int:
     return (n + m - 1) // m * m
@@ -189,26 +207,26 @@ class ConvNetTrainer:
         self._bound: Optional[nn.Module] = None
         self._model_ref = weakref.ref(model)
         # opt-in (not yet measured on a B200): wgrad chains on a second stream, see _conv_bwd
-        self._side = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and os.environ.get("COLEARN_CONV_STREAMS") == "1") else None
-        self._fuse_shadow_t = os.environ.get("COLEARN_CONV_SHADOW_T") == "1"
+        self._side = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and schedule_flag("STREAMS")) else None
+        self._fuse_shadow_t = bool(schedule_flag("SHADOW_T"))
         # opt-in: BatchNorm reduction + finalize in one launch (ticket counter, last block finalises)
         self.bn_counters = (torch.zeros(max(cv.cout for cv in self.convs) // 64, device=dev, dtype=torch.int32)
-                            if os.environ.get("COLEARN_CONV_FUSED_BN") == "1" and act_dtype == BF else None)
+                            if schedule_flag("FUSED_BN") and act_dtype == BF else None)
         self._graph = None
         self._graph_key = None
         z = lambda *s, dt=act_dtype: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
         # opt-in (not yet measured on a B200): split-K for the GEMMs with too few output tiles to fill 148 SMs
         # opt-in (not yet measured on a B200): wgrad GEMMs on MN-major operands — no dz^T / col^T transposes
-        self._wgrad_mn = (os.environ.get("COLEARN_CONV_WGRAD_MN") == "1") if wgrad_mn is None else bool(wgrad_mn)
+        self._wgrad_mn = bool(schedule_flag("WGRAD_MN")) if wgrad_mn is None else bool(wgrad_mn)
         # opt-in: dgrad GEMMs against the packed weights themselves (MN-major B operand) — no W^T copies to refresh
-        self._dgrad_kn = (os.environ.get("COLEARN_CONV_DGRAD_KN") == "1") if dgrad_kn is None else bool(dgrad_kn)
+        self._dgrad_kn = bool(schedule_flag("DGRAD_KN")) if dgrad_kn is None else bool(dgrad_kn)
         # opt-in: implicit GEMM for the stride-1 3x3 convolutions (1: forward + dgrad, 2: wgrad too)
-        self._implicit = int(os.environ.get("COLEARN_CONV_IMPLICIT", "0") or 0) if implicit is None else int(implicit)
+        self._implicit = schedule_flag("IMPLICIT") if implicit is None else int(implicit)
         for cv in self.convs:
             cv.implicit = (self._implicit > 0 and cv.k == 3 and cv.pad == 1 and cv.cout % 64 == 0
                            and C.implicit_ok(cv.h, cv.w, cv.cin, cv.stride, B))
         # COLEARN_CONV_SPLITK=1: wgrads only; =2: forwards too
-        self._splitk = int(os.environ.get("COLEARN_CONV_SPLITK", "0") or 0) if split_k is None else int(split_k)
+        self._splitk = schedule_flag("SPLITK") if split_k is None else int(split_k)
         for cv in self.convs:
             cv.s_fwd = self._pick_split(cv.m, cv.cout_pad, cv.K_pad, min_slices=8) if self._splitk >= 2 else 1
             cv.s_wgrad = self._pick_split(cv.cout_pad, cv.K_pad, cv.m, min_slices=4) if self._splitk >= 1 else 1
