@@ -37,6 +37,7 @@ class Arguments:
     dtype: str = "fp32"            # fp32 | bf16 (box mode: bf16 shadow of the broadcast for the tcgen05 consumers)
     save_every: int = 0            # >0: checkpoint every N rounds, not only after the last one
     synthetic: int = 0             # >0: generate this many synthetic UNSW-shaped rows
+    dataset: str = "unsw"          # data.DATASET_REGISTRY entry that reads test_path (user datasets: data.register_dataset)
     n_train_items_enc: int = 1000  # fc.py:432
     precision_fractional: int = 3  # fc.py:433
 

@@ -26,7 +26,7 @@ from typing import Any, Dict, List, Optional
 import torch
 
 from .. import ops, settings
-from ..data import NetworkTrafficDataset, federate, synthetic_for_model, BaseDataset
+from ..data import federate, synthetic_for_model, BaseDataset
 from ..fl.fedavg import normalized_weights
 from ..fl.trainer import FitConfig, local_fit, make_perm, resolve_loss
 from ..fl.evaluate import evaluate
@@ -233,7 +233,8 @@ class Coordinator(BusClient):
         if self.args.synthetic and self.args.synthetic > 0:
             x, y = synthetic_for_model(self.args.model, self.args.synthetic, seed=self.args.seed)
             return BaseDataset(x, y)
-        return NetworkTrafficDataset(self.args.test_path)
+        from ..data import load_dataset
+        return load_dataset(getattr(self.args, "dataset", "unsw"), self.args.test_path)
 
     def _fit_config(self, mode: str) -> FitConfig:
         loss = self.args.loss

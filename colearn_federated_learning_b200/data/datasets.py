@@ -138,3 +138,31 @@ def dataset_tensors(ds, device: Optional[torch.device] = None) -> Tuple[torch.Te
     if device is not None:
         x, y = x.to(device), y.to(device)
     return x, y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# dataset registry: what ``--dataset NAME`` resolves to on both CLIs (the reference tells its users to write their own
+# ``datasets.py`` and edit ``remote_worker.py`` / ``starting_training_local``, README.md:119-169)
+# ------------------------------------------------------------------------------------------------------------------
+DATASET_REGISTRY = {"unsw": NetworkTrafficDataset}
+
+
+def register_dataset(name: str, factory, overwrite: bool = False) -> None:
+    """``factory(path) -> dataset`` with ``.data`` / ``.targets`` (array-likes or tensors, one row per sample), e.g. a
+    :class:`BaseDataset`.  Selected with ``--dataset NAME`` together with ``-dt/--training`` (worker) or ``--test-path``
+    (coordinator, local / encrypted mode and evaluation)."""
+    if not name or not isinstance(name, str):
+        raise ValueError("dataset name must be a non-empty string")
+    if name in DATASET_REGISTRY and not overwrite:
+        raise ValueError(f"dataset {name!r} is already registered (pass overwrite=True to replace it)")
+    if not callable(factory):
+        raise TypeError("factory must be callable")
+    DATASET_REGISTRY[name] = factory
+
+
+def load_dataset(name: str, path: str):
+    try:
+        factory = DATASET_REGISTRY[name]
+    except KeyError:
+        raise ValueError(f"unknown dataset {name!r}; choose from {sorted(DATASET_REGISTRY)} or register one (--plugin)") from None
+    return factory(path)

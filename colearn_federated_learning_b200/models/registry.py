@@ -29,6 +29,48 @@ DEFAULT_LOSS = {"ffnn": "bce", "testing_remote": "sse", "net": "xent", "mlp": "x
                 "wide_mlp": "xent", "resnet18": "xent"}
 
 
+def register_model(name: str, factory: Callable[..., nn.Module], default_loss: str = "xent", overwrite: bool = False) -> None:
+    """Add a user architecture under ``--model NAME`` (the reference asks its users to edit ``client_federated.py`` and
+    ``starting_training_local`` instead, README.md:119-169).  ``factory()`` must return a fresh ``nn.Module``; an
+    :class:`~colearn_federated_learning_b200.models.mlp.MLPNet` (any layer sizes) trains through the persistent-kernel /
+    layer-wise / native host executors, every other module through the autograd path with this repo's flat SGD and
+    loss kernels.  Coordinator and workers must register the same name (models travel as flat parameter vectors, never
+    as code): load the registering module on both sides with ``--plugin``."""
+    if not name or not isinstance(name, str):
+        raise ValueError("model name must be a non-empty string")
+    if name in MODEL_REGISTRY and not overwrite:
+        raise ValueError(f"model {name!r} is already registered (pass overwrite=True to replace it)")
+    if default_loss not in ("bce", "sse", "xent", "mse"):
+        raise ValueError(f"unknown loss {default_loss!r}")
+    if not callable(factory):
+        raise TypeError("factory must be callable")
+    MODEL_REGISTRY[name] = factory
+    DEFAULT_LOSS[name] = default_loss
+
+
+def load_plugins(specs) -> List[str]:
+    """Import user modules that call :func:`register_model` / ``data.register_dataset`` (``--plugin`` on both CLIs).
+    A spec is a dotted module name or a path to a ``.py`` file."""
+    import importlib
+    import importlib.util
+    import os
+
+    loaded = []
+    for spec in specs or []:
+        if spec.endswith(".py") or os.sep in spec:
+            path = os.path.abspath(spec)
+            name = "colearn_plugin_" + os.path.splitext(os.path.basename(path))[0]
+            sp = importlib.util.spec_from_file_location(name, path)
+            if sp is None or sp.loader is None:
+                raise ImportError(f"cannot load plugin {spec!r}")
+            mod = importlib.util.module_from_spec(sp)
+            sp.loader.exec_module(mod)
+        else:
+            mod = importlib.import_module(spec)
+        loaded.append(mod.__name__)
+    return loaded
+
+
 def build_model(name: str, **kwargs) -> nn.Module:
     try:
         return MODEL_REGISTRY[name](**kwargs)

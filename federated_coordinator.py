@@ -51,6 +51,10 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--log-interval", type=int, default=d.log_interval)
     parser.add_argument("--test-path", type=str, default=d.test_path, help="CSV used by local/encrypted mode and evaluation")
     parser.add_argument("--synthetic", type=int, default=0, help="use N synthetic UNSW-shaped rows instead of --test-path")
+    parser.add_argument("--dataset", default="unsw", help="dataset adapter that reads --test-path (data.register_dataset; default: the Bot-IoT CSV adapter)")
+    parser.add_argument("--plugin", action="append", default=[], metavar="MODULE_OR_FILE",
+                        help="import this module / .py file first: it may call models.register_model / data.register_dataset "
+                             "(the reference's 'use your own model/dataset' without editing sources; repeatable)")
     parser.add_argument("--weighted", action="store_true", help="sample-count weighted FedAvg (default: uniform, like the reference)")
     parser.add_argument("--select", type=int, default=None, help="train at most k of the collected workers")
     parser.add_argument("--selection", choices=["all", "first", "random"], default="all")
@@ -86,6 +90,7 @@ def arguments_from_cli(ns: argparse.Namespace) -> Arguments:
     a.log_interval, a.test_path, a.synthetic, a.weighted = ns.log_interval, ns.test_path, ns.synthetic, ns.weighted
     a.no_cuda, a.backend = ns.no_cuda, ns.backend
     a.dtype, a.save_every = ns.dtype, max(0, ns.save_every)
+    a.dataset = ns.dataset
     return a
 
 
@@ -139,5 +144,16 @@ def main(args: argparse.Namespace) -> None:
             broker.stop()
 
 
+def parse_cli(argv=None) -> argparse.Namespace:
+    """Plugins are imported before the real parser is built, so that ``--model`` accepts what they register."""
+    pre = argparse.ArgumentParser(add_help=False)
+    pre.add_argument("--plugin", action="append", default=[])
+    known, _ = pre.parse_known_args(argv)
+    if known.plugin:
+        from colearn_federated_learning_b200.models import load_plugins
+        load_plugins(known.plugin)
+    return build_parser().parse_args(argv)
+
+
 if __name__ == "__main__":
-    main(build_parser().parse_args())
+    main(parse_cli())

@@ -36,6 +36,9 @@ _OPTIONS = (
     (("--data-model",), dict(default="ffnn", help="architecture the synthetic data is shaped for (resnet18: 32x32 images, net: "
                                                   "28x28, testing_remote: 2 features, otherwise the ten UNSW-IoT features)")),
     (("--seed",), dict(type=int, default=0)),
+    (("--dataset",), dict(default="unsw", help="dataset adapter that reads -dt / -di (data.register_dataset; default: the Bot-IoT CSV adapter)")),
+    (("--plugin",), dict(action="append", default=[], metavar="MODULE_OR_FILE",
+                         help="import this module / .py file first: it may call models.register_model / data.register_dataset (repeatable)")),
     (("--no-cuda",), dict(action="store_true", help="serve fits on the CPU even if a GPU is present")),
     (("--no-will",), dict(action="store_true", help="do not register the NOT_READY last-will with the broker")),
     (("--tls-ca",), dict(default=None, help="CA bundle: verify the broker; with --tls-cert also demand a client certificate from the coordinator")),
@@ -53,13 +56,13 @@ def build_parser() -> argparse.ArgumentParser:
 
 def pick_dataset(args):
     """--synthetic N > the CSV given with -dt > the reference's XOR toy set (rw.py:75-80)."""
-    from colearn_federated_learning_b200.data import BaseDataset, NetworkTrafficDataset, synthetic_for_model, xor_toy_dataset
+    from colearn_federated_learning_b200.data import BaseDataset, load_dataset, synthetic_for_model, xor_toy_dataset
 
     if args.synthetic > 0:
         return BaseDataset(*synthetic_for_model(args.data_model, args.synthetic, seed=args.seed))
     if args.training:
         logging.info("training data: %s", args.training)
-        return NetworkTrafficDataset(args.training)
+        return load_dataset(args.dataset, args.training)
     return xor_toy_dataset()
 
 
@@ -69,8 +72,10 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
     from colearn_federated_learning_b200.control.bus import BusClient
     from colearn_federated_learning_b200.control.event_parser import format_event
     from colearn_federated_learning_b200.control.workers import WorkerServer
-    from colearn_federated_learning_b200.data import NetworkTrafficDataset
+    from colearn_federated_learning_b200.data import load_dataset
+    from colearn_federated_learning_b200.models import load_plugins
 
+    load_plugins(args.plugin)
     logging.basicConfig(format="%(asctime)s: %(message)s", level=logging.INFO, datefmt="%H:%M:%S")
     identity = f"{args.host}:{args.port}"
     on_gpu = torch.cuda.is_available() and not args.no_cuda
@@ -82,8 +87,8 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
     server.add_dataset(pick_dataset(args), key="training")                       # rw.py:108
     if args.inference:
         logging.info("inference data: %s", args.inference)
-        rows = NetworkTrafficDataset(args.inference).data
-        server.load_data([torch.tensor(r).float() for r in rows], tag="inference")   # rw.py:102-104
+        rows = load_dataset(args.dataset, args.inference).data
+        server.load_data([torch.as_tensor(r).float() for r in rows], tag="inference")   # rw.py:102-104
 
     # one bus identity per device (the reference's shared literal id gets duplicates kicked)
     bus = BusClient(client_id="worker-" + identity, transport="tcp")

@@ -253,3 +253,77 @@ def test_bench_paper_experiment_runs_end_to_end():
     assert out["config"]["name"] == "paper" and out["config"]["rounds_per_training"] == 12 and out["config"]["workers"] == 2
     assert out["unit"] == "rounds/s" and out["value"] > 1.0 and out["vs_baseline"] > 8
     assert len(out["config"]["final_losses"]) == 2
+
+
+def test_plugin_registers_model_and_dataset_for_both_clis(tmp_path):
+    """The reference's "use your own model/dataset" (README.md:119-169) without editing sources: a plugin registers a
+    new architecture and a dataset adapter; the coordinator CLI trains it in VirtualWorker mode, a worker hosts it."""
+    import math
+    import subprocess
+    import sys
+
+    import torch
+
+    from colearn_federated_learning_b200.data import DATASET_REGISTRY, load_dataset, register_dataset
+    from colearn_federated_learning_b200.models import MODEL_REGISTRY, build_model, load_plugins, register_model
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    plugin = os.path.join(root, "examples", "my_plugin.py")
+    csv_path = tmp_path / "moons.csv"
+    g = torch.Generator().manual_seed(0)
+    with open(csv_path, "w") as f:
+        for i in range(200):
+            lab = i % 2
+            a = float(torch.rand(1, generator=g)) * math.pi
+            x0 = math.cos(a) + (1.0 if lab else 0.0) + 0.05 * float(torch.randn(1, generator=g))
+            x1 = (math.sin(a) if not lab else 0.5 - math.sin(a)) + 0.05 * float(torch.randn(1, generator=g))
+            f.write(f"{x0:.5f},{x1:.5f},{lab}\n")
+    # registry API
+    assert load_plugins([plugin]) and "tiny_mlp" in MODEL_REGISTRY and "two_moons_csv" in DATASET_REGISTRY
+    assert build_model("tiny_mlp").spec.dims == (2, 16, 16, 2)
+    assert len(load_dataset("two_moons_csv", str(csv_path))) == 200
+    with pytest.raises(ValueError):
+        register_model("tiny_mlp", lambda: None)                       # duplicate without overwrite
+    with pytest.raises(ValueError):
+        register_dataset("unsw", lambda p: None)
+    with pytest.raises(ValueError):
+        load_dataset("nope", "x")
+    # coordinator CLI: VirtualWorker mode on the plugin's model + dataset, driven by two bus events
+    ckpt = tmp_path / "plug.pth"
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    coord = subprocess.Popen([sys.executable, os.path.join(root, "federated_coordinator.py"), "-t", "topic/state", "-w", "1", "-p", str(port),
+                              "--host", "127.0.0.1", "--embedded-broker", "--exit-after", "1", "--plugin", plugin, "--model", "tiny_mlp",
+                              "--dataset", "two_moons_csv", "--test-path", str(csv_path), "--checkpoint", str(ckpt), "--no-cuda", "--lr", "0.05"],
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        from colearn_federated_learning_b200.control.bus import BusClient
+        import time
+        deadline = time.time() + 60
+        pub = BusClient("plug-pub", transport="tcp")
+        while True:
+            try:
+                pub.connect("127.0.0.1", port)
+                break
+            except OSError:
+                assert time.time() < deadline and coord.poll() is None, "coordinator did not come up"
+                time.sleep(0.2)
+        pub.loop_start()
+        pub.publish("topic/state", "(192.168.1.7, TRAINING)")
+        pub.publish("topic/state", "(192.168.1.8, TRAINING)")
+        out, _ = coord.communicate(timeout=120)
+        pub.loop_stop()
+    finally:
+        if coord.poll() is None:
+            coord.kill()
+    assert coord.returncode == 0, out[-3000:]
+    sd = torch.load(str(ckpt))
+    assert list(sd) == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias"] and sd["fc1.weight"].shape == (16, 2)
+    # worker CLI accepts the same plugin / dataset flags
+    import remote_worker
+    ns = remote_worker.build_parser().parse_args(["--host", "127.0.0.1", "-b", "x", "-t", "t", "--plugin", plugin, "--dataset", "two_moons_csv",
+                                                  "-dt", str(csv_path)])
+    ds = remote_worker.pick_dataset(ns)
+    assert len(ds) == 200 and ds.data.shape[1] == 2
