@@ -260,6 +260,9 @@ def bench_paper(args) -> None:
                    "seconds_per_round": total_s / K / rounds, "published_seconds_per_round": 8.827,
                    "worker_device": "cuda (persistent kernel)" if use_cuda else "cpu (native host executor)",
                    "final_losses": {k: float(v) for k, v in final_losses.items()},
+                   "bytes_coordinator_to_workers_per_round": c.windower.last_result.get("bytes_out", 0) // rounds,
+                   "bytes_workers_to_coordinator_per_round": c.windower.last_result.get("bytes_in", 0) // rounds,
+                   "published_bytes_per_round": "~72 kB to 2 workers, ~30.6 kB back per worker (paper §4.3)",
                    "baseline_ref": "0.1133 rounds/s = 12 rounds x 1000 it on 2x RPi 3B+ (BASELINE.md)"},
         "e2e": {"value": value, "unit": "rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "timing": "the measurement is already end to end (host clock around whole trainings, model shipped over TCP both ways every round)"},

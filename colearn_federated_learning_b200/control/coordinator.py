@@ -359,7 +359,11 @@ class Coordinator(BusClient):
                     log.info("Worker %s failed this round: %r", wid, e)
                     return wid, None, None, 0
 
+            traffic = lambda w: (getattr(w, "bytes_sent", 0), getattr(w, "bytes_received", 0))  # noqa: E731 - any handle type
+            sent0 = {wid: traffic(w) for wid, w in alive.items()}
             results = await asyncio.gather(*[one(wid, w) for wid, w in alive.items()])
+            bytes_out = sum(traffic(w)[0] - sent0[wid][0] for wid, w in to_train.items() if wid in sent0)
+            bytes_in = sum(traffic(w)[1] - sent0[wid][1] for wid, w in to_train.items() if wid in sent0)
             flats, counts, ids = [], [], []
             for wid, flat, loss, n in results:
                 if flat is not None:
@@ -377,7 +381,10 @@ class Coordinator(BusClient):
                 th = theta.to(self.device)
                 ops.fedavg_apply(th, stacked, w, self.args.server_lr)
                 theta = th.cpu()
-            self.metrics.end_round(r, time.time() - t0, selected=ids, n_k=counts)
+            # traffic of this round: model + fit config towards the devices, trained model + loss back (paper §4.3)
+            self.metrics.end_round(r, time.time() - t0, selected=ids, n_k=counts, bytes_out=bytes_out, bytes_in=bytes_in)
+            result["bytes_out"] = result.get("bytes_out", 0) + bytes_out
+            result["bytes_in"] = result.get("bytes_in", 0) + bytes_in
             self._maybe_checkpoint(model, theta, r, {"workers": list(to_train.keys()), "mode": "remote"})
             if not alive:
                 break

@@ -64,9 +64,11 @@ class VirtualWorker:
 # ---------------------------------------------------------------------------------------------
 # framing
 # ---------------------------------------------------------------------------------------------
-def _send_msg(sock: socket.socket, obj: Dict[str, Any]) -> None:
+def _send_msg(sock: socket.socket, obj: Dict[str, Any]) -> int:
+    """Returns the number of bytes put on the wire (frame header included)."""
     data = msgpack.packb(obj, use_bin_type=True)
     sock.sendall(struct.pack(">I", len(data)) + data)
+    return 4 + len(data)
 
 
 def _recv_exact(sock: socket.socket, n: int) -> bytes:
@@ -82,10 +84,12 @@ def _recv_exact(sock: socket.socket, n: int) -> bytes:
 MAX_FRAME = 1 << 30   # 1 GiB: five times the largest arena in the model zoo (wide MLP, 201.6 MB)
 
 
-def _recv_msg(sock: socket.socket) -> Dict[str, Any]:
+def _recv_msg(sock: socket.socket, counter: Optional[List[int]] = None) -> Dict[str, Any]:
     (n,) = struct.unpack(">I", _recv_exact(sock, 4))
     if n > MAX_FRAME:
         raise ConnectionError(f"frame of {n} bytes exceeds the {MAX_FRAME}-byte limit")
+    if counter is not None:
+        counter[0] += 4 + n
     return msgpack.unpackb(_recv_exact(sock, n), raw=False)
 
 
@@ -242,6 +246,10 @@ class RemoteWorkerClient:
             sock = ssl_context.wrap_socket(sock, server_hostname=host)
         self._sock: Optional[socket.socket] = sock
         self._sock.settimeout(None)
+        # application-level traffic of this handle (the paper's §4.3 measures the same two directions with psutil:
+        # ~36 kB per worker and round towards the device, ~30.6 kB back, for a 9.6 kB model)
+        self.bytes_sent = 0
+        self.bytes_received = 0
 
     def _call(self, req: Dict[str, Any], timeout: Optional[float] = None) -> Dict[str, Any]:
         with self._lock:
@@ -249,8 +257,10 @@ class RemoteWorkerClient:
                 raise ConnectionError(f"worker {self.id} is closed")
             try:
                 self._sock.settimeout(timeout)
-                _send_msg(self._sock, req)
-                resp = _recv_msg(self._sock)
+                self.bytes_sent += _send_msg(self._sock, req)
+                got = [0]
+                resp = _recv_msg(self._sock, got)
+                self.bytes_received += got[0]
             except (OSError, ConnectionError, struct.error):
                 # a timed-out / broken exchange leaves the stream out of step (the late reply would be read as the
                 # answer to the next request): the handle is dead from here on

@@ -180,6 +180,11 @@ def test_remote_rounds_over_tcp_workers(tmp_path):
         assert c.args.federate_after_n_batches == 1000                     # round>1 rule (fc.py:533-535)
         assert w1.fits_served == 3 and w2.fits_served == 3
         assert os.path.exists(c.path) and len(settings.training_devices) == 0
+        # traffic accounting (paper §4.3): per round and worker one fit request (2 401 fp32 parameters + config) out and
+        # the trained parameters + loss back — ~9.7 kB each way against the reference's ~36 kB / ~30.6 kB
+        recs = [r for r in c.metrics.records if "bytes_out" in r]
+        assert len(recs) == 3 and all(2 * 9604 < r["bytes_out"] < 2 * 11000 and 2 * 9604 < r["bytes_in"] < 2 * 11000 for r in recs)
+        assert res["bytes_out"] == sum(r["bytes_out"] for r in recs) and res["bytes_in"] == sum(r["bytes_in"] for r in recs)
     finally:
         w1.stop(); w2.stop()
 
