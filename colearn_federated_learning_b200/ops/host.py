@@ -31,6 +31,8 @@ def load(build_if_missing: bool = False):
     with _lock:
         if _state["mod"] is not None:
             return _state["mod"]
+        if _state["tried"] and not build_if_missing:
+            return None                                   # negative result is cached: available() runs once per fit
         hits = sorted(glob.glob(os.path.join(_HERE, "_colearn_host*.so")))
         if not hits and build_if_missing:
             try:
