@@ -275,9 +275,9 @@ class ConvNetTrainer:
         return s if s >= max(2, min_slices) else 1
 
     def _needs_wT(self, cv: _Conv) -> bool:
-        """A bf16 ``Wᵀ`` copy is the dgrad's K-major B operand — explicit schedule without ``dgrad_kn``, and every
-        implicit dgrad (rows ``(tap, ci)``, columns ``co``)."""
-        return cv.implicit or not self._dgrad_kn
+        """A bf16 ``Wᵀ`` copy is the dgrad's K-major B operand; ``dgrad_kn`` (explicit and implicit schedule alike) reads
+        the packed weights instead."""
+        return not self._dgrad_kn
 
     def _gemm_fwd(self, cv: _Conv) -> None:
         """``cv.z = cv.col · Wpᵀ`` (bf16), split-K when the layer has few output tiles."""
@@ -448,8 +448,12 @@ class ConvNetTrainer:
         if cv.implicit and cv.x_in is not None:
             # dx[p, ci] = Σ_(tap, co) dz[p + pad − tap, co]·Wᵀ[(tap, ci), co] (+ the identity branch's gradient): dz boxes
             # through the 4-D map, no dcol, no col2im
-            C.conv_gemm("dgrad", cv.dz, cv.wT, cv.n, cv.oh, cv.ow, cv.cout, cv.k, cv.k, cv.pad, out_bf16=dx, addend=add,
-                        rows_per_tap=cv.cin)
+            if self._dgrad_kn:     # ... against the packed weights themselves (MN-major B), no W^T copy
+                C.conv_gemm("dgrad", cv.dz, self._w(cv.entry), cv.n, cv.oh, cv.ow, cv.cout, cv.k, cv.k, cv.pad, out_bf16=dx,
+                            addend=add, rows_per_tap=cv.cin, w_packed=True)
+            else:
+                C.conv_gemm("dgrad", cv.dz, cv.wT, cv.n, cv.oh, cv.ow, cv.cout, cv.k, cv.k, cv.pad, out_bf16=dx, addend=add,
+                            rows_per_tap=cv.cin)
             self.launches += 1
             return
         dcol = self.dcol[: cv.m * cv.K_pad].view(cv.m, cv.K_pad)

@@ -347,7 +347,7 @@ def implicit_ok(h: int, w: int, c: int, stride: int, n: int = 128) -> bool:
 
 def conv_gemm(kind: str, act: torch.Tensor, other: torch.Tensor, n: int, h: int, w: int, c: int, kh: int, kw: int, pad: int, *,
               out_bf16: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None, rows_per_tap: int = 0,
-              m_pad: int = 0, k_pad: int = 0, sgd_master: Optional[torch.Tensor] = None, sgd_lr: float = 0.0,
+              m_pad: int = 0, k_pad: int = 0, w_packed: bool = False, sgd_master: Optional[torch.Tensor] = None, sgd_lr: float = 0.0,
               sgd_shadow: Optional[torch.Tensor] = None, split_k: int = 0, split_out: Optional[torch.Tensor] = None) -> None:
     """The three GEMMs of a stride-1 convolution with the NHWC activation ``act`` (``[n*h*w, c]`` bf16) as an implicit
     operand (``csrc/conv_ops.cuh``: ``ConvAddr``; boxes of whole images through a 4-D tensor map, TMA zero fill = the
@@ -355,7 +355,8 @@ def conv_gemm(kind: str, act: torch.Tensor, other: torch.Tensor, n: int, h: int,
 
     * ``"fwd"``   ``out[p, co] = Σ act[p + tap − pad, ·]·other[co, tap·c + ·]`` — ``other`` = packed weights ``[Cout_pad, K_pad]``
     * ``"dgrad"`` ``out[p, ci] = Σ act[p + pad − tap, ·]·other[tap·rows_per_tap + ci, ·] (+ addend)`` — ``act`` = dz
-      ``[pixels, c = Cout]``, ``other`` = ``Wᵀ`` ``[K_pad, Cout]``, ``rows_per_tap`` = Cin
+      ``[pixels, c = Cout]``, ``other`` = ``Wᵀ`` ``[K_pad, Cout]``, ``rows_per_tap`` = Cin; with ``w_packed=True`` ``other`` is
+      the packed ``Wp[Cout_pad, K_pad]`` itself (MN-major B operand: no ``Wᵀ`` copy to keep in step with the updates)
     * ``"wgrad"`` ``dW[co, tap·c + ·] = Σ_p other[p, co]·act[p + tap − pad, ·]`` — ``other`` = dz ``[pixels, Cout]``; the
       result (``[m_pad, k_pad]``, K padding = zeros) goes through the fused SGD epilogue or the split-K partials.
 
@@ -367,11 +368,11 @@ def conv_gemm(kind: str, act: torch.Tensor, other: torch.Tensor, n: int, h: int,
         mod = _ext.require()
         if kind == "wgrad":
             assert m_pad > 0 and k_pad >= taps * c
-            geom = [2, 0, c, kh, kw, pad, h, w, n, 0, m_pad, k_pad, m]
+            geom = [2, 0, c, kh, kw, pad, h, w, n, 0, m_pad, k_pad, m, 0]
         elif kind == "fwd":
-            geom = [1, 0, c, kh, kw, pad, h, w, n, 0, m, out_bf16.shape[1] if out_bf16 is not None else other.shape[0], taps * c]
+            geom = [1, 0, c, kh, kw, pad, h, w, n, 0, m, out_bf16.shape[1] if out_bf16 is not None else other.shape[0], taps * c, 0]
         else:
-            geom = [1, 1, c, kh, kw, pad, h, w, n, rows_per_tap, m, rows_per_tap, taps * c]
+            geom = [1, 1, c, kh, kw, pad, h, w, n, rows_per_tap, m, rows_per_tap, taps * c, 1 if w_packed else 0]
         mod.gemm_tcgen05(act, other, None, False, None, out_bf16, None, None, sgd_master, float(sgd_lr), sgd_shadow, None, None,
                          0, 0, 1, 0, 0, 0, 0, int(split_k or 0), split_out, 0, False, addend, geom)
         return
@@ -392,7 +393,7 @@ def conv_gemm(kind: str, act: torch.Tensor, other: torch.Tensor, n: int, h: int,
         out_bf16.copy_(col.float() @ other[:, :k].float().t())
     elif kind == "dgrad":
         cin = rows_per_tap
-        wt = other[: taps * cin].float()                                    # [taps*cin, cout]
+        wt = (other[:c, : taps * cin].t() if w_packed else other[: taps * cin, :c]).float()   # [taps*cin, cout]
         dcol = act[:m].float() @ wt.t()                                     # [m, taps*cin], k = (tap, ci)
         dx = torch.zeros(m, cin, dtype=out_bf16.dtype)
         col2im(dcol.to(out_bf16.dtype), dx, addend, n, h, w, cin, kh, kw, 1, pad)

@@ -372,10 +372,10 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   TORCH_CHECK(!conv.empty() || (mn ? A.size(0) == B.size(0) : (b_kn ? A.size(1) <= B.size(0) : A.size(1) == B.size(1))),
               mn ? "A[K,a_cols], B[K,N]" : (b_kn ? "A[M,K], B[>=K,N]" : "A[M,K], B[N,K]"));
   c10::cuda::CUDAGuard guard(A.device());
-  // conv (implicit GEMM) = [mode, flip, C, KH, KW, pad, H, W, n_images, b_rows_per_tap, M, N, K]: A is the NHWC activation
+  // conv (implicit GEMM) = [mode, flip, C, KH, KW, pad, H, W, n_images, b_rows_per_tap, M, N, K, b_mn]: A is the NHWC activation
   // [n_images*H*W, C] read through a 4-D tensor map, B the other operand (mode 1: K-major weights; mode 2: dz [pixels, a_cols])
   const bool is_conv = !conv.empty();
-  TORCH_CHECK(!is_conv || (conv.size() == 13 && !mn && !b_kn), "conv = 13 ints, exclusive with mn_m / b_kn");
+  TORCH_CHECK(!is_conv || (conv.size() == 14 && !mn && !b_kn), "conv = 14 ints, exclusive with mn_m / b_kn");
   const int M = is_conv ? (int)conv[10] : (mn ? (int)mn_m : (int)A.size(0));
   const int N = is_conv ? (int)conv[11] : ((mn || b_kn) ? (int)B.size(1) : (int)B.size(0));
   const int K = is_conv ? (int)conv[12] : (mn ? (int)A.size(0) : (int)A.size(1));
@@ -416,7 +416,7 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
     convops::ConvAddr& g = ep.conv;
     g.mode = (int)conv[0]; g.flip = (int)conv[1]; g.C = (int)conv[2]; g.KH = (int)conv[3]; g.KW = (int)conv[4]; g.pad = (int)conv[5];
     const int H = (int)conv[6], W = (int)conv[7];
-    g.HW = H * W; g.n_images = (int)conv[8]; g.b_rows_per_tap = (int)conv[9];
+    g.HW = H * W; g.n_images = (int)conv[8]; g.b_rows_per_tap = (int)conv[9]; g.b_mn = (int)conv[13];
     TORCH_CHECK(A.numel() == (int64_t)g.n_images * H * W * g.C, "activation must be [n_images*H*W, C]");
     static const int dbg_lbo = std::getenv("COLEARN_UMMA_MN_LBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_LBO")) : 0;
     static const int dbg_sbo = std::getenv("COLEARN_UMMA_MN_SBO") ? std::atoi(std::getenv("COLEARN_UMMA_MN_SBO")) : 0;

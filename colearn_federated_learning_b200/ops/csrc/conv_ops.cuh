@@ -514,6 +514,7 @@ struct ConvAddr {
   int HW;          // H*W of the activation: 1, 4, 16 or 64 (whole images per box)
   int n_images;    // N (a fully padded K/N block is pushed out of bounds with this)
   int b_rows_per_tap;  // mode 1 / flip 1: rows of W^T per tap (= Cin of the convolution = N of the GEMM)
+  int b_mn;        // mode 1 / flip 1: the weight operand is the packed Wp[co, (tap, ci)] itself (MN-major B) instead of W^T
 };
 struct ConvBox {
   int c, w, h, n;  // 4-D TMA coordinates of the activation box

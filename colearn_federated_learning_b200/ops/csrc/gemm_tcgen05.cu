@@ -431,11 +431,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
-          if (CL == 1 && !MN && !BMN && ep.conv.mode == 1) {
+          if (CL == 1 && !MN && ep.conv.mode == 1) {
             // implicit-GEMM convolution, forward / dgrad: the A tile is the activation box of this tap (conv_ops.cuh)
             const convops::ConvBox bx = convops::conv_kblock(ep.conv, kb, m0, n0);
             tma_load_4d(smem_a + stage * kStageBytesA, &tmap_a, bx.c, bx.w, bx.h, bx.n, &bars->full[stage]);
-            tma_load_2d(smem_b + stage * kStageBytesB, &tmap_b, bx.b_col, bx.b_row, &bars->full[stage]);
+            if (BMN) {
+              // dgrad against the packed weights Wp[co, (tap, ci)] themselves (MN-major B): the K index (co) runs over
+              // ROWS, the N index over the columns of this tap — the same two numbers with their roles swapped
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(smem_b + stage * kStageBytesB + j * kMnBoxBytes, &tmap_b, bx.b_row + j * 64, bx.b_col, &bars->full[stage]);
+            } else {
+              tma_load_2d(smem_b + stage * kStageBytesB, &tmap_b, bx.b_col, bx.b_row, &bars->full[stage]);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -890,7 +898,7 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
 
 const char* gemm_tcgen05_last_error() { return g_last_error.c_str(); }
 
-template <int BN, bool WGRAD>
+template <int BN, bool WGRAD, bool BMN = WGRAD>
 cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const void* other, int other_rows, int other_cols,
                           int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
   using C = Cfg<BN>;
@@ -899,8 +907,8 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
   if (WGRAD) {   // A = dz [K pixels, a_cols] MN-major boxes, B = activation boxes of 64 pixels
     if (!make_tmap(other, other_rows, other_cols, 64, &ta) || !make_tmap_4d(act, n_images, H, W, ep.conv.C, 64 / HW, &tb))
       return cudaErrorInvalidValue;
-  } else {       // A = activation boxes of 128 pixels, B = K-major weights [other_rows, other_cols]
-    if (!make_tmap_4d(act, n_images, H, W, ep.conv.C, 128 / HW, &ta) || !make_tmap(other, other_rows, other_cols, BN, &tb))
+  } else {       // A = activation boxes of 128 pixels, B = K-major weights [other_rows, other_cols] (MN-major: 64-row boxes)
+    if (!make_tmap_4d(act, n_images, H, W, ep.conv.C, 128 / HW, &ta) || !make_tmap(other, other_rows, other_cols, BMN ? 64 : BN, &tb))
       return cudaErrorInvalidValue;
   }
   static bool configured[64] = {false};
@@ -908,7 +916,7 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, WGRAD, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem, conv) failed"; return e; }
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
@@ -917,7 +925,7 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
   int units = num_sms[dev & 63];
   if (work < units) units = work;
   if (units < 1) units = 1;
-  gemm_tcgen05_kernel<BN, 1, WGRAD, WGRAD><<<units, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+  gemm_tcgen05_kernel<BN, 1, WGRAD, BMN><<<units, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
   return cudaGetLastError();
 }
 
@@ -940,7 +948,9 @@ cudaError_t launch_gemm_tcgen05_conv(const void* act, int n_images, int H, int W
   if (g.mode == 1) {
     // M = pixels (whole images per 128-row tile), K = taps * C
     if (M != n_images * HW || K != g.KH * g.KW * g.C) { g_last_error = "implicit conv GEMM (A): M = N*H*W, K = KH*KW*C"; return cudaErrorInvalidValue; }
-    if (g.flip ? (other_rows < (g.KH * g.KW - 1) * g.b_rows_per_tap + N || other_cols < g.C || g.b_rows_per_tap <= 0)
+    if (g.b_mn && !g.flip) { g_last_error = "implicit conv GEMM: the MN-major weight operand is the dgrad's"; return cudaErrorInvalidValue; }
+    const int need_n = (g.KH * g.KW - 1) * g.b_rows_per_tap + N;   // dgrad: last tap's block of N weight rows / columns
+    if (g.flip ? (g.b_rows_per_tap <= 0 || (g.b_mn ? (other_cols < need_n || other_rows < g.C) : (other_rows < need_n || other_cols < g.C)))
                : (other_rows < N || other_cols < K)) {
       g_last_error = "implicit conv GEMM (A): weight matrix too small";
       return cudaErrorInvalidValue;
@@ -968,6 +978,11 @@ cudaError_t launch_gemm_tcgen05_conv(const void* act, int n_images, int H, int W
   if (g.mode == 2) {
     if (wide) return launch_conv_t<256, true>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
     return launch_conv_t<128, true>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
+  }
+  if (g.b_mn) {
+    if (wide) return launch_conv_t<256, false, true>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
+    if (N % 128) return launch_conv_t<64, false, true>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
+    return launch_conv_t<128, false, true>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
   }
   if (wide) return launch_conv_t<256, false>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);
   if (N % 128) return launch_conv_t<64, false>(act, n_images, H, W, other, other_rows, other_cols, M, N, K, ep, s);

@@ -82,6 +82,16 @@ def test_producer_addressing_reproduces_the_three_conv_gemms(n, h, w, cin, cout)
                 a = tma_box(dz, c0, w0, h0, ni, 128 // hw)
                 got[m0:m0 + 128, n0_:n0_ + 64] += a @ wT[b_row:b_row + 64, b_col:b_col + 64].t()
     torch.testing.assert_close(got, dx_ref, rtol=1e-9, atol=1e-9)
+    # ... and against the packed weights themselves (MN-major B): the same two numbers with swapped roles — b_col is the
+    # ROW (co) of the [64 co x 64 ci] box, b_row its first COLUMN (tap*cin + n0)
+    got = torch.zeros(m, cin, dtype=torch.float64)
+    for m0 in range(0, m, 128):
+        for n0_ in range(0, cin, 64):
+            for kb in range(9 * cout // 64):
+                c0, w0, h0, ni, b_col, b_row = emul.conv_kblock(geom, kb, m0, n0_)
+                a = tma_box(dz, c0, w0, h0, ni, 128 // hw)
+                got[m0:m0 + 128, n0_:n0_ + 64] += a @ wp[b_col:b_col + 64, b_row:b_row + 64]
+    torch.testing.assert_close(got, dx_ref, rtol=1e-9, atol=1e-9)
 
     # wgrad: reduction over 64-pixel blocks; A = dz [pixels, cout], B = x boxes of 64 pixels per (tap, 64 channels)
     k_pad = (9 * cin + 127) // 128 * 128
@@ -124,6 +134,9 @@ def test_conv_gemm_definitions_match_autograd(n, h, w, cin, cout):
     dx = torch.zeros(m, cin)
     conv.conv_gemm("dgrad", dz, wT, n, h, w, cout, 3, 3, 1, out_bf16=dx, addend=add, rows_per_tap=cin)
     torch.testing.assert_close(dx, xr.grad.permute(0, 2, 3, 1).reshape(m, cin) + add, rtol=1e-4, atol=1e-4)
+    dx2 = torch.zeros(m, cin)
+    conv.conv_gemm("dgrad", dz, wp, n, h, w, cout, 3, 3, 1, out_bf16=dx2, addend=add, rows_per_tap=cin, w_packed=True)
+    torch.testing.assert_close(dx2, dx, rtol=1e-5, atol=1e-5)
     master = wp.clone()
     conv.conv_gemm("wgrad", act, dz, n, h, w, cin, 3, 3, 1, m_pad=cout_pad, k_pad=k_pad, sgd_master=master, sgd_lr=0.5)
     part = torch.zeros(2 * cout_pad * k_pad + 100)                      # a larger shared scratch buffer is fine
@@ -134,7 +147,8 @@ def test_conv_gemm_definitions_match_autograd(n, h, w, cin, cout):
     torch.testing.assert_close(master, want, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("level,extra", [(1, {}), (2, {}), (2, {"split_k": 1, "dgrad_kn": False})])
+@pytest.mark.parametrize("level,extra", [(1, {}), (2, {}), (2, {"split_k": 1, "dgrad_kn": False}),
+                                         (2, {"split_k": 1, "dgrad_kn": True, "wgrad_mn": True})])
 def test_implicit_schedule_is_the_same_step(level, extra):
     """``implicit=1``: forward and dgrad of the stride-1 3x3 convolutions read the activations through 4-D boxes (no
     im2col on the forward path, no dcol / col2im); ``implicit=2``: the wgrad too (no col at all).  Same products as

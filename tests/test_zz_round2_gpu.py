@@ -326,6 +326,22 @@ def test_implicit_conv_forward_and_dgrad(n, h, w, cin, cout):
 
 @unvalidated
 @pytest.mark.parametrize("n,h,w,cin,cout", IMPLICIT_GEOMS)
+def test_implicit_conv_dgrad_packed_weights(n, h, w, cin, cout):
+    """The implicit dgrad against the packed weights themselves (MN-major B operand, no W^T copy)."""
+    dev = _dev()
+    from colearn_federated_learning_b200.ops import conv as C
+    d = _implicit_case(n, h, w, cin, cout)
+    m = d["m"]
+    add = torch.randn(m, cin).to(torch.bfloat16)
+    dx2 = torch.full((m, cin), 7.0, device=dev, dtype=torch.bfloat16)
+    C.conv_gemm("dgrad", d["dz"].to(dev), d["wp"].to(dev), n, h, w, cout, 3, 3, 1, out_bf16=dx2, addend=add.to(dev), rows_per_tap=cin,
+                w_packed=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dx2.float().cpu(), d["dx"] + add.float(), rtol=2e-2, atol=5e-2)
+
+
+@unvalidated
+@pytest.mark.parametrize("n,h,w,cin,cout", IMPLICIT_GEOMS)
 def test_implicit_conv_wgrad(n, h, w, cin, cout):
     dev = _dev()
     from colearn_federated_learning_b200.ops import conv as C
