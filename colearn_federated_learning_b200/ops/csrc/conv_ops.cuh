@@ -495,6 +495,28 @@ CL_HD void pack_body(const PackArgs& a, long long e) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Work decomposition of the persistent tcgen05 GEMM (gemm_tcgen05.cu).  Every role of a CTA (TMA producer, MMA issuer,
+// epilogue warps) walks the same list: work unit w = blockIdx.x, blockIdx.x + gridDim.x, ...;  w / S is the output tile,
+// w % S the K slice (S = split_k, 1 = off).  Host+device so that the CPU test-suite can check that the units tile the
+// output exactly once and that the slices partition K.
+// L2-friendly rasterisation: the tiles are walked in groups of kGroupM m-units x all n-blocks (m fastest inside a group),
+// so that the CTAs running concurrently share a small set of A row-slabs and B column-slabs (an 8192^3 GEMM has 134 MB
+// of A alone; the naive order streams all of it once per n-block).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kGroupM = 8;
+CL_HD void work_to_tile(int w, int m_units, int n_tiles, int& m_unit, int& n_blk) {
+  const int group_size = kGroupM * n_tiles;
+  const int group_id = w / group_size;
+  const int first_m = group_id * kGroupM;
+  const int gsz = (m_units - first_m) < kGroupM ? (m_units - first_m) : kGroupM;
+  const int r = w - group_id * group_size;
+  m_unit = first_m + (r % gsz);
+  n_blk = r / gsz;
+}
+// k-block range of K slice s of S: [split_kb(s), split_kb(s + 1)); non-empty for every s when num_kb >= S
+CL_HD int split_kb(int num_kb, int s, int S) { return (int)(((long long)num_kb * s) / S); }
+
+// ------------------------------------------------------------------------------------------------------
 // Implicit GEMM addressing (stride-1 convolutions on NHWC activations whose images are <= 128 pixels).
 // The activation [N, H, W, C] is described to TMA as a 4-D tensor (c, w, h, n); a GEMM tile of 128 (or 64) pixels is a
 // box of whole images (c: 64, w: W, h: H, n: pixels / (H*W)), and tap (kh, kw) of the filter is the same box moved by

@@ -225,22 +225,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// L2-friendly rasterisation: walk the work units in groups of kGroupM m-units x all n-blocks (m fastest inside a group),
-// so that the CTAs running concurrently share a small set of A row-slabs and B column-slabs (an 8192^3 GEMM has 134 MB
-// of A alone; the naive order streams all of it once per n-block).
-constexpr int kGroupM = 8;
-__device__ __forceinline__ void work_to_tile(int w, int m_units, int n_tiles, int& m_unit, int& n_blk) {
-  const int group_size = kGroupM * n_tiles;
-  const int group_id = w / group_size;
-  const int first_m = group_id * kGroupM;
-  const int gsz = (m_units - first_m) < kGroupM ? (m_units - first_m) : kGroupM;
-  const int r = w - group_id * group_size;
-  m_unit = first_m + (r % gsz);
-  n_blk = r / gsz;
-}
-
-// k-block range of K slice s of S: [split_kb(s), split_kb(s + 1)); non-empty for every s when num_kb >= S
-__host__ __device__ __forceinline__ int split_kb(int num_kb, int s, int S) { return (int)(((long long)num_kb * s) / S); }
+// Work decomposition (tile rasterisation, split-K slices): host+device functions in conv_ops.cuh (GemmSched), shared
+// with the CPU test-suite
+using convops::split_kb;
+using convops::work_to_tile;
 
 struct SharedBarriers {
   uint64_t full[kMaxStages];

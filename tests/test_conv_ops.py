@@ -382,3 +382,24 @@ def test_splitk_reduce_rejects_bad_arguments():
             conv.splitk_reduce(p, 3, 8, out_bf16=torch.zeros(8, dtype=BF))             # part too small
         with pytest.raises(RuntimeError):
             conv.splitk_reduce(p, 2, 8, out_bf16=torch.zeros(4, dtype=BF))             # output too small
+
+
+@pytest.mark.parametrize("m_units,n_tiles,num_kb,split,grid", [(1, 1, 512, 64, 148), (1, 5, 128, 16, 148), (32, 16, 16, 1, 148), (9, 7, 33, 5, 13),
+                                                             (256, 1, 4, 1, 148), (3, 3, 7, 7, 4), (17, 2, 9, 2, 148)])
+def test_gemm_work_decomposition_covers_every_tile_and_partitions_k(m_units, n_tiles, num_kb, split, grid):
+    """The persistent GEMM's work list (the host build of ``work_to_tile`` / ``split_kb``, the functions every warp role
+    of the kernel walks): over all CTAs each (tile, K slice) appears exactly once, the slices of a tile are disjoint,
+    non-empty and cover all k-blocks, and the slices of one tile sit on consecutive CTAs (they run concurrently)."""
+    emul = conv.load_emulator()
+    seen = {}
+    for cta in range(min(grid, m_units * n_tiles * split)):
+        for mu, nb, ks, lo, hi in emul.gemm_work_list(cta, min(grid, m_units * n_tiles * split), m_units, n_tiles, num_kb, split):
+            assert 0 <= mu < m_units and 0 <= nb < n_tiles and 0 <= ks < split and lo < hi
+            assert (mu, nb, ks) not in seen
+            seen[(mu, nb, ks)] = (lo, hi, cta)
+    assert len(seen) == m_units * n_tiles * split
+    for mu in range(m_units):
+        for nb in range(n_tiles):
+            ranges = [seen[(mu, nb, ks)][:2] for ks in range(split)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == num_kb
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(split - 1))
