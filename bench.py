@@ -70,7 +70,8 @@ def parse_args():
 def reference_unavailable() -> None:
     why = ("reference is a flat script tree without setup.py/pyproject (pip: 'not installable') and needs "
            "syft==0.2.x + torch 1.4 + paho-mqtt, none of which are in the offline wheelhouse")
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:     # under torchrun every rank gets here; one JSON line for the job
+        print(json.dumps({"impl": "reference", "unavailable": why}))
 
 
 def make_data(model: str, total: int, rank: int, world: int, seed: int = 0):
