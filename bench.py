@@ -19,6 +19,11 @@ with, every round, the H2D copy of the round's shard from pinned host memory and
 the round's loss, timed by the host clock.  ``--impl reference`` reports that the reference
 cannot be installed offline; ``--impl torch_nccl`` runs the stock-PyTorch + NCCL
 comparator from ``baseline/`` for the same metric/config.
+
+Other ``--config`` values: ``cfg3`` / ``cfg4`` / ``cfg5`` / ``ffnn`` (the remaining BASELINE configs on the GPU engine) and
+four host-clocked end-to-end runs of the reference's own published experiments through the classic control plane, which
+also run on a box without a GPU: ``cfg1`` (VirtualWorker mode), ``paper`` (12 rounds x 1000 it, 2 remote worker
+processes over TCP — paper Table 1), ``fulldata`` (733 672 samples on one remote worker) and ``smpc`` (the encrypted demo).
 """
 from __future__ import annotations
 

@@ -339,7 +339,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
       for (int j = 0; j < 32; ++j) tp[(size_t)(col + j) * M + row] = __float2bfloat16(f[j]);
     }
   }
-      }
+}
 
 // CL = 2: thread-block cluster of two CTAs working on vertically adjacent tiles (same n-block).  Each CTA fetches
 // its own A tile and HALF of the shared B tile, multicasting that half into both CTAs' shared memory, which cuts
