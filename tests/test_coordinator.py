@@ -356,3 +356,47 @@ def test_remote_round_fans_out_to_all_devices_at_once(tmp_path):
     assert len(res["losses"]) == 40 and res["dropped"] == [] and all(w.closed for w in snapshot.values())
     assert dt < 1.5, dt      # 2 rounds x 0.25 s + overhead; behind the default executor (cpu_count + 4 threads): >= 2 s here
     assert len(settings.training_devices) == 0
+
+
+def test_silent_remote_worker_is_dropped_after_the_fit_timeout(tmp_path):
+    """SURVEY §4 fault injection: a device that accepts the fit request and never answers ("edge devices do not fail in
+    the training phases" is an assumption of the paper, p.6; the reference would block forever in ``async_fit``).  With
+    ``--fit-timeout`` the round finishes with the devices that did answer and the silent one is dropped for good."""
+    import socket
+    import threading
+
+    good, pg = _worker(seed=1)
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(4)
+    ps = srv.getsockname()[1]
+    held = []
+
+    def black_hole():
+        while True:
+            try:
+                conn, _ = srv.accept()
+            except OSError:
+                return
+            held.append(conn)                                  # read nothing, answer nothing, keep the socket open
+
+    threading.Thread(target=black_hole, daemon=True).start()
+    try:
+        c, pub, clock = make(tmp_path, remote=True, rounds=2, fit_timeout=0.5)
+        pub.publish(TOPIC, f"(127.0.0.1, {pg}, TRAINING)")
+        pub.publish(TOPIC, f"(127.0.0.1, {ps}, TRAINING)")
+        c.drain()
+        assert len(settings.training_devices) == 2
+        t0 = time.time()
+        clock.advance(1.0)
+        took = time.time() - t0
+        res = c.windower.last_result
+        assert res["dropped"] == [f"127.0.0.1:{ps}"] and list(res["losses"]) == [f"127.0.0.1:{pg}"]
+        assert good.fits_served == 2                           # the second round ran with the surviving device only
+        assert 0.4 < took < 5.0                                # one timeout, not one per round
+        assert os.path.exists(c.path) and len(settings.training_devices) == 0
+    finally:
+        good.stop()
+        srv.close()
+        for s in held:
+            s.close()
