@@ -69,6 +69,7 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--filter-file", type=str, default=None)
     parser.add_argument("--metrics", type=str, default=None, help="write per-round JSONL here")
     parser.add_argument("--round-log", type=str, default=None, help="write the reference-format round log here")
+    parser.add_argument("--metrics-port", type=int, default=0, help="serve Prometheus metrics (rounds, round time, losses, traffic) on this port")
     parser.add_argument("--evaluate", action="store_true", help="evaluate the global model on --test-path after training")
     parser.add_argument("--embedded-broker", action="store_true", help="start the TCP bus broker inside this process")
     parser.add_argument("--tls-ca", default=None, help="CA bundle: verify the broker / the devices (and, with --tls-cert on the embedded broker, demand client certificates)")
@@ -120,11 +121,16 @@ def main(args: argparse.Namespace) -> None:
         for spec in args.inject:
             broker.broker.inject_from_spec(spec)
             logging.info("fault injection active: %s", spec)
+    exporter = None
+    if args.metrics_port:
+        from colearn_federated_learning_b200.utils.metrics import PrometheusExporter
+        exporter = PrometheusExporter(args.metrics_port)
+        logging.info("Prometheus metrics on http://127.0.0.1:%d/metrics", exporter.port)
     coordinator = Coordinator(args.window, args.remote, args.federated_round, args.encryption, args.iot,
                               args=arguments_from_cli(args), transport="tcp", path=args.checkpoint,
                               strict_events=args.strict_events, select_k=args.select, selection=args.selection,
                               fit_timeout=args.fit_timeout, filter_file=args.filter_file,
-                              metrics=RoundLogger(args.metrics, args.round_log), evaluate_after=args.evaluate,
+                              metrics=RoundLogger(args.metrics, args.round_log, exporter=exporter), evaluate_after=args.evaluate,
                               worker_ssl_context=client_tls)
     if client_tls is not None:
         coordinator.tls_set(context=client_tls)

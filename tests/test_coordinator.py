@@ -400,3 +400,30 @@ def test_silent_remote_worker_is_dropped_after_the_fit_timeout(tmp_path):
         srv.close()
         for s in held:
             s.close()
+
+
+def test_prometheus_exporter_serves_round_metrics(tmp_path):
+    """``--metrics-port``: rounds, round time, per-device loss and traffic as Prometheus series."""
+    import urllib.request
+
+    from colearn_federated_learning_b200.utils.metrics import PrometheusExporter, RoundLogger
+
+    w1, p1 = _worker(seed=1)
+    w2, p2 = _worker(seed=2)
+    exp = PrometheusExporter(0)
+    try:
+        c, pub, clock = make(tmp_path, remote=True, rounds=3, metrics=RoundLogger(exporter=exp))
+        pub.publish(TOPIC, f"(127.0.0.1, {p1}, TRAINING)")
+        pub.publish(TOPIC, f"(127.0.0.1, {p2}, TRAINING)")
+        c.drain()
+        clock.advance(1.0)
+        body = urllib.request.urlopen(f"http://127.0.0.1:{exp.port}/metrics", timeout=5).read().decode()
+        series = dict(line.rsplit(" ", 1) for line in body.splitlines() if line and not line.startswith("#"))
+        assert float(series["colearn_rounds_total"]) == 3 and float(series["colearn_trainings_total"]) == 1
+        assert float(series["colearn_round_seconds_count"]) == 3 and float(series["colearn_round_selected_workers"]) == 2
+        assert float(series["colearn_bytes_to_workers_total"]) > 3 * 2 * 9604
+        assert float(series["colearn_bytes_from_workers_total"]) > 3 * 2 * 9604
+        assert f'colearn_worker_last_loss{{worker="127.0.0.1:{p1}"}}' in series
+    finally:
+        exp.close()
+        w1.stop(); w2.stop()
