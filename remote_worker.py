@@ -41,6 +41,11 @@ _OPTIONS = (
                          help="import this module / .py file first: it may call models.register_model / data.register_dataset (repeatable)")),
     (("--no-cuda",), dict(action="store_true", help="serve fits on the CPU even if a GPU is present")),
     (("--no-will",), dict(action="store_true", help="do not register the NOT_READY last-will with the broker")),
+    (("--broker-wait",), dict(type=float, default=30.0, metavar="SECONDS",
+                              help="keep retrying for this long when the broker is not reachable yet (devices often boot before it)")),
+    (("--reannounce",), dict(type=float, default=0.0, metavar="SECONDS",
+                             help="repeat the announcement every SECONDS (the coordinator deregisters a device after each training; "
+                                  "the reference's devices have to publish again by hand). 0 = announce once, like the reference")),
     (("--tls-ca",), dict(default=None, help="CA bundle: verify the broker; with --tls-cert also demand a client certificate from the coordinator")),
     (("--tls-cert",), dict(default=None, help="this device's certificate (RPC server side and client certificate towards the broker)")),
     (("--tls-key",), dict(default=None, help="private key belonging to --tls-cert")),
@@ -98,9 +103,26 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
     if not args.no_will:
         # if this process dies without a DISCONNECT the broker withdraws the device on our behalf
         bus.will_set(args.topic, format_event(args.host, "NOT_READY", args.port))
-    bus.connect(args.broker, args.broker_port)
+    import time
+    deadline = time.monotonic() + max(0.0, args.broker_wait)
+    while True:
+        try:
+            bus.connect(args.broker, args.broker_port)
+            break
+        except OSError as e:                                                      # refused / unreachable: the broker may still be starting
+            if time.monotonic() >= deadline:
+                raise
+            logging.info("broker %s:%d not reachable yet (%r), retrying", args.broker, args.broker_port, e)
+            time.sleep(0.5)
     announcement = format_event(args.host, args.event, args.port)
-    delayed = Timer(args.wait, bus.publish, args=(args.topic, announcement))     # rw.py:110-114
+    def announce() -> None:
+        bus.publish(args.topic, announcement)
+        if args.reannounce > 0:                                                   # stay available for the next windows
+            again = Timer(args.reannounce, announce)
+            again.daemon = True
+            again.start()
+
+    delayed = Timer(args.wait, announce)                                          # rw.py:110-114
     delayed.daemon = True
     delayed.start()
     try:

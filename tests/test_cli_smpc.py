@@ -327,3 +327,27 @@ def test_plugin_registers_model_and_dataset_for_both_clis(tmp_path):
                                                   "-dt", str(csv_path)])
     ds = remote_worker.pick_dataset(ns)
     assert len(ds) == 200 and ds.data.shape[1] == 2
+
+
+def test_worker_reannounce_joins_consecutive_trainings(tmp_path):
+    """``remote_worker.py --reannounce S``: the coordinator deregisters a device after each training (fc.py:386-392), so
+    a device that announces once only ever takes part in one; with ``--reannounce`` it is back for the next window.  Two
+    trainings complete with one long-running worker process and nobody publishing by hand."""
+    bport, wport = _free_port(), _free_port()
+    ckpt = str(tmp_path / "test.pth")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    coord = subprocess.Popen([sys.executable, os.path.join(ROOT, "federated_coordinator.py"), "-t", "topic/state", "-r", "-w", "1",
+                              "-p", str(bport), "--host", "127.0.0.1", "--embedded-broker", "--exit-after", "2", "--no-cuda",
+                              "--checkpoint", ckpt], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    worker = subprocess.Popen([sys.executable, os.path.join(ROOT, "remote_worker.py"), "--host", "127.0.0.1", "-p", str(wport), "-b", "127.0.0.1",
+                               "--broker-port", str(bport), "-t", "topic/state", "-w", "3", "--reannounce", "1.5", "--synthetic", "64",
+                               "--no-cuda"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    try:
+        out, _ = coord.communicate(timeout=120)
+    finally:
+        worker.terminate()
+        worker.wait(timeout=10)
+        if coord.poll() is None:
+            coord.kill()
+    assert coord.returncode == 0, out[-3000:]
+    assert out.count("Total training time") == 2 and os.path.exists(ckpt)
