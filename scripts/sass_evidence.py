@@ -11,7 +11,6 @@ import glob
 import os
 import re
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sorted(glob.glob(os.path.join(ROOT, "colearn_federated_learning_b200", "ops", "_colearn_C*.so")))[0]
