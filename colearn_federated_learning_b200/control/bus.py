@@ -26,7 +26,7 @@ import socketserver
 import threading
 import time
 from dataclasses import dataclass, field
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 from . import mqtt
 
@@ -423,6 +423,14 @@ class BusClient:
         # loop_start()/loop_forever() survive a raising callback (logged); drain()/loop() called directly from
         # tests re-raise unless this is set
         self.suppress_callback_errors = False
+        # TCP transport: after an UNEXPECTED disconnect (broker restart, network blip) reconnect with exponential
+        # back-off and restore the subscriptions — what paho's loop_forever() gives the reference for free.
+        # reconnect_delay_set(0, 0) switches it off.
+        self._reconnect_min, self._reconnect_max = 1.0, 30.0
+        self._subscriptions: Dict[str, int] = {}
+        self._addr: Optional[Tuple[str, int, int]] = None
+        self._reconnector: Optional[threading.Thread] = None
+        self.reconnects = 0
 
     # Default callbacks (paho signatures) — overridable --------------------------------
     def on_connect(self, client, userdata, flags, rc) -> None:  # noqa: D401
@@ -451,6 +459,10 @@ class BusClient:
         from .tls import client_context
         self._ssl_context = context or client_context(ca_certs, certfile, keyfile, check_hostname=check_hostname)
 
+    def reconnect_delay_set(self, min_delay: float = 1.0, max_delay: float = 30.0) -> None:
+        """paho's ``reconnect_delay_set``; ``(0, 0)`` disables the automatic reconnect of the TCP transport."""
+        self._reconnect_min, self._reconnect_max = float(min_delay), float(max_delay)
+
     def username_pw_set(self, username: Optional[str], password: Optional[str] = None) -> None:
         self._username = username
         self._password = password.encode("utf-8") if isinstance(password, str) else password
@@ -475,6 +487,7 @@ class BusClient:
                 raise ConnectionRefusedError(f"MQTT broker refused the connection (return code {rc})")
             sock.settimeout(None)
             self._sock, self._rfile, self._keepalive = sock, rfile, keepalive
+            self._addr = (host, port, keepalive)
             self._closing.clear()
             self._reader = threading.Thread(target=self._tcp_reader, name="bus-reader", daemon=True)
             self._reader.start()
@@ -523,6 +536,36 @@ class BusClient:
                 self.on_disconnect(self, None, rc)
             except Exception:  # noqa: BLE001
                 log.exception("on_disconnect raised")
+            if rc != 0 and self._reconnect_max > 0 and self._addr is not None:
+                self._reconnector = threading.Thread(target=self._reconnect_loop, name="bus-reconnect", daemon=True)
+                self._reconnector.start()
+
+    def _reconnect_loop(self) -> None:
+        delay = max(0.05, self._reconnect_min)
+        host, port, keepalive = self._addr  # type: ignore[misc]
+        while not self._closing.is_set():
+            if self._closing.wait(delay):
+                return
+            try:
+                old = self._sock
+                if old is not None:
+                    try:
+                        old.close()
+                    except OSError:
+                        pass
+                self.connect(host, port, keepalive)
+            except OSError as e:
+                log.info("bus reconnect to %s:%d failed (%r); next attempt in %.1f s", host, port, e, min(delay * 2, self._reconnect_max))
+                delay = min(delay * 2, self._reconnect_max)
+                continue
+            self.reconnects += 1
+            for topic, qos in list(self._subscriptions.items()):
+                try:
+                    self.subscribe(topic, qos)
+                except OSError:
+                    break                                   # dropped again: the new reader thread schedules the next attempt
+            log.info("bus reconnected to %s:%d (%d subscription(s) restored)", host, port, len(self._subscriptions))
+            return
 
     def _ping_loop(self) -> None:
         period = max(0.05, self._keepalive / 2.0)
@@ -558,6 +601,7 @@ class BusClient:
 
     def subscribe(self, topic: str, qos: int = 0):
         if self._transport == "tcp":
+            self._subscriptions[topic] = qos          # restored after an automatic reconnect
             pid = self._next_pid()
             self._send(mqtt.subscribe(pid, [(topic, qos)]))
             self.wait_for_ack(mqtt.SUBACK, pid)       # like mosquitto_sub: return once the subscription is live
@@ -568,6 +612,7 @@ class BusClient:
 
     def unsubscribe(self, topic: str):
         if self._transport == "tcp":
+            self._subscriptions.pop(topic, None)
             pid = self._next_pid()
             self._send(mqtt.unsubscribe(pid, [topic]))
             self.wait_for_ack(mqtt.UNSUBACK, pid)

@@ -204,3 +204,56 @@ def test_in_process_bus_has_the_same_retained_and_unsubscribe_semantics():
     c.unsubscribe("cfg/+")
     b.publish("cfg/x", b"3")
     assert c.drain() == 0
+
+
+def test_client_reconnects_after_a_broker_restart_and_restores_subscriptions():
+    """paho's loop_forever() reconnects after a broker outage; so does the TCP bus client: exponential back-off, then the
+    subscriptions are restored and messages flow again.  A deliberate disconnect() does not reconnect."""
+    import time
+
+    from colearn_federated_learning_b200.control.bus import BusClient, TcpBroker
+
+    broker = TcpBroker("127.0.0.1", 0).start()
+    port = broker.port
+    got = []
+    sub = BusClient("sub", transport="tcp")
+    sub.reconnect_delay_set(0.1, 0.5)
+    sub.on_message = lambda c, u, m: got.append(m.payload)
+    down = []
+    sub.on_disconnect = lambda c, u, rc: down.append(rc)
+    sub.connect("127.0.0.1", port)
+    sub.subscribe("topic/state")
+    sub.loop_start()
+    pub = BusClient("pub", transport="tcp")
+    pub.connect("127.0.0.1", port)
+    pub.publish("topic/state", "one")
+    deadline = time.time() + 5
+    while not got and time.time() < deadline:
+        time.sleep(0.01)
+    assert got == [b"one"]
+    pub.disconnect()
+    broker.stop()                                            # outage: the subscriber loses its connection
+    deadline = time.time() + 5
+    while not down and time.time() < deadline:
+        time.sleep(0.01)
+    assert down and down[0] != 0
+    time.sleep(0.4)                                          # a few failed attempts while nothing listens
+    broker2 = TcpBroker("127.0.0.1", port).start()
+    try:
+        deadline = time.time() + 10
+        while sub.reconnects == 0 and time.time() < deadline:
+            time.sleep(0.02)
+        assert sub.reconnects == 1
+        pub2 = BusClient("pub2", transport="tcp")
+        pub2.connect("127.0.0.1", port)
+        deadline = time.time() + 5
+        while len(got) < 2 and time.time() < deadline:
+            pub2.publish("topic/state", "two")               # the restored subscription delivers again
+            time.sleep(0.05)
+        assert got[-1] == b"two"
+        sub.disconnect()                                     # deliberate: rc 0, no reconnect
+        time.sleep(0.3)
+        assert sub.reconnects == 1 and down[-1] == 0
+        pub2.disconnect()
+    finally:
+        broker2.stop()
