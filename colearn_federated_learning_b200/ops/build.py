@@ -22,6 +22,7 @@ OBJ = os.path.join(CSRC, "_obj")
 EXT_NAME = "_colearn_C"
 EMUL_NAME = "_colearn_emul"     # CPU emulator of the conv kernels (tests on boxes without a GPU)
 HOST_NAME = "_colearn_host"     # native CPU executor of the MLP local fit (devices / boxes without a GPU)
+SIMT_NAME = "_colearn_simt"     # the persistent-MLP CUDA kernels compiled for the CPU through csrc/host_shim.h (tests)
 
 CU_SOURCES = ["mlp_persistent.cu", "elementwise.cu", "comm.cu", "gemm_tcgen05.cu", "convnet.cu"]
 CPP_SOURCES = ["bindings.cpp"]
@@ -128,6 +129,40 @@ def build_host(force: bool = False) -> str:
     return out
 
 
+def simt_path() -> str:
+    suffix = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+    return os.path.join(HERE, SIMT_NAME + suffix)
+
+
+def build_simt_emul(force: bool = False) -> str:
+    """g++ build of ``csrc/simt_emul.cpp``: ``mlp_persistent.cu`` + ``mlp_v2.inc`` — the kernel sources themselves —
+    compiled for the CPU with one OS thread per CUDA thread (``csrc/host_shim.h``).  Needs C++20 (``std::barrier``) and
+    the CUDA headers, no GPU and no CUDA libraries."""
+    ce, cuda_home, inc, flags = _cxx_setup()
+    os.makedirs(OBJ, exist_ok=True)
+    out = simt_path()
+    src = os.path.join(CSRC, "simt_emul.cpp")
+    cxx_flags = [f for f in flags if f not in ("-O2", "-std=c++17")] + ["-O1", "-std=c++20", "-pthread", "-Wno-unknown-pragmas",
+                                                                        f"-DTORCH_EXTENSION_NAME={SIMT_NAME}"]
+    h = hashlib.sha1()
+    for dep in ("simt_emul.cpp", "host_shim.h", "mlp_persistent.cu", "mlp_v2.inc", "colearn_kernels.h", "conv_ops.cuh"):
+        with open(os.path.join(CSRC, dep), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(cxx_flags).encode())
+    obj = os.path.join(OBJ, f"simt_emul.cpp.{h.hexdigest()[:16]}.o")
+    if force or not os.path.exists(obj) or not os.path.exists(out):
+        for name in os.listdir(OBJ):
+            if name.startswith("simt_emul.cpp.") and name.endswith(".o"):
+                os.remove(os.path.join(OBJ, name))
+        _run(["g++", *cxx_flags, *inc, "-c", src, "-o", obj], "simt_emul.cpp")
+        link = ["g++", "-shared", obj, "-o", out, "-pthread"]
+        for d in ce.library_paths(device_type="cpu"):
+            link += [f"-L{d}", f"-Wl,-rpath,{d}"]
+        link += ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python"]
+        _run(link, "link_simt")
+    return out
+
+
 def build_all(force: bool = False, verbose: bool = True) -> str:
     ce, cuda_home, inc, base_cxx = _cxx_setup()
 
@@ -169,7 +204,7 @@ def build_all(force: bool = False, verbose: bool = True) -> str:
     # drop stale cached objects (every source edit leaves one behind)
     keep = {os.path.basename(o) for o in objs}
     for name in os.listdir(OBJ):
-        if name.endswith(".o") and name not in keep and not name.startswith(("conv_emul.cpp.", "mlp_host.cpp.")):
+        if name.endswith(".o") and name not in keep and not name.startswith(("conv_emul.cpp.", "mlp_host.cpp.", "simt_emul.cpp.")):
             os.remove(os.path.join(OBJ, name))
     build_host(force=force)      # the CPU executor ships with every build (CPU-only boxes: `--host` builds it alone)
     return out
@@ -181,7 +216,9 @@ def main(argv=None) -> int:
     ``--host`` builds only the CPU executor (no nvcc needed: edge devices), ``--emul`` only the conv-kernel emulator."""
     argv = sys.argv[1:] if argv is None else argv
     force = "--force" in argv
-    if "--emul" in argv:
+    if "--simt" in argv:
+        print(build_simt_emul(force=force))
+    elif "--emul" in argv:
         print(build_emul(force=force))
     elif "--host" in argv:
         print(build_host(force=force))

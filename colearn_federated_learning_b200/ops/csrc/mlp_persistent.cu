@@ -83,6 +83,10 @@ template <class N> struct Totals {
 };
 
 // ---- memory-model helpers ----------------------------------------------------------------------
+#ifdef COLEARN_HOST_SHIM
+inline uint32_t ld_acquire_sys(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -91,6 +95,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+#endif
 
 // ---- per-layer device functions ----------------------------------------------------------------
 template <class N, int LI, bool RELU>
@@ -268,7 +273,7 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
   using Tot = Totals<N>;
   constexpr int SP = Tot::smem_params;
   constexpr int DIN = N::DIN, DOUT = N::DOUT, ROWM = Tot::ROW_MAX, EPT = Tot::EPT;
-  extern __shared__ __align__(16) float smem[];
+  COLEARN_DYN_SMEM(float, smem);
 
   const ClientDesc d = descs[blockIdx.x];
   const int tid = threadIdx.x;
@@ -439,7 +444,7 @@ mlp_forward_kernel(const float* __restrict__ theta, const float* __restrict__ x,
   using Tot = Totals<N>;
   constexpr int SP = Tot::smem_params;
   constexpr int L = N::L, DIN = N::DIN, DOUT = N::DOUT;
-  extern __shared__ __align__(16) float smem[];
+  COLEARN_DYN_SMEM(float, smem);
   float* sP = smem;
   float* sX = sP + SP;
   float* sAct = sX + DIN;
@@ -481,7 +486,7 @@ cudaError_t launch_t(const ClientDesc* descs, int n_clients, SgdHyper hp, cudaSt
     if (e != cudaSuccess) return e;
     configured[dev & 63] = bytes;
   }
-  mlp_local_sgd_kernel<N><<<n_clients, NT, bytes, stream>>>(descs, hp);
+  COLEARN_LAUNCH(mlp_local_sgd_kernel<N>, n_clients, NT, bytes, stream, descs, hp);
   return cudaGetLastError();
 }
 
@@ -499,7 +504,7 @@ cudaError_t forward_t(const float* theta, const float* x, float* out, int n, cud
   }
   int blocks = n < 148 * 2 ? n : 148 * 2;
   if (blocks < 1) blocks = 1;
-  mlp_forward_kernel<N><<<blocks, NT, bytes, stream>>>(theta, x, out, n);
+  COLEARN_LAUNCH(mlp_forward_kernel<N>, blocks, NT, bytes, stream, theta, x, out, n);
   return cudaGetLastError();
 }
 
