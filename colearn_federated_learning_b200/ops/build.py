@@ -144,18 +144,21 @@ def build_simt_emul(force: bool = False) -> str:
     src = os.path.join(CSRC, "simt_emul.cpp")
     cxx_flags = [f for f in flags if f not in ("-O2", "-std=c++17")] + ["-O1", "-std=c++20", "-pthread", "-Wno-unknown-pragmas",
                                                                         f"-DTORCH_EXTENSION_NAME={SIMT_NAME}"]
+    sources = ["simt_emul.cpp", "simt_mlp.cpp", "simt_elementwise.cpp", "simt_comm.cpp"]
     h = hashlib.sha1()
-    for dep in ("simt_emul.cpp", "host_shim.h", "mlp_persistent.cu", "mlp_v2.inc", "colearn_kernels.h", "conv_ops.cuh"):
+    for dep in sources + ["host_shim.h", "mlp_persistent.cu", "mlp_v2.inc", "elementwise.cu", "comm.cu", "colearn_kernels.h", "conv_ops.cuh"]:
         with open(os.path.join(CSRC, dep), "rb") as f:
             h.update(f.read())
     h.update(" ".join(cxx_flags).encode())
-    obj = os.path.join(OBJ, f"simt_emul.cpp.{h.hexdigest()[:16]}.o")
-    if force or not os.path.exists(obj) or not os.path.exists(out):
+    stamp = h.hexdigest()[:16]
+    objs = [os.path.join(OBJ, f"{src}.{stamp}.simt.o") for src in sources]
+    if force or not all(os.path.exists(o) for o in objs) or not os.path.exists(out):
         for name in os.listdir(OBJ):
-            if name.startswith("simt_emul.cpp.") and name.endswith(".o"):
+            if name.endswith(".simt.o"):
                 os.remove(os.path.join(OBJ, name))
-        _run(["g++", *cxx_flags, *inc, "-c", src, "-o", obj], "simt_emul.cpp")
-        link = ["g++", "-shared", obj, "-o", out, "-pthread"]
+        with ThreadPoolExecutor(max_workers=4) as pool:
+            list(pool.map(lambda so: _run(["g++", *cxx_flags, *inc, "-c", os.path.join(CSRC, so[0]), "-o", so[1]], so[0]), zip(sources, objs)))
+        link = ["g++", "-shared", *objs, "-o", out, "-pthread"]
         for d in ce.library_paths(device_type="cpu"):
             link += [f"-L{d}", f"-Wl,-rpath,{d}"]
         link += ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python"]
@@ -204,7 +207,7 @@ def build_all(force: bool = False, verbose: bool = True) -> str:
     # drop stale cached objects (every source edit leaves one behind)
     keep = {os.path.basename(o) for o in objs}
     for name in os.listdir(OBJ):
-        if name.endswith(".o") and name not in keep and not name.startswith(("conv_emul.cpp.", "mlp_host.cpp.", "simt_emul.cpp.")):
+        if name.endswith(".o") and name not in keep and not name.startswith(("conv_emul.cpp.", "mlp_host.cpp.")) and not name.endswith(".simt.o"):
             os.remove(os.path.join(OBJ, name))
     build_host(force=force)      # the CPU executor ships with every build (CPU-only boxes: `--host` builds it alone)
     return out

@@ -23,10 +23,31 @@
 #include "colearn_kernels.h"
 
 #include <cuda_bf16.h>
+#ifdef COLEARN_HOST_SHIM
+#include <stdlib.h>
+
+#include <chrono>
+#endif
 
 namespace colearn {
 namespace {
 
+#ifdef COLEARN_HOST_SHIM
+// CPU build (csrc/host_shim.h, tests): "peer" pointers are ordinary host pointers of the emulated ranks; the NVLS
+// multimem forms have no host equivalent (the tests drive the P2P paths), release/acquire map to __atomic builtins
+inline uint32_t ld_acquire_sys(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline float4 ld_peer_f4(const float4* p) { return *p; }
+inline void st_peer_f4(float4* p, const float4& v) { *p = v; }
+inline void multimem_st_f4(float4*, const float4&) { abort(); }
+inline float4 multimem_ld_reduce_f4(const float4*) { abort(); }
+inline void multimem_st_b64(uint2*, const uint2&) { abort(); }
+inline unsigned long long shim_globaltimer() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline uint32_t ld_acquire_gpu(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_gpu(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -58,6 +79,20 @@ __device__ __forceinline__ float4 multimem_ld_reduce_f4(const float4* p) {
 __device__ __forceinline__ void multimem_st_b64(uint2* p, const uint2& v) {
   asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
 }
+__device__ __forceinline__ unsigned long long shim_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#endif
 __device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   uint2 r;
@@ -86,12 +121,12 @@ star_round_kernel(StarRoundArgs a) {
         if (tid == 0) s_mask = 0u;
         __syncthreads();
         if (tid < a.world && ((mask >> tid) & 1u)) {
-          unsigned long long t0, t1;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          const unsigned long long t0 = shim_globaltimer();
+          unsigned long long t1;
           bool ok = false;
           do {
             ok = ld_acquire_sys(a.arrive_flags + tid) >= a.arrive_epoch;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            t1 = shim_globaltimer();
           } while (!ok && (t1 - t0) < a.timeout_ns);
           if (ok) atomicOr(&s_mask, 1u << tid);
         }
@@ -99,12 +134,12 @@ star_round_kernel(StarRoundArgs a) {
         if (tid == 0) {
           a.decision[1] = s_mask;
           __threadfence();
-          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.decision), "r"(a.arrive_epoch) : "memory");
+          st_release_gpu(a.decision, a.arrive_epoch);
         }
       } else {
         if (tid == 0) {
           uint32_t v;
-          do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.decision) : "memory"); } while (v < a.arrive_epoch);
+          do { v = ld_acquire_gpu(a.decision); } while (v < a.arrive_epoch);
           s_mask = a.decision[1];
         }
       }
@@ -390,20 +425,20 @@ p2p_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t 
 cudaError_t launch_star_round(const StarRoundArgs& a, int n_blocks, cudaStream_t s) {
   if (a.world > 16) return cudaErrorInvalidValue;
   if (n_blocks < 1) n_blocks = 1;
-  star_round_kernel<<<n_blocks, 256, 0, s>>>(a);
+  COLEARN_LAUNCH(star_round_kernel, n_blocks, 256, 0, s, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s) {
   if (a.world > 8 || (a.n & 3) || (a.chunk_elems & 3)) return cudaErrorInvalidValue;
   if (n_blocks < 1) n_blocks = 1;
-  twoshot_fedavg_kernel<<<n_blocks, 512, 0, s>>>(a);
+  COLEARN_LAUNCH(twoshot_fedavg_kernel, n_blocks, 512, 0, s, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_signal_peers(const PeerFlags& flags, int world, uint32_t value, cudaStream_t s) {
   if (world > 16) return cudaErrorInvalidValue;
-  signal_peers_kernel<<<1, 32, 0, s>>>(flags, world, value);
+  COLEARN_LAUNCH(signal_peers_kernel, 1, 32, 0, s, flags, world, value);
   return cudaGetLastError();
 }
 
@@ -411,35 +446,39 @@ cudaError_t launch_reduce_push(const float* slots, int k, int64_t stride, int64_
                                float* loss_dst, uint32_t* flag, uint32_t value, uint32_t* counter, int n_blocks,
                                cudaStream_t s) {
   if (n_blocks < 1) n_blocks = 1;
-  reduce_push_kernel<<<n_blocks, 256, 0, s>>>(slots, k, stride, n, dst, losses, loss_dst, flag, value, counter);
+  COLEARN_LAUNCH(reduce_push_kernel, n_blocks, 256, 0, s, slots, k, stride, n, dst, losses, loss_dst, flag, value, counter);
   return cudaGetLastError();
 }
 cudaError_t launch_set_flag(uint32_t* flag, uint32_t value, cudaStream_t s) {
-  set_flag_kernel<<<1, 1, 0, s>>>(flag, value);
+  COLEARN_LAUNCH(set_flag_kernel, 1, 1, 0, s, flag, value);
   return cudaGetLastError();
 }
 cudaError_t launch_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t s) {
-  wait_flag_kernel<<<1, 1, 0, s>>>(flag, value);
+  COLEARN_LAUNCH(wait_flag_kernel, 1, 1, 0, s, flag, value);
   return cudaGetLastError();
 }
 cudaError_t launch_wait_flags(const uint32_t* flags, int count, uint32_t value, cudaStream_t s) {
-  wait_flags_kernel<<<1, 128, 0, s>>>(flags, count, value);
+  COLEARN_LAUNCH(wait_flags_kernel, 1, 128, 0, s, flags, count, value);
   return cudaGetLastError();
 }
 cudaError_t launch_wait_flags_dev(const uint32_t* flags, int count, const uint32_t* value_ptr, cudaStream_t s) {
-  wait_flags_dev_kernel<<<1, 128, 0, s>>>(flags, count, value_ptr);
+  COLEARN_LAUNCH(wait_flags_dev_kernel, 1, 128, 0, s, flags, count, value_ptr);
   return cudaGetLastError();
 }
 cudaError_t launch_p2p_copy(float* dst, const float* src, int64_t n, uint32_t* flag, uint32_t flag_value,
                             int n_blocks, cudaStream_t s) {
   static uint32_t* counter = nullptr;
   if (flag != nullptr && counter == nullptr) {
+#ifdef COLEARN_HOST_SHIM
+    counter = new uint32_t(0);
+#else
     cudaError_t e = cudaMalloc(&counter, sizeof(uint32_t));
     if (e != cudaSuccess) return e;
     cudaMemset(counter, 0, sizeof(uint32_t));
+#endif
   }
   if (n_blocks < 1) n_blocks = 1;
-  p2p_copy_kernel<<<n_blocks, 512, 0, s>>>(dst, src, n, flag, flag_value, counter);
+  COLEARN_LAUNCH(p2p_copy_kernel, n_blocks, 512, 0, s, dst, src, n, flag, flag_value, counter);
   return cudaGetLastError();
 }
 

@@ -358,35 +358,35 @@ __global__ void l2_flush_kernel(float* __restrict__ buf, int64_t n) {
 }  // namespace
 
 cudaError_t launch_sgd_step(float* p, const float* g, float lr, int64_t n, cudaStream_t s) {
-  sgd_step_kernel<<<grid_for(n), kThreads, 0, s>>>(p, g, lr, n);
+  COLEARN_LAUNCH(sgd_step_kernel, grid_for(n), kThreads, 0, s, p, g, lr, n);
   return cudaGetLastError();
 }
 cudaError_t launch_sgd_step_bf16grad(float* p, const void* g, float lr, int64_t n, cudaStream_t s) {
-  sgd_step_bf16grad_kernel<<<grid_for(n), kThreads, 0, s>>>(p, reinterpret_cast<const __nv_bfloat16*>(g), lr, n);
+  COLEARN_LAUNCH(sgd_step_bf16grad_kernel, grid_for(n), kThreads, 0, s, p, reinterpret_cast<const __nv_bfloat16*>(g), lr, n);
   return cudaGetLastError();
 }
 cudaError_t launch_fedavg_apply(float* theta, const float* slots, int64_t slot_stride, const float* weights,
                                 int k, float server_lr, int64_t n, cudaStream_t s) {
   if (k > 64) return cudaErrorInvalidValue;
-  fedavg_kernel<true><<<grid_for(n), kThreads, 0, s>>>(theta, slots, slot_stride, weights, k, server_lr, n);
+  COLEARN_LAUNCH(fedavg_kernel<true>, grid_for(n), kThreads, 0, s, theta, slots, slot_stride, weights, k, server_lr, n);
   return cudaGetLastError();
 }
 cudaError_t launch_fedavg_flat(float* out, const float* slots, int64_t slot_stride, const float* weights,
                                int k, int64_t n, cudaStream_t s) {
   if (k > 64) return cudaErrorInvalidValue;
-  fedavg_kernel<false><<<grid_for(n), kThreads, 0, s>>>(out, slots, slot_stride, weights, k, 1.f, n);
+  COLEARN_LAUNCH(fedavg_kernel<false>, grid_for(n), kThreads, 0, s, out, slots, slot_stride, weights, k, 1.f, n);
   return cudaGetLastError();
 }
 cudaError_t launch_sigmoid_bce(const float* z, const float* y, float* dz, float* loss_out, int64_t n, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(loss_out, 0, sizeof(float), s);
   if (e != cudaSuccess) return e;
-  sigmoid_bce_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(z, y, dz, loss_out, n);
+  COLEARN_LAUNCH(sigmoid_bce_kernel, grid_for(n, 1), kThreads, 0, s, z, y, dz, loss_out, n);
   return cudaGetLastError();
 }
 cudaError_t launch_sse(const float* out, const float* y, float* dz, float* loss_out, int64_t n, float scale, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(loss_out, 0, sizeof(float), s);
   if (e != cudaSuccess) return e;
-  sse_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(out, y, dz, loss_out, n, scale);
+  COLEARN_LAUNCH(sse_kernel, grid_for(n, 1), kThreads, 0, s, out, y, dz, loss_out, n, scale);
   return cudaGetLastError();
 }
 cudaError_t launch_softmax_xent(const void* logits, int is_bf16, const int64_t* labels, float* dl, void* dl_bf16,
@@ -398,9 +398,9 @@ cudaError_t launch_softmax_xent(const void* logits, int is_bf16, const int64_t* 
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   if (is_bf16)
-    softmax_xent_kernel<true><<<blocks, kThreads, 0, s>>>(logits, labels, dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16), loss_out, rows, cols);
+    COLEARN_LAUNCH(softmax_xent_kernel<true>, blocks, kThreads, 0, s, logits, labels, dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16), loss_out, rows, cols);
   else
-    softmax_xent_kernel<false><<<blocks, kThreads, 0, s>>>(logits, labels, dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16), loss_out, rows, cols);
+    COLEARN_LAUNCH(softmax_xent_kernel<false>, blocks, kThreads, 0, s, logits, labels, dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16), loss_out, rows, cols);
   return cudaGetLastError();
 }
 cudaError_t launch_eval_binary(const float* p, const float* y, float* loss_sum, int* correct, int64_t n, cudaStream_t s) {
@@ -408,7 +408,7 @@ cudaError_t launch_eval_binary(const float* p, const float* y, float* loss_sum, 
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(correct, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  eval_binary_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(p, y, loss_sum, correct, n);
+  COLEARN_LAUNCH(eval_binary_kernel, grid_for(n, 1), kThreads, 0, s, p, y, loss_sum, correct, n);
   return cudaGetLastError();
 }
 cudaError_t launch_argmax_rows(const float* x, int64_t* out, int rows, int cols, cudaStream_t s) {
@@ -416,47 +416,47 @@ cudaError_t launch_argmax_rows(const float* x, int64_t* out, int rows, int cols,
   int blocks = (rows + wpb - 1) / wpb;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  argmax_rows_kernel<<<blocks, kThreads, 0, s>>>(x, out, rows, cols);
+  COLEARN_LAUNCH(argmax_rows_kernel, blocks, kThreads, 0, s, x, out, rows, cols);
   return cudaGetLastError();
 }
 cudaError_t launch_minmax_scale(const float* x, float* out, int rows, int cols, cudaStream_t s) {
-  minmax_scale_kernel<<<cols, 1024, 0, s>>>(x, out, rows, cols);
+  COLEARN_LAUNCH(minmax_scale_kernel, cols, 1024, 0, s, x, out, rows, cols);
   return cudaGetLastError();
 }
 cudaError_t launch_feistel_permutation(int* out, int n, int rows, uint64_t seed, cudaStream_t s) {
-  feistel_perm_kernel<<<grid_for((int64_t)n * rows, 1), kThreads, 0, s>>>(out, n, rows, seed);
+  COLEARN_LAUNCH(feistel_perm_kernel, grid_for((int64_t)n * rows, 1), kThreads, 0, s, out, n, rows, seed);
   return cudaGetLastError();
 }
 cudaError_t launch_fp32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t s) {
-  fp32_to_bf16_kernel<<<grid_for(n), kThreads, 0, s>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  COLEARN_LAUNCH(fp32_to_bf16_kernel, grid_for(n), kThreads, 0, s, in, reinterpret_cast<__nv_bfloat16*>(out), n);
   return cudaGetLastError();
 }
 cudaError_t launch_transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t s) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), rows, cols);
+  COLEARN_LAUNCH(transpose_bf16_kernel, grid, block, 0, s, reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), rows, cols);
   return cudaGetLastError();
 }
 cudaError_t launch_fix_precision(const float* x, long long* out, int64_t n, double base, cudaStream_t s) {
-  fix_precision_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(x, out, n, base);
+  COLEARN_LAUNCH(fix_precision_kernel, grid_for(n, 1), kThreads, 0, s, x, out, n, base);
   return cudaGetLastError();
 }
 cudaError_t launch_float_precision(const long long* x, float* out, int64_t n, double inv_base, cudaStream_t s) {
-  float_precision_kernel<<<grid_for(n, 1), kThreads, 0, s>>>(x, out, n, inv_base);
+  COLEARN_LAUNCH(float_precision_kernel, grid_for(n, 1), kThreads, 0, s, x, out, n, inv_base);
   return cudaGetLastError();
 }
 cudaError_t launch_ring_matmul(const long long* A, const long long* B, long long* C, int M, int K, int N, cudaStream_t s) {
   dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
-  ring_matmul_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const unsigned long long*>(A), reinterpret_cast<const unsigned long long*>(B),
-                                            reinterpret_cast<unsigned long long*>(C), M, K, N);
+  COLEARN_LAUNCH(ring_matmul_kernel, grid, block, 0, s, reinterpret_cast<const unsigned long long*>(A),
+                 reinterpret_cast<const unsigned long long*>(B), reinterpret_cast<unsigned long long*>(C), M, K, N);
   return cudaGetLastError();
 }
 cudaError_t launch_bias_sgd_from_partials(float* bias, const float* partials, int rows, int n, int64_t row_stride, float lr,
                                           float* grad_out, int n_bias, cudaStream_t s) {
-  bias_sgd_from_partials_kernel<<<(n + 255) / 256, 256, 0, s>>>(bias, partials, rows, n, row_stride, lr, grad_out, n_bias);
+  COLEARN_LAUNCH(bias_sgd_from_partials_kernel, (n + 255) / 256, 256, 0, s, bias, partials, rows, n, row_stride, lr, grad_out, n_bias);
   return cudaGetLastError();
 }
 cudaError_t launch_l2_flush(float* buf, int64_t n, cudaStream_t s) {
-  l2_flush_kernel<<<148 * 8, kThreads, 0, s>>>(buf, n);
+  COLEARN_LAUNCH(l2_flush_kernel, 148 * 8, kThreads, 0, s, buf, n);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,10 @@ namespace colearn_shim {
 
 struct Dim3 {
   unsigned x = 1, y = 1, z = 1;
+  Dim3() = default;
+  Dim3(unsigned x_, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+  Dim3(const dim3& d) : x(d.x), y(d.y), z(d.z) {}       // NOLINT: launch sites pass dim3 or plain ints
+  unsigned count() const { return x * y * z; }
 };
 
 struct Block {
@@ -46,6 +50,7 @@ struct Block {
     slots.assign((size_t)((n + 31) / 32) * 32, 0ull);
   }
   int nthreads;
+  Dim3 block_idx, block_dim, grid_dim;
   std::barrier<> bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<unsigned long long> slots;   // one 8-byte exchange slot per lane
@@ -53,8 +58,8 @@ struct Block {
 };
 
 inline thread_local Dim3 t_threadIdx;
+inline thread_local unsigned t_linear = 0;               // threadIdx.x + threadIdx.y * blockDim.x + ...: warps are formed from it
 inline thread_local Block* t_block = nullptr;
-inline Dim3 g_blockIdx, g_blockDim, g_gridDim;
 
 inline float* dyn_smem() {
   uintptr_t p = reinterpret_cast<uintptr_t>(t_block->dyn.data());
@@ -62,13 +67,13 @@ inline float* dyn_smem() {
 }
 
 inline void syncthreads() { t_block->bar.arrive_and_wait(); }
-inline void syncwarp() { t_block->warp_bar[t_threadIdx.x / 32]->arrive_and_wait(); }
+inline void syncwarp() { t_block->warp_bar[t_linear / 32]->arrive_and_wait(); }
 
 template <class T>
 inline T shfl_from(T v, int src_lane) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
   Block* b = t_block;
-  const int w = t_threadIdx.x / 32, l = t_threadIdx.x % 32;
+  const int w = t_linear / 32, l = t_linear % 32;
   unsigned long long bits = 0;
   memcpy(&bits, &v, sizeof(T));
   b->slots[(size_t)w * 32 + l] = bits;
@@ -80,41 +85,63 @@ inline T shfl_from(T v, int src_lane) {
   return r;
 }
 
-// Runs `body()` once per CUDA thread, block after block.
-template <class F>
-inline void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& body) {
-  g_gridDim = Dim3{grid, 1, 1};
-  g_blockDim = Dim3{block, 1, 1};
-  for (unsigned b = 0; b < grid; ++b) {
-    g_blockIdx = Dim3{b, 1, 1};
-    Block blk((int)block, smem_bytes);
-    std::vector<std::thread> threads;
-    threads.reserve(block);
-    for (unsigned t = 0; t < block; ++t)
-      threads.emplace_back([&, t] {
-        t_threadIdx = Dim3{t, 1, 1};
-        t_block = &blk;
-        body();
-        // an exited thread no longer takes part in barriers (CUDA semantics)
-        blk.bar.arrive_and_drop();
-        blk.warp_bar[t / 32]->arrive_and_drop();
-      });
-    for (auto& th : threads) th.join();
+// all 32 lanes' values of one warp (for the reductions that have no shuffle form)
+template <class T>
+inline void warp_gather(T v, T (&out)[32]) {
+  Block* b = t_block;
+  const int w = t_linear / 32, l = t_linear % 32;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  b->slots[(size_t)w * 32 + l] = bits;
+  b->warp_bar[w]->arrive_and_wait();
+  const int lanes = (w * 32 + 32 <= b->nthreads) ? 32 : b->nthreads - w * 32;
+  for (int i = 0; i < 32; ++i) {
+    T r{};
+    if (i < lanes) memcpy(&r, &b->slots[(size_t)w * 32 + i], sizeof(T));
+    out[i] = r;
   }
+  b->warp_bar[w]->arrive_and_wait();
+}
+
+// Runs `body()` once per CUDA thread, block after block (x fastest, like the hardware's linear block order).
+template <class F>
+inline void launch(Dim3 grid, Dim3 block, size_t smem_bytes, F&& body) {
+  const unsigned nthreads = block.count();
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        Block blk((int)nthreads, smem_bytes);
+        blk.block_idx = Dim3{bx, by, bz};
+        blk.block_dim = block;
+        blk.grid_dim = grid;
+        std::vector<std::thread> threads;
+        threads.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t)
+          threads.emplace_back([&, t] {
+            t_linear = t;
+            t_threadIdx = Dim3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+            t_block = &blk;
+            body();
+            // an exited thread no longer takes part in barriers (CUDA semantics)
+            blk.bar.arrive_and_drop();
+            blk.warp_bar[t / 32]->arrive_and_drop();
+          });
+        for (auto& th : threads) th.join();
+      }
 }
 
 }  // namespace colearn_shim
 
 #define threadIdx (::colearn_shim::t_threadIdx)
-#define blockIdx (::colearn_shim::g_blockIdx)
-#define blockDim (::colearn_shim::g_blockDim)
-#define gridDim (::colearn_shim::g_gridDim)
+#define blockIdx (::colearn_shim::t_block->block_idx)
+#define blockDim (::colearn_shim::t_block->block_dim)
+#define gridDim (::colearn_shim::t_block->grid_dim)
 
 inline void __syncthreads() { ::colearn_shim::syncthreads(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { ::colearn_shim::syncwarp(); }
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask, int = 32) {
-  return ::colearn_shim::shfl_from(v, (int)(::colearn_shim::t_threadIdx.x % 32) ^ lane_mask);
+  return ::colearn_shim::shfl_from(v, (int)(::colearn_shim::t_linear % 32) ^ lane_mask);
 }
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src_lane, int = 32) {
@@ -122,9 +149,31 @@ inline T __shfl_sync(unsigned, T v, int src_lane, int = 32) {
 }
 template <class T>
 inline T __shfl_down_sync(unsigned, T v, unsigned delta, int = 32) {
-  const int l = (int)(::colearn_shim::t_threadIdx.x % 32);
+  const int l = (int)(::colearn_shim::t_linear % 32);
   return ::colearn_shim::shfl_from(v, l + (int)delta < 32 ? l + (int)delta : l);
 }
+inline int __reduce_add_sync(unsigned, int v) {
+  int all[32];
+  ::colearn_shim::warp_gather(v, all);
+  int s = 0;
+  for (int i = 0; i < 32; ++i) s += all[i];
+  return s;
+}
+template <class T>
+inline T __ldcs(const T* p) { return *p; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+// atomics (threads of a block are real OS threads here)
+inline float atomicAdd(float* p, float v) {
+  unsigned* up = reinterpret_cast<unsigned*>(p);
+  unsigned old = __atomic_load_n(up, __ATOMIC_RELAXED), want;
+  do { want = __float_as_uint(__uint_as_float(old) + v); } while (!__atomic_compare_exchange_n(up, &old, want, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED));
+  return __uint_as_float(old);
+}
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 template <class T>
@@ -142,8 +191,10 @@ inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 #define cudaFuncSetAttribute(...) cudaSuccess
 #define cudaGetDevice(p) (*(p) = 0, cudaSuccess)
 #define cudaGetLastError() cudaSuccess
+#define cudaMemsetAsync(ptr, value, bytes, stream) (memset((ptr), (value), (bytes)), cudaSuccess)
+#define cudaMemset(ptr, value, bytes) (memset((ptr), (value), (bytes)), cudaSuccess)
 
 #define COLEARN_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::colearn_shim::dyn_smem())
 #define COLEARN_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  ::colearn_shim::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+  ::colearn_shim::launch(::colearn_shim::Dim3(grid), ::colearn_shim::Dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
 #define COLEARN_KERNEL_NAME(...) __VA_ARGS__

@@ -1,11 +1,11 @@
-// CPU build of the persistent-MLP kernels (mlp_persistent.cu + mlp_v2.inc) through host_shim.h: the same source the GPU
-// runs, one OS thread per CUDA thread.  Tests only (ops/build.py::build_simt_emul, tests/test_simt_emul.py).
+// Python face of the SIMT-on-CPU build: mlp_persistent.cu (+ mlp_v2.inc), elementwise.cu and comm.cu — the kernel
+// sources themselves — are compiled with g++ through host_shim.h (simt_mlp.cpp / simt_elementwise.cpp / simt_comm.cpp,
+// one OS thread per CUDA thread) and driven here through the same launch_* entry points bindings.cpp uses on a GPU.
+// Tests only (ops/build.py::build_simt_emul, tests/test_simt_emul.py).
 #define COLEARN_HOST_SHIM 1
 #include <torch/extension.h>
 
-#include "host_shim.h"
-
-#include "mlp_persistent.cu"   // NOLINT(bugprone-suspicious-include): the kernel source itself
+#include "colearn_kernels.h"
 
 namespace py = pybind11;
 
@@ -80,11 +80,165 @@ Tensor mlp_forward(int64_t net_kind, Tensor theta, Tensor x, int64_t d_out) {
   }
   return out;
 }
+
+// ---- elementwise.cu ---------------------------------------------------------------------------------------------
+#define CK(expr) TORCH_CHECK((expr) == cudaSuccess, "launch failed: " #expr)
+float* fmut(Tensor& t, const char* name) { return const_cast<float*>(fptr(t, name)); }
+
+void sgd_step(Tensor p, Tensor g, double lr) { CK(colearn::launch_sgd_step(fmut(p, "p"), fptr(g, "g"), (float)lr, p.numel(), nullptr)); }
+void fedavg_apply(Tensor theta, Tensor slots, Tensor w, double server_lr) {
+  TORCH_CHECK(slots.dim() == 2 && slots.size(1) == theta.numel() && w.numel() == slots.size(0), "slots [K, P], weights [K]");
+  CK(colearn::launch_fedavg_apply(fmut(theta, "theta"), fptr(slots, "slots"), slots.size(1), fptr(w, "w"), (int)slots.size(0),
+                                  (float)server_lr, theta.numel(), nullptr));
+}
+Tensor fedavg_flat(Tensor slots, Tensor w) {
+  Tensor out = torch::zeros({slots.size(1)}, torch::kFloat);
+  CK(colearn::launch_fedavg_flat(out.data_ptr<float>(), fptr(slots, "slots"), slots.size(1), fptr(w, "w"), (int)slots.size(0), slots.size(1), nullptr));
+  return out;
+}
+std::tuple<Tensor, Tensor> sigmoid_bce(Tensor z, Tensor y) {
+  Tensor dz = torch::zeros_like(z), loss = torch::zeros({}, torch::kFloat);
+  CK(colearn::launch_sigmoid_bce(fptr(z, "z"), fptr(y, "y"), dz.data_ptr<float>(), loss.data_ptr<float>(), z.numel(), nullptr));
+  return {loss, dz};
+}
+std::tuple<Tensor, Tensor> sse_loss(Tensor out, Tensor y, double scale) {
+  Tensor dz = torch::zeros_like(out), loss = torch::zeros({}, torch::kFloat);
+  CK(colearn::launch_sse(fptr(out, "out"), fptr(y, "y"), dz.data_ptr<float>(), loss.data_ptr<float>(), out.numel(), (float)scale, nullptr));
+  return {loss, dz};
+}
+std::tuple<Tensor, Tensor> softmax_xent(Tensor logits, Tensor labels) {
+  TORCH_CHECK(logits.dim() == 2 && labels.scalar_type() == at::kLong && labels.numel() == logits.size(0), "logits [R, C], labels int64 [R]");
+  Tensor dl = torch::zeros_like(logits), loss = torch::zeros({}, torch::kFloat);
+  CK(colearn::launch_softmax_xent(fptr(logits, "logits"), 0, labels.data_ptr<int64_t>(), dl.data_ptr<float>(), nullptr, loss.data_ptr<float>(),
+                                  (int)logits.size(0), (int)logits.size(1), nullptr));
+  return {loss, dl};
+}
+std::tuple<Tensor, Tensor> eval_binary(Tensor p, Tensor y) {
+  Tensor loss = torch::zeros({}, torch::kFloat), correct = torch::zeros({}, torch::kInt);
+  CK(colearn::launch_eval_binary(fptr(p, "p"), fptr(y, "y"), loss.data_ptr<float>(), correct.data_ptr<int>(), p.numel(), nullptr));
+  return {loss, correct};
+}
+Tensor argmax_rows(Tensor x) {
+  Tensor out = torch::zeros({x.size(0), 1}, torch::kLong);
+  CK(colearn::launch_argmax_rows(fptr(x, "x"), out.data_ptr<int64_t>(), (int)x.size(0), (int)x.size(1), nullptr));
+  return out;
+}
+Tensor minmax_scale(Tensor x) {
+  Tensor out = torch::zeros_like(x);
+  CK(colearn::launch_minmax_scale(fptr(x, "x"), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), nullptr));
+  return out;
+}
+Tensor feistel_permutation(int64_t n, int64_t rows, int64_t seed) {
+  Tensor out = torch::zeros({rows, n}, torch::kInt);
+  CK(colearn::launch_feistel_permutation(out.data_ptr<int>(), (int)n, (int)rows, (uint64_t)seed, nullptr));
+  return out;
+}
+Tensor transpose_bf16(Tensor x) {
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.is_contiguous() && x.dim() == 2, "bf16 matrix");
+  Tensor out = torch::zeros({x.size(1), x.size(0)}, x.options());
+  CK(colearn::launch_transpose_bf16(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), nullptr));
+  return out;
+}
+Tensor ring_matmul(Tensor a, Tensor b) {
+  TORCH_CHECK(a.scalar_type() == at::kLong && b.scalar_type() == at::kLong && a.is_contiguous() && b.is_contiguous(), "int64 matrices");
+  Tensor c = torch::zeros({a.size(0), b.size(1)}, torch::kLong);
+  CK(colearn::launch_ring_matmul(reinterpret_cast<const long long*>(a.data_ptr<int64_t>()), reinterpret_cast<const long long*>(b.data_ptr<int64_t>()),
+                                 reinterpret_cast<long long*>(c.data_ptr<int64_t>()), (int)a.size(0), (int)a.size(1), (int)b.size(1), nullptr));
+  return c;
+}
+
+// ---- comm.cu: W emulated ranks = W sets of buffers in this process; kernels of different ranks run one after the other -----
+// Coordinator-side star round: slots [W, P] (already holding w_k * theta_k), arrive flags int32 [W], inboxes [W, P] (row k =
+// rank k's inbox), bcast flags int32 [W].  Returns the arrived mask (deadline mode) or the select mask.
+int64_t star_round(Tensor theta, Tensor slots, Tensor arrive, int64_t arrive_epoch, Tensor inboxes, Tensor bcast_flags, int64_t bcast_epoch,
+                   int64_t select_mask, double server_lr, bool do_reduce, bool do_bcast, int64_t n_blocks, double timeout_ms,
+                   std::vector<double> weights) {
+  const int W = (int)slots.size(0);
+  colearn::StarRoundArgs a;
+  memset(&a, 0, sizeof(a));
+  a.theta = fmut(theta, "theta");
+  a.slots = fptr(slots, "slots");
+  a.slot_stride = slots.size(1);
+  a.arrive_flags = reinterpret_cast<const uint32_t*>(arrive.data_ptr<int>());
+  a.arrive_epoch = (uint32_t)arrive_epoch;
+  for (int k = 0; k < W; ++k) {
+    a.peer_inbox[k] = inboxes.data_ptr<float>() + (int64_t)k * inboxes.size(1);
+    a.peer_bcast_flag[k] = reinterpret_cast<uint32_t*>(bcast_flags.data_ptr<int>()) + k;
+    a.weights[k] = k < (int)weights.size() ? (float)weights[k] : 0.f;
+  }
+  a.bcast_epoch = (uint32_t)bcast_epoch;
+  a.select_mask = (uint32_t)select_mask;
+  a.world = W;
+  a.server_lr = (float)server_lr;
+  a.n = theta.numel();
+  a.do_reduce = do_reduce ? 1 : 0;
+  a.do_bcast = do_bcast ? 1 : 0;
+  static uint32_t counter = 0, decision[2] = {0, 0};
+  a.grid_counter = &counter;
+  a.timeout_ns = (unsigned long long)(timeout_ms * 1e6);
+  a.decision = decision;
+  {
+    py::gil_scoped_release nogil;
+    CK(colearn::launch_star_round(a, (int)n_blocks, nullptr));
+  }
+  return timeout_ms > 0 && do_reduce ? (int64_t)decision[1] : select_mask;
+}
+
+// One rank's two-shot kernel (P2P path): works [W, n] (row k = rank k's fp32 arena), shadows [W, n] bf16 or none, chunk flags
+// int32 [W, n_chunks]; `arrive` (this rank's int32 [W]) must already carry `epoch` for every selected rank.
+void twoshot_fedavg(int64_t rank, Tensor works, c10::optional<Tensor> shadows, Tensor chunk_flags, Tensor arrive, Tensor weights,
+                    c10::optional<Tensor> theta_prev, int64_t epoch, int64_t select_mask, double server_lr, int64_t chunk_elems, int64_t n_blocks) {
+  const int W = (int)works.size(0);
+  colearn::TwoShotArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int k = 0; k < W; ++k) {
+    a.work[k] = works.data_ptr<float>() + (int64_t)k * works.size(1);
+    a.shadow_bf16[k] = shadows.has_value() ? static_cast<void*>(static_cast<char*>(shadows->data_ptr()) + (int64_t)k * shadows->size(1) * 2) : nullptr;
+    a.chunk_flags[k] = reinterpret_cast<uint32_t*>(chunk_flags.data_ptr<int>()) + (int64_t)k * chunk_flags.size(1);
+  }
+  a.arrive_flags = reinterpret_cast<const uint32_t*>(arrive.data_ptr<int>());
+  a.weights = fptr(weights, "weights");
+  a.theta_prev = theta_prev.has_value() ? theta_prev->data_ptr<float>() : nullptr;
+  a.epoch = (uint32_t)epoch;
+  a.select_mask = (uint32_t)select_mask;
+  a.server_lr = (float)server_lr;
+  a.n = works.size(1);
+  a.chunk_elems = chunk_elems;
+  a.world = W;
+  a.rank = (int)rank;
+  {
+    py::gil_scoped_release nogil;
+    CK(colearn::launch_twoshot_fedavg(a, (int)n_blocks, nullptr));
+  }
+}
+
+void reduce_push(Tensor slots, Tensor dst, Tensor losses, Tensor loss_dst, Tensor flag, int64_t value, int64_t n_blocks) {
+  static uint32_t counter = 0;
+  py::gil_scoped_release nogil;
+  CK(colearn::launch_reduce_push(fptr(slots, "slots"), (int)slots.size(0), slots.size(1), slots.size(1), fmut(dst, "dst"), fptr(losses, "losses"),
+                                 fmut(loss_dst, "loss_dst"), reinterpret_cast<uint32_t*>(flag.data_ptr<int>()), (uint32_t)value, &counter,
+                                 (int)n_blocks, nullptr));
+}
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-  m.doc() = "persistent-MLP CUDA kernels compiled for the CPU through a SIMT shim (tests only)";
+  m.doc() = "the CUDA kernels of mlp_persistent.cu / elementwise.cu / comm.cu compiled for the CPU through a SIMT shim (tests only)";
   m.def("mlp_local_sgd", &mlp_local_sgd);
   m.def("mlp_forward", &mlp_forward);
   m.def("mlp_net_params", [](int64_t kind) { return (int64_t)colearn::mlp_net_num_params((int)kind); });
+  m.def("sgd_step", &sgd_step);
+  m.def("fedavg_apply", &fedavg_apply);
+  m.def("fedavg_flat", &fedavg_flat);
+  m.def("sigmoid_bce", &sigmoid_bce);
+  m.def("sse_loss", &sse_loss);
+  m.def("softmax_xent", &softmax_xent);
+  m.def("eval_binary", &eval_binary);
+  m.def("argmax_rows", &argmax_rows);
+  m.def("minmax_scale", &minmax_scale);
+  m.def("feistel_permutation", &feistel_permutation);
+  m.def("transpose_bf16", &transpose_bf16);
+  m.def("ring_matmul", &ring_matmul);
+  m.def("star_round", &star_round);
+  m.def("twoshot_fedavg", &twoshot_fedavg);
+  m.def("reduce_push", &reduce_push);
 }

@@ -98,3 +98,139 @@ def test_forward_kernel_on_cpu(simt, kind):
     x = torch.rand(41, dims[0])
     got = simt.mlp_forward(kind, flat, x, dims[-1])
     torch.testing.assert_close(got, reference.mlp_forward(flat, dims, x, act)[0], rtol=1e-4, atol=1e-5)
+
+
+# ---- elementwise.cu on the CPU -------------------------------------------------------------------------------------------
+def test_elementwise_kernels_on_cpu(simt):
+    torch.manual_seed(0)
+    n = 5000 + 3                                             # not a multiple of the vector width: scalar tails run too
+    p, g = torch.randn(n), torch.randn(n)
+    want = p - 0.05 * g
+    simt.sgd_step(p, g, 0.05)
+    torch.testing.assert_close(p, want, rtol=1e-6, atol=1e-6)
+    k = 5
+    slots, w, theta = torch.randn(k, n), torch.softmax(torch.randn(k), 0), torch.randn(n)
+    torch.testing.assert_close(simt.fedavg_flat(slots, w), reference.fedavg_flat(slots, w), rtol=1e-5, atol=1e-5)
+    want = reference.fedavg_apply(theta.clone(), slots, w, 0.7)
+    simt.fedavg_apply(theta, slots, w, 0.7)
+    torch.testing.assert_close(theta, want, rtol=1e-5, atol=1e-5)
+    z, y = torch.randn(777) * 3, (torch.rand(777) > 0.5).float()
+    loss, dz = simt.sigmoid_bce(z, y)
+    rl, rdz = reference.sigmoid_bce(z, y)
+    torch.testing.assert_close(loss, rl, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dz, rdz, rtol=1e-4, atol=1e-6)
+    out, yy = torch.randn(64, 3), torch.randn(64, 3)
+    for mean in (False, True):
+        loss, dz = simt.sse_loss(out, yy, 1.0 / 64 if mean else 1.0)
+        rl, rdz = reference.loss_and_dz(out, yy, "mse" if mean else "sse", "none")
+        torch.testing.assert_close(loss, rl, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(dz, rdz, rtol=1e-5, atol=1e-6)
+    logits, labels = torch.randn(200, 10) * 2, torch.randint(0, 10, (200,))
+    loss, dl = simt.softmax_xent(logits, labels)
+    rl, rdl = reference.softmax_xent(logits, labels)
+    torch.testing.assert_close(loss, rl, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dl, rdl, rtol=1e-4, atol=1e-6)
+    prob = torch.rand(999).clamp(1e-4, 1 - 1e-4)
+    tgt = (torch.rand(999) > 0.5).float()
+    loss, correct = simt.eval_binary(prob, tgt)
+    rl, rc = reference.eval_binary(prob.view(-1, 1), tgt.view(-1, 1))
+    torch.testing.assert_close(loss, rl, rtol=1e-4, atol=1e-3)
+    assert int(correct) == int(rc)
+    x = torch.randn(300, 7)
+    assert torch.equal(simt.argmax_rows(x), x.argmax(1, keepdim=True))
+    feats = torch.rand(500, 10) * 7 - 2
+    lo, hi = feats.min(0).values, feats.max(0).values
+    torch.testing.assert_close(simt.minmax_scale(feats), (feats - lo) / (hi - lo), rtol=1e-5, atol=1e-6)
+
+
+def test_feistel_permutation_transpose_and_ring_matmul_on_cpu(simt):
+    perm = simt.feistel_permutation(1000, 3, 42)
+    assert perm.shape == (3, 1000)
+    for r in range(3):
+        assert sorted(perm[r].tolist()) == list(range(1000))         # a bijection of [0, n) per row (cycle walking)
+    assert not torch.equal(perm[0], perm[1]) and not torch.equal(perm[0], torch.arange(1000, dtype=torch.int32))
+    assert torch.equal(perm, simt.feistel_permutation(1000, 3, 42)) and not torch.equal(perm, simt.feistel_permutation(1000, 3, 43))
+    x = torch.randn(70, 45).to(torch.bfloat16)
+    assert torch.equal(simt.transpose_bf16(x), x.t().contiguous())
+    a = torch.randint(-2 ** 62, 2 ** 62, (9, 20))
+    b = torch.randint(-2 ** 62, 2 ** 62, (20, 13))
+    assert torch.equal(simt.ring_matmul(a, b), a @ b)                # arithmetic mod 2^64 (int64 wrap-around)
+
+
+# ---- comm.cu on the CPU: W emulated ranks = W sets of buffers, kernels of different ranks run one after the other ----------
+def test_star_round_kernel_on_cpu(simt):
+    torch.manual_seed(1)
+    W, P = 4, 1003                                            # P not a multiple of 4: scalar tail
+    theta = torch.randn(P)
+    weights = [0.4, 0.3, 0.2, 0.1]
+    models = [torch.randn(P) for _ in range(W)]
+    slots = torch.stack([w * m for w, m in zip(weights, models)])
+    arrive = torch.full((W,), 5, dtype=torch.int32)
+    inboxes, bflags = torch.zeros(W, P), torch.zeros(W, dtype=torch.int32)
+    th = theta.clone()
+    simt.star_round(th, slots, arrive, 5, inboxes, bflags, 6, 0b1111, 0.5, True, True, 3, 0.0, weights)
+    want = theta + 0.5 * (sum(w * m for w, m in zip(weights, models)) - theta)
+    torch.testing.assert_close(th, want, rtol=1e-5, atol=1e-5)
+    assert all(torch.equal(inboxes[k], th) for k in range(W)) and bflags.tolist() == [6] * W
+    # subset selection: only ranks 0 and 2 contribute / receive the broadcast
+    inboxes.zero_(); bflags.zero_()
+    th = theta.clone()
+    sl = torch.stack([0.5 * models[0], torch.full((P,), 99.0), 0.5 * models[2], torch.full((P,), 99.0)])
+    simt.star_round(th, sl, arrive, 5, inboxes, bflags, 6, 0b0101, 1.0, True, True, 2, 0.0, [0.5, 0, 0.5, 0])
+    torch.testing.assert_close(th, 0.5 * (models[0] + models[2]), rtol=1e-5, atol=1e-5)
+    assert torch.equal(inboxes[0], th) and torch.equal(inboxes[2], th) and float(inboxes[1].abs().max()) == 0 and bflags.tolist() == [6, 0, 6, 0]
+    # deadline: rank 3 never arrives -> dropped after the timeout, the sum is renormalised over the weight that arrived
+    late = torch.tensor([5, 5, 5, 4], dtype=torch.int32)
+    th = theta.clone()
+    mask = simt.star_round(th, slots, late, 5, inboxes, bflags, 7, 0b1111, 1.0, True, True, 3, 20.0, weights)
+    assert mask == 0b0111
+    torch.testing.assert_close(th, sum(w * m for w, m in zip(weights[:3], models[:3])) / 0.9, rtol=1e-4, atol=1e-5)
+    # nobody arrives: theta is kept
+    th = theta.clone()
+    mask = simt.star_round(th, slots, torch.zeros(W, dtype=torch.int32), 5, inboxes, bflags, 8, 0b1111, 1.0, True, False, 2, 5.0, weights)
+    assert mask == 0 and torch.equal(th, theta)
+
+
+@pytest.mark.parametrize("server_lr", [1.0, 0.5])
+def test_twoshot_fedavg_kernel_on_cpu(simt, server_lr):
+    torch.manual_seed(2)
+    W, n, chunk = 4, 4 * 350, 64                              # 22 chunks (the last one short), owner of chunk c = c % W
+    weights = torch.tensor([0.1, 0.2, 0.3, 0.4])
+    trained = torch.randn(W, n)
+    prev = torch.randn(n)
+    works = trained.clone()
+    shadows = torch.zeros(W, n, dtype=torch.bfloat16)
+    n_chunks = (n + chunk - 1) // chunk
+    flags = torch.zeros(W, n_chunks, dtype=torch.int32)
+    prevs = [prev.clone() for _ in range(W)]
+    arrive = torch.full((W,), 3, dtype=torch.int32)
+    for r in range(W):                                          # every rank reduces the chunks it owns and writes them everywhere
+        simt.twoshot_fedavg(r, works, shadows, flags, arrive, weights, prevs[r] if server_lr != 1.0 else None, 3, 0b1111, server_lr, chunk, 2)
+    avg = (weights.view(-1, 1) * trained).sum(0)
+    want = avg if server_lr == 1.0 else prev + server_lr * (avg - prev)
+    for k in range(W):
+        torch.testing.assert_close(works[k], want, rtol=1e-5, atol=1e-5)
+        assert torch.equal(shadows[k], works[k].to(torch.bfloat16))
+    assert int(flags.min()) == 3 and int(flags.max()) == 3
+
+
+def test_twoshot_subset_and_reduce_push_on_cpu(simt):
+    torch.manual_seed(3)
+    W, n, chunk = 4, 512, 128
+    trained = torch.randn(W, n)
+    works = trained.clone()
+    flags = torch.zeros(W, n // chunk, dtype=torch.int32)
+    weights = torch.tensor([0.5, 0.0, 0.5, 0.0])
+    arrive = torch.tensor([9, 0, 9, 0], dtype=torch.int32)      # ranks 1 and 3 are not selected and never arrive
+    for r in range(W):
+        simt.twoshot_fedavg(r, works, None, flags, arrive, weights, None, 9, 0b0101, 1.0, chunk, 1)
+    for k in range(W):                                          # every rank (selected or not) receives the new model
+        torch.testing.assert_close(works[k], 0.5 * (trained[0] + trained[2]), rtol=1e-5, atol=1e-5)
+    # many virtual clients per GPU: local sum of C pre-scaled client models pushed as one contribution
+    C, P = 6, 1001
+    slots, losses = torch.randn(C, P), torch.rand(C, 2)
+    dst, loss_dst, flag = torch.zeros(P), torch.zeros(2), torch.zeros(1, dtype=torch.int32)
+    simt.reduce_push(slots, dst, losses.reshape(-1).contiguous(), loss_dst, flag, 11, 3)
+    torch.testing.assert_close(dst, slots.sum(0), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(loss_dst, losses.mean(0), rtol=1e-5, atol=1e-6)
+    assert int(flag) == 11
