@@ -29,7 +29,7 @@ import torch.nn.functional as F
 
 from . import _ext
 
-_EMUL = {"on": False, "mod": None}
+_EMUL = {"on": False, "mod": None, "simt": None}
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -58,6 +58,36 @@ def emulated():
         yield
     finally:
         _EMUL["on"] = prev
+
+
+def load_simt(build_if_missing: bool = True):
+    """Import (building on first use) ``_colearn_simt``: the conv kernels' CUDA *launchers and kernels* (csrc/convnet.cu)
+    compiled for the CPU through csrc/host_shim.h — one OS thread per CUDA thread (tests only)."""
+    if _EMUL["simt"] is None:
+        hits = sorted(glob.glob(os.path.join(_HERE, "_colearn_simt*.so")))
+        if build_if_missing:
+            from . import build
+            hits = [build.build_simt_emul()]           # no-op when the objects are current
+        if not hits:
+            raise FileNotFoundError("_colearn_simt*.so not built (python -m colearn_federated_learning_b200.ops.build --simt)")
+        spec = importlib.util.spec_from_file_location("_colearn_simt", hits[0])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)  # type: ignore[union-attr]
+        _EMUL["simt"] = mod
+    return _EMUL["simt"]
+
+
+@contextlib.contextmanager
+def simt():
+    """Route CPU tensors through the SIMT-on-CPU build of the kernels themselves (grid mapping, shared-memory phases,
+    atomics included) instead of the PyTorch definitions."""
+    mod = load_simt()
+    prev_on, prev_mod = _EMUL["on"], _EMUL["mod"]
+    _EMUL["on"], _EMUL["mod"] = True, mod
+    try:
+        yield
+    finally:
+        _EMUL["on"], _EMUL["mod"] = prev_on, prev_mod
 
 
 def _native(t: torch.Tensor):

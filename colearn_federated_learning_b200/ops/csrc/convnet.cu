@@ -68,57 +68,57 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_finalize_kernel(const Bn
 }  // namespace
 
 cudaError_t launch_im2col(const Im2colArgs& a, cudaStream_t s) {
-  im2col_kernel<<<map_grid(im2col_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(im2col_kernel, map_grid(im2col_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_col2im(const Col2imArgs& a, cudaStream_t s) {
-  col2im_kernel<<<map_grid(col2im_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(col2im_kernel, map_grid(col2im_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_reduce(const BnReduceArgs& a, cudaStream_t s) {
   dim3 grid(a.C / kBnCols, bn_nseg(a));
-  bn_reduce_kernel<<<grid, kBnThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(bn_reduce_kernel, grid, kBnThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_reduce_finalize(const BnFusedArgs& a, cudaStream_t s) {
   dim3 grid(a.r.C / kBnCols, bn_nseg(a.r));
-  bn_reduce_finalize_kernel<<<grid, kBnThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(bn_reduce_finalize_kernel, grid, kBnThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t s) {
-  bn_finalize_kernel<<<(a.C + 63) / 64, 64, 0, s>>>(a);
+  COLEARN_LAUNCH(bn_finalize_kernel, (a.C + 63) / 64, 64, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_apply(const BnApplyArgs& a, cudaStream_t s) {
-  bn_apply_kernel<<<map_grid(bn_apply_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(bn_apply_kernel, map_grid(bn_apply_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd(const BnBwdArgs& a, cudaStream_t s) {
-  bn_bwd_kernel<<<map_grid(bn_bwd_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(bn_bwd_kernel, map_grid(bn_bwd_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool_fwd(const PoolArgs& a, cudaStream_t s) {
-  maxpool_fwd_kernel<<<map_grid(maxpool_fwd_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(maxpool_fwd_kernel, map_grid(maxpool_fwd_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool_bwd(const PoolArgs& a, cudaStream_t s) {
-  maxpool_bwd_kernel<<<map_grid(maxpool_bwd_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(maxpool_bwd_kernel, map_grid(maxpool_bwd_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_avgpool_fwd(const AvgPoolArgs& a, cudaStream_t s) {
-  avgpool_fwd_kernel<<<map_grid(avgpool_fwd_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(avgpool_fwd_kernel, map_grid(avgpool_fwd_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_avgpool_bwd(const AvgPoolArgs& a, cudaStream_t s) {
-  avgpool_bwd_kernel<<<map_grid(avgpool_bwd_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(avgpool_bwd_kernel, map_grid(avgpool_bwd_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_pack(const PackArgs& a, cudaStream_t s) {
-  pack_kernel<<<map_grid(a.total), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(pack_kernel, map_grid(a.total), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 cudaError_t launch_splitk_reduce(const SplitKReduceArgs& a, cudaStream_t s) {
-  splitk_reduce_kernel<<<map_grid(splitk_reduce_items(a)), kMapThreads, 0, s>>>(a);
+  COLEARN_LAUNCH(splitk_reduce_kernel, map_grid(splitk_reduce_items(a)), kMapThreads, 0, s, a);
   return cudaGetLastError();
 }
 

@@ -2,7 +2,7 @@
 // g++ and runs them with one OS thread per CUDA thread, so that the CPU test-suite executes the *same source* the GPU
 // runs — the flagship persistent-MLP kernel included (tests only; never used to train).
 //
-//   thread block      one block at a time, blockDim.x std::threads
+//   thread block      one block at a time; blockDim.x*y*z std::threads per launch walk the blocks together
 //   __syncthreads()   std::barrier over the live threads of the block (a thread that returns from the kernel drops out,
 //                     like an exited CUDA thread)
 //   __shfl_*_sync()   per-warp exchange slots between two warp barriers (all 32 lanes of a warp must take part, which
@@ -103,31 +103,47 @@ inline void warp_gather(T v, T (&out)[32]) {
   b->warp_bar[w]->arrive_and_wait();
 }
 
-// Runs `body()` once per CUDA thread, block after block (x fastest, like the hardware's linear block order).
+// Runs `body()` once per CUDA thread, block after block (x fastest, like the hardware's linear block order).  The OS
+// threads are created once per launch and walk the blocks together: between two blocks they meet at `next`, whose
+// completion step replaces the Block object (fresh barriers: threads that exited early in one block take part again).
 template <class F>
 inline void launch(Dim3 grid, Dim3 block, size_t smem_bytes, F&& body) {
   const unsigned nthreads = block.count();
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        Block blk((int)nthreads, smem_bytes);
-        blk.block_idx = Dim3{bx, by, bz};
-        blk.block_dim = block;
-        blk.grid_dim = grid;
-        std::vector<std::thread> threads;
-        threads.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t)
-          threads.emplace_back([&, t] {
-            t_linear = t;
-            t_threadIdx = Dim3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-            t_block = &blk;
-            body();
-            // an exited thread no longer takes part in barriers (CUDA semantics)
-            blk.bar.arrive_and_drop();
-            blk.warp_bar[t / 32]->arrive_and_drop();
-          });
-        for (auto& th : threads) th.join();
+  const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+  if (nthreads == 0 || nblocks == 0) return;
+  std::unique_ptr<Block> cur;
+  unsigned long long next_b = 0;
+  auto advance = [&]() noexcept {
+    if (next_b < nblocks) {
+      cur = std::make_unique<Block>((int)nthreads, smem_bytes);
+      cur->block_idx = Dim3{(unsigned)(next_b % grid.x), (unsigned)((next_b / grid.x) % grid.y), (unsigned)(next_b / ((unsigned long long)grid.x * grid.y))};
+      cur->block_dim = block;
+      cur->grid_dim = grid;
+    } else {
+      cur.reset();
+    }
+    ++next_b;
+  };
+  advance();
+  std::barrier next((std::ptrdiff_t)nthreads, advance);
+  std::vector<std::thread> threads;
+  threads.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t)
+    threads.emplace_back([&, t] {
+      t_linear = t;
+      t_threadIdx = Dim3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      for (;;) {
+        Block* blk = cur.get();
+        if (blk == nullptr) break;
+        t_block = blk;
+        body();
+        // an exited thread no longer takes part in this block's barriers (CUDA semantics)
+        blk->bar.arrive_and_drop();
+        blk->warp_bar[t / 32]->arrive_and_drop();
+        next.arrive_and_wait();
       }
+    });
+  for (auto& th : threads) th.join();
 }
 
 }  // namespace colearn_shim

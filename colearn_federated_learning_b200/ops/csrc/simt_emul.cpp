@@ -219,10 +219,33 @@ void reduce_push(Tensor slots, Tensor dst, Tensor losses, Tensor loss_dst, Tenso
                                  fmut(loss_dst, "loss_dst"), reinterpret_cast<uint32_t*>(flag.data_ptr<int>()), (uint32_t)value, &counter,
                                  (int)n_blocks, nullptr));
 }
+
+// ---- convnet.cu: the launchers themselves (grid mapping, two-phase blocks, the ticket-counter BatchNorm reduction) behind the
+// torch-facing wrappers of conv_bindings.inc — a third instantiation next to the GPU one and the body emulator ----------------
+inline void ck(cudaError_t e, const char* what) { TORCH_CHECK(e == cudaSuccess, what, " failed"); }
+struct ConvSimtExec {
+  static constexpr bool kCuda = false;
+  static void im2col(const colearn::convops::Im2colArgs& a) { ck(colearn::launch_im2col(a, nullptr), "im2col"); }
+  static void col2im(const colearn::convops::Col2imArgs& a) { ck(colearn::launch_col2im(a, nullptr), "col2im"); }
+  static void bn_reduce(const colearn::convops::BnReduceArgs& a) { ck(colearn::launch_bn_reduce(a, nullptr), "bn_reduce"); }
+  static void bn_finalize(const colearn::convops::BnFinalizeArgs& a) { ck(colearn::launch_bn_finalize(a, nullptr), "bn_finalize"); }
+  static void bn_reduce_finalize(const colearn::convops::BnFusedArgs& a) { ck(colearn::launch_bn_reduce_finalize(a, nullptr), "bn_reduce_finalize"); }
+  static void bn_apply(const colearn::convops::BnApplyArgs& a) { ck(colearn::launch_bn_apply(a, nullptr), "bn_apply"); }
+  static void bn_bwd(const colearn::convops::BnBwdArgs& a) { ck(colearn::launch_bn_bwd(a, nullptr), "bn_bwd"); }
+  static void maxpool_fwd(const colearn::convops::PoolArgs& a) { ck(colearn::launch_maxpool_fwd(a, nullptr), "maxpool_fwd"); }
+  static void maxpool_bwd(const colearn::convops::PoolArgs& a) { ck(colearn::launch_maxpool_bwd(a, nullptr), "maxpool_bwd"); }
+  static void avgpool_fwd(const colearn::convops::AvgPoolArgs& a) { ck(colearn::launch_avgpool_fwd(a, nullptr), "avgpool_fwd"); }
+  static void avgpool_bwd(const colearn::convops::AvgPoolArgs& a) { ck(colearn::launch_avgpool_bwd(a, nullptr), "avgpool_bwd"); }
+  static void pack(const colearn::convops::PackArgs& a) { ck(colearn::launch_pack(a, nullptr), "pack"); }
+  static void splitk_reduce(const colearn::convops::SplitKReduceArgs& a) { ck(colearn::launch_splitk_reduce(a, nullptr), "splitk_reduce"); }
+};
 }  // namespace
 
+#include "conv_bindings.inc"
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-  m.doc() = "the CUDA kernels of mlp_persistent.cu / elementwise.cu / comm.cu compiled for the CPU through a SIMT shim (tests only)";
+  m.doc() = "the CUDA kernels of mlp_persistent.cu / elementwise.cu / comm.cu / convnet.cu compiled for the CPU through a SIMT shim (tests only)";
+  convbind::register_ops<ConvSimtExec>(m);
   m.def("mlp_local_sgd", &mlp_local_sgd);
   m.def("mlp_forward", &mlp_forward);
   m.def("mlp_net_params", [](int64_t kind) { return (int64_t)colearn::mlp_net_num_params((int)kind); });

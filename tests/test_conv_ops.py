@@ -37,6 +37,9 @@ def backend_ctx(backend):
     if backend == "emul":
         with conv.emulated():
             yield torch.device("cpu")
+    elif backend == "simt":          # the CUDA launchers + kernels themselves on the CPU (csrc/host_shim.h)
+        with conv.simt():
+            yield torch.device("cpu")
     else:
         if not torch.cuda.is_available():
             pytest.skip("needs a GPU")

@@ -234,3 +234,29 @@ def test_twoshot_subset_and_reduce_push_on_cpu(simt):
     torch.testing.assert_close(dst, slots.sum(0), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(loss_dst, losses.mean(0), rtol=1e-5, atol=1e-6)
     assert int(flag) == 11
+
+
+# ---- convnet.cu on the CPU: the launchers and kernels themselves (grid-stride maps, two-phase blocks, the ticket-counter
+# BatchNorm reduction with its atomics / fences), behind the same Python ops the GPU uses --------------------------------
+def test_conv_kernels_on_cpu(simt):
+    import test_conv_ops as T
+
+    T.test_im2col_and_col2im_kernels("simt", (2, 64, 8, 8, 3, 1, 1))
+    T.test_im2col_and_col2im_kernels("simt", (2, 64, 8, 8, 3, 2, 1))
+    T.test_im2col_and_col2im_kernels("simt", (2, 16, 9, 7, 3, 2, 1))
+    T.test_im2col_stem_reads_the_user_batch_directly("simt", "nchw_f32")
+    T.test_pooling_kernels("simt", (2, 64, 16, 16, 3, 2, 1))
+    T.test_pooling_kernels("simt", (1, 8, 6, 6, 2, 2, 0))
+    T.test_pack_and_unpack_params("simt")
+    T._splitk_reduce_case("simt", 16, 128, 640)
+    T._splitk_reduce_case("simt", 5, 4, 12)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("m,c,ldx", [(128, 64, 128), (2048, 128, 128), (100, 64, 64), (1030, 256, 256)])
+def test_batchnorm_kernels_on_cpu(simt, m, c, ldx, fused):
+    """``bn_reduce`` / ``bn_finalize`` / ``bn_apply`` / ``bn_bwd`` and (fused) ``bn_reduce_finalize_kernel`` — the single-launch
+    reduction whose last block per channel group (atomic ticket, __threadfence) finalises and resets the counter."""
+    import test_conv_ops as T
+
+    T._batchnorm_case("simt", m, c, ldx, fused=fused)
