@@ -144,9 +144,9 @@ def build_simt_emul(force: bool = False) -> str:
     src = os.path.join(CSRC, "simt_emul.cpp")
     cxx_flags = [f for f in flags if f not in ("-O2", "-std=c++17")] + ["-O1", "-std=c++20", "-pthread", "-Wno-unknown-pragmas",
                                                                         f"-DTORCH_EXTENSION_NAME={SIMT_NAME}"]
-    sources = ["simt_emul.cpp", "simt_mlp.cpp", "simt_elementwise.cpp", "simt_comm.cpp", "simt_convnet.cpp"]
+    sources = ["simt_emul.cpp", "simt_mlp.cpp", "simt_elementwise.cpp", "simt_comm.cpp", "simt_convnet.cpp", "simt_gemm.cpp"]
     h = hashlib.sha1()
-    for dep in sources + ["host_shim.h", "mlp_persistent.cu", "mlp_v2.inc", "elementwise.cu", "comm.cu", "convnet.cu", "conv_bindings.inc", "colearn_kernels.h", "conv_ops.cuh"]:
+    for dep in sources + ["host_shim.h", "mlp_persistent.cu", "mlp_v2.inc", "elementwise.cu", "comm.cu", "convnet.cu", "gemm_tcgen05.cu", "tcgen05_host_model.h", "conv_bindings.inc", "colearn_kernels.h", "conv_ops.cuh"]:
         with open(os.path.join(CSRC, dep), "rb") as f:
             h.update(f.read())
     h.update(" ".join(cxx_flags).encode())
@@ -156,7 +156,7 @@ def build_simt_emul(force: bool = False) -> str:
         for name in os.listdir(OBJ):
             if name.endswith(".simt.o"):
                 os.remove(os.path.join(OBJ, name))
-        with ThreadPoolExecutor(max_workers=5) as pool:
+        with ThreadPoolExecutor(max_workers=6) as pool:
             list(pool.map(lambda so: _run(["g++", *cxx_flags, *inc, "-c", os.path.join(CSRC, so[0]), "-o", so[1]], so[0]), zip(sources, objs)))
         link = ["g++", "-shared", *objs, "-o", out, "-pthread"]
         for d in ce.library_paths(device_type="cpu"):

@@ -394,8 +394,9 @@ def conv_gemm(kind: str, act: torch.Tensor, other: torch.Tensor, n: int, h: int,
     from .linear import gemm_bf16
     m = n * h * w
     taps = kh * kw
-    if act.is_cuda:
-        mod = _ext.require()
+    simt_mod = _EMUL["mod"] if (_EMUL["on"] and not act.is_cuda and hasattr(_EMUL["mod"], "gemm_tcgen05")) else None
+    if act.is_cuda or simt_mod is not None:
+        mod = _ext.require() if act.is_cuda else simt_mod
         if kind == "wgrad":
             assert m_pad > 0 and k_pad >= taps * c
             geom = [2, 0, c, kh, kw, pad, h, w, n, 0, m_pad, k_pad, m, 0]
@@ -403,6 +404,10 @@ def conv_gemm(kind: str, act: torch.Tensor, other: torch.Tensor, n: int, h: int,
             geom = [1, 0, c, kh, kw, pad, h, w, n, 0, m, out_bf16.shape[1] if out_bf16 is not None else other.shape[0], taps * c, 0]
         else:
             geom = [1, 1, c, kh, kw, pad, h, w, n, rows_per_tap, m, rows_per_tap, taps * c, 1 if w_packed else 0]
+        if simt_mod is not None:   # the kernel source on the functional tcgen05 / TMA model (csrc/tcgen05_host_model.h)
+            mod.gemm_tcgen05(act, other, None, False, None, out_bf16, None, None, sgd_master, float(sgd_lr), sgd_shadow, None, None,
+                             0, int(split_k or 0), split_out, 0, False, addend, geom)
+            return
         mod.gemm_tcgen05(act, other, None, False, None, out_bf16, None, None, sgd_master, float(sgd_lr), sgd_shadow, None, None,
                          0, 0, 1, 0, 0, 0, 0, int(split_k or 0), split_out, 0, False, addend, geom)
         return

@@ -50,6 +50,9 @@ struct Cfg {
 
 std::string g_last_error;
 
+#ifdef COLEARN_HOST_SHIM
+#include "tcgen05_host_model.h"   // functional CPU model of mbarrier / TMA / tcgen05 / TMEM (tests)
+#else
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -191,6 +194,12 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the three fences / hints the kernels issue inline (macros, so that the statements stay exactly where they were)
+#define tmap_prefetch(t) asm volatile("prefetch.tensormap [%0];" ::"l"(t) : "memory")
+#define fence_mbarrier_init() asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory")
+#define fence_proxy_async() asm volatile("fence.proxy.async.global;" ::: "memory")
+
+#endif  // COLEARN_HOST_SHIM
 
 // K-major, 128B-swizzled smem operand descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, ignored for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
@@ -358,7 +367,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
   constexpr int kStages = C::kStages, kTmemCols = C::kTmemCols;
   constexpr uint32_t kStageBytesA = C::kStageBytesA, kStageBytesB = C::kStageBytesB, kStageBytes = C::kStageBytes;
-  extern __shared__ uint8_t smem_raw[];
+  COLEARN_DYN_SMEM_UNALIGNED(uint8_t, smem_raw);
   // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -376,11 +385,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int work0 = blockIdx.x / CL, work_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    tmap_prefetch(&tmap_a);
+    tmap_prefetch(&tmap_b);
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], CL); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], kEpilogueWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbarrier_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
   tc_fence_before();
@@ -414,7 +423,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int64_t c = b_lo; c <= b_hi; ++c)
               while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
           }
-          asm volatile("fence.proxy.async.global;" ::: "memory");
+          fence_proxy_async();
         }
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -552,6 +561,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 PFN_encodeTiled get_encode() {
+#ifdef COLEARN_HOST_SHIM
+  return nullptr;
+#endif
   static PFN_encodeTiled fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -577,6 +589,14 @@ struct MapKeyHash {
 
 bool make_tmap(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
   // row-major [rows, cols] bf16; box = [box_rows rows, 64 cols] (64 bf16 = one 128-byte swizzle row)
+#ifdef COLEARN_HOST_SHIM
+  {
+    const long long dims[2] = {cols, rows}, strides[1] = {(long long)cols * 2};
+    const int box[2] = {BK, box_rows};
+    shim_encode_tiled(out, ptr, 2, dims, strides, box);
+    return true;
+  }
+#endif
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
@@ -602,6 +622,14 @@ bool make_tmap(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* o
 
 bool make_tmap_4d(const void* ptr, int n_images, int H, int W, int C, int box_images, CUtensorMap* out) {
   // NHWC bf16 activation as (c, w, h, n); box = 64 channels x whole images (SW128: one box line = 64 channels = 128 bytes)
+#ifdef COLEARN_HOST_SHIM
+  {
+    const long long dims[4] = {C, W, H, n_images}, strides[3] = {(long long)C * 2, (long long)W * C * 2, (long long)H * W * C * 2};
+    const int box[4] = {64, W, H, box_images};
+    shim_encode_tiled(out, ptr, 4, dims, strides, box);
+    return true;
+  }
+#endif
   struct Key { const void* p; int n, h, w, c, b; bool operator==(const Key& o) const { return p == o.p && n == o.n && h == o.h && w == o.w && c == o.c && b == o.b; } };
   struct KeyHash { size_t operator()(const Key& k) const {
     return std::hash<const void*>()(k.p) ^ (size_t)k.n * 1000003u ^ (size_t)k.h * 10007u ^ (size_t)k.w * 131u ^ (size_t)k.c * 31u ^ (size_t)k.b * 7u; } };
@@ -647,6 +675,12 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
   int units = num_sms[dev & 63] / CL;          // persistent: one CTA (or CTA pair) per SM (pair)
   if (work < units) units = work;
   if (units < 1) units = 1;
+#ifdef COLEARN_HOST_SHIM
+  if (CL != 1) { g_last_error = "clusters are not modelled on the host"; return cudaErrorNotSupported; }
+  void (*kern)(CUtensorMap, CUtensorMap, int, int, int, GemmEpilogue) = gemm_tcgen05_kernel<BN, CL>;
+  COLEARN_LAUNCH(kern, units * CL, kThreads, C::kSmemBytes, s, ta, tb, M, N, K, ep);
+  return cudaSuccess;
+#else
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(units * CL);
   cfg.blockDim = dim3(kThreads);
@@ -660,8 +694,8 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
   cfg.attrs = attr;
   cfg.numAttrs = (CL > 1) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CL>, ta, tb, M, N, K, ep);
+#endif
 }
-
 
 // MN-major operands: A [K, a_cols] (AMN) or [M, K]; B [b_rows >= K, N] row-major bf16, boxes of [64 rows x 64 columns]
 template <int BN, bool AMN>
@@ -684,7 +718,8 @@ cudaError_t launch_mn(const void* A, int a_cols, const void* B, int b_rows, int 
   int units = num_sms[dev & 63];
   if (work < units) units = work;
   if (units < 1) units = 1;
-  gemm_tcgen05_kernel<BN, 1, AMN, true><<<units, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+  void (*kern)(CUtensorMap, CUtensorMap, int, int, int, GemmEpilogue) = gemm_tcgen05_kernel<BN, 1, AMN, true>;
+  COLEARN_LAUNCH(kern, units, kThreads, C::kSmemBytes, s, ta, tb, M, N, K, ep);
   return cudaGetLastError();
 }
 
@@ -716,7 +751,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   using C = Cfg2SM;
   constexpr int BN = C::BN, kStages = C::kStages, kTmemCols = C::kTmemCols;
   constexpr uint32_t kStageBytesA = C::kStageBytesA, kStageBytesB = C::kStageBytesB, kStageBytes = C::kStageBytes;
-  extern __shared__ uint8_t smem_raw[];
+  COLEARN_DYN_SMEM_UNALIGNED(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kStageBytesA;
@@ -730,8 +765,8 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   const int work0 = blockIdx.x >> 1, work_stride = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    tmap_prefetch(&tmap_a);
+    tmap_prefetch(&tmap_b);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bars->full[i], 2);                  // (leader only is waited on) both producers arrive
       mbar_init(&bars->empty[i], 1);                 // leader's commit, multicast to both CTAs
@@ -740,7 +775,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       mbar_init(&bars->tmem_full[i], 1);             // leader's commit, multicast to both CTAs
       mbar_init(&bars->tmem_empty[i], 2 * kEpilogueWarps);   // (leader's is waited on) both CTAs' epilogue warps
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbarrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
   tc_fence_before();
@@ -771,7 +806,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             for (int64_t c = b_lo; c <= b_hi; ++c)
               while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
           }
-          asm volatile("fence.proxy.async.global;" ::: "memory");
+          fence_proxy_async();
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -867,6 +902,11 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
   int units = num_sms[dev & 63] / 2;
   if (work < units) units = work;
   if (units < 1) units = 1;
+#ifdef COLEARN_HOST_SHIM
+  (void)units;
+  g_last_error = "cta_group::2 is not modelled on the host";
+  return cudaErrorNotSupported;
+#else
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(units * 2);
   cfg.blockDim = dim3(kThreads);
@@ -880,6 +920,7 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel, ta, tb, M, N, K, ep);
+#endif
 }
 
 }  // namespace
@@ -913,7 +954,8 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
   int units = num_sms[dev & 63];
   if (work < units) units = work;
   if (units < 1) units = 1;
-  gemm_tcgen05_kernel<BN, 1, WGRAD, BMN><<<units, kThreads, C::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+  void (*kern)(CUtensorMap, CUtensorMap, int, int, int, GemmEpilogue) = gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>;
+  COLEARN_LAUNCH(kern, units, kThreads, C::kSmemBytes, s, ta, tb, M, N, K, ep);
   return cudaGetLastError();
 }
 
@@ -1035,7 +1077,11 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
   // BN=256 when it divides N and leaves enough tiles to fill the machine; BN=128 otherwise
   // cta_group::2 (two SMs per 256x256 tile): forced with cluster == 3, automatic when the shape allows it and there
   // are enough tile pairs to fill the machine (measured: 1 485 vs 1 263 TFLOP/s at 4096^3, equal at 1024x4096x4096)
+#ifdef COLEARN_HOST_SHIM
+  const bool can_2sm = false;                      // cta_group::2 / clusters are GPU-only
+#else
   const bool can_2sm = (M % 256 == 0) && (N % 256 == 0);
+#endif
   if (ep.cluster == 3 && !can_2sm) { g_last_error = "cta_group::2 needs M%256==0 and N%256==0"; return cudaErrorInvalidValue; }
   if (ep.cluster == 3 || (ep.cluster == 0 && ep.tile_n == 0 && can_2sm && (int64_t)(M / 256) * (N / 256) >= 60))
     return launch_2sm(A, B, M, N, K, ep, s);

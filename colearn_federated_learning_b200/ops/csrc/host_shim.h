@@ -21,7 +21,9 @@
 #include <string.h>
 
 #include <barrier>
+#include <chrono>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -55,6 +57,13 @@ struct Block {
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<unsigned long long> slots;   // one 8-byte exchange slot per lane
   std::vector<float> dyn;                  // dynamic shared memory (16-byte aligned start, see dyn_smem())
+  // per-block scratch outside shared memory (the tcgen05 model keeps the CTA's tensor memory here)
+  float* scratch(size_t n) {
+    std::call_once(scratch_once, [&] { scratch_buf.assign(n, 0.f); });
+    return scratch_buf.data();
+  }
+  std::once_flag scratch_once;
+  std::vector<float> scratch_buf;
 };
 
 inline thread_local Dim3 t_threadIdx;
@@ -206,11 +215,13 @@ inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 // runtime calls the launchers make: nothing to configure on the host
 #define cudaFuncSetAttribute(...) cudaSuccess
 #define cudaGetDevice(p) (*(p) = 0, cudaSuccess)
+#define cudaDeviceGetAttribute(p, attr, dev) (*(p) = 4, cudaSuccess)   /* "4 SMs": persistent kernels walk several tiles per CTA */
 #define cudaGetLastError() cudaSuccess
 #define cudaMemsetAsync(ptr, value, bytes, stream) (memset((ptr), (value), (bytes)), cudaSuccess)
 #define cudaMemset(ptr, value, bytes) (memset((ptr), (value), (bytes)), cudaSuccess)
 
 #define COLEARN_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::colearn_shim::dyn_smem())
+#define COLEARN_DYN_SMEM_UNALIGNED(type, name) COLEARN_DYN_SMEM(type, name)
 #define COLEARN_LAUNCH(kernel, grid, block, smem, stream, ...) \
   ::colearn_shim::launch(::colearn_shim::Dim3(grid), ::colearn_shim::Dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
 #define COLEARN_KERNEL_NAME(...) __VA_ARGS__

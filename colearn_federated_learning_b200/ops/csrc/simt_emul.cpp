@@ -220,6 +220,64 @@ void reduce_push(Tensor slots, Tensor dst, Tensor losses, Tensor loss_dst, Tenso
                                  (int)n_blocks, nullptr));
 }
 
+// ---- gemm_tcgen05.cu on the functional tcgen05 / TMA / mbarrier model (tcgen05_host_model.h) ---------------------------------
+// Same argument meaning as bindings.cpp::gemm_tcgen05 (minus the cross-GPU ready flags and the cluster modes).
+void gemm_tcgen05(Tensor A, Tensor B, c10::optional<Tensor> bias, bool relu, c10::optional<Tensor> relu_mask, c10::optional<Tensor> out_bf16,
+                  c10::optional<Tensor> out_f32, c10::optional<Tensor> out_bf16_t, c10::optional<Tensor> sgd_master, double sgd_lr,
+                  c10::optional<Tensor> sgd_shadow, c10::optional<Tensor> sgd_shadow_t, c10::optional<Tensor> colsum, int64_t tile_n,
+                  int64_t split_k, c10::optional<Tensor> split_out, int64_t mn_m, bool b_kn, c10::optional<Tensor> addend,
+                  std::vector<int64_t> conv) {
+  TORCH_CHECK(!A.is_cuda() && !B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16 && A.is_contiguous() &&
+              B.is_contiguous() && A.dim() == 2 && B.dim() == 2, "A, B: contiguous CPU bf16 matrices");
+  const bool mn = mn_m > 0, is_conv = !conv.empty();
+  TORCH_CHECK(!is_conv || conv.size() == 14, "conv = 14 ints");
+  const int M = is_conv ? (int)conv[10] : (mn ? (int)mn_m : (int)A.size(0));
+  const int N = is_conv ? (int)conv[11] : ((mn || b_kn) ? (int)B.size(1) : (int)B.size(0));
+  const int K = is_conv ? (int)conv[12] : (mn ? (int)A.size(0) : (int)A.size(1));
+  colearn::GemmEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  auto ptr = [&](const c10::optional<Tensor>& t, at::ScalarType st, int64_t numel, const char* name) -> void* {
+    if (!t.has_value()) return nullptr;
+    TORCH_CHECK(!t->is_cuda() && t->scalar_type() == st && t->is_contiguous() && t->numel() >= numel, name, ": dtype / size");
+    return t->data_ptr();
+  };
+  ep.bias = (const float*)ptr(bias, at::kFloat, N, "bias");
+  ep.relu = relu ? 1 : 0;
+  ep.relu_mask = ptr(relu_mask, at::kBFloat16, (int64_t)M * N, "relu_mask");
+  ep.out_bf16 = ptr(out_bf16, at::kBFloat16, (int64_t)M * N, "out_bf16");
+  ep.out_f32 = (float*)ptr(out_f32, at::kFloat, (int64_t)M * N, "out_f32");
+  ep.out_bf16_t = ptr(out_bf16_t, at::kBFloat16, (int64_t)M * N, "out_bf16_t");
+  ep.sgd_master = (float*)ptr(sgd_master, at::kFloat, (int64_t)M * N, "sgd_master");
+  ep.sgd_lr = (float)sgd_lr;
+  ep.sgd_shadow = ptr(sgd_shadow, at::kBFloat16, (int64_t)M * N, "sgd_shadow");
+  ep.sgd_shadow_t = ptr(sgd_shadow_t, at::kBFloat16, (int64_t)M * N, "sgd_shadow_t");
+  ep.colsum = (float*)ptr(colsum, at::kFloat, (int64_t)(M / 32) * N, "colsum");
+  ep.addend = ptr(addend, at::kBFloat16, (int64_t)M * N, "addend");
+  ep.ready_chunk_elems = 1;
+  ep.tile_n = (int)tile_n;
+  if (split_k > 1) {
+    ep.split_k = (int)split_k;
+    ep.split_out = (float*)ptr(split_out, at::kFloat, split_k * (int64_t)M * N, "split_out");
+    TORCH_CHECK(ep.split_out != nullptr, "split_out");
+  }
+  cudaError_t e;
+  {
+    py::gil_scoped_release nogil;
+    if (is_conv) {
+      colearn::convops::ConvAddr& g = ep.conv;
+      g.mode = (int)conv[0]; g.flip = (int)conv[1]; g.C = (int)conv[2]; g.KH = (int)conv[3]; g.KW = (int)conv[4]; g.pad = (int)conv[5];
+      const int H = (int)conv[6], W = (int)conv[7];
+      g.HW = H * W; g.n_images = (int)conv[8]; g.b_rows_per_tap = (int)conv[9]; g.b_mn = (int)conv[13];
+      e = colearn::launch_gemm_tcgen05_conv(A.data_ptr(), g.n_images, H, W, B.data_ptr(), (int)B.size(0), (int)B.size(1), M, N, K, ep, nullptr);
+    } else if (mn || b_kn) {
+      e = colearn::launch_gemm_tcgen05_mn(A.data_ptr(), mn ? 1 : 0, (int)A.size(1), B.data_ptr(), (int)B.size(0), M, N, K, ep, nullptr);
+    } else {
+      e = colearn::launch_gemm_tcgen05(A.data_ptr(), B.data_ptr(), M, N, K, ep, nullptr);
+    }
+  }
+  TORCH_CHECK(e == cudaSuccess, "gemm_tcgen05 (host model): ", colearn::gemm_tcgen05_last_error());
+}
+
 // ---- convnet.cu: the launchers themselves (grid mapping, two-phase blocks, the ticket-counter BatchNorm reduction) behind the
 // torch-facing wrappers of conv_bindings.inc — a third instantiation next to the GPU one and the body emulator ----------------
 inline void ck(cudaError_t e, const char* what) { TORCH_CHECK(e == cudaSuccess, what, " failed"); }
@@ -246,6 +304,7 @@ struct ConvSimtExec {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "the CUDA kernels of mlp_persistent.cu / elementwise.cu / comm.cu / convnet.cu compiled for the CPU through a SIMT shim (tests only)";
   convbind::register_ops<ConvSimtExec>(m);
+  m.def("gemm_tcgen05", &gemm_tcgen05);
   m.def("mlp_local_sgd", &mlp_local_sgd);
   m.def("mlp_forward", &mlp_forward);
   m.def("mlp_net_params", [](int64_t kind) { return (int64_t)colearn::mlp_net_num_params((int)kind); });

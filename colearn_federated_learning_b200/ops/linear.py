@@ -38,16 +38,20 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
     ``split_k = S > 1`` (skinny problems: few output tiles, long reduction): the K range is cut into S slices that
     run as independent work units; slice ``s`` stores its raw fp32 accumulator to ``split_out[s]`` (``[S, M, N]``)
     and no other epilogue option may be given — ``ops.conv.splitk_reduce`` sums the slices and applies the epilogue."""
+    from . import conv as _conv
+    # tests (ops.conv.simt()): CPU bf16 operands go to the kernel SOURCE on the functional tcgen05 / TMA / mbarrier model
+    simt_mod = (_conv._EMUL["mod"] if (not a.is_cuda and _conv._EMUL["on"] and hasattr(_conv._EMUL["mod"], "gemm_tcgen05")
+                                       and a.dtype == torch.bfloat16 and not ready_flags and not cluster) else None)
     if mn_m:
         assert a.shape[0] == b.shape[0] and a.shape[1] <= mn_m and mn_m % 128 == 0 and a.shape[1] % 8 == 0
         assert not ready_flags and not cluster, "the MN-major form has no cluster / ready-flag variant"
-        if not a.is_cuda:   # reference: bring the operands to the K-major form of the definition below
+        if not a.is_cuda and simt_mod is None:   # reference: bring the operands to the K-major form of the definition below
             at = a.new_zeros(mn_m, a.shape[0])
             at[: a.shape[1]].copy_(a.t())
             a, b, mn_m = at, b.t().contiguous(), 0
     if b_kn:
         assert not mn_m and a.shape[1] <= b.shape[0] and not ready_flags and not cluster
-        if not a.is_cuda:
+        if not a.is_cuda and simt_mod is None:
             b, b_kn = b[: a.shape[1]].t().contiguous(), False
     m_out, n_out = (mn_m, b.shape[1]) if mn_m else (a.shape[0], b.shape[1] if b_kn else b.shape[0])
     k_red = a.shape[0] if mn_m else a.shape[1]
@@ -56,6 +60,11 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
         assert (bias is None and not relu and relu_mask is None and out_bf16 is None and out_f32 is None and out_bf16_t is None
                 and sgd_master is None and colsum is None and not ready_flags and addend is None), "split-K stores raw partials only"
         assert k_red // 64 >= split_k, "split_k must not exceed K/64"
+    if simt_mod is not None:
+        simt_mod.gemm_tcgen05(a.contiguous(), b.contiguous(), bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
+                              float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(tile_n), int(split_k or 0), split_out, int(mn_m or 0),
+                              bool(b_kn), addend, [])
+        return
     if not a.is_cuda:
         if split_k and split_k > 1:   # same slice boundaries as the kernel: k-blocks of 64, slice s = [nkb*s/S, nkb*(s+1)/S)
             nkb = a.shape[1] // 64

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from colearn_federated_learning_b200.models import build_model, flatten_params
+from colearn_federated_learning_b200 import ops
 from colearn_federated_learning_b200.ops import reference
 
 NETS = {  # kind: (model name, dims, output activation, losses)
@@ -260,3 +261,114 @@ def test_batchnorm_kernels_on_cpu(simt, m, c, ldx, fused):
     import test_conv_ops as T
 
     T._batchnorm_case("simt", m, c, ldx, fused=fused)
+
+
+# ---- gemm_tcgen05.cu on the functional tcgen05 / TMA / mbarrier / TMEM model (csrc/tcgen05_host_model.h) ------------------
+def _gemm(simt, a, b, **kw):
+    simt.gemm_tcgen05(a, b, kw.get("bias"), kw.get("relu", False), kw.get("relu_mask"), kw.get("out_bf16"), kw.get("out_f32"),
+                      kw.get("out_bf16_t"), kw.get("sgd_master"), kw.get("sgd_lr", 0.0), kw.get("sgd_shadow"), kw.get("sgd_shadow_t"),
+                      kw.get("colsum"), kw.get("tile_n", 0), kw.get("split_k", 0), kw.get("split_out"), kw.get("mn_m", 0),
+                      kw.get("b_kn", False), kw.get("addend"), kw.get("conv", []))
+
+
+def _bf(*shape):
+    return torch.randn(*shape).to(torch.bfloat16)
+
+
+def test_tcgen05_gemm_source_on_the_cpu_model_k_major(simt):
+    """The persistent TMA -> tcgen05.mma -> TMEM -> epilogue pipeline (mbarrier phases, 4 "SMs" walking up to 8 tiles each,
+    double-buffered accumulators) and every fused epilogue.  This path runs on B200s, so exact agreement here calibrates
+    the model (swizzle, descriptor decode) for the operand modes that have not run on a GPU yet."""
+    torch.manual_seed(0)
+    for m, n, k, tile_n in [(128, 128, 64, 0), (1024, 256, 192, 128), (512, 512, 128, 256), (256, 384, 64, 0)]:
+        a, b = _bf(m, k), _bf(n, k)
+        out = torch.full((m, n), 7.0)
+        _gemm(simt, a, b, out_f32=out, tile_n=tile_n)
+        torch.testing.assert_close(out, a.float() @ b.float().t(), rtol=1e-5, atol=1e-4)
+    m, n, k = 256, 256, 128
+    a, b, bias = _bf(m, k), _bf(n, k), torch.randn(n)
+    acc = torch.relu(a.float() @ b.float().t() + bias)
+    ob, ot, cs = torch.zeros(m, n, dtype=torch.bfloat16), torch.zeros(n, m, dtype=torch.bfloat16), torch.zeros(m // 32, n)
+    _gemm(simt, a, b, bias=bias, relu=True, out_bf16=ob, out_bf16_t=ot, colsum=cs)
+    assert torch.equal(ob, acc.to(torch.bfloat16)) and torch.equal(ot, ob.t().contiguous())
+    torch.testing.assert_close(cs, acc.view(m // 32, 32, n).sum(1), rtol=1e-4, atol=1e-3)
+    mask, add = _bf(m, n), _bf(m, n)
+    of = torch.zeros(m, n)
+    _gemm(simt, a, b, relu_mask=mask, addend=add, out_f32=of)
+    torch.testing.assert_close(of, (a.float() @ b.float().t()) * (mask.float() > 0) + add.float(), rtol=1e-5, atol=1e-4)
+    master0 = torch.randn(m, n)
+    master, sh, sht = master0.clone(), torch.zeros(m, n, dtype=torch.bfloat16), torch.zeros(n, m, dtype=torch.bfloat16)
+    _gemm(simt, a, b, sgd_master=master, sgd_lr=0.25, sgd_shadow=sh, sgd_shadow_t=sht)
+    torch.testing.assert_close(master, master0 - 0.25 * (a.float() @ b.float().t()), rtol=1e-5, atol=1e-4)
+    assert torch.equal(sh, master.to(torch.bfloat16)) and torch.equal(sht, sh.t().contiguous())
+    # split-K: slices that do not divide the k-blocks evenly, more work units than CTAs
+    a, b = _bf(256, 64 * 7), _bf(256, 64 * 7)
+    part = torch.full((3 * 256 * 256 + 16,), 7.0)
+    _gemm(simt, a, b, split_k=3, split_out=part)
+    torch.testing.assert_close(part[: 3 * 256 * 256].view(3, 256, 256).sum(0), a.float() @ b.float().t(), rtol=1e-5, atol=1e-3)
+    assert float(part[3 * 256 * 256:].min()) == 7.0
+    want = torch.zeros(3 * 256 * 256)
+    ops.gemm_bf16(a, b, split_k=3, split_out=want)                       # same slice boundaries as the CPU definition
+    torch.testing.assert_close(part[: 3 * 256 * 256], want, rtol=1e-5, atol=1e-3)
+
+
+def test_tcgen05_gemm_source_on_the_cpu_model_mn_major(simt):
+    """MN-major UMMA operands (boxes of 64 rows x 64 columns, LBO 8192 / SBO 1024, +2048 bytes per UMMA): wgrad form AᵀB
+    with TMA zero fill for the missing columns, dgrad form A·B[:K], with split-K and the fused SGD epilogue."""
+    torch.manual_seed(1)
+    for kd, ac, m, n in [(64, 128, 128, 128), (128, 64, 128, 128), (512, 64, 128, 640), (256, 256, 256, 256)]:
+        a, b = _bf(kd, ac), _bf(kd, n)
+        out = torch.full((m, n), 7.0)
+        _gemm(simt, a, b, mn_m=m, out_f32=out)
+        want = torch.zeros(m, n)
+        want[:ac] = a.float().t() @ b.float()
+        torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-3)
+    for m, kd, rows, n in [(128, 64, 64, 128), (256, 64, 128, 640), (128, 128, 128, 256)]:
+        a, b = _bf(m, kd), _bf(rows, n)
+        out = torch.zeros(m, n)
+        _gemm(simt, a, b, b_kn=True, out_f32=out)
+        torch.testing.assert_close(out, a.float() @ b[:kd].float(), rtol=1e-5, atol=1e-3)
+    a, b = _bf(512, 64), _bf(512, 256)
+    want = torch.zeros(128, 256)
+    want[:64] = a.float().t() @ b.float()
+    part = torch.zeros(4 * 128 * 256)
+    _gemm(simt, a, b, mn_m=128, split_k=4, split_out=part)
+    torch.testing.assert_close(part.view(4, 128, 256).sum(0), want, rtol=1e-5, atol=1e-3)
+    master, sh = torch.ones(128, 256), torch.zeros(128, 256, dtype=torch.bfloat16)
+    _gemm(simt, a, b, mn_m=128, sgd_master=master, sgd_lr=0.5, sgd_shadow=sh)
+    torch.testing.assert_close(master, 1 - 0.5 * want, rtol=1e-5, atol=1e-3)
+    assert torch.equal(sh, master.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(4, 8, 8, 64, 64), (8, 4, 4, 128, 128), (32, 2, 2, 128, 64), (128, 1, 1, 64, 128), (8, 4, 4, 64, 128)])
+def test_implicit_conv_kernels_on_the_cpu_model(simt, n, h, w, cin, cout):
+    """Forward / dgrad (K-major W^T and packed MN-major weights, residual addend, 128x64 tile) / wgrad (MN-major 4-D boxes,
+    fused SGD, split-K) of a stride-1 3x3 convolution: the producer's 4-D TMA boxes on the model against autograd."""
+    from test_zz_round2_gpu import _implicit_case
+    from colearn_federated_learning_b200.ops import conv as C
+
+    d = _implicit_case(n, h, w, cin, cout)
+    m, cp, kp = d["m"], d["cout_pad"], d["k_pad"]
+    with C.simt():
+        out = torch.full((m, cp), 7.0, dtype=torch.bfloat16)
+        C.conv_gemm("fwd", d["act"], d["wp"], n, h, w, cin, 3, 3, 1, out_bf16=out)
+        part = torch.zeros(3 * m * cp)
+        C.conv_gemm("fwd", d["act"], d["wp"], n, h, w, cin, 3, 3, 1, split_k=3, split_out=part)
+        add = torch.randn(m, cin).to(torch.bfloat16)
+        dx, dx2 = torch.zeros(m, cin, dtype=torch.bfloat16), torch.zeros(m, cin, dtype=torch.bfloat16)
+        C.conv_gemm("dgrad", d["dz"], d["wp"][:cout].t().contiguous(), n, h, w, cout, 3, 3, 1, out_bf16=dx, addend=add, rows_per_tap=cin)
+        C.conv_gemm("dgrad", d["dz"], d["wp"], n, h, w, cout, 3, 3, 1, out_bf16=dx2, addend=add, rows_per_tap=cin, w_packed=True)
+        master, sh = torch.zeros(cp, kp), torch.zeros(cp, kp, dtype=torch.bfloat16)
+        C.conv_gemm("wgrad", d["act"], d["dz"], n, h, w, cin, 3, 3, 1, m_pad=cp, k_pad=kp, sgd_master=master, sgd_lr=-1.0, sgd_shadow=sh)
+        s = max(2, min(4, m // 64))
+        wpart = torch.zeros(s * cp * kp)
+        C.conv_gemm("wgrad", d["act"], d["dz"], n, h, w, cin, 3, 3, 1, m_pad=cp, k_pad=kp, split_k=s, split_out=wpart)
+    torch.testing.assert_close(out[:, :cout].float(), d["z"], rtol=2e-2, atol=3e-2)
+    assert float(out[:, cout:].float().abs().max() if cp > cout else 0.0) == 0.0
+    torch.testing.assert_close(part.view(3, m, cp).sum(0)[:, :cout], d["z"], rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(dx.float(), d["dx"] + add.float(), rtol=2e-2, atol=5e-2)
+    assert torch.equal(dx, dx2)                                              # same products, same accumulation order
+    torch.testing.assert_close(master[:cout, :9 * cin], d["dw"], rtol=1e-4, atol=1e-3)
+    assert float(master[cout:].abs().max() if cp > cout else 0.0) == 0.0 and float(master[:, 9 * cin:].abs().max() if kp > 9 * cin else 0.0) == 0.0
+    assert torch.equal(sh, master.to(torch.bfloat16))
+    torch.testing.assert_close(wpart.view(s, cp, kp).sum(0), master, rtol=1e-4, atol=1e-3)
