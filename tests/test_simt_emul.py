@@ -372,3 +372,39 @@ def test_implicit_conv_kernels_on_the_cpu_model(simt, n, h, w, cin, cout):
     assert float(master[cout:].abs().max() if cp > cout else 0.0) == 0.0 and float(master[:, 9 * cin:].abs().max() if kp > 9 * cin else 0.0) == 0.0
     assert torch.equal(sh, master.to(torch.bfloat16))
     torch.testing.assert_close(wpart.view(s, cp, kp).sum(0), master, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("COLEARN_RUN_SLOW") != "1", reason="~4 minutes: set COLEARN_RUN_SLOW=1")
+def test_whole_resnet18_step_from_kernel_sources_on_the_cpu_model(simt, monkeypatch):
+    """One ResNet-18 SGD step (batch 128) with EVERY kernel — im2col / BatchNorm / pooling / packing, the tcgen05 GEMMs with
+    their fused epilogues, the loss, the flat SGD — running from its CUDA source on the CPU (SIMT shim + tcgen05 / TMA model):
+    (1) the default schedule agrees with the PyTorch definitions of the ops; (2) the schedule that has not run on a GPU
+    yet (implicit GEMM level 2, MN-major wgrad, packed-weight dgrad, split-K, single-launch BatchNorm reduction) produces the
+    same parameter update as the default schedule.  Measured on the authoring box: loss 2.58854 for both, update cosine
+    1.000 between the schedules, 0.975 against the definitions (bf16 rounding points), 80-120 s per step."""
+    from colearn_federated_learning_b200.fl.convnet import ConvNetTrainer
+    from colearn_federated_learning_b200.models.resnet import ResNet18
+    from colearn_federated_learning_b200.ops import conv as C
+
+    torch.manual_seed(0)
+    model = ResNet18(10)
+    flat0 = flatten_params(model).clone()
+    x, y = torch.randn(128, 3, 32, 32), torch.randint(0, 10, (128,))
+
+    def run(on_model, **kw):
+        flat = flat0.clone()
+        tr = ConvNetTrainer(model, "cpu", 128, (32, 32), **kw)
+        import contextlib
+        with (C.simt() if on_model else contextlib.nullcontext()):
+            tr.load(flat, None)
+            loss = float(tr.step(x, y, 0.05))
+            tr.store(flat, None)
+        return (flat - flat0).double(), loss
+
+    cos = lambda a, b: float((a * b).sum() / (a.norm() * b.norm()))  # noqa: E731
+    d_def, l_def = run(False)
+    d_src, l_src = run(True)
+    assert abs(l_def - l_src) < 2e-2 and cos(d_def, d_src) > 0.95
+    monkeypatch.setenv("COLEARN_CONV_FUSED_BN", "1")
+    d_new, l_new = run(True, implicit=2, wgrad_mn=True, dgrad_kn=True, split_k=1)
+    assert abs(l_new - l_src) < 1e-3 and cos(d_new, d_src) > 0.999
