@@ -98,7 +98,12 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 #endif
 
 // ---- per-layer device functions ----------------------------------------------------------------
-template <class N, int LI, bool RELU>
+// OWN_ONLY (the training kernel): threads past the last (neuron, lane) pair skip the weight reads instead of shadowing
+// the last neuron's row — their result was always discarded, but in the training loop those reads raced with the owner
+// thread's rank-1 update of that row from the previous step (no barrier separates the two by design: every weight is read
+// and written by the same thread).  Found by the CPU race check (scripts/racecheck_cpu.sh); the inference kernel keeps
+// the original form.
+template <class N, int LI, bool RELU, bool OWN_ONLY = false>
 __device__ __forceinline__ void fwd_layer(const float* __restrict__ sP, const float* __restrict__ a_in,
                                           float* __restrict__ a_out, int tid) {
   using Ly = Layer<N, LI>;
@@ -108,10 +113,12 @@ __device__ __forceinline__ void fwd_layer(const float* __restrict__ sP, const fl
   const int t = tid % T;
   const float* w = sP + Offs<N, LI>::smem + n * KP;
   float acc0 = 0.f, acc1 = 0.f;
+  if (!OWN_ONLY || valid) {
 #pragma unroll
-  for (int k = t, j = 0; k < K; k += T, ++j) {
-    if (j & 1) acc1 = fmaf(w[k], a_in[k], acc1);
-    else acc0 = fmaf(w[k], a_in[k], acc0);
+    for (int k = t, j = 0; k < K; k += T, ++j) {
+      if (j & 1) acc1 = fmaf(w[k], a_in[k], acc1);
+      else acc0 = fmaf(w[k], a_in[k], acc0);
+    }
   }
   float acc = acc0 + acc1;
 #pragma unroll
@@ -160,15 +167,15 @@ __device__ __forceinline__ void rank1_update(float* __restrict__ sP, const float
   }
 }
 
-template <class N, int LI>
+template <class N, int LI, bool OWN_ONLY = false>
 struct FwdChain {
   static __device__ __forceinline__ void run(const float* sP, const float* a0, float* acts, int tid) {
     constexpr bool last = (LI == N::L - 1);
     const float* a_in = (LI == 0) ? a0 : acts + Offs<N, LI - (LI > 0)>::act;
     float* a_out = acts + Offs<N, LI>::act;
-    fwd_layer<N, LI, !last>(sP, a_in, a_out, tid);
+    fwd_layer<N, LI, !last, OWN_ONLY>(sP, a_in, a_out, tid);
     __syncthreads();
-    if constexpr (!last) FwdChain<N, LI + 1>::run(sP, a0, acts, tid);
+    if constexpr (!last) FwdChain<N, LI + 1, OWN_ONLY>::run(sP, a0, acts, tid);
   }
 };
 
@@ -367,7 +374,7 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
       float* acts = sAct + parity * Tot::acts;
       const float inv_b = 1.f / (float)cur_batch;
 
-      FwdChain<N, 0>::run(sP, a0, acts, tid);
+      FwdChain<N, 0, true>::run(sP, a0, acts, tid);
       if (tid < 32) {
         const float v = loss_and_dz<N>(acts + Offs<N, N::L - 1>::act, sDz + Offs<N, N::L - 1>::act,
                                        yrow, hp.loss, inv_b, tid);

@@ -408,3 +408,27 @@ def test_whole_resnet18_step_from_kernel_sources_on_the_cpu_model(simt, monkeypa
     monkeypatch.setenv("COLEARN_CONV_FUSED_BN", "1")
     d_new, l_new = run(True, implicit=2, wgrad_mn=True, dgrad_kn=True, split_k=1)
     assert abs(l_new - l_src) < 1e-3 and cos(d_new, d_src) > 0.999
+
+
+def test_racecheck_of_the_simt_kernels_on_cpu(tmp_path):
+    """compute-sanitizer racecheck without a GPU (scripts/racecheck_cpu.sh): the persistent-MLP (every variant / net /
+    batch mode), elementwise, comm and BatchNorm kernels are compiled for the CPU with -fsanitize=thread and run on small
+    workloads — a shared-memory access pair that is not ordered by __syncthreads / a shuffle / a release-acquire flag would
+    be reported as a data race.  (It found one: the weights-in-shared-memory variant's idle threads used to shadow-read
+    the last neuron's row while its owner updated it; benign, fixed.)"""
+    import os
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", str(tmp_path / "probe")], input="int main(){return 0;}",
+                           capture_output=True, text=True)
+    if probe.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available")
+    p = subprocess.run(["sh", os.path.join(root, "scripts", "racecheck_cpu.sh"), str(tmp_path / "build")], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-4000:]
+    assert "WARNING: ThreadSanitizer" not in p.stdout + p.stderr
+    for part in ("mlp kernels ok", "elementwise kernels ok", "comm kernels ok", "conv kernels ok"):
+        assert part in p.stdout
