@@ -134,5 +134,39 @@ int main() {
     CK(launch_bn_reduce_finalize(fb, nullptr));
   }
   printf("conv kernels ok\n");
+  // ---- tcgen05 GEMM on the functional model: the TMA -> MMA -> epilogue pipeline is ordered by mbarriers only -------------------
+  {
+    auto bf = [](size_t n) { std::vector<__nv_bfloat16> v(n); for (auto& x : v) x = __float2bfloat16(frand() - 0.5f); return v; };
+    GemmEpilogue ep;
+    // K-major: 16 tiles on 4 CTAs (both accumulator stages, smem ring wrap-around), then split-K
+    {
+      const int M = 512, N = 512, K = 64 * 5;
+      auto a = bf((size_t)M * K), b = bf((size_t)N * K);
+      std::vector<float> out((size_t)M * N), part((size_t)3 * M * N);
+      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.out_f32 = out.data(); ep.tile_n = 128;
+      CK(launch_gemm_tcgen05(a.data(), b.data(), M, N, K, ep, nullptr));
+      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.split_k = 3; ep.split_out = part.data();
+      CK(launch_gemm_tcgen05(a.data(), b.data(), M, N, K, ep, nullptr));
+    }
+    // MN-major wgrad form with the fused SGD epilogue
+    {
+      const int Kd = 256, ac = 64, M = 128, N = 384;
+      auto a = bf((size_t)Kd * ac), b = bf((size_t)Kd * N);
+      std::vector<float> master((size_t)M * N, 1.f);
+      std::vector<__nv_bfloat16> shadow((size_t)M * N);
+      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.sgd_master = master.data(); ep.sgd_lr = 0.1f; ep.sgd_shadow = shadow.data();
+      CK(launch_gemm_tcgen05_mn(a.data(), 1, ac, b.data(), Kd, M, N, Kd, ep, nullptr));
+    }
+    // implicit-GEMM forward: 4 images of 8x8, 64 -> 64 channels
+    {
+      const int n = 4, H = 8, W = 8, C = 64, M = n * H * W, N = 128, K = 9 * C;
+      auto act = bf((size_t)M * C), wp = bf((size_t)N * 640);
+      std::vector<__nv_bfloat16> out((size_t)M * N);
+      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.out_bf16 = out.data();
+      ep.conv.mode = 1; ep.conv.C = C; ep.conv.KH = 3; ep.conv.KW = 3; ep.conv.pad = 1; ep.conv.HW = H * W; ep.conv.n_images = n;
+      CK(launch_gemm_tcgen05_conv(act.data(), n, H, W, wp.data(), N, 640, M, N, K, ep, nullptr));
+    }
+  }
+  printf("gemm kernels ok\n");
   return 0;
 }

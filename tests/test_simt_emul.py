@@ -430,5 +430,5 @@ def test_racecheck_of_the_simt_kernels_on_cpu(tmp_path):
     p = subprocess.run(["sh", os.path.join(root, "scripts", "racecheck_cpu.sh"), str(tmp_path / "build")], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, (p.stdout + p.stderr)[-4000:]
     assert "WARNING: ThreadSanitizer" not in p.stdout + p.stderr
-    for part in ("mlp kernels ok", "elementwise kernels ok", "comm kernels ok", "conv kernels ok"):
+    for part in ("mlp kernels ok", "elementwise kernels ok", "comm kernels ok", "conv kernels ok", "gemm kernels ok"):
         assert part in p.stdout
