@@ -230,6 +230,8 @@ class ConvNetTrainer:
         for cv in self.convs:
             cv.s_fwd = self._pick_split(cv.m, cv.cout_pad, cv.K_pad, min_slices=8) if self._splitk >= 2 else 1
             cv.s_wgrad = self._pick_split(cv.cout_pad, cv.K_pad, cv.m, min_slices=4) if self._splitk >= 1 else 1
+            if cv.implicit and cv.h * cv.w == 1:
+                cv.s_fwd = 1       # 1x1 images: the implicit GEMM walks the centre tap only (K = C), nothing left to split
         # fp32 partial accumulators [S, M, N]; forward and wgrad have their own (the wgrad chains may run on a side stream)
         self.kpart_f = z(max([cv.s_fwd * cv.m * cv.cout_pad for cv in self.convs if cv.s_fwd > 1] or [4]), dt=torch.float32)
         self.kpart_w = z(max([cv.s_wgrad * cv.cout_pad * cv.K_pad for cv in self.convs if cv.s_wgrad > 1] or [4]), dt=torch.float32)

@@ -537,6 +537,9 @@ struct ConvAddr {
   int n_images;    // N (a fully padded K/N block is pushed out of bounds with this)
   int b_rows_per_tap;  // mode 1 / flip 1: rows of W^T per tap (= Cin of the convolution = N of the GEMM)
   int b_mn;        // mode 1 / flip 1: the weight operand is the packed Wp[co, (tap, ci)] itself (MN-major B) instead of W^T
+  int tap_lo;      // mode 1: first filter tap of the K loop and ...
+  int tap_cnt;     // ... how many (0 = all KH*KW).  1x1 images only ever see the centre tap — every other tap's box lies
+                   // entirely in the padding — so the launcher walks that one tap (K = C instead of KH*KW*C)
 };
 struct ConvBox {
   int c, w, h, n;  // 4-D TMA coordinates of the activation box
@@ -545,7 +548,7 @@ struct ConvBox {
 // mode 1: k-block kb (64 channels of one tap) of the output tile starting at pixel m0 / output column n0
 CL_HD ConvBox conv_kblock(const ConvAddr& g, int kb, int m0, int n0) {
   const int cblocks = g.C / 64;
-  const int tap = kb / cblocks, cb = kb % cblocks;
+  const int tap = g.tap_lo + kb / cblocks, cb = kb % cblocks;
   const int kh = tap / g.KW, kw = tap % g.KW;
   ConvBox b;
   b.c = cb * 64;
@@ -556,7 +559,7 @@ CL_HD ConvBox conv_kblock(const ConvAddr& g, int kb, int m0, int n0) {
     b.b_col = cb * 64;                          // K index inside W^T's row = output channel of the convolution
     b.b_row = tap * g.b_rows_per_tap + n0;
   } else {
-    b.b_col = kb * 64;                          // k = tap*C + c, the packed weights' own column order
+    b.b_col = tap * g.C + cb * 64;              // k = tap*C + c, the packed weights' own column order
     b.b_row = n0;
   }
   return b;

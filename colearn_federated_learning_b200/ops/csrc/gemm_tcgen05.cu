@@ -960,9 +960,16 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
 }
 
 cudaError_t launch_gemm_tcgen05_conv(const void* act, int n_images, int H, int W, const void* other, int other_rows, int other_cols,
-                                     int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
-  const convops::ConvAddr& g = ep.conv;
+                                     int M, int N, int K, const GemmEpilogue& ep_in, cudaStream_t s) {
+  GemmEpilogue ep = ep_in;
+  convops::ConvAddr& g = ep.conv;
   const int HW = H * W;
+  // 1x1 images (the last ResNet stage at 32x32 input): with KH = KW = 2*pad + 1 only the centre tap overlaps the image, all
+  // other boxes are pure padding = zeros — walk that single tap (the caller still describes the full convolution)
+  const bool centre_only = g.mode == 1 && HW == 1 && g.KH == 2 * g.pad + 1 && g.KW == 2 * g.pad + 1 && g.KH * g.KW > 1 &&
+                           K == g.KH * g.KW * g.C && ep.split_k <= 1;
+  g.tap_lo = centre_only ? g.pad * g.KW + g.pad : 0;
+  g.tap_cnt = centre_only ? 1 : g.KH * g.KW;
   if ((g.mode != 1 && g.mode != 2) || g.C <= 0 || (g.C % 64) || g.KH <= 0 || g.KW <= 0 || g.pad < 0 || g.HW != HW ||
       !(HW == 1 || HW == 4 || HW == 16 || HW == 64) || W > 256 || H > 256 || g.n_images != n_images) {
     g_last_error = "implicit conv GEMM: mode 1|2, C%64==0, H*W in {1,4,16,64}, consistent geometry";
@@ -978,6 +985,7 @@ cudaError_t launch_gemm_tcgen05_conv(const void* act, int n_images, int H, int W
   if (g.mode == 1) {
     // M = pixels (whole images per 128-row tile), K = taps * C
     if (M != n_images * HW || K != g.KH * g.KW * g.C) { g_last_error = "implicit conv GEMM (A): M = N*H*W, K = KH*KW*C"; return cudaErrorInvalidValue; }
+    if (centre_only) K = g.C;
     if (g.b_mn && !g.flip) { g_last_error = "implicit conv GEMM: the MN-major weight operand is the dgrad's"; return cudaErrorInvalidValue; }
     const int need_n = (g.KH * g.KW - 1) * g.b_rows_per_tap + N;   // dgrad: last tap's block of N weight rows / columns
     if (g.flip ? (g.b_rows_per_tap <= 0 || (g.b_mn ? (other_cols < need_n || other_rows < g.C) : (other_rows < need_n || other_cols < g.C)))
