@@ -405,6 +405,7 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.ready_elem_offset = ready_elem_offset;
   ep.tile_n = (int)tile_n;
   ep.cluster = (int)cluster;
+  ep.pdl = pdl_enabled() ? 1 : 0;      // COLEARN_PDL=1: programmatic dependent launch (docs/ROUND2_NOTES.md)
   if (split_k > 1) {
     TORCH_CHECK(split_out.has_value() && split_out->is_cuda() && split_out->scalar_type() == at::kFloat && split_out->is_contiguous() &&
                 split_out->numel() >= split_k * (int64_t)M * N, "split_out must be a contiguous CUDA fp32 tensor with >= split_k*M*N elements");

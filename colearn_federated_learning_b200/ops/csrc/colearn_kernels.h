@@ -13,7 +13,47 @@
 #define COLEARN_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #define COLEARN_DYN_SMEM_UNALIGNED(type, name) extern __shared__ type name[]
 #define COLEARN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// Programmatic dependent launch (opt-in, COLEARN_PDL=1; docs/ROUND2_NOTES.md): a kernel variant compiled with the prologue
+// first waits for the grids it depends on (full completion + memory visibility), then lets ITS dependents be scheduled, so
+// the launch latency of kernel i+2 hides behind the execution of kernel i+1.  Both instructions are no-ops for a launch
+// without the programmatic attribute.
+#define COLEARN_PDL_PROLOGUE()                                          \
+  do {                                                                  \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                  \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     \
+  } while (0)
+#else
+#define COLEARN_PDL_PROLOGUE() ((void)0)
 #endif
+
+#include <cstdlib>
+namespace colearn {
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("COLEARN_PDL"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+#if defined(__CUDACC__) && !defined(COLEARN_HOST_SHIM)
+// one-argument kernels (the conv / BatchNorm / pooling family): plain launch, or the PDL variant with the attribute
+template <class Arg>
+inline cudaError_t launch_maybe_pdl(void (*plain)(const Arg), void (*pdl)(const Arg), dim3 grid, dim3 block, cudaStream_t s, const Arg& a) {
+  if (!pdl_enabled()) {
+    plain<<<grid, block, 0, s>>>(a);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, pdl, a);
+}
+#endif
+}  // namespace colearn
 
 namespace colearn {
 
@@ -228,6 +268,8 @@ struct GemmEpilogue {
   // implicit-GEMM convolution: one operand is an NHWC activation read through a 4-D tensor map (conv_ops.cuh)
   convops::ConvAddr conv;
   const void* addend;       // bf16 [M,N] added to the accumulator before the bf16/fp32 outputs (residual gradient), or nullptr
+  int pdl;                  // 1: launched with the programmatic-dependent-launch attribute; the kernel runs COLEARN_PDL_PROLOGUE
+                            // after its own set-up (barrier init, TMEM allocation, tensor-map prefetch overlap the predecessor)
 };
 // A: [M,K] bf16 row-major, B: [N,K] bf16 row-major.  M%128==0, N%128==0, K%64==0.
 cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int K,

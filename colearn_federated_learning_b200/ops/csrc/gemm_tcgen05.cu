@@ -397,6 +397,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (CL == 2) cluster_sync_all();   // the peer may multicast into my smem / arrive on my barriers from now on
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // programmatic dependent launch: everything above overlapped the predecessor's tail; nothing below may touch global
+  // memory before the grids this launch depends on have completed
+  if (ep.pdl) COLEARN_PDL_PROLOGUE();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -686,15 +689,46 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (ep.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (CL > 1) ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CL>, ta, tb, M, N, K, ep);
 #endif
+}
+
+// plain 1-CTA launch, with the programmatic-dependent-launch attribute when ep.pdl
+inline cudaError_t launch_1cta(void (*kern)(CUtensorMap, CUtensorMap, int, int, int, GemmEpilogue), int units, int smem_bytes, cudaStream_t s,
+                               const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& ep) {
+#ifndef COLEARN_HOST_SHIM
+  if (ep.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(units);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep);
+  }
+#endif
+  COLEARN_LAUNCH(kern, units, kThreads, smem_bytes, s, ta, tb, M, N, K, ep);
+  return cudaGetLastError();
 }
 
 // MN-major operands: A [K, a_cols] (AMN) or [M, K]; B [b_rows >= K, N] row-major bf16, boxes of [64 rows x 64 columns]
@@ -718,9 +752,7 @@ cudaError_t launch_mn(const void* A, int a_cols, const void* B, int b_rows, int 
   int units = num_sms[dev & 63];
   if (work < units) units = work;
   if (units < 1) units = 1;
-  void (*kern)(CUtensorMap, CUtensorMap, int, int, int, GemmEpilogue) = gemm_tcgen05_kernel<BN, 1, AMN, true>;
-  COLEARN_LAUNCH(kern, units, kThreads, C::kSmemBytes, s, ta, tb, M, N, K, ep);
-  return cudaGetLastError();
+  return launch_1cta(gemm_tcgen05_kernel<BN, 1, AMN, true>, units, C::kSmemBytes, s, ta, tb, M, N, K, ep);
 }
 
 
@@ -783,6 +815,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (ep.pdl) COLEARN_PDL_PROLOGUE();
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): my A rows + my half of the B rows, bytes credited to the leader's barrier =====
@@ -912,13 +945,15 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ep.pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, gemm_tcgen05_2sm_kernel, ta, tb, M, N, K, ep);
 #endif
 }
@@ -954,9 +989,7 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
   int units = num_sms[dev & 63];
   if (work < units) units = work;
   if (units < 1) units = 1;
-  void (*kern)(CUtensorMap, CUtensorMap, int, int, int, GemmEpilogue) = gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>;
-  COLEARN_LAUNCH(kern, units, kThreads, C::kSmemBytes, s, ta, tb, M, N, K, ep);
-  return cudaGetLastError();
+  return launch_1cta(gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>, units, C::kSmemBytes, s, ta, tb, M, N, K, ep);
 }
 
 cudaError_t launch_gemm_tcgen05_conv(const void* act, int n_images, int H, int W, const void* other, int other_rows, int other_cols,

@@ -33,7 +33,7 @@ def main():
     cfg = FitConfig(model="resnet18", loss="xent", batch_size=args.batch, epochs=1, lr=0.01, shuffle=True, seed=1)
     steps = args.samples // args.batch
     out = {"steps_per_fit": steps, "batch": args.batch,
-           "flags": {k: v for k, v in os.environ.items() if k.startswith("COLEARN_CONV_")}}
+           "flags": {k: v for k, v in os.environ.items() if k.startswith("COLEARN_CONV_") or k == "COLEARN_PDL"}}
 
     def timed(fn):
         for _ in range(2):

@@ -53,3 +53,5 @@ if ok:
     for k, v in sorted((best[2] or {}).items()):
         if k.startswith("COLEARN_CONV_") and k != "COLEARN_CONV_PATH":
             print(f'       "{k[len("COLEARN_CONV_"):]}": {v},')
+        elif k == "COLEARN_PDL":
+            print("       (+ COLEARN_PDL=1: process-wide launch attribute, see docs/ROUND2_NOTES.md 1a)")

@@ -32,7 +32,7 @@ for flags in "COLEARN_CONV_FUSED_BN=1" "COLEARN_CONV_STREAMS=1" "COLEARN_CONV_SH
              "COLEARN_CONV_WGRAD_MN=1" "COLEARN_CONV_DGRAD_KN=1" "COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_SPLITK=1" \
              "COLEARN_CONV_FUSED_BN=1 COLEARN_CONV_STREAMS=1 COLEARN_CONV_SHADOW_T=1" \
              "COLEARN_CONV_IMPLICIT=1" "COLEARN_CONV_IMPLICIT=2" "$IMP" "$IMP COLEARN_CONV_STREAMS=1" \
-             "$ALL" "$ALL COLEARN_CONV_STREAMS=1" "COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_DGRAD_KN=1 COLEARN_CONV_SPLITK=2 COLEARN_CONV_FUSED_BN=1"; do
+             "$ALL" "$ALL COLEARN_CONV_STREAMS=1" "COLEARN_PDL=1" "$IMP COLEARN_PDL=1" "COLEARN_CONV_WGRAD_MN=1 COLEARN_CONV_DGRAD_KN=1 COLEARN_CONV_SPLITK=2 COLEARN_CONV_FUSED_BN=1"; do
   tag=$(echo "$flags" | tr ' =' '__' | sed 's/COLEARN_CONV_//g')
   env $flags timeout 60 python scripts/bench_convnet.py --reps 3 --only native_eager,native_graph \
       > "gpurun_out/r2_convnet_${tag}.json" 2> "gpurun_out/r2_convnet_${tag}.err"

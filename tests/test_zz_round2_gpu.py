@@ -395,3 +395,51 @@ def test_implicit_step_matches_default_schedule(flags, monkeypatch):
     got = run()
     cos = float((got * base).sum() / (got.norm() * base.norm()))
     assert cos > 0.9 and torch.isfinite(got).all(), cos
+
+
+# ---- programmatic dependent launch (COLEARN_PDL=1): same kernels, same order, so the update must be bit-identical ------------------
+_PDL_SCRIPT = """
+import hashlib, torch
+from colearn_federated_learning_b200.fl.convnet import ConvNetTrainer
+from colearn_federated_learning_b200.models.registry import flatten_params
+from colearn_federated_learning_b200.models.resnet import ResNet18
+dev = torch.device('cuda:0')
+torch.manual_seed(0)
+x = torch.randn(256, 3, 32, 32, device=dev); y = torch.randint(0, 10, (256,), device=dev)
+torch.manual_seed(1)
+model = ResNet18(10).to(dev)
+flat = flatten_params(model)
+tr = ConvNetTrainer(model, dev, 128, (32, 32))
+tr.load(flat, model)
+for rep in range(3):
+    for lo in (0, 128):
+        tr._graph_step(x[lo:lo + 128], y[lo:lo + 128], 0.05)
+tr.store(flat, model)
+torch.cuda.synchronize()
+print('HASH', hashlib.sha256(flat.cpu().numpy().tobytes()).hexdigest(), bool(torch.isfinite(flat).all()))
+"""
+
+
+@unvalidated
+@pytest.mark.parametrize("flags", [{}, {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_DGRAD_KN": "1", "COLEARN_CONV_SPLITK": "1",
+                                        "COLEARN_CONV_FUSED_BN": "1", "COLEARN_CONV_IMPLICIT": "2"}])
+def test_programmatic_dependent_launch_is_bit_identical(flags):
+    """Every kernel of the step waits (griddepcontrol.wait) before its first global access, so enabling the attribute may
+    only move launch latency, never a value.  The flag is read once per process: two subprocesses."""
+    import subprocess
+    import sys
+    _dev()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(pdl):
+        env = dict(os.environ, **flags)
+        env.pop("COLEARN_PDL", None)
+        if pdl:
+            env["COLEARN_PDL"] = "1"
+        out = subprocess.run([sys.executable, "-c", _PDL_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][-1].split()
+        assert line[2] == "True"
+        return line[1]
+
+    assert run(False) == run(True)
