@@ -169,24 +169,38 @@ class LayerwiseMLPTrainer:
         self.launches += L + 4
         return loss
 
-    def backward(self, flat: torch.Tensor, lr: float) -> None:
-        """dgrad with the old weights first, then the (fused) update of layer l."""
+    def backward(self, flat: torch.Tensor, lr: float, produced=None) -> None:
+        """dgrad with the old weights first, then the (fused) update of layer l.
+
+        ``produced`` (:class:`ops.produced.ProducedSpec`, last step of a round only): fused wgrad → FedAvg reduce.  The
+        fused-SGD epilogues report the blocks of final parameters they wrote and everything else that finalises a piece
+        of the arena is followed by ``produced.mark`` — every arena element exactly once — so that the overlapped
+        two-shot kernel reduces layer ``l`` while layers ``l-1 … 0`` are still in their backward pass.  Wᵀ is not
+        rebuilt on that step (the next round derives it from the broadcast)."""
         L = self.L
+        end = self.offsets[L - 1][1] + self.dims[L]              # first element after the parameters (arena tail)
+        if produced is not None:
+            produced.mark(end, produced.n)
         for l in range(L - 1, -1, -1):
             if l > 0:
                 ops.gemm_bf16(self.dz[l], self.WsT[l], relu_mask=self.a[l], out_bf16=self.dz[l - 1],
-                              out_bf16_t=self.dzT[l - 1], colsum=self.dbp[l - 1])
+                              out_bf16_t=self.dzT[l - 1], colsum=self.dbp[l - 1],
+                              max_ctas=produced.max_ctas if produced is not None else 0)
             if self.exact[l]:
                 # fused SGD on the fp32 master + bf16 shadow; W^T is rebuilt by the coalesced transpose kernel
                 # (2-byte transposed stores from the epilogue cost more than a separate 64 MB pass)
-                ops.gemm_bf16(self.dzT[l], self.aT[l], sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l])
-                ops.transpose_bf16(self.Ws[l], self.WsT[l])
+                ops.gemm_bf16(self.dzT[l], self.aT[l], sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l],
+                              produced=(produced, self.offsets[l][0]) if produced is not None else None)
+                if produced is None:
+                    ops.transpose_bf16(self.Ws[l], self.WsT[l])
             else:
                 ops.gemm_bf16(self.dzT[l], self.aT[l], out_f32=self.dw_edge[l])
                 w = self._w(flat, l)
                 w.sub_(self.dw_edge[l][: w.shape[0], : w.shape[1]], alpha=lr)
                 self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
                 ops.transpose_bf16(self.Ws[l], self.WsT[l])
+                if produced is not None:
+                    produced.mark(self.offsets[l][0], self.offsets[l][0] + w.numel())
             b = self._b(flat, l)
             if l == L - 1:
                 b.sub_(self.db[l][: b.shape[0]], alpha=lr)          # head: gradient came from the loss kernel
@@ -194,6 +208,8 @@ class LayerwiseMLPTrainer:
                 ops.bias_sgd_from_partials(b, self.dbp[l], lr)       # hidden: reduce the epilogue partials + SGD
             if not self.exact[l]:
                 self.bias_p[l][: b.shape[0]].copy_(b)
+            if produced is not None:
+                produced.mark(self.offsets[l][1], self.offsets[l][1] + b.shape[0])
         self.launches += 2 * L + 4
 
     def step(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
@@ -201,15 +217,26 @@ class LayerwiseMLPTrainer:
         self.backward(flat, lr)
         return loss
 
+    def n_steps(self, n: int, cfg) -> int:
+        steps = (n // self.B) * cfg.epochs
+        if cfg.max_nr_batches and cfg.max_nr_batches > 0:
+            steps = min(steps, cfg.max_nr_batches)
+        return steps
+
     def fit(self, flat: torch.Tensor, x: torch.Tensor, y: torch.Tensor, cfg, perm: Optional[torch.Tensor],
-            ready: Optional[ReadySpec] = None, wait_chunks=None) -> torch.Tensor:
+            ready: Optional[ReadySpec] = None, wait_chunks=None, produced=None, before_last_backward=None) -> torch.Tensor:
         """Local SGD in place on ``flat`` (full batches only; a tail < batch_size is dropped).
 
         With ``ready`` (fused broadcast consumption) the order is: wait only for the chunks of the
         padded edge layers → first forward, whose GEMMs poll the per-chunk flags of the big layers
         while the rest of the broadcast is still in flight → ``wait_chunks(None)`` for everything
-        (peers must be done reading this rank's arena before SGD writes it) → W^T + backward."""
+        (peers must be done reading this rank's arena before SGD writes it) → W^T + backward.
+
+        ``produced`` + ``before_last_backward`` (fused wgrad → FedAvg reduce): the backward of the round's LAST step
+        reports what it finalises (:meth:`backward`); the callback runs right before it is queued — the engine launches
+        the overlapped two-shot kernel on its side stream there."""
         n, B = x.shape[0], self.B
+        total = self.n_steps(n, cfg)
         if ready is not None and wait_chunks is not None:
             for l in range(self.L):
                 if not self.exact[l]:
@@ -231,7 +258,10 @@ class LayerwiseMLPTrainer:
                     if wait_chunks is not None:
                         wait_chunks(None)
                     self.refresh_exact(flat, from_broadcast=True)
-                self.backward(flat, cfg.lr)
+                final = produced is not None and it == total - 1
+                if final and before_last_backward is not None:
+                    before_last_backward()
+                self.backward(flat, cfg.lr, produced if final else None)
                 it += 1
                 if limit is not None and it >= limit:
                     return last
@@ -241,7 +271,7 @@ class LayerwiseMLPTrainer:
 
     # -- CUDA graph of a whole local fit (launch-bound inner loop -> one replay per round) -----------------
     def build_round_graph(self, flat: torch.Tensor, x: torch.Tensor, y: torch.Tensor, lr: float, n_steps: int,
-                          ready: ReadySpec, n_chunks: int) -> None:
+                          ready: ReadySpec, n_chunks: int, produced=None) -> None:
         """Capture ``n_steps`` SGD steps of a *fused-broadcast* round into one CUDA graph:
 
             wait(edge-layer chunks) -> edge shadows -> [gather batch -> forward (GEMMs poll the broadcast
@@ -249,7 +279,11 @@ class LayerwiseMLPTrainer:
 
         Everything round-specific is device-resident: the epoch the flag waits compare against lives in
         ``ready.epoch_ptr``, the sample order in ``self.g_idx``.  ~45 launches + Python per step collapse
-        into one ``replay()``."""
+        into one ``replay()``.
+
+        With ``produced`` (fused wgrad → FedAvg reduce) the round is TWO graphs: everything up to the last forward, and
+        the last backward with its reports; :meth:`run_round_graph` calls ``between()`` between the two replays (the
+        engine launches the overlapped two-shot kernel there, on its side stream)."""
         ext = ops._ext.require()
         dev = flat.device
         self.g_idx = torch.zeros(n_steps, self.B, dtype=torch.long, device=dev)
@@ -276,15 +310,21 @@ class LayerwiseMLPTrainer:
                 if s_i == 0:
                     wait(None)
                     self.refresh_exact(flat, from_broadcast=True)
-                self.backward(flat, lr)
+                if produced is None or s_i < n_steps - 1:
+                    self.backward(flat, lr)
             self.g_loss.copy_(loss)
 
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             body()
+        self.graph_tail = None
+        if produced is not None:
+            self.graph_tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_tail):
+                self.backward(flat, lr, produced)
 
-    def run_round_graph(self, perm: Optional[torch.Tensor], n: int) -> torch.Tensor:
+    def run_round_graph(self, perm: Optional[torch.Tensor], n: int, between=None) -> torch.Tensor:
         """Replay the captured round on the sample order ``perm`` (int32 ``[epochs, n]`` or None)."""
         need = self.g_steps * self.B
         if perm is None:
@@ -297,4 +337,8 @@ class LayerwiseMLPTrainer:
             order = flat_perm[:need]
         self.g_idx.copy_(order.view(self.g_steps, self.B))
         self.graph.replay()
+        if getattr(self, "graph_tail", None) is not None:
+            if between is not None:
+                between()
+            self.graph_tail.replay()
         return self.g_loss

@@ -406,10 +406,10 @@ def conv_gemm(kind: str, act: torch.Tensor, other: torch.Tensor, n: int, h: int,
             geom = [1, 1, c, kh, kw, pad, h, w, n, rows_per_tap, m, rows_per_tap, taps * c, 1 if w_packed else 0]
         if simt_mod is not None:   # the kernel source on the functional tcgen05 / TMA model (csrc/tcgen05_host_model.h)
             mod.gemm_tcgen05(act, other, None, False, None, out_bf16, None, None, sgd_master, float(sgd_lr), sgd_shadow, None, None,
-                             0, int(split_k or 0), split_out, 0, False, addend, geom)
+                             0, int(split_k or 0), split_out, 0, False, addend, geom, [])
             return
         mod.gemm_tcgen05(act, other, None, False, None, out_bf16, None, None, sgd_master, float(sgd_lr), sgd_shadow, None, None,
-                         0, 0, 1, 0, 0, 0, 0, int(split_k or 0), split_out, 0, False, addend, geom)
+                         0, 0, 1, 0, 0, 0, 0, int(split_k or 0), split_out, 0, False, addend, geom, [])
         return
     # --- definitions --------------------------------------------------------------------------------------------
     x4 = nhwc_view(act, n, h, w, c)

@@ -267,7 +267,8 @@ void star_round(int64_t theta, int64_t slots, int64_t slot_stride, int64_t arriv
 void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std::vector<int64_t> chunk_flags,
                     int64_t arrive_flags, int64_t weights, int64_t theta_prev, int64_t epoch, int64_t select_mask,
                     double server_lr, int64_t n, int64_t chunk_elems, int64_t rank, int64_t n_blocks,
-                    std::vector<int64_t> peer_arrive, bool wait_all, int64_t mc_work, int64_t mc_shadow) {
+                    std::vector<int64_t> peer_arrive, bool wait_all, int64_t mc_work, int64_t mc_shadow, int64_t produced,
+                    double produced_timeout_s) {
   TwoShotArgs a;
   std::memset(&a, 0, sizeof(a));
   a.world = (int)work.size();
@@ -291,6 +292,9 @@ void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std:
   a.wait_all = wait_all ? 1 : 0;
   a.mc_work = ptr_of<float>(mc_work);
   a.mc_shadow = ptr_of<void>(mc_shadow);
+  // overlapped form (fused wgrad GEMM -> FedAvg reduce): my [world, n_chunks] table of produced epochs
+  a.produced = ptr_of<const uint32_t>(produced);
+  a.produced_timeout_ns = produced_timeout_s > 0 ? (unsigned long long)(produced_timeout_s * 1e9) : 0ull;
   check(launch_twoshot_fedavg(a, (int)n_blocks, cur_stream()), "twoshot_fedavg");
 }
 
@@ -354,6 +358,13 @@ torch::Tensor tensor_from_ptr(int64_t p, int64_t numel, int64_t dtype_code, int6
   return torch::from_blob(ptr_of<void>(p), {numel}, [](void*) {}, opts);
 }
 
+#include "produced_bindings.inc"
+void produced_mark(int64_t sig, int64_t chunk_elems, int64_t lo, int64_t hi) {
+  int shift = 0;
+  while (((int64_t)1 << shift) < chunk_elems) ++shift;
+  check(launch_produced_mark(ptr_of<const ProducedSignal>(sig), shift, lo, hi, cur_stream()), "produced_mark");
+}
+
 // ---- tcgen05 GEMM -----------------------------------------------------------------------------------------
 void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor> bias, bool relu,
                   c10::optional<torch::Tensor> relu_mask, c10::optional<torch::Tensor> out_bf16,
@@ -362,7 +373,8 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
                   c10::optional<torch::Tensor> sgd_shadow_t, c10::optional<torch::Tensor> colsum,
                   int64_t ready_flags, int64_t ready_epoch, int64_t ready_chunk_elems, int64_t ready_elem_offset, int64_t tile_n,
                   int64_t ready_epoch_ptr, int64_t cluster, int64_t split_k, c10::optional<torch::Tensor> split_out,
-                  int64_t mn_m, bool b_kn, c10::optional<torch::Tensor> addend, std::vector<int64_t> conv) {
+                  int64_t mn_m, bool b_kn, c10::optional<torch::Tensor> addend, std::vector<int64_t> conv,
+                  std::vector<int64_t> produced) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "A,B must be CUDA bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.is_contiguous() && B.is_contiguous(), "A, B must be contiguous matrices");
   // mn_m > 0: "MN-major" operands A[K, a_cols], B[K, N] (C = A^T B, M = mn_m >= a_cols);
@@ -406,6 +418,13 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.tile_n = (int)tile_n;
   ep.cluster = (int)cluster;
   ep.pdl = pdl_enabled() ? 1 : 0;      // COLEARN_PDL=1: programmatic dependent launch (docs/ROUND2_NOTES.md)
+  // produced = [ProducedSignal* (device), arena element of sgd_master[0, 0], max_ctas]: fused wgrad -> FedAvg reduce
+  if (!produced.empty()) {
+    TORCH_CHECK(produced.size() == 3, "produced = [signal_ptr, elem_offset, max_ctas]");
+    ep.produced = ptr_of<const ProducedSignal>(produced[0]);
+    ep.produced_elem_offset = produced[1];
+    ep.max_ctas = (int)produced[2];
+  }
   if (split_k > 1) {
     TORCH_CHECK(split_out.has_value() && split_out->is_cuda() && split_out->scalar_type() == at::kFloat && split_out->is_contiguous() &&
                 split_out->numel() >= split_k * (int64_t)M * N, "split_out must be a contiguous CUDA fp32 tensor with >= split_k*M*N elements");
@@ -490,6 +509,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("transpose_bf16", &transpose_bf16);
   m.def("star_round", &star_round);
   m.def("twoshot_fedavg", &twoshot_fedavg);
+  m.def("produced_signal_pack", &produced_signal_pack);
+  m.def("produced_mark", &produced_mark);
   m.def("reduce_push", &reduce_push);
   m.def("set_flag", &set_flag);
   m.def("wait_flag", &wait_flag);

@@ -148,6 +148,21 @@ cudaError_t launch_ring_matmul(const long long* A, const long long* B, long long
 cudaError_t launch_transpose_bf16(const void* in, void* out, int rows, int cols, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
+// Fused wgrad GEMM -> FedAvg reduce: per-chunk "produced" reports of the last local step (device side in produced.cuh)
+// ---------------------------------------------------------------------------------------------
+struct ProducedSignal {
+  uint32_t* count;            // local [n_chunks] element counters, zero at rest (the completing add resets its chunk)
+  uint32_t* flags[16];        // flags[o]: rank o's [world, n_chunks] table (peer pointers); I write row `rank`
+  const uint32_t* epoch_ptr;  // published value = *epoch_ptr + epoch_add (device-resident so that CUDA graphs replay)
+  int64_t n;                  // arena elements that get reported (every one exactly once per round)
+  uint32_t epoch_add;
+  int chunk_shift;            // chunk_elems = 1 << chunk_shift
+  int world, rank, n_chunks;
+};
+// every element of arena range [lo, hi) is final (biases, padded edge layers, the tail): one thread per chunk
+cudaError_t launch_produced_mark(const ProducedSignal* sig_dev, int chunk_shift, int64_t lo, int64_t hi, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
 // Cross-GPU collectives over NVLink peer memory (comm.cu)
 // ---------------------------------------------------------------------------------------------
 // Coordinator-side "star" round step for small models:
@@ -207,6 +222,10 @@ struct TwoShotArgs {
   void* mc_shadow;              // multicast alias of the bf16 shadow arena (or nullptr)
   int signal_arrive;            // fold the "local training done" signal into this kernel
   int wait_all;                 // spin at the end until every chunk of MY arena carries `epoch`
+  // overlapped mode (fused wgrad -> reduce): my [world, n_chunks] table of produced epochs.  The kernel runs NEXT TO the last
+  // local step instead of after it and waits per chunk for table[k][c] >= epoch of every selected rank k, not for arrive_flags
+  const uint32_t* produced;
+  unsigned long long produced_timeout_ns;   // trap instead of hanging when a chunk never completes (0 = wait forever)
 };
 cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s);
 
@@ -268,6 +287,11 @@ struct GemmEpilogue {
   // implicit-GEMM convolution: one operand is an NHWC activation read through a 4-D tensor map (conv_ops.cuh)
   convops::ConvAddr conv;
   const void* addend;       // bf16 [M,N] added to the accumulator before the bf16/fp32 outputs (residual gradient), or nullptr
+  // fused wgrad -> FedAvg reduce (needs sgd_master): each epilogue warp reports the block of the master matrix it finished,
+  // produced_elem_offset = arena element of master[0, 0] (see ProducedSignal)
+  const ProducedSignal* produced;
+  int64_t produced_elem_offset;
+  int max_ctas;             // > 0: cap the persistent grid (leave SMs to a communication kernel running next to the GEMM)
   int pdl;                  // 1: launched with the programmatic-dependent-launch attribute; the kernel runs COLEARN_PDL_PROLOGUE
                             // after its own set-up (barrier init, TMEM allocation, tensor-map prefetch overlap the predecessor)
 };

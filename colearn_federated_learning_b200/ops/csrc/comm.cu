@@ -21,8 +21,11 @@
 // written with st.release.sys; consumers spin with ld.acquire.sys (and add fence.proxy.async before
 // TMA reads — see gemm_tcgen05.cu).  Flags carry monotonically increasing epochs, never reset.
 #include "colearn_kernels.h"
+#include "produced.cuh"
 
 #include <cuda_bf16.h>
+
+#include <cstdio>
 #ifdef COLEARN_HOST_SHIM
 #include <stdlib.h>
 
@@ -219,6 +222,96 @@ star_round_kernel(StarRoundArgs a) {
 // belongs to rank (c % world) (interleaved ownership keeps every rank's NVLink ports busy for the
 // whole kernel and lets early layers become ready first on every peer).  A CTA processes whole
 // chunks so that it can publish the chunk's ready flag by itself.
+// one owned chunk: pull it from every selected rank, apply, push it to every rank (fp32 + bf16), publish its flag
+__device__ __forceinline__ void twoshot_chunk(const TwoShotArgs& a, const int64_t c, const float* sw, const int tid) {
+  const int64_t lo = c * a.chunk_elems;
+  const int64_t hi = (lo + a.chunk_elems < a.n) ? lo + a.chunk_elems : a.n;
+  const int64_t len4 = (hi - lo) >> 2;  // n and chunk_elems are multiples of 4
+  if (a.mc_work != nullptr) {
+    // NVLS path (all ranks selected, uniform weights): the switch sums the W copies on the way in
+    // (ingress P/W instead of (W-1)P/W) and replicates the result on the way out (egress P/W).
+    const float w = sw[0];
+    const float4* src = reinterpret_cast<const float4*>(a.mc_work) + (lo >> 2);
+    float4* dst = reinterpret_cast<float4*>(a.mc_work) + (lo >> 2);
+    uint2* dsh = a.mc_shadow ? reinterpret_cast<uint2*>(a.mc_shadow) + (lo >> 2) : nullptr;
+    for (int64_t j = tid; j < len4; j += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + u * blockDim.x < len4) v[u] = multimem_ld_reduce_f4(src + j + u * blockDim.x);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j + u * blockDim.x < len4) {
+          v[u].x *= w; v[u].y *= w; v[u].z *= w; v[u].w *= w;
+          multimem_st_f4(dst + j + u * blockDim.x, v[u]);
+          if (dsh) multimem_st_b64(dsh + j + u * blockDim.x, pack_bf16x4(v[u]));
+        }
+      }
+    }
+  } else
+  // two float4 per thread per iteration: 2 x (#selected peers) 16-byte peer loads in flight per thread
+  for (int64_t j = tid; j < len4; j += 2 * blockDim.x) {
+    const int64_t e4a = (lo >> 2) + j;
+    const int64_t jb = j + blockDim.x;
+    const bool has_b = jb < len4;
+    const int64_t e4b = (lo >> 2) + jb;
+    float4 va[8], vb[8];   // world <= 8 on an HGX box (checked by the launcher)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < a.world && ((a.select_mask >> k) & 1u)) {
+        va[k] = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4a);
+        if (has_b) vb[k] = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4b);
+      }
+    }
+    float4 acca = make_float4(0.f, 0.f, 0.f, 0.f), accb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < a.world && ((a.select_mask >> k) & 1u)) {
+        const float w = sw[k];
+        acca.x = fmaf(w, va[k].x, acca.x); acca.y = fmaf(w, va[k].y, acca.y);
+        acca.z = fmaf(w, va[k].z, acca.z); acca.w = fmaf(w, va[k].w, acca.w);
+        if (has_b) {
+          accb.x = fmaf(w, vb[k].x, accb.x); accb.y = fmaf(w, vb[k].y, accb.y);
+          accb.z = fmaf(w, vb[k].z, accb.z); accb.w = fmaf(w, vb[k].w, accb.w);
+        }
+      }
+    }
+    if (a.theta_prev != nullptr) {
+      float4 t = reinterpret_cast<float4*>(a.theta_prev)[e4a];
+      t.x = fmaf(a.server_lr, acca.x - t.x, t.x); t.y = fmaf(a.server_lr, acca.y - t.y, t.y);
+      t.z = fmaf(a.server_lr, acca.z - t.z, t.z); t.w = fmaf(a.server_lr, acca.w - t.w, t.w);
+      reinterpret_cast<float4*>(a.theta_prev)[e4a] = t;
+      acca = t;
+      if (has_b) {
+        float4 u = reinterpret_cast<float4*>(a.theta_prev)[e4b];
+        u.x = fmaf(a.server_lr, accb.x - u.x, u.x); u.y = fmaf(a.server_lr, accb.y - u.y, u.y);
+        u.z = fmaf(a.server_lr, accb.z - u.z, u.z); u.w = fmaf(a.server_lr, accb.w - u.w, u.w);
+        reinterpret_cast<float4*>(a.theta_prev)[e4b] = u;
+        accb = u;
+      }
+    }
+    const uint2 pa = pack_bf16x4(acca), pb = pack_bf16x4(accb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < a.world) {
+        st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4a, acca);
+        if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4a] = pa;
+        if (has_b) {
+          st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4b, accb);
+          if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4b] = pb;
+        }
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < a.world) {
+    __threadfence_system();
+    st_release_sys(a.chunk_flags[tid] + c, a.epoch);
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(512)
 twoshot_fedavg_kernel(TwoShotArgs a) {
   const int tid = threadIdx.x;
@@ -239,97 +332,82 @@ twoshot_fedavg_kernel(TwoShotArgs a) {
   for (int64_t oc = blockIdx.x; ; oc += gridDim.x) {
     const int64_t c = a.rank + oc * a.world;
     if (c >= n_chunks) break;
-    const int64_t lo = c * a.chunk_elems;
-    const int64_t hi = (lo + a.chunk_elems < a.n) ? lo + a.chunk_elems : a.n;
-    const int64_t len4 = (hi - lo) >> 2;  // n and chunk_elems are multiples of 4
-    if (a.mc_work != nullptr) {
-      // NVLS path (all ranks selected, uniform weights): the switch sums the W copies on the way in
-      // (ingress P/W instead of (W-1)P/W) and replicates the result on the way out (egress P/W).
-      const float w = sw[0];
-      const float4* src = reinterpret_cast<const float4*>(a.mc_work) + (lo >> 2);
-      float4* dst = reinterpret_cast<float4*>(a.mc_work) + (lo >> 2);
-      uint2* dsh = a.mc_shadow ? reinterpret_cast<uint2*>(a.mc_shadow) + (lo >> 2) : nullptr;
-      for (int64_t j = tid; j < len4; j += 4 * blockDim.x) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (j + u * blockDim.x < len4) v[u] = multimem_ld_reduce_f4(src + j + u * blockDim.x);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (j + u * blockDim.x < len4) {
-            v[u].x *= w; v[u].y *= w; v[u].z *= w; v[u].w *= w;
-            multimem_st_f4(dst + j + u * blockDim.x, v[u]);
-            if (dsh) multimem_st_b64(dsh + j + u * blockDim.x, pack_bf16x4(v[u]));
-          }
-        }
-      }
-    } else
-    // two float4 per thread per iteration: 2 x (#selected peers) 16-byte peer loads in flight per thread
-    for (int64_t j = tid; j < len4; j += 2 * blockDim.x) {
-      const int64_t e4a = (lo >> 2) + j;
-      const int64_t jb = j + blockDim.x;
-      const bool has_b = jb < len4;
-      const int64_t e4b = (lo >> 2) + jb;
-      float4 va[8], vb[8];   // world <= 8 on an HGX box (checked by the launcher)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (k < a.world && ((a.select_mask >> k) & 1u)) {
-          va[k] = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4a);
-          if (has_b) vb[k] = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4b);
-        }
-      }
-      float4 acca = make_float4(0.f, 0.f, 0.f, 0.f), accb = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (k < a.world && ((a.select_mask >> k) & 1u)) {
-          const float w = sw[k];
-          acca.x = fmaf(w, va[k].x, acca.x); acca.y = fmaf(w, va[k].y, acca.y);
-          acca.z = fmaf(w, va[k].z, acca.z); acca.w = fmaf(w, va[k].w, acca.w);
-          if (has_b) {
-            accb.x = fmaf(w, vb[k].x, accb.x); accb.y = fmaf(w, vb[k].y, accb.y);
-            accb.z = fmaf(w, vb[k].z, accb.z); accb.w = fmaf(w, vb[k].w, accb.w);
-          }
-        }
-      }
-      if (a.theta_prev != nullptr) {
-        float4 t = reinterpret_cast<float4*>(a.theta_prev)[e4a];
-        t.x = fmaf(a.server_lr, acca.x - t.x, t.x); t.y = fmaf(a.server_lr, acca.y - t.y, t.y);
-        t.z = fmaf(a.server_lr, acca.z - t.z, t.z); t.w = fmaf(a.server_lr, acca.w - t.w, t.w);
-        reinterpret_cast<float4*>(a.theta_prev)[e4a] = t;
-        acca = t;
-        if (has_b) {
-          float4 u = reinterpret_cast<float4*>(a.theta_prev)[e4b];
-          u.x = fmaf(a.server_lr, accb.x - u.x, u.x); u.y = fmaf(a.server_lr, accb.y - u.y, u.y);
-          u.z = fmaf(a.server_lr, accb.z - u.z, u.z); u.w = fmaf(a.server_lr, accb.w - u.w, u.w);
-          reinterpret_cast<float4*>(a.theta_prev)[e4b] = u;
-          accb = u;
-        }
-      }
-      const uint2 pa = pack_bf16x4(acca), pb = pack_bf16x4(accb);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (k < a.world) {
-          st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4a, acca);
-          if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4a] = pa;
-          if (has_b) {
-            st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4b, accb);
-            if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4b] = pb;
-          }
-        }
-      }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < a.world) {
-      __threadfence_system();
-      st_release_sys(a.chunk_flags[tid] + c, a.epoch);
-    }
-    __syncthreads();
+    twoshot_chunk(a, c, sw, tid);
   }
   // (3) optionally hold the stream until the whole arena of THIS rank has been refreshed by its owners
   if (a.wait_all) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < n_chunks; c += (int64_t)gridDim.x * blockDim.x)
       while (ld_acquire_sys(a.chunk_flags[a.rank] + c) < a.epoch) __nanosleep(40);
+  }
+}
+
+
+// Overlapped form (fused wgrad GEMM -> FedAvg reduce, produced.cuh): runs on a few CTAs NEXT TO the last local step.
+// Chunks are taken in whatever order the producers of all selected ranks finish them (the backward pass finalises the
+// last layers first): each CTA sweeps its owned chunks, newest-first, and processes those whose produced epochs have
+// arrived from every selected rank.
+__global__ void __launch_bounds__(512)
+twoshot_overlap_kernel(TwoShotArgs a) {
+  const int tid = threadIdx.x;
+  __shared__ float sw[16];
+  __shared__ int s_ready;
+  __shared__ unsigned long long s_done[8];      // up to 512 owned chunks per CTA and pass
+  if (tid < a.world) sw[tid] = a.weights[tid];
+  const int64_t n_chunks = (a.n + a.chunk_elems - 1) / a.chunk_elems;
+  const int64_t owned = (n_chunks - a.rank + a.world - 1) / a.world;                  // c = rank + oc * world, oc < owned
+  const int64_t mine = (owned - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;   // oc = blockIdx.x + i * gridDim.x, i < mine
+  const unsigned long long t0 = shim_globaltimer();
+  for (int64_t base = 0; base < mine; base += 512) {
+    const int cnt = (int)((mine - base < 512) ? mine - base : 512);
+    if (tid < 8) s_done[tid] = 0ull;
+    __syncthreads();
+    int left = cnt;
+    while (left > 0) {
+      int progressed = 0;
+      for (int i = cnt - 1; i >= 0; --i) {
+        if ((s_done[i >> 6] >> (i & 63)) & 1ull) continue;                         // uniform: read by all threads
+        const int64_t c = a.rank + ((int64_t)blockIdx.x + (base + i) * gridDim.x) * a.world;
+        if (tid == 0) s_ready = 1;
+        __syncthreads();
+        if (tid < a.world && ((a.select_mask >> tid) & 1u) && ld_acquire_sys(a.produced + (int64_t)tid * n_chunks + c) < a.epoch) s_ready = 0;
+        __syncthreads();
+        const int ready = s_ready;
+        __syncthreads();
+        if (!ready) continue;
+        twoshot_chunk(a, c, sw, tid);
+        if (tid == 0) s_done[i >> 6] |= 1ull << (i & 63);
+        __syncthreads();
+        --left;
+        progressed = 1;
+      }
+      if (!progressed) {
+        if (a.produced_timeout_ns != 0 && shim_globaltimer() - t0 > a.produced_timeout_ns) {
+#ifndef COLEARN_HOST_SHIM
+          if (tid == 0) printf("twoshot_overlap_kernel: rank %d block %d still waits for %d chunk(s) after %llu ns\n", a.rank, (int)blockIdx.x, left, a.produced_timeout_ns);
+          __trap();
+#else
+          abort();
+#endif
+        }
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+  }
+  if (a.wait_all) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < n_chunks; c += (int64_t)gridDim.x * blockDim.x)
+      while (ld_acquire_sys(a.chunk_flags[a.rank] + c) < a.epoch) __nanosleep(40);
+  }
+}
+
+// every element of [lo, hi) is final: one thread per chunk reports the overlap (kernel boundary = the stores are done)
+__global__ void produced_mark_kernel(const ProducedSignal* sig, int64_t lo, int64_t hi) {
+  const int64_t c = (lo >> sig->chunk_shift) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c_lo = c << sig->chunk_shift, c_hi = (c + 1) << sig->chunk_shift;
+  const int64_t b = lo > c_lo ? lo : c_lo, e = hi < c_hi ? hi : c_hi;
+  if (e > b) {
+    __threadfence_system();
+    produced_add(sig, c, (uint32_t)(e - b));
   }
 }
 
@@ -432,7 +510,20 @@ cudaError_t launch_star_round(const StarRoundArgs& a, int n_blocks, cudaStream_t
 cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s) {
   if (a.world > 8 || (a.n & 3) || (a.chunk_elems & 3)) return cudaErrorInvalidValue;
   if (n_blocks < 1) n_blocks = 1;
+  if (a.produced != nullptr) {
+    COLEARN_LAUNCH(twoshot_overlap_kernel, n_blocks, 512, 0, s, a);
+    return cudaGetLastError();
+  }
   COLEARN_LAUNCH(twoshot_fedavg_kernel, n_blocks, 512, 0, s, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_produced_mark(const ProducedSignal* sig_dev, int chunk_shift, int64_t lo, int64_t hi, cudaStream_t s) {
+  if (sig_dev == nullptr || lo < 0 || hi < lo || chunk_shift < 2 || chunk_shift > 30) return cudaErrorInvalidValue;
+  if (hi == lo) return cudaSuccess;
+  const int64_t chunks = ((hi - 1) >> chunk_shift) - (lo >> chunk_shift) + 1;
+  const int threads = 128;
+  COLEARN_LAUNCH(produced_mark_kernel, (int)((chunks + threads - 1) / threads), threads, 0, s, sig_dev, lo, hi);
   return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@
 //   warps 2-9: epilogue (2 per TMEM lane quarter)  tcgen05.ld 32x32b.x32 -> regs -> fused epilogue -> global
 //   TMEM     : 2 accumulator stages x 128 columns (epilogue of tile i overlaps mainloop of tile i+1)
 #include "colearn_kernels.h"
+#include "produced.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -546,6 +547,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+      // fused wgrad -> FedAvg reduce: this warp's 32 x BN/2 block of the master matrix is final (the __syncwarp above
+      // ordered the 32 lanes' stores before lane 0's fence)
+      if (ep.produced != nullptr && lane == 0) {
+        __threadfence_system();
+        produced_block(ep.produced, ep.produced_elem_offset, m0 + q * 32, 32, N, n0 + half * (BN / 2), BN / 2);
+      }
     }
   }
 
@@ -676,6 +683,7 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
   }
   const int work = (M / BM / CL) * (N / BN) * ((CL == 1 && ep.split_k > 1) ? ep.split_k : 1);
   int units = num_sms[dev & 63] / CL;          // persistent: one CTA (or CTA pair) per SM (pair)
+  if (ep.max_ctas > 0 && ep.max_ctas / CL < units) units = ep.max_ctas / CL;
   if (work < units) units = work;
   if (units < 1) units = 1;
 #ifdef COLEARN_HOST_SHIM
@@ -750,6 +758,7 @@ cudaError_t launch_mn(const void* A, int a_cols, const void* B, int b_rows, int 
   }
   const int work = (M / BM) * (N / BN) * (ep.split_k > 1 ? ep.split_k : 1);
   int units = num_sms[dev & 63];
+  if (ep.max_ctas > 0 && ep.max_ctas < units) units = ep.max_ctas;
   if (work < units) units = work;
   if (units < 1) units = 1;
   return launch_1cta(gemm_tcgen05_kernel<BN, 1, AMN, true>, units, C::kSmemBytes, s, ta, tb, M, N, K, ep);
@@ -904,6 +913,10 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       if (lane == 0) {
         if (leader) mbar_arrive(&bars->tmem_empty[as]);
         else mbar_arrive_remote(mapa_shared(smem_u32(&bars->tmem_empty[as]), 0u));
+        if (ep.produced != nullptr) {      // fused wgrad -> FedAvg reduce, see the 1-CTA kernel
+          __threadfence_system();
+          produced_block(ep.produced, ep.produced_elem_offset, m0 + q * 32, 32, N, n0 + half * (BN / 2), BN / 2);
+        }
       }
     }
   }
@@ -933,6 +946,7 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
   }
   const int work = (M / (2 * BM)) * (N / C::BN);
   int units = num_sms[dev & 63] / 2;
+  if (ep.max_ctas > 0 && ep.max_ctas / 2 < units) units = ep.max_ctas / 2;
   if (work < units) units = work;
   if (units < 1) units = 1;
 #ifdef COLEARN_HOST_SHIM
@@ -987,6 +1001,7 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
   }
   const int work = (M / BM) * (N / BN) * (ep.split_k > 1 ? ep.split_k : 1);
   int units = num_sms[dev & 63];
+  if (ep.max_ctas > 0 && ep.max_ctas < units) units = ep.max_ctas;
   if (work < units) units = work;
   if (units < 1) units = 1;
   return launch_1cta(gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>, units, C::kSmemBytes, s, ta, tb, M, N, K, ep);
@@ -1101,6 +1116,10 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
     return cudaErrorInvalidValue;
   }
   if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) { g_last_error = "operands must be 16-byte aligned"; return cudaErrorInvalidValue; }
+  if (ep.produced != nullptr && (ep.sgd_master == nullptr || ep.split_k > 1)) {
+    g_last_error = "produced reports come from the fused-SGD epilogue (needs sgd_master, no split_k)";
+    return cudaErrorInvalidValue;
+  }
   if (ep.split_k > 1) {
     // split-K: raw fp32 partials only, 1-CTA kernel; 128x256 tiles whenever N allows (half the B smem traffic per FLOP)
     if (ep.split_out == nullptr) { g_last_error = "split_k needs split_out"; return cudaErrorInvalidValue; }

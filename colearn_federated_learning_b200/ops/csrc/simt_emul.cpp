@@ -187,7 +187,8 @@ int64_t star_round(Tensor theta, Tensor slots, Tensor arrive, int64_t arrive_epo
 // One rank's two-shot kernel (P2P path): works [W, n] (row k = rank k's fp32 arena), shadows [W, n] bf16 or none, chunk flags
 // int32 [W, n_chunks]; `arrive` (this rank's int32 [W]) must already carry `epoch` for every selected rank.
 void twoshot_fedavg(int64_t rank, Tensor works, c10::optional<Tensor> shadows, Tensor chunk_flags, Tensor arrive, Tensor weights,
-                    c10::optional<Tensor> theta_prev, int64_t epoch, int64_t select_mask, double server_lr, int64_t chunk_elems, int64_t n_blocks) {
+                    c10::optional<Tensor> theta_prev, int64_t epoch, int64_t select_mask, double server_lr, int64_t chunk_elems, int64_t n_blocks,
+                    c10::optional<Tensor> produced, double produced_timeout_s) {
   const int W = (int)works.size(0);
   colearn::TwoShotArgs a;
   memset(&a, 0, sizeof(a));
@@ -206,6 +207,11 @@ void twoshot_fedavg(int64_t rank, Tensor works, c10::optional<Tensor> shadows, T
   a.chunk_elems = chunk_elems;
   a.world = W;
   a.rank = (int)rank;
+  if (produced.has_value()) {      // [W (owner), W (producer), n_chunks] int32: this rank's table is produced[rank]
+    TORCH_CHECK(produced->dim() == 3 && produced->size(0) == W && produced->size(1) == W && produced->is_contiguous(), "produced");
+    a.produced = reinterpret_cast<const uint32_t*>(produced->data_ptr<int>()) + rank * W * produced->size(2);
+    a.produced_timeout_ns = produced_timeout_s > 0 ? (unsigned long long)(produced_timeout_s * 1e9) : 0ull;
+  }
   {
     py::gil_scoped_release nogil;
     CK(colearn::launch_twoshot_fedavg(a, (int)n_blocks, nullptr));
@@ -220,13 +226,21 @@ void reduce_push(Tensor slots, Tensor dst, Tensor losses, Tensor loss_dst, Tenso
                                  (int)n_blocks, nullptr));
 }
 
+#include "produced_bindings.inc"
+void produced_mark(int64_t sig, int64_t chunk_elems, int64_t lo, int64_t hi) {
+  int shift = 0;
+  while (((int64_t)1 << shift) < chunk_elems) ++shift;
+  py::gil_scoped_release nogil;
+  CK(colearn::launch_produced_mark(reinterpret_cast<const colearn::ProducedSignal*>(static_cast<uintptr_t>(sig)), shift, lo, hi, nullptr));
+}
+
 // ---- gemm_tcgen05.cu on the functional tcgen05 / TMA / mbarrier model (tcgen05_host_model.h) ---------------------------------
 // Same argument meaning as bindings.cpp::gemm_tcgen05 (minus the cross-GPU ready flags and the cluster modes).
 void gemm_tcgen05(Tensor A, Tensor B, c10::optional<Tensor> bias, bool relu, c10::optional<Tensor> relu_mask, c10::optional<Tensor> out_bf16,
                   c10::optional<Tensor> out_f32, c10::optional<Tensor> out_bf16_t, c10::optional<Tensor> sgd_master, double sgd_lr,
                   c10::optional<Tensor> sgd_shadow, c10::optional<Tensor> sgd_shadow_t, c10::optional<Tensor> colsum, int64_t tile_n,
                   int64_t split_k, c10::optional<Tensor> split_out, int64_t mn_m, bool b_kn, c10::optional<Tensor> addend,
-                  std::vector<int64_t> conv) {
+                  std::vector<int64_t> conv, std::vector<int64_t> produced) {
   TORCH_CHECK(!A.is_cuda() && !B.is_cuda() && A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16 && A.is_contiguous() &&
               B.is_contiguous() && A.dim() == 2 && B.dim() == 2, "A, B: contiguous CPU bf16 matrices");
   const bool mn = mn_m > 0, is_conv = !conv.empty();
@@ -255,6 +269,12 @@ void gemm_tcgen05(Tensor A, Tensor B, c10::optional<Tensor> bias, bool relu, c10
   ep.addend = ptr(addend, at::kBFloat16, (int64_t)M * N, "addend");
   ep.ready_chunk_elems = 1;
   ep.tile_n = (int)tile_n;
+  if (!produced.empty()) {
+    TORCH_CHECK(produced.size() == 3, "produced = [signal_ptr, elem_offset, max_ctas]");
+    ep.produced = reinterpret_cast<const colearn::ProducedSignal*>(static_cast<uintptr_t>(produced[0]));
+    ep.produced_elem_offset = produced[1];
+    ep.max_ctas = (int)produced[2];
+  }
   if (split_k > 1) {
     ep.split_k = (int)split_k;
     ep.split_out = (float*)ptr(split_out, at::kFloat, split_k * (int64_t)M * N, "split_out");
@@ -322,5 +342,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ring_matmul", &ring_matmul);
   m.def("star_round", &star_round);
   m.def("twoshot_fedavg", &twoshot_fedavg);
+  m.def("produced_signal_pack", &produced_signal_pack);
+  m.def("produced_mark", &produced_mark);
   m.def("reduce_push", &reduce_push);
 }

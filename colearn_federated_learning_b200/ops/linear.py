@@ -23,7 +23,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
               ready_chunk_elems: int = 1, ready_elem_offset: int = 0, tile_n: int = 0,
               ready_epoch_ptr: int = 0, cluster: int = 0, split_k: int = 0,
               split_out: Optional[torch.Tensor] = None, mn_m: int = 0, b_kn: bool = False,
-              addend: Optional[torch.Tensor] = None) -> None:
+              addend: Optional[torch.Tensor] = None, produced=None, max_ctas: int = 0) -> None:
     """Launch the tcgen05 GEMM; results land in the provided output tensors.
 
     ``mn_m = M > 0`` selects the "MN-major" form ``C[M, N] = Aᵀ·B`` for ``a[K, a_cols]`` (``a_cols <= M``, the missing
@@ -37,7 +37,18 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
 
     ``split_k = S > 1`` (skinny problems: few output tiles, long reduction): the K range is cut into S slices that
     run as independent work units; slice ``s`` stores its raw fp32 accumulator to ``split_out[s]`` (``[S, M, N]``)
-    and no other epilogue option may be given — ``ops.conv.splitk_reduce`` sums the slices and applies the epilogue."""
+    and no other epilogue option may be given — ``ops.conv.splitk_reduce`` sums the slices and applies the epilogue.
+
+    ``produced = (ProducedSpec, elem_offset)`` (with ``sgd_master``, a view of the work arena starting at element
+    ``elem_offset``): fused wgrad → FedAvg reduce — each epilogue warp reports the block of final parameters it wrote
+    (``ops.produced``), and ``ProducedSpec.max_ctas`` caps the persistent grid so that the overlapped two-shot kernel
+    keeps its SMs; ``max_ctas`` alone caps the grid of a GEMM that only runs next to that kernel (the dgrads of the
+    last backward)."""
+    prod_arg = [0, 0, int(max_ctas)] if max_ctas else []
+    if produced is not None:
+        assert sgd_master is not None and not (split_k and split_k > 1), "produced reports come from the fused-SGD epilogue"
+        if produced[0].sig is not None:
+            prod_arg = produced[0].gemm_arg(produced[1])
     from . import conv as _conv
     # tests (ops.conv.simt()): CPU bf16 operands go to the kernel SOURCE on the functional tcgen05 / TMA / mbarrier model
     simt_mod = (_conv._EMUL["mod"] if (not a.is_cuda and _conv._EMUL["on"] and hasattr(_conv._EMUL["mod"], "gemm_tcgen05")
@@ -63,7 +74,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
     if simt_mod is not None:
         simt_mod.gemm_tcgen05(a.contiguous(), b.contiguous(), bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
                               float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(tile_n), int(split_k or 0), split_out, int(mn_m or 0),
-                              bool(b_kn), addend, [])
+                              bool(b_kn), addend, [], prod_arg)
         return
     if not a.is_cuda:
         if split_k and split_k > 1:   # same slice boundaries as the kernel: k-blocks of 64, slice s = [nkb*s/S, nkb*(s+1)/S)
@@ -90,6 +101,8 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
                 sgd_shadow.copy_(sgd_master)
             if sgd_shadow_t is not None:
                 sgd_shadow_t.copy_(sgd_master.t())
+            if produced is not None:
+                produced[0].mark(produced[1], produced[1] + sgd_master.numel())
             return
         if out_f32 is not None:
             out_f32.copy_(acc)
@@ -101,7 +114,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
     _ext.require().gemm_tcgen05(a, b, bias, bool(relu), relu_mask, out_bf16, out_f32, out_bf16_t, sgd_master,
                                 float(sgd_lr), sgd_shadow, sgd_shadow_t, colsum, int(ready_flags), int(ready_epoch),
                                 int(ready_chunk_elems), int(ready_elem_offset), int(tile_n), int(ready_epoch_ptr), int(cluster),
-                                int(split_k or 0), split_out, int(mn_m or 0), bool(b_kn), addend, [])
+                                int(split_k or 0), split_out, int(mn_m or 0), bool(b_kn), addend, [], prod_arg)
 
 
 def linear_forward(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,

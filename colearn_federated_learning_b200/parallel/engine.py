@@ -66,7 +66,7 @@ class FederatedEngine:
                  server_lr: float = 1.0, coordinator_rank: int = 0, algo: str = "auto", seed: int = 1,
                  shuffle: bool = True, chunk_elems: int = 0, bf16_shadow: bool = False,
                  round_deadline_ms: float = 0.0, clients_per_rank: int = 1,
-                 model_kwargs: Optional[Dict[str, Any]] = None) -> None:
+                 model_kwargs: Optional[Dict[str, Any]] = None, overlap_reduce: Optional[bool] = None) -> None:
         self.rank = dist.get_rank(group) if _dist_ready() else 0
         self.world = dist.get_world_size(group) if _dist_ready() else 1
         self.group = group
@@ -114,6 +114,13 @@ class FederatedEngine:
         self.clients_per_rank = max(1, int(clients_per_rank))
         self.use_graphs = os.environ.get("COLEARN_CUDA_GRAPHS", "1") != "0"
         self.use_nvls = os.environ.get("COLEARN_NVLS", "1") != "0"   # multimem.ld_reduce / multimem.st in the two-shot kernel
+        # fused wgrad GEMM -> FedAvg reduce (ops/produced.py, opt-in until measured): the two-shot kernel runs on
+        # `overlap_ctas` CTAs NEXT TO the last local backward pass and reduces chunks as the wgrad epilogues report them
+        if overlap_reduce is None:
+            overlap_reduce = os.environ.get("COLEARN_OVERLAP_REDUCE", "0") == "1"
+        self.overlap_reduce = bool(overlap_reduce) and algo == "twoshot" and backend == "fused"
+        self.overlap_ctas = max(1, int(os.environ.get("COLEARN_OVERLAP_CTAS", "16")))
+        self.overlap_timeout_s = float(os.environ.get("COLEARN_OVERLAP_TIMEOUT_S", "20"))
         self.epoch = 0          # monotonically increasing flag epoch (never reset)
         self.rounds_done = 0
         self.x: Optional[torch.Tensor] = None
@@ -142,6 +149,8 @@ class FederatedEngine:
                       "flags": (64, torch.int32), "losses": (2 * W, torch.float32)}
             if self.bf16_shadow:
                 layout["shadow"] = (P4, torch.bfloat16)
+            if self.overlap_reduce:
+                layout["produced"] = (W * self.n_chunks, torch.int32)   # [producer rank, chunk] epochs of the chunks I own
         self.arena = SymmetricArena(layout, self.device, self.group)
         self.ext = ops._ext.require()
         self.grid_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
@@ -380,10 +389,27 @@ class FederatedEngine:
                 self._lw = LayerwiseMLPTrainer(self.spec, self.theta[: self.P], self.cfg.batch_size, shadow=shadow)
         return self._lw
 
-    def _local_train_inplace(self, round_idx: int, epoch: int) -> torch.Tensor:
+    def _produced_spec(self):
+        """:class:`ops.produced.ProducedSpec` of this rank (fused wgrad -> reduce), or None when the mode is off / unusable."""
+        if not self.overlap_reduce or self._layerwise_trainer() is None:
+            return None
+        if getattr(self, "_prod", None) is None:
+            from ..ops.produced import ProducedSpec
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            self.prod_count = torch.zeros(self.n_chunks, dtype=torch.int32, device=self.device)
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+            self._prod = ProducedSpec.device(self.ext, self.prod_count, self.arena.peer_ptrs("produced"), self.epoch_dev, 1,
+                                             chunk_elems=self.chunk_elems, n=self.P4, rank=self.rank,
+                                             max_ctas=max(8, sms - self.overlap_ctas))
+        return self._prod
+
+    def _local_train_inplace(self, round_idx: int, epoch: int, produced=None, overlapped=None) -> torch.Tensor:
         """Local fit in place on the work arena.  Wide MLPs: tcgen05 layer-wise trainer whose first
         forward GEMMs consume the previous round's broadcast chunk by chunk (flags of ``epoch-1``);
-        everything else: torch autograd (cuDNN convs) + this repo's loss / SGD kernels."""
+        everything else: torch autograd (cuDNN convs) + this repo's loss / SGD kernels.
+
+        ``produced`` / ``overlapped`` (fused wgrad -> FedAvg reduce): the last backward reports what it finalises and
+        ``overlapped()`` — the launch of the two-shot kernel on the side stream — runs right before it is queued."""
         flat = self.theta[: self.P]
         lw = self._layerwise_trainer()
         if lw is None:
@@ -408,10 +434,15 @@ class FederatedEngine:
                     steps = min(steps, self.cfg.max_nr_batches)
                 self.ext.set_flag(self.epoch_dev.data_ptr(), epoch - 1)
                 lw.build_round_graph(flat, xs, self.y, self.cfg.lr, steps,
-                                     ReadySpec(cf_ptr, self.chunk_elems, 0, self.epoch_dev.data_ptr()), self.n_chunks)
+                                     ReadySpec(cf_ptr, self.chunk_elems, 0, self.epoch_dev.data_ptr()), self.n_chunks,
+                                     produced=self._produced_spec())
             self.ext.set_flag(self.epoch_dev.data_ptr(), epoch - 1)
-            last = lw.run_round_graph(perm, n)
-            self._last_path = "layerwise+fused_bcast+cuda_graph"
+            if produced is None and getattr(lw, "graph_tail", None) is not None:
+                # a round without the overlap (partial selection) on a trainer captured for it: the reports are made anyway
+                # (counters return to zero, the tables are simply not read); the classic two-shot follows in stream order
+                overlapped = None
+            last = lw.run_round_graph(perm, n, between=overlapped)
+            self._last_path = "layerwise+fused_bcast+cuda_graph" + ("+overlap_reduce" if produced is not None else "")
             self._train_launches = 3                     # epoch flag, sample order copy, graph replay
             return last
         ready = ReadySpec(cf_ptr, self.chunk_elems, epoch - 1) if fused else None
@@ -427,8 +458,10 @@ class FederatedEngine:
         if not fused:
             wait_chunks(None)
         before = lw.launches
-        last = lw.fit(flat, xs, self.y, self.cfg, perm, ready, wait_chunks)
-        self._last_path = "layerwise+fused_bcast" if fused else "layerwise"
+        if produced is not None:
+            self.ext.set_flag(self.epoch_dev.data_ptr(), epoch - 1)      # the reports publish *epoch_dev + 1
+        last = lw.fit(flat, xs, self.y, self.cfg, perm, ready, wait_chunks, produced=produced, before_last_backward=overlapped)
+        self._last_path = ("layerwise+fused_bcast" if fused else "layerwise") + ("+overlap_reduce" if produced is not None else "")
         self._train_launches = lw.launches - before
         return last
 
@@ -460,24 +493,44 @@ class FederatedEngine:
                     self.set_local_data(self.x, self.y)
                 self.x.copy_(hx, non_blocking=True)
                 self.y.copy_(hy.view(-1, 1), non_blocking=True)
-            if (masks[i] >> r) & 1:
-                self._train_launches = 0
-                last = self._local_train_inplace(self.rounds_done + i, e)
-                losses_log[i, r, 0] = last
-                losses_log[i, r, 1] = last
-                launches += self._train_launches
-            elif e > 1:
-                ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e - 1)
             wts = self._round_weights(masks[i])
             self.weights_dev[:W].copy_(torch.tensor(wts, dtype=torch.float32), non_blocking=True)
             need_wait = read_back or i == rounds - 1   # otherwise the next round's consumer polls the flags
             sel_w = [w for k, w in enumerate(wts) if (masks[i] >> k) & 1]
             nvls = (self.use_nvls and arena.has_multicast and masks[i] == (1 << W) - 1 and W > 1
                     and max(sel_w) - min(sel_w) < 1e-7)
-            ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
-                               0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, n_blocks, arrive_ptrs, need_wait,
-                               arena.mc_ptr("work") if nvls else 0,
-                               arena.mc_ptr("shadow") if (nvls and self.bf16_shadow) else 0)
+
+            def twoshot(blocks: int, produced_ptr: int):
+                ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
+                                   0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, blocks,
+                                   arrive_ptrs if not produced_ptr else [], need_wait,
+                                   arena.mc_ptr("work") if nvls else 0,
+                                   arena.mc_ptr("shadow") if (nvls and self.bf16_shadow) else 0,
+                                   produced_ptr, self.overlap_timeout_s if produced_ptr else 0.0)
+
+            # fused wgrad -> FedAvg reduce: every rank trains this round, so every rank's last backward reports its chunks
+            prod = self._produced_spec() if masks[i] == (1 << W) - 1 else None
+            launched = [False]
+
+            def overlapped():
+                main = torch.cuda.current_stream(dev)
+                self.comm_stream.wait_stream(main)          # weights, epoch flag and the steps before the last backward
+                with torch.cuda.stream(self.comm_stream):
+                    twoshot(self.overlap_ctas, arena.ptr("produced"))
+                launched[0] = True
+
+            if (masks[i] >> r) & 1:
+                self._train_launches = 0
+                last = self._local_train_inplace(self.rounds_done + i, e, prod, overlapped if prod is not None else None)
+                losses_log[i, r, 0] = last
+                losses_log[i, r, 1] = last
+                launches += self._train_launches
+            elif e > 1:
+                ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e - 1)
+            if launched[0]:
+                torch.cuda.current_stream(dev).wait_stream(self.comm_stream)
+            else:
+                twoshot(n_blocks, 0)
             self._last_nvls = bool(nvls)
             launches += 1
             if read_back:

@@ -79,7 +79,7 @@ def main():
                                arena.peer_ptrs("chunk_flags"), arena.ptr("flags", None, 1), weights.data_ptr(), 0, e,
                                (1 << world) - 1, 1.0, P4, chunk, rank, n_blocks, arrive, True,
                                arena.mc_ptr("work") if use_nvls else 0,
-                               arena.mc_ptr("shadow") if (use_nvls and args.shadow) else 0)
+                               arena.mc_ptr("shadow") if (use_nvls and args.shadow) else 0, 0, 0.0)
 
         iters = 20 if P4 < (1 << 22) else 8
         ms = timed(ours, iters, world, device)

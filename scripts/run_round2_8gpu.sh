@@ -20,5 +20,12 @@ timeout 200 $TR --nproc-per-node 8 --master-port 29711 bench.py --gpus 8 --steps
     > gpurun_out/r2_8_cfg4_n8_nccl.json 2> gpurun_out/r2_8_cfg4_n8_nccl.err
 timeout 200 $TR --nproc-per-node 8 --master-port 29712 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_8_cfg2_n8.json 2> gpurun_out/r2_8_cfg2_n8.err
 timeout 200 $TR --nproc-per-node 8 --master-port 29713 bench.py --gpus 8 --steps 10 --warmup 3 --config cfg5 > gpurun_out/r2_8_cfg5_n8.json 2> gpurun_out/r2_8_cfg5_n8.err
+# fused wgrad GEMM -> FedAvg reduce (opt-in): the same cfg5 round with the two-shot kernel running next to the last backward
+COLEARN_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_multigpu.py -m gpu -q --timeout 280 -k wide_overlap > gpurun_out/r2_8_overlap_test.log 2>&1; echo "rc=$?" >> gpurun_out/r2_8_overlap_test.log
+tail -n 3 gpurun_out/r2_8_overlap_test.log
+for C in 8 16 32; do
+  COLEARN_OVERLAP_REDUCE=1 COLEARN_OVERLAP_CTAS=$C timeout 200 $TR --nproc-per-node 8 --master-port $((29720+C)) bench.py --gpus 8 --steps 10 --warmup 3 --config cfg5 \
+      > gpurun_out/r2_8_cfg5_n8_overlap$C.json 2> gpurun_out/r2_8_cfg5_n8_overlap$C.err
+done
 for f in gpurun_out/r2_8_*.json; do echo "== $f"; cut -c1-260 $f; done
 tail -n 3 gpurun_out/r2_8_cfg4_n8.err | cut -c1-300

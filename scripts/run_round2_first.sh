@@ -12,7 +12,8 @@ mkdir -p gpurun_out
 : > gpurun_out/r2_unvalidated_tests.log
 for grp in "resnet_eval" "fused_batchnorm or optional_step" "splitk_reduce or gemm_split_k or split_k_step" \
            "mn_major_operands or mn_major_b_operand or mn_major_fused" "mn_major_wgrad_step" \
-           "implicit_conv_forward" "implicit_conv_wgrad or implicit_conv_dgrad_packed" "implicit_step"; do
+           "implicit_conv_forward" "implicit_conv_wgrad or implicit_conv_dgrad_packed" "implicit_step" \
+           "programmatic_dependent_launch" "overlapped_reduce"; do
   echo "=== group: $grp" >> gpurun_out/r2_unvalidated_tests.log
   COLEARN_RUN_UNVALIDATED=1 timeout 240 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider -k "$grp" \
       >> gpurun_out/r2_unvalidated_tests.log 2>&1
@@ -51,3 +52,8 @@ timeout 80 python bench.py --config cfg4 --steps 5 --warmup 3 > gpurun_out/r2_be
 cut -c1-300 gpurun_out/r2_bench_cfg4_n1.json
 timeout 60 python bench.py --config cfg1 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg1.json 2> gpurun_out/r2_bench_cfg1.err
 cut -c1-200 gpurun_out/r2_bench_cfg1.json
+# cfg5 (wide MLP on the tcgen05 layer-wise trainer) at N=1: serial round vs fused wgrad -> FedAvg reduce (world 1 only shows the cost
+# of the reports + the capped grids; the gain needs N > 1: scripts/run_round2_8gpu.sh)
+timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1.json 2> gpurun_out/r2_bench_cfg5_n1.err
+COLEARN_OVERLAP_REDUCE=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_overlap.json 2> gpurun_out/r2_bench_cfg5_n1_overlap.err
+cut -c1-260 gpurun_out/r2_bench_cfg5_n1.json gpurun_out/r2_bench_cfg5_n1_overlap.json

@@ -1,0 +1,109 @@
+"""Fused wgrad GEMM → FedAvg reduce (ops/produced.py, csrc/produced.cuh): host-side bookkeeping on the PyTorch definitions,
+then the whole round — layer-wise trainer, epilogue reports, overlapped two-shot — from the kernel SOURCES on the CPU
+(SIMT shim + functional tcgen05 model).  The GPU run of the same path is in tests/test_zz_round2_gpu.py."""
+import copy
+
+import pytest
+import torch
+
+from colearn_federated_learning_b200 import ops
+from colearn_federated_learning_b200.fl import FitConfig
+from colearn_federated_learning_b200.fl.layerwise import LayerwiseMLPTrainer
+from colearn_federated_learning_b200.models import MLPNet, MLPSpec
+from colearn_federated_learning_b200.models.registry import flatten_params
+from colearn_federated_learning_b200.ops.produced import ProducedSpec
+
+
+def _arena(spec, seed, extra=12):
+    torch.manual_seed(seed)
+    flat = flatten_params(MLPNet(spec)).clone()
+    n = (flat.numel() + 3) // 4 * 4 + extra                     # + a tail the parameters do not cover
+    arena = torch.zeros(n)
+    arena[: flat.numel()] = flat
+    return arena, flat.numel()
+
+
+@pytest.mark.parametrize("chunk", [256, 4096, 65536])
+def test_last_backward_reports_every_arena_element_exactly_once(chunk):
+    spec = MLPSpec((10, 128, 256, 2), "none", "xent")            # edge layers (padded) + one exact layer
+    cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
+    arena, P = _arena(spec, 0)
+    base = arena.clone()
+    torch.manual_seed(1)
+    x, y = torch.rand(384, 10), torch.randint(0, 2, (384, 1)).float()
+    n = arena.numel()
+    n_chunks = (n + chunk - 1) // chunk
+    W, rank = 3, 1
+    tables = torch.zeros(W, W, n_chunks, dtype=torch.int32)
+    epoch = torch.tensor([4], dtype=torch.int32)
+    sp = ProducedSpec.reference(tables, epoch, 1, chunk_elems=chunk, n=n, rank=rank)
+    calls = []
+    tr = LayerwiseMLPTrainer(spec, arena[:P], 128)
+
+    def before_last():
+        # nothing has been reported when the overlapped two-shot is launched
+        calls.append(int(tables.abs().sum()))
+
+    tr.fit(arena[:P], x, y, cfg, None, produced=sp, before_last_backward=before_last)
+    assert calls == [0]
+    assert sp.idle()
+    for c in range(n_chunks):
+        assert int(tables[c % W, rank, c]) == 5
+    assert int((tables != 0).sum()) == n_chunks                  # nothing outside the owners' rows of this producer
+    # same parameters as a fit without the reports
+    tr2 = LayerwiseMLPTrainer(spec, base[:P], 128)
+    tr2.fit(base[:P], x, y, cfg, None)
+    assert torch.equal(arena, base)
+
+
+def test_reference_spec_rejects_double_reports():
+    tables = torch.zeros(2, 2, 4, dtype=torch.int32)
+    sp = ProducedSpec.reference(tables, torch.tensor([0], dtype=torch.int32), 1, chunk_elems=64, n=256, rank=0)
+    sp.mark(0, 100)
+    with pytest.raises(AssertionError):
+        sp.mark(60, 120)
+
+
+def test_round_from_kernel_sources_with_overlapped_reduce():
+    """Two emulated ranks, wide-MLP round: the last backward's wgrad GEMMs (kernel source on the tcgen05 model) report
+    their blocks, the overlapped two-shot kernel (kernel source on the SIMT shim) reduces on the produced tables alone;
+    result = FedAvg of two independent plain fits."""
+    from colearn_federated_learning_b200.ops import conv as conv_ops
+    simt = conv_ops.load_simt()
+    if simt is None or not hasattr(simt, "produced_mark"):
+        pytest.skip("SIMT build unavailable")
+    spec = MLPSpec((10, 128, 128, 2), "none", "xent")
+    cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
+    W, chunk = 2, 2048
+    arenas, data = [], []
+    for r in range(W):
+        a, P = _arena(spec, 0, extra=0)                            # same initial model on both ranks
+        arenas.append(a)
+        torch.manual_seed(10 + r)
+        data.append((torch.rand(256, 10), torch.randint(0, 2, (256, 1)).float()))
+    n = arenas[0].numel()
+    n_chunks = (n + chunk - 1) // chunk
+    works = torch.stack(arenas).contiguous()
+    plain = works.clone()
+    tables = torch.zeros(W, W, n_chunks, dtype=torch.int32)
+    epoch = torch.tensor([0], dtype=torch.int32)
+    with conv_ops.simt():
+        for r in range(W):
+            count = torch.zeros(n_chunks, dtype=torch.int32)
+            sp = ProducedSpec.device(simt, count, [tables[o].data_ptr() for o in range(W)], epoch, 1, chunk_elems=chunk, n=n, rank=r,
+                                     max_ctas=2)
+            tr = LayerwiseMLPTrainer(spec, works[r, :P], 128)
+            tr.fit(works[r, :P], data[r][0], data[r][1], cfg, None, produced=sp)
+            assert sp.idle()
+            tr2 = LayerwiseMLPTrainer(spec, plain[r, :P], 128)
+            tr2.fit(plain[r, :P], data[r][0], data[r][1], cfg, None)
+    torch.testing.assert_close(works, plain, rtol=0, atol=0)
+    assert int(tables.min(dim=1).values.sum()) >= 0 and all(int(tables[c % W, k, c]) == 1 for c in range(n_chunks) for k in range(W))
+    weights = torch.tensor([0.5, 0.5])
+    flags = torch.zeros(W, n_chunks, dtype=torch.int32)
+    arrive = torch.zeros(W, dtype=torch.int32)
+    for r in range(W):
+        simt.twoshot_fedavg(r, works, None, flags, arrive, weights, None, 1, 0b11, 1.0, chunk, 2, tables, 10.0)
+    want = plain.mean(0)
+    for k in range(W):
+        torch.testing.assert_close(works[k], want, rtol=1e-6, atol=1e-6)

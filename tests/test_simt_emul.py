@@ -206,7 +206,7 @@ def test_twoshot_fedavg_kernel_on_cpu(simt, server_lr):
     prevs = [prev.clone() for _ in range(W)]
     arrive = torch.full((W,), 3, dtype=torch.int32)
     for r in range(W):                                          # every rank reduces the chunks it owns and writes them everywhere
-        simt.twoshot_fedavg(r, works, shadows, flags, arrive, weights, prevs[r] if server_lr != 1.0 else None, 3, 0b1111, server_lr, chunk, 2)
+        simt.twoshot_fedavg(r, works, shadows, flags, arrive, weights, prevs[r] if server_lr != 1.0 else None, 3, 0b1111, server_lr, chunk, 2, None, 0.0)
     avg = (weights.view(-1, 1) * trained).sum(0)
     want = avg if server_lr == 1.0 else prev + server_lr * (avg - prev)
     for k in range(W):
@@ -224,7 +224,7 @@ def test_twoshot_subset_and_reduce_push_on_cpu(simt):
     weights = torch.tensor([0.5, 0.0, 0.5, 0.0])
     arrive = torch.tensor([9, 0, 9, 0], dtype=torch.int32)      # ranks 1 and 3 are not selected and never arrive
     for r in range(W):
-        simt.twoshot_fedavg(r, works, None, flags, arrive, weights, None, 9, 0b0101, 1.0, chunk, 1)
+        simt.twoshot_fedavg(r, works, None, flags, arrive, weights, None, 9, 0b0101, 1.0, chunk, 1, None, 0.0)
     for k in range(W):                                          # every rank (selected or not) receives the new model
         torch.testing.assert_close(works[k], 0.5 * (trained[0] + trained[2]), rtol=1e-5, atol=1e-5)
     # many virtual clients per GPU: local sum of C pre-scaled client models pushed as one contribution
@@ -268,7 +268,7 @@ def _gemm(simt, a, b, **kw):
     simt.gemm_tcgen05(a, b, kw.get("bias"), kw.get("relu", False), kw.get("relu_mask"), kw.get("out_bf16"), kw.get("out_f32"),
                       kw.get("out_bf16_t"), kw.get("sgd_master"), kw.get("sgd_lr", 0.0), kw.get("sgd_shadow"), kw.get("sgd_shadow_t"),
                       kw.get("colsum"), kw.get("tile_n", 0), kw.get("split_k", 0), kw.get("split_out"), kw.get("mn_m", 0),
-                      kw.get("b_kn", False), kw.get("addend"), kw.get("conv", []))
+                      kw.get("b_kn", False), kw.get("addend"), kw.get("conv", []), kw.get("produced", []))
 
 
 def _bf(*shape):
@@ -432,3 +432,87 @@ def test_racecheck_of_the_simt_kernels_on_cpu(tmp_path):
     assert "WARNING: ThreadSanitizer" not in p.stdout + p.stderr
     for part in ("mlp kernels ok", "elementwise kernels ok", "comm kernels ok", "conv kernels ok", "gemm kernels ok"):
         assert part in p.stdout
+
+
+# ---- fused wgrad GEMM -> FedAvg reduce (csrc/produced.cuh): epilogue reports + produced_mark + twoshot_overlap_kernel ----------------
+@pytest.mark.parametrize("chunk", [2048, 8192])
+def test_fused_wgrad_to_twoshot_reduce_on_cpu(simt, chunk):
+    """Two emulated ranks.  Each runs its last-step wgrad GEMM with the fused-SGD epilogue on a master matrix inside its
+    arena; the epilogue warps report finished blocks, produced_mark covers the rest of the arena, and the overlapped
+    two-shot (polling the produced tables instead of the arrive flags) then averages exactly the updated parameters."""
+    from colearn_federated_learning_b200.ops.produced import ProducedSpec
+    torch.manual_seed(11)
+    W, M, N, K = 2, 256, 256, 128
+    head, tail = 1000, 520                                      # arena = [head | master M x N | tail]; offsets not chunk-aligned
+    n = head + M * N + tail
+    assert n % 4 == 0
+    n_chunks = (n + chunk - 1) // chunk
+    works = torch.randn(W, n)
+    start = works.clone()
+    tables = torch.zeros(W, W, n_chunks, dtype=torch.int32)
+    epoch = torch.tensor([6], dtype=torch.int32)                # published value = 6 + 1
+    lr = 0.05
+    want_rank = []
+    for r in range(W):
+        count = torch.zeros(n_chunks, dtype=torch.int32)
+        flag_ptrs = [tables[o].data_ptr() for o in range(W)]
+        sp = ProducedSpec.device(simt, count, flag_ptrs, epoch, 1, chunk_elems=chunk, n=n, rank=r, max_ctas=3)
+        a, b = _bf(M, K), _bf(N, K)
+        master = works[r, head:head + M * N].view(M, N)
+        shadow = torch.zeros(M, N, dtype=torch.bfloat16)
+        _gemm(simt, a, b, sgd_master=master, sgd_lr=lr, sgd_shadow=shadow, produced=sp.gemm_arg(head))
+        w_want = start[r].clone()
+        w_want[head:head + M * N] -= lr * (a.float() @ b.float().t()).reshape(-1)
+        torch.testing.assert_close(works[r], w_want, rtol=1e-4, atol=1e-4)
+        want_rank.append(w_want)
+        # chunks fully inside the matrix are already published, the ones shared with head / tail are not
+        inside = [c for c in range(n_chunks) if c * chunk >= head and min(n, (c + 1) * chunk) <= head + M * N]
+        assert inside and all(int(tables[c % W, r, c]) == 7 for c in inside)
+        edge = [c for c in range(n_chunks) if c not in inside]
+        assert all(int(tables[c % W, r, c]) == 0 for c in edge)
+        sp.mark(0, head)
+        sp.mark(head + M * N, n)
+        assert all(int(tables[c % W, r, c]) == 7 for c in range(n_chunks)) and sp.idle()
+    # the overlapped two-shot: arrive flags are never raised, only the produced tables carry the epoch
+    weights = torch.tensor([0.25, 0.75])
+    flags = torch.zeros(W, n_chunks, dtype=torch.int32)
+    arrive = torch.zeros(W, dtype=torch.int32)
+    shadows = torch.zeros(W, n, dtype=torch.bfloat16)
+    for r in range(W):
+        simt.twoshot_fedavg(r, works, shadows, flags, arrive, weights, None, 7, 0b11, 1.0, chunk, 2, tables, 5.0)
+    want = 0.25 * want_rank[0] + 0.75 * want_rank[1]
+    for k in range(W):
+        torch.testing.assert_close(works[k], want, rtol=1e-5, atol=1e-5)
+        assert torch.equal(shadows[k], works[k].to(torch.bfloat16))
+    assert int(flags.min()) == 7
+
+
+def test_overlapped_twoshot_takes_chunks_as_they_are_produced(simt):
+    """The overlapped kernel must not wait in chunk order: a producer thread publishes the chunks newest-first (the order
+    of a backward pass) with pauses; the kernel finishes although chunk 0 only arrives last."""
+    import threading
+    import time
+    torch.manual_seed(12)
+    W, chunk, n = 2, 64, 64 * 9 + 20
+    n_chunks = (n + chunk - 1) // chunk
+    trained = torch.randn(W, n)
+    works = trained.clone()
+    tables = torch.zeros(W, W, n_chunks, dtype=torch.int32)
+    tables[:, 1, :] = 4                                          # rank 1 is done with everything
+    flags = torch.zeros(W, n_chunks, dtype=torch.int32)
+    weights = torch.tensor([0.5, 0.5])
+    arrive = torch.zeros(W, dtype=torch.int32)
+
+    def producer():
+        for c in range(n_chunks - 1, -1, -1):
+            time.sleep(0.01)
+            tables[c % W, 0, c] = 4
+
+    th = threading.Thread(target=producer)
+    th.start()
+    simt.twoshot_fedavg(0, works, None, flags, arrive, weights, None, 4, 0b11, 1.0, chunk, 2, tables, 20.0)
+    th.join()
+    simt.twoshot_fedavg(1, works, None, flags, arrive, weights, None, 4, 0b11, 1.0, chunk, 2, tables, 20.0)
+    for k in range(W):
+        torch.testing.assert_close(works[k], trained.mean(0), rtol=1e-5, atol=1e-5)
+    assert int(flags.min()) == 4
