@@ -7,6 +7,8 @@
 #define COLEARN_HOST_SHIM 1
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "colearn_kernels.h"
@@ -165,6 +167,41 @@ int main() {
       memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.out_bf16 = out.data();
       ep.conv.mode = 1; ep.conv.C = C; ep.conv.KH = 3; ep.conv.KW = 3; ep.conv.pad = 1; ep.conv.HW = H * W; ep.conv.n_images = n;
       CK(launch_gemm_tcgen05_conv(act.data(), n, H, W, wp.data(), N, 640, M, N, K, ep, nullptr));
+    }
+    // fused wgrad -> FedAvg reduce: fused-SGD epilogue with per-chunk reports into an unaligned arena, marks for the rest, then the
+    // overlapped two-shot of two ranks while a host thread publishes rank 1's chunks newest-first
+    {
+      const int W = 2, M = 256, N = 256, Kd = 128, head = 1000, tail = 520, shift = 11;
+      const int64_t n = head + (int64_t)M * N + tail, chunk = 1 << shift, n_chunks = (n + chunk - 1) / chunk;
+      std::vector<float> works((size_t)W * n, 0.5f), weights(W, 0.5f);
+      std::vector<uint32_t> tables((size_t)W * W * n_chunks, 0), count(n_chunks, 0), cflags((size_t)W * n_chunks, 0), arr(W, 0), epoch(1, 8);
+      auto a = bf((size_t)M * Kd), b = bf((size_t)N * Kd);
+      ProducedSignal sig;
+      memset(&sig, 0, sizeof(sig));
+      sig.count = count.data(); sig.epoch_ptr = epoch.data(); sig.epoch_add = 1; sig.n = n; sig.chunk_shift = shift; sig.world = W; sig.rank = 0; sig.n_chunks = (int)n_chunks;
+      for (int o = 0; o < W; ++o) sig.flags[o] = tables.data() + (size_t)o * W * n_chunks;
+      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.sgd_master = works.data() + head; ep.sgd_lr = 0.1f;
+      ep.produced = &sig; ep.produced_elem_offset = head; ep.max_ctas = 3;
+      CK(launch_gemm_tcgen05(a.data(), b.data(), M, N, Kd, ep, nullptr));
+      CK(launch_produced_mark(&sig, shift, 0, head, nullptr));
+      CK(launch_produced_mark(&sig, shift, head + (int64_t)M * N, n, nullptr));
+      for (int64_t c = 0; c < n_chunks; ++c)
+        if (tables[(size_t)(c % W) * W * n_chunks + c] != 9 || count[c] != 0) { fprintf(stderr, "chunk %lld not published\n", (long long)c); return 1; }
+      std::thread producer([&] {
+        for (int64_t c = n_chunks - 1; c >= 0; --c) {
+          std::this_thread::sleep_for(std::chrono::milliseconds(2));
+          __atomic_store_n(&tables[(size_t)(c % W) * W * n_chunks + (size_t)1 * n_chunks + c], 9u, __ATOMIC_RELEASE);
+        }
+      });
+      for (int r = 0; r < W; ++r) {
+        TwoShotArgs t;
+        memset(&t, 0, sizeof(t));
+        for (int k = 0; k < W; ++k) { t.work[k] = works.data() + (size_t)k * n; t.chunk_flags[k] = cflags.data() + (size_t)k * n_chunks; }
+        t.arrive_flags = arr.data(); t.weights = weights.data(); t.epoch = 9; t.select_mask = 3; t.server_lr = 1.f; t.n = n; t.chunk_elems = chunk;
+        t.world = W; t.rank = r; t.produced = tables.data() + (size_t)r * W * n_chunks; t.produced_timeout_ns = 20000000000ull;
+        CK(launch_twoshot_fedavg(t, 2, nullptr));
+      }
+      producer.join();
     }
   }
   printf("gemm kernels ok\n");
