@@ -418,12 +418,16 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.tile_n = (int)tile_n;
   ep.cluster = (int)cluster;
   ep.pdl = pdl_enabled() ? 1 : 0;      // COLEARN_PDL=1: programmatic dependent launch (docs/ROUND2_NOTES.md)
+  // COLEARN_GEMM_STAGED=1: line-coalesced epilogue (a 4th element of `produced` >= 0 overrides it per call)
+  static const int staged_env = (std::getenv("COLEARN_GEMM_STAGED") && std::getenv("COLEARN_GEMM_STAGED")[0] == '1') ? 1 : 0;
+  ep.staged = staged_env;
   // produced = [ProducedSignal* (device), arena element of sgd_master[0, 0], max_ctas]: fused wgrad -> FedAvg reduce
   if (!produced.empty()) {
-    TORCH_CHECK(produced.size() == 3, "produced = [signal_ptr, elem_offset, max_ctas]");
+    TORCH_CHECK(produced.size() == 3 || produced.size() == 4, "produced = [signal_ptr, elem_offset, max_ctas(, staged)]");
     ep.produced = ptr_of<const ProducedSignal>(produced[0]);
     ep.produced_elem_offset = produced[1];
     ep.max_ctas = (int)produced[2];
+    if (produced.size() == 4 && produced[3] >= 0) ep.staged = (int)produced[3];
   }
   if (split_k > 1) {
     TORCH_CHECK(split_out.has_value() && split_out->is_cuda() && split_out->scalar_type() == at::kFloat && split_out->is_contiguous() &&

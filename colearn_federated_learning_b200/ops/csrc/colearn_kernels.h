@@ -291,6 +291,7 @@ struct GemmEpilogue {
   // produced_elem_offset = arena element of master[0, 0] (see ProducedSignal)
   const ProducedSignal* produced;
   int64_t produced_elem_offset;
+  int staged;               // 1: line-coalesced epilogue through a per-warp shared-memory transpose (epilogue_chunk_staged)
   int max_ctas;             // > 0: cap the persistent grid (leave SMs to a communication kernel running next to the GEMM)
   int pdl;                  // 1: launched with the programmatic-dependent-launch attribute; the kernel runs COLEARN_PDL_PROLOGUE
                             // after its own set-up (barrier init, TMEM allocation, tensor-map prefetch overlap the predecessor)

@@ -13,7 +13,7 @@ mkdir -p gpurun_out
 for grp in "resnet_eval" "fused_batchnorm or optional_step" "splitk_reduce or gemm_split_k or split_k_step" \
            "mn_major_operands or mn_major_b_operand or mn_major_fused" "mn_major_wgrad_step" \
            "implicit_conv_forward" "implicit_conv_wgrad or implicit_conv_dgrad_packed" "implicit_step" \
-           "programmatic_dependent_launch" "overlapped_reduce"; do
+           "programmatic_dependent_launch" "overlapped_reduce" "staged_epilogue"; do
   echo "=== group: $grp" >> gpurun_out/r2_unvalidated_tests.log
   COLEARN_RUN_UNVALIDATED=1 timeout 240 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider -k "$grp" \
       >> gpurun_out/r2_unvalidated_tests.log 2>&1
@@ -57,3 +57,8 @@ cut -c1-200 gpurun_out/r2_bench_cfg1.json
 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1.json 2> gpurun_out/r2_bench_cfg5_n1.err
 COLEARN_OVERLAP_REDUCE=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_overlap.json 2> gpurun_out/r2_bench_cfg5_n1_overlap.err
 cut -c1-260 gpurun_out/r2_bench_cfg5_n1.json gpurun_out/r2_bench_cfg5_n1_overlap.json
+# row-per-thread vs line-coalesced GEMM epilogue per mode (wide-MLP layer shapes), then cfg5 with it
+timeout 120 python scripts/bench_gemm_epilogue.py > gpurun_out/r2_gemm_epilogue.json 2> gpurun_out/r2_gemm_epilogue.err
+cut -c1-1500 gpurun_out/r2_gemm_epilogue.json
+COLEARN_GEMM_STAGED=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_staged.json 2> gpurun_out/r2_bench_cfg5_n1_staged.err
+cut -c1-260 gpurun_out/r2_bench_cfg5_n1_staged.json

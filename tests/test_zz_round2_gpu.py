@@ -471,3 +471,39 @@ def test_overlapped_reduce_single_gpu_is_bit_identical(graphs, monkeypatch):
             assert int(eng.arena.tensor("produced")[: eng.n_chunks].min()) == eng.epoch
     assert paths[1].endswith("+overlap_reduce") and not paths[0].endswith("+overlap_reduce"), paths
     assert torch.isfinite(flats[1]).all() and torch.equal(flats[0], flats[1])
+
+
+# ---- line-coalesced GEMM epilogue (COLEARN_GEMM_STAGED=1 / staged=True); tests/test_simt_emul.py has the CPU evidence --------------
+@unvalidated
+@pytest.mark.parametrize("m,n,k,tile_n,cluster", [(256, 256, 192, 0, 0), (256, 256, 192, 0, 3), (512, 768, 448, 256, 1),
+                                                  (1024, 4096, 1024, 0, 0), (384, 128, 64, 128, 0)])
+def test_staged_epilogue_bit_identical_on_device(m, n, k, tile_n, cluster):
+    from colearn_federated_learning_b200 import ops
+    dev = _dev()
+    torch.manual_seed(31)
+    bf = torch.bfloat16
+    a, b = (torch.randn(m, k, device=dev) * 0.3).to(bf), (torch.randn(n, k, device=dev) * 0.3).to(bf)
+    bias, mask, addend = torch.randn(n, device=dev), torch.randn(m, n, device=dev).to(bf), torch.randn(m, n, device=dev).to(bf)
+    m0 = torch.randn(m, n, device=dev)
+
+    def run(staged):
+        kw = dict(tile_n=tile_n, cluster=cluster, staged=staged)
+        r = {}
+        o, ot = torch.zeros(m, n, device=dev, dtype=bf), torch.zeros(n, m, device=dev, dtype=bf)
+        ops.gemm_bf16(a, b, bias=bias, relu=True, out_bf16=o, out_bf16_t=ot, **kw)
+        r["fwd"], r["fwd_t"] = o, ot
+        o, ot, of, cs = torch.zeros(m, n, device=dev, dtype=bf), torch.zeros(n, m, device=dev, dtype=bf), torch.zeros(m, n, device=dev), torch.zeros(m // 32, n, device=dev)
+        ops.gemm_bf16(a, b, relu_mask=mask, addend=addend, out_bf16=o, out_bf16_t=ot, out_f32=of, colsum=cs, **kw)
+        r["dgrad"], r["dgrad_t"], r["dgrad_f"], r["colsum"] = o, ot, of, cs
+        master, sh, sht = m0.clone(), torch.zeros(m, n, device=dev, dtype=bf), torch.zeros(n, m, device=dev, dtype=bf)
+        ops.gemm_bf16(a, b, sgd_master=master, sgd_lr=0.05, sgd_shadow=sh, sgd_shadow_t=sht, **kw)
+        r["master"], r["shadow"], r["shadow_t"] = master, sh, sht
+        torch.cuda.synchronize()
+        return r
+
+    plain, staged = run(False), run(True)
+    for key in plain:
+        if key == "colsum":
+            torch.testing.assert_close(staged[key], plain[key], rtol=1e-5, atol=1e-3)
+        else:
+            assert torch.equal(staged[key], plain[key]), key
