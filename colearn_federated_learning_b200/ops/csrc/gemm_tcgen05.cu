@@ -52,6 +52,23 @@ struct Cfg {
 
 std::string g_last_error;
 
+// Opt-in limit of dynamic shared memory: operand stages + barriers, plus the staged epilogue's transpose buffers when the
+// device grants them (B200: 227 KB per CTA; 225 KB asked).  If it does not, the default epilogue keeps working and a
+// staged launch is refused.
+bool g_staged_ok[64] = {};
+inline cudaError_t configure_smem(const void* kernel, int base_bytes, int dev) {
+#ifdef COLEARN_HOST_SHIM
+  (void)kernel; (void)base_bytes;
+  g_staged_ok[dev & 63] = true;
+  return cudaSuccess;
+#else
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, base_bytes + kEpilogueStageBytes);
+  if (e == cudaSuccess) { g_staged_ok[dev & 63] = true; return e; }
+  (void)cudaGetLastError();
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, base_bytes);
+#endif
+}
+
 #ifdef COLEARN_HOST_SHIM
 #include "tcgen05_host_model.h"   // functional CPU model of mbarrier / TMA / tcgen05 / TMEM (tests)
 #else
@@ -787,11 +804,12 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes + kEpilogueStageBytes);
+    cudaError_t e = configure_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<BN, CL>), C::kSmemBytes, dev);
     if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem) failed"; return e; }
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
+  if (ep.staged && !g_staged_ok[dev & 63]) { g_last_error = "staged epilogue: the device does not grant the extra 32 KB of shared memory"; return cudaErrorInvalidValue; }
   const int work = (M / BM / CL) * (N / BN) * ((CL == 1 && ep.split_k > 1) ? ep.split_k : 1);
   int units = num_sms[dev & 63] / CL;          // persistent: one CTA (or CTA pair) per SM (pair)
   if (ep.max_ctas > 0 && ep.max_ctas / CL < units) units = ep.max_ctas / CL;
@@ -862,11 +880,12 @@ cudaError_t launch_mn(const void* A, int a_cols, const void* B, int b_rows, int 
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, AMN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes + kEpilogueStageBytes);
+    cudaError_t e = configure_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<BN, 1, AMN, true>), C::kSmemBytes, dev);
     if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem, mn) failed"; return e; }
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
+  if (ep.staged && !g_staged_ok[dev & 63]) { g_last_error = "staged epilogue: the device does not grant the extra 32 KB of shared memory"; return cudaErrorInvalidValue; }
   const int work = (M / BM) * (N / BN) * (ep.split_k > 1 ? ep.split_k : 1);
   int units = num_sms[dev & 63];
   if (ep.max_ctas > 0 && ep.max_ctas < units) units = ep.max_ctas;
@@ -1052,11 +1071,12 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes + kEpilogueStageBytes);
+    cudaError_t e = configure_smem(reinterpret_cast<const void*>(gemm_tcgen05_2sm_kernel), C::kSmemBytes, dev);
     if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem, 2sm) failed"; return e; }
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
+  if (ep.staged && !g_staged_ok[dev & 63]) { g_last_error = "staged epilogue: the device does not grant the extra 32 KB of shared memory"; return cudaErrorInvalidValue; }
   const int work = (M / (2 * BM)) * (N / C::BN);
   int units = num_sms[dev & 63] / 2;
   if (ep.max_ctas > 0 && ep.max_ctas / 2 < units) units = ep.max_ctas / 2;
@@ -1107,11 +1127,12 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes + kEpilogueStageBytes);
+    cudaError_t e = configure_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>), C::kSmemBytes, dev);
     if (e != cudaSuccess) { g_last_error = "cudaFuncSetAttribute(smem, conv) failed"; return e; }
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
+  if (ep.staged && !g_staged_ok[dev & 63]) { g_last_error = "staged epilogue: the device does not grant the extra 32 KB of shared memory"; return cudaErrorInvalidValue; }
   const int work = (M / BM) * (N / BN) * (ep.split_k > 1 ? ep.split_k : 1);
   int units = num_sms[dev & 63];
   if (ep.max_ctas > 0 && ep.max_ctas < units) units = ep.max_ctas;
