@@ -114,7 +114,6 @@ def _rank_main(rank, world, port, out_path, case):
     try:
         from colearn_federated_learning_b200 import ops
         from colearn_federated_learning_b200.data import synthetic_unsw
-        from colearn_federated_learning_b200.fl.trainer import local_fit
         from colearn_federated_learning_b200.ops import reference as R
         from colearn_federated_learning_b200.parallel import FederatedEngine
         dev = torch.device("cuda", rank)

@@ -1,12 +1,9 @@
 """Fused wgrad GEMM → FedAvg reduce (ops/produced.py, csrc/produced.cuh): host-side bookkeeping on the PyTorch definitions,
 then the whole round — layer-wise trainer, epilogue reports, overlapped two-shot — from the kernel SOURCES on the CPU
 (SIMT shim + functional tcgen05 model).  The GPU run of the same path is in tests/test_zz_round2_gpu.py."""
-import copy
-
 import pytest
 import torch
 
-from colearn_federated_learning_b200 import ops
 from colearn_federated_learning_b200.fl import FitConfig
 from colearn_federated_learning_b200.fl.layerwise import LayerwiseMLPTrainer
 from colearn_federated_learning_b200.models import MLPNet, MLPSpec
