@@ -91,7 +91,8 @@ struct SgdHyper {
   int max_steps;   // <= 0: unlimited (PySyft max_nr_batches semantics)
   int loss;        // LossKind
   float lr;
-  int variant;     // 0/2: register-resident weights (default), 1: smem-resident weights (v1)
+  int variant;     // 0/2: register-resident weights, 256 threads; 3: 128 threads (default of ops/fused_mlp.py); 4: 64 threads;
+                   // 1: smem-resident weights (v1)
 };
 
 // Returns cudaError_t from the launch.  descs lives in device memory ([n_clients]).

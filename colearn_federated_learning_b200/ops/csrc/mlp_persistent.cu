@@ -443,6 +443,12 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
 #include "mlp_v2.inc"
 #undef V2_NS
 #undef V2_NT
+// 64 threads: one thread per neuron of a 64-wide layer (no shuffle levels in the dot products, two warps per barrier)
+#define V2_NS v2_64
+#define V2_NT 64
+#include "mlp_v2.inc"
+#undef V2_NS
+#undef V2_NT
 
 // ---- batched forward (inference / evaluation) --------------------------------------------------------
 template <class N>
@@ -519,8 +525,17 @@ cudaError_t forward_t(const float* theta, const float* x, float* out, int n, cud
 
 cudaError_t launch_mlp_local_sgd(int net_kind, const ClientDesc* descs, int n_clients, SgdHyper hp,
                                  cudaStream_t stream) {
-  // variant 2 (default): register-resident weights, 256-thread CTA; 3: same with 128 threads;
+  // variant 3 (default, set by ops/fused_mlp.py): register-resident weights, 128-thread CTA; 2: same with 256 threads;
+  // 4: same with 64 threads (one thread per neuron, not yet measured);
   // 1: first version with smem-resident weights (kept for A/B measurements)
+  if (hp.variant == 4) {
+    switch (net_kind) {
+      case NET_FFNN: return v2_64::launch2<FFNNNet>(descs, n_clients, hp, stream);
+      case NET_MLP64: return v2_64::launch2<MLP64Net>(descs, n_clients, hp, stream);
+      case NET_TESTING_REMOTE: return v2_64::launch2<TestingRemoteNet>(descs, n_clients, hp, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (hp.variant == 3) {
     switch (net_kind) {
       case NET_FFNN: return v2_128::launch2<FFNNNet>(descs, n_clients, hp, stream);

@@ -23,7 +23,8 @@ NET_KINDS = {
 }
 LOSS_CODES = {"bce": 0, "sse": 1, "xent": 2, "mse": 3}
 # 3 = register-resident weights, 128-thread CTA (default: fastest measured, profiles/r1_call4_*), 2 = same with
-# 256 threads, 1 = smem-resident weights (first version, kept for A/B runs)
+# 256 threads, 4 = same with 64 threads (one thread per neuron; not yet measured), 1 = smem-resident weights (first
+# version, kept for A/B runs)
 KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "3"))
 
 PtrLike = Union[torch.Tensor, int, None]

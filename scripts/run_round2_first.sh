@@ -62,3 +62,9 @@ timeout 120 python scripts/bench_gemm_epilogue.py > gpurun_out/r2_gemm_epilogue.
 cut -c1-1500 gpurun_out/r2_gemm_epilogue.json
 COLEARN_GEMM_STAGED=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_staged.json 2> gpurun_out/r2_bench_cfg5_n1_staged.err
 cut -c1-260 gpurun_out/r2_bench_cfg5_n1_staged.json
+# headline kernel: 64-thread CTA variant of the persistent MLP kernel next to the default (128 threads)
+timeout 120 python scripts/microbench.py --only mlp --out gpurun_out/r2_microbench_mlp.json > gpurun_out/r2_microbench_mlp.log 2>&1
+grep variant gpurun_out/r2_microbench_mlp.log | cut -c1-220
+timeout 60 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_cfg2_n1.json 2> gpurun_out/r2_bench_cfg2_n1.err
+COLEARN_MLP_VARIANT=4 timeout 60 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_cfg2_n1_variant4.json 2> gpurun_out/r2_bench_cfg2_n1_variant4.err
+cut -c1-200 gpurun_out/r2_bench_cfg2_n1.json gpurun_out/r2_bench_cfg2_n1_variant4.json
