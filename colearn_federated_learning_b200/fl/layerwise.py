@@ -18,6 +18,7 @@ The 10-wide input and 2-wide head are zero-padded to tile multiples (128).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -60,8 +61,12 @@ class LayerwiseMLPTrainer:
             tr = cls._cache[key] = cls(spec, flat, batch_size)
         return tr
 
-    def __init__(self, spec: MLPSpec, flat: torch.Tensor, batch_size: int, shadow: Optional[torch.Tensor] = None) -> None:
+    def __init__(self, spec: MLPSpec, flat: torch.Tensor, batch_size: int, shadow: Optional[torch.Tensor] = None,
+                 dgrad_kn: Optional[bool] = None) -> None:
         self.spec, self.B, self.dev = spec, batch_size, flat.device
+        # opt-in (COLEARN_MLP_DGRAD_KN=1, not yet measured): the dgrad reads W_l [out, in] in place as an MN-major B operand
+        # (gemm_bf16(b_kn=True)), so no W^T copy exists: one 64 MB transpose pass per 4096 x 4096 layer and step less
+        self.dgrad_kn = (os.environ.get("COLEARN_MLP_DGRAD_KN", "0") == "1") if dgrad_kn is None else bool(dgrad_kn)
         self.dims = list(spec.dims)
         self.L = spec.n_layers
         self.offsets = spec.offsets()
@@ -82,7 +87,7 @@ class LayerwiseMLPTrainer:
                 self.Ws.append(shadow[off:off + n * k].view(n, k))   # zero-copy view of the broadcast payload
             else:
                 self.Ws.append(torch.zeros(self.kp[l + 1], self.kp[l], device=dev, dtype=bf))
-            self.WsT.append(torch.zeros(self.kp[l], self.kp[l + 1], device=dev, dtype=bf))
+            self.WsT.append(None if self.dgrad_kn else torch.zeros(self.kp[l], self.kp[l + 1], device=dev, dtype=bf))
         self.bias_p = [torch.zeros(self.kp[l + 1], device=dev) for l in range(self.L)]
         # activations (a[0] = padded input) and their transposes, gradients and their transposes
         self.a = [torch.zeros(B, self.kp[l], device=dev, dtype=bf) for l in range(self.L)]
@@ -111,6 +116,10 @@ class LayerwiseMLPTrainer:
         hi = self.offsets[l][1] + self.dims[l + 1] - 1
         return lo // chunk_elems, hi // chunk_elems
 
+    def _refresh_t(self, l: int) -> None:
+        if not self.dgrad_kn:
+            ops.transpose_bf16(self.Ws[l], self.WsT[l])
+
     def refresh_edge(self, flat: torch.Tensor) -> None:
         """Padded bf16 shadows (+ transposes, padded biases) of the layers that need padding."""
         for l in range(self.L):
@@ -119,7 +128,7 @@ class LayerwiseMLPTrainer:
             w = self._w(flat, l)
             self.Ws[l].zero_()
             self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
-            ops.transpose_bf16(self.Ws[l], self.WsT[l])
+            self._refresh_t(l)
             self.bias_p[l].zero_()
             self.bias_p[l][: self.dims[l + 1]].copy_(self._b(flat, l))
 
@@ -130,7 +139,7 @@ class LayerwiseMLPTrainer:
                 continue
             if not (from_broadcast and self.shadow_arena is not None):
                 self.Ws[l].copy_(ops.fp32_to_bf16(self._w(flat, l).contiguous().view(-1)).view_as(self.Ws[l]))
-            ops.transpose_bf16(self.Ws[l], self.WsT[l])
+            self._refresh_t(l)
 
     def refresh_shadows(self, flat: torch.Tensor, from_broadcast: bool = False) -> None:
         self.refresh_edge(flat)
@@ -183,8 +192,8 @@ class LayerwiseMLPTrainer:
             produced.mark(end, produced.n)
         for l in range(L - 1, -1, -1):
             if l > 0:
-                ops.gemm_bf16(self.dz[l], self.WsT[l], relu_mask=self.a[l], out_bf16=self.dz[l - 1],
-                              out_bf16_t=self.dzT[l - 1], colsum=self.dbp[l - 1],
+                ops.gemm_bf16(self.dz[l], self.Ws[l] if self.dgrad_kn else self.WsT[l], b_kn=self.dgrad_kn, relu_mask=self.a[l],
+                              out_bf16=self.dz[l - 1], out_bf16_t=self.dzT[l - 1], colsum=self.dbp[l - 1],
                               max_ctas=produced.max_ctas if produced is not None else 0)
             if self.exact[l]:
                 # fused SGD on the fp32 master + bf16 shadow; W^T is rebuilt by the coalesced transpose kernel
@@ -192,13 +201,13 @@ class LayerwiseMLPTrainer:
                 ops.gemm_bf16(self.dzT[l], self.aT[l], sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l],
                               produced=(produced, self.offsets[l][0]) if produced is not None else None)
                 if produced is None:
-                    ops.transpose_bf16(self.Ws[l], self.WsT[l])
+                    self._refresh_t(l)
             else:
                 ops.gemm_bf16(self.dzT[l], self.aT[l], out_f32=self.dw_edge[l])
                 w = self._w(flat, l)
                 w.sub_(self.dw_edge[l][: w.shape[0], : w.shape[1]], alpha=lr)
                 self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
-                ops.transpose_bf16(self.Ws[l], self.WsT[l])
+                self._refresh_t(l)
                 if produced is not None:
                     produced.mark(self.offsets[l][0], self.offsets[l][0] + w.numel())
             b = self._b(flat, l)

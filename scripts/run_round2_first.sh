@@ -23,7 +23,7 @@ if want tests; then
   for grp in "resnet_eval" "fused_batchnorm or optional_step" "splitk_reduce or gemm_split_k or split_k_step" \
              "mn_major_operands or mn_major_b_operand or mn_major_fused" "mn_major_wgrad_step" \
              "implicit_conv_forward" "implicit_conv_wgrad or implicit_conv_dgrad_packed" "implicit_step" \
-             "programmatic_dependent_launch" "overlapped_reduce" "staged_epilogue"; do
+             "programmatic_dependent_launch" "overlapped_reduce" "staged_epilogue" "weights_in_place"; do
     echo "=== group: $grp" >> gpurun_out/r2_unvalidated_tests.log
     COLEARN_RUN_UNVALIDATED=1 timeout 240 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider -k "$grp" \
         >> gpurun_out/r2_unvalidated_tests.log 2>&1
@@ -78,6 +78,9 @@ if want gemm; then
   cut -c1-1500 gpurun_out/r2_gemm_epilogue.json
   COLEARN_GEMM_STAGED=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_staged.json 2> gpurun_out/r2_bench_cfg5_n1_staged.err
   cut -c1-260 gpurun_out/r2_bench_cfg5_n1_staged.json
+  COLEARN_MLP_DGRAD_KN=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_dgradkn.json 2> gpurun_out/r2_bench_cfg5_n1_dgradkn.err
+  COLEARN_MLP_DGRAD_KN=1 COLEARN_GEMM_STAGED=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_dgradkn_staged.json 2> gpurun_out/r2_bench_cfg5_n1_dgradkn_staged.err
+  cut -c1-260 gpurun_out/r2_bench_cfg5_n1_dgradkn.json gpurun_out/r2_bench_cfg5_n1_dgradkn_staged.json
   # headline kernel: 64-thread CTA variant of the persistent MLP kernel next to the default (128 threads)
   timeout 120 python scripts/microbench.py --only mlp --out gpurun_out/r2_microbench_mlp.json > gpurun_out/r2_microbench_mlp.log 2>&1
   grep variant gpurun_out/r2_microbench_mlp.log | cut -c1-220

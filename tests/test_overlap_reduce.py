@@ -104,3 +104,25 @@ def test_round_from_kernel_sources_with_overlapped_reduce():
     want = plain.mean(0)
     for k in range(W):
         torch.testing.assert_close(works[k], want, rtol=1e-6, atol=1e-6)
+
+
+# ---- layer-wise trainer without W^T copies (COLEARN_MLP_DGRAD_KN=1): dgrad reads W_l in place as an MN-major B operand -------------
+def test_layerwise_dgrad_against_weights_in_place():
+    from colearn_federated_learning_b200.ops import conv as conv_ops
+    spec = MLPSpec((10, 128, 256, 128, 2), "none", "xent")
+    cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
+    torch.manual_seed(5)
+    x, y = torch.rand(256, 10), torch.randint(0, 2, (256, 1)).float()
+    a0, P = _arena(spec, 3, extra=0)
+    a1, a2 = a0.clone(), a0.clone()
+    LayerwiseMLPTrainer(spec, a0[:P], 128, dgrad_kn=False).fit(a0[:P], x, y, cfg, None)
+    tr = LayerwiseMLPTrainer(spec, a1[:P], 128, dgrad_kn=True)
+    assert all(t is None for t in tr.WsT)                       # no transposed copies exist
+    tr.fit(a1[:P], x, y, cfg, None)
+    assert torch.equal(a0, a1)                                   # definitions: same products, same order
+    simt = conv_ops.load_simt()
+    if simt is None or not hasattr(simt, "gemm_tcgen05"):
+        pytest.skip("SIMT build unavailable")
+    with conv_ops.simt():                                        # kernel source: MN-major B operand on the tcgen05 model
+        LayerwiseMLPTrainer(spec, a2[:P], 128, dgrad_kn=True).fit(a2[:P], x, y, cfg, None)
+    torch.testing.assert_close(a2, a0, rtol=2e-3, atol=2e-3)

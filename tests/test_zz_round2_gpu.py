@@ -507,3 +507,26 @@ def test_staged_epilogue_bit_identical_on_device(m, n, k, tile_n, cluster):
             torch.testing.assert_close(staged[key], plain[key], rtol=1e-5, atol=1e-3)
         else:
             assert torch.equal(staged[key], plain[key]), key
+
+
+@unvalidated
+def test_layerwise_trainer_dgrad_against_weights_in_place_on_device():
+    """COLEARN_MLP_DGRAD_KN=1: the wide-MLP dgrad reads W_l in place (MN-major B operand) — no W^T copies, no transposes."""
+    from colearn_federated_learning_b200.fl import FitConfig
+    from colearn_federated_learning_b200.fl.layerwise import LayerwiseMLPTrainer
+    from colearn_federated_learning_b200.models import MLPNet, MLPSpec
+    dev = _dev()
+    torch.manual_seed(0)
+    spec = MLPSpec((10, 256, 512, 256, 2), "none", "xent")
+    flat0 = flatten_params(MLPNet(spec)).clone().to(dev)
+    x, y = torch.rand(384, 10, device=dev), torch.randint(0, 2, (384, 1), device=dev).float()
+    cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
+    outs = []
+    for kn in (False, True):
+        flat = flat0.clone()
+        tr = LayerwiseMLPTrainer(spec, flat, 128, dgrad_kn=kn)
+        tr.fit(flat, x, y, cfg, None)
+        torch.cuda.synchronize()
+        outs.append(flat)
+    assert torch.isfinite(outs[1]).all()
+    assert float((outs[0] - outs[1]).abs().max()) < 2e-3 * max(1.0, float(outs[0].abs().max()))
