@@ -91,7 +91,7 @@ struct SgdHyper {
   int max_steps;   // <= 0: unlimited (PySyft max_nr_batches semantics)
   int loss;        // LossKind
   float lr;
-  int variant;     // 0/2: register-resident weights, 256 threads; 3: 128 threads (default of ops/fused_mlp.py); 4: 64 threads;
+  int variant;     // 0/2: register-resident weights, 256 threads; 3: 128 threads (default of ops/fused_mlp.py); 4: 64 threads; 5: 128 threads, blocked slices;
                    // 1: smem-resident weights (v1)
 };
 

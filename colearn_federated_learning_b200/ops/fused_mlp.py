@@ -23,7 +23,8 @@ NET_KINDS = {
 }
 LOSS_CODES = {"bce": 0, "sse": 1, "xent": 2, "mse": 3}
 # 3 = register-resident weights, 128-thread CTA (default: fastest measured, profiles/r1_call4_*), 2 = same with
-# 256 threads, 4 = same with 64 threads (one thread per neuron; not yet measured), 1 = smem-resident weights (first
+# 256 threads, 4 = same with 64 threads (one thread per neuron; not yet measured), 5 = 128 threads with blocked reduction
+# slices (LDS.128) and pre-scaled dz (not yet measured; predicted -14 %), 1 = smem-resident weights (first
 # version, kept for A/B runs)
 KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "3"))
 

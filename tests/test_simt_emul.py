@@ -44,7 +44,7 @@ def _data(dims, loss, n, seed):
     return x, y
 
 
-CASES = [(k, loss, v, b) for k, (_, _, _, losses) in NETS.items() for loss in losses for v, b in ((3, 1), (2, 1), (1, 1), (3, 4), (4, 1), (4, 4))]
+CASES = [(k, loss, v, b) for k, (_, _, _, losses) in NETS.items() for loss in losses for v, b in ((3, 1), (2, 1), (1, 1), (3, 4), (4, 1), (4, 4), (5, 1), (5, 4))]
 
 
 @pytest.mark.parametrize("kind,loss,variant,batch", CASES)
