@@ -62,11 +62,14 @@ class LayerwiseMLPTrainer:
         return tr
 
     def __init__(self, spec: MLPSpec, flat: torch.Tensor, batch_size: int, shadow: Optional[torch.Tensor] = None,
-                 dgrad_kn: Optional[bool] = None) -> None:
+                 dgrad_kn: Optional[bool] = None, wgrad_mn: Optional[bool] = None) -> None:
         self.spec, self.B, self.dev = spec, batch_size, flat.device
         # opt-in (COLEARN_MLP_DGRAD_KN=1, not yet measured): the dgrad reads W_l [out, in] in place as an MN-major B operand
         # (gemm_bf16(b_kn=True)), so no W^T copy exists: one 64 MB transpose pass per 4096 x 4096 layer and step less
         self.dgrad_kn = (os.environ.get("COLEARN_MLP_DGRAD_KN", "0") == "1") if dgrad_kn is None else bool(dgrad_kn)
+        # opt-in (COLEARN_MLP_WGRAD_MN=1, not yet measured): the wgrad reads dz_l [B, out] and a_l [B, in] in place as MN-major
+        # operands (gemm_bf16(mn_m=...)): no transposed activations / gradients are written by the producing epilogues
+        self.wgrad_mn = (os.environ.get("COLEARN_MLP_WGRAD_MN", "0") == "1") if wgrad_mn is None else bool(wgrad_mn)
         self.dims = list(spec.dims)
         self.L = spec.n_layers
         self.offsets = spec.offsets()
@@ -91,9 +94,9 @@ class LayerwiseMLPTrainer:
         self.bias_p = [torch.zeros(self.kp[l + 1], device=dev) for l in range(self.L)]
         # activations (a[0] = padded input) and their transposes, gradients and their transposes
         self.a = [torch.zeros(B, self.kp[l], device=dev, dtype=bf) for l in range(self.L)]
-        self.aT = [torch.zeros(self.kp[l], B, device=dev, dtype=bf) for l in range(self.L)]
+        self.aT = [None if self.wgrad_mn else torch.zeros(self.kp[l], B, device=dev, dtype=bf) for l in range(self.L)]
         self.dz = [torch.zeros(B, self.kp[l + 1], device=dev, dtype=bf) for l in range(self.L)]
-        self.dzT = [torch.zeros(self.kp[l + 1], B, device=dev, dtype=bf) for l in range(self.L)]
+        self.dzT = [None if self.wgrad_mn else torch.zeros(self.kp[l + 1], B, device=dev, dtype=bf) for l in range(self.L)]
         self.logits = torch.zeros(B, self.kp[self.L], device=dev)
         self.db = [torch.zeros(self.kp[l + 1], device=dev) for l in range(self.L)]
         # bias-gradient partials written by the dgrad epilogue: one row per 32 batch rows (no atomics)
@@ -157,7 +160,8 @@ class LayerwiseMLPTrainer:
         L = self.L
         self.a[0].zero_()
         self.a[0][:, : self.dims[0]].copy_(x)
-        ops.transpose_bf16(self.a[0], self.aT[0])
+        if not self.wgrad_mn:
+            ops.transpose_bf16(self.a[0], self.aT[0])
         for l in range(L):
             kw = {}
             if ready is not None and self.exact[l] and self.shadow_arena is not None:
@@ -172,7 +176,8 @@ class LayerwiseMLPTrainer:
         loss, dlog = ops.softmax_xent(self.logits[:, :nc].contiguous(), labels)
         self.dz[L - 1].zero_()
         self.dz[L - 1][:, :nc].copy_(dlog)
-        ops.transpose_bf16(self.dz[L - 1], self.dzT[L - 1])
+        if not self.wgrad_mn:
+            ops.transpose_bf16(self.dz[L - 1], self.dzT[L - 1])
         self.db[L - 1].zero_()
         self.db[L - 1][:nc].copy_(dlog.sum(0))
         self.launches += L + 4
@@ -198,12 +203,12 @@ class LayerwiseMLPTrainer:
             if self.exact[l]:
                 # fused SGD on the fp32 master + bf16 shadow; W^T is rebuilt by the coalesced transpose kernel
                 # (2-byte transposed stores from the epilogue cost more than a separate 64 MB pass)
-                ops.gemm_bf16(self.dzT[l], self.aT[l], sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l],
-                              produced=(produced, self.offsets[l][0]) if produced is not None else None)
+                self._wgrad(l, sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l],
+                            produced=(produced, self.offsets[l][0]) if produced is not None else None)
                 if produced is None:
                     self._refresh_t(l)
             else:
-                ops.gemm_bf16(self.dzT[l], self.aT[l], out_f32=self.dw_edge[l])
+                self._wgrad(l, out_f32=self.dw_edge[l])
                 w = self._w(flat, l)
                 w.sub_(self.dw_edge[l][: w.shape[0], : w.shape[1]], alpha=lr)
                 self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
@@ -220,6 +225,13 @@ class LayerwiseMLPTrainer:
             if produced is not None:
                 produced.mark(self.offsets[l][1], self.offsets[l][1] + b.shape[0])
         self.launches += 2 * L + 4
+
+    def _wgrad(self, l: int, **epilogue) -> None:
+        """``dW_l = dz_lᵀ · a_l`` with the given epilogue: K-major operands from the transposed copies, or the MN-major form."""
+        if self.wgrad_mn:
+            ops.gemm_bf16(self.dz[l], self.a[l], mn_m=self.kp[l + 1], **epilogue)
+        else:
+            ops.gemm_bf16(self.dzT[l], self.aT[l], **epilogue)
 
     def step(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
         loss = self.forward(flat, x, labels)

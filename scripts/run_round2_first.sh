@@ -80,6 +80,8 @@ if want gemm; then
   cut -c1-260 gpurun_out/r2_bench_cfg5_n1_staged.json
   COLEARN_MLP_DGRAD_KN=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_dgradkn.json 2> gpurun_out/r2_bench_cfg5_n1_dgradkn.err
   COLEARN_MLP_DGRAD_KN=1 COLEARN_GEMM_STAGED=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_dgradkn_staged.json 2> gpurun_out/r2_bench_cfg5_n1_dgradkn_staged.err
+  COLEARN_MLP_DGRAD_KN=1 COLEARN_MLP_WGRAD_MN=1 COLEARN_GEMM_STAGED=1 timeout 80 python bench.py --config cfg5 --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg5_n1_untransposed_staged.json 2> gpurun_out/r2_bench_cfg5_n1_untransposed_staged.err
+  cut -c1-260 gpurun_out/r2_bench_cfg5_n1_untransposed_staged.json
   cut -c1-260 gpurun_out/r2_bench_cfg5_n1_dgradkn.json gpurun_out/r2_bench_cfg5_n1_dgradkn_staged.json
   # headline kernel: 64-thread CTA variant of the persistent MLP kernel next to the default (128 threads)
   timeout 120 python scripts/microbench.py --only mlp --out gpurun_out/r2_microbench_mlp.json > gpurun_out/r2_microbench_mlp.log 2>&1

@@ -126,3 +126,25 @@ def test_layerwise_dgrad_against_weights_in_place():
     with conv_ops.simt():                                        # kernel source: MN-major B operand on the tcgen05 model
         LayerwiseMLPTrainer(spec, a2[:P], 128, dgrad_kn=True).fit(a2[:P], x, y, cfg, None)
     torch.testing.assert_close(a2, a0, rtol=2e-3, atol=2e-3)
+
+
+def test_layerwise_wgrad_from_untransposed_operands():
+    """COLEARN_MLP_WGRAD_MN=1 (+ DGRAD_KN): no transposed activation / gradient / weight copy exists any more."""
+    from colearn_federated_learning_b200.ops import conv as conv_ops
+    spec = MLPSpec((10, 128, 256, 128, 2), "none", "xent")
+    cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
+    torch.manual_seed(6)
+    x, y = torch.rand(256, 10), torch.randint(0, 2, (256, 1)).float()
+    a0, P = _arena(spec, 4, extra=0)
+    a1, a2 = a0.clone(), a0.clone()
+    LayerwiseMLPTrainer(spec, a0[:P], 128, dgrad_kn=False, wgrad_mn=False).fit(a0[:P], x, y, cfg, None)
+    tr = LayerwiseMLPTrainer(spec, a1[:P], 128, dgrad_kn=True, wgrad_mn=True)
+    assert all(t is None for t in tr.WsT + tr.aT + tr.dzT)
+    tr.fit(a1[:P], x, y, cfg, None)
+    assert torch.equal(a0, a1)
+    simt = conv_ops.load_simt()
+    if simt is None or not hasattr(simt, "gemm_tcgen05"):
+        pytest.skip("SIMT build unavailable")
+    with conv_ops.simt():                                        # kernel source: MN-major A and B operands + fused SGD epilogue
+        LayerwiseMLPTrainer(spec, a2[:P], 128, dgrad_kn=True, wgrad_mn=True).fit(a2[:P], x, y, cfg, None)
+    torch.testing.assert_close(a2, a0, rtol=2e-3, atol=2e-3)

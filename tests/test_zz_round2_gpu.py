@@ -522,11 +522,12 @@ def test_layerwise_trainer_dgrad_against_weights_in_place_on_device():
     x, y = torch.rand(384, 10, device=dev), torch.randint(0, 2, (384, 1), device=dev).float()
     cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
     outs = []
-    for kn in (False, True):
+    for kn in (False, True, "both"):
         flat = flat0.clone()
-        tr = LayerwiseMLPTrainer(spec, flat, 128, dgrad_kn=kn)
+        tr = LayerwiseMLPTrainer(spec, flat, 128, dgrad_kn=bool(kn), wgrad_mn=(kn == "both"))
         tr.fit(flat, x, y, cfg, None)
         torch.cuda.synchronize()
         outs.append(flat)
-    assert torch.isfinite(outs[1]).all()
-    assert float((outs[0] - outs[1]).abs().max()) < 2e-3 * max(1.0, float(outs[0].abs().max()))
+    for o in outs[1:]:
+        assert torch.isfinite(o).all()
+        assert float((outs[0] - o).abs().max()) < 2e-3 * max(1.0, float(outs[0].abs().max()))
