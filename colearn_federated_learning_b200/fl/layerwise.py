@@ -103,6 +103,7 @@ class LayerwiseMLPTrainer:
         self.dbp = [torch.zeros(B // 32, self.kp[l + 1], device=dev) for l in range(self.L)]
         self.dw_edge = {l: torch.zeros(self.kp[l + 1], self.kp[l], device=dev) for l in range(self.L) if not self.exact[l]}
         self.launches = 0
+        self._wt_fresh = [False] * self.L                     # W_l^T matches the bf16 shadow W_l
 
     # -- parameter views -----------------------------------------------------------------------------
     def _w(self, flat: torch.Tensor, l: int) -> torch.Tensor:
@@ -120,8 +121,19 @@ class LayerwiseMLPTrainer:
         return lo // chunk_elems, hi // chunk_elems
 
     def _refresh_t(self, l: int) -> None:
+        """Rebuild ``W_lᵀ`` from the bf16 shadow ``W_l`` (a 64 MB pass for a 4096 × 4096 layer: 20 µs, 19 % of the kernel time
+        of a wide-MLP round in the round-1 launch-time capture).  The copy is only needed by the NEXT dgrad, so the wgrad
+        merely marks it stale and the dgrad refreshes it on demand: the transposes behind the last step of a fit — dead
+        work, the next fit starts from ``refresh_exact`` — are never launched."""
         if not self.dgrad_kn:
             ops.transpose_bf16(self.Ws[l], self.WsT[l])
+        self._wt_fresh[l] = True
+
+    def sync_transposes(self) -> None:
+        """Bring every stale ``W_lᵀ`` up to date (callers that read ``WsT`` outside :meth:`backward`)."""
+        for l in range(self.L):
+            if not self._wt_fresh[l]:
+                self._refresh_t(l)
 
     def refresh_edge(self, flat: torch.Tensor) -> None:
         """Padded bf16 shadows (+ transposes, padded biases) of the layers that need padding."""
@@ -197,6 +209,8 @@ class LayerwiseMLPTrainer:
             produced.mark(end, produced.n)
         for l in range(L - 1, -1, -1):
             if l > 0:
+                if not self._wt_fresh[l]:
+                    self._refresh_t(l)
                 ops.gemm_bf16(self.dz[l], self.Ws[l] if self.dgrad_kn else self.WsT[l], b_kn=self.dgrad_kn, relu_mask=self.a[l],
                               out_bf16=self.dz[l - 1], out_bf16_t=self.dzT[l - 1], colsum=self.dbp[l - 1],
                               max_ctas=produced.max_ctas if produced is not None else 0)
@@ -205,14 +219,13 @@ class LayerwiseMLPTrainer:
                 # (2-byte transposed stores from the epilogue cost more than a separate 64 MB pass)
                 self._wgrad(l, sgd_master=self._w(flat, l), sgd_lr=lr, sgd_shadow=self.Ws[l],
                             produced=(produced, self.offsets[l][0]) if produced is not None else None)
-                if produced is None:
-                    self._refresh_t(l)
+                self._wt_fresh[l] = False
             else:
                 self._wgrad(l, out_f32=self.dw_edge[l])
                 w = self._w(flat, l)
                 w.sub_(self.dw_edge[l][: w.shape[0], : w.shape[1]], alpha=lr)
                 self.Ws[l][: w.shape[0], : w.shape[1]].copy_(w)
-                self._refresh_t(l)
+                self._wt_fresh[l] = False
                 if produced is not None:
                     produced.mark(self.offsets[l][0], self.offsets[l][0] + w.numel())
             b = self._b(flat, l)

@@ -225,6 +225,7 @@ def test_layerwise_tcgen05_trainer_matches_autograd():
     assert abs(float(last) - float(l)) < 2e-2
     assert (flat.cpu() - ref).abs().max() < 5e-3, (flat.cpu() - ref).abs().max()
     # shadows are consistent with the fp32 master after the fused-SGD epilogue
+    tr.sync_transposes()          # W^T is refreshed on demand (by the next dgrad): bring it up to date before looking at it
     w2 = flat[spec.offsets()[1][0]: spec.offsets()[1][0] + 256 * 256].view(256, 256)
     assert torch.equal(tr.Ws[1], w2.to(torch.bfloat16)) and torch.equal(tr.WsT[1], w2.t().contiguous().to(torch.bfloat16))
 

@@ -148,3 +148,42 @@ def test_layerwise_wgrad_from_untransposed_operands():
     with conv_ops.simt():                                        # kernel source: MN-major A and B operands + fused SGD epilogue
         LayerwiseMLPTrainer(spec, a2[:P], 128, dgrad_kn=True, wgrad_mn=True).fit(a2[:P], x, y, cfg, None)
     torch.testing.assert_close(a2, a0, rtol=2e-3, atol=2e-3)
+
+
+def test_transposes_are_refreshed_on_demand_and_never_after_the_last_step(monkeypatch):
+    """W^T is only rebuilt when a dgrad needs it: a fit of S steps launches (S - 1) x L weight transposes behind its
+    wgrads instead of S x L (the ones after the last step were dead work: the next fit starts from refresh_exact)."""
+    from colearn_federated_learning_b200.fl import layerwise as lw_mod
+    spec = MLPSpec((10, 128, 256, 128, 2), "none", "xent")
+    cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
+    torch.manual_seed(7)
+    x, y = torch.rand(384, 10), torch.randint(0, 2, (384, 1)).float()
+    a0, P = _arena(spec, 5, extra=0)
+    tr = LayerwiseMLPTrainer(spec, a0[:P], 128)
+    calls = []
+    real = lw_mod.ops.transpose_bf16
+
+    def counting(src, out=None):
+        calls.append(src.data_ptr())
+        return real(src, out)
+
+    monkeypatch.setattr(lw_mod.ops, "transpose_bf16", counting)
+    tr.fit(a0[:P], x, y, cfg, None)                              # 3 steps
+    L = spec.n_layers
+    w_ptrs = {w.data_ptr() for w in tr.Ws}
+    n_w = sum(1 for c in calls if c in w_ptrs)
+    # fit start: L refreshes; then dgrads of steps 2 and 3 refresh layers 1 .. L-1 (layer 0 has no dgrad)
+    assert n_w == L + 2 * (L - 1), (n_w, calls)
+    assert not any(tr._wt_fresh[1:])                             # stale after the last wgrad ...
+    tr.sync_transposes()                                         # ... until somebody asks
+    for l in range(L):
+        assert torch.equal(tr.WsT[l], tr.Ws[l].t().contiguous())
+    # two consecutive fits == one trainer doing the same steps with eager transposes (reference: recompute from scratch)
+    b0, _ = _arena(spec, 5, extra=0)
+    tr2 = LayerwiseMLPTrainer(spec, b0[:P], 128)
+    tr2.fit(b0[:P], x, y, cfg, None)
+    assert torch.equal(a0, b0)
+    tr.fit(a0[:P], x, y, cfg, None)
+    tr2.sync_transposes()
+    tr2.fit(b0[:P], x, y, cfg, None)
+    assert torch.equal(a0, b0)
