@@ -189,7 +189,7 @@ class LayerwiseMLPTrainer:
         if not self.wgrad_mn:
             ops.transpose_bf16(self.dz[L - 1], self.dzT[L - 1])
         self.db[L - 1][:nc].copy_(dlog.sum(0))
-        self.launches += L + 1
+        self.launches += L + 1 + (0 if self.wgrad_mn else 2)       # own kernels: L GEMMs, the loss, two transposes
         return loss
 
     def backward(self, flat: torch.Tensor, lr: float, produced=None) -> None:
