@@ -310,13 +310,18 @@ class FederatedEngine:
         bflag_ptrs = arena.peer_ptrs("flags")
         n_blocks = max(1, min(148, (P4 // 4 + 255) // 256))
         is_coord = r == self.coord
-        losses_log = torch.zeros(rounds, W, 2, device=dev) if is_coord else None
-        arrived_log = torch.zeros(rounds, dtype=torch.int32, device=dev)
+        # every row of losses_log is overwritten by the round's copy; arrived_log is only read in deadline mode: no fill
+        # launches in front of the round's first kernel (single-round calls pay them every call)
+        losses_log = torch.empty(rounds, W, 2, device=dev) if is_coord else None
+        arrived_log = (torch.zeros(rounds, dtype=torch.int32, device=dev) if self.round_deadline_ms > 0
+                       else torch.empty(rounds, dtype=torch.int32, device=dev))
         launches = 0
         if _dist_ready() and W > 1 and self._barrier:
             dist.barrier(group=self.group)
         torch.cuda.synchronize(dev)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if getattr(self, "_star_events", None) is None:
+            self._star_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev0, ev1 = self._star_events
         ev0.record()
 
         def star(do_reduce: bool, do_bcast: bool, mask_reduce: int, mask_bcast: int, arrive_epoch: int, bcast_epoch: int):
