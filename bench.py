@@ -421,6 +421,24 @@ def main() -> None:
                    "h2d_bytes_per_step": int(hx.numel() * hx.element_size() + hy.numel() * hy.element_size()),
                    "d2h_bytes_per_step": int(engine.loss_host.numel() * 4) if rank == 0 else 8,
                    "timing": "host clock, max over ranks, sync both sides"}
+            # the same K rounds through ONE run_rounds(K) call: every round still copies its inputs H2D from pinned memory
+            # and its losses D2H, but the host reads the losses one round late (engine.loss_history) — reported next to the
+            # per-call figure, never instead of it (first measured in round 2)
+            # opt-in (COLEARN_BENCH_E2E_ONE_CALL=1): a rank-local failure inside it would leave the other ranks in a collective
+            if getattr(engine, "algo", "") == "star" and os.environ.get("COLEARN_BENCH_E2E_ONE_CALL") == "1":
+                try:
+                    engine.run_rounds(2, masks=mask, host_inputs=[(hx, hy)] * 2, read_back="pipelined", barrier=False)
+                    torch.cuda.synchronize()
+                    if world > 1:
+                        dist.barrier()
+                    t0 = time.perf_counter()
+                    engine.run_rounds(K, masks=mask, host_inputs=[(hx, hy)] * K, read_back="pipelined", barrier=False)
+                    torch.cuda.synchronize()
+                    wall_p = max_over_ranks(time.perf_counter() - t0)
+                    extra["e2e_one_call_rounds_per_s"] = K / wall_p
+                    extra["e2e_one_call_losses_read"] = len(engine.loss_history) if rank == 0 else None
+                except Exception as exc:  # noqa: BLE001 - an unmeasured path must never take the bench line down
+                    extra["e2e_one_call_error"] = repr(exc)[:200]
         impl = "ours"
     else:  # torch_nccl comparator
         from baseline.torch_nccl_fedavg import TorchNcclFedAvg

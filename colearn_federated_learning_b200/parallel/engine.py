@@ -230,11 +230,12 @@ class FederatedEngine:
         return [int(m) & full for m in masks]
 
     def run_rounds(self, rounds: int, masks=None, host_inputs: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
-                   read_back: bool = False, barrier: bool = True) -> RoundReport:
+                   read_back=False, barrier: bool = True) -> RoundReport:
         """Run ``rounds`` federated rounds.  ``masks``: selection bitmask(s) (bit k = rank k
         trains).  ``host_inputs``: per-round pinned-host ``(x, y)`` for this rank, copied H2D
         inside the round (end-to-end mode); ``read_back`` additionally copies each round's losses
-        D2H and synchronises per round.  ``barrier=False`` skips the host-side process-group
+        D2H and synchronises per round; ``read_back="pipelined"`` (star path) still copies every round's
+        losses D2H but lets the host read them one round late (``loss_history``), so the GPU does not wait for the host.  ``barrier=False`` skips the host-side process-group
         barriers around the timed region (rounds are self-synchronising through device flags)."""
         self._barrier = barrier
         if self.x is None and host_inputs is None:
@@ -323,6 +324,14 @@ class FederatedEngine:
             self._star_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev0, ev1 = self._star_events
         ev0.record()
+        # read_back="pipelined": every round's losses are still copied to the host, but the host reads them one round late
+        pipelined = read_back == "pipelined"
+        if pipelined:
+            if getattr(self, "loss_ring", None) is None:
+                self.loss_ring = torch.zeros(2, 2 * W, dtype=torch.float32).pin_memory()
+                self._ring_ev = (torch.cuda.Event(), torch.cuda.Event())
+            ring_ev = self._ring_ev
+            self.loss_history: List[torch.Tensor] = []
 
         def star(do_reduce: bool, do_bcast: bool, mask_reduce: int, mask_bcast: int, arrive_epoch: int, bcast_epoch: int):
             wts = [float(v) for v in self._round_weights(mask_reduce)] if do_reduce else [0.0] * W
@@ -364,11 +373,29 @@ class FederatedEngine:
                 losses_log[i].copy_(arena.tensor("losses").view(W, 2), non_blocking=True)
                 if self.round_deadline_ms > 0:
                     arrived_log[i].copy_(self.decision[1], non_blocking=True)
-                if read_back:
+                if pipelined:
+                    # lagged read-back: round i's losses go to pinned slot i % 2; the host waits for round i-1's copy only
+                    # after round i is enqueued, so the GPU never idles behind the host
+                    slot = i & 1
+                    self.loss_ring[slot].copy_(arena.tensor("losses"), non_blocking=True)
+                    ring_ev[slot].record()
+                    if i >= 1:
+                        ring_ev[1 - slot].synchronize()
+                        self.loss_history.append(self.loss_ring[1 - slot].clone())
+                elif read_back:
                     self.loss_host.copy_(arena.tensor("losses"), non_blocking=True)
                     torch.cuda.current_stream(dev).synchronize()
+            elif pipelined:
+                ring_ev[i & 1].record()
+                if i >= 1:
+                    ring_ev[1 - (i & 1)].synchronize()        # bound the run-ahead of a worker rank to one round
             elif read_back:
                 torch.cuda.current_stream(dev).synchronize()
+        if pipelined and rounds > 0:
+            ring_ev[(rounds - 1) & 1].synchronize()
+            if is_coord:
+                self.loss_history.append(self.loss_ring[(rounds - 1) & 1].clone())
+                self.loss_host.copy_(self.loss_history[-1])
         ev1.record()
         torch.cuda.synchronize(dev)
         self.epoch = e0 + rounds + 1

@@ -27,5 +27,7 @@ for C in 8 16 32; do
   COLEARN_OVERLAP_REDUCE=1 COLEARN_OVERLAP_CTAS=$C timeout 200 $TR --nproc-per-node 8 --master-port $((29720+C)) bench.py --gpus 8 --steps 10 --warmup 3 --config cfg5 \
       > gpurun_out/r2_8_cfg5_n8_overlap$C.json 2> gpurun_out/r2_8_cfg5_n8_overlap$C.err
 done
+# headline e2e through ONE run_rounds(K) call with the lagged loss read-back (opt-in measurement)
+COLEARN_BENCH_E2E_ONE_CALL=1 timeout 200 $TR --nproc-per-node 8 --master-port 29761 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_8_cfg2_n8_e2e_one_call.json 2> gpurun_out/r2_8_cfg2_n8_e2e_one_call.err
 for f in gpurun_out/r2_8_*.json; do echo "== $f"; cut -c1-260 $f; done
 tail -n 3 gpurun_out/r2_8_cfg4_n8.err | cut -c1-300

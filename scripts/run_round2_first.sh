@@ -86,7 +86,7 @@ if want gemm; then
   # headline kernel: 64-thread CTA variant of the persistent MLP kernel next to the default (128 threads)
   timeout 120 python scripts/microbench.py --only mlp --out gpurun_out/r2_microbench_mlp.json > gpurun_out/r2_microbench_mlp.log 2>&1
   grep variant gpurun_out/r2_microbench_mlp.log | cut -c1-220
-  timeout 60 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_cfg2_n1.json 2> gpurun_out/r2_bench_cfg2_n1.err
+  COLEARN_BENCH_E2E_ONE_CALL=1 timeout 60 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_cfg2_n1.json 2> gpurun_out/r2_bench_cfg2_n1.err
   COLEARN_MLP_VARIANT=5 timeout 60 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_cfg2_n1_variant5.json 2> gpurun_out/r2_bench_cfg2_n1_variant5.err
   COLEARN_MLP_VARIANT=4 timeout 60 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_cfg2_n1_variant4.json 2> gpurun_out/r2_bench_cfg2_n1_variant4.err
   cut -c1-200 gpurun_out/r2_bench_cfg2_n1.json gpurun_out/r2_bench_cfg2_n1_variant5.json gpurun_out/r2_bench_cfg2_n1_variant4.json
