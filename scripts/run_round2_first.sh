@@ -23,7 +23,7 @@ if want tests; then
   for grp in "resnet_eval" "fused_batchnorm or optional_step" "splitk_reduce or gemm_split_k or split_k_step" \
              "mn_major_operands or mn_major_b_operand or mn_major_fused" "mn_major_wgrad_step" \
              "implicit_conv_forward" "implicit_conv_wgrad or implicit_conv_dgrad_packed" "implicit_step" \
-             "programmatic_dependent_launch" "overlapped_reduce" "staged_epilogue" "weights_in_place" "new_variants"; do
+             "programmatic_dependent_launch" "overlapped_reduce" "staged_epilogue" "weights_in_place" "new_variants" "pipelined_read_back"; do
     echo "=== group: $grp" >> gpurun_out/r2_unvalidated_tests.log
     COLEARN_RUN_UNVALIDATED=1 timeout 240 python -m pytest tests/test_zz_round2_gpu.py -q -m gpu --tb=short -p no:cacheprovider -k "$grp" \
         >> gpurun_out/r2_unvalidated_tests.log 2>&1

@@ -558,3 +558,26 @@ def test_persistent_mlp_new_variants_match_reference(bsz, n, epochs, max_b, vari
         torch.cuda.synchronize()
         assert torch.allclose(got.cpu(), ref, atol=2e-4, rtol=2e-3), (ctor.__name__, loss, (got.cpu() - ref).abs().max())
         assert torch.allclose(last.cpu(), ref_last, atol=1e-3, rtol=1e-2)
+
+
+@unvalidated
+def test_star_engine_pipelined_read_back_single_gpu():
+    """read_back="pipelined": every round's losses reach the host (one round late), results equal the synchronous mode."""
+    from colearn_federated_learning_b200.data import synthetic_unsw
+    from colearn_federated_learning_b200.parallel import FederatedEngine
+    dev = _dev()
+    x, y = synthetic_unsw(300, seed=2)
+    hx, hy = x.pin_memory(), y.pin_memory()
+    flats, hist = [], None
+    for mode in (True, "pipelined"):
+        eng = FederatedEngine("mlp", backend="fused", device=dev, batch_size=1, lr=0.05, seed=7, shuffle=False)
+        eng.set_local_data(x, y)
+        rep = eng.run_rounds(5, host_inputs=[(hx, hy)] * 5, read_back=mode, barrier=False)
+        torch.cuda.synchronize()
+        flats.append(eng.global_flat().clone())
+        if mode == "pipelined":
+            hist = torch.stack(eng.loss_history)
+            assert hist.shape[0] == 5
+            assert torch.allclose(hist[:, :2], rep.losses[:, 0, :].cpu(), atol=0, rtol=0)
+            assert torch.equal(eng.loss_host[:2], hist[-1, :2])
+    assert torch.equal(flats[0], flats[1])
