@@ -201,19 +201,32 @@ class Coordinator(BusClient):
 
     # ------------------------------------------------------------------ training dispatch
     def _start_training(self, snapshot: "OrderedDict[str, Any]") -> Any:
+        from ..models.registry import num_params
+        from ..utils.threads import small_model_threads
         self._in_flight = dict(snapshot)
+        sizes = self.__dict__.setdefault("_param_counts", {})
+        if self.args.model not in sizes:
+            try:
+                sizes[self.args.model] = num_params(build_model(self.args.model))
+            except Exception:  # noqa: BLE001 - an unknown model fails later, with the proper message
+                sizes[self.args.model] = 0
         try:
-            if self.remote:
-                loop = asyncio.new_event_loop()  # fresh loop inside the timer thread (fc.py:194-203)
-                try:
-                    return loop.run_until_complete(self.training_remote(snapshot))
-                finally:
-                    loop.close()
-            if self.encryption:
-                return self.starting_training_enc(snapshot)
-            return self.starting_training_local(snapshot)
+            # small models on the CPU: one intra-op thread (utils/threads.py: OpenMP fork/join costs more than the ops)
+            with small_model_threads(sizes[self.args.model], self.device):
+                return self._dispatch_training(snapshot)
         finally:
             self._in_flight = {}
+
+    def _dispatch_training(self, snapshot: "OrderedDict[str, Any]") -> Any:
+        if self.remote:
+            loop = asyncio.new_event_loop()  # fresh loop inside the timer thread (fc.py:194-203)
+            try:
+                return loop.run_until_complete(self.training_remote(snapshot))
+            finally:
+                loop.close()
+        if self.encryption:
+            return self.starting_training_enc(snapshot)
+        return self.starting_training_local(snapshot)
 
     def _policy(self, lower: int, upper: int, policy: Optional[str] = None) -> SelectionPolicy:
         return SelectionPolicy(lower_bound=lower, upper_bound=upper, policy=policy or self.selection,

@@ -188,7 +188,9 @@ class WorkerServer:
                 spec = getattr(model, "spec", None)
                 if spec is not None and not spec.flatten_input and x.shape[1] != spec.dims[0]:
                     return {"ok": False, "error": f"dataset has {x.shape[1]} features, {cfg.model} wants {spec.dims[0]}"}
-                loss, path = local_fit(flat, model, x, y, cfg, round_idx=self._round)
+                from ..utils.threads import small_model_threads
+                with small_model_threads(flat.numel(), flat.device):   # tiny models on a CPU device: no OpenMP fork/join
+                    loss, path = local_fit(flat, model, x, y, cfg, round_idx=self._round)
                 self._round += 1
                 self.fits_served += 1
                 return {"ok": True, "params": _to_bytes(flat), "loss": float(loss), "n": int(x.shape[0]), "path": path}

@@ -427,3 +427,25 @@ def test_prometheus_exporter_serves_round_metrics(tmp_path):
     finally:
         exp.close()
         w1.stop(); w2.stop()
+
+
+def test_small_model_sections_run_with_one_intra_op_thread():
+    """utils/threads.py: the coordinator's training section for a few-thousand-parameter model must not pay OpenMP
+    fork/join per op; the previous thread setting is restored afterwards, large models keep the pool."""
+    from colearn_federated_learning_b200.utils.threads import small_model_threads
+    before = torch.get_num_threads()
+    if before == 1:
+        pytest.skip("single-threaded torch build / environment")
+    with small_model_threads(4866, torch.device("cpu")):
+        assert torch.get_num_threads() == 1
+    assert torch.get_num_threads() == before
+    with small_model_threads(11_000_000, torch.device("cpu")):
+        assert torch.get_num_threads() == before
+    with small_model_threads(4866, torch.device("cuda", 0)):
+        assert torch.get_num_threads() == before
+    try:
+        with small_model_threads(10, None):
+            raise RuntimeError("x")
+    except RuntimeError:
+        pass
+    assert torch.get_num_threads() == before
