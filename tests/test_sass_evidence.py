@@ -55,3 +55,27 @@ def test_comm_kernels_use_multimem_and_system_scope_flags(sass):
     assert "STRONG.SYS" in star
     mlp = _kernels(sass, "mlp_local_sgd_kernel_v2")
     assert mlp and all("STRONG.SYS" in t for t in mlp.values())  # wait / signal flags of the persistent kernel
+
+
+def test_opt_in_paths_compile_to_the_instructions_their_docs_claim(sass):
+    # line-coalesced epilogue: explicit 128-bit shared-memory accesses, no generic LD / ST, in every GEMM instantiation
+    for name, text in {**_kernels(sass, "gemm_tcgen05_kernel"), **_kernels(sass, "gemm_tcgen05_2sm_kernel")}.items():
+        assert text.count("STS.128") >= 16 and text.count("LDS.128") >= 16, name
+        assert not re.search(r"\bST\.E\.128\b|\bLD\.E\.128\b", text), name
+    # programmatic dependent launch: every conv / BatchNorm / pooling kernel exists twice, the PDL twin starts with
+    # griddepcontrol.wait / launch_dependents; the plain twin has neither
+    conv = {k: v for k, v in sass.items() if re.search(r"(im2col|col2im|bn_apply|bn_bwd|bn_reduce|bn_finalize|maxpool|avgpool|pack|splitk_reduce)\w*kernel", k)}
+    with_pdl = [k for k, v in conv.items() if "ACQBULK" in v and "PREEXIT" in v]
+    without = [k for k, v in conv.items() if "ACQBULK" not in v and "PREEXIT" not in v]
+    assert len(with_pdl) == len(without) == 13, (len(with_pdl), len(without))
+    for text in {**_kernels(sass, "gemm_tcgen05_kernel"), **_kernels(sass, "gemm_tcgen05_2sm_kernel")}.values():
+        assert "ACQBULK" in text and "PREEXIT" in text          # behind `if (ep.pdl)`, after the kernel's own set-up
+    # fused wgrad -> FedAvg reduce: the overlapped two-shot polls .sys-scope flags and shares the reduce body
+    overlap = next(iter(_kernels(sass, "twoshot_overlap_kernel").values()))
+    assert "STRONG.SYS" in overlap and "LDGMC" in overlap
+    assert _kernels(sass, "produced_mark_kernel")
+    # persistent MLP, variant 5: 128-bit shared-memory loads of the blocked slices; the default variant has none
+    v5 = {k: v for k, v in _kernels(sass, "mlp_local_sgd_kernel_v2").items() if "7v2_128b" in k and "Li64ELi64" in k}
+    v3 = {k: v for k, v in _kernels(sass, "mlp_local_sgd_kernel_v2").items() if "6v2_128" in k and "Li64ELi64" in k}
+    assert len(v5) == 2 and all(t.count("LDS.128") >= 16 for t in v5.values())
+    assert len(v3) == 2 and all("LDS.128" not in t for t in v3.values())
