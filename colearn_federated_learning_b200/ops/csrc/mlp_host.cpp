@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -220,6 +221,122 @@ void run_fit(const Net& net, Task& t, const Hyper& hp, Scratch& sc) {
   t.mean = it > 0 ? (float)(loss_sum / it) : 0.f;
 }
 
+// ---- fixed-shape fast path (batch 1) --------------------------------------------------------------------------------------
+// The reference's three networks have compile-time layer widths: with constant trip counts the compiler unrolls and
+// vectorises every dot product / AXPY exactly (no remainder loops, no alignment peeling — which is most of the time for
+// 10- to 64-element loops): 1.33 -> 0.69 us per step for the 10-64-64-2 net, 0.99 -> 0.51 for the FFNN on the authoring box.
+// Same operations as run_fit (batch 1); only the association inside a dot product follows the vector width the compiler
+// picks, so the two paths agree to rounding (1e-7 against the PyTorch reference after 600 steps), not bit for bit.
+// COLEARN_HOST_GENERIC=1 forces the generic loop.
+template <int... D>
+struct Shape {
+  static constexpr int L = sizeof...(D) - 1;
+  static constexpr int dims[sizeof...(D)] = {D...};
+  static constexpr int max_dim() { int m = 0; for (int d : dims) m = d > m ? d : m; return m; }
+  static constexpr int w_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += dims[i] * dims[i + 1] + dims[i + 1]; return o; }
+  static constexpr int b_off(int l) { return w_off(l) + dims[l] * dims[l + 1]; }
+  static bool matches(const Net& net) {
+    if (net.layers() != L) return false;
+    for (int i = 0; i <= L; ++i) if (net.dims[i] != dims[i]) return false;
+    return true;
+  }
+};
+
+template <class S, int l>
+__attribute__((always_inline)) inline void fixed_forward(const float* theta, float (*acts)[S::max_dim()], bool sigmoid_out) {
+  if constexpr (l < S::L) {
+    constexpr int K = S::dims[l], N = S::dims[l + 1];
+    const float* w = theta + S::w_off(l);
+    const float* b = theta + S::b_off(l);
+    const float* in = acts[l];
+    float* out = acts[l + 1];
+    for (int j = 0; j < N; ++j) {
+      const float* wr = w + j * K;
+      float s = 0.f;
+#pragma omp simd reduction(+ : s)
+      for (int i = 0; i < K; ++i) s += wr[i] * in[i];
+      s += b[j];
+      if (l < S::L - 1) s = s > 0.f ? s : 0.f;
+      else if (sigmoid_out) s = 1.f / (1.f + std::exp(-s));
+      out[j] = s;
+    }
+    fixed_forward<S, l + 1>(theta, acts, sigmoid_out);
+  }
+}
+
+template <class S, int l>
+__attribute__((always_inline)) inline void fixed_backward(float* theta, const float (*acts)[S::max_dim()], float* dz, float* dprev, float lr) {
+  if constexpr (l >= 0) {
+    constexpr int K = S::dims[l], N = S::dims[l + 1];
+    float* w = theta + S::w_off(l);
+    float* b = theta + S::b_off(l);
+    const float* a = acts[l];
+    if constexpr (l > 0) {   // dz_{l-1} = (W^T dz) * relu'(a) with the weights of BEFORE this step
+      for (int i = 0; i < K; ++i) dprev[i] = 0.f;
+      for (int j = 0; j < N; ++j) {
+        const float g = dz[j];
+        const float* wr = w + j * K;
+#pragma omp simd
+        for (int i = 0; i < K; ++i) dprev[i] += g * wr[i];
+      }
+      for (int i = 0; i < K; ++i)
+        if (!(a[i] > 0.f)) dprev[i] = 0.f;
+    }
+    for (int j = 0; j < N; ++j) {
+      const float g = lr * dz[j];
+      float* wr = w + j * K;
+#pragma omp simd
+      for (int i = 0; i < K; ++i) wr[i] -= g * a[i];
+      b[j] -= g;
+    }
+    if constexpr (l > 0) fixed_backward<S, l - 1>(theta, acts, dprev, dz, lr);   // dz / dprev swap roles
+  }
+}
+
+template <class S>
+COLEARN_CLONES void run_fit_fixed(const Net& net, Task& t, const Hyper& hp, Scratch& sc) {
+  constexpr int MD = S::max_dim(), L = S::L;
+  alignas(64) float acts[L + 1][MD];
+  alignas(64) float dz[MD], dprev[MD];
+  sc.dout.assign((size_t)net.dims[L], 0.f);
+  float* theta = t.theta;
+  double loss_sum = 0.0;
+  int it = 0;
+  bool done = false;
+  for (int e = 0; e < hp.epochs && !done; ++e) {
+    const int* order = t.perm ? t.perm + (int64_t)(e % t.perm_rows) * t.n : nullptr;
+    for (int lo = 0; lo < t.n && !done; ++lo) {
+      const int idx = order ? order[lo] : lo;
+      std::memcpy(acts[0], t.x + (int64_t)idx * S::dims[0], sizeof(float) * S::dims[0]);
+      fixed_forward<S, 0>(theta, acts, net.sigmoid_out);
+      const float* y = t.y + (int64_t)idx * t.y_dim;
+      t.last = loss_and_dout(net, hp.loss, &acts[0][0], (L + 1) * MD, MD, &y, t.y_dim, 1, sc.dout.data());
+      loss_sum += t.last;
+      std::memcpy(dz, sc.dout.data(), sizeof(float) * S::dims[L]);
+      fixed_backward<S, L - 1>(theta, acts, dz, dprev, hp.lr);
+      ++it;
+      if (hp.max_steps > 0 && it >= hp.max_steps) done = true;
+    }
+  }
+  t.steps = it;
+  t.mean = it > 0 ? (float)(loss_sum / it) : 0.f;
+}
+
+using ShapeMLP64 = Shape<10, 64, 64, 2>;         // BASELINE MLP
+using ShapeFFNN = Shape<10, 50, 30, 10, 1>;      // the reference's FFNN (cf.py:22-44)
+using ShapeTestingRemote = Shape<2, 50, 10, 1>;  // the reference's TestingRemote (cf.py:46-55)
+
+// one local fit: the fixed-shape path for the known networks at batch 1, the generic loop otherwise
+inline void run_fit_any(const Net& net, Task& t, const Hyper& hp, Scratch& sc) {
+  static const bool generic_only = std::getenv("COLEARN_HOST_GENERIC") != nullptr;
+  if (hp.batch == 1 && !generic_only) {
+    if (ShapeMLP64::matches(net)) return run_fit_fixed<ShapeMLP64>(net, t, hp, sc);
+    if (ShapeFFNN::matches(net)) return run_fit_fixed<ShapeFFNN>(net, t, hp, sc);
+    if (ShapeTestingRemote::matches(net)) return run_fit_fixed<ShapeTestingRemote>(net, t, hp, sc);
+  }
+  run_fit(net, t, hp, sc);
+}
+
 Task make_task(const Net& net, const torch::Tensor& theta, const torch::Tensor& x, const torch::Tensor& y,
                const c10::optional<torch::Tensor>& perm) {
   auto ok = [](const torch::Tensor& t, at::ScalarType st) { return !t.is_cuda() && t.scalar_type() == st && t.is_contiguous(); };
@@ -264,13 +381,13 @@ torch::Tensor mlp_local_sgd_host(std::vector<int64_t> dims, bool sigmoid_out, st
     py::gil_scoped_release nogil;
     if (nthreads == 1) {
       Scratch sc;
-      for (auto& t : tasks) run_fit(net, t, hp, sc);
+      for (auto& t : tasks) run_fit_any(net, t, hp, sc);
     } else {
       std::vector<std::thread> pool;
       for (int w = 0; w < nthreads; ++w)
         pool.emplace_back([&, w] {
           Scratch sc;
-          for (size_t i = w; i < K; i += nthreads) run_fit(net, tasks[i], hp, sc);
+          for (size_t i = w; i < K; i += nthreads) run_fit_any(net, tasks[i], hp, sc);
         });
       for (auto& th : pool) th.join();
     }

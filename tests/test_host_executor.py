@@ -1,4 +1,5 @@
 """Native CPU executor of the MLP local fit (ops/csrc/mlp_host.cpp) against the PyTorch definitions (ops/reference.py)."""
+import os
 import time
 
 import pytest
@@ -159,3 +160,36 @@ def test_host_fit_matches_reference_on_random_architectures():
         assert abs(float(res[0, 0]) - float(last)) <= 2e-4 * max(1.0, abs(float(last)))
 
     prop()
+
+
+def test_fixed_shape_fast_path_agrees_with_the_generic_loop():
+    """The reference's three networks take a compile-time-shape path at batch 1 (csrc/mlp_host.cpp: run_fit_fixed); the
+    generic loop (COLEARN_HOST_GENERIC=1, read once per process) must agree with it to rounding."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, hashlib\n"
+        "from colearn_federated_learning_b200.ops import host, reference as R\n"
+        "from colearn_federated_learning_b200.models import MLP, FFNN, TestingRemote, flatten_params\n"
+        "torch.set_num_threads(1)\n"
+        "for ctor, loss in ((MLP, 'xent'), (FFNN, 'bce'), (TestingRemote, 'mse')):\n"
+        "    torch.manual_seed(3); m = ctor()\n"
+        "    dims, act = m.spec.dims, m.spec.out_activation\n"
+        "    x = torch.rand(200, dims[0]); y = (torch.rand(200, 1) > 0.5).float()\n"
+        "    flat = flatten_params(m).clone()\n"
+        "    out = host.mlp_local_sgd_multi(dims, act, [flat], [x], [y], [R.make_permutation(200, 1, 0)], 1, 0.05, 1, -1, loss)\n"
+        "    print('RES', ctor.__name__, ' '.join(f'{v:.9e}' for v in flat[:64].tolist()), f'{float(out[0, 0]):.9e}')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for generic in (False, True):
+        env = dict(os.environ)
+        env.pop("COLEARN_HOST_GENERIC", None)
+        if generic:
+            env["COLEARN_HOST_GENERIC"] = "1"
+        p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-1500:]
+        outs.append([ln.split()[2:] for ln in p.stdout.splitlines() if ln.startswith("RES")])
+    assert len(outs[0]) == len(outs[1]) == 3
+    for a, b in zip(outs[0], outs[1]):
+        va, vb = torch.tensor([float(v) for v in a]), torch.tensor([float(v) for v in b])
+        assert torch.allclose(va, vb, rtol=1e-4, atol=1e-5), float((va - vb).abs().max())
