@@ -18,9 +18,11 @@ SMALL_MODEL_PARAMS = 1 << 20
 
 @contextlib.contextmanager
 def small_model_threads(n_params: int, device=None):
-    """``with small_model_threads(P, device):`` — one intra-op thread while a small model trains on the CPU."""
-    on_cpu = device is None or torch.device(device).type == "cpu"
-    if not on_cpu or n_params > SMALL_MODEL_PARAMS or torch.get_num_threads() == 1:
+    """``with small_model_threads(P, device):`` — one CPU intra-op thread while a small model trains."""
+    # `device` is informational: with the model on a GPU the host-side ops of the window (state-dict copies, checkpoint
+    # (de)serialisation, index bookkeeping) are just as small, and the setting only concerns CPU intra-op threads
+    del device
+    if n_params > SMALL_MODEL_PARAMS or torch.get_num_threads() == 1:
         yield
         return
     before = torch.get_num_threads()
