@@ -266,6 +266,8 @@ struct SharedBarriers {
   uint32_t tmem_base;
 };
 
+static_assert(sizeof(SharedBarriers) <= 256, "the barriers own 256 bytes behind the operand stages; the staged epilogue's buffers follow");
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
