@@ -1,0 +1,89 @@
+"""Call sites of the C++ extension take positional arguments only (the bindings define no keywords): a call with the
+wrong number of arguments would only fail on a GPU.  This test compares, statically, every call of an extension function
+in the package / scripts / tests with the arity pybind reports for the built modules (CUDA extension, SIMT build, host
+executor — all importable on a CPU-only box)."""
+import ast
+import glob
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _arities(mod):
+    out = {}
+    for name in dir(mod):
+        fn = getattr(mod, name)
+        doc = getattr(fn, "__doc__", None) or ""
+        first = doc.splitlines()[0] if doc else ""
+        if not first.startswith(name + "("):
+            continue
+        inner = first[len(name) + 1: first.rfind(")")]
+        out[name] = len(re.findall(r"\barg\d+:", inner))
+    return out
+
+
+@pytest.fixture(scope="module")
+def arities():
+    from colearn_federated_learning_b200.ops import _ext, conv, host
+    mods = {}
+    cuda_mod = _ext.load()
+    if cuda_mod is None:
+        pytest.skip("CUDA extension not built")
+    mods["cuda"] = _arities(cuda_mod)
+    simt = conv.load_simt()
+    if simt is not None:
+        mods["simt"] = _arities(simt)
+    if host.available():
+        mods["host"] = _arities(host.load())
+    return mods
+
+
+# receiver names that denote a given module at the call sites
+RECEIVERS = {"cuda": {"ext", "_ext.require()", "self.ext", "self._ext", "_ext.load()"}, "simt": {"simt", "simt_mod"}, "host": {"mod"}}
+
+
+def _calls(path):
+    tree = ast.parse(open(path).read(), filename=path)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute):
+            try:
+                recv = ast.unparse(node.func.value)
+            except Exception:  # noqa: BLE001
+                continue
+            if any(isinstance(a, ast.Starred) for a in node.args) or node.keywords:
+                continue
+            yield recv, node.func.attr, len(node.args), node.lineno
+
+
+def test_extension_call_sites_pass_the_number_of_arguments_the_bindings_take(arities):
+    files = (glob.glob(os.path.join(ROOT, "colearn_federated_learning_b200", "**", "*.py"), recursive=True)
+             + glob.glob(os.path.join(ROOT, "scripts", "*.py")) + glob.glob(os.path.join(ROOT, "tests", "*.py"))
+             + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")])
+    checked, bad = 0, []
+    for path in files:
+        for recv, fn, nargs, line in _calls(path):
+            for kind, names in RECEIVERS.items():
+                if kind == "host" and not path.endswith(os.path.join("ops", "host.py")):
+                    continue
+                if recv in names and kind in arities and fn in arities[kind]:
+                    checked += 1
+                    if nargs != arities[kind][fn]:
+                        bad.append(f"{os.path.relpath(path, ROOT)}:{line}: {recv}.{fn}() passes {nargs} args, the {kind} binding takes {arities[kind][fn]}")
+    # `mod.<fn>(...)` in ops/conv.py addresses the CUDA extension or the SIMT build depending on the branch: either arity
+    for path in files:
+        if path.endswith(os.path.join("ops", "host.py")):
+            continue
+        for recv, fn, nargs, line in _calls(path):
+            if recv in ("mod", "self.mod"):
+                want = {arities[k][fn] for k in ("cuda", "simt") if k in arities and fn in arities[k]}
+                if want:
+                    checked += 1
+                    if nargs not in want:
+                        bad.append(f"{os.path.relpath(path, ROOT)}:{line}: mod.{fn}() passes {nargs} args, bindings take {sorted(want)}")
+    assert not bad, "\n".join(bad)
+    seen = {fn for path in files for recv, fn, _, _ in _calls(path) if recv in RECEIVERS['cuda'] | {'mod', 'self.mod'}}
+    assert {'twoshot_fedavg', 'gemm_tcgen05', 'produced_mark', 'star_round'} <= seen, seen
+    assert checked >= 40, checked                                # the scan really found the call sites
