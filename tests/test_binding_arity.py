@@ -87,3 +87,31 @@ def test_extension_call_sites_pass_the_number_of_arguments_the_bindings_take(ari
     seen = {fn for path in files for recv, fn, _, _ in _calls(path) if recv in RECEIVERS['cuda'] | {'mod', 'self.mod'}}
     assert {'twoshot_fedavg', 'gemm_tcgen05', 'produced_mark', 'star_round'} <= seen, seen
     assert checked >= 40, checked                                # the scan really found the call sites
+
+
+def test_extension_accepts_the_argument_types_the_python_layer_passes():
+    """pybind converts the arguments before the function body runs: on a CPU-only box the body then fails (no device, CPU
+    tensors) with a RuntimeError — a TypeError would mean the Python layer passes something the binding cannot take."""
+    import torch
+
+    from colearn_federated_learning_b200.ops import _ext
+    ext = _ext.load()
+    if ext is None:
+        pytest.skip("CUDA extension not built")
+    if torch.cuda.is_available():
+        pytest.skip("meant for the CPU-only box (the calls below would launch kernels on garbage pointers)")
+    ptrs = [4096, 8192]
+    # parallel/engine.py::_run_twoshot (classic and overlapped form)
+    for produced, timeout, arrive in ((0, 0.0, [16, 32]), (123456, 20.0, [])):
+        with pytest.raises(RuntimeError):
+            ext.twoshot_fedavg(ptrs, ptrs, ptrs, 64, 128, 0, 3, 0b11, 1.0, 4096, 2048, 0, 16, arrive, True, 0, 0, produced, timeout)
+    with pytest.raises(RuntimeError):
+        ext.produced_mark(4096, 2048, 0, 100)
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    m = torch.zeros(128, 128)
+    # ops/linear.py::gemm_bf16 with every optional group in the form it is passed (CPU tensors are rejected by a TORCH_CHECK)
+    for prod in ([], [0, 0, 132], [4096, 512, 132], [0, 0, 0, 1], [4096, 512, 132, 0]):
+        with pytest.raises(RuntimeError):
+            ext.gemm_tcgen05(a, a, None, False, None, None, None, None, m, 0.1, None, None, None, 0, 0, 1, 0, 0, 0, 0, 0, None, 0, False, None, [], prod)
+    packed = ext.produced_signal_pack(4096, [8192, 12288], 16384, 1, 2048, 1, 3, 6000)
+    assert packed.dtype == torch.uint8 and packed.numel() >= 160
