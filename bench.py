@@ -499,7 +499,9 @@ def main() -> None:
                        "total_samples": total, "samples_per_worker": n_local, "local_epochs": epochs,
                        "local_sgd_steps_per_round": steps_per_round, "selected_workers": select_k or world,
                        "fedavg": "sample-count weighted", "l2": "flushed between timed rounds (160 MB write)" if flush_buf is not None else "not flushed",
-                       "baseline_ref": "0.1133 rounds/s = 12 rounds x 1000 it on 2x RPi 3B+ (BASELINE.md)", **extra},
+                       "baseline_ref": "0.1133 rounds/s = 12 rounds x 1000 it on 2x RPi 3B+ (BASELINE.md)",
+                       # opt-in switches in effect (all default to off: an empty dict is the validated configuration)
+                       "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("COLEARN_")}, **extra},
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []),
                        "power_w_max": clocks.get("power_w_max"), "samples": clocks.get("samples")},
             "e2e": e2e,
