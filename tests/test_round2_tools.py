@@ -48,3 +48,20 @@ def test_round2_scripts_parse_and_select_stages(tmp_path):
     text = open(os.path.join(ROOT, "scripts", "run_round2_first.sh")).read()
     for stage in ("tests", "conv", "prof", "gemm"):
         assert f"if want {stage}; then" in text
+
+
+def test_script_groups_cover_every_gated_gpu_test():
+    """scripts/run_round2_first.sh runs the gated GPU tests in per-group pytest processes (-k expressions of the form
+    "a or b"): every term must select something and every test of tests/test_zz_round2_gpu.py must be selected."""
+    import ast
+    import re
+    text = open(os.path.join(ROOT, "scripts", "run_round2_first.sh")).read()
+    groups = re.findall(r'"([^"]+)"', re.search(r"for grp in (.*?); do", text, flags=re.S).group(1))
+    terms = [t.strip() for g in groups for t in g.split(" or ")]
+    tree = ast.parse(open(os.path.join(ROOT, "tests", "test_zz_round2_gpu.py")).read())
+    tests = [n.name for n in tree.body if isinstance(n, ast.FunctionDef) and n.name.startswith("test_")]
+    assert len(groups) >= 14 and len(tests) >= 20
+    for t in terms:
+        assert any(t in name for name in tests), f"group term {t!r} selects nothing"
+    for name in tests:
+        assert any(t in name for t in terms), f"{name} is in no group of scripts/run_round2_first.sh"
