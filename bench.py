@@ -324,7 +324,10 @@ def bench_smpc(args) -> None:
 def main() -> None:
     args = parse_args()
     if args.impl == "reference":
-        reference_unavailable()
+        # the unmodified reference from baseline/_ref on its own stock path; nothing of this repo's package is imported
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import reference_arm
+        reference_arm.main(args)
         return
     if args.config == "cfg1":
         bench_cfg1(args)
