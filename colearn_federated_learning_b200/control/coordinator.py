@@ -85,6 +85,7 @@ class Coordinator(BusClient):
         self.last_predictions: Optional[List[int]] = None
         self.trainings_done = 0
         self._in_flight: Dict[str, Any] = {}      # id -> handle of the devices a running training is using
+        self._withdrawn: set = set()              # ids that sent NOT_READY while their fit was in flight
 
         self.windower = TemporalWindow(self.registry, window, self._start_training, timer_factory,
                                        lower_bound=0, rearm_if_pending=rearm_if_pending)
@@ -97,81 +98,85 @@ class Coordinator(BusClient):
         log.info("mid: " + str(mid))
 
     def on_message(self, mqttc, obj, msg: Message) -> None:
-        log.info(msg.topic + " " + str(msg.qos) + " " + str(msg.payload))
-        try:
-            self.event_parser.set_message(msg.payload)
-            ip_address = self.event_parser.ip_address()
-        except (IndexError, ValueError, UnicodeDecodeError):
-            log.info("Some problems occurred")
+        """One bus event (fc.py:131-289): decode it, build the device handle its state needs, run the state's handler
+        from ``_STATE_HANDLERS``.  Malformed payloads, filtered addresses and unknown states end in one log line."""
+        log.info("%s %s %s", msg.topic, msg.qos, msg.payload)
+        event = self._decode_event(msg.payload)
+        if event is None:
+            log.info("Event ignored: payload is not a valid '(ip[, port], STATE)' tuple for this mode")
             return
+        handler = self._STATE_HANDLERS[event["state"]]
+        handle = None
+        if event["state"] != "NOT_READY":
+            handle = self._open_handle(event)
+            if handle is None:
+                return
+        getattr(self, handler)(event, handle)
+        log.info("ONMESSAGE: Training devices: " + str(self.registry))
+        log.info("ONMESSAGE: All known workers: " + str(list(self.known_workers)))
 
-        worker = None
-        state = None
-        port = -1
+    _STATE_HANDLERS = {"TRAINING": "_on_training", "INFERENCE": "_on_inference", "NOT_READY": "_on_not_ready"}
+
+    def _decode_event(self, payload) -> Optional[Dict[str, Any]]:
+        """``{ip, port, state, id}`` of a payload, or None.  Local events are ``(ip, STATE)``, remote ones
+        ``(ip, port, STATE)``; the device id is ``ip`` / ``ip:port`` (fc.py:149,162)."""
+        ev = self.event_parser.parse(payload, remote=self.remote)
+        if ev is None:
+            return None
+        ident = f"{ev.ip}:{ev.port}" if self.remote else ev.ip
+        return {"ip": ev.ip, "port": ev.port, "state": ev.state, "id": ident}
+
+    def _open_handle(self, event: Dict[str, Any]):
+        """The object a TRAINING / INFERENCE event registers: an in-process VirtualWorker, or a connection to the
+        device's RPC server.  A device that cannot be reached is skipped (fc.py:166-170)."""
+        if not self.remote:
+            log.info("Local testing")
+            return VirtualWorker(event["id"], self.device)
+        log.info("Remote execution, worker id %s", event["id"])
         try:
-            if not self.remote:
-                log.info("Local testing")
-                state = self.event_parser.state(local=True)
-                if ip_address != -1 and state is not None and state != "NOT_READY":
-                    worker = VirtualWorker(str(ip_address), self.device)
-                elif state == "NOT_READY":
-                    log.info("NOT_READY state received")
-                else:
-                    log.info("Ip address or state not valid")
-            else:
-                log.info("Remote execution")
-                state = self.event_parser.state()
-                port = self.event_parser.port()
-                if port != -1 and ip_address != -1 and state is not None and state != "NOT_READY":
-                    identifier = str(ip_address) + ":" + str(port)
-                    log.info("Remote worker idetifier: " + identifier)
-                    try:
-                        worker = RemoteWorkerClient(identifier, str(ip_address), port, verbose=True,
-                                                    ssl_context=self.worker_ssl_context)
-                    except OSError as e:  # connection refused etc. → device skipped (fc.py:166-170)
-                        log.info("Error " + repr(e))
-                elif state == "NOT_READY":
-                    log.info("NOT_READY state received")
-                else:
-                    log.info("Server worker: no worker gerated")
-        except (IndexError, ValueError):
-            log.info("Some problems occurred")
-            return
+            return RemoteWorkerClient(event["id"], event["ip"], event["port"], verbose=True, ssl_context=self.worker_ssl_context)
+        except OSError as e:
+            log.info("Device %s unreachable, skipped: %r", event["id"], e)
+            return None
 
-        if worker is not None or (state == "NOT_READY" and ip_address != -1):
-            if state == "TRAINING":
-                # a device that announces twice (duplicate delivery, reconnect) replaces its handle; the old
-                # connection is closed unless a training in flight is still using it (that one closes it itself)
-                old = self.known_workers.get(worker.id)
-                if old is not None and old is not worker and worker.id not in self._in_flight:
-                    try:
-                        old.close()
-                    except Exception:  # noqa: BLE001
-                        pass
-                self.known_workers[worker.id] = worker
-                armed = self.windower.on_training(worker.id, worker)
-                log.info(worker)
-                if armed:
-                    log.info("Timer starting")
-            elif state == "INFERENCE":
-                if self.remote:
-                    self._inference(worker)
-                else:
-                    log.info("Inference not implemented for local purpose")
-            elif state == "NOT_READY":
-                log.info(str(ip_address) + " is not ready anymore, removing from the known lists")
-                identifier = (str(ip_address) + ":" + str(port)) if self.remote else str(ip_address)
-                removed = self.windower.on_not_ready(identifier)
-                if removed is not None:
-                    log.info("Worker to remove: " + str(removed))
-                    removed.close()
-                self.known_workers.pop(identifier, None)
-            else:
-                log.info("No behavior defined for this event")
-            log.info("ONMESSAGE: Training devices: " + str(self.registry))
-            log.info("ONMESSAGE: All known workers: " + str(list(self.known_workers)))
+    def _on_training(self, event: Dict[str, Any], worker) -> None:
+        # a device that announces twice (duplicate delivery, reconnect) replaces its handle; the old connection is closed
+        # unless a training in flight is still using it (that one closes it itself)
+        old = self.known_workers.get(worker.id)
+        if old is not None and old is not worker and worker.id not in self._in_flight:
+            self._close_quietly(old)
+        self.known_workers[worker.id] = worker
+        armed = self.windower.on_training(worker.id, worker)
+        log.info(worker)
+        if armed:
+            log.info("Timer starting")
+
+    def _on_inference(self, event: Dict[str, Any], worker) -> None:
+        if self.remote:
+            self._inference(worker)
         else:
-            log.info("Some problems occurred")
+            log.info("Inference is a remote-mode feature (local mode only tests the plumbing)")
+
+    def _on_not_ready(self, event: Dict[str, Any], _worker) -> None:
+        ident = event["id"]
+        log.info("%s withdrew (NOT_READY): removing it from the known lists", ident)
+        removed = self.windower.on_not_ready(ident)
+        if removed is not None:
+            if self._in_flight.get(ident) is removed:
+                # its fit RPC is running and holds the connection's lock: closing here would block the bus thread until the
+                # fit returns (forever for a hung device).  The training that uses the handle closes it when it finishes.
+                self._withdrawn.add(ident)
+                log.info("Worker %s is training right now; its connection is closed by that training", ident)
+            else:
+                self._close_quietly(removed)
+        self.known_workers.pop(ident, None)
+
+    @staticmethod
+    def _close_quietly(handle) -> None:
+        try:
+            handle.close()
+        except Exception:  # noqa: BLE001 - a dead socket must not take the bus thread down
+            pass
 
     # ------------------------------------------------------------------ lifecycle
     def run(self, host: str, port: int, topic: str, forever: bool = True) -> None:
@@ -358,6 +363,32 @@ class Coordinator(BusClient):
         self.metrics.start_training(cfg.max_nr_batches)
         result: Dict[str, Any] = {"workers": list(to_train.keys()), "losses": {}, "rounds": self.enabled_round, "dropped": []}
         alive = OrderedDict(to_train)
+        try:
+            theta = await self._remote_rounds(alive, to_train, theta, cfg, loop, pool, model, result)
+        finally:
+            # whatever happened above, the devices' sockets are closed and they leave the registry (fc.py:573-580, 595-597)
+            pool.shutdown(wait=False)
+            for wid, worker in to_train.items():
+                log.info("Closing socket for " + str(wid))
+                self._close_quietly(worker)
+            self._withdrawn.difference_update(to_train.keys())
+            self._deregister(to_train.keys())
+        unflatten_params(model, theta)
+        save_model(model, self.path, meta={"model": self.args.model, "rounds": self.enabled_round, "workers": list(to_train.keys()), "mode": "remote"})
+        eval_loss = None
+        if self.evaluate_after:
+            ds = self._dataset()
+            from ..data import dataset_tensors
+            x, y = dataset_tensors(ds, self.device)
+            eval_loss = evaluate(model.to(self.device), x, y, verbose=False)["loss"]
+            result["eval_loss"] = eval_loss
+        self.metrics.end_training(eval_loss)
+        self.trainings_done += 1
+        return result
+
+    async def _remote_rounds(self, alive, to_train, theta, cfg, loop, pool, model, result) -> torch.Tensor:
+        """The round loop of ``training_remote`` (fc.py:540-568): fan the fit RPC out to every live device, FedAvg what came
+        back, repeat.  Returns the final global parameters."""
         for r in range(self.enabled_round):
             log.info("\n\n#### ROUND {} #####".format(r))
             t0 = time.time()
@@ -367,6 +398,13 @@ class Coordinator(BusClient):
                 try:
                     fut = loop.run_in_executor(pool, lambda: worker.fit(theta, rcfg, timeout=self.fit_timeout))
                     flat, loss, n = await fut
+                    # a device's reply is untrusted input: a wrong-length or non-finite model would poison (or abort) the
+                    # whole average, so such a device counts as failed for this round
+                    flat = torch.as_tensor(flat, dtype=torch.float32).reshape(-1)
+                    if flat.numel() != theta.numel():
+                        raise ValueError(f"model of {flat.numel()} parameters returned, expected {theta.numel()}")
+                    if not bool(torch.isfinite(flat).all()):
+                        raise ValueError("model with non-finite parameters returned")
                     return wid, flat, loss, n
                 except Exception as e:  # noqa: BLE001 - a failing worker must not sink the round
                     log.info("Worker %s failed this round: %r", wid, e)
@@ -401,23 +439,7 @@ class Coordinator(BusClient):
             self._maybe_checkpoint(model, theta, r, {"workers": list(to_train.keys()), "mode": "remote"})
             if not alive:
                 break
-        pool.shutdown(wait=False)
-        for wid, worker in to_train.items():
-            log.info("Closing socket for " + str(wid))
-            worker.close()
-        self._deregister(to_train.keys())
-        unflatten_params(model, theta)
-        save_model(model, self.path, meta={"model": self.args.model, "rounds": self.enabled_round, "workers": list(to_train.keys()), "mode": "remote"})
-        eval_loss = None
-        if self.evaluate_after:
-            ds = self._dataset()
-            from ..data import dataset_tensors
-            x, y = dataset_tensors(ds, self.device)
-            eval_loss = evaluate(model.to(self.device), x, y, verbose=False)["loss"]
-            result["eval_loss"] = eval_loss
-        self.metrics.end_training(eval_loss)
-        self.trainings_done += 1
-        return result
+        return theta
 
     # ------------------------------------------------------------------ inference (remote only)
     def _inference(self, worker: RemoteWorkerClient) -> None:

@@ -50,15 +50,17 @@ def client_context(cafile: Optional[str] = None, certfile: Optional[str] = None,
 
 
 def contexts_from_cli(cafile: Optional[str], certfile: Optional[str], keyfile: Optional[str], server: bool,
-                      require_client_cert: bool = False) -> Optional[ssl.SSLContext]:
-    """CLI helper: no TLS flags → None (plain TCP, the reference's behaviour)."""
+                      require_client_cert: bool = False, check_hostname: bool = True) -> Optional[ssl.SSLContext]:
+    """CLI helper: no TLS flags → None (plain TCP, the reference's behaviour).  Client contexts verify the peer's name /
+    IP SAN by default — with a deployment-wide CA, chain verification alone would let any device holding *a* certificate
+    pose as the broker or as another device; ``--tls-no-verify-hostname`` is the explicit opt-out."""
     if not (cafile or certfile):
         return None
     if server:
         if not (certfile and keyfile):
             raise SystemExit("a TLS server needs --tls-cert and --tls-key")
         return server_context(certfile, keyfile, cafile, require_client_cert)
-    return client_context(cafile, certfile, keyfile, check_hostname=False)
+    return client_context(cafile, certfile, keyfile, check_hostname=check_hostname)
 
 
 def make_test_pki(directory: str, hosts=("127.0.0.1", "localhost")) -> Dict[str, str]:

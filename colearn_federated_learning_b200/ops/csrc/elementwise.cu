@@ -75,9 +75,13 @@ template <bool APPLY>
 __global__ void fedavg_kernel(float* __restrict__ theta, const float* __restrict__ slots,
                               int64_t slot_stride, const float* __restrict__ weights, int k,
                               float server_lr, int64_t n) {
-  __shared__ float sw[64];
-  if (threadIdx.x < k && threadIdx.x < 64) sw[threadIdx.x] = weights[threadIdx.x];
+  // no cap on the number of workers (the coordinator's upper bound is 100, selection 'all' applies none): the first
+  // kSw weights are staged in shared memory, any beyond that are read through the read-only cache
+  constexpr int kSw = 256;
+  __shared__ float sw[kSw];
+  for (int c = threadIdx.x; c < k && c < kSw; c += blockDim.x) sw[c] = weights[c];
   __syncthreads();
+  auto wt = [&](int c) -> float { return c < kSw ? sw[c] : __ldg(weights + c); };
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool aligned = (((uintptr_t)theta | (uintptr_t)slots) & 15) == 0 && (slot_stride & 3) == 0;
@@ -87,7 +91,7 @@ __global__ void fedavg_kernel(float* __restrict__ theta, const float* __restrict
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int c = 0; c < k; ++c) {
         const float4 v = __ldcs(reinterpret_cast<const float4*>(slots + c * slot_stride) + j);
-        const float w = sw[c];
+        const float w = wt(c);
         acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
         acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
       }
@@ -103,13 +107,13 @@ __global__ void fedavg_kernel(float* __restrict__ theta, const float* __restrict
     }
     for (int64_t j = (n4 << 2) + i0; j < n; j += stride) {
       float acc = 0.f;
-      for (int c = 0; c < k; ++c) acc = fmaf(sw[c], slots[c * slot_stride + j], acc);
+      for (int c = 0; c < k; ++c) acc = fmaf(wt(c), slots[c * slot_stride + j], acc);
       theta[j] = APPLY ? fmaf(server_lr, acc - theta[j], theta[j]) : acc;
     }
   } else {
     for (int64_t j = i0; j < n; j += stride) {
       float acc = 0.f;
-      for (int c = 0; c < k; ++c) acc = fmaf(sw[c], slots[c * slot_stride + j], acc);
+      for (int c = 0; c < k; ++c) acc = fmaf(wt(c), slots[c * slot_stride + j], acc);
       theta[j] = APPLY ? fmaf(server_lr, acc - theta[j], theta[j]) : acc;
     }
   }
@@ -367,13 +371,13 @@ cudaError_t launch_sgd_step_bf16grad(float* p, const void* g, float lr, int64_t 
 }
 cudaError_t launch_fedavg_apply(float* theta, const float* slots, int64_t slot_stride, const float* weights,
                                 int k, float server_lr, int64_t n, cudaStream_t s) {
-  if (k > 64) return cudaErrorInvalidValue;
+  if (k < 1) return cudaErrorInvalidValue;
   COLEARN_LAUNCH(fedavg_kernel<true>, grid_for(n), kThreads, 0, s, theta, slots, slot_stride, weights, k, server_lr, n);
   return cudaGetLastError();
 }
 cudaError_t launch_fedavg_flat(float* out, const float* slots, int64_t slot_stride, const float* weights,
                                int k, int64_t n, cudaStream_t s) {
-  if (k > 64) return cudaErrorInvalidValue;
+  if (k < 1) return cudaErrorInvalidValue;
   COLEARN_LAUNCH(fedavg_kernel<false>, grid_for(n), kThreads, 0, s, out, slots, slot_stride, weights, k, 1.f, n);
   return cudaGetLastError();
 }

@@ -438,11 +438,6 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
 #include "mlp_v2.inc"
 #undef V2_NS
 #undef V2_NT
-#define V2_NS v2_256
-#define V2_NT 256
-#include "mlp_v2.inc"
-#undef V2_NS
-#undef V2_NT
 // 128 threads, blocked reduction slices + pre-scaled dz (see the V2_BLOCKED comment in mlp_v2.inc)
 #define V2_NS v2_128b
 #define V2_NT 128
@@ -451,10 +446,14 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
 #undef V2_BLOCKED
 #undef V2_NS
 #undef V2_NT
-// 64 threads: one thread per neuron of a 64-wide layer (no shuffle levels in the dot products, two warps per barrier)
-#define V2_NS v2_64
-#define V2_NT 64
+// the blocked kernel with packed fp32 math (fma.rn.f32x2 / SASS FFMA2; see the V2_PACKED comment in mlp_v2.inc)
+#define V2_NS v2_128p
+#define V2_NT 128
+#define V2_BLOCKED 1
+#define V2_PACKED 1
 #include "mlp_v2.inc"
+#undef V2_PACKED
+#undef V2_BLOCKED
 #undef V2_NS
 #undef V2_NT
 
@@ -533,23 +532,23 @@ cudaError_t forward_t(const float* theta, const float* x, float* out, int n, cud
 
 cudaError_t launch_mlp_local_sgd(int net_kind, const ClientDesc* descs, int n_clients, SgdHyper hp,
                                  cudaStream_t stream) {
-  // variant 3 (default, set by ops/fused_mlp.py): register-resident weights, 128-thread CTA; 2: same with 256 threads;
-  // 4: same with 64 threads (one thread per neuron, not yet measured); 5: 128 threads, blocked slices (LDS.128) +
-  // pre-scaled dz (not yet measured);
-  // 1: first version with smem-resident weights (kept for A/B measurements)
+  // variant 5 (default, set by ops/fused_mlp.py): register-resident weights, 128-thread CTA, blocked reduction slices
+  // (LDS.128) + pre-scaled dz: 0.665 us/step (MLP 10-64-64-2) / 0.717 (FFNN) on a B200; 3: the same kernel with strided
+  // slices (the round-1 default: 0.699 / 0.795); 1: first version with smem-resident weights (1.66).  The 256-thread
+  // (0.83) and 64-thread (0.77) CTA shapes lost the A/B runs and were removed (profiles/README.md).
+  if (hp.variant == 6) {
+    switch (net_kind) {
+      case NET_FFNN: return v2_128p::launch2<FFNNNet>(descs, n_clients, hp, stream);
+      case NET_MLP64: return v2_128p::launch2<MLP64Net>(descs, n_clients, hp, stream);
+      case NET_TESTING_REMOTE: return v2_128p::launch2<TestingRemoteNet>(descs, n_clients, hp, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (hp.variant == 5) {
     switch (net_kind) {
       case NET_FFNN: return v2_128b::launch2<FFNNNet>(descs, n_clients, hp, stream);
       case NET_MLP64: return v2_128b::launch2<MLP64Net>(descs, n_clients, hp, stream);
       case NET_TESTING_REMOTE: return v2_128b::launch2<TestingRemoteNet>(descs, n_clients, hp, stream);
-      default: return cudaErrorInvalidValue;
-    }
-  }
-  if (hp.variant == 4) {
-    switch (net_kind) {
-      case NET_FFNN: return v2_64::launch2<FFNNNet>(descs, n_clients, hp, stream);
-      case NET_MLP64: return v2_64::launch2<MLP64Net>(descs, n_clients, hp, stream);
-      case NET_TESTING_REMOTE: return v2_64::launch2<TestingRemoteNet>(descs, n_clients, hp, stream);
       default: return cudaErrorInvalidValue;
     }
   }
@@ -561,14 +560,7 @@ cudaError_t launch_mlp_local_sgd(int net_kind, const ClientDesc* descs, int n_cl
       default: return cudaErrorInvalidValue;
     }
   }
-  if (hp.variant != 1) {
-    switch (net_kind) {
-      case NET_FFNN: return v2_256::launch2<FFNNNet>(descs, n_clients, hp, stream);
-      case NET_MLP64: return v2_256::launch2<MLP64Net>(descs, n_clients, hp, stream);
-      case NET_TESTING_REMOTE: return v2_256::launch2<TestingRemoteNet>(descs, n_clients, hp, stream);
-      default: return cudaErrorInvalidValue;
-    }
-  }
+  if (hp.variant != 1) return cudaErrorInvalidValue;
   switch (net_kind) {
     case NET_FFNN: return launch_t<FFNNNet>(descs, n_clients, hp, stream);
     case NET_MLP64: return launch_t<MLP64Net>(descs, n_clients, hp, stream);

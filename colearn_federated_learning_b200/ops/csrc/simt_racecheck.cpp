@@ -36,7 +36,7 @@ int main() {
   const int din[3] = {10, 10, 2}, dout[3] = {1, 2, 1};
   const int losses[3] = {LOSS_BCE, LOSS_XENT, LOSS_SSE};
   for (int kind = 0; kind < 3; ++kind)
-    for (int variant = 1; variant <= 5; ++variant)
+    for (int variant : {1, 3, 5, 6})
       for (int batch : {1, 3}) {
         const int P = mlp_net_num_params(kind), n = 7;
         std::vector<float> theta = randv(P, 0.3f), x = randv((size_t)n * din[kind]), y((size_t)n * (kind == 1 ? 1 : dout[kind]));

@@ -22,11 +22,10 @@ NET_KINDS = {
     ((2, 50, 10, 1), "none"): 2,
 }
 LOSS_CODES = {"bce": 0, "sse": 1, "xent": 2, "mse": 3}
-# 3 = register-resident weights, 128-thread CTA (default: fastest measured, profiles/r1_call4_*), 2 = same with
-# 256 threads, 4 = same with 64 threads (one thread per neuron; not yet measured), 5 = 128 threads with blocked reduction
-# slices (LDS.128) and pre-scaled dz (not yet measured; predicted -14 %), 1 = smem-resident weights (first
-# version, kept for A/B runs)
-KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "3"))
+# 5 = register-resident weights, 128-thread CTA, blocked reduction slices (LDS.128) + pre-scaled dz (default: fastest
+# measured — 0.665 us/step for the 10-64-64-2 MLP, 0.717 for the FFNN, profiles/README.md), 3 = the same kernel with
+# strided slices (round-1 default: 0.699 / 0.795), 1 = smem-resident weights (first version: 1.66)
+KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "5"))
 
 PtrLike = Union[torch.Tensor, int, None]
 

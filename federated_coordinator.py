@@ -75,6 +75,8 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--tls-ca", default=None, help="CA bundle: verify the broker / the devices (and, with --tls-cert on the embedded broker, demand client certificates)")
     parser.add_argument("--tls-cert", default=None, help="certificate for the embedded broker / client certificate towards broker and devices")
     parser.add_argument("--tls-key", default=None, help="private key belonging to --tls-cert")
+    parser.add_argument("--tls-no-verify-hostname", action="store_true",
+                        help="verify the certificate chain only, not that the certificate names the broker / device address")
     parser.add_argument("--inject", action="append", default=[], metavar="SPEC",
                         help="fault injection on the embedded broker: drop:<regex> | dup:<regex> | delay:<seconds>:<regex> (repeatable)")
     parser.add_argument("--exit-after", type=int, default=0, help="exit after N completed trainings (0 = run forever)")
@@ -112,7 +114,8 @@ def main(args: argparse.Namespace) -> None:
     from colearn_federated_learning_b200.control.tls import contexts_from_cli
 
     broker = None
-    client_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=False)
+    client_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=False,
+                                   check_hostname=not args.tls_no_verify_hostname)
     if args.embedded_broker:
         server_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=True,
                                        require_client_cert=bool(args.tls_ca)) if args.tls_cert else None
@@ -137,8 +140,15 @@ def main(args: argparse.Namespace) -> None:
     try:
         if args.exit_after > 0:
             coordinator.run(args.host, args.port, args.topic, forever=False)
-            while coordinator.trainings_done < args.exit_after:
+            # a window whose training raised counts too (it is in the scheduler's history with an "error" entry):
+            # otherwise one failing training would keep this loop spinning forever
+            def finished() -> int:
+                failed = sum(1 for rec in coordinator.windower.history if "error" in rec)
+                return coordinator.trainings_done + failed
+            while finished() < args.exit_after:
                 time.sleep(0.05)
+            if coordinator.windower.last_error is not None:
+                logging.error("last training failed: %r", coordinator.windower.last_error)
             coordinator.shutdown()
         else:
             coordinator.run(args.host, args.port, args.topic)

@@ -49,6 +49,7 @@ _OPTIONS = (
     (("--tls-ca",), dict(default=None, help="CA bundle: verify the broker; with --tls-cert also demand a client certificate from the coordinator")),
     (("--tls-cert",), dict(default=None, help="this device's certificate (RPC server side and client certificate towards the broker)")),
     (("--tls-key",), dict(default=None, help="private key belonging to --tls-cert")),
+    (("--tls-no-verify-hostname",), dict(action="store_true", help="verify the broker's certificate chain only, not its name / IP SAN")),
 )
 
 
@@ -97,7 +98,8 @@ def main(args: argparse.Namespace) -> None:  # pragma: no cover - exercised by t
 
     # one bus identity per device (the reference's shared literal id gets duplicates kicked)
     bus = BusClient(client_id="worker-" + identity, transport="tcp")
-    bus_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=False)
+    bus_tls = contexts_from_cli(args.tls_ca, args.tls_cert, args.tls_key, server=False,
+                                check_hostname=not args.tls_no_verify_hostname)
     if bus_tls is not None:
         bus.tls_set(context=bus_tls)
     if not args.no_will:

@@ -21,7 +21,7 @@ def test_extension_loaded():
 
 @pytest.mark.parametrize("ctor,loss", [(FFNN, "bce"), (FFNN, "sse"), (MLP, "xent"), (TestingRemote, "sse"), (TestingRemote, "mse")])
 @pytest.mark.parametrize("bsz,n,epochs,max_b", [(1, 97, 1, -1), (1, 200, 2, 150), (8, 203, 2, -1), (32, 64, 3, 5)])
-@pytest.mark.parametrize("variant", [2, 3, 1])
+@pytest.mark.parametrize("variant", [5, 6, 3, 1])
 def test_persistent_mlp_matches_reference(ctor, loss, bsz, n, epochs, max_b, variant):
     torch.manual_seed(0)
     model = ctor()

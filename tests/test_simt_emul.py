@@ -1,8 +1,8 @@
 """The persistent-MLP CUDA kernels (csrc/mlp_persistent.cu + mlp_v2.inc — the flagship op of BASELINE configs 1-3)
 executed on the CPU: the kernel *source* is compiled with g++ through csrc/host_shim.h (one OS thread per CUDA thread,
 __syncthreads / warp shuffles / dynamic shared memory emulated) and compared with the PyTorch definitions, exactly
-like tests/test_gpu_kernels.py does on a B200.  Every variant: v1 (weights in shared memory, 256 threads), v2 with 256
-and with 128 threads (register-resident row + column copies, replicated head)."""
+like tests/test_gpu_kernels.py does on a B200.  Every variant: v1 (weights in shared memory, 256 threads), v2 with 128
+threads (register-resident row + column copies, replicated head) in its strided (3), blocked (5) and blocked + packed-FMA (6) forms."""
 import pytest
 import torch
 
@@ -44,7 +44,7 @@ def _data(dims, loss, n, seed):
     return x, y
 
 
-CASES = [(k, loss, v, b) for k, (_, _, _, losses) in NETS.items() for loss in losses for v, b in ((3, 1), (2, 1), (1, 1), (3, 4), (4, 1), (4, 4), (5, 1), (5, 4))]
+CASES = [(k, loss, v, b) for k, (_, _, _, losses) in NETS.items() for loss in losses for v, b in ((3, 1), (1, 1), (3, 4), (5, 1), (5, 4), (6, 1), (6, 4))]
 
 
 @pytest.mark.parametrize("kind,loss,variant,batch", CASES)

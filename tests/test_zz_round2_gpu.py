@@ -533,33 +533,6 @@ def test_layerwise_trainer_dgrad_against_weights_in_place_on_device():
         assert float((outs[0] - o).abs().max()) < 2e-3 * max(1.0, float(outs[0].abs().max()))
 
 
-# ---- persistent MLP kernel variants written after the budget ran out: 5 = blocked slices (LDS.128) + pre-scaled dz, 4 = 64 threads ----
-@unvalidated
-@pytest.mark.parametrize("variant", [5, 4])
-@pytest.mark.parametrize("bsz,n,epochs,max_b", [(1, 97, 1, -1), (1, 200, 2, 150), (8, 203, 2, -1), (32, 64, 3, 5)])
-def test_persistent_mlp_new_variants_match_reference(bsz, n, epochs, max_b, variant):
-    from colearn_federated_learning_b200 import ops
-    from colearn_federated_learning_b200.models import FFNN, MLP, TestingRemote
-    from colearn_federated_learning_b200.ops import reference as R
-    dev = _dev()
-    for ctor, loss in ((FFNN, "bce"), (FFNN, "sse"), (MLP, "xent"), (TestingRemote, "sse"), (TestingRemote, "mse")):
-        torch.manual_seed(0)
-        model = ctor()
-        spec = model.spec
-        flat0 = flatten_params(model).clone()
-        x = torch.rand(n, spec.dims[0])
-        y = torch.randint(0, spec.dims[-1], (n, 1)).float() if loss == "xent" else (torch.rand(n, spec.dims[-1]) > 0.5).float()
-        perm = R.make_permutation(n, epochs, seed=5)
-        ref = flat0.clone()
-        ref_last = R.mlp_local_sgd(ref, spec.dims, x, y, perm, bsz, 0.05, epochs, max_b, loss, spec.out_activation)
-        got = flat0.clone().to(dev)
-        last = ops.mlp_local_sgd(got, spec.dims, x.to(dev), y.to(dev), perm.to(dev), bsz, 0.05, epochs, max_b, loss,
-                                 spec.out_activation, variant=variant)
-        torch.cuda.synchronize()
-        assert torch.allclose(got.cpu(), ref, atol=2e-4, rtol=2e-3), (ctor.__name__, loss, (got.cpu() - ref).abs().max())
-        assert torch.allclose(last.cpu(), ref_last, atol=1e-3, rtol=1e-2)
-
-
 @unvalidated
 def test_star_engine_pipelined_read_back_single_gpu():
     """read_back="pipelined": every round's losses reach the host (one round late), results equal the synchronous mode."""
