@@ -47,6 +47,9 @@ CONFIGS = {
                                              "4 481.6 s = 163.7 SGD steps/s on an RPi 3B+)"),
     "smpc": ("ffnn", 1000, 1, 1, None, "the reference's SMPC demo (paper Fig. 7): encrypted training of the FFNN on 1000 secret-shared items, "
                                        "2 workers + crypto provider (federated_coordinator.py -e code path)"),
+    "ref_local": ("ffnn", 8192, 1, 1, None, "the reference's local (VirtualWorker) training, fc.py:318-392, with one worker per GPU: FFNN 10-50-30-10-1 "
+                                            "(the reference's production model), sum-squared-error, batch 1, SGD lr 0.01, 1 local epoch over a fixed "
+                                            "8192-row CSV split into N contiguous shards, uniform FedAvg — the SAME config `--impl reference` runs"),
     "cfg1": ("mlp", 2048, 1, 1, None, "federated_coordinator.py VirtualWorker mode, 2 workers, 10-feature MLP, 1 round (BASELINE config 1, plumbing)"),
     "cfg2": ("mlp", 8192, 1, 1, None, "3-layer MLP 10-64-64-2, 1 local epoch, all workers (BASELINE config 2)"),
     "cfg3": ("mlp", 8192, 1, 5, 4, "same MLP, 5 local epochs, temporal window selects 4 of 8 (BASELINE config 3)"),
@@ -62,7 +65,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_nccl"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="default: ref_local (the config the reference arm runs) with BASELINE config 2 attached")
     ap.add_argument("--samples", type=int, default=None, help="total samples across all workers (strong scaling)")
     ap.add_argument("--batch-size", type=int, default=None)
     ap.add_argument("--local-epochs", type=int, default=None)
@@ -70,13 +74,6 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     return ap.parse_args()
-
-
-def reference_unavailable() -> None:
-    why = ("reference is a flat script tree without setup.py/pyproject (pip: 'not installable') and needs "
-           "syft==0.2.x + torch 1.4 + paho-mqtt, none of which are in the offline wheelhouse")
-    if int(os.environ.get("RANK", "0")) == 0:     # under torchrun every rank gets here; one JSON line for the job
-        print(json.dumps({"impl": "reference", "unavailable": why}))
 
 
 def make_data(model: str, total: int, rank: int, world: int, seed: int = 0):
@@ -321,6 +318,226 @@ def bench_smpc(args) -> None:
         "gpu_launches": 0}))
 
 
+def load_ref_local_data(total: int, rank: int, world: int):
+    """The config both bench arms share: the synthetic Bot-IoT CSV the reference arm trains on (written by the same
+    numpy-only generator, same seed), read through THIS repo's ``NetworkTrafficDataset`` (CSV -> feature selection -> MinMax),
+    split into ``world`` contiguous shards like ``dataset.federate(workers)`` (fc.py:347-350)."""
+    import tempfile
+
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    from reference_arm import write_synthetic_csv
+    from colearn_federated_learning_b200.data import NetworkTrafficDataset, shard_bounds
+
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "synthetic_unsw.csv")
+        write_synthetic_csv(path, total, seed=0)
+        x, y = NetworkTrafficDataset(path).tensors()
+    lo, hi = shard_bounds(total, world)[rank]
+    return x[lo:hi].contiguous(), y[lo:hi].contiguous()
+
+
+def run_engine_config(args, name: str, rank: int, world: int, device, full: bool = True):
+    """Measure one GPU config through ``FederatedEngine``; returns the JSON record on rank 0 (None elsewhere).
+    ``full=False``: the short form attached to the default line for a second config (no e2e-sync / self-check extras)."""
+    import torch
+    import torch.distributed as dist
+    from colearn_federated_learning_b200 import ops
+    from colearn_federated_learning_b200.parallel import FederatedEngine
+    from colearn_federated_learning_b200.utils.monitors import NvmlSampler
+
+    model, total, bsz, epochs, select_k, desc = CONFIGS[name]
+    total = args.samples or total
+    bsz = args.batch_size or bsz
+    epochs = args.local_epochs or epochs
+    K, W = args.steps, max(3, args.warmup)
+    ref_local = name == "ref_local"
+    x, y = load_ref_local_data(total, rank, world) if ref_local else make_data(model, total, rank, world)
+    n_local = x.shape[0]
+    mask = None
+    if select_k is not None and select_k < world:
+        mask = (1 << select_k) - 1  # registration order = rank order ("first" policy)
+    flush_buf = None if args.no_flush else torch.empty(160 * 1024 * 1024 // 4, device=device)  # 160 MB > 126 MB L2
+
+    def max_over_ranks(v: float) -> float:
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # reference local mode: sum-squared-error (cf.py:112), uniform FedAvg (PySyft federated_avg); BASELINE configs: n_k weights
+    engine = FederatedEngine(model, backend="fused", device=device, batch_size=bsz, lr=args.lr, local_epochs=epochs,
+                             weighted=not ref_local, loss="sse" if ref_local else "auto", seed=1, bf16_shadow=(model == "wide_mlp"))
+    engine.set_local_data(x, y)
+    for _ in range(W):
+        engine.run_rounds(1, masks=mask)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = NvmlSampler(index=device.index or 0, period_s=0.02)
+    sampler.start()
+    dev_ms, launches = 0.0, 0
+    for _ in range(K):
+        if flush_buf is not None:
+            ops.l2_flush(flush_buf)
+        rep = engine.run_rounds(1, masks=mask)
+        dev_ms += rep.device_ms
+        launches += rep.launches
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    dev_ms = max_over_ranks(dev_ms)
+    extra = dict(rep.extra)
+    # K rounds enqueued in one call: no host in the loop, no flush (what a training of K rounds costs on the device)
+    rep_p = engine.run_rounds(K, masks=mask)
+    extra["pipelined_rounds_per_s"] = K / (max_over_ranks(rep_p.device_ms) * 1e-3)
+    extra["final_mean_loss"] = float(rep_p.losses[-1, :, 1].mean()) if (rep_p.losses is not None and rank == 0) else None
+
+    e2e = None
+    if not args.no_e2e:
+        hx, hy = x.pin_memory(), y.pin_memory()
+        h2d = int(hx.numel() * hx.element_size() + hy.numel() * hy.element_size())
+        d2h = int(engine.loss_host.numel() * 4) if rank == 0 else 8
+
+        def timed(fn) -> float:
+            fn(2)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            fn(K)
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t0)
+
+        def per_call(k):       # one public-API call per round: H2D of the round's shard, the round, D2H of its losses, host sync
+            for _ in range(k):
+                engine.run_rounds(1, masks=mask, host_inputs=[(hx, hy)], read_back=True, barrier=False)
+
+        def one_call(k):       # the same k rounds in ONE call: every round still copies its inputs in and its losses out, the host
+            engine.run_rounds(k, masks=mask, host_inputs=[(hx, hy)] * k, read_back="pipelined", barrier=False)   # reads them one round late
+
+        wall_sync = timed(per_call)
+        if engine.algo == "star":
+            wall = timed(one_call)
+            losses_read = len(engine.loss_history) if rank == 0 else None
+            e2e = {"value": K / wall, "unit": "rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "timing": "host clock around ONE run_rounds(K) call, max over ranks, sync both sides; every round copies its shard "
+                             "H2D from pinned memory and its losses D2H; the host reads round i's losses while round i+1 runs",
+                   "losses_read_on_host": losses_read, "per_call_sync_value": K / wall_sync}
+        else:
+            e2e = {"value": K / wall_sync, "unit": "rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "timing": "host clock, one run_rounds(1) call per round with a host sync after its D2H, max over ranks"}
+
+    check = None
+    if full:
+        check = engine.verify_round(mask)        # fused round vs dist.broadcast + same local fit + dist.reduce, same inputs
+
+    value = K / (dev_ms * 1e-3)
+    if rank != 0:
+        return None
+    steps_per_round = epochs * ((n_local + bsz - 1) // bsz)
+    cfg = {"name": name, "model": model, "description": desc, "global_batch": bsz * world,
+           "batch_size_per_worker": bsz, "seq_len": None, "parallelism": f"fedavg-dp{world}",
+           "total_samples": total, "samples_per_worker": n_local, "local_epochs": epochs,
+           "local_sgd_steps_per_round": steps_per_round, "selected_workers": select_k or world,
+           "loss": engine.cfg.loss, "lr": args.lr,
+           "fedavg": "uniform (reference federated_avg)" if ref_local else "sample-count weighted",
+           "l2": "flushed between timed rounds (160 MB write)" if flush_buf is not None else "not flushed",
+           "shuffle": "keyed Feistel order computed inside the worker kernel every round (inside the timed region)",
+           "baseline_ref": "0.1133 rounds/s = 12 rounds x 1000 it on 2x RPi 3B+ (BASELINE.md)",
+           "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("COLEARN_")}, **extra}
+    if check is not None:
+        cfg["self_check"] = check
+    return {
+        "metric": "FL rounds/sec (whole box, device-timed, max over ranks)",
+        "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": value / PUBLISHED_ROUNDS_PER_S,
+        "dtype": "bf16" if model in ("resnet18", "wide_mlp") else "fp32",
+        "data": ("synthetic UNSW-IoT-shaped CSV (Bot-IoT 10-best header) / random-init weights" if ref_local else
+                 "synthetic UNSW-IoT-shaped features / random-init weights" if model != "resnet18"
+                 else "synthetic 32x32 images / random-init weights"),
+        "impl": "ours", "config": cfg,
+        "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []),
+                   "power_w_max": clocks.get("power_w_max"), "samples": clocks.get("samples")},
+        "e2e": e2e, "gpu_launches": launches,
+    }
+
+
+def run_torch_nccl(args, name: str, rank: int, world: int, device):
+    """The stock-PyTorch + NCCL comparator (baseline/torch_nccl_fedavg.py) on the same config."""
+    import torch
+    import torch.distributed as dist
+    from baseline.torch_nccl_fedavg import TorchNcclFedAvg
+    from colearn_federated_learning_b200.models import build_model, DEFAULT_LOSS
+    from colearn_federated_learning_b200.utils.monitors import NvmlSampler
+
+    model, total, bsz, epochs, select_k, desc = CONFIGS[name]
+    total, bsz, epochs = args.samples or total, args.batch_size or bsz, args.local_epochs or epochs
+    K, W = args.steps, max(3, args.warmup)
+    ref_local = name == "ref_local"
+    x, y = load_ref_local_data(total, rank, world) if ref_local else make_data(model, total, rank, world)
+    mask = (1 << select_k) - 1 if (select_k is not None and select_k < world) else None
+    flush_buf = None if args.no_flush else torch.empty(160 * 1024 * 1024 // 4, device=device)
+
+    def max_over_ranks(v: float) -> float:
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    torch.manual_seed(1)
+    eng = TorchNcclFedAvg(build_model(model), device, loss="sse" if ref_local else DEFAULT_LOSS[model], batch_size=bsz, lr=args.lr,
+                          epochs=epochs, weighted=not ref_local, bf16_autocast=(model in ("resnet18", "wide_mlp")))
+    eng.set_local_data(x, y)
+    hx, hy = x.pin_memory(), y.pin_memory()
+    for _ in range(W):
+        eng.run_round(mask)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = NvmlSampler(index=device.index or 0, period_s=0.02)
+    sampler.start()
+    dev_ms = 0.0
+    for _ in range(K):
+        if flush_buf is not None:
+            flush_buf.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.run_round(mask)
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms += e0.elapsed_time(e1)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    dev_ms = max_over_ranks(dev_ms)
+    e2e = None
+    if not args.no_e2e:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            eng.run_round(mask, host_inputs=(hx, hy))
+        torch.cuda.synchronize()
+        wall = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": K / wall, "unit": "rounds/s",
+               "h2d_bytes_per_step": int(hx.numel() * hx.element_size() + hy.numel() * hy.element_size()),
+               "d2h_bytes_per_step": 4, "timing": "host clock, max over ranks, sync both sides"}
+    if rank != 0:
+        return None
+    value = K / (dev_ms * 1e-3)
+    return {"metric": "FL rounds/sec (whole box, device-timed, max over ranks)", "value": value, "unit": "rounds/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": value / PUBLISHED_ROUNDS_PER_S, "dtype": "bf16" if model in ("resnet18", "wide_mlp") else "fp32",
+            "data": "synthetic / random-init weights", "impl": "torch_nccl_comparator",
+            "config": {"name": name, "model": model, "description": desc, "total_samples": total, "samples_per_worker": int(x.shape[0]),
+                       "batch_size_per_worker": bsz, "local_epochs": epochs, "parallelism": f"fedavg-dp{world}",
+                       "l2": "flushed between timed rounds" if flush_buf is not None else "not flushed",
+                       "shuffle": "torch.randperm on the host + H2D every round (inside the timed region)"},
+            "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", [])},
+            "e2e": e2e, "gpu_launches": 0}
+
+
 def main() -> None:
     args = parse_args()
     if args.impl == "reference":
@@ -329,20 +546,20 @@ def main() -> None:
         import reference_arm
         reference_arm.main(args)
         return
-    if args.config == "cfg1":
+    default_line = args.config is None
+    name = args.config or "ref_local"
+    if name == "cfg1":
         bench_cfg1(args)
         return
-    if args.config in ("paper", "fulldata"):
+    if name in ("paper", "fulldata"):
+        args.config = name
         bench_paper(args)
         return
-    if args.config == "smpc":
+    if name == "smpc":
         bench_smpc(args)
         return
 
-    import torch
-    import torch.distributed as dist
     from colearn_federated_learning_b200.parallel import init_distributed, shutdown
-    from colearn_federated_learning_b200.utils.monitors import NvmlSampler
 
     rank, world, device = init_distributed()
     if world != args.gpus and rank == 0:
@@ -350,166 +567,20 @@ def main() -> None:
     if device.type != "cuda":
         print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device on this box"}))
         return
-
-    model, total, bsz, epochs, select_k, desc = CONFIGS[args.config]
-    total = args.samples or total
-    bsz = args.batch_size or bsz
-    epochs = args.local_epochs or epochs
-    K, W = args.steps, max(3, args.warmup)
-    x, y = make_data(model, total, rank, world)
-    n_local = x.shape[0]
-    mask = None
-    if select_k is not None and select_k < world:
-        mask = (1 << select_k) - 1  # registration order = rank order ("first" policy)
-
-    flush_buf = None
-    if not args.no_flush:
-        flush_buf = torch.empty(160 * 1024 * 1024 // 4, device=device)  # 160 MB > 126 MB L2
-
-    def max_over_ranks(v: float) -> float:
-        t = torch.tensor([v], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sampler = NvmlSampler(index=device.index or 0, period_s=0.02)
-    launches = 0
-    extra = {}
-
-    if args.impl == "ours":
-        from colearn_federated_learning_b200 import ops
-        from colearn_federated_learning_b200.parallel import FederatedEngine
-
-        engine = FederatedEngine(model, backend="fused", device=device, batch_size=bsz, lr=args.lr, local_epochs=epochs,
-                                 weighted=True, seed=1, bf16_shadow=(model == "wide_mlp"))
-        engine.set_local_data(x, y)
-        for _ in range(W):
-            engine.run_rounds(1, masks=mask)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        sampler.start()
-        dev_ms = 0.0
-        for _ in range(K):
-            if flush_buf is not None:
-                ops.l2_flush(flush_buf)
-            rep = engine.run_rounds(1, masks=mask)
-            dev_ms += rep.device_ms
-            launches += rep.launches
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop()
-        dev_ms = max_over_ranks(dev_ms)
-        extra = dict(rep.extra)
-        # pipelined variant: K rounds enqueued in one call, no host in the loop, no flush
-        rep_p = engine.run_rounds(K, masks=mask)
-        extra["pipelined_rounds_per_s"] = K / (max_over_ranks(rep_p.device_ms) * 1e-3)
-        extra["final_mean_loss"] = float(rep_p.losses[-1, :, 1].mean()) if rep_p.losses is not None else None
-
-        e2e = None
-        if not args.no_e2e:
-            hx, hy = x.pin_memory(), y.pin_memory()
-            for _ in range(2):
-                engine.run_rounds(1, masks=mask, host_inputs=[(hx, hy)], read_back=True, barrier=False)
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            for _ in range(K):
-                engine.run_rounds(1, masks=mask, host_inputs=[(hx, hy)], read_back=True, barrier=False)
-            torch.cuda.synchronize()
-            wall = max_over_ranks(time.perf_counter() - t0)
-            e2e = {"value": K / wall, "unit": "rounds/s",
-                   "h2d_bytes_per_step": int(hx.numel() * hx.element_size() + hy.numel() * hy.element_size()),
-                   "d2h_bytes_per_step": int(engine.loss_host.numel() * 4) if rank == 0 else 8,
-                   "timing": "host clock, max over ranks, sync both sides"}
-            # the same K rounds through ONE run_rounds(K) call: every round still copies its inputs H2D from pinned memory
-            # and its losses D2H, but the host reads the losses one round late (engine.loss_history) — reported next to the
-            # per-call figure, never instead of it (first measured in round 2)
-            # opt-in (COLEARN_BENCH_E2E_ONE_CALL=1): a rank-local failure inside it would leave the other ranks in a collective
-            if getattr(engine, "algo", "") == "star" and os.environ.get("COLEARN_BENCH_E2E_ONE_CALL") == "1":
-                try:
-                    engine.run_rounds(2, masks=mask, host_inputs=[(hx, hy)] * 2, read_back="pipelined", barrier=False)
-                    torch.cuda.synchronize()
-                    if world > 1:
-                        dist.barrier()
-                    t0 = time.perf_counter()
-                    engine.run_rounds(K, masks=mask, host_inputs=[(hx, hy)] * K, read_back="pipelined", barrier=False)
-                    torch.cuda.synchronize()
-                    wall_p = max_over_ranks(time.perf_counter() - t0)
-                    extra["e2e_one_call_rounds_per_s"] = K / wall_p
-                    extra["e2e_one_call_losses_read"] = len(engine.loss_history) if rank == 0 else None
-                except Exception as exc:  # noqa: BLE001 - an unmeasured path must never take the bench line down
-                    extra["e2e_one_call_error"] = repr(exc)[:200]
-        impl = "ours"
-    else:  # torch_nccl comparator
-        from baseline.torch_nccl_fedavg import TorchNcclFedAvg
-        from colearn_federated_learning_b200.models import build_model, DEFAULT_LOSS
-
-        torch.manual_seed(1)
-        eng = TorchNcclFedAvg(build_model(model), device, loss=DEFAULT_LOSS[model], batch_size=bsz, lr=args.lr,
-                              epochs=epochs, weighted=True, bf16_autocast=(model in ("resnet18", "wide_mlp")))
-        eng.set_local_data(x, y)
-        hx, hy = x.pin_memory(), y.pin_memory()
-        for _ in range(W):
-            eng.run_round(mask)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        sampler.start()
-        dev_ms = 0.0
-        for _ in range(K):
-            if flush_buf is not None:
-                flush_buf.fill_(1.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            eng.run_round(mask)
-            e1.record()
-            torch.cuda.synchronize()
-            dev_ms += e0.elapsed_time(e1)
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop()
-        dev_ms = max_over_ranks(dev_ms)
-        e2e = None
-        if not args.no_e2e:
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(K):
-                eng.run_round(mask, host_inputs=(hx, hy))
-            torch.cuda.synchronize()
-            wall = max_over_ranks(time.perf_counter() - t0)
-            e2e = {"value": K / wall, "unit": "rounds/s",
-                   "h2d_bytes_per_step": int(hx.numel() * hx.element_size() + hy.numel() * hy.element_size()),
-                   "d2h_bytes_per_step": 4, "timing": "host clock, max over ranks, sync both sides"}
-        impl = "torch_nccl_comparator"
-
-    value = K / (dev_ms * 1e-3)
-    if rank == 0:
-        steps_per_round = epochs * ((n_local + bsz - 1) // bsz)
-        out = {
-            "metric": "FL rounds/sec (whole box, device-timed, max over ranks)",
-            "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": value / PUBLISHED_ROUNDS_PER_S,
-            "dtype": "bf16" if model in ("resnet18", "wide_mlp") else "fp32",
-            "data": "synthetic UNSW-IoT-shaped features / random-init weights" if model != "resnet18"
-                    else "synthetic 32x32 images / random-init weights",
-            "impl": impl,
-            "config": {"name": args.config, "model": model, "description": desc, "global_batch": bsz * world,
-                       "batch_size_per_worker": bsz, "seq_len": None, "parallelism": f"fedavg-dp{world}",
-                       "total_samples": total, "samples_per_worker": n_local, "local_epochs": epochs,
-                       "local_sgd_steps_per_round": steps_per_round, "selected_workers": select_k or world,
-                       "fedavg": "sample-count weighted", "l2": "flushed between timed rounds (160 MB write)" if flush_buf is not None else "not flushed",
-                       "baseline_ref": "0.1133 rounds/s = 12 rounds x 1000 it on 2x RPi 3B+ (BASELINE.md)",
-                       # opt-in switches in effect (all default to off: an empty dict is the validated configuration)
-                       "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("COLEARN_")}, **extra},
-            "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []),
-                       "power_w_max": clocks.get("power_w_max"), "samples": clocks.get("samples")},
-            "e2e": e2e,
-            "gpu_launches": launches,
-        }
+    if args.impl == "torch_nccl":
+        out = run_torch_nccl(args, name, rank, world, device)
+    else:
+        out = run_engine_config(args, name, rank, world, device)
+        if default_line:
+            # the default line is the config BOTH arms can run (the reference's own model and local-training path); BASELINE.json's
+            # config 2 (MLP 10-64-64-2, n_k-weighted) is measured in the same process and attached, so the round-1 headline
+            # (BENCH_r01: cfg2) stays comparable
+            also = run_engine_config(args, "cfg2", rank, world, device, full=False)
+            if out is not None and also is not None:
+                out["config"]["also_measured"] = {"cfg2": {k: also[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches")}
+                                                  | {"description": also["config"]["description"],
+                                                     "pipelined_rounds_per_s": also["config"].get("pipelined_rounds_per_s")}}
+    if rank == 0 and out is not None:
         print(json.dumps(out))
     shutdown()
 

@@ -34,17 +34,19 @@ from ..ops import conv as C
 BF = torch.bfloat16
 PAD = 128
 
-# Step schedule (docs/ROUND2_NOTES.md).  Every entry is a re-scheduling / operand-layout choice with the same
-# mathematical result; an entry goes to its non-zero value here once its row has been measured on a B200.  The
-# environment (COLEARN_CONV_<NAME>=<int>) overrides in both directions, constructor arguments override the environment.
+# Step schedule.  Every entry is a re-scheduling / operand-layout choice with the same mathematical result.  The values
+# below are the fastest combination measured on a B200 (profiles/README.md, round 2: 1.87 ms -> 1.07 ms per batch-128
+# ResNet-18 step); 0 everywhere is the round-1 schedule (explicit im2col, K-major operands from transposed copies, one
+# stream).  The environment (COLEARN_CONV_<NAME>=<int>) overrides in both directions, constructor arguments override
+# the environment.
 SCHEDULE_DEFAULTS = {
-    "STREAMS": 0,     # 1: wgrad chains on a second stream inside the step graph
-    "SHADOW_T": 0,    # 1: W^T written by the wgrad epilogue instead of a transpose launch
-    "FUSED_BN": 0,    # 1: BatchNorm reduction + finalize in one launch
-    "SPLITK": 0,      # 1: split-K for the skinny wgrad GEMMs, 2: also the layer4 forwards
-    "WGRAD_MN": 0,    # 1: wgrad GEMMs read dz / col in place (MN-major operands)
-    "DGRAD_KN": 0,    # 1: dgrad GEMMs read the packed weights (MN-major B), no W^T copies
-    "IMPLICIT": 0,    # 1: implicit-GEMM forward + dgrad for the stride-1 3x3 convs, 2: wgrad too
+    "STREAMS": 1,     # 1: wgrad chains on a second stream inside the step graph
+    "SHADOW_T": 0,    # 1: W^T written by the wgrad epilogue instead of a transpose launch (moot with DGRAD_KN: no W^T exists)
+    "FUSED_BN": 1,    # 1: BatchNorm reduction + finalize in one launch
+    "SPLITK": 1,      # 1: split-K for the skinny wgrad GEMMs, 2: also the layer4 forwards
+    "WGRAD_MN": 1,    # 1: wgrad GEMMs read dz / col in place (MN-major operands)
+    "DGRAD_KN": 1,    # 1: dgrad GEMMs read the packed weights (MN-major B), no W^T copies
+    "IMPLICIT": 2,    # 1: implicit-GEMM forward + dgrad for the stride-1 3x3 convs, 2: wgrad too
 }
 
 

@@ -64,12 +64,13 @@ class LayerwiseMLPTrainer:
     def __init__(self, spec: MLPSpec, flat: torch.Tensor, batch_size: int, shadow: Optional[torch.Tensor] = None,
                  dgrad_kn: Optional[bool] = None, wgrad_mn: Optional[bool] = None) -> None:
         self.spec, self.B, self.dev = spec, batch_size, flat.device
-        # opt-in (COLEARN_MLP_DGRAD_KN=1, not yet measured): the dgrad reads W_l [out, in] in place as an MN-major B operand
-        # (gemm_bf16(b_kn=True)), so no W^T copy exists: one 64 MB transpose pass per 4096 x 4096 layer and step less
-        self.dgrad_kn = (os.environ.get("COLEARN_MLP_DGRAD_KN", "0") == "1") if dgrad_kn is None else bool(dgrad_kn)
-        # opt-in (COLEARN_MLP_WGRAD_MN=1, not yet measured): the wgrad reads dz_l [B, out] and a_l [B, in] in place as MN-major
+        # default (COLEARN_MLP_DGRAD_KN=0 restores the W^T copies): the dgrad reads W_l [out, in] in place as an MN-major B
+        # operand (gemm_bf16(b_kn=True)), so no W^T copy exists: one 64 MB transpose pass per 4096 x 4096 layer and step less.
+        # Measured on a B200, cfg5 at N=1: 179.2 -> 205.5 rounds/s; with the in-place wgrad below 209.5 (profiles/README.md)
+        self.dgrad_kn = (os.environ.get("COLEARN_MLP_DGRAD_KN", "1") == "1") if dgrad_kn is None else bool(dgrad_kn)
+        # default (COLEARN_MLP_WGRAD_MN=0: transposed copies): the wgrad reads dz_l [B, out] and a_l [B, in] in place as MN-major
         # operands (gemm_bf16(mn_m=...)): no transposed activations / gradients are written by the producing epilogues
-        self.wgrad_mn = (os.environ.get("COLEARN_MLP_WGRAD_MN", "0") == "1") if wgrad_mn is None else bool(wgrad_mn)
+        self.wgrad_mn = (os.environ.get("COLEARN_MLP_WGRAD_MN", "1") == "1") if wgrad_mn is None else bool(wgrad_mn)
         self.dims = list(spec.dims)
         self.L = spec.n_layers
         self.offsets = spec.offsets()

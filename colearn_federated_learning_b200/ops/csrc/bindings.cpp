@@ -30,7 +30,7 @@ inline T* ptr_of(int64_t p) { return reinterpret_cast<T*>(static_cast<uintptr_t>
 py::bytes make_client_desc(int64_t x, int64_t y, int64_t perm, int64_t theta_in, int64_t theta_out,
                            int64_t loss_out, int64_t wait_flag, int64_t wait_value, int64_t signal_flag,
                            int64_t signal_value, int64_t n, int64_t perm_rows, int64_t y_dim,
-                           double out_scale, int64_t delta_mode) {
+                           double out_scale, int64_t delta_mode, int64_t perm_seed, int64_t perm_row0) {
   ClientDesc d;
   std::memset(&d, 0, sizeof(d));
   d.x = ptr_of<const float>(x);
@@ -48,6 +48,8 @@ py::bytes make_client_desc(int64_t x, int64_t y, int64_t perm, int64_t theta_in,
   d.signal_value = (uint32_t)signal_value;
   d.out_scale = (float)out_scale;
   d.delta_mode = (int)delta_mode;
+  d.perm_seed = (uint64_t)perm_seed;
+  d.perm_row0 = (int)perm_row0;
   return py::bytes(reinterpret_cast<const char*>(&d), sizeof(d));
 }
 int64_t client_desc_size() { return (int64_t)sizeof(ClientDesc); }
@@ -163,6 +165,14 @@ torch::Tensor minmax_scale(torch::Tensor x) {
   return out;
 }
 torch::Tensor feistel_permutation(int64_t n, int64_t rows, int64_t seed, torch::Device device) {
+  if (device.is_cpu()) {   // the same bijection on the host (tests; CPU-side users of a kernel-generated order)
+    auto out = torch::empty({rows, n}, torch::TensorOptions().dtype(at::kInt));
+    const FeistelDomain dom = feistel_domain((uint32_t)n);
+    int* p = out.data_ptr<int>();
+    for (int64_t r = 0; r < rows; ++r)
+      for (int64_t i = 0; i < n; ++i) p[r * n + i] = (int)feistel_index((uint32_t)i, (uint32_t)n, dom, (uint64_t)seed, (int)r);
+    return out;
+  }
   c10::cuda::CUDAGuard guard(device);
   auto out = torch::empty({rows, n}, torch::TensorOptions().dtype(at::kInt).device(device));
   check(launch_feistel_permutation(out.data_ptr<int>(), (int)n, (int)rows, (uint64_t)seed, cur_stream()), "feistel");
@@ -417,17 +427,13 @@ void gemm_tcgen05(torch::Tensor A, torch::Tensor B, c10::optional<torch::Tensor>
   ep.ready_elem_offset = ready_elem_offset;
   ep.tile_n = (int)tile_n;
   ep.cluster = (int)cluster;
-  ep.pdl = pdl_enabled() ? 1 : 0;      // COLEARN_PDL=1: programmatic dependent launch (docs/ROUND2_NOTES.md)
-  // COLEARN_GEMM_STAGED=1: line-coalesced epilogue (a 4th element of `produced` >= 0 overrides it per call)
-  static const int staged_env = (std::getenv("COLEARN_GEMM_STAGED") && std::getenv("COLEARN_GEMM_STAGED")[0] == '1') ? 1 : 0;
-  ep.staged = staged_env;
+  ep.pdl = pdl_enabled() ? 1 : 0;      // programmatic dependent launch (on unless COLEARN_PDL=0)
   // produced = [ProducedSignal* (device), arena element of sgd_master[0, 0], max_ctas]: fused wgrad -> FedAvg reduce
   if (!produced.empty()) {
-    TORCH_CHECK(produced.size() == 3 || produced.size() == 4, "produced = [signal_ptr, elem_offset, max_ctas(, staged)]");
+    TORCH_CHECK(produced.size() == 3, "produced = [signal_ptr, elem_offset, max_ctas]");
     ep.produced = ptr_of<const ProducedSignal>(produced[0]);
     ep.produced_elem_offset = produced[1];
     ep.max_ctas = (int)produced[2];
-    if (produced.size() == 4 && produced[3] >= 0) ep.staged = (int)produced[3];
   }
   if (split_k > 1) {
     TORCH_CHECK(split_out.has_value() && split_out->is_cuda() && split_out->scalar_type() == at::kFloat && split_out->is_contiguous() &&

@@ -250,35 +250,14 @@ __global__ void minmax_scale_kernel(const float* __restrict__ x, float* __restri
     out[(size_t)r * cols + c] = (x[(size_t)r * cols + c] - lo) * inv;
 }
 
-// Keyed bijection on [0, n): 4-round Feistel network over 2*hb bits with cycle walking.
-__device__ __forceinline__ uint32_t mix32(uint32_t x, uint32_t k) {
-  x ^= k; x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
-  return x;
-}
+// Keyed random permutations, one row per epoch (the bijection itself: feistel_index in colearn_kernels.h)
 __global__ void feistel_perm_kernel(int* __restrict__ out, int n, int rows, uint64_t seed) {
-  int bits = 1;
-  while ((1u << bits) < (uint32_t)n) ++bits;
-  const int hb = (bits + 1) >> 1;  // half width
-  const uint32_t mask = (1u << hb) - 1u;
+  const FeistelDomain dom = feistel_domain((uint32_t)n);
   const int64_t total = (int64_t)n * rows;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     const int row = (int)(e / n);
-    uint32_t v = (uint32_t)(e - (int64_t)row * n);
-    const uint32_t k0 = (uint32_t)seed ^ (0x51ED270Bu * (uint32_t)(row + 1));
-    const uint32_t k1 = (uint32_t)(seed >> 32) + 0x68E31DA4u * (uint32_t)(row + 1);
-    do {
-      uint32_t l = v >> hb, r = v & mask;
-#pragma unroll
-      for (int round = 0; round < 4; ++round) {
-        const uint32_t f = mix32(r, (round & 1 ? k1 : k0) + 0x9E3779B9u * round) & mask;
-        const uint32_t nl = r;
-        r = l ^ f;
-        l = nl;
-      }
-      v = (l << hb) | r;
-    } while (v >= (uint32_t)n);
-    out[e] = (int)v;
+    out[e] = (int)feistel_index((uint32_t)(e - (int64_t)row * n), (uint32_t)n, dom, seed, row);
   }
 }
 

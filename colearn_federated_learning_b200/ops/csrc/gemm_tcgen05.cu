@@ -36,7 +36,6 @@ constexpr int UMMA_K = 16;
 constexpr int kAccStages = 2;
 constexpr int kEpilogueWarps = 8;                 // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kEpilogueStageBytes = kEpilogueWarps * 32 * 32 * 4;   // GemmEpilogue::staged: one 32 x 32 fp32 transpose buffer per warp
 constexpr int kMaxStages = 6;
 // Tile config.  BN = 256 halves the B-operand smem traffic per FLOP (128x128x16 UMMAs sit exactly at the
 // 128 B/clk smem limit: 8 KB of operands per 64-cycle instruction; 128x256x16 needs 12 KB per 128 cycles).
@@ -52,19 +51,13 @@ struct Cfg {
 
 std::string g_last_error;
 
-// Opt-in limit of dynamic shared memory: operand stages + barriers, plus the staged epilogue's transpose buffers when the
-// device grants them (B200: 227 KB per CTA; 225 KB asked).  If it does not, the default epilogue keeps working and a
-// staged launch is refused.
-bool g_staged_ok[64] = {};
+// Opt-in limit of dynamic shared memory: operand stages + barriers
 inline cudaError_t configure_smem(const void* kernel, int base_bytes, int dev) {
 #ifdef COLEARN_HOST_SHIM
-  (void)kernel; (void)base_bytes;
-  g_staged_ok[dev & 63] = true;
+  (void)kernel; (void)base_bytes; (void)dev;
   return cudaSuccess;
 #else
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, base_bytes + kEpilogueStageBytes);
-  if (e == cudaSuccess) { g_staged_ok[dev & 63] = true; return e; }
-  (void)cudaGetLastError();
+  (void)dev;
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, base_bytes);
 #endif
 }
@@ -266,7 +259,7 @@ struct SharedBarriers {
   uint32_t tmem_base;
 };
 
-static_assert(sizeof(SharedBarriers) <= 256, "the barriers own 256 bytes behind the operand stages; the staged epilogue's buffers follow");
+static_assert(sizeof(SharedBarriers) <= 256, "the barriers own 256 bytes behind the operand stages");
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -371,111 +364,6 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const Ge
   }
 }
 
-// Line-coalesced form of epilogue_chunk (GemmEpilogue::staged).  tcgen05.ld hands every lane one accumulator ROW, so the
-// row-per-thread epilogue touches 32 different 128-byte lines with every 16-byte access: 32 L1 wavefronts per instruction,
-// which — not DRAM — bounds the read-modify-write of the fused-SGD wgrad (measured 2.8 TB/s, profiles/README.md §3).  Here the
-// warp transposes its 32 x 32 fp32 block through a private 4 KB shared-memory buffer (16-byte units XOR-swizzled with the
-// row, so both the row-per-lane writes and the 4-rows-per-instruction reads are bank-conflict free) and every global
-// access of the [M, N] row-major operands (fp32 master, bf16 shadow / output / ReLU mask / addend) covers 4 full rows of
-// 128 contiguous bytes per instruction.  The transposed bf16 copies are written from the row-per-lane layout (there the
-// 32 lanes ARE 32 consecutive rows = 64 contiguous bytes of a transposed row), after a second trip through the buffer when
-// the values changed in between (mask, addend, SGD).
-constexpr int kStageBytesPerWarp = 32 * 32 * 4;
-#ifdef COLEARN_HOST_SHIM
-inline void sts_f4(float4* p, const float4& v) { *p = v; }
-inline float4 lds_f4(const float4* p) { return *p; }
-#else
-// explicit shared-window accesses (through a generic pointer the compiler emits generic LD / ST)
-__device__ __forceinline__ void sts_f4(float4* p, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float4 lds_f4(const float4* p) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-#endif
-__device__ __forceinline__ void epilogue_chunk_staged(const uint32_t (&v)[32], const GemmEpilogue& ep, int row, int col, int lane,
-                                                      int q, int m0, int M, int N, float4* st) {
-  float f[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  if (ep.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] += __ldg(ep.bias + col + j);
-  }
-  if (ep.relu) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sts_f4(st + lane * 8 + (j ^ (lane & 7)), make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
-  __syncwarp();
-  const int sub = lane >> 3, u = lane & 7;
-  const int row0 = row - lane;                    // first row of this warp's 32-row block
-  const bool changed = ep.relu_mask != nullptr || ep.addend != nullptr || ep.sgd_master != nullptr;
-  const bool need_t = ep.sgd_master != nullptr ? ep.sgd_shadow_t != nullptr : ep.out_bf16_t != nullptr;
-  float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = 4 * i + sub;
-    const int slot = r * 8 + (u ^ (r & 7));
-    float4 x = lds_f4(st + slot);
-    const size_t g = (size_t)(row0 + r) * N + col + u * 4;
-    if (ep.relu_mask != nullptr) {
-      const uint2 mv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(ep.relu_mask) + g));
-      // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-      if (!((mv.x & 0xFFFFu) != 0 && !(mv.x & 0x8000u))) x.x = 0.f;
-      if (!((mv.x >> 16) != 0 && !(mv.x & 0x80000000u))) x.y = 0.f;
-      if (!((mv.y & 0xFFFFu) != 0 && !(mv.y & 0x8000u))) x.z = 0.f;
-      if (!((mv.y >> 16) != 0 && !(mv.y & 0x80000000u))) x.w = 0.f;
-    }
-    if (ep.addend != nullptr) {
-      const uint2 av = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(ep.addend) + g));
-      x.x += __uint_as_float(av.x << 16); x.y += __uint_as_float(av.x & 0xFFFF0000u);
-      x.z += __uint_as_float(av.y << 16); x.w += __uint_as_float(av.y & 0xFFFF0000u);
-    }
-    cs0 += x.x; cs1 += x.y; cs2 += x.z; cs3 += x.w;
-    if (ep.sgd_master != nullptr) {
-      float4* mp = reinterpret_cast<float4*>(ep.sgd_master + g);
-      float4 w = *mp;
-      w.x = fmaf(-ep.sgd_lr, x.x, w.x); w.y = fmaf(-ep.sgd_lr, x.y, w.y);
-      w.z = fmaf(-ep.sgd_lr, x.z, w.z); w.w = fmaf(-ep.sgd_lr, x.w, w.w);
-      *mp = w;
-      x = w;                                      // from here on: the new weights
-      if (ep.sgd_shadow != nullptr)
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.sgd_shadow) + g) = make_uint2(pack2(x.x, x.y), pack2(x.z, x.w));
-    } else {
-      if (ep.out_f32 != nullptr) *reinterpret_cast<float4*>(ep.out_f32 + g) = x;
-      if (ep.out_bf16 != nullptr)
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + g) = make_uint2(pack2(x.x, x.y), pack2(x.z, x.w));
-    }
-    if (need_t && changed) sts_f4(st + slot, x);
-  }
-  if (ep.colsum != nullptr) {
-    // bias gradient partials: rows of this block are spread over (i, sub); lanes with equal u hold the same 4 columns
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      cs0 += __shfl_xor_sync(0xffffffffu, cs0, o); cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
-      cs2 += __shfl_xor_sync(0xffffffffu, cs2, o); cs3 += __shfl_xor_sync(0xffffffffu, cs3, o);
-    }
-    if (sub == 0) *reinterpret_cast<float4*>(ep.colsum + (size_t)((m0 >> 5) + q) * N + col + u * 4) = make_float4(cs0, cs1, cs2, cs3);
-  }
-  if (need_t) {
-    if (changed) {
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = lds_f4(st + lane * 8 + (j ^ (lane & 7)));
-        f[4 * j] = t.x; f[4 * j + 1] = t.y; f[4 * j + 2] = t.z; f[4 * j + 3] = t.w;
-      }
-    }
-    __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(ep.sgd_master != nullptr ? ep.sgd_shadow_t : ep.out_bf16_t);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) tp[(size_t)(col + j) * M + row] = __float2bfloat16(f[j]);
-  }
-  __syncwarp();                                   // the next chunk reuses the buffer
-}
 
 // CL = 2: thread-block cluster of two CTAs working on vertically adjacent tiles (same n-block).  Each CTA fetches
 // its own A tile and HALF of the shared B tile, multicasting that half into both CTAs' shared memory, which cuts
@@ -643,8 +531,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;          // 0: columns [0, BN/2), 1: [BN/2, BN)
-    // ep.staged: this warp's 4 KB transpose buffer behind the barriers (the launch then asks for kEpilogueStageBytes more)
-    float4* stage_buf = reinterpret_cast<float4*>(smem + kStages * kStageBytes + 256 + (warp - 2) * kStageBytesPerWarp);
     int local = 0;
     for (int tile = work0; tile < total_work; tile += work_stride, ++local) {
       int mu, nb;
@@ -668,8 +554,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int g = 0; g < 8; ++g)
             op[g] = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
                                 __uint_as_float(v[g * 4 + 3]));
-        } else if (ep.staged) {
-          epilogue_chunk_staged(v, ep, row, n0 + c0, lane, q, m0, M, N, stage_buf);
         } else {
           epilogue_chunk(v, ep, row, n0 + c0, lane, q, m0, M, N);
         }
@@ -811,7 +695,6 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
-  if (ep.staged && !g_staged_ok[dev & 63]) { g_last_error = "staged epilogue: the device does not grant the extra 32 KB of shared memory"; return cudaErrorInvalidValue; }
   const int work = (M / BM / CL) * (N / BN) * ((CL == 1 && ep.split_k > 1) ? ep.split_k : 1);
   int units = num_sms[dev & 63] / CL;          // persistent: one CTA (or CTA pair) per SM (pair)
   if (ep.max_ctas > 0 && ep.max_ctas / CL < units) units = ep.max_ctas / CL;
@@ -820,13 +703,13 @@ cudaError_t launch_t(const void* A, const void* B, int M, int N, int K, const Ge
 #ifdef COLEARN_HOST_SHIM
   if (CL != 1) { g_last_error = "clusters are not modelled on the host"; return cudaErrorNotSupported; }
   void (*kern)(CUtensorMap, CUtensorMap, int, int, int, GemmEpilogue) = gemm_tcgen05_kernel<BN, CL>;
-  COLEARN_LAUNCH(kern, units * CL, kThreads, C::kSmemBytes + (ep.staged ? kEpilogueStageBytes : 0), s, ta, tb, M, N, K, ep);
+  COLEARN_LAUNCH(kern, units * CL, kThreads, C::kSmemBytes, s, ta, tb, M, N, K, ep);
   return cudaSuccess;
 #else
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(units * CL);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = C::kSmemBytes + (ep.staged ? kEpilogueStageBytes : 0);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -887,13 +770,12 @@ cudaError_t launch_mn(const void* A, int a_cols, const void* B, int b_rows, int 
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
-  if (ep.staged && !g_staged_ok[dev & 63]) { g_last_error = "staged epilogue: the device does not grant the extra 32 KB of shared memory"; return cudaErrorInvalidValue; }
   const int work = (M / BM) * (N / BN) * (ep.split_k > 1 ? ep.split_k : 1);
   int units = num_sms[dev & 63];
   if (ep.max_ctas > 0 && ep.max_ctas < units) units = ep.max_ctas;
   if (work < units) units = work;
   if (units < 1) units = 1;
-  return launch_1cta(gemm_tcgen05_kernel<BN, 1, AMN, true>, units, C::kSmemBytes + (ep.staged ? kEpilogueStageBytes : 0), s, ta, tb, M, N, K, ep);
+  return launch_1cta(gemm_tcgen05_kernel<BN, 1, AMN, true>, units, C::kSmemBytes, s, ta, tb, M, N, K, ep);
 }
 
 
@@ -1023,7 +905,6 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     // ===== epilogue warps 2..9 (both CTAs): my 128 rows of the 256-row tile =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    float4* stage_buf = reinterpret_cast<float4*>(smem + kStages * kStageBytes + 256 + (warp - 2) * kStageBytesPerWarp);
     int local = 0;
     for (int tile = work0; tile < total_work; tile += work_stride, ++local) {
       int mu, nb;
@@ -1039,8 +920,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
         tmem_ld_wait();
-        if (ep.staged) epilogue_chunk_staged(v, ep, row, n0 + c0, lane, q, m0, M, N, stage_buf);
-        else epilogue_chunk(v, ep, row, n0 + c0, lane, q, m0, M, N);
+        epilogue_chunk(v, ep, row, n0 + c0, lane, q, m0, M, N);
       }
       tc_fence_before();
       __syncwarp();
@@ -1078,7 +958,6 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
-  if (ep.staged && !g_staged_ok[dev & 63]) { g_last_error = "staged epilogue: the device does not grant the extra 32 KB of shared memory"; return cudaErrorInvalidValue; }
   const int work = (M / (2 * BM)) * (N / C::BN);
   int units = num_sms[dev & 63] / 2;
   if (ep.max_ctas > 0 && ep.max_ctas / 2 < units) units = ep.max_ctas / 2;
@@ -1092,7 +971,7 @@ cudaError_t launch_2sm(const void* A, const void* B, int M, int N, int K, const 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(units * 2);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = C::kSmemBytes + (ep.staged ? kEpilogueStageBytes : 0);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1134,13 +1013,12 @@ cudaError_t launch_conv_t(const void* act, int n_images, int H, int W, const voi
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
-  if (ep.staged && !g_staged_ok[dev & 63]) { g_last_error = "staged epilogue: the device does not grant the extra 32 KB of shared memory"; return cudaErrorInvalidValue; }
   const int work = (M / BM) * (N / BN) * (ep.split_k > 1 ? ep.split_k : 1);
   int units = num_sms[dev & 63];
   if (ep.max_ctas > 0 && ep.max_ctas < units) units = ep.max_ctas;
   if (work < units) units = work;
   if (units < 1) units = 1;
-  return launch_1cta(gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>, units, C::kSmemBytes + (ep.staged ? kEpilogueStageBytes : 0), s, ta, tb, M, N, K, ep);
+  return launch_1cta(gemm_tcgen05_kernel<BN, 1, WGRAD, BMN>, units, C::kSmemBytes, s, ta, tb, M, N, K, ep);
 }
 
 cudaError_t launch_gemm_tcgen05_conv(const void* act, int n_images, int H, int W, const void* other, int other_rows, int other_cols,

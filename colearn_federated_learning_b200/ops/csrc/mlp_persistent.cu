@@ -326,6 +326,7 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
   }
   const int n_chunks = (int)((Q + CHUNK - 1) / CHUNK);
 
+  const FeistelDomain fdom = feistel_domain((uint32_t)(n > 0 ? n : 1));   // in-kernel shuffle (ClientDesc::perm_seed)
   float pre[EPT];
   auto issue_loads = [&](int chunk) {
 #pragma unroll
@@ -338,7 +339,8 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
         if (q < Q) {
           const int ep = (int)(q / n);
           const int pos = (int)(q - (long long)ep * n);
-          const int idx = d.perm ? __ldg(d.perm + (size_t)(ep % d.perm_rows) * n + pos) : pos;
+          const int idx = d.perm ? __ldg(d.perm + (size_t)(ep % d.perm_rows) * n + pos)
+                                 : (d.perm_seed ? (int)feistel_index((uint32_t)pos, (uint32_t)n, fdom, d.perm_seed, d.perm_row0 + ep) : pos);
           pre[j] = (c < DIN) ? __ldg(d.x + (size_t)idx * DIN + c) : __ldg(d.y + (size_t)idx * ydim + (c - DIN));
         }
       }

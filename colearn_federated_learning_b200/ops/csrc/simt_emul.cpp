@@ -270,11 +270,10 @@ void gemm_tcgen05(Tensor A, Tensor B, c10::optional<Tensor> bias, bool relu, c10
   ep.ready_chunk_elems = 1;
   ep.tile_n = (int)tile_n;
   if (!produced.empty()) {
-    TORCH_CHECK(produced.size() == 3 || produced.size() == 4, "produced = [signal_ptr, elem_offset, max_ctas(, staged)]");
+    TORCH_CHECK(produced.size() == 3, "produced = [signal_ptr, elem_offset, max_ctas]");
     ep.produced = reinterpret_cast<const colearn::ProducedSignal*>(static_cast<uintptr_t>(produced[0]));
     ep.produced_elem_offset = produced[1];
     ep.max_ctas = (int)produced[2];
-    if (produced.size() == 4 && produced[3] >= 0) ep.staged = (int)produced[3];
   }
   if (split_k > 1) {
     ep.split_k = (int)split_k;

@@ -22,10 +22,21 @@ NET_KINDS = {
     ((2, 50, 10, 1), "none"): 2,
 }
 LOSS_CODES = {"bce": 0, "sse": 1, "xent": 2, "mse": 3}
-# 5 = register-resident weights, 128-thread CTA, blocked reduction slices (LDS.128) + pre-scaled dz (default: fastest
-# measured — 0.665 us/step for the 10-64-64-2 MLP, 0.717 for the FFNN, profiles/README.md), 3 = the same kernel with
-# strided slices (round-1 default: 0.699 / 0.795), 1 = smem-resident weights (first version: 1.66)
-KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "5"))
+# Kernel variants: 5 = register-resident weights, 128-thread CTA, blocked reduction slices (LDS.128) + pre-scaled dz;
+# 6 = 5 with packed fp32 math (fma.rn.f32x2 -> SASS FFMA2); 3 = strided slices (the round-1 default); 1 = smem-resident
+# weights (first version).  Measured on a B200 (us per batch-1 SGD step, profiles/README.md):
+#                 v1      v3      v5      v6
+#   MLP 10-64-64-2  1.664   0.699   0.665   0.632     <- 64-wide layers: every dot product / update is FFMA2-shaped
+#   FFNN            1.623   0.795   0.717   0.731     <- odd slice lengths (50 / 30 / 10): the packed form only adds pairing moves
+# 0 (default) picks the fastest measured variant per net.
+KERNEL_VARIANT = int(__import__("os").environ.get("COLEARN_MLP_VARIANT", "0"))
+BEST_VARIANT = {0: 5, 1: 6, 2: 5}          # net kind (NET_KINDS values) -> variant
+
+
+def resolve_variant(kind: int, variant: Optional[int] = None) -> int:
+    v = KERNEL_VARIANT if variant is None else int(variant)
+    return BEST_VARIANT.get(kind, 5) if v == 0 else v
+
 
 PtrLike = Union[torch.Tensor, int, None]
 
@@ -58,6 +69,8 @@ class ClientTask:
     signal_value: int = 0
     out_scale: float = 1.0
     delta_mode: bool = False
+    perm_seed: int = 0                   # != 0 with perm=None: the kernel's gather computes the keyed Feistel order itself
+    perm_row0: int = 0                   # ... epoch e uses row perm_row0 + e of device_permutation(n, *, perm_seed)
     _keep: list = field(default_factory=list, repr=False)
 
     def pack(self) -> bytes:
@@ -68,7 +81,8 @@ class ClientTask:
         return ext.make_client_desc(_ptr(self.x), _ptr(self.y), _ptr(self.perm), _ptr(self.theta_in),
                                     _ptr(self.theta_out), _ptr(self.loss_out), _ptr(self.wait_flag),
                                     int(self.wait_value), _ptr(self.signal_flag), int(self.signal_value),
-                                    n, rows, y_dim, float(self.out_scale), int(bool(self.delta_mode)))
+                                    n, rows, y_dim, float(self.out_scale), int(bool(self.delta_mode)),
+                                    int(self.perm_seed) if self.perm is None else 0, int(self.perm_row0))
 
 
 def build_client_descs(tasks: Sequence[ClientTask], device) -> torch.Tensor:
@@ -99,7 +113,7 @@ def mlp_local_sgd_multi(dims: Sequence[int], out_activation: str, descs: torch.T
         raise ValueError("bce needs a sigmoid head")
     _ext.require().mlp_local_sgd(kind, descs, int(desc_offset), int(n_clients), int(batch_size), int(epochs),
                                  int(max_nr_batches if max_nr_batches is not None else -1), LOSS_CODES[loss], float(lr),
-                                 int(KERNEL_VARIANT if variant is None else variant))
+                                 resolve_variant(kind, variant))
 
 
 def mlp_local_sgd(flat: torch.Tensor, dims: Sequence[int], x: torch.Tensor, y: torch.Tensor,

@@ -23,8 +23,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
               ready_chunk_elems: int = 1, ready_elem_offset: int = 0, tile_n: int = 0,
               ready_epoch_ptr: int = 0, cluster: int = 0, split_k: int = 0,
               split_out: Optional[torch.Tensor] = None, mn_m: int = 0, b_kn: bool = False,
-              addend: Optional[torch.Tensor] = None, produced=None, max_ctas: int = 0,
-              staged: Optional[bool] = None) -> None:
+              addend: Optional[torch.Tensor] = None, produced=None, max_ctas: int = 0) -> None:
     """Launch the tcgen05 GEMM; results land in the provided output tensors.
 
     ``mn_m = M > 0`` selects the "MN-major" form ``C[M, N] = Aᵀ·B`` for ``a[K, a_cols]`` (``a_cols <= M``, the missing
@@ -44,18 +43,12 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, bias: Optional[torch.Tensor] 
     ``elem_offset``): fused wgrad → FedAvg reduce — each epilogue warp reports the block of final parameters it wrote
     (``ops.produced``), and ``ProducedSpec.max_ctas`` caps the persistent grid so that the overlapped two-shot kernel
     keeps its SMs; ``max_ctas`` alone caps the grid of a GEMM that only runs next to that kernel (the dgrads of the
-    last backward).
-
-    ``staged=True`` selects the line-coalesced epilogue: every warp transposes its 32×32 accumulator block through shared
-    memory so that all accesses of the row-major ``[M, N]`` operands cover full 128-byte lines (``None``: the process-wide
-    ``COLEARN_GEMM_STAGED`` setting)."""
-    prod_arg = [0, 0, int(max_ctas)] if (max_ctas or staged is not None) else []
+    last backward)."""
+    prod_arg = [0, 0, int(max_ctas)] if max_ctas else []
     if produced is not None:
         assert sgd_master is not None and not (split_k and split_k > 1), "produced reports come from the fused-SGD epilogue"
         if produced[0].sig is not None:
             prod_arg = produced[0].gemm_arg(produced[1])
-    if staged is not None:          # explicit choice of the line-coalesced epilogue (default: COLEARN_GEMM_STAGED)
-        prod_arg = prod_arg + [1 if staged else 0]
     from . import conv as _conv
     # tests (ops.conv.simt()): CPU bf16 operands go to the kernel SOURCE on the functional tcgen05 / TMA / mbarrier model
     simt_mod = (_conv._EMUL["mod"] if (not a.is_cuda and _conv._EMUL["on"] and hasattr(_conv._EMUL["mod"], "gemm_tcgen05")

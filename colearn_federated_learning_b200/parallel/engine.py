@@ -37,6 +37,7 @@ from ..fl.fedavg import normalized_weights
 from ..fl.trainer import FitConfig, local_fit, resolve_loss
 from ..models import MLPNet, build_model, flatten_params, num_params, state_dict_from_flat
 from ..utils.checkpoint import save_state_dict
+from ..utils.tracing import PhaseTimer, nvtx_range
 
 log = logging.getLogger(__name__)
 
@@ -66,7 +67,8 @@ class FederatedEngine:
                  server_lr: float = 1.0, coordinator_rank: int = 0, algo: str = "auto", seed: int = 1,
                  shuffle: bool = True, chunk_elems: int = 0, bf16_shadow: bool = False,
                  round_deadline_ms: float = 0.0, clients_per_rank: int = 1,
-                 model_kwargs: Optional[Dict[str, Any]] = None, overlap_reduce: Optional[bool] = None) -> None:
+                 model_kwargs: Optional[Dict[str, Any]] = None, overlap_reduce: Optional[bool] = None,
+                 phase_timing: Optional[bool] = None) -> None:
         self.rank = dist.get_rank(group) if _dist_ready() else 0
         self.world = dist.get_world_size(group) if _dist_ready() else 1
         self.group = group
@@ -121,6 +123,12 @@ class FederatedEngine:
         self.overlap_reduce = bool(overlap_reduce) and algo == "twoshot" and backend == "fused"
         self.overlap_ctas = max(1, int(os.environ.get("COLEARN_OVERLAP_CTAS", "16")))
         self.overlap_timeout_s = float(os.environ.get("COLEARN_OVERLAP_TIMEOUT_S", "20"))
+        # per-phase device timing: CUDA-event pairs around the H2D copy / broadcast / local fit / reduce+apply /
+        # read-back launches of every round, reported as RoundReport.extra["phases_ms"]; the NVTX ranges of the same phases
+        # (COLEARN_NVTX=1) are always in place.  Off by default: the event records cost ~1 us each on the 20 kB-model rounds.
+        if phase_timing is None:
+            phase_timing = os.environ.get("COLEARN_PHASE_TIMING", "0") == "1"
+        self.phase_timing = bool(phase_timing)
         self.epoch = 0          # monotonically increasing flag epoch (never reset)
         self.rounds_done = 0
         self.x: Optional[torch.Tensor] = None
@@ -247,6 +255,59 @@ class FederatedEngine:
             return self._run_star(rounds, ms, host_inputs, read_back)
         return self._run_twoshot(rounds, ms, host_inputs, read_back)
 
+    # ------------------------------------------------------------------------------------------ tracing
+    def _phase(self, name: str):
+        """Context manager around the launches of one phase of a round: NVTX range + (with ``phase_timing``) an event pair."""
+        timer = getattr(self, "_phases", None)
+        return timer.phase(name) if timer is not None else nvtx_range(name)
+
+    def _phases_begin(self) -> None:
+        self._phases = PhaseTimer(self.device) if self.phase_timing else None
+
+    def _phases_end(self) -> Optional[Dict[str, float]]:
+        timer, self._phases = getattr(self, "_phases", None), None
+        return {k: round(v, 4) for k, v in timer.summary().items()} if timer is not None else None
+
+    # ------------------------------------------------------------------------------------------ self check
+    def verify_round(self, mask: Optional[int] = None) -> Dict[str, Any]:
+        """Run ONE more round twice on the same inputs — through the fused path, and with ``dist.broadcast`` + the same local
+        fit + ``dist.reduce`` (NCCL) + a host-side apply — and report the difference on the coordinator.  The local fits are
+        bit-identical (same kernel, same sample order), so what is compared is the communication: broadcast, per-worker
+        ``n_k`` scale, selection mask, reduce order, server apply.  ``star`` path only (``{"skipped": ...}`` otherwise)."""
+        if self.backend != "fused" or self.algo != "star" or self.clients_per_rank != 1:
+            return {"skipped": f"verify_round covers the fused star path with one client per rank (algo={self.algo})"}
+        W, r, dev, cfg = self.world, self.rank, self.device, self.cfg
+        full = (1 << W) - 1
+        mask = full if mask is None else (int(mask) & full)
+        theta0 = self.theta[: self.P].clone()
+        if _dist_ready() and W > 1:
+            dist.broadcast(theta0, src=self.coord, group=self.group)                     # K1, library form
+        w = self._round_weights(mask)[r]
+        contrib = torch.zeros_like(theta0)
+        if (mask >> r) & 1:
+            local = theta0.clone()
+            perm = None
+            if cfg.shuffle:
+                pseed = ((self.seed * 1000003 + 17 * r + 1) & 0x7FFFFFFFFFFF) | 1
+                row0 = self.rounds_done * cfg.epochs
+                perm = ops.device_permutation(self.n_local, row0 + cfg.epochs, pseed, dev)[row0:].contiguous()
+            ops.mlp_local_sgd(local, self.spec.dims, self.x, self.y, perm, cfg.batch_size, cfg.lr, cfg.epochs, cfg.max_nr_batches,
+                              cfg.loss, self.spec.out_activation)
+            contrib = local * w
+        if _dist_ready() and W > 1:
+            dist.reduce(contrib, dst=self.coord, group=self.group)                       # K2 + K3, library form
+        expected = theta0 + self.server_lr * (contrib - theta0)
+        rep = self.run_rounds(1, masks=mask)
+        got = self.theta[: self.P]
+        out: Dict[str, Any] = {"algo": self.algo, "provider": rep.extra.get("provider"), "multicast": rep.extra.get("multicast"),
+                               "mask": mask, "world": W}
+        if r == self.coord:
+            err = float((got - expected).abs().max())
+            ref = float(expected.abs().max())
+            out.update(max_abs_err=err, max_abs_ref=ref, rel_err=err / max(ref, 1e-30), moved=float((got - theta0).abs().max()),
+                       ok=bool(err <= 1e-5 * max(ref, 1.0) and torch.isfinite(got).all()))
+        return out
+
     # ------------------------------------------------------------------------------------------ star
     def _run_star(self, rounds: int, masks: List[int], host_inputs, read_back: bool) -> RoundReport:
         ext, arena, W, P4, r = self.ext, self.arena, self.world, self.P4, self.rank
@@ -262,9 +323,9 @@ class FederatedEngine:
         coord_loss = arena.ptr("losses", self.coord, 2 * r)
         coord_arrive = arena.ptr("flags", self.coord, 1 + r)
         C = self.clients_per_rank
-        # Single-round calls (the e2e / per-step usage) reuse a cached plan: descriptors + sample orders for the next
-        # kPlanRounds rounds are built once; a call then costs no descriptor packing, no H2D of descriptors and no
-        # permutation launch.  Epochs advance by 2 per single-round call (broadcast, then reduce without broadcast).
+        # Single-round calls (the e2e / per-step usage) reuse a cached plan: the descriptors of the next kPlanRounds rounds
+        # are packed once; a call then costs no descriptor packing and no H2D of descriptors (the shuffle itself happens
+        # inside the worker kernel).  Epochs advance by 2 per single-round call (broadcast, then reduce without broadcast).
         kPlanRounds = 256
         plan_key = (masks[0], n, self.x.data_ptr(), cfg.batch_size, cfg.epochs, cfg.max_nr_batches, cfg.lr, C)
         plan = getattr(self, "_star_plan", None)
@@ -276,20 +337,21 @@ class FederatedEngine:
         else:
             cap = kPlanRounds if rounds == 1 else rounds
             stride = 2 if rounds == 1 else 1
-            perm = ops.device_permutation(n, cfg.epochs * cap, self.seed * 1000003 + self.rounds_done + 17 * r, dev) \
-                if cfg.shuffle else None
+            # sample order: the worker kernel's gather computes the keyed Feistel index of every sample it prefetches
+            # (ClientDesc::perm_seed / perm_row0), so a round's shuffle costs no launch, no table and is inside whatever
+            # region times the round; round i, epoch e uses row (rounds_done + i) * epochs + e of the rank's / client's key
+            pseed = ((self.seed * 1000003 + 17 * r + 1) & 0x7FFFFFFFFFFF) | 1 if cfg.shuffle else 0
             tasks = []
             if C > 1:
                 from ..data import shard_bounds
                 cb = [b for b in shard_bounds(n, C)]
-                cperm = [ops.device_permutation(hi - lo, cfg.epochs * cap, self.seed * 7919 + self.rounds_done + 131 * c + 17 * r, dev)
-                         if (cfg.shuffle and hi > lo) else None for c, (lo, hi) in enumerate(cb)]
             for i in range(cap):
                 w = self._round_weights(masks[i] if rounds > 1 else masks[0])[r]
-                p = perm[i * cfg.epochs:(i + 1) * cfg.epochs] if perm is not None else None
+                row0 = (self.rounds_done + i) * cfg.epochs
                 ev = e0 + stride * i + 1
                 if C == 1:
-                    tasks.append(ops.ClientTask(x=self.x, y=self.y, theta_in=arena.ptr("inbox"), theta_out=coord_slots, perm=p,
+                    tasks.append(ops.ClientTask(x=self.x, y=self.y, theta_in=arena.ptr("inbox"), theta_out=coord_slots,
+                                                perm_seed=pseed, perm_row0=row0,
                                                 loss_out=coord_loss, wait_flag=arena.ptr("flags"), wait_value=ev,
                                                 signal_flag=coord_arrive, signal_value=ev, out_scale=w))
                 else:
@@ -299,14 +361,13 @@ class FederatedEngine:
                         share = ((hi - lo) / max(1, n)) if self.weighted else 1.0 / C
                         tasks.append(ops.ClientTask(x=self.x[lo:hi], y=self.y[lo:hi], theta_in=arena.ptr("inbox"),
                                                     theta_out=self.client_slots[c],
-                                                    perm=(cperm[c][i * cfg.epochs:(i + 1) * cfg.epochs] if cperm[c] is not None else None),
+                                                    perm_seed=(pseed + 2 * 7919 * (c + 1)) if pseed else 0, perm_row0=row0,
                                                     loss_out=self.client_losses[c],
                                                     wait_flag=arena.ptr("flags"), wait_value=ev, out_scale=w * share))
             descs = ops.build_client_descs(tasks, dev)
             desc_base = 0
             if rounds == 1:
-                self._star_plan = {"key": plan_key, "descs": descs, "perm": perm, "cperm": cperm if C > 1 else None,
-                                   "cap": cap, "used": 1, "e0": e0}
+                self._star_plan = {"key": plan_key, "descs": descs, "cap": cap, "used": 1, "e0": e0}
         inbox_ptrs = arena.peer_ptrs("inbox")
         bflag_ptrs = arena.peer_ptrs("flags")
         n_blocks = max(1, min(148, (P4 // 4 + 255) // 256))
@@ -352,24 +413,29 @@ class FederatedEngine:
                            self.decision.data_ptr())
             return 1
 
+        self._phases_begin()
         if is_coord:
-            launches += star(False, True, 0, masks[0], 0, e0 + 1)
+            with self._phase("bcast"):
+                launches += star(False, True, 0, masks[0], 0, e0 + 1)
         for i in range(rounds):
             if host_inputs is not None:
-                hx, hy = host_inputs[i]
-                self.x.copy_(hx, non_blocking=True)
-                self.y.copy_(hy.view(-1, 1), non_blocking=True)
+                with self._phase("h2d"):
+                    hx, hy = host_inputs[i]
+                    self.x.copy_(hx, non_blocking=True)
+                    self.y.copy_(hy.view(-1, 1), non_blocking=True)
             if (masks[i] >> r) & 1:
-                ops.mlp_local_sgd_multi(self.spec.dims, self.spec.out_activation, descs, C, cfg.batch_size, cfg.lr,
-                                        cfg.epochs, cfg.max_nr_batches, cfg.loss, desc_offset=desc_base + i * C)
-                launches += 1
-                if C > 1:
-                    ext.reduce_push(self.client_slots.data_ptr(), C, P4, P4, coord_slots, self.client_losses.data_ptr(),
-                                    coord_loss, coord_arrive, e0 + i + 1, self.push_counter.data_ptr(), n_blocks)
+                with self._phase("local_fit"):
+                    ops.mlp_local_sgd_multi(self.spec.dims, self.spec.out_activation, descs, C, cfg.batch_size, cfg.lr,
+                                            cfg.epochs, cfg.max_nr_batches, cfg.loss, desc_offset=desc_base + i * C)
                     launches += 1
+                    if C > 1:
+                        ext.reduce_push(self.client_slots.data_ptr(), C, P4, P4, coord_slots, self.client_losses.data_ptr(),
+                                        coord_loss, coord_arrive, e0 + i + 1, self.push_counter.data_ptr(), n_blocks)
+                        launches += 1
             if is_coord:
                 last = i == rounds - 1
-                launches += star(True, not last, masks[i], masks[i + 1] if not last else 0, e0 + i + 1, e0 + i + 2)
+                with self._phase("reduce_apply" if last else "reduce_apply_bcast"):
+                    launches += star(True, not last, masks[i], masks[i + 1] if not last else 0, e0 + i + 1, e0 + i + 2)
                 losses_log[i].copy_(arena.tensor("losses").view(W, 2), non_blocking=True)
                 if self.round_deadline_ms > 0:
                     arrived_log[i].copy_(self.decision[1], non_blocking=True)
@@ -398,6 +464,7 @@ class FederatedEngine:
                 self.loss_host.copy_(self.loss_history[-1])
         ev1.record()
         torch.cuda.synchronize(dev)
+        phases = self._phases_end()
         self.epoch = e0 + rounds + 1
         self.rounds_done += rounds
         if _dist_ready() and W > 1 and self._barrier:
@@ -405,7 +472,7 @@ class FederatedEngine:
         nsel = [bin(m).count("1") for m in masks]
         return RoundReport(rounds, W, "fused", "star", ev0.elapsed_time(ev1), losses_log, launches,
                            bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel),
-                           extra={"provider": arena.provider, "multicast": arena.has_multicast,
+                           extra={"provider": arena.provider, "multicast": arena.has_multicast, "phases_ms": phases,
                                   "arrived_masks": arrived_log.tolist() if (is_coord and self.round_deadline_ms > 0) else None})
 
     # ------------------------------------------------------------------------------------------ twoshot
@@ -515,6 +582,7 @@ class FederatedEngine:
         torch.cuda.synchronize(dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        self._phases_begin()
         for i in range(rounds):
             e = e0 + i + 1
             if host_inputs is not None:
@@ -523,8 +591,9 @@ class FederatedEngine:
                     self.x = torch.empty(hx.shape, device=dev, dtype=torch.float32)
                     self.y = torch.empty(hy.shape[0], 1, device=dev)
                     self.set_local_data(self.x, self.y)
-                self.x.copy_(hx, non_blocking=True)
-                self.y.copy_(hy.view(-1, 1), non_blocking=True)
+                with self._phase("h2d"):
+                    self.x.copy_(hx, non_blocking=True)
+                    self.y.copy_(hy.view(-1, 1), non_blocking=True)
             wts = self._round_weights(masks[i])
             self.weights_dev[:W].copy_(torch.tensor(wts, dtype=torch.float32), non_blocking=True)
             need_wait = read_back or i == rounds - 1   # otherwise the next round's consumer polls the flags
@@ -553,7 +622,8 @@ class FederatedEngine:
 
             if (masks[i] >> r) & 1:
                 self._train_launches = 0
-                last = self._local_train_inplace(self.rounds_done + i, e, prod, overlapped if prod is not None else None)
+                with self._phase("local_fit(+fused_bcast_consume)"):
+                    last = self._local_train_inplace(self.rounds_done + i, e, prod, overlapped if prod is not None else None)
                 losses_log[i, r, 0] = last
                 losses_log[i, r, 1] = last
                 launches += self._train_launches
@@ -562,7 +632,8 @@ class FederatedEngine:
             if launched[0]:
                 torch.cuda.current_stream(dev).wait_stream(self.comm_stream)
             else:
-                twoshot(n_blocks, 0)
+                with self._phase("twoshot_reduce_apply_bcast"):
+                    twoshot(n_blocks, 0)
             self._last_nvls = bool(nvls)
             launches += 1
             if read_back:
@@ -570,6 +641,7 @@ class FederatedEngine:
                 torch.cuda.current_stream(dev).synchronize()
         ev1.record()
         torch.cuda.synchronize(dev)
+        phases = self._phases_end()
         self.epoch = e0 + rounds
         self.rounds_done += rounds
         if _dist_ready() and W > 1 and self._barrier:
@@ -577,7 +649,7 @@ class FederatedEngine:
         nsel = [bin(m).count("1") for m in masks]
         return RoundReport(rounds, W, "fused", "twoshot", ev0.elapsed_time(ev1), losses_log, launches,
                            bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel),
-                           extra={"provider": arena.provider, "train_path": getattr(self, "_last_path", None),
+                           extra={"provider": arena.provider, "train_path": getattr(self, "_last_path", None), "phases_ms": phases,
                                   "n_chunks": self.n_chunks, "nvls": getattr(self, "_last_nvls", False)})
 
     # ------------------------------------------------------------------------------------------ cpu / gloo
@@ -585,24 +657,29 @@ class FederatedEngine:
         W, r = self.world, self.rank
         t0 = time.perf_counter()
         losses_log = torch.zeros(rounds, W, 2)
+        self._phases_begin()
         for i in range(rounds):
-            if _dist_ready() and W > 1:
-                dist.broadcast(self.theta, src=self.coord, group=self.group)          # K1
+            with self._phase("bcast"):
+                if _dist_ready() and W > 1:
+                    dist.broadcast(self.theta, src=self.coord, group=self.group)          # K1
             local = self.theta.clone()
             loss = torch.zeros(())
             if (masks[i] >> r) & 1:
-                loss, _ = local_fit(local, self.model, self.x, self.y, self.cfg, self.rounds_done + i)
+                with self._phase("local_fit"):
+                    loss, _ = local_fit(local, self.model, self.x, self.y, self.cfg, self.rounds_done + i)
             w = self._round_weights(masks[i])[r]
             contrib = local * w
             lvec = torch.zeros(W, 2)
             lvec[r, 0] = float(loss)
-            if _dist_ready() and W > 1:
-                dist.reduce(contrib, dst=self.coord, group=self.group)                 # K2 + K3
-                dist.reduce(lvec, dst=self.coord, group=self.group)
-            if r == self.coord:
-                self.theta.add_(self.server_lr * (contrib - self.theta))
-                losses_log[i] = lvec
+            with self._phase("reduce_apply"):
+                if _dist_ready() and W > 1:
+                    dist.reduce(contrib, dst=self.coord, group=self.group)                 # K2 + K3
+                    dist.reduce(lvec, dst=self.coord, group=self.group)
+                if r == self.coord:
+                    self.theta.add_(self.server_lr * (contrib - self.theta))
+                    losses_log[i] = lvec
         self.rounds_done += rounds
         nsel = [bin(m).count("1") for m in masks]
         return RoundReport(rounds, W, "cpu", "gloo", (time.perf_counter() - t0) * 1e3, losses_log, 0,
-                           bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel))
+                           bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel),
+                           extra={"phases_ms": self._phases_end()})

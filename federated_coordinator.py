@@ -83,6 +83,16 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--box", action="store_true", help="multi-GPU box mode under torchrun (rank 0 = coordinator)")
     parser.add_argument("--backend", choices=["auto", "fused", "nccl", "cpu"], default="auto")
     parser.add_argument("--clients-per-gpu", type=int, default=1, help="--box: virtual federated devices hosted by each GPU (one CTA each)")
+    parser.add_argument("--round-deadline-ms", type=float, default=0.0,
+                        help="--box: a selected worker that has not delivered its model this many ms after the coordinator started its "
+                             "reduce is dropped from that round (weights renormalised); 0 = wait for everyone")
+    parser.add_argument("--box-event", default="TRAINING", help="--box: the state every rank announces at start (rw.py --event)")
+    parser.add_argument("--box-script", default=None, metavar="RANK:STATE:AFTER[,...]",
+                        help="--box: further events, e.g. '3:NOT_READY:0,2:INFERENCE:1' = rank 3 withdraws right after its announcement, "
+                             "rank 2 asks for inference once it has seen one training complete")
+    parser.add_argument("--box-no-reannounce", action="store_true",
+                        help="--box: devices do not ask for training again after a training they took part in")
+    parser.add_argument("--box-inference-rows", type=int, default=5, help="--box: rows of its shard every rank tags as inference data")
     return parser
 
 

@@ -32,3 +32,16 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture
 def tmp_ckpt(tmp_path):
     return str(tmp_path / "test.pth")
+
+
+@pytest.fixture
+def legacy_conv_schedule(monkeypatch):
+    """The round-1 ResNet step schedule (every entry of fl.convnet.SCHEDULE_DEFAULTS at 0).  Tests that switch ONE
+    re-scheduling on and compare it with "the base" were written against that base; the shipped defaults (the fastest
+    measured combination) are covered by the tests that do not use this fixture."""
+    from colearn_federated_learning_b200.fl import convnet
+    for k in list(convnet.SCHEDULE_DEFAULTS):
+        monkeypatch.setitem(convnet.SCHEDULE_DEFAULTS, k, 0)
+    for k in list(os.environ):
+        if k.startswith("COLEARN_CONV_"):
+            monkeypatch.delenv(k, raising=False)

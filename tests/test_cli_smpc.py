@@ -161,6 +161,18 @@ def test_encrypted_training_tracks_plaintext_training():
     assert not torch.equal(before, after) and (m(x) > 0.5).all()
 
 
+def _closed_windows(stderr: str):
+    """[(sorted members, sorted selected), ...] of the 'window closed:' log lines (devices register in arrival order)."""
+    import ast
+    import re
+    out = []
+    for ln in stderr.splitlines():
+        m = re.search(r"window closed: members=(\[.*?\]) selected=(\[.*?\])", ln)
+        if m:
+            out.append((sorted(ast.literal_eval(m.group(1))), sorted(ast.literal_eval(m.group(2)))))
+    return out
+
+
 def test_box_mode_cli_two_ranks_gloo(tmp_path):
     """``federated_coordinator.py --box`` under torchrun: rank 0 runs parser/window/selection on the in-process bus,
     both ranks train, rank 0 writes the reference-format checkpoint (CPU/gloo stand-in for the fused GPU path)."""
@@ -169,13 +181,36 @@ def test_box_mode_cli_two_ranks_gloo(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "federated_coordinator.py"),
                           "-t", "topic/state", "--box", "--model", "mlp", "--synthetic", "128", "-f", "2", "--weighted",
-                          "-w", "1", "--checkpoint", ckpt, "--batch-size", "4"], env=env, capture_output=True, text=True,
+                          "-w", "1", "--checkpoint", ckpt, "--batch-size", "4", "--exit-after", "1"], env=env, capture_output=True, text=True,
                          timeout=240, cwd=str(tmp_path))
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "window closed: members=['10.0.0.1:8777', '10.0.0.2:8778']" in out.stderr
+    assert _closed_windows(out.stderr) == [(["10.0.0.1:8777", "10.0.0.2:8778"],) * 2]     # (members, selected), arrival order ignored
     assert out.stderr.count("Loss for worker id: 10.0.0.") == 4
     state = torch.load(ckpt, weights_only=True)
     assert state["fc1.weight"].shape == (64, 10) and state["fc3.weight"].shape == (2, 64)
+
+
+def test_box_mode_is_a_coordinator_service(tmp_path):
+    """``--box`` serves window after window like the reference coordinator (fc.py:294-300): devices ask again after a
+    training, NOT_READY withdraws one from the open window, a withdrawn device that announces later rides the next window,
+    INFERENCE runs the global model on the asking rank's tagged rows, ``--evaluate`` scores every trained model, and the
+    job ends after ``--exit-after`` trainings."""
+    ckpt = str(tmp_path / "test.pth")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "federated_coordinator.py"),
+                          "-t", "topic/state", "--box", "--model", "ffnn", "--synthetic", "64", "-w", "1", "--checkpoint", ckpt,
+                          "--batch-size", "4", "--exit-after", "3", "--evaluate",
+                          "--box-script", "1:NOT_READY:1,1:INFERENCE:1,1:TRAINING:2"], env=env, capture_output=True, text=True,
+                         timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-3000:]
+    both, only0 = ["10.0.0.1:8777", "10.0.0.2:8778"], ["10.0.0.1:8777"]
+    assert _closed_windows(out.stderr) == [(both, both), (only0, only0), (both, both)], out.stderr[-3000:]
+    assert "10.0.0.2:8778 is not ready anymore" in out.stderr
+    inf = [ln for ln in out.stderr.splitlines() if "inference on 10.0.0.2:8778: [" in ln]
+    assert len(inf) == 1 and inf[0].count(",") == 4                              # 5 tagged rows -> 5 predictions
+    assert out.stderr.count("Loss evaluation global model after training") == 3
+    assert torch.load(ckpt, weights_only=True)["fc4.weight"].shape == (1, 10)
 
 
 def test_box_mode_metrics_jsonl_and_periodic_checkpoints(tmp_path):
@@ -188,7 +223,8 @@ def test_box_mode_metrics_jsonl_and_periodic_checkpoints(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "federated_coordinator.py"),
                           "-t", "topic/state", "--box", "--model", "mlp", "--synthetic", "96", "-f", "3", "-w", "1",
-                          "--checkpoint", ckpt, "--batch-size", "8", "--metrics", metrics, "--save-every", "1", "--dtype", "bf16"],
+                          "--checkpoint", ckpt, "--batch-size", "8", "--metrics", metrics, "--save-every", "1", "--dtype", "bf16",
+                          "--exit-after", "1"],
                          env=env, capture_output=True, text=True, timeout=240, cwd=str(tmp_path))
     assert out.returncode == 0, out.stderr[-2000:]
     recs = [json.loads(l) for l in open(metrics)]

@@ -315,7 +315,7 @@ def test_pack_and_unpack_params(backend):
 @pytest.mark.parametrize("m,c,ldx", [(128, 64, 128), (8192, 64, 128), (512, 256, 256), (4100, 512, 512)])
 def test_fused_batchnorm_reduction_kernel_bodies_on_host(m, c, ldx):
     """Single-launch BatchNorm reduction (the last block of a column group finalises, the ticket counter resets
-    itself): the host build of the bodies against the definitions.  The sm_100a run lives in test_zz_round2_gpu."""
+    itself): the host build of the bodies against the definitions.  The sm_100a run lives in test_gpu_schedules."""
     _batchnorm_case("emul", m, c, ldx, fused=True)
 
 

@@ -62,6 +62,7 @@ def test_fp32_oracle_step_equals_autograd():
             assert int(m.num_batches_tracked) == 1
 
 
+@pytest.mark.usefixtures("legacy_conv_schedule")
 @pytest.mark.parametrize("level", [1, 2])
 def test_split_k_schedule_is_the_same_step(level):
     """Split-K (wgrads of the stem / layer1 / layer2 cut over pixel slices, level 2: the layer4 forwards too) only
@@ -97,6 +98,7 @@ def test_split_k_schedule_is_the_same_step(level):
     assert float((d0 * d1).sum() / (d0.norm() * d1.norm())) > (0.999 if level == 1 else 0.95)
 
 
+@pytest.mark.usefixtures("legacy_conv_schedule")
 @pytest.mark.parametrize("split", [0, 1])
 def test_mn_major_wgrad_schedule_is_the_same_step(split):
     """``wgrad_mn``: the wgrad GEMMs read ``dz`` / ``col`` in place (reduction over rows) instead of transposed copies —

@@ -10,7 +10,8 @@ import torch.multiprocessing as mp
 from colearn_federated_learning_b200.data import synthetic_unsw
 from colearn_federated_learning_b200.models import MLP, flatten_params
 from colearn_federated_learning_b200.parallel import FederatedEngine
-from colearn_federated_learning_b200.parallel.box import collect_plan, rank_identity, worker_id_to_rank
+from colearn_federated_learning_b200.parallel.box import (BoxAgent, BoxControl, DictStore, StoreRelay, parse_box_script, rank_identity,
+                                                          worker_id_to_rank)
 from colearn_federated_learning_b200.control.event_parser import format_event
 
 
@@ -74,10 +75,56 @@ def test_two_process_gloo_weighted_fedavg_and_selection(tmp_path):
     assert torch.allclose(res["theta"], c, atol=1e-5)
 
 
+def _serve_commands(relay, control, executed, stop):
+    """What rank 0's main thread does in BoxService.serve: take commands in order, "execute" them, report completion."""
+    import json
+    while True:
+        item = relay.wait_next("commands", stop=stop.is_set)
+        if item is None:
+            return
+        seq, raw = item
+        cmd = json.loads(raw)
+        executed.append(cmd)
+        control.command_done(seq)
+
+
 def test_box_control_plane_builds_selection_mask():
-    payloads = [format_event(*[rank_identity(r)[0], "TRAINING", rank_identity(r)[1]]) for r in range(8)]
-    plan = collect_plan(8, 0.05, "topic/state", payloads, iot=False, select_k=4, selection="first", seed=1)
-    assert plan["mask"] == 0b1111 and len(plan["members"]) == 8            # BASELINE config 3: 4 of 8
-    plan = collect_plan(8, 0.05, "topic/state", payloads[:3] + ["(bad, 1, TRAINING)"], False, None, "all", 1)
-    assert plan["mask"] == 0b111
+    """Store log -> in-process bus -> parser / registry / temporal window / selection -> `train` command with the mask."""
+    import threading
+    from colearn_federated_learning_b200.control.window import FakeClock
+    store, clock = DictStore(), FakeClock()
+    control = BoxControl(StoreRelay(store), 8, 1.0, "topic/state", select_k=4, selection="first", timer_factory=clock, rounds=3)
+    executed, stop = [], threading.Event()
+    t = threading.Thread(target=_serve_commands, args=(StoreRelay(store), control, executed, stop), daemon=True)
+    t.start()
+    try:
+        agents = [BoxAgent(StoreRelay(store), r, reannounce=False) for r in range(8)]
+        for a in agents:
+            a.start()
+        StoreRelay(store).post("events", "(bad, 1, TRAINING)")                # malformed: ignored
+        StoreRelay(store).post("events", "(10.0.0.99, 9999, TRAINING)")        # not a rank of this box: ignored
+        assert control.pump() == 10 and len(control.registry) == 8
+        clock.advance(1.0)                                                     # window closes: BASELINE config 3 = 4 of 8
+        assert executed[0]["op"] == "train" and executed[0]["mask"] == 0b1111 and executed[0]["rounds"] == 3
+        assert len(control.history[0]["members"]) == 8 and len(control.registry) == 4   # the unselected four stay registered ...
+        clock.advance(1.0)                                                     # ... and the re-armed window trains them next
+        assert executed[1]["mask"] == 0b11110000 and len(control.registry) == 0
+        # NOT_READY inside the window withdraws a device; a late TRAINING during a training rides the next window
+        agents[0].publish("TRAINING"); agents[1].publish("TRAINING"); agents[1].publish("NOT_READY")
+        control.pump()
+        clock.advance(1.0)
+        assert executed[2]["mask"] == 0b1
+        # INFERENCE becomes a command for that rank right away
+        agents[5].publish("INFERENCE")
+        control.pump()
+        import time
+        deadline = time.time() + 5
+        while len(executed) < 4 and time.time() < deadline:                    # taken by the consumer thread
+            time.sleep(0.005)
+        assert executed[3] == {"op": "inference", "rank": 5, "worker": "10.0.0.6:8782"}
+    finally:
+        stop.set()
+        control.stop()
+        t.join(timeout=2)
     assert worker_id_to_rank("10.0.0.6:8782") == 5
+    assert parse_box_script("3:NOT_READY:0, 2:inference:1,3:TRAINING:2", 3) == [("NOT_READY", 0), ("TRAINING", 2)]

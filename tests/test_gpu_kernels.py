@@ -68,6 +68,32 @@ def test_persistent_mlp_multi_client_scale_and_delta():
         assert torch.allclose(slots[i].cpu(), want, atol=2e-4, rtol=2e-3)
 
 
+@pytest.mark.parametrize("variant", [5, 6, 3, 1])
+def test_in_kernel_shuffle_equals_the_tabulated_permutation(variant):
+    """ClientDesc::perm_seed: the gather of the persistent kernel computes the keyed Feistel order itself — same bits as
+    training through the table feistel_perm_kernel writes for that seed (rows perm_row0 .. perm_row0 + epochs - 1), and the
+    host implementation of the bijection agrees with the device one."""
+    torch.manual_seed(4)
+    dev = _dev()
+    model = MLP()
+    spec = model.spec
+    theta = flatten_params(model).clone().to(dev)
+    n, epochs, seed, row0 = 333, 3, 987654321, 5
+    x, y = torch.rand(n, 10, device=dev), torch.randint(0, 2, (n, 1), device=dev).float()
+    table = ops.device_permutation(n, row0 + epochs, seed, dev)
+    host = ops._ext.require().feistel_permutation(n, row0 + epochs, seed, torch.device("cpu"))
+    assert torch.equal(table.cpu(), host)
+    outs = []
+    for kw in (dict(perm=table[row0:].contiguous()), dict(perm_seed=seed, perm_row0=row0)):
+        out, loss = torch.zeros_like(theta), torch.zeros(2, device=dev)
+        descs = ops.build_client_descs([ops.ClientTask(x=x, y=y, theta_in=theta, theta_out=out, loss_out=loss, **kw)], dev)
+        ops.mlp_local_sgd_multi(spec.dims, spec.out_activation, descs, 1, batch_size=1, lr=0.05, epochs=epochs, loss="xent", variant=variant)
+        torch.cuda.synchronize()
+        outs.append((out.clone(), loss.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert not torch.equal(outs[0][0], theta)
+
+
 def test_mlp_forward():
     torch.manual_seed(2)
     for ctor in (FFNN, MLP, TestingRemote):

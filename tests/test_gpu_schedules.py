@@ -1,7 +1,8 @@
-"""GPU tests written after round 1's GPU budget was spent: they exercise code that is built only from kernels
-already validated on a B200 (tests/test_conv_ops.py, tests/test_convnet_trainer.py) but has not itself run on one
-yet.  The file sorts last on purpose, so that under ``pytest -x`` a surprise here cannot mask the validated suites.
-"""
+"""GPU tests of the ResNet-18 step schedules, the GEMM operand / scheduling modes behind them (split-K, MN-major operands,
+implicit-GEMM convolution, programmatic dependent launch) and the engine modes added in round 2.  Every re-scheduling is
+compared with the round-1 schedule (fixture ``legacy_conv_schedule``: all of fl.convnet.SCHEDULE_DEFAULTS at 0); the
+shipped defaults — the fastest measured combination — are the "all switches" rows of these tests plus
+tests/test_convnet_trainer.py.  First run on a B200 in round 2 (profiles/README.md)."""
 import os
 
 import pytest
@@ -12,12 +13,7 @@ from colearn_federated_learning_b200.fl.evaluate import evaluate, predict
 from colearn_federated_learning_b200.models.registry import flatten_params
 from colearn_federated_learning_b200.models.resnet import ResNet18
 
-pytestmark = pytest.mark.gpu
-
-# opt-in code paths (off by default in the product) are only exercised on request, so that an unmeasured
-# optimisation can never turn the round-end GPU suite red:  COLEARN_RUN_UNVALIDATED=1 pytest -m gpu tests/test_zz_round2_gpu.py
-unvalidated = pytest.mark.skipif(os.environ.get("COLEARN_RUN_UNVALIDATED") != "1",
-                                 reason="opt-in kernel/schedule not yet measured on a B200 (set COLEARN_RUN_UNVALIDATED=1)")
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("legacy_conv_schedule")]
 
 
 def _dev():
@@ -53,7 +49,6 @@ def test_resnet_eval_mode_inference_on_own_kernels():
     assert res["accuracy"] > 0.9 and res["n"] == x.shape[0]
 
 
-@unvalidated
 @pytest.mark.parametrize("m,c,ldx", [(128, 64, 128), (8192, 64, 128), (512, 256, 256), (4100, 512, 512)])
 def test_fused_batchnorm_reduction_kernel(m, c, ldx):
     """``bn_reduce_finalize_kernel`` (ticket counter, last block finalises) against the two-kernel definitions."""
@@ -62,7 +57,6 @@ def test_fused_batchnorm_reduction_kernel(m, c, ldx):
     _batchnorm_case("cuda", m, c, ldx, fused=True)
 
 
-@unvalidated
 @pytest.mark.parametrize("flags", [{"COLEARN_CONV_STREAMS": "1"}, {"COLEARN_CONV_SHADOW_T": "1"}, {"COLEARN_CONV_FUSED_BN": "1"},
                                    {"COLEARN_CONV_STREAMS": "1", "COLEARN_CONV_SHADOW_T": "1", "COLEARN_CONV_FUSED_BN": "1"}])
 def test_optional_step_optimisations_do_not_change_the_result(flags, monkeypatch):
@@ -98,7 +92,6 @@ def test_optional_step_optimisations_do_not_change_the_result(flags, monkeypatch
         assert torch.equal(got, base)
 
 
-@unvalidated
 @pytest.mark.parametrize("splits,rows,cols", [(2, 128, 128), (16, 128, 640), (64, 128, 256), (5, 4, 12)])
 def test_splitk_reduce_kernel(splits, rows, cols):
     _dev()
@@ -106,7 +99,6 @@ def test_splitk_reduce_kernel(splits, rows, cols):
     _splitk_reduce_case("cuda", splits, rows, cols)
 
 
-@unvalidated
 @pytest.mark.parametrize("m,n,k,s,tile_n", [(128, 256, 32768, 64, 0), (128, 640, 8192, 16, 0), (256, 128, 4096, 3, 0),
                                             (512, 512, 1024, 4, 128), (128, 512, 4608, 9, 256), (1024, 256, 512, 8, 0)])
 def test_gemm_split_k_partials(m, n, k, s, tile_n):
@@ -137,36 +129,40 @@ def test_gemm_split_k_partials(m, n, k, s, tile_n):
     torch.testing.assert_close(out.float().cpu(), ref.float().cpu(), rtol=1.6e-2, atol=0.5)
 
 
-@unvalidated
-@pytest.mark.parametrize("level", ["1", "2"])
-def test_split_k_step_matches_default_schedule(level, monkeypatch):
-    """COLEARN_CONV_SPLITK: two ResNet-18 steps (one eager, one through the CUDA graph) against the default schedule —
-    the split only changes the fp32 summation order of the affected GEMMs."""
-    dev = _dev()
+def _one_step_update(dev, graph: bool):
+    """Parameter update of ONE ResNet-18 step (eager, or the first replay of the step graph) from a fixed initial state."""
     torch.manual_seed(0)
-    x = torch.randn(256, 3, 32, 32, device=dev)
-    y = torch.randint(0, 10, (256,), device=dev)
+    x = torch.randn(128, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (128,), device=dev)
+    torch.manual_seed(1)
+    model = ResNet18(10).to(dev)
+    flat = flatten_params(model)
+    flat0 = flat.clone()
+    tr = ConvNetTrainer(model, dev, 128, (32, 32))
+    tr.load(flat, model)
+    (tr._graph_step if graph else tr.step)(x, y, 0.05)
+    tr.store(flat, model)
+    torch.cuda.synchronize()
+    return flat.clone() - flat0
 
-    def run():
-        torch.manual_seed(1)
-        model = ResNet18(10).to(dev)
-        flat = flatten_params(model)
-        flat0 = flat.clone()
-        tr = ConvNetTrainer(model, dev, 128, (32, 32))
-        tr.load(flat, model)
-        for lo in (0, 128):
-            tr._graph_step(x[lo:lo + 128], y[lo:lo + 128], 0.05)
-        tr.store(flat, model)
-        torch.cuda.synchronize()
-        return flat.clone() - flat0
 
-    monkeypatch.delenv("COLEARN_CONV_SPLITK", raising=False)
-    base = run()
-    monkeypatch.setenv("COLEARN_CONV_SPLITK", level)
-    got = run()
+def _assert_same_step(got, base, cos_min=0.9995):
+    """One step apart, two schedules differ by fp32 summation order / bf16 rounding only.  (TWO steps are no test: at this
+    learning rate a 1e-6 relative perturbation of the parameters after step 1 already moves the 2-step update to cosine
+    0.982 under the SAME schedule — measured, profiles/README.md — so a 2-step comparison measures chaos, not kernels.)"""
     cos = float((got * base).sum() / (got.norm() * base.norm()))
-    assert cos > 0.98, cos
-    assert torch.isfinite(got).all()
+    rel = float((got - base).norm() / base.norm())
+    assert torch.isfinite(got).all() and cos > cos_min and rel < 0.03, (cos, rel)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("level", ["1", "2"])
+def test_split_k_step_matches_default_schedule(level, graph, monkeypatch):
+    """COLEARN_CONV_SPLITK: the split only changes the fp32 summation order of the affected GEMMs."""
+    dev = _dev()
+    base = _one_step_update(dev, graph)
+    monkeypatch.setenv("COLEARN_CONV_SPLITK", level)
+    _assert_same_step(_one_step_update(dev, graph), base)
 
 
 def _mn_case(dev, kdim, a_cols, m, n, split=0):
@@ -191,7 +187,6 @@ def _mn_case(dev, kdim, a_cols, m, n, split=0):
     return got, want, tol
 
 
-@unvalidated
 @pytest.mark.parametrize("kdim,a_cols,m,n,split", [(64, 128, 128, 128, 0), (128, 64, 128, 128, 0), (8192, 64, 128, 640, 0),
                                                    (32768, 64, 128, 256, 64), (512, 256, 256, 2304, 0), (128, 512, 512, 4608, 0),
                                                    (8192, 64, 128, 640, 16), (2048, 128, 128, 1152, 4)])
@@ -202,7 +197,6 @@ def test_gemm_mn_major_operands(kdim, a_cols, m, n, split):
     torch.testing.assert_close(got, want, **tol)
 
 
-@unvalidated
 @pytest.mark.parametrize("m,kdim,b_rows,n", [(128, 64, 64, 128), (8192, 64, 128, 640), (2048, 128, 128, 1152), (512, 256, 256, 2304),
                                              (128, 512, 512, 4608), (32768, 64, 128, 256)])
 def test_gemm_mn_major_b_operand(m, kdim, b_rows, n):
@@ -220,7 +214,6 @@ def test_gemm_mn_major_b_operand(m, kdim, b_rows, n):
     torch.testing.assert_close(out.float(), want, rtol=1.6e-2, atol=2e-2 * (kdim / 64) ** 0.5)
 
 
-@unvalidated
 def test_gemm_mn_major_fused_sgd_epilogue():
     dev = _dev()
     from colearn_federated_learning_b200 import ops
@@ -238,7 +231,6 @@ def test_gemm_mn_major_fused_sgd_epilogue():
     assert torch.equal(shadow, master.to(torch.bfloat16)) and torch.equal(shadow_t, shadow.t().contiguous())
 
 
-@unvalidated
 @pytest.mark.parametrize("flags", [{"COLEARN_CONV_WGRAD_MN": "1"}, {"COLEARN_CONV_DGRAD_KN": "1"},
                                    {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_SPLITK": "1"},
                                    {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_DGRAD_KN": "1", "COLEARN_CONV_SPLITK": "1",
@@ -247,32 +239,11 @@ def test_gemm_mn_major_fused_sgd_epilogue():
                                     "COLEARN_CONV_STREAMS": "1", "COLEARN_CONV_FUSED_BN": "1"}])
 def test_mn_major_wgrad_step_matches_default_schedule(flags, monkeypatch):
     dev = _dev()
-    torch.manual_seed(0)
-    x = torch.randn(256, 3, 32, 32, device=dev)
-    y = torch.randint(0, 10, (256,), device=dev)
-
-    def run():
-        torch.manual_seed(1)
-        model = ResNet18(10).to(dev)
-        flat = flatten_params(model)
-        flat0 = flat.clone()
-        tr = ConvNetTrainer(model, dev, 128, (32, 32))
-        tr.load(flat, model)
-        for lo in (0, 128):
-            tr._graph_step(x[lo:lo + 128], y[lo:lo + 128], 0.05)
-        tr.store(flat, model)
-        torch.cuda.synchronize()
-        return flat.clone() - flat0
-
-    for k in ("COLEARN_CONV_WGRAD_MN", "COLEARN_CONV_DGRAD_KN", "COLEARN_CONV_SPLITK", "COLEARN_CONV_STREAMS", "COLEARN_CONV_FUSED_BN",
-              "COLEARN_CONV_SHADOW_T"):
-        monkeypatch.delenv(k, raising=False)
-    base = run()
+    graph = "COLEARN_CONV_STREAMS" in flags            # the second stream only exists inside the captured step
+    base = _one_step_update(dev, graph)
     for k, v in flags.items():
         monkeypatch.setenv(k, v)
-    got = run()
-    cos = float((got * base).sum() / (got.norm() * base.norm()))
-    assert cos > 0.98 and torch.isfinite(got).all(), cos
+    _assert_same_step(_one_step_update(dev, graph), base)
 
 
 # ---- implicit-GEMM convolution (4-D TMA boxes): tests/test_implicit_conv.py has the host-side evidence -----------------
@@ -297,7 +268,6 @@ def _implicit_case(n, h, w, cin, cout):
                 z=nhwc(z.detach(), cout), dx=nhwc(xr.grad, cin), dw=wr.grad.permute(0, 2, 3, 1).reshape(cout, -1))
 
 
-@unvalidated
 @pytest.mark.parametrize("n,h,w,cin,cout", IMPLICIT_GEOMS)
 def test_implicit_conv_forward_and_dgrad(n, h, w, cin, cout):
     dev = _dev()
@@ -324,7 +294,6 @@ def test_implicit_conv_forward_and_dgrad(n, h, w, cin, cout):
     torch.testing.assert_close(dx.float().cpu(), d["dx"] + add.float(), rtol=2e-2, atol=5e-2)
 
 
-@unvalidated
 @pytest.mark.parametrize("n,h,w,cin,cout", IMPLICIT_GEOMS)
 def test_implicit_conv_dgrad_packed_weights(n, h, w, cin, cout):
     """The implicit dgrad against the packed weights themselves (MN-major B operand, no W^T copy)."""
@@ -340,7 +309,6 @@ def test_implicit_conv_dgrad_packed_weights(n, h, w, cin, cout):
     torch.testing.assert_close(dx2.float().cpu(), d["dx"] + add.float(), rtol=2e-2, atol=5e-2)
 
 
-@unvalidated
 @pytest.mark.parametrize("n,h,w,cin,cout", IMPLICIT_GEOMS)
 def test_implicit_conv_wgrad(n, h, w, cin, cout):
     dev = _dev()
@@ -363,41 +331,20 @@ def test_implicit_conv_wgrad(n, h, w, cin, cout):
     torch.testing.assert_close(part[: s * cp * kp].view(s, cp, kp).sum(0), master, rtol=1e-3, atol=1e-3 * scale)
 
 
-@unvalidated
 @pytest.mark.parametrize("flags", [{"COLEARN_CONV_IMPLICIT": "1"}, {"COLEARN_CONV_IMPLICIT": "2"},
                                    {"COLEARN_CONV_IMPLICIT": "2", "COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_DGRAD_KN": "1",
-                                    "COLEARN_CONV_SPLITK": "1", "COLEARN_CONV_FUSED_BN": "1"}])
+                                    "COLEARN_CONV_SPLITK": "1", "COLEARN_CONV_FUSED_BN": "1"},
+                                   {"COLEARN_CONV_IMPLICIT": "2", "COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_DGRAD_KN": "1",
+                                    "COLEARN_CONV_SPLITK": "1", "COLEARN_CONV_FUSED_BN": "1", "COLEARN_CONV_STREAMS": "1"}])   # = SCHEDULE_DEFAULTS
 def test_implicit_step_matches_default_schedule(flags, monkeypatch):
     dev = _dev()
-    torch.manual_seed(0)
-    x = torch.randn(256, 3, 32, 32, device=dev)
-    y = torch.randint(0, 10, (256,), device=dev)
-
-    def run():
-        torch.manual_seed(1)
-        model = ResNet18(10).to(dev)
-        flat = flatten_params(model)
-        flat0 = flat.clone()
-        tr = ConvNetTrainer(model, dev, 128, (32, 32))
-        tr.load(flat, model)
-        for lo in (0, 128):
-            tr._graph_step(x[lo:lo + 128], y[lo:lo + 128], 0.05)
-        tr.store(flat, model)
-        torch.cuda.synchronize()
-        return flat.clone() - flat0
-
-    for k in ("COLEARN_CONV_IMPLICIT", "COLEARN_CONV_WGRAD_MN", "COLEARN_CONV_DGRAD_KN", "COLEARN_CONV_SPLITK", "COLEARN_CONV_STREAMS",
-              "COLEARN_CONV_FUSED_BN", "COLEARN_CONV_SHADOW_T"):
-        monkeypatch.delenv(k, raising=False)
-    base = run()
+    base = _one_step_update(dev, True)
     for k, v in flags.items():
         monkeypatch.setenv(k, v)
-    got = run()
-    cos = float((got * base).sum() / (got.norm() * base.norm()))
-    assert cos > 0.9 and torch.isfinite(got).all(), cos
+    _assert_same_step(_one_step_update(dev, True), base, cos_min=0.999)
 
 
-# ---- programmatic dependent launch (COLEARN_PDL=1): same kernels, same order, so the update must be bit-identical ------------------
+# ---- programmatic dependent launch (default; COLEARN_PDL=0 = off): same kernels, same order, so the update must be bit-identical ------------------
 _PDL_SCRIPT = """
 import hashlib, torch
 from colearn_federated_learning_b200.fl.convnet import ConvNetTrainer
@@ -420,7 +367,6 @@ print('HASH', hashlib.sha256(flat.cpu().numpy().tobytes()).hexdigest(), bool(tor
 """
 
 
-@unvalidated
 @pytest.mark.parametrize("flags", [{}, {"COLEARN_CONV_WGRAD_MN": "1", "COLEARN_CONV_DGRAD_KN": "1", "COLEARN_CONV_SPLITK": "1",
                                         "COLEARN_CONV_FUSED_BN": "1", "COLEARN_CONV_IMPLICIT": "2"}])
 def test_programmatic_dependent_launch_is_bit_identical(flags):
@@ -433,9 +379,7 @@ def test_programmatic_dependent_launch_is_bit_identical(flags):
 
     def run(pdl):
         env = dict(os.environ, **flags)
-        env.pop("COLEARN_PDL", None)
-        if pdl:
-            env["COLEARN_PDL"] = "1"
+        env["COLEARN_PDL"] = "1" if pdl else "0"
         out = subprocess.run([sys.executable, "-c", _PDL_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         line = [ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][-1].split()
@@ -446,7 +390,6 @@ def test_programmatic_dependent_launch_is_bit_identical(flags):
 
 
 # ---- fused wgrad GEMM -> FedAvg reduce (COLEARN_OVERLAP_REDUCE=1 / overlap_reduce=True); tests/test_overlap_reduce.py has the CPU evidence ----
-@unvalidated
 @pytest.mark.parametrize("graphs", ["1", "0"])
 def test_overlapped_reduce_single_gpu_is_bit_identical(graphs, monkeypatch):
     """World 1: the two-shot kernel on the side stream owns every chunk and takes them as the last backward's wgrad
@@ -473,43 +416,6 @@ def test_overlapped_reduce_single_gpu_is_bit_identical(graphs, monkeypatch):
     assert torch.isfinite(flats[1]).all() and torch.equal(flats[0], flats[1])
 
 
-# ---- line-coalesced GEMM epilogue (COLEARN_GEMM_STAGED=1 / staged=True); tests/test_simt_emul.py has the CPU evidence --------------
-@unvalidated
-@pytest.mark.parametrize("m,n,k,tile_n,cluster", [(256, 256, 192, 0, 0), (256, 256, 192, 0, 3), (512, 768, 448, 256, 1),
-                                                  (1024, 4096, 1024, 0, 0), (384, 128, 64, 128, 0)])
-def test_staged_epilogue_bit_identical_on_device(m, n, k, tile_n, cluster):
-    from colearn_federated_learning_b200 import ops
-    dev = _dev()
-    torch.manual_seed(31)
-    bf = torch.bfloat16
-    a, b = (torch.randn(m, k, device=dev) * 0.3).to(bf), (torch.randn(n, k, device=dev) * 0.3).to(bf)
-    bias, mask, addend = torch.randn(n, device=dev), torch.randn(m, n, device=dev).to(bf), torch.randn(m, n, device=dev).to(bf)
-    m0 = torch.randn(m, n, device=dev)
-
-    def run(staged):
-        kw = dict(tile_n=tile_n, cluster=cluster, staged=staged)
-        r = {}
-        o, ot = torch.zeros(m, n, device=dev, dtype=bf), torch.zeros(n, m, device=dev, dtype=bf)
-        ops.gemm_bf16(a, b, bias=bias, relu=True, out_bf16=o, out_bf16_t=ot, **kw)
-        r["fwd"], r["fwd_t"] = o, ot
-        o, ot, of, cs = torch.zeros(m, n, device=dev, dtype=bf), torch.zeros(n, m, device=dev, dtype=bf), torch.zeros(m, n, device=dev), torch.zeros(m // 32, n, device=dev)
-        ops.gemm_bf16(a, b, relu_mask=mask, addend=addend, out_bf16=o, out_bf16_t=ot, out_f32=of, colsum=cs, **kw)
-        r["dgrad"], r["dgrad_t"], r["dgrad_f"], r["colsum"] = o, ot, of, cs
-        master, sh, sht = m0.clone(), torch.zeros(m, n, device=dev, dtype=bf), torch.zeros(n, m, device=dev, dtype=bf)
-        ops.gemm_bf16(a, b, sgd_master=master, sgd_lr=0.05, sgd_shadow=sh, sgd_shadow_t=sht, **kw)
-        r["master"], r["shadow"], r["shadow_t"] = master, sh, sht
-        torch.cuda.synchronize()
-        return r
-
-    plain, staged = run(False), run(True)
-    for key in plain:
-        if key == "colsum":
-            torch.testing.assert_close(staged[key], plain[key], rtol=1e-5, atol=1e-3)
-        else:
-            assert torch.equal(staged[key], plain[key]), key
-
-
-@unvalidated
 def test_layerwise_trainer_dgrad_against_weights_in_place_on_device():
     """COLEARN_MLP_DGRAD_KN=1: the wide-MLP dgrad reads W_l in place (MN-major B operand) — no W^T copies, no transposes."""
     from colearn_federated_learning_b200.fl import FitConfig
@@ -533,7 +439,6 @@ def test_layerwise_trainer_dgrad_against_weights_in_place_on_device():
         assert float((outs[0] - o).abs().max()) < 2e-3 * max(1.0, float(outs[0].abs().max()))
 
 
-@unvalidated
 def test_star_engine_pipelined_read_back_single_gpu():
     """read_back="pipelined": every round's losses reach the host (one round late), results equal the synchronous mode."""
     from colearn_federated_learning_b200.data import synthetic_unsw

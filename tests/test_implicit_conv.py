@@ -4,7 +4,7 @@ The GPU-less evidence has two parts: (1) the *addressing* — the exact host+dev
 (``conv_kblock`` / ``conv_nblock``, called here through the host build) drives a Python model of tiled 4-D TMA boxes
 (whole images, zero fill outside the tensor) and must reproduce conv2d / its input gradient / its weight gradient;
 (2) the *definitions* of ``ops.conv.conv_gemm`` agree with autograd, and the trainer with the implicit schedule
-agrees with the default one.  The sm_100a runs live in tests/test_zz_round2_gpu.py."""
+agrees with the default one.  The sm_100a runs live in tests/test_gpu_schedules.py."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -147,6 +147,7 @@ def test_conv_gemm_definitions_match_autograd(n, h, w, cin, cout):
     torch.testing.assert_close(master, want, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.usefixtures("legacy_conv_schedule")
 @pytest.mark.parametrize("level,extra", [(1, {}), (2, {}), (2, {"split_k": 1, "dgrad_kn": False}),
                                          (2, {"split_k": 1, "dgrad_kn": True, "wgrad_mn": True})])
 def test_implicit_schedule_is_the_same_step(level, extra):

@@ -1,6 +1,6 @@
 """Fused wgrad GEMM → FedAvg reduce (ops/produced.py, csrc/produced.cuh): host-side bookkeeping on the PyTorch definitions,
 then the whole round — layer-wise trainer, epilogue reports, overlapped two-shot — from the kernel SOURCES on the CPU
-(SIMT shim + functional tcgen05 model).  The GPU run of the same path is in tests/test_zz_round2_gpu.py."""
+(SIMT shim + functional tcgen05 model).  The GPU run of the same path is in tests/test_gpu_schedules.py."""
 import pytest
 import torch
 

@@ -344,7 +344,7 @@ def test_tcgen05_gemm_source_on_the_cpu_model_mn_major(simt):
 def test_implicit_conv_kernels_on_the_cpu_model(simt, n, h, w, cin, cout):
     """Forward / dgrad (K-major W^T and packed MN-major weights, residual addend, 128x64 tile) / wgrad (MN-major 4-D boxes,
     fused SGD, split-K) of a stride-1 3x3 convolution: the producer's 4-D TMA boxes on the model against autograd."""
-    from test_zz_round2_gpu import _implicit_case
+    from test_gpu_schedules import _implicit_case
     from colearn_federated_learning_b200.ops import conv as C
 
     d = _implicit_case(n, h, w, cin, cout)
@@ -518,63 +518,3 @@ def test_overlapped_twoshot_takes_chunks_as_they_are_produced(simt):
     assert int(flags.min()) == 4
 
 
-# ---- line-coalesced epilogue (GemmEpilogue::staged): per-warp 32x32 transpose through swizzled shared memory -------------------------
-@pytest.mark.parametrize("tile_n", [128, 256])
-def test_staged_epilogue_matches_row_per_thread_epilogue(simt, tile_n):
-    """Every epilogue mode through both forms of the epilogue on the functional model: identical bits (the bias-gradient
-    partial sums associate differently, so those compare with a tolerance)."""
-    torch.manual_seed(21)
-    M, N, K = 256, 256, 128
-    a, b = _bf(M, K), _bf(N, K)
-    bias = torch.randn(N)
-    mask = torch.randn(M, N).to(torch.bfloat16)
-    addend = torch.randn(M, N).to(torch.bfloat16)
-
-    def run(staged):
-        st = [0, 0, 0, 1 if staged else 0]
-        res = {}
-        # forward: bias + ReLU, bf16 output + transposed copy
-        o, ot = torch.zeros(M, N, dtype=torch.bfloat16), torch.zeros(N, M, dtype=torch.bfloat16)
-        _gemm(simt, a, b, bias=bias, relu=True, out_bf16=o, out_bf16_t=ot, tile_n=tile_n, produced=st)
-        res["fwd"], res["fwd_t"] = o, ot
-        # dgrad: ReLU mask + residual addend, bf16 + transposed + fp32 outputs, bias-gradient partials
-        o, ot, of = torch.zeros(M, N, dtype=torch.bfloat16), torch.zeros(N, M, dtype=torch.bfloat16), torch.zeros(M, N)
-        cs = torch.zeros(M // 32, N)
-        _gemm(simt, a, b, relu_mask=mask, addend=addend, out_bf16=o, out_bf16_t=ot, out_f32=of, colsum=cs, tile_n=tile_n, produced=st)
-        res["dgrad"], res["dgrad_t"], res["dgrad_f"], res["colsum"] = o, ot, of, cs
-        # wgrad: fused SGD on the fp32 master, bf16 shadow + transposed shadow
-        torch.manual_seed(22)
-        master = torch.randn(M, N)
-        sh, sht = torch.zeros(M, N, dtype=torch.bfloat16), torch.zeros(N, M, dtype=torch.bfloat16)
-        _gemm(simt, a, b, sgd_master=master, sgd_lr=0.05, sgd_shadow=sh, sgd_shadow_t=sht, tile_n=tile_n, produced=st)
-        res["master"], res["shadow"], res["shadow_t"] = master, sh, sht
-        return res
-
-    plain, staged = run(False), run(True)
-    for k in plain:
-        if k == "colsum":
-            torch.testing.assert_close(staged[k], plain[k], rtol=1e-5, atol=1e-4)
-        else:
-            assert torch.equal(staged[k], plain[k]), k
-    acc = a.float() @ b.float().t()
-    torch.testing.assert_close(staged["dgrad_f"], acc * (mask.float() > 0) + addend.float(), rtol=1e-4, atol=1e-4)
-    assert torch.equal(staged["dgrad_t"], staged["dgrad"].t().contiguous()) and torch.equal(staged["shadow_t"], staged["shadow"].t().contiguous())
-    torch.testing.assert_close(staged["colsum"].sum(0), staged["dgrad_f"].sum(0), rtol=1e-4, atol=1e-3)
-
-
-def test_staged_epilogue_with_produced_reports_and_mn_major_operands(simt):
-    """The staged epilogue composes with the other modes that share the kernel: MN-major wgrad operands and the per-chunk
-    produced reports of the fused wgrad -> FedAvg reduce."""
-    from colearn_federated_learning_b200.ops.produced import ProducedSpec
-    torch.manual_seed(23)
-    Kd, ac, M, N, chunk = 128, 128, 128, 256, 4096
-    a, b = _bf(Kd, ac), _bf(Kd, N)
-    n = M * N
-    arena = torch.randn(n)
-    want = arena - 0.1 * (a.float().t() @ b.float()).reshape(-1)
-    tables = torch.zeros(1, 1, n // chunk, dtype=torch.int32)
-    epoch = torch.tensor([2], dtype=torch.int32)
-    sp = ProducedSpec.device(simt, torch.zeros(n // chunk, dtype=torch.int32), [tables.data_ptr()], epoch, 1, chunk_elems=chunk, n=n, rank=0)
-    _gemm(simt, a, b, mn_m=M, sgd_master=arena.view(M, N), sgd_lr=0.1, produced=sp.gemm_arg(0) + [1])
-    torch.testing.assert_close(arena, want, rtol=1e-4, atol=1e-4)
-    assert int(tables.min()) == 3 and sp.idle()
