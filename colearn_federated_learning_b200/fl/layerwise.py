@@ -47,6 +47,23 @@ class LayerwiseMLPTrainer:
 
     @staticmethod
     def supports(spec: MLPSpec, cfg) -> bool:
+        """Any MLP with at least one hidden layer: widths that are not multiples of 128 are zero-padded (a padded hidden
+        neuron has zero weights and bias, outputs relu(0) = 0 and receives a zero gradient through the ReLU mask), batches
+        that are not are padded with rows whose loss gradient is zero (:meth:`forward`), so the 128-row UMMA tiles always
+        see full operands.  Losses: softmax cross-entropy on a linear head, BCE / SSE / MSE on a sigmoid or linear head."""
+        hidden = spec.dims[1:-1]
+        if len(hidden) < 1 or cfg.batch_size < 1:
+            return False
+        if cfg.loss == "xent":
+            return spec.out_activation == "none"
+        if cfg.loss == "bce":
+            return spec.out_activation == "sigmoid"
+        return cfg.loss in ("sse", "mse") and spec.out_activation in ("none", "sigmoid")
+
+    @staticmethod
+    def supports_fused(spec: MLPSpec, cfg) -> bool:
+        """The stricter shape the fused-broadcast / CUDA-graph round of the engine is built for: every hidden layer and the
+        batch fill whole 128-wide tiles, cross-entropy head (BASELINE config 5)."""
         hidden = spec.dims[1:-1]
         return (len(hidden) >= 1 and all(h % 128 == 0 for h in hidden) and cfg.batch_size % 128 == 0
                 and cfg.loss == "xent" and spec.out_activation == "none")
@@ -63,7 +80,10 @@ class LayerwiseMLPTrainer:
 
     def __init__(self, spec: MLPSpec, flat: torch.Tensor, batch_size: int, shadow: Optional[torch.Tensor] = None,
                  dgrad_kn: Optional[bool] = None, wgrad_mn: Optional[bool] = None) -> None:
-        self.spec, self.B, self.dev = spec, batch_size, flat.device
+        # b = the caller's batch size, B = rows of every activation / gradient matrix (whole 128-row tiles); rows >= b carry a
+        # zero loss gradient, so they take part in no update
+        self.spec, self.b, self.B, self.dev = spec, int(batch_size), _pad_to(int(batch_size)), flat.device
+        self._dz_rows = 0                                      # rows of dz[L-1] written since it was last all-zero
         # default (COLEARN_MLP_DGRAD_KN=0 restores the W^T copies): the dgrad reads W_l [out, in] in place as an MN-major B
         # operand (gemm_bf16(b_kn=True)), so no W^T copy exists: one 64 MB transpose pass per 4096 x 4096 layer and step less.
         # Measured on a B200, cfg5 at N=1: 179.2 -> 205.5 rounds/s; with the in-place wgrad below 209.5 (profiles/README.md)
@@ -76,7 +96,7 @@ class LayerwiseMLPTrainer:
         self.offsets = spec.offsets()
         self.kp = [_pad_to(d) for d in self.dims]          # padded widths
         dev, bf = self.dev, torch.bfloat16
-        B = batch_size
+        B = self.B
         self.shadow_arena = shadow                           # bf16 arena written by the two-shot broadcast (or None)
         # bf16 shadows W_l [out_p, in_p] and W_l^T [in_p, out_p]
         self.Ws: List[torch.Tensor] = []
@@ -166,12 +186,26 @@ class LayerwiseMLPTrainer:
         return self._b(flat, l) if self.exact[l] else self.bias_p[l]
 
     # -- one SGD step = forward() + backward() ------------------------------------------------------------
+    def _head_loss(self, z: torch.Tensor, target: torch.Tensor, loss: str):
+        """(loss, dL/dz) of the head for ``z[nv, nc]`` (fp32 logits of the valid rows)."""
+        if loss == "xent":
+            return ops.softmax_xent(z, target.reshape(-1).long())
+        y = target.reshape(z.shape).float()
+        sig = self.spec.out_activation == "sigmoid"
+        if loss == "bce":
+            return ops.sigmoid_bce(z, y)                         # fused sigmoid + mean BCE, dz = (p - y) / numel
+        out = torch.sigmoid(z) if sig else z
+        val, g = ops.sse_loss(out.contiguous(), y, mean=(loss == "mse"))
+        return val, (g * out * (1.0 - out) if sig else g)
+
     def forward(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor,
-                ready: Optional[ReadySpec] = None) -> torch.Tensor:
-        """``ready`` (:class:`ReadySpec`): the GEMMs of the exact layers poll the
-        two-shot broadcast's per-chunk flags from their TMA producer warp (first step of a round)."""
+                ready: Optional[ReadySpec] = None, loss: str = "xent") -> torch.Tensor:
+        """``x``: ``nv <= B`` samples (rows ``nv .. B-1`` of the activations keep whatever finite values they had; their loss
+        gradient is zero).  ``ready`` (:class:`ReadySpec`): the GEMMs of the exact layers poll the two-shot broadcast's
+        per-chunk flags from their TMA producer warp (first step of a round)."""
         L = self.L
-        self.a[0][:, : self.dims[0]].copy_(x)                    # the padding columns are zero since __init__ and never written
+        nv = int(x.shape[0])
+        self.a[0][:nv, : self.dims[0]].copy_(x)                  # the padding columns are zero since __init__ and never written
         if not self.wgrad_mn:
             ops.transpose_bf16(self.a[0], self.aT[0])
         for l in range(L):
@@ -185,13 +219,16 @@ class LayerwiseMLPTrainer:
             else:
                 ops.gemm_bf16(self.a[l], self.Ws[l], bias=self._bias(flat, l), out_f32=self.logits, **kw)
         nc = self.dims[-1]
-        loss, dlog = ops.softmax_xent(self.logits[:, :nc].contiguous(), labels)
-        self.dz[L - 1][:, :nc].copy_(dlog)                       # (same: only the first nc columns are ever written)
+        loss_val, dlog = self._head_loss(self.logits[:nv, :nc].contiguous(), labels, loss)
+        if nv < self._dz_rows:                                   # a shorter batch than before: rows nv.. must carry no gradient
+            self.dz[L - 1][nv:self._dz_rows].zero_()
+        self._dz_rows = nv
+        self.dz[L - 1][:nv, :nc].copy_(dlog)                     # (only the first nc columns are ever written)
         if not self.wgrad_mn:
             ops.transpose_bf16(self.dz[L - 1], self.dzT[L - 1])
         self.db[L - 1][:nc].copy_(dlog.sum(0))
         self.launches += L + 1 + (0 if self.wgrad_mn else 2)       # own kernels: L GEMMs, the loss, two transposes
-        return loss
+        return loss_val
 
     def backward(self, flat: torch.Tensor, lr: float, produced=None) -> None:
         """dgrad with the old weights first, then the (fused) update of layer l.
@@ -244,13 +281,14 @@ class LayerwiseMLPTrainer:
         else:
             ops.gemm_bf16(self.dzT[l], self.aT[l], **epilogue)
 
-    def step(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor, lr: float) -> torch.Tensor:
-        loss = self.forward(flat, x, labels)
+    def step(self, flat: torch.Tensor, x: torch.Tensor, labels: torch.Tensor, lr: float, loss: str = "xent") -> torch.Tensor:
+        loss_val = self.forward(flat, x, labels, loss=loss)
         self.backward(flat, lr)
-        return loss
+        return loss_val
 
     def n_steps(self, n: int, cfg) -> int:
-        steps = (n // self.B) * cfg.epochs
+        """SGD steps of a fit: every epoch walks the whole shard in batches of ``b`` (the last one may be short)."""
+        steps = ((n + self.b - 1) // self.b) * cfg.epochs
         if cfg.max_nr_batches and cfg.max_nr_batches > 0:
             steps = min(steps, cfg.max_nr_batches)
         return steps
@@ -267,7 +305,7 @@ class LayerwiseMLPTrainer:
         ``produced`` + ``before_last_backward`` (fused wgrad → FedAvg reduce): the backward of the round's LAST step
         reports what it finalises (:meth:`backward`); the callback runs right before it is queued — the engine launches
         the overlapped two-shot kernel on its side stream there."""
-        n, B = x.shape[0], self.B
+        n, b = x.shape[0], self.b
         total = self.n_steps(n, cfg)
         if ready is not None and wait_chunks is not None:
             for l in range(self.L):
@@ -276,16 +314,17 @@ class LayerwiseMLPTrainer:
         self.refresh_edge(flat)
         if ready is None:
             self.refresh_exact(flat, from_broadcast=False)
-        labels_all = y.reshape(-1).long()
+        loss = getattr(cfg, "loss", "xent")
+        targets = y.reshape(-1).long() if loss == "xent" else y.reshape(n, -1).float()
         it = 0
         limit = cfg.max_nr_batches if cfg.max_nr_batches and cfg.max_nr_batches > 0 else None
         last = torch.zeros((), device=flat.device)
         for e in range(cfg.epochs):
             order = perm[e % perm.shape[0]].long() if perm is not None else torch.arange(n, device=flat.device)
-            for lo in range(0, n - B + 1, B):
-                idx = order[lo:lo + B]
+            for lo in range(0, n, b):                            # the reference's loaders keep the short last batch (C27)
+                idx = order[lo:lo + b]
                 first = it == 0 and ready is not None
-                last = self.forward(flat, x[idx], labels_all[idx], ready if first else None)
+                last = self.forward(flat, x[idx], targets[idx], ready if first else None, loss=loss)
                 if first:
                     if wait_chunks is not None:
                         wait_chunks(None)

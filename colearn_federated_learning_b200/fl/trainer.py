@@ -16,6 +16,7 @@ Three execution paths, chosen by :func:`local_fit`:
 """
 from __future__ import annotations
 
+import logging
 import os
 from dataclasses import dataclass, asdict
 from typing import Any, Dict, Optional, Tuple
@@ -160,7 +161,38 @@ def local_fit(flat: torch.Tensor, model: nn.Module, x: torch.Tensor, y: torch.Te
             last = tr.fit(flat, model, x, y, cfg, perm)
             LAST_FIT_LAUNCHES = tr.launches - before
             return last, "convnet"
+    if flat.is_cuda:
+        _library_path_guard(model, cfg, x)
     unflatten_params(model, flat)
     last = torch_fit(model, x, y, cfg, perm, autocast_bf16=flat.is_cuda)
     flatten_params(model, out=flat)
     return last, "torch"
+
+
+_WARNED_LIBRARY_PATH: set = set()
+
+
+def _library_path_guard(model: nn.Module, cfg: FitConfig, x: torch.Tensor) -> None:
+    """CUDA tensors never reach autograd + cuBLAS / cuDNN silently.
+
+    * The architectures this repo ships kernels for — every :class:`MLPNet` and ``ResNet18`` — must train on them: a shape
+      the kernels do not cover (e.g. a ResNet shard that is not a whole number of 128-image batches, or images smaller
+      than 32x32) RAISES here instead of quietly switching libraries.  ``COLEARN_CONV_PATH=torch`` is the explicit request
+      for the cuDNN path of conv nets, ``COLEARN_ALLOW_AUTOGRAD=1`` the general one.
+    * A user-registered architecture (``models.register_model`` with an arbitrary ``nn.Module``) has no hand-written
+      kernels by construction; it trains through autograd with this repo's flat SGD step, announced once per class."""
+    from ..models.resnet import ResNet18
+    allow = os.environ.get("COLEARN_ALLOW_AUTOGRAD", "0") == "1"
+    builtin = isinstance(model, (MLPNet, ResNet18))
+    explicit_conv = isinstance(model, ResNet18) and os.environ.get("COLEARN_CONV_PATH", "").strip().lower() == "torch"
+    if builtin and not (allow or explicit_conv):
+        what = (f"MLP {tuple(model.spec.dims)} with loss={cfg.loss!r}, batch_size={cfg.batch_size}" if isinstance(model, MLPNet) else
+                f"ResNet18 on input {tuple(x.shape)} with loss={cfg.loss!r}, batch_size={cfg.batch_size} "
+                "(the conv kernels need xent, batch_size % 128 == 0, shard size % batch_size == 0, images >= 32x32)")
+        raise RuntimeError(f"no sm_100a kernel path for {what}; refusing to fall back to autograd + cuBLAS/cuDNN on a CUDA tensor. "
+                           "Set COLEARN_ALLOW_AUTOGRAD=1 (or COLEARN_CONV_PATH=torch for conv nets) to request the library path.")
+    key = type(model).__name__
+    if key not in _WARNED_LIBRARY_PATH:
+        _WARNED_LIBRARY_PATH.add(key)
+        logging.getLogger(__name__).warning("%s trains through autograd + library kernels (%s); only this repo's flat SGD step is its own",
+                                            key, "requested by environment" if (allow or explicit_conv) else "user-registered architecture")

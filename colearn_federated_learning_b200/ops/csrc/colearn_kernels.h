@@ -68,13 +68,16 @@ namespace colearn {
 #else
 #define COLEARN_HD inline
 #endif
-struct FeistelDomain { int hb; uint32_t mask; };
+// The network is UNBALANCED when the index needs an odd number of bits (left half lb = bits / 2, right half rb = bits - lb;
+// a round maps (l, r) -> (r, l ^ F(r)), so the two widths swap every round and are back after the 4th): the domain is
+// exactly 2^bits < 2 n, i.e. no rejections at all for a power-of-two n and fewer than one per index otherwise.
+struct FeistelDomain { int lb, rb; };
 COLEARN_HD FeistelDomain feistel_domain(uint32_t n) {
   int bits = 1;
   while ((1u << bits) < n) ++bits;
   FeistelDomain d;
-  d.hb = (bits + 1) >> 1;
-  d.mask = (1u << d.hb) - 1u;
+  d.lb = bits >> 1;
+  d.rb = bits - d.lb;
   return d;
 }
 COLEARN_HD uint32_t feistel_mix32(uint32_t x, uint32_t k) {
@@ -84,16 +87,18 @@ COLEARN_HD uint32_t feistel_mix32(uint32_t x, uint32_t k) {
 COLEARN_HD uint32_t feistel_index(uint32_t v, uint32_t n, FeistelDomain dom, uint64_t seed, int row) {
   const uint32_t k0 = (uint32_t)seed ^ (0x51ED270Bu * (uint32_t)(row + 1));
   const uint32_t k1 = (uint32_t)(seed >> 32) + 0x68E31DA4u * (uint32_t)(row + 1);
+  const uint32_t ml = (1u << dom.lb) - 1u, mr = (1u << dom.rb) - 1u;
   do {
-    uint32_t l = v >> dom.hb, r = v & dom.mask;
+    uint32_t l = v >> dom.rb, r = v & mr;          // l: lb bits, r: rb bits
 #pragma unroll
     for (int round = 0; round < 4; ++round) {
-      const uint32_t f = feistel_mix32(r, (round & 1 ? k1 : k0) + 0x9E3779B9u * round) & dom.mask;
+      // even rounds: l has lb bits; odd rounds: the halves have swapped widths
+      const uint32_t f = feistel_mix32(r, (round & 1 ? k1 : k0) + 0x9E3779B9u * round) & ((round & 1) ? mr : ml);
       const uint32_t nl = r;
       r = l ^ f;
       l = nl;
     }
-    v = (l << dom.hb) | r;
+    v = (l << dom.rb) | r;
   } while (v >= n);
   return v;
 }

@@ -168,16 +168,16 @@ int main() {
       ep.conv.mode = 1; ep.conv.C = C; ep.conv.KH = 3; ep.conv.KW = 3; ep.conv.pad = 1; ep.conv.HW = H * W; ep.conv.n_images = n;
       CK(launch_gemm_tcgen05_conv(act.data(), n, H, W, wp.data(), N, 640, M, N, K, ep, nullptr));
     }
-    // line-coalesced epilogue: the per-warp transpose buffer is ordered by __syncwarp only (mask + transposed copy = both trips)
+    // epilogue modes with transposed copies (dgrad: mask + transposed output + column sums; wgrad: fused SGD + both shadows)
     {
       const int M = 256, N = 256, K = 128;
       auto a = bf((size_t)M * K), b = bf((size_t)N * K), mask = bf((size_t)M * N);
       std::vector<__nv_bfloat16> out((size_t)M * N), out_t((size_t)M * N);
       std::vector<float> cs((size_t)(M / 32) * N), master((size_t)M * N, 1.f);
-      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.staged = 1; ep.relu_mask = mask.data(); ep.out_bf16 = out.data();
+      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.relu_mask = mask.data(); ep.out_bf16 = out.data();
       ep.out_bf16_t = out_t.data(); ep.colsum = cs.data();
       CK(launch_gemm_tcgen05(a.data(), b.data(), M, N, K, ep, nullptr));
-      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.staged = 1; ep.sgd_master = master.data(); ep.sgd_lr = 0.1f;
+      memset(&ep, 0, sizeof(ep)); ep.ready_chunk_elems = 1; ep.sgd_master = master.data(); ep.sgd_lr = 0.1f;
       ep.sgd_shadow = out.data(); ep.sgd_shadow_t = out_t.data(); ep.tile_n = 256;
       CK(launch_gemm_tcgen05(a.data(), b.data(), M, N, K, ep, nullptr));
     }

@@ -483,7 +483,7 @@ class FederatedEngine:
         self._lw_checked, self._lw = True, None
         if self.spec is not None:
             from ..fl.layerwise import LayerwiseMLPTrainer
-            if LayerwiseMLPTrainer.supports(self.spec, self.cfg):
+            if LayerwiseMLPTrainer.supports_fused(self.spec, self.cfg):
                 shadow = self.arena.tensor("shadow") if self.bf16_shadow else None
                 self._lw = LayerwiseMLPTrainer(self.spec, self.theta[: self.P], self.cfg.batch_size, shadow=shadow)
         return self._lw
@@ -525,7 +525,7 @@ class FederatedEngine:
         cf_ptr = self.arena.ptr("chunk_flags")
         fused = epoch > 1 and self.bf16_shadow
         xs = self.x.view(n, -1)
-        if fused and self.use_graphs:
+        if fused and self.use_graphs and n % self.cfg.batch_size == 0:
             # launch-bound inner loop -> ONE CUDA-graph replay per round (flag epoch + sample order are device-side)
             if getattr(lw, "graph", None) is None:
                 steps = (n // self.cfg.batch_size) * self.cfg.epochs

@@ -238,8 +238,8 @@ def test_layerwise_tcgen05_trainer_matches_autograd():
     x, y = torch.rand(384, 10), torch.randint(0, 2, (384, 1)).float()
     cfg = FitConfig(model="x", loss="xent", batch_size=128, lr=0.1)
     assert LayerwiseMLPTrainer.supports(spec, cfg)
-    tr = LayerwiseMLPTrainer(spec, flat, 128)
-    last = tr.fit(flat, x.to(dev), y.to(dev), cfg, None)
+    tr = LayerwiseMLPTrainer(spec, flat, 128, dgrad_kn=False, wgrad_mn=False)   # K-major form (W^T copies kept); the default
+    last = tr.fit(flat, x.to(dev), y.to(dev), cfg, None)                         # in-place operand form: test_gpu_schedules.py
     torch.cuda.synchronize()
     opt = torch.optim.SGD(m.parameters(), lr=0.1)
     for lo in (0, 128, 256):

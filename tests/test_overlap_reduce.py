@@ -159,7 +159,7 @@ def test_transposes_are_refreshed_on_demand_and_never_after_the_last_step(monkey
     torch.manual_seed(7)
     x, y = torch.rand(384, 10), torch.randint(0, 2, (384, 1)).float()
     a0, P = _arena(spec, 5, extra=0)
-    tr = LayerwiseMLPTrainer(spec, a0[:P], 128)
+    tr = LayerwiseMLPTrainer(spec, a0[:P], 128, dgrad_kn=False, wgrad_mn=False)      # the K-major form: W^T copies exist
     calls = []
     real = lw_mod.ops.transpose_bf16
 
@@ -180,7 +180,7 @@ def test_transposes_are_refreshed_on_demand_and_never_after_the_last_step(monkey
         assert torch.equal(tr.WsT[l], tr.Ws[l].t().contiguous())
     # two consecutive fits == one trainer doing the same steps with eager transposes (reference: recompute from scratch)
     b0, _ = _arena(spec, 5, extra=0)
-    tr2 = LayerwiseMLPTrainer(spec, b0[:P], 128)
+    tr2 = LayerwiseMLPTrainer(spec, b0[:P], 128, dgrad_kn=False, wgrad_mn=False)
     tr2.fit(b0[:P], x, y, cfg, None)
     assert torch.equal(a0, b0)
     tr.fit(a0[:P], x, y, cfg, None)
