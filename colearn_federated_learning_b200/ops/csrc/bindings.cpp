@@ -54,6 +54,14 @@ py::bytes make_client_desc(int64_t x, int64_t y, int64_t perm, int64_t theta_in,
 }
 int64_t client_desc_size() { return (int64_t)sizeof(ClientDesc); }
 
+// limit of every bounded cross-GPU flag wait on the CURRENT device (colearn_kernels.h: spin_wait_ge); 0 = wait forever
+void set_spin_limit(double seconds) {
+  const unsigned long long ns = seconds <= 0 ? 0ull : (unsigned long long)(seconds * 1e9);
+  check(set_spin_limit_comm(ns), "set_spin_limit (comm)");
+  check(set_spin_limit_mlp(ns), "set_spin_limit (mlp)");
+  check(set_spin_limit_gemm(ns), "set_spin_limit (gemm)");
+}
+
 void mlp_local_sgd(int64_t net_kind, torch::Tensor descs, int64_t desc_offset, int64_t n_clients,
                    int64_t batch_size, int64_t epochs, int64_t max_steps, int64_t loss, double lr, int64_t variant) {
   TORCH_CHECK(descs.is_cuda() && descs.scalar_type() == at::kByte && descs.is_contiguous(), "descs must be CUDA uint8");
@@ -494,6 +502,7 @@ struct ConvCudaExec {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "colearn_federated_learning_b200 sm_100a kernels";
   m.def("make_client_desc", &make_client_desc);
+  m.def("set_spin_limit", &set_spin_limit);
   m.def("client_desc_size", &client_desc_size);
   m.def("mlp_local_sgd", &mlp_local_sgd);
   m.def("mlp_net_params", &mlp_net_params);

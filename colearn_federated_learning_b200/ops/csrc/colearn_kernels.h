@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdio>
+
 #include "conv_ops.cuh"
 
 // The SIMT kernels that also run on the CPU for the test-suite (host_shim.h) declare their dynamic shared memory and
@@ -57,6 +59,54 @@ inline cudaError_t launch_maybe_pdl(void (*plain)(const Arg), void (*pdl)(const 
 }  // namespace colearn
 
 namespace colearn {
+
+// ---------------------------------------------------------------------------------------------
+// Bounded cross-GPU flag wait.  Every "wait until a peer raised this flag to >= want" of the round protocol (broadcast flag
+// in the worker kernels, arrive / chunk flags in the star and two-shot kernels, per-chunk ready flags in the GEMM's TMA
+// producer) goes through spin_wait_ge: ld.acquire.sys + __nanosleep, and once the wait exceeds the limit — a peer that died or
+// wedged never signals — it prints what it was waiting for and traps, so the launch FAILS (cudaErrorLaunchFailure on the
+// host, the round raises) instead of hanging the box until some outer watchdog kills the job.  The limit is generous (120 s,
+// COLEARN_SPIN_TIMEOUT_S at module load; 0 = wait forever): a coordinator legitimately waits for a whole local fit.
+// One copy of the limit per translation unit (no relocatable device code): set_spin_limit_* in each .cu.
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDACC__) && !defined(COLEARN_HOST_SHIM)
+static __device__ unsigned long long g_spin_limit_ns = 120ull * 1000000000ull;
+__device__ __forceinline__ uint32_t spin_ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long spin_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void spin_wait_failed(const uint32_t* p, uint32_t want, uint32_t have, const char* what) {
+  printf("colearn: %s: flag %p stayed at %u (< %u) beyond the spin limit: a peer never signalled; failing the launch "
+         "(block %d, thread %d)\n", what, (const void*)p, have, want, (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void spin_wait_ge(const uint32_t* p, uint32_t want, unsigned sleep_ns, const char* what) {
+  uint32_t v = spin_ld_acquire_sys(p);
+  if (v >= want) return;
+  const unsigned long long limit = g_spin_limit_ns, t0 = spin_globaltimer();
+  unsigned it = 0;
+  while ((v = spin_ld_acquire_sys(p)) < want) {
+    __nanosleep(sleep_ns);
+    if (limit != 0 && (++it & 1023u) == 0 && spin_globaltimer() - t0 > limit) spin_wait_failed(p, want, v, what);
+  }
+}
+#define COLEARN_DEFINE_SPIN_LIMIT_SETTER(name)                                                         \
+  cudaError_t name(unsigned long long ns) { return cudaMemcpyToSymbol(g_spin_limit_ns, &ns, sizeof(ns)); }
+#else
+inline void spin_wait_ge(const uint32_t* p, uint32_t want, unsigned, const char*) {
+  while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < want) {}
+}
+#define COLEARN_DEFINE_SPIN_LIMIT_SETTER(name) cudaError_t name(unsigned long long) { return cudaSuccess; }
+#endif
+cudaError_t set_spin_limit_comm(unsigned long long ns);
+cudaError_t set_spin_limit_mlp(unsigned long long ns);
+cudaError_t set_spin_limit_gemm(unsigned long long ns);
 
 // ---------------------------------------------------------------------------------------------
 // Keyed bijection on [0, n) (shuffle=True of the reference's loaders): 4-round Feistel network over 2*hb bits

@@ -116,7 +116,7 @@ star_round_kernel(StarRoundArgs a) {
   if (a.do_reduce) {
     if (a.timeout_ns == 0) {
       if (tid < a.world && ((mask >> tid) & 1u))
-        while (ld_acquire_sys(a.arrive_flags + tid) < a.arrive_epoch) __nanosleep(20);
+        spin_wait_ge(a.arrive_flags + tid, a.arrive_epoch, 20, "star_round: arrive flag of a selected worker");
       __syncthreads();
     } else {
       __shared__ uint32_t s_mask;
@@ -324,7 +324,7 @@ twoshot_fedavg_kernel(TwoShotArgs a) {
   if (tid < a.world) {
     sw[tid] = a.weights[tid];
     if ((a.select_mask >> tid) & 1u)
-      while (ld_acquire_sys(a.arrive_flags + tid) < a.epoch) __nanosleep(20);
+      spin_wait_ge(a.arrive_flags + tid, a.epoch, 20, "twoshot_fedavg: arrive flag of a selected rank");
   }
   __syncthreads();
   const int64_t n_chunks = (a.n + a.chunk_elems - 1) / a.chunk_elems;
@@ -337,7 +337,7 @@ twoshot_fedavg_kernel(TwoShotArgs a) {
   // (3) optionally hold the stream until the whole arena of THIS rank has been refreshed by its owners
   if (a.wait_all) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < n_chunks; c += (int64_t)gridDim.x * blockDim.x)
-      while (ld_acquire_sys(a.chunk_flags[a.rank] + c) < a.epoch) __nanosleep(40);
+      spin_wait_ge(a.chunk_flags[a.rank] + c, a.epoch, 40, "twoshot_fedavg: chunk flag of my arena (its owner never pushed it)");
   }
 }
 
@@ -396,7 +396,7 @@ twoshot_overlap_kernel(TwoShotArgs a) {
   }
   if (a.wait_all) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < n_chunks; c += (int64_t)gridDim.x * blockDim.x)
-      while (ld_acquire_sys(a.chunk_flags[a.rank] + c) < a.epoch) __nanosleep(40);
+      spin_wait_ge(a.chunk_flags[a.rank] + c, a.epoch, 40, "twoshot_fedavg: chunk flag of my arena (its owner never pushed it)");
   }
 }
 
@@ -459,18 +459,18 @@ __global__ void signal_peers_kernel(PeerFlags f, int world, uint32_t value) {
   if ((int)threadIdx.x < world) st_release_sys(f.ptr[threadIdx.x], value);
 }
 __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value) {
-  while (ld_acquire_sys(flag) < value) __nanosleep(50);
+  spin_wait_ge(flag, value, 50, "wait_flag");
 }
 // wait until every one of `count` consecutive flags reached `value`
 __global__ void wait_flags_kernel(const uint32_t* flags, int count, uint32_t value) {
   for (int i = threadIdx.x; i < count; i += blockDim.x)
-    while (ld_acquire_sys(flags + i) < value) __nanosleep(50);
+    spin_wait_ge(flags + i, value, 50, "wait_flags: chunk flag of the previous round's broadcast");
 }
 
 __global__ void wait_flags_dev_kernel(const uint32_t* flags, int count, const uint32_t* value_ptr) {
   const uint32_t value = ld_acquire_sys(value_ptr);
   for (int i = threadIdx.x; i < count; i += blockDim.x)
-    while (ld_acquire_sys(flags + i) < value) __nanosleep(50);
+    spin_wait_ge(flags + i, value, 50, "wait_flags: chunk flag of the previous round's broadcast");
 }
 
 __global__ void __launch_bounds__(512)
@@ -572,5 +572,7 @@ cudaError_t launch_p2p_copy(float* dst, const float* src, int64_t n, uint32_t* f
   COLEARN_LAUNCH(p2p_copy_kernel, n_blocks, 512, 0, s, dst, src, n, flag, flag_value, counter);
   return cudaGetLastError();
 }
+
+COLEARN_DEFINE_SPIN_LIMIT_SETTER(set_spin_limit_comm)
 
 }  // namespace colearn

@@ -434,12 +434,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int64_t c_lo = (ep.ready_elem_offset + (int64_t)n0 * K) / ep.ready_chunk_elems;
           const int64_t c_hi = (ep.ready_elem_offset + (int64_t)(n0 + BN) * K - 1) / ep.ready_chunk_elems;
           for (int64_t c = c_lo; c <= c_hi; ++c)
-            while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
+            spin_wait_ge(ep.ready_flags + c, want, 64, "gemm_tcgen05: ready flag of a broadcast weight chunk");
           if (ep.bias != nullptr) {  // the layer's fp32 bias directly follows its weight in the flat arena
             const int64_t b_lo = (ep.ready_elem_offset + (int64_t)N * K + n0) / ep.ready_chunk_elems;
             const int64_t b_hi = (ep.ready_elem_offset + (int64_t)N * K + n0 + BN - 1) / ep.ready_chunk_elems;
             for (int64_t c = b_lo; c <= b_hi; ++c)
-              while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
+              spin_wait_ge(ep.ready_flags + c, want, 64, "gemm_tcgen05: ready flag of a broadcast weight chunk");
           }
           fence_proxy_async();
         }
@@ -855,12 +855,12 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           const int64_t c_lo = (ep.ready_elem_offset + (int64_t)nb0 * K) / ep.ready_chunk_elems;
           const int64_t c_hi = (ep.ready_elem_offset + (int64_t)(nb0 + BN / 2) * K - 1) / ep.ready_chunk_elems;
           for (int64_t c = c_lo; c <= c_hi; ++c)
-            while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
+            spin_wait_ge(ep.ready_flags + c, want, 64, "gemm_tcgen05: ready flag of a broadcast weight chunk");
           if (ep.bias != nullptr) {
             const int64_t b_lo = (ep.ready_elem_offset + (int64_t)N * K + n0) / ep.ready_chunk_elems;
             const int64_t b_hi = (ep.ready_elem_offset + (int64_t)N * K + n0 + BN - 1) / ep.ready_chunk_elems;
             for (int64_t c = b_lo; c <= b_hi; ++c)
-              while (ld_acquire_sys(ep.ready_flags + c) < want) __nanosleep(64);
+              spin_wait_ge(ep.ready_flags + c, want, 64, "gemm_tcgen05: ready flag of a broadcast weight chunk");
           }
           fence_proxy_async();
         }
@@ -1172,5 +1172,7 @@ cudaError_t launch_gemm_tcgen05(const void* A, const void* B, int M, int N, int 
   }
   return launch_t<128, 1>(A, B, M, N, K, ep, s);
 }
+
+COLEARN_DEFINE_SPIN_LIMIT_SETTER(set_spin_limit_gemm)
 
 }  // namespace colearn

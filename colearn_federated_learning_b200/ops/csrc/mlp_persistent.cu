@@ -297,7 +297,7 @@ mlp_local_sgd_kernel(const ClientDesc* __restrict__ descs, SgdHyper hp) {
   // (1) wait for the broadcast of this round's global model to land
   if (d.wait_flag != nullptr) {
     if (tid == 0) {
-      while (ld_acquire_sys(d.wait_flag) < d.wait_value) __nanosleep(32);
+      spin_wait_ge(d.wait_flag, d.wait_value, 32, "mlp_local_sgd: broadcast flag of this round");
     }
     __syncthreads();
   }
@@ -598,5 +598,7 @@ cudaError_t launch_mlp_forward(int net_kind, const float* theta, const float* x,
     default: return cudaErrorInvalidValue;
   }
 }
+
+COLEARN_DEFINE_SPIN_LIMIT_SETTER(set_spin_limit_mlp)
 
 }  // namespace colearn

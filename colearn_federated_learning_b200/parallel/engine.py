@@ -161,6 +161,10 @@ class FederatedEngine:
                 layout["produced"] = (W * self.n_chunks, torch.int32)   # [producer rank, chunk] epochs of the chunks I own
         self.arena = SymmetricArena(layout, self.device, self.group)
         self.ext = ops._ext.require()
+        # every cross-GPU flag wait of the round kernels is bounded: past this many seconds without the peer's signal the
+        # kernel traps and the round raises instead of hanging the box (0 = wait forever)
+        self.spin_timeout_s = float(os.environ.get("COLEARN_SPIN_TIMEOUT_S", "120"))
+        self.ext.set_spin_limit(self.spin_timeout_s)
         self.grid_counter = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.decision = torch.zeros(2, dtype=torch.int32, device=self.device)
         self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -567,8 +571,11 @@ class FederatedEngine:
     def _run_twoshot(self, rounds: int, masks: List[int], host_inputs, read_back: bool) -> RoundReport:
         ext, arena, W, P4, r = self.ext, self.arena, self.world, self.P4, self.rank
         dev = self.device
-        if abs(self.server_lr - 1.0) > 1e-12:
-            raise NotImplementedError("twoshot supports server_lr == 1 (plain FedAvg) in this version")
+        use_prev = abs(self.server_lr - 1.0) > 1e-12
+        if use_prev and getattr(self, "theta_prev", None) is None:
+            # server_lr != 1: theta <- theta + lr_s (sum_k w_k theta_k - theta) needs the model the round started from, and the
+            # ranks train IN PLACE on the arena — every rank keeps a copy (one local P-element pass per round)
+            self.theta_prev = torch.empty(P4, device=dev)
         work_ptrs = arena.peer_ptrs("work")
         shadow_ptrs = arena.peer_ptrs("shadow") if self.bf16_shadow else []
         cflag_ptrs = arena.peer_ptrs("chunk_flags")
@@ -596,14 +603,18 @@ class FederatedEngine:
                     self.y.copy_(hy.view(-1, 1), non_blocking=True)
             wts = self._round_weights(masks[i])
             self.weights_dev[:W].copy_(torch.tensor(wts, dtype=torch.float32), non_blocking=True)
+            if use_prev:
+                if e > 1:
+                    ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e - 1)      # the arena holds the whole previous result
+                self.theta_prev.copy_(arena.tensor("work"))
             need_wait = read_back or i == rounds - 1   # otherwise the next round's consumer polls the flags
             sel_w = [w for k, w in enumerate(wts) if (masks[i] >> k) & 1]
             nvls = (self.use_nvls and arena.has_multicast and masks[i] == (1 << W) - 1 and W > 1
-                    and max(sel_w) - min(sel_w) < 1e-7)
+                    and max(sel_w) - min(sel_w) < 1e-7 and not use_prev)
 
             def twoshot(blocks: int, produced_ptr: int):
                 ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
-                                   0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, blocks,
+                                   self.theta_prev.data_ptr() if use_prev else 0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, blocks,
                                    arrive_ptrs if not produced_ptr else [], need_wait,
                                    arena.mc_ptr("work") if nvls else 0,
                                    arena.mc_ptr("shadow") if (nvls and self.bf16_shadow) else 0,

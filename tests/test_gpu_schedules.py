@@ -459,3 +459,59 @@ def test_star_engine_pipelined_read_back_single_gpu():
             assert torch.allclose(hist[:, :2], rep.losses[:, 0, :].cpu(), atol=0, rtol=0)
             assert torch.equal(eng.loss_host[:2], hist[-1, :2])
     assert torch.equal(flats[0], flats[1])
+
+
+def test_twoshot_engine_applies_the_server_learning_rate():
+    """server_lr != 1 on the large-model (two-shot) path: theta <- theta + lr_s (sum_k w_k theta_k - theta).  The ranks train in
+    place on the arena, so the engine keeps the round's starting model; world 1: theta_1 = theta_0 + lr_s (fit(theta_0) - theta_0)."""
+    from colearn_federated_learning_b200.data import synthetic_unsw
+    from colearn_federated_learning_b200.parallel import FederatedEngine
+    dev = _dev()
+    xs, ys = synthetic_unsw(256, seed=21)
+    outs = {}
+    for lr_s in (1.0, 0.5):
+        eng = FederatedEngine("wide_mlp", backend="fused", device=dev, batch_size=128, lr=0.05, seed=6, chunk_elems=4096, bf16_shadow=True,
+                              model_kwargs={"width": 256, "depth": 3}, server_lr=lr_s)
+        eng.set_local_data(xs, ys)
+        theta0 = eng.global_flat().clone()
+        rep = eng.run_rounds(1)
+        torch.cuda.synchronize()
+        outs[lr_s] = (theta0, eng.global_flat().clone(), eng.arena.tensor("shadow")[: eng.P].clone())
+        assert rep.extra["nvls"] is False
+    theta0, full, _ = outs[1.0]
+    _, half, shadow = outs[0.5]
+    assert torch.equal(outs[0.5][0], theta0) and not torch.equal(full, theta0)
+    torch.testing.assert_close(half, theta0 + 0.5 * (full - theta0), rtol=1e-6, atol=1e-7)
+    assert torch.equal(shadow, half.to(torch.bfloat16))
+
+
+_SPIN_SCRIPT = """
+import torch
+from colearn_federated_learning_b200.ops import _ext
+ext = _ext.require()
+dev = torch.device('cuda:0')
+torch.cuda.set_device(dev)
+ext.set_spin_limit(0.3)                       # seconds
+flags = torch.zeros(4, dtype=torch.int32, device=dev)
+ext.wait_flags(flags.data_ptr(), 4, 7)        # nobody will ever raise these
+try:
+    torch.cuda.synchronize()
+    print('NO_ERROR')
+except Exception as e:
+    print('TRAPPED', type(e).__name__)
+"""
+
+
+def test_a_wait_for_a_peer_that_never_signals_fails_the_launch_instead_of_hanging():
+    """Every cross-GPU flag wait is bounded (colearn_kernels.h: spin_wait_ge): past the limit the kernel says what it was
+    waiting for and traps, the host sees a launch failure.  The CUDA context is dead afterwards: subprocess."""
+    import subprocess
+    import sys
+    import time
+    _dev()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t0 = time.time()
+    out = subprocess.run([sys.executable, "-c", _SPIN_SCRIPT], cwd=root, capture_output=True, text=True, timeout=120)
+    assert "TRAPPED" in out.stdout, (out.stdout[-500:], out.stderr[-1500:])
+    assert "stayed at 0 (< 7)" in out.stdout + out.stderr and "wait_flags" in out.stdout + out.stderr
+    assert time.time() - t0 < 60
