@@ -448,6 +448,30 @@ def run_engine_config(args, name: str, rank: int, world: int, device, full: bool
            "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("COLEARN_")}, **extra}
     if check is not None:
         cfg["self_check"] = check
+    if engine.algo == "twoshot":
+        # roofline of the round (BASELINE.json: "the slower of its compute at peak and its bytes over NVLink at link bandwidth"):
+        # compute = the rank's local fit (MLP: 6 FLOP per parameter and sample) at the MEASURED bf16 matmul peak; link = the
+        # all-reduce-with-broadcast of the arena through one GPU's NVLink port, (W-1)/W of the model per direction, fp32 in and
+        # fp32 + bf16 shadow out, at 900 GB/s per direction
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak_tflops = float(peaks.get("bf16_tflops", 1693.2))
+        P = engine.P
+        flops = 6.0 * P * n_local * epochs if model == "wide_mlp" else None
+        out_bytes = P * (4 + (2 if engine.bf16_shadow else 0))
+        link_bytes = (world - 1) / world * max(P * 4, out_bytes)
+        t_compute = flops / (peak_tflops * 1e12) * 1e3 if flops else None
+        t_link = link_bytes / 900e9 * 1e3
+        bound = max(t_compute or 0.0, t_link)
+        ms = dev_ms / K
+        cfg["roofline"] = {"compute_ms_at_measured_peak": t_compute, "peak_bf16_tflops": peak_tflops, "link_ms_at_900GBps_per_dir": t_link,
+                           "link_bytes_per_dir_per_gpu": int(link_bytes), "bound_ms": bound, "roofline_frac": (bound / ms) if bound else None,
+                           "achieved_tflops_per_gpu": (flops / (ms * 1e-3) / 1e12) if flops else None,
+                           "note": "frac = max(compute at peak, bytes at link rate) / measured round time"}
     return {
         "metric": "FL rounds/sec (whole box, device-timed, max over ranks)",
         "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,

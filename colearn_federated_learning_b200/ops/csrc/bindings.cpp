@@ -30,7 +30,7 @@ inline T* ptr_of(int64_t p) { return reinterpret_cast<T*>(static_cast<uintptr_t>
 py::bytes make_client_desc(int64_t x, int64_t y, int64_t perm, int64_t theta_in, int64_t theta_out,
                            int64_t loss_out, int64_t wait_flag, int64_t wait_value, int64_t signal_flag,
                            int64_t signal_value, int64_t n, int64_t perm_rows, int64_t y_dim,
-                           double out_scale, int64_t delta_mode, int64_t perm_seed, int64_t perm_row0) {
+                           double out_scale, int64_t delta_mode, int64_t perm_seed, int64_t perm_row0, int64_t perm_scratch) {
   ClientDesc d;
   std::memset(&d, 0, sizeof(d));
   d.x = ptr_of<const float>(x);
@@ -50,9 +50,15 @@ py::bytes make_client_desc(int64_t x, int64_t y, int64_t perm, int64_t theta_in,
   d.delta_mode = (int)delta_mode;
   d.perm_seed = (uint64_t)perm_seed;
   d.perm_row0 = (int)perm_row0;
+  d.perm_scratch = ptr_of<int>(perm_scratch);
   return py::bytes(reinterpret_cast<const char*>(&d), sizeof(d));
 }
 int64_t client_desc_size() { return (int64_t)sizeof(ClientDesc); }
+
+// p[0:n] *= scale for a raw device pointer (the symmetric work arena)
+void scale_inplace(int64_t ptr, int64_t n, double scale) {
+  check(launch_scale_inplace(ptr_of<float>(ptr), (float)scale, n, cur_stream()), "scale_inplace");
+}
 
 // limit of every bounded cross-GPU flag wait on the CURRENT device (colearn_kernels.h: spin_wait_ge); 0 = wait forever
 void set_spin_limit(double seconds) {
@@ -60,6 +66,7 @@ void set_spin_limit(double seconds) {
   check(set_spin_limit_comm(ns), "set_spin_limit (comm)");
   check(set_spin_limit_mlp(ns), "set_spin_limit (mlp)");
   check(set_spin_limit_gemm(ns), "set_spin_limit (gemm)");
+  check(preload_comm_kernels(), "preload_comm_kernels");     // same call site: once per device, before any round
 }
 
 void mlp_local_sgd(int64_t net_kind, torch::Tensor descs, int64_t desc_offset, int64_t n_clients,
@@ -503,6 +510,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "colearn_federated_learning_b200 sm_100a kernels";
   m.def("make_client_desc", &make_client_desc);
   m.def("set_spin_limit", &set_spin_limit);
+  m.def("scale_inplace", &scale_inplace);
   m.def("client_desc_size", &client_desc_size);
   m.def("mlp_local_sgd", &mlp_local_sgd);
   m.def("mlp_net_params", &mlp_net_params);

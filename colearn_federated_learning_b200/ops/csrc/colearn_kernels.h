@@ -105,6 +105,7 @@ inline void spin_wait_ge(const uint32_t* p, uint32_t want, unsigned, const char*
 #define COLEARN_DEFINE_SPIN_LIMIT_SETTER(name) cudaError_t name(unsigned long long) { return cudaSuccess; }
 #endif
 cudaError_t set_spin_limit_comm(unsigned long long ns);
+cudaError_t preload_comm_kernels();   // force the lazy loader for every kernel of comm.cu (see there)
 cudaError_t set_spin_limit_mlp(unsigned long long ns);
 cudaError_t set_spin_limit_gemm(unsigned long long ns);
 
@@ -179,8 +180,10 @@ struct ClientDesc {
   float out_scale;         // FedAvg weight w_k pre-applied by the producer
   int delta_mode;          // 0: out = w*theta_k ; 1: out = w*(theta_k - theta_in)
   int perm_row0;           // in-kernel shuffle: epoch e of this fit uses permutation row perm_row0 + e
-  uint64_t perm_seed;      // != 0 (and perm == nullptr): sample order = feistel_index(pos, n, key(perm_seed, row)) computed by
-                           // the gather itself — the same bijection feistel_perm_kernel tabulates, without a table or a launch
+  uint64_t perm_seed;      // != 0 (and perm == nullptr): the kernel fills perm_scratch with feistel_index(pos, n, key(perm_seed,
+                           // perm_row0 + epoch)) for every epoch of the fit before it waits for the broadcast — the bijection
+                           // feistel_perm_kernel tabulates, without a separate launch
+  int* perm_scratch;       // [epochs of this fit, n] ints owned by this client (device memory), used with perm_seed
 };
 
 struct SgdHyper {
@@ -207,6 +210,7 @@ cudaError_t launch_mlp_forward(int net_kind, const float* theta, const float* x,
 // Elementwise / reduction kernels (elementwise.cu)
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_sgd_step(float* param, const float* grad, float lr, int64_t n, cudaStream_t s);
+cudaError_t launch_scale_inplace(float* p, float scale, int64_t n, cudaStream_t s);   // p *= scale
 cudaError_t launch_sgd_step_bf16grad(float* param, const void* grad_bf16, float lr, int64_t n,
                                      cudaStream_t s);
 // theta <- theta + server_lr * (sum_k w[k] * slots[k*stride .. ] - theta)   (weights sum to 1)

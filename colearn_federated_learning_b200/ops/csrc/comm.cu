@@ -575,4 +575,24 @@ cudaError_t launch_p2p_copy(float* dst, const float* src, int64_t n, uint32_t* f
 
 COLEARN_DEFINE_SPIN_LIMIT_SETTER(set_spin_limit_comm)
 
+// CUDA loads a kernel's code lazily at its first launch, and that load can need the device to be idle.  Kernels of this file
+// spin on flags that OTHER kernels raise (the overlapped two-shot waits for the last backward pass' reports; the workers wait
+// for the coordinator's broadcast), so a kernel that is launched for the first time while a spinning kernel is resident can
+// deadlock the device (seen on a B200: the first produced_mark_kernel next to twoshot_overlap_kernel).  Touching the function
+// attributes forces the load; the engine calls this once per device before any round.
+cudaError_t preload_comm_kernels() {
+#ifndef COLEARN_HOST_SHIM
+  cudaFuncAttributes attr;
+  const void* kernels[] = {(const void*)star_round_kernel, (const void*)twoshot_fedavg_kernel, (const void*)twoshot_overlap_kernel,
+                           (const void*)produced_mark_kernel, (const void*)reduce_push_kernel, (const void*)set_flag_kernel,
+                           (const void*)signal_peers_kernel, (const void*)wait_flag_kernel, (const void*)wait_flags_kernel,
+                           (const void*)wait_flags_dev_kernel, (const void*)p2p_copy_kernel};
+  for (const void* k : kernels) {
+    cudaError_t e = cudaFuncGetAttributes(&attr, k);
+    if (e != cudaSuccess) return e;
+  }
+#endif
+  return cudaSuccess;
+}
+
 }  // namespace colearn

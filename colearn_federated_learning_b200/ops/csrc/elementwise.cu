@@ -63,6 +63,26 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+// p *= scale in place: a rank pre-scales its trained arena by its FedAvg weight n_k / sum n (0 for a rank that was not
+// selected) so that the in-switch multimem.ld_reduce of the two-shot kernel — which sums every member of the multicast group
+// with equal weight — yields the weighted / subset average
+__global__ void scale_inplace_kernel(float* __restrict__ p, float scale, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)p) & 15) == 0) {
+    const int64_t n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (int64_t j = i; j < n4; j += stride) {
+      float4 a = p4[j];
+      a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+      p4[j] = a;
+    }
+    for (int64_t j = (n4 << 2) + i; j < n; j += stride) p[j] *= scale;
+  } else {
+    for (int64_t j = i; j < n; j += stride) p[j] *= scale;
+  }
+}
+
 __global__ void sgd_step_bf16grad_kernel(float* __restrict__ p, const __nv_bfloat16* __restrict__ g,
                                          float lr, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -342,6 +362,10 @@ __global__ void l2_flush_kernel(float* __restrict__ buf, int64_t n) {
 
 cudaError_t launch_sgd_step(float* p, const float* g, float lr, int64_t n, cudaStream_t s) {
   COLEARN_LAUNCH(sgd_step_kernel, grid_for(n), kThreads, 0, s, p, g, lr, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_scale_inplace(float* p, float scale, int64_t n, cudaStream_t s) {
+  COLEARN_LAUNCH(scale_inplace_kernel, grid_for(n), kThreads, 0, s, p, scale, n);
   return cudaGetLastError();
 }
 cudaError_t launch_sgd_step_bf16grad(float* p, const void* g, float lr, int64_t n, cudaStream_t s) {

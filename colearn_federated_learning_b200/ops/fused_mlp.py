@@ -69,20 +69,24 @@ class ClientTask:
     signal_value: int = 0
     out_scale: float = 1.0
     delta_mode: bool = False
-    perm_seed: int = 0                   # != 0 with perm=None: the kernel's gather computes the keyed Feistel order itself
-    perm_row0: int = 0                   # ... epoch e uses row perm_row0 + e of device_permutation(n, *, perm_seed)
+    perm_seed: int = 0                   # != 0 with perm=None: the kernel tabulates the keyed Feistel order itself (before it
+    perm_row0: int = 0                   # waits for the broadcast); epoch e = row perm_row0 + e of device_permutation(n, *, perm_seed)
+    perm_scratch: Optional[torch.Tensor] = None   # int32 [epochs of the fit * n] device scratch for that table (required with perm_seed)
     _keep: list = field(default_factory=list, repr=False)
 
     def pack(self) -> bytes:
         ext = _ext.require()
         n = int(self.x.shape[0])
+        if self.perm is None and self.perm_seed:
+            assert self.perm_scratch is not None and self.perm_scratch.dtype == torch.int32 and self.perm_scratch.numel() >= n, \
+                "perm_seed needs an int32 perm_scratch of >= epochs * n elements on the kernel's device"
         y_dim = int(self.y.shape[1]) if self.y.dim() == 2 else 1
         rows = int(self.perm.shape[0]) if self.perm is not None else 1
         return ext.make_client_desc(_ptr(self.x), _ptr(self.y), _ptr(self.perm), _ptr(self.theta_in),
                                     _ptr(self.theta_out), _ptr(self.loss_out), _ptr(self.wait_flag),
                                     int(self.wait_value), _ptr(self.signal_flag), int(self.signal_value),
                                     n, rows, y_dim, float(self.out_scale), int(bool(self.delta_mode)),
-                                    int(self.perm_seed) if self.perm is None else 0, int(self.perm_row0))
+                                    int(self.perm_seed) if self.perm is None else 0, int(self.perm_row0), _ptr(self.perm_scratch))
 
 
 def build_client_descs(tasks: Sequence[ClientTask], device) -> torch.Tensor:

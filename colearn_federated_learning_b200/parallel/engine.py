@@ -341,21 +341,27 @@ class FederatedEngine:
         else:
             cap = kPlanRounds if rounds == 1 else rounds
             stride = 2 if rounds == 1 else 1
-            # sample order: the worker kernel's gather computes the keyed Feistel index of every sample it prefetches
-            # (ClientDesc::perm_seed / perm_row0), so a round's shuffle costs no launch, no table and is inside whatever
-            # region times the round; round i, epoch e uses row (rounds_done + i) * epochs + e of the rank's / client's key
+            # sample order: the worker kernel tabulates the keyed Feistel permutation of its epochs itself, before it waits for
+            # the round's broadcast (ClientDesc::perm_seed / perm_row0 / perm_scratch) — a round's shuffle costs no launch and is
+            # inside whatever region times the round; round i, epoch e uses row (rounds_done + i) * epochs + e of the client's key
             pseed = ((self.seed * 1000003 + 17 * r + 1) & 0x7FFFFFFFFFFF) | 1 if cfg.shuffle else 0
             tasks = []
             if C > 1:
                 from ..data import shard_bounds
                 cb = [b for b in shard_bounds(n, C)]
+            # scratch of the kernel-made permutation tables: [epochs, n_client] ints per client, reused every round
+            sizes_c = [n] if C == 1 else [hi - lo for lo, hi in cb]
+            key_s = (tuple(sizes_c), cfg.epochs)
+            if pseed and getattr(self, "_perm_scratch_key", None) != key_s:
+                self._perm_scratch = [torch.empty(max(1, cfg.epochs * max(1, m)), dtype=torch.int32, device=dev) for m in sizes_c]
+                self._perm_scratch_key = key_s
             for i in range(cap):
                 w = self._round_weights(masks[i] if rounds > 1 else masks[0])[r]
                 row0 = (self.rounds_done + i) * cfg.epochs
                 ev = e0 + stride * i + 1
                 if C == 1:
                     tasks.append(ops.ClientTask(x=self.x, y=self.y, theta_in=arena.ptr("inbox"), theta_out=coord_slots,
-                                                perm_seed=pseed, perm_row0=row0,
+                                                perm_seed=pseed, perm_row0=row0, perm_scratch=self._perm_scratch[0] if pseed else None,
                                                 loss_out=coord_loss, wait_flag=arena.ptr("flags"), wait_value=ev,
                                                 signal_flag=coord_arrive, signal_value=ev, out_scale=w))
                 else:
@@ -366,6 +372,7 @@ class FederatedEngine:
                         tasks.append(ops.ClientTask(x=self.x[lo:hi], y=self.y[lo:hi], theta_in=arena.ptr("inbox"),
                                                     theta_out=self.client_slots[c],
                                                     perm_seed=(pseed + 2 * 7919 * (c + 1)) if pseed else 0, perm_row0=row0,
+                                                    perm_scratch=self._perm_scratch[c] if pseed else None,
                                                     loss_out=self.client_losses[c],
                                                     wait_flag=arena.ptr("flags"), wait_value=ev, out_scale=w * share))
             descs = ops.build_client_descs(tasks, dev)
@@ -406,11 +413,13 @@ class FederatedEngine:
                                inbox_ptrs, bflag_ptrs, bcast_epoch, 0, mask_reduce, self.server_lr, P4, True, False,
                                self.grid_counter.data_ptr(), n_blocks, self.round_deadline_ms, wts, self.decision.data_ptr())
                 ext.star_round(self.theta.data_ptr(), arena.ptr("slots"), P4, arena.ptr("flags", None, 1), arrive_epoch,
-                               inbox_ptrs, bflag_ptrs, bcast_epoch, arena.mc_ptr("inbox") if mask_bcast == (1 << W) - 1 else 0,
+                               inbox_ptrs, bflag_ptrs, bcast_epoch, arena.mc_ptr("inbox"),
                                mask_bcast, self.server_lr, P4, False, True, self.grid_counter.data_ptr(), n_blocks, 0.0, wts, 0)
                 return 2
             mask = mask_reduce if do_reduce else mask_bcast
-            mc = arena.mc_ptr("inbox") if (do_bcast and mask == (1 << W) - 1) else 0
+            # NVLS broadcast also for a subset: multimem.st lands in every rank's inbox (one egress copy, the switch replicates);
+            # only the selected ranks get their flag raised, the others never look at theirs
+            mc = arena.mc_ptr("inbox") if do_bcast else 0
             ext.star_round(self.theta.data_ptr(), arena.ptr("slots"), P4, arena.ptr("flags", None, 1), arrive_epoch,
                            inbox_ptrs, bflag_ptrs, bcast_epoch, mc, mask, self.server_lr, P4, do_reduce, do_bcast,
                            self.grid_counter.data_ptr(), n_blocks, self.round_deadline_ms if do_reduce else 0.0, wts,
@@ -609,19 +618,27 @@ class FederatedEngine:
                 self.theta_prev.copy_(arena.tensor("work"))
             need_wait = read_back or i == rounds - 1   # otherwise the next round's consumer polls the flags
             sel_w = [w for k, w in enumerate(wts) if (masks[i] >> k) & 1]
-            nvls = (self.use_nvls and arena.has_multicast and masks[i] == (1 << W) - 1 and W > 1
-                    and max(sel_w) - min(sel_w) < 1e-7 and not use_prev)
+            full = (1 << W) - 1
+            # NVLS (multimem.ld_reduce sums every member of the multicast group with equal weight inside the switch):
+            #   uniform weights over all ranks   -> reduce as is, scale the sum by 1/W in the kernel
+            #   n_k weights and / or a subset    -> every rank first scales its own arena by its weight (0 when it was not
+            #                                       selected: it presents zeros), the kernel sums with weight 1 over ALL ranks
+            nvls = self.use_nvls and arena.has_multicast and W > 1 and not use_prev and bool(sel_w)
+            prescale = nvls and (masks[i] != full or max(sel_w) - min(sel_w) >= 1e-7)
+            if prescale:
+                self.weights_dev[:W].fill_(1.0)
 
             def twoshot(blocks: int, produced_ptr: int):
                 ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
-                                   self.theta_prev.data_ptr() if use_prev else 0, e, masks[i], self.server_lr, P4, self.chunk_elems, r, blocks,
+                                   self.theta_prev.data_ptr() if use_prev else 0, e, full if prescale else masks[i], self.server_lr, P4,
+                                   self.chunk_elems, r, blocks,
                                    arrive_ptrs if not produced_ptr else [], need_wait,
                                    arena.mc_ptr("work") if nvls else 0,
                                    arena.mc_ptr("shadow") if (nvls and self.bf16_shadow) else 0,
                                    produced_ptr, self.overlap_timeout_s if produced_ptr else 0.0)
 
             # fused wgrad -> FedAvg reduce: every rank trains this round, so every rank's last backward reports its chunks
-            prod = self._produced_spec() if masks[i] == (1 << W) - 1 else None
+            prod = self._produced_spec() if (masks[i] == full and not prescale) else None
             launched = [False]
 
             def overlapped():
@@ -644,6 +661,9 @@ class FederatedEngine:
                 torch.cuda.current_stream(dev).wait_stream(self.comm_stream)
             else:
                 with self._phase("twoshot_reduce_apply_bcast"):
+                    if prescale:
+                        ext.scale_inplace(arena.ptr("work"), P4, float(wts[r]))
+                        launches += 1
                     twoshot(n_blocks, 0)
             self._last_nvls = bool(nvls)
             launches += 1

@@ -89,7 +89,10 @@ def main():
         rec = {"P": P, "bytes": 4 * P4, "world": world, "provider": arena.provider, "multicast": arena.has_multicast,
                "twoshot_ms": ms, "twoshot_busbw_GBps": bus / ms / 1e6 if world > 1 else None,
                "nccl_allreduce_ms": ms_nccl, "nccl_busbw_GBps": bus / ms_nccl / 1e6 if world > 1 else None,
-               "shadow_bf16": args.shadow, "chunk_elems": chunk, "nvls": use_nvls, "blocks": n_blocks, "tag": args.tag}
+               "shadow_bf16": args.shadow, "chunk_elems": chunk, "nvls": use_nvls, "blocks": n_blocks, "tag": args.tag,
+               # fraction of NVLink 5's 900 GB/s per direction (BASELINE.json); busbw is directly comparable with it
+               "twoshot_frac_of_900GBps": (bus / ms / 1e6 / 900.0) if world > 1 else None,
+               "nccl_frac_of_900GBps": (bus / ms_nccl / 1e6 / 900.0) if world > 1 else None}
         results.append(rec)
         if rank == 0:
             print(json.dumps(rec), flush=True)

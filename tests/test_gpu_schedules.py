@@ -390,30 +390,43 @@ def test_programmatic_dependent_launch_is_bit_identical(flags):
 
 
 # ---- fused wgrad GEMM -> FedAvg reduce (COLEARN_OVERLAP_REDUCE=1 / overlap_reduce=True); tests/test_overlap_reduce.py has the CPU evidence ----
+_OVERLAP_SCRIPT = """
+import torch
+from colearn_federated_learning_b200.data import synthetic_unsw
+from colearn_federated_learning_b200.parallel import FederatedEngine
+dev = torch.device('cuda:0')
+flats, paths = [], []
+for overlap in (False, True):
+    eng = FederatedEngine('wide_mlp', backend='fused', device=dev, batch_size=128, lr=0.05, seed=6, chunk_elems=4096,
+                          bf16_shadow=True, model_kwargs={'width': 512, 'depth': 3}, overlap_reduce=overlap)
+    xs, ys = synthetic_unsw(384, seed=20)
+    eng.set_local_data(xs, ys)
+    rep = eng.run_rounds(3)
+    torch.cuda.synchronize()
+    flats.append(eng.global_flat().clone())
+    paths.append(rep.extra['train_path'])
+    assert torch.equal(eng.arena.tensor('shadow')[: eng.P], flats[-1].to(torch.bfloat16))
+    if overlap:
+        assert bool((eng.prod_count == 0).all())
+        assert int(eng.arena.tensor('produced')[: eng.n_chunks].min()) == eng.epoch
+assert paths[1].endswith('+overlap_reduce') and not paths[0].endswith('+overlap_reduce'), paths
+assert torch.isfinite(flats[1]).all() and torch.equal(flats[0], flats[1])
+print('OVERLAP_OK')
+"""
+
+
 @pytest.mark.parametrize("graphs", ["1", "0"])
-def test_overlapped_reduce_single_gpu_is_bit_identical(graphs, monkeypatch):
+def test_overlapped_reduce_single_gpu_is_bit_identical(graphs):
     """World 1: the two-shot kernel on the side stream owns every chunk and takes them as the last backward's wgrad
-    epilogues (grid capped to leave it its SMs) report them.  Same kernels and order of additions as the serial round."""
-    from colearn_federated_learning_b200.data import synthetic_unsw
-    from colearn_federated_learning_b200.parallel import FederatedEngine
-    dev = _dev()
-    monkeypatch.setenv("COLEARN_CUDA_GRAPHS", graphs)
-    flats, paths = [], []
-    for overlap in (False, True):
-        eng = FederatedEngine("wide_mlp", backend="fused", device=dev, batch_size=128, lr=0.05, seed=6, chunk_elems=4096,
-                              bf16_shadow=True, model_kwargs={"width": 512, "depth": 3}, overlap_reduce=overlap)
-        xs, ys = synthetic_unsw(384, seed=20)
-        eng.set_local_data(xs, ys)
-        rep = eng.run_rounds(3)
-        torch.cuda.synchronize()
-        flats.append(eng.global_flat().clone())
-        paths.append(rep.extra["train_path"])
-        assert torch.equal(eng.arena.tensor("shadow")[: eng.P], flats[-1].to(torch.bfloat16))
-        if overlap:
-            assert bool((eng.prod_count == 0).all())
-            assert int(eng.arena.tensor("produced")[: eng.n_chunks].min()) == eng.epoch
-    assert paths[1].endswith("+overlap_reduce") and not paths[0].endswith("+overlap_reduce"), paths
-    assert torch.isfinite(flats[1]).all() and torch.equal(flats[0], flats[1])
+    epilogues (grid capped to leave it its SMs) report them.  Same kernels and order of additions as the serial round.
+    (Own process: if a chunk is never reported the kernel's watchdog traps, which kills the CUDA context.)"""
+    import subprocess
+    import sys
+    _dev()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, COLEARN_CUDA_GRAPHS=graphs, COLEARN_OVERLAP_TIMEOUT_S="5")
+    out = subprocess.run([sys.executable, "-c", _OVERLAP_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "OVERLAP_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-2500:])
 
 
 def test_layerwise_trainer_dgrad_against_weights_in_place_on_device():

@@ -96,13 +96,20 @@ def test_engine_twoshot_single_gpu_resnet_round():
     from colearn_federated_learning_b200.data import synthetic_images
     from colearn_federated_learning_b200.parallel import FederatedEngine
     dev = torch.device("cuda", 0)
-    eng = FederatedEngine("resnet18", backend="fused", device=dev, batch_size=32, lr=0.05, seed=1)
-    x, y = synthetic_images(64, seed=0)
+    eng = FederatedEngine("resnet18", backend="fused", device=dev, batch_size=128, lr=0.05, seed=1)
+    x, y = synthetic_images(256, seed=0)
     eng.set_local_data(x, y.float().view(-1, 1))
     t0 = eng.global_flat().clone()
     rep = eng.run_rounds(2)
     assert rep.algo == "twoshot" and torch.isfinite(eng.global_flat()).all() and not torch.equal(eng.global_flat(), t0)
+    assert rep.extra["train_path"] == "convnet"                  # this repo's conv / BatchNorm kernels + tcgen05 GEMMs, not cuDNN
     assert float(rep.losses[1, 0, 0]) < float(rep.losses[0, 0, 0]) * 1.5
+    # a shape the conv kernels do not cover raises instead of switching to cuDNN (fl/trainer.py: _library_path_guard)
+    eng32 = FederatedEngine("resnet18", backend="fused", device=dev, batch_size=32, lr=0.05, seed=1)
+    eng32.set_local_data(x[:64], y[:64].float().view(-1, 1))
+    import pytest as _pytest
+    with _pytest.raises(RuntimeError, match="no sm_100a kernel path"):
+        eng32.run_rounds(1)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -160,6 +167,34 @@ def _rank_main(rank, world, port, out_path, case):
             if rank == 0:
                 torch.save({"same": same, "shadow_ok": bool(shadow_ok), "moved": not torch.equal(flat, theta0),
                             "finite": bool(torch.isfinite(flat).all()), "n_chunks": rep.extra["n_chunks"]}, out_path)
+        elif case == "twoshot_nvls_weighted":
+            # n_k-weighted and subset rounds on the NVLS path (every rank pre-scales its arena by its weight, 0 when it was not
+            # selected, then the switch sums all members) against the P2P path of the same rounds
+            sizes2 = [256, 128, 384, 128, 256, 128, 384, 128][:world]
+            xs, ys = synthetic_unsw(sizes2[rank], seed=30 + rank)
+            masks = [(1 << world) - 1, (0b01 if world == 2 else 0b0110), (1 << world) - 1]
+            outs, nvls_flags = [], []
+            for use in ("1", "0"):
+                os.environ["COLEARN_NVLS"] = use
+                eng = FederatedEngine("wide_mlp", backend="fused", device=dev, batch_size=128, lr=0.05, seed=9, chunk_elems=4096,
+                                      bf16_shadow=True, weighted=True, model_kwargs={"width": 256, "depth": 3})
+                eng.set_local_data(xs, ys)
+                per_round = []
+                for m in masks:
+                    rep = eng.run_rounds(1, masks=m)
+                    per_round.append(bool(rep.extra["nvls"]))
+                torch.cuda.synchronize()
+                outs.append(eng.global_flat().clone())
+                nvls_flags.append(per_round)
+                multicast = eng.arena.has_multicast
+            os.environ.pop("COLEARN_NVLS", None)
+            allf = [torch.zeros_like(outs[0]) for _ in range(world)]
+            dist.all_gather(allf, outs[0])
+            if rank == 0:
+                scale = float(outs[1].abs().max())
+                torch.save({"err": float((outs[0] - outs[1]).abs().max()) / scale, "same": all(torch.equal(allf[0], f) for f in allf),
+                            "nvls_rounds": nvls_flags[0], "p2p_rounds": nvls_flags[1], "multicast": bool(multicast),
+                            "finite": bool(torch.isfinite(outs[0]).all())}, out_path)
         elif case == "twoshot_kernel":
             # direct numerics of twoshot_fedavg_kernel: P2P path (non-uniform weights, subset mask) and NVLS path
             from colearn_federated_learning_b200.parallel.symm import SymmetricArena
@@ -270,7 +305,7 @@ def _rank_main(rank, world, port, out_path, case):
 
 
 @pytest.mark.multigpu
-@pytest.mark.parametrize("case", ["star", "twoshot", "twoshot_kernel", "wide", "deadline", "wide_overlap"])
+@pytest.mark.parametrize("case", ["star", "twoshot", "twoshot_kernel", "twoshot_nvls_weighted", "wide", "deadline", "wide_overlap"])
 def test_fused_collectives_multi_rank(tmp_path, case):
     if case == "wide_overlap" and os.environ.get("COLEARN_RUN_UNVALIDATED") != "1":
         pytest.skip("opt-in path not yet measured on a B200 (set COLEARN_RUN_UNVALIDATED=1)")
@@ -291,6 +326,11 @@ def test_fused_collectives_multi_rank(tmp_path, case):
     elif case == "wide_overlap":
         assert res["same"] and res["identical"] and res["shadow_ok"] and res["idle"] and res["finite"], res
         assert res["paths"][1].endswith("+overlap_reduce") and not res["paths"][0].endswith("+overlap_reduce"), res
+    elif case == "twoshot_nvls_weighted":
+        assert res["same"] and res["finite"] and res["err"] < 2e-3, res         # bf16 shadows + switch-defined reduction order
+        assert res["p2p_rounds"] == [False, False, False], res
+        if res["multicast"]:
+            assert res["nvls_rounds"] == [True, True, True], res                 # weighted AND subset rounds take the in-switch reduce
     elif case == "twoshot":
         assert res["same"] and res["shadow_ok"] and res["moved"] and res["finite"], res
     else:
