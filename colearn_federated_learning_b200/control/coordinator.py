@@ -432,6 +432,7 @@ class Coordinator(BusClient):
                 th = theta.to(self.device)
                 ops.fedavg_apply(th, stacked, w, self.args.server_lr)
                 theta = th.cpu()
+                self._average_buffers(model, [getattr(alive.get(wid), "last_buffers", None) for wid in ids], w.cpu())
             # traffic of this round: model + fit config towards the devices, trained model + loss back (paper §4.3)
             self.metrics.end_round(r, time.time() - t0, selected=ids, n_k=counts, bytes_out=bytes_out, bytes_in=bytes_in)
             result["bytes_out"] = result.get("bytes_out", 0) + bytes_out
@@ -440,6 +441,22 @@ class Coordinator(BusClient):
             if not alive:
                 break
         return theta
+
+    @staticmethod
+    def _average_buffers(model, buffers, weights) -> None:
+        """BatchNorm models in remote mode: the devices return their running statistics next to the parameters; the global
+        model gets their FedAvg-weighted mean (PySyft's federated_avg averages parameters only — with it the reference could
+        not train a BatchNorm model remotely at all; documented in docs/PARITY.md)."""
+        mine = [b for b in model.buffers() if b.is_floating_point()]
+        total = sum(b.numel() for b in mine)
+        if not mine or any(b is None or b.numel() != total or not bool(torch.isfinite(b).all()) for b in buffers):
+            return
+        avg = (torch.stack([b.float() for b in buffers]) * weights.view(-1, 1).float()).sum(0)
+        off = 0
+        with torch.no_grad():
+            for b in mine:
+                b.copy_(avg[off:off + b.numel()].view_as(b).to(b.device))
+                off += b.numel()
 
     # ------------------------------------------------------------------ inference (remote only)
     def _inference(self, worker: RemoteWorkerClient) -> None:

@@ -193,7 +193,14 @@ class WorkerServer:
                     loss, path = local_fit(flat, model, x, y, cfg, round_idx=self._round)
                 self._round += 1
                 self.fits_served += 1
-                return {"ok": True, "params": _to_bytes(flat), "loss": float(loss), "n": int(x.shape[0]), "path": path}
+                reply = {"ok": True, "params": _to_bytes(flat), "loss": float(loss), "n": int(x.shape[0]), "path": path}
+                # floating-point buffers the fit updated on this device (BatchNorm running statistics): the flat arena holds
+                # named_parameters only, so without them the coordinator would save trained weights next to the INITIAL running
+                # stats and every eval-mode use of the checkpoint would be meaningless (FFNN / MLPs have none: nothing is sent)
+                bufs = [b.detach().reshape(-1).float() for b in model.buffers() if b.is_floating_point()]
+                if bufs:
+                    reply["buffers"] = _to_bytes(torch.cat(bufs))
+                return reply
         if op == "predict":
             data = self.tagged.get(req.get("tag", "inference"), [])
             if not data:
@@ -283,6 +290,7 @@ class RemoteWorkerClient:
         """Broadcast leg + remote local-SGD + gather leg (cf.py:209-211) in one RPC."""
         resp = self._call({"op": "fit", "config": cfg.to_dict(), "params": _to_bytes(flat),
                            "dataset_key": dataset_key}, timeout=timeout)
+        self.last_buffers = _from_bytes(resp["buffers"]) if resp.get("buffers") else None     # BatchNorm statistics, if any
         return _from_bytes(resp["params"]), float(resp["loss"]), int(resp["n"])
 
     def search(self, tag: str) -> int:

@@ -449,3 +449,39 @@ def test_small_model_sections_run_with_one_intra_op_thread():
     except RuntimeError:
         pass
     assert torch.get_num_threads() == before
+
+
+def test_remote_mode_returns_and_averages_batchnorm_statistics(tmp_path):
+    """The flat arena carries parameters only; a device's BatchNorm running statistics come back next to them and the
+    saved global model holds their FedAvg mean instead of the initial (0, 1) statistics."""
+    from torch import nn
+    from colearn_federated_learning_b200.models import register_model
+
+    class BnToy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.bn, self.fc2 = nn.Linear(10, 8), nn.BatchNorm1d(8), nn.Linear(8, 2)
+
+        def forward(self, x):
+            return self.fc2(torch.relu(self.bn(self.fc1(x))))
+
+    register_model("bn_toy", BnToy, default_loss="xent", overwrite=True)
+    w1, p1 = _worker(seed=1)
+    w2, p2 = _worker(seed=2)
+    try:
+        a = Arguments(lr=0.05)
+        a.model, a.batch_size = "bn_toy", 16
+        c, pub, clock = make(tmp_path, remote=True, rounds=2, args=a)
+        pub.publish(TOPIC, f"(127.0.0.1, {p1}, TRAINING)")
+        pub.publish(TOPIC, f"(127.0.0.1, {p2}, TRAINING)")
+        c.drain()
+        clock.advance(1.0)
+        res = c.windower.last_result
+        assert res["dropped"] == [] and len(res["losses"]) == 2
+        state = torch.load(c.path, weights_only=True)
+        assert float(state["bn.running_mean"].abs().max()) > 0 and not torch.allclose(state["bn.running_var"], torch.ones(8))
+        devs = [w._models["bn_toy"][0].state_dict() for w in (w1, w2)]
+        want = (devs[0]["bn.running_mean"] + devs[1]["bn.running_mean"]) / 2          # equal shards -> equal weights
+        assert torch.allclose(state["bn.running_mean"], want.cpu(), atol=1e-6)
+    finally:
+        w1.stop(); w2.stop()

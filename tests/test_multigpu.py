@@ -307,8 +307,6 @@ def _rank_main(rank, world, port, out_path, case):
 @pytest.mark.multigpu
 @pytest.mark.parametrize("case", ["star", "twoshot", "twoshot_kernel", "twoshot_nvls_weighted", "wide", "deadline", "wide_overlap"])
 def test_fused_collectives_multi_rank(tmp_path, case):
-    if case == "wide_overlap" and os.environ.get("COLEARN_RUN_UNVALIDATED") != "1":
-        pytest.skip("opt-in path not yet measured on a B200 (set COLEARN_RUN_UNVALIDATED=1)")
     world = min(torch.cuda.device_count(), 8)
     out = str(tmp_path / "out.pt")
     mp.spawn(_rank_main, args=(world, _free_port(), out, case), nprocs=world, join=True)
