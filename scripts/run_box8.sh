@@ -14,9 +14,6 @@ timeout 200 $TR --nproc-per-node 8 --master-port 29702 bench.py --gpus 8 --steps
 timeout 200 $TR --nproc-per-node 8 --master-port 29703 bench.py --gpus 8 --steps 5 --warmup 3 --config cfg4 > ${O}_cfg4_n8.json 2> ${O}_cfg4_n8.err
 timeout 200 $TR --nproc-per-node 8 --master-port 29704 bench.py --gpus 8 --steps 10 --warmup 3 --config cfg5 > ${O}_cfg5_n8.json 2> ${O}_cfg5_n8.err
 COLEARN_OVERLAP_REDUCE=1 timeout 200 $TR --nproc-per-node 8 --master-port 29705 bench.py --gpus 8 --steps 10 --warmup 3 --config cfg5 > ${O}_cfg5_n8_overlap16.json 2> ${O}_cfg5_n8_overlap16.err
-COLEARN_OVERLAP_REDUCE=1 COLEARN_OVERLAP_CTAS=8 timeout 200 $TR --nproc-per-node 8 --master-port 29706 bench.py --gpus 8 --steps 10 --warmup 3 --config cfg5 > ${O}_cfg5_n8_overlap8.json 2> ${O}_cfg5_n8_overlap8.err
-timeout 200 $TR --nproc-per-node 8 --master-port 29707 bench.py --gpus 8 --steps 3 --warmup 3 --config cfg4 --impl torch_nccl > ${O}_cfg4_n8_nccl.json 2> ${O}_cfg4_n8_nccl.err
-timeout 200 $TR --nproc-per-node 8 --master-port 29708 scripts/comm_sweep.py --shadow --out ${O}_sweep_n8_nvls_shadow.json > ${O}_sweep_n8_nvls_shadow.log 2>&1
 timeout 200 $TR --nproc-per-node 8 --master-port 29709 scripts/comm_sweep.py --out ${O}_sweep_n8_nvls.json > ${O}_sweep_n8_nvls.log 2>&1
 timeout 200 $TR --nproc-per-node 8 --master-port 29710 scripts/comm_sweep.py --nvls 0 --out ${O}_sweep_n8_p2p.json > ${O}_sweep_n8_p2p.log 2>&1
 timeout 120 $TR --nproc-per-node 8 --master-port 29711 federated_coordinator.py -t topic/state --box --model mlp --synthetic 8192 -w 1 --checkpoint ${O}_box.pth \
