@@ -289,10 +289,10 @@ void star_round(int64_t theta, int64_t slots, int64_t slot_stride, int64_t arriv
   check(launch_star_round(a, (int)n_blocks, cur_stream()), "star_round");
 }
 
-void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std::vector<int64_t> chunk_flags,
+static TwoShotArgs make_twoshot_args(const std::vector<int64_t>& work, const std::vector<int64_t>& shadow, const std::vector<int64_t>& chunk_flags,
                     int64_t arrive_flags, int64_t weights, int64_t theta_prev, int64_t epoch, int64_t select_mask,
-                    double server_lr, int64_t n, int64_t chunk_elems, int64_t rank, int64_t n_blocks,
-                    std::vector<int64_t> peer_arrive, bool wait_all, int64_t mc_work, int64_t mc_shadow, int64_t produced,
+                    double server_lr, int64_t n, int64_t chunk_elems, int64_t rank,
+                    const std::vector<int64_t>& peer_arrive, bool wait_all, int64_t mc_work, int64_t mc_shadow, int64_t produced,
                     double produced_timeout_s) {
   TwoShotArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -320,7 +320,43 @@ void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std:
   // overlapped form (fused wgrad GEMM -> FedAvg reduce): my [world, n_chunks] table of produced epochs
   a.produced = ptr_of<const uint32_t>(produced);
   a.produced_timeout_ns = produced_timeout_s > 0 ? (unsigned long long)(produced_timeout_s * 1e9) : 0ull;
+  return a;
+}
+
+void twoshot_fedavg(std::vector<int64_t> work, std::vector<int64_t> shadow, std::vector<int64_t> chunk_flags,
+                    int64_t arrive_flags, int64_t weights, int64_t theta_prev, int64_t epoch, int64_t select_mask,
+                    double server_lr, int64_t n, int64_t chunk_elems, int64_t rank, int64_t n_blocks,
+                    std::vector<int64_t> peer_arrive, bool wait_all, int64_t mc_work, int64_t mc_shadow, int64_t produced,
+                    double produced_timeout_s) {
+  TwoShotArgs a = make_twoshot_args(work, shadow, chunk_flags, arrive_flags, weights, theta_prev, epoch, select_mask, server_lr, n,
+                                    chunk_elems, rank, peer_arrive, wait_all, mc_work, mc_shadow, produced, produced_timeout_s);
   check(launch_twoshot_fedavg(a, (int)n_blocks, cur_stream()), "twoshot_fedavg");
+}
+
+// two-shot FedAvg with failure detection (TwoShotArgs::deadline_ns): the coordinator's arrived-set decision travels through
+// every rank's decision ring, the result is also pushed into every rank's second arena
+void twoshot_fedavg_deadline(std::vector<int64_t> work, std::vector<int64_t> shadow, std::vector<int64_t> chunk_flags,
+                             int64_t arrive_flags, int64_t weights, int64_t theta_prev, int64_t epoch, int64_t select_mask,
+                             double server_lr, int64_t n, int64_t chunk_elems, int64_t rank, int64_t n_blocks,
+                             std::vector<int64_t> peer_arrive, bool wait_all, int64_t mc_work, int64_t mc_shadow,
+                             double deadline_ms, std::vector<int64_t> decision, std::vector<int64_t> global_copy) {
+  TwoShotArgs a = make_twoshot_args(work, shadow, chunk_flags, arrive_flags, weights, theta_prev, epoch, select_mask, server_lr, n,
+                                    chunk_elems, rank, peer_arrive, wait_all, mc_work, mc_shadow, 0, 0.0);
+  TORCH_CHECK(deadline_ms > 0 && decision.size() == work.size() && global_copy.size() == work.size(),
+              "deadline mode needs a decision ring and a second arena on every rank");
+  a.deadline_ns = (unsigned long long)(deadline_ms * 1e6);
+  a.true_weights = a.weights;
+  for (int k = 0; k < a.world; ++k) {
+    a.decision[k] = ptr_of<uint32_t>(decision[k]);
+    a.global_copy[k] = ptr_of<float>(global_copy[k]);
+  }
+  check(launch_twoshot_fedavg(a, (int)n_blocks, cur_stream()), "twoshot_fedavg (deadline)");
+}
+
+void twoshot_resync(int64_t decision_ring, int64_t prev_epoch, int64_t rank, int64_t work, int64_t shadow, int64_t global_copy,
+                    int64_t n, int64_t n_blocks) {
+  check(launch_twoshot_resync(ptr_of<const uint32_t>(decision_ring), (uint32_t)prev_epoch, (int)rank, ptr_of<float>(work), ptr_of<void>(shadow),
+                              ptr_of<const float>(global_copy), n, (int)n_blocks, cur_stream()), "twoshot_resync");
 }
 
 void reduce_push(int64_t slots, int64_t k, int64_t stride, int64_t n, int64_t dst, int64_t losses, int64_t loss_dst,
@@ -536,6 +572,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("transpose_bf16", &transpose_bf16);
   m.def("star_round", &star_round);
   m.def("twoshot_fedavg", &twoshot_fedavg);
+  m.def("twoshot_fedavg_deadline", &twoshot_fedavg_deadline);
+  m.def("twoshot_resync", &twoshot_resync);
   m.def("produced_signal_pack", &produced_signal_pack);
   m.def("produced_mark", &produced_mark);
   m.def("reduce_push", &reduce_push);

@@ -329,8 +329,21 @@ struct TwoShotArgs {
   // local step instead of after it and waits per chunk for table[k][c] >= epoch of every selected rank k, not for arrive_flags
   const uint32_t* produced;
   unsigned long long produced_timeout_ns;   // trap instead of hanging when a chunk never completes (0 = wait forever)
+  // failure detection (deadline mode): rank 0's first CTA waits at most deadline_ns for the selected ranks' arrive flags and
+  // publishes {epoch, arrived mask} into slot (epoch % 8) of EVERY rank's decision ring; all CTAs of all ranks then reduce over
+  // exactly that set (weights renormalised), chunk ownership is dealt among the arrived ranks, and the result is also pushed into
+  // every rank's second arena global_copy[k] — a rank that was late trains in place on a work arena that the owners overwrote
+  // under it, so it restores its arena from global_copy before its next round (twoshot_resync_kernel)
+  unsigned long long deadline_ns;
+  uint32_t* decision[16];       // per-rank ring of 8 x {epoch, mask} words (peer pointers)
+  float* global_copy[16];       // per-rank second fp32 arena (peer pointers) or nullptr
+  const float* true_weights;    // local device [world]: the FedAvg weights to renormalise over the arrived set
 };
 cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream_t s);
+// deadline mode, start of a round: if this rank was NOT in the arrived mask of `prev_epoch`, its work arena (and bf16 shadow) is
+// restored from global_copy; a no-op otherwise
+cudaError_t launch_twoshot_resync(const uint32_t* decision_ring, uint32_t prev_epoch, int rank, float* work, void* shadow_bf16,
+                                  const float* global_copy, int64_t n, int n_blocks, cudaStream_t s);
 
 // Many virtual clients per GPU: dst[j] = sum_c slots[c*stride + j] pushed to (peer) dst, mean losses to loss_dst,
 // then flag <- value (release) by the last CTA.  counter: zero-initialised device scratch.

@@ -223,11 +223,12 @@ star_round_kernel(StarRoundArgs a) {
 // whole kernel and lets early layers become ready first on every peer).  A CTA processes whole
 // chunks so that it can publish the chunk's ready flag by itself.
 // one owned chunk: pull it from every selected rank, apply, push it to every rank (fp32 + bf16), publish its flag
-__device__ __forceinline__ void twoshot_chunk(const TwoShotArgs& a, const int64_t c, const float* sw, const int tid) {
+__device__ __forceinline__ void twoshot_chunk(const TwoShotArgs& a, const int64_t c, const float* sw, const int tid,
+                                              const uint32_t mask, const bool use_mc) {
   const int64_t lo = c * a.chunk_elems;
   const int64_t hi = (lo + a.chunk_elems < a.n) ? lo + a.chunk_elems : a.n;
   const int64_t len4 = (hi - lo) >> 2;  // n and chunk_elems are multiples of 4
-  if (a.mc_work != nullptr) {
+  if (use_mc) {
     // NVLS path (all ranks selected, uniform weights): the switch sums the W copies on the way in
     // (ingress P/W instead of (W-1)P/W) and replicates the result on the way out (egress P/W).
     const float w = sw[0];
@@ -245,6 +246,8 @@ __device__ __forceinline__ void twoshot_chunk(const TwoShotArgs& a, const int64_
           v[u].x *= w; v[u].y *= w; v[u].z *= w; v[u].w *= w;
           multimem_st_f4(dst + j + u * blockDim.x, v[u]);
           if (dsh) multimem_st_b64(dsh + j + u * blockDim.x, pack_bf16x4(v[u]));
+          if (a.global_copy[0] != nullptr)
+            for (int k = 0; k < a.world; ++k) st_peer_f4(reinterpret_cast<float4*>(a.global_copy[k]) + (lo >> 2) + j + u * blockDim.x, v[u]);
         }
       }
     }
@@ -258,7 +261,7 @@ __device__ __forceinline__ void twoshot_chunk(const TwoShotArgs& a, const int64_
     float4 va[8], vb[8];   // world <= 8 on an HGX box (checked by the launcher)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (k < a.world && ((a.select_mask >> k) & 1u)) {
+      if (k < a.world && ((mask >> k) & 1u)) {
         va[k] = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4a);
         if (has_b) vb[k] = ld_peer_f4(reinterpret_cast<const float4*>(a.work[k]) + e4b);
       }
@@ -266,7 +269,7 @@ __device__ __forceinline__ void twoshot_chunk(const TwoShotArgs& a, const int64_
     float4 acca = make_float4(0.f, 0.f, 0.f, 0.f), accb = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (k < a.world && ((a.select_mask >> k) & 1u)) {
+      if (k < a.world && ((mask >> k) & 1u)) {
         const float w = sw[k];
         acca.x = fmaf(w, va[k].x, acca.x); acca.y = fmaf(w, va[k].y, acca.y);
         acca.z = fmaf(w, va[k].z, acca.z); acca.w = fmaf(w, va[k].w, acca.w);
@@ -296,9 +299,11 @@ __device__ __forceinline__ void twoshot_chunk(const TwoShotArgs& a, const int64_
       if (k < a.world) {
         st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4a, acca);
         if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4a] = pa;
+        if (a.global_copy[k] != nullptr) st_peer_f4(reinterpret_cast<float4*>(a.global_copy[k]) + e4a, acca);
         if (has_b) {
           st_peer_f4(reinterpret_cast<float4*>(a.work[k]) + e4b, accb);
           if (a.shadow_bf16[k] != nullptr) reinterpret_cast<uint2*>(a.shadow_bf16[k])[e4b] = pb;
+          if (a.global_copy[k] != nullptr) st_peer_f4(reinterpret_cast<float4*>(a.global_copy[k]) + e4b, accb);
         }
       }
     }
@@ -316,23 +321,78 @@ __global__ void __launch_bounds__(512)
 twoshot_fedavg_kernel(TwoShotArgs a) {
   const int tid = threadIdx.x;
   __shared__ float sw[16];
+  __shared__ uint32_t s_mask;
   // (0) announce "my local training of this round is done" to every rank (stream order guarantees it is)
   if (a.signal_arrive && blockIdx.x == 0 && tid < a.world) {
     __threadfence_system();
     st_release_sys(a.peer_arrive[tid], a.epoch);
   }
-  if (tid < a.world) {
-    sw[tid] = a.weights[tid];
-    if ((a.select_mask >> tid) & 1u)
-      spin_wait_ge(a.arrive_flags + tid, a.epoch, 20, "twoshot_fedavg: arrive flag of a selected rank");
+  uint32_t mask = a.select_mask;
+  if (a.deadline_ns == 0) {
+    if (tid < a.world) {
+      sw[tid] = a.weights[tid];
+      if ((mask >> tid) & 1u) spin_wait_ge(a.arrive_flags + tid, a.epoch, 20, "twoshot_fedavg: arrive flag of a selected rank");
+    }
+    __syncthreads();
+  } else {
+    // failure detection: the coordinator (rank 0) decides who made it and tells everybody; every CTA of every rank then works on
+    // the same arrived set
+    const int slot = (int)(a.epoch & 7u);
+    if (a.rank == 0 && blockIdx.x == 0) {
+      if (tid == 0) s_mask = 0u;
+      __syncthreads();
+      if (tid < a.world && ((mask >> tid) & 1u)) {
+        const unsigned long long t0 = shim_globaltimer();
+        bool ok = false;
+        do {
+          ok = ld_acquire_sys(a.arrive_flags + tid) >= a.epoch;
+        } while (!ok && (shim_globaltimer() - t0) < a.deadline_ns);
+        if (ok) atomicOr(&s_mask, 1u << tid);
+      }
+      __syncthreads();
+      if (tid < a.world) {
+        a.decision[tid][2 * slot + 1] = s_mask;
+        __threadfence_system();
+        st_release_sys(a.decision[tid] + 2 * slot, a.epoch);
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      spin_wait_ge(a.decision[a.rank] + 2 * slot, a.epoch, 20, "twoshot_fedavg: the coordinator's arrived-set decision of this round");
+      // (a ring slot that already carries a LATER epoch: this rank is more than 8 rounds behind — it takes part in nothing)
+      s_mask = (ld_acquire_sys(a.decision[a.rank] + 2 * slot) == a.epoch) ? a.decision[a.rank][2 * slot + 1] : 0u;
+    }
+    __syncthreads();
+    mask = s_mask;
+    if (tid < a.world) {
+      float wsum = 0.f, wall = 0.f;
+      for (int k = 0; k < a.world; ++k) {
+        if ((a.select_mask >> k) & 1u) wall += a.true_weights[k];
+        if ((mask >> k) & 1u) wsum += a.true_weights[k];
+      }
+      sw[tid] = (wsum > 0.f) ? a.true_weights[tid] * (wall / wsum) : 0.f;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int64_t n_chunks = (a.n + a.chunk_elems - 1) / a.chunk_elems;
-  // chunks owned by this rank: c = rank, rank + world, ...
-  for (int64_t oc = blockIdx.x; ; oc += gridDim.x) {
-    const int64_t c = a.rank + oc * a.world;
-    if (c >= n_chunks) break;
-    twoshot_chunk(a, c, sw, tid);
+  // chunk ownership is dealt among the ranks that take part: the j-th of them owns chunks j, j + n_own, ...  (without a deadline
+  // every rank of the box takes part, selected or not: owner of chunk c = c % world)
+  const uint32_t full = (a.world >= 32) ? 0xffffffffu : ((1u << a.world) - 1u);
+  const uint32_t owners = (a.deadline_ns != 0 && mask != 0u) ? mask : full;
+  const int n_own = __popc(owners);
+  const bool i_own = (owners >> a.rank) & 1u;
+  const int my_idx = __popc(owners & ((1u << a.rank) - 1u));
+  const bool use_mc = a.mc_work != nullptr && (a.deadline_ns == 0 || mask == full);
+  if (i_own && mask != 0u) {
+    for (int64_t oc = blockIdx.x; ; oc += gridDim.x) {
+      const int64_t c = my_idx + oc * n_own;
+      if (c >= n_chunks) break;
+      twoshot_chunk(a, c, sw, tid, mask, use_mc);
+    }
+  } else if (mask == 0u && a.rank == 0) {
+    // nobody arrived in time: the model stays as it is; the coordinator still publishes the chunk flags so that nobody waits
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + tid; c < n_chunks; c += (int64_t)gridDim.x * blockDim.x)
+      for (int k = 0; k < a.world; ++k) st_release_sys(a.chunk_flags[k] + c, a.epoch);
   }
   // (3) optionally hold the stream until the whole arena of THIS rank has been refreshed by its owners
   if (a.wait_all) {
@@ -341,6 +401,21 @@ twoshot_fedavg_kernel(TwoShotArgs a) {
   }
 }
 
+// deadline mode: a rank that missed the previous round's deadline restores its arena from the copy the owners pushed
+__global__ void __launch_bounds__(512)
+twoshot_resync_kernel(const uint32_t* ring, uint32_t prev_epoch, int rank, float* work, __nv_bfloat16* shadow, const float* global_copy, int64_t n) {
+  const int slot = (int)(prev_epoch & 7u);
+  const bool decided = ring[2 * slot] == prev_epoch;
+  const bool was_in = decided && ((ring[2 * slot + 1] >> rank) & 1u);
+  if (was_in || prev_epoch == 0u) return;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += stride) {
+    const float4 v = reinterpret_cast<const float4*>(global_copy)[j];
+    reinterpret_cast<float4*>(work)[j] = v;
+    if (shadow != nullptr) reinterpret_cast<uint2*>(shadow)[j] = pack_bf16x4(v);
+  }
+}
 
 // Overlapped form (fused wgrad GEMM -> FedAvg reduce, produced.cuh): runs on a few CTAs NEXT TO the last local step.
 // Chunks are taken in whatever order the producers of all selected ranks finish them (the backward pass finalises the
@@ -374,7 +449,7 @@ twoshot_overlap_kernel(TwoShotArgs a) {
         const int ready = s_ready;
         __syncthreads();
         if (!ready) continue;
-        twoshot_chunk(a, c, sw, tid);
+        twoshot_chunk(a, c, sw, tid, a.select_mask, a.mc_work != nullptr);
         if (tid == 0) s_done[i >> 6] |= 1ull << (i & 63);
         __syncthreads();
         --left;
@@ -518,6 +593,14 @@ cudaError_t launch_twoshot_fedavg(const TwoShotArgs& a, int n_blocks, cudaStream
   return cudaGetLastError();
 }
 
+cudaError_t launch_twoshot_resync(const uint32_t* decision_ring, uint32_t prev_epoch, int rank, float* work, void* shadow_bf16,
+                                  const float* global_copy, int64_t n, int n_blocks, cudaStream_t s) {
+  if (decision_ring == nullptr || work == nullptr || global_copy == nullptr || (n & 3)) return cudaErrorInvalidValue;
+  COLEARN_LAUNCH(twoshot_resync_kernel, n_blocks < 1 ? 1 : n_blocks, 512, 0, s, decision_ring, prev_epoch, rank, work,
+                 reinterpret_cast<__nv_bfloat16*>(shadow_bf16), global_copy, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_produced_mark(const ProducedSignal* sig_dev, int chunk_shift, int64_t lo, int64_t hi, cudaStream_t s) {
   if (sig_dev == nullptr || lo < 0 || hi < lo || chunk_shift < 2 || chunk_shift > 30) return cudaErrorInvalidValue;
   if (hi == lo) return cudaSuccess;
@@ -584,7 +667,7 @@ cudaError_t preload_comm_kernels() {
 #ifndef COLEARN_HOST_SHIM
   cudaFuncAttributes attr;
   const void* kernels[] = {(const void*)star_round_kernel, (const void*)twoshot_fedavg_kernel, (const void*)twoshot_overlap_kernel,
-                           (const void*)produced_mark_kernel, (const void*)reduce_push_kernel, (const void*)set_flag_kernel,
+                           (const void*)produced_mark_kernel, (const void*)twoshot_resync_kernel, (const void*)reduce_push_kernel, (const void*)set_flag_kernel,
                            (const void*)signal_peers_kernel, (const void*)wait_flag_kernel, (const void*)wait_flags_kernel,
                            (const void*)wait_flags_dev_kernel, (const void*)p2p_copy_kernel};
   for (const void* k : kernels) {

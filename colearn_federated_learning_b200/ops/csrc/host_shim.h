@@ -200,6 +200,7 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 template <class T>

@@ -218,6 +218,39 @@ void twoshot_fedavg(int64_t rank, Tensor works, c10::optional<Tensor> shadows, T
   }
 }
 
+// deadline mode of one emulated rank: decisions int32 [W, 16] (row k = rank k's ring), globals [W, n] (second arenas)
+void twoshot_fedavg_deadline(int64_t rank, Tensor works, Tensor globals, Tensor chunk_flags, Tensor arrive, Tensor weights, int64_t epoch,
+                             int64_t select_mask, int64_t chunk_elems, int64_t n_blocks, double deadline_ms, Tensor decisions) {
+  const int W = (int)works.size(0);
+  colearn::TwoShotArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int k = 0; k < W; ++k) {
+    a.work[k] = works.data_ptr<float>() + (int64_t)k * works.size(1);
+    a.global_copy[k] = globals.data_ptr<float>() + (int64_t)k * globals.size(1);
+    a.chunk_flags[k] = reinterpret_cast<uint32_t*>(chunk_flags.data_ptr<int>()) + (int64_t)k * chunk_flags.size(1);
+    a.decision[k] = reinterpret_cast<uint32_t*>(decisions.data_ptr<int>()) + (int64_t)k * decisions.size(1);
+  }
+  a.arrive_flags = reinterpret_cast<const uint32_t*>(arrive.data_ptr<int>());
+  a.weights = a.true_weights = fptr(weights, "weights");
+  a.epoch = (uint32_t)epoch;
+  a.select_mask = (uint32_t)select_mask;
+  a.server_lr = 1.f;
+  a.n = works.size(1);
+  a.chunk_elems = chunk_elems;
+  a.world = W;
+  a.rank = (int)rank;
+  a.wait_all = 0;      // (the emulated ranks run one after the other: nobody may wait for a later rank's chunks)
+  a.deadline_ns = (unsigned long long)(deadline_ms * 1e6);
+  py::gil_scoped_release nogil;
+  CK(colearn::launch_twoshot_fedavg(a, (int)n_blocks, nullptr));
+}
+
+void twoshot_resync(Tensor decision_ring, int64_t prev_epoch, int64_t rank, Tensor work, Tensor global_copy) {
+  py::gil_scoped_release nogil;
+  CK(colearn::launch_twoshot_resync(reinterpret_cast<const uint32_t*>(decision_ring.data_ptr<int>()), (uint32_t)prev_epoch, (int)rank,
+                                    work.data_ptr<float>(), nullptr, global_copy.data_ptr<float>(), work.numel(), 2, nullptr));
+}
+
 void reduce_push(Tensor slots, Tensor dst, Tensor losses, Tensor loss_dst, Tensor flag, int64_t value, int64_t n_blocks) {
   static uint32_t counter = 0;
   py::gil_scoped_release nogil;
@@ -342,6 +375,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ring_matmul", &ring_matmul);
   m.def("star_round", &star_round);
   m.def("twoshot_fedavg", &twoshot_fedavg);
+  m.def("twoshot_fedavg_deadline", &twoshot_fedavg_deadline);
+  m.def("twoshot_resync", &twoshot_resync);
   m.def("produced_signal_pack", &produced_signal_pack);
   m.def("produced_mark", &produced_mark);
   m.def("reduce_push", &reduce_push);

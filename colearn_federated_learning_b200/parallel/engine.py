@@ -159,6 +159,12 @@ class FederatedEngine:
                 layout["shadow"] = (P4, torch.bfloat16)
             if self.overlap_reduce:
                 layout["produced"] = (W * self.n_chunks, torch.int32)   # [producer rank, chunk] epochs of the chunks I own
+            if self.round_deadline_ms > 0:
+                # failure detection on the two-shot path: the coordinator's arrived-set decisions (ring of 8 x {epoch, mask}) and
+                # a second arena that also receives every round's result — a rank that missed a deadline trained in place on a work
+                # arena the owners overwrote under it and restores it from there (comm.cu: twoshot_resync_kernel)
+                layout["decision"] = (16, torch.int32)
+                layout["global"] = (P4, torch.float32)
         self.arena = SymmetricArena(layout, self.device, self.group)
         self.ext = ops._ext.require()
         # every cross-GPU flag wait of the round kernels is bounded: past this many seconds without the peer's signal the
@@ -580,6 +586,10 @@ class FederatedEngine:
     def _run_twoshot(self, rounds: int, masks: List[int], host_inputs, read_back: bool) -> RoundReport:
         ext, arena, W, P4, r = self.ext, self.arena, self.world, self.P4, self.rank
         dev = self.device
+        deadline = self.round_deadline_ms > 0
+        if deadline:
+            assert self.coord == 0, "the two-shot deadline protocol takes rank 0 as the coordinator"
+            decision_ptrs, global_ptrs = arena.peer_ptrs("decision"), arena.peer_ptrs("global")
         use_prev = abs(self.server_lr - 1.0) > 1e-12
         if use_prev and getattr(self, "theta_prev", None) is None:
             # server_lr != 1: theta <- theta + lr_s (sum_k w_k theta_k - theta) needs the model the round started from, and the
@@ -625,10 +635,25 @@ class FederatedEngine:
             #                                       selected: it presents zeros), the kernel sums with weight 1 over ALL ranks
             nvls = self.use_nvls and arena.has_multicast and W > 1 and not use_prev and bool(sel_w)
             prescale = nvls and (masks[i] != full or max(sel_w) - min(sel_w) >= 1e-7)
+            if deadline and prescale:          # (a dropped rank's pre-scaled arena could not be renormalised away inside the switch)
+                nvls = prescale = False
+            if deadline and e > 1:
+                # a rank that missed round e-1's deadline restores its arena from the second arena before it trains again
+                ext.wait_flags(arena.ptr("chunk_flags"), self.n_chunks, e - 1)
+                ext.twoshot_resync(arena.ptr("decision"), e - 1, r, arena.ptr("work"), arena.ptr("shadow") if self.bf16_shadow else 0,
+                                   arena.ptr("global"), P4, 148)
             if prescale:
                 self.weights_dev[:W].fill_(1.0)
 
             def twoshot(blocks: int, produced_ptr: int):
+                if deadline:
+                    ext.twoshot_fedavg_deadline(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
+                                                self.theta_prev.data_ptr() if use_prev else 0, e, masks[i], self.server_lr, P4,
+                                                self.chunk_elems, r, blocks, arrive_ptrs, need_wait,
+                                                arena.mc_ptr("work") if nvls else 0,
+                                                arena.mc_ptr("shadow") if (nvls and self.bf16_shadow) else 0,
+                                                self.round_deadline_ms, decision_ptrs, global_ptrs)
+                    return
                 ext.twoshot_fedavg(work_ptrs, shadow_ptrs, cflag_ptrs, arena.ptr("flags", None, 1), self.weights_dev.data_ptr(),
                                    self.theta_prev.data_ptr() if use_prev else 0, e, full if prescale else masks[i], self.server_lr, P4,
                                    self.chunk_elems, r, blocks,
@@ -638,7 +663,7 @@ class FederatedEngine:
                                    produced_ptr, self.overlap_timeout_s if produced_ptr else 0.0)
 
             # fused wgrad -> FedAvg reduce: every rank trains this round, so every rank's last backward reports its chunks
-            prod = self._produced_spec() if (masks[i] == full and not prescale) else None
+            prod = self._produced_spec() if (masks[i] == full and not prescale and not deadline) else None
             launched = [False]
 
             def overlapped():
@@ -678,10 +703,16 @@ class FederatedEngine:
         if _dist_ready() and W > 1 and self._barrier:
             dist.barrier(group=self.group)
         nsel = [bin(m).count("1") for m in masks]
+        arrived = None
+        if deadline:
+            ring = arena.tensor("decision").cpu().tolist()
+            arrived = [(ring[2 * ((e0 + i + 1) & 7) + 1] if ring[2 * ((e0 + i + 1) & 7)] == e0 + i + 1 else None) for i in range(rounds)]
+        self._arrived_masks = arrived
         return RoundReport(rounds, W, "fused", "twoshot", ev0.elapsed_time(ev1), losses_log, launches,
                            bytes_bcast=4 * self.P * sum(nsel), bytes_reduce=4 * self.P * sum(nsel),
                            extra={"provider": arena.provider, "train_path": getattr(self, "_last_path", None), "phases_ms": phases,
-                                  "n_chunks": self.n_chunks, "nvls": getattr(self, "_last_nvls", False)})
+                                  "n_chunks": self.n_chunks, "nvls": getattr(self, "_last_nvls", False),
+                                  "arrived_masks": getattr(self, "_arrived_masks", None)})
 
     # ------------------------------------------------------------------------------------------ cpu / gloo
     def _run_cpu(self, rounds: int, masks: List[int]) -> RoundReport:

@@ -195,6 +195,44 @@ def _rank_main(rank, world, port, out_path, case):
                 torch.save({"err": float((outs[0] - outs[1]).abs().max()) / scale, "same": all(torch.equal(allf[0], f) for f in allf),
                             "nvls_rounds": nvls_flags[0], "p2p_rounds": nvls_flags[1], "multicast": bool(multicast),
                             "finite": bool(torch.isfinite(outs[0]).all())}, out_path)
+        elif case == "twoshot_deadline":
+            # failure detection on the large-model path: rank 1's shard is 24x bigger, it misses the coordinator's deadline in
+            # round 1, the round completes on the ranks that arrived (weights renormalised, chunk ownership dealt among them);
+            # before round 2 the late rank restores its arena from the second arena and — with a generous deadline — takes part
+            n_r = 3072 if rank == 1 else 128
+            xs, ys = synthetic_unsw(n_r, seed=40 + rank)
+            eng = FederatedEngine("wide_mlp", backend="fused", device=dev, batch_size=128, lr=0.05, seed=11, chunk_elems=4096,
+                                  bf16_shadow=True, weighted=False, round_deadline_ms=1.0, model_kwargs={"width": 512, "depth": 3})
+            eng.set_local_data(xs, ys)
+            theta0 = eng.global_flat().clone()
+            rep1 = eng.run_rounds(1)
+            torch.cuda.synchronize()
+            after1 = eng.arena.tensor("global")[: eng.P].clone()           # what the owners pushed (the late rank's work arena is garbage)
+            # reference of round 1 on every arrived rank: same trainer class, same data, from theta0
+            from colearn_federated_learning_b200.fl.layerwise import LayerwiseMLPTrainer
+            loc = theta0.clone()
+            tr = LayerwiseMLPTrainer(eng.spec, loc, 128)
+            from colearn_federated_learning_b200.fl.trainer import make_perm
+            tr.fit(loc, xs.to(dev), ys.to(dev), eng.cfg, make_perm(n_r, eng.cfg, dev, 0))
+            locs = [torch.zeros_like(loc) for _ in range(world)]
+            dist.all_gather(locs, loc)
+            eng.round_deadline_ms = 5000.0                                  # round 2: everybody makes it
+            rep2 = eng.run_rounds(1)
+            torch.cuda.synchronize()
+            flat2 = eng.global_flat().clone()
+            allf = [torch.zeros_like(flat2) for _ in range(world)]
+            dist.all_gather(allf, flat2)
+            alla = [torch.zeros_like(after1) for _ in range(world)]
+            dist.all_gather(alla, after1)
+            if rank == 0:
+                arrived = rep1.extra["arrived_masks"][0]
+                sel = [k for k in range(world) if (arrived >> k) & 1]
+                want = sum(locs[k] for k in sel) / len(sel)
+                torch.save({"arrived1": arrived, "arrived2": rep2.extra["arrived_masks"][0], "world": world,
+                            "err1": float((after1 - want).abs().max() / want.abs().max()),
+                            "global_same": all(torch.equal(alla[0], a) for a in alla),
+                            "same2": all(torch.equal(allf[0], f) for f in allf), "finite": bool(torch.isfinite(flat2).all()),
+                            "moved2": not torch.equal(flat2, after1)}, out_path)
         elif case == "twoshot_kernel":
             # direct numerics of twoshot_fedavg_kernel: P2P path (non-uniform weights, subset mask) and NVLS path
             from colearn_federated_learning_b200.parallel.symm import SymmetricArena
@@ -305,7 +343,7 @@ def _rank_main(rank, world, port, out_path, case):
 
 
 @pytest.mark.multigpu
-@pytest.mark.parametrize("case", ["star", "twoshot", "twoshot_kernel", "twoshot_nvls_weighted", "wide", "deadline", "wide_overlap"])
+@pytest.mark.parametrize("case", ["star", "twoshot", "twoshot_kernel", "twoshot_nvls_weighted", "twoshot_deadline", "wide", "deadline", "wide_overlap"])
 def test_fused_collectives_multi_rank(tmp_path, case):
     world = min(torch.cuda.device_count(), 8)
     out = str(tmp_path / "out.pt")
@@ -324,6 +362,10 @@ def test_fused_collectives_multi_rank(tmp_path, case):
     elif case == "wide_overlap":
         assert res["same"] and res["identical"] and res["shadow_ok"] and res["idle"] and res["finite"], res
         assert res["paths"][1].endswith("+overlap_reduce") and not res["paths"][0].endswith("+overlap_reduce"), res
+    elif case == "twoshot_deadline":
+        assert (res["arrived1"] >> 1) & 1 == 0 and res["arrived1"] & 1 == 1, res       # the slow rank 1 was dropped from round 1 ...
+        assert res["err1"] < 2e-3 and res["global_same"], res                          # ... which is the mean over those that arrived
+        assert res["arrived2"] == (1 << res["world"]) - 1 and res["same2"] and res["finite"] and res["moved2"], res
     elif case == "twoshot_nvls_weighted":
         assert res["same"] and res["finite"] and res["err"] < 2e-3, res         # bf16 shadows + switch-defined reduction order
         assert res["p2p_rounds"] == [False, False, False], res

@@ -518,3 +518,59 @@ def test_overlapped_twoshot_takes_chunks_as_they_are_produced(simt):
     assert int(flags.min()) == 4
 
 
+
+
+# ---- two-shot FedAvg with a deadline: arrived-set decision, ownership over the arrived ranks, second arena, resync ----------------
+def test_twoshot_deadline_drops_a_late_rank_and_lets_it_resync(simt):
+    """Kernel source on the CPU, three emulated ranks: rank 2 has not signalled when the coordinator's deadline expires.  The
+    round completes on ranks 0 and 1 (weights renormalised, chunk ownership dealt between the two), every arena — the late
+    rank's included — receives the result in its second arena, and the late rank, whose work arena was overwritten while it
+    "trained", restores it from there before its next round."""
+    W, n, chunk = 3, 4096 + 256, 1024
+    n_chunks = (n + chunk - 1) // chunk
+    torch.manual_seed(0)
+    works = torch.randn(W, n)
+    trained = works.clone()
+    globals_ = torch.zeros(W, n)
+    flags = torch.zeros(W, n_chunks, dtype=torch.int32)
+    decisions = torch.zeros(W, 16, dtype=torch.int32)
+    weights = torch.zeros(16)
+    weights[:3] = torch.tensor([0.5, 0.3, 0.2])
+    epoch = 5
+    arrive = [torch.zeros(W, dtype=torch.int32) for _ in range(W)]
+    for a in arrive:
+        a[0] = a[1] = epoch                                   # ranks 0 and 1 finished their local fit; rank 2 did not
+    def run_ranks(ranks, w, ep):                               # one emulated rank after the other, the coordinator (which decides) first
+        for r in ranks:
+            simt.twoshot_fedavg_deadline(r, w, globals_, flags, arrive[r], weights, ep, 0b111, chunk, 2, 2.0, decisions)
+
+    run_ranks((0, 1), works, epoch)
+    want = (0.5 * trained[0] + 0.3 * trained[1]) / 0.8        # renormalised over the arrived weight
+    assert decisions[:, 2 * (epoch % 8)].tolist() == [epoch] * W and decisions[:, 2 * (epoch % 8) + 1].tolist() == [0b011] * W
+    for k in range(W):
+        torch.testing.assert_close(globals_[k], want, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(works[k], want, rtol=1e-6, atol=1e-6)
+    assert bool((flags == epoch).all())
+    # the late rank arrives afterwards: it is not in the decision, owns nothing, changes nothing
+    works[2].normal_()                                        # (what its in-place training left behind)
+    for a in arrive:
+        a[2] = epoch
+    before = (works[:2].clone(), globals_.clone())
+    simt.twoshot_fedavg_deadline(2, works, globals_, flags, arrive[2], weights, epoch, 0b111, chunk, 2, 2.0, decisions)
+    assert torch.equal(works[:2], before[0]) and torch.equal(globals_, before[1])
+    # next round: rank 2 restores its arena from the second arena, the ranks that were in the decision do not
+    w0 = works[0].clone()
+    simt.twoshot_resync(decisions[2], epoch, 2, works[2], globals_[2])
+    simt.twoshot_resync(decisions[0], epoch, 0, works[0], globals_[0].zero_())
+    torch.testing.assert_close(works[2], want, rtol=1e-6, atol=1e-6)
+    assert torch.equal(works[0], w0)
+    # everybody in time: same result as the plain kernel, ownership over all three
+    epoch += 1
+    works2 = trained.clone()
+    for a in arrive:
+        a[:] = epoch
+    run_ranks(range(W), works2, epoch)
+    full = 0.5 * trained[0] + 0.3 * trained[1] + 0.2 * trained[2]
+    for k in range(W):
+        torch.testing.assert_close(works2[k], full, rtol=1e-6, atol=1e-6)
+    assert decisions[:, 2 * (epoch % 8) + 1].tolist() == [0b111] * W
