@@ -494,9 +494,75 @@ class BoxService:
         return self.results
 
 
+def run_box_encrypted(cli, args: Arguments, rank: int, world: int, device) -> Optional[Dict[str, Any]]:
+    """``--box -e``: the reference's encrypted demo (fc.py:394-472) with the roles on ranks — rank 0 = coordinator + crypto
+    provider (dealer), two other ranks (ranks 1 and 2; ranks 0 and 1 on a 2-GPU box) = the share holders; one temporal window
+    admits the devices, the first two share holders must be in it.  Shares travel dealer -> party point to point, the
+    per-multiplication opens go party <-> party through this repo's P2P kernels on GPUs (``smpc/dist.py``)."""
+    from ..models import MLPNet, build_model
+    from ..smpc import PartyContext, train_encrypted_dist
+    from ..utils.checkpoint import save_model
+
+    store = _c10d_store() if (dist.is_available() and dist.is_initialized()) else DictStore()
+    ctx = PartyContext(device, seed=args.seed)            # (collective: creates the pair's subgroup / exchange buffers)
+    agent = BoxAgent(StoreRelay(store), rank, event=getattr(cli, "box_event", "TRAINING") or "TRAINING", reannounce=False)
+    control = None
+    if rank == 0:
+        control = BoxControl(StoreRelay(store), world, float(cli.window), cli.topic, iot=cli.iot, selection="all", seed=args.seed,
+                             filter_file=cli.filter_file, strict=cli.strict_events)
+        control.start()
+    agent.start()
+    relay = StoreRelay(store)
+    seq, raw = relay.wait_next("commands")
+    cmd = json.loads(raw)
+    result = None
+    try:
+        mask = int(cmd.get("mask", 0)) if cmd.get("op") == "train" else 0
+        if not ((mask >> ctx.p0) & 1 and (mask >> ctx.p1) & 1):
+            log.info("No behaviour defined for a number of workers less than 2 (share holders %d and %d must both be in the window)", ctx.p0, ctx.p1)
+            return None
+        torch.manual_seed(args.seed)
+        model = build_model(args.model)
+        if not isinstance(model, MLPNet):
+            raise SystemExit("encrypted training supports the MLP family only")
+        if rank == 0 and os.path.exists(cli.checkpoint) and checkpoint_compatible(model, cli.checkpoint):
+            load_or_init(model, cli.checkpoint)
+        n_items = int(args.n_train_items_enc)
+        x = y = None
+        if args.synthetic and args.synthetic > 0:
+            xs, ys = synthetic_for_model(args.model, max(args.synthetic, n_items), seed=args.seed)
+        else:
+            xs, ys = NetworkTrafficDataset(args.test_path).tensors()
+        n_items = min(n_items, len(xs))
+        if ctx.is_dealer:
+            order = torch.randperm(len(xs), generator=torch.Generator().manual_seed(args.seed))[:n_items]   # cf.py:269-277
+            x, y = xs[order].to(device), ys[order].view(n_items, -1).to(device)
+        if ctx.is_dealer or ctx.party is not None:
+            model.to(device)
+            log.info("Encryption and distribution of the model...")
+            last, info = train_encrypted_dist(model, x, y, n_items, int(model.spec.dims[0]), int(model.spec.dims[-1]), args, ctx)
+            if rank == 0:
+                save_model(model.cpu(), cli.checkpoint, meta={"model": args.model, "mode": "encrypted-box", **{k: info[k] for k in ("dealer", "parties")}})
+                log.info("End encryption: last loss %s, %d Beaver triples, %d comparisons, %.3f s", last, info["triples"], info["comparisons"], info["seconds"])
+                result = {"last_loss": last, **info}
+            elif ctx.party is not None:
+                log.info("share holder %d: %d opens, %d bytes exchanged with the other share holder (%d through p2p_copy_kernel)",
+                         ctx.party, info["opens"], info["bytes_between_parties"], info["p2p_opens"])
+        return result
+    finally:
+        if control is not None:
+            control.command_done(seq)
+            control.stop()
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+
+
 def run_box_coordinator(cli, args: Arguments) -> None:
     rank, world, device = init_distributed()
     try:
-        BoxService(cli, args, rank, world, device).serve()
+        if getattr(cli, "encryption", False):
+            run_box_encrypted(cli, args, rank, world, device)
+        else:
+            BoxService(cli, args, rank, world, device).serve()
     finally:
         shutdown()

@@ -14,3 +14,4 @@ helper learns the sign and a scaled magnitude, nothing about the scale).  Semi-h
 from .sharing import (CryptoProvider, SharedTensor, fix_precision, float_precision, share, BASE,  # noqa: F401
                       PRECISION_FRACTIONAL)
 from .mlp import SharedMLP, encrypted_sgd_step  # noqa: F401
+from .dist import DistShared, PartyContext, train_encrypted_dist  # noqa: F401,E402

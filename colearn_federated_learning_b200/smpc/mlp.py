@@ -33,8 +33,10 @@ class SharedMLP:
         """``model.get().float_precision()`` (fc.py:454)."""
         with torch.no_grad():
             for layer, w, b in zip(model.layers(), self.W, self.b):
-                layer.weight.copy_(float_precision(w.get()))
-                layer.bias.copy_(float_precision(b.get()))
+                wv, bv = w.get(), b.get()          # (distributed demo: only the dealer gets the plaintext, the parties None)
+                if wv is not None:
+                    layer.weight.copy_(float_precision(wv).to(layer.weight.device))
+                    layer.bias.copy_(float_precision(bv).to(layer.bias.device))
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x: SharedTensor):

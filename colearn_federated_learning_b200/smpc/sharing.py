@@ -138,6 +138,8 @@ class SharedTensor:
         return self.provider.positive_bit(self.shares[0] * t, self.shares[1] * t)
 
 
-def share(secret: torch.Tensor, provider: CryptoProvider) -> SharedTensor:
+def share(secret: torch.Tensor, provider) -> "SharedTensor":
+    if hasattr(provider, "deal"):     # smpc.dist.PartyContext: the dealer's value is shared out, the other ranks pass the shape
+        return provider.share(secret if provider.is_dealer else None, tuple(secret.shape))
     r = _rand_ring(secret.shape, provider.gen, secret.device)
     return SharedTensor([r, secret - r], provider)

@@ -83,6 +83,7 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("--box", action="store_true", help="multi-GPU box mode under torchrun (rank 0 = coordinator)")
     parser.add_argument("--backend", choices=["auto", "fused", "nccl", "cpu"], default="auto")
     parser.add_argument("--clients-per-gpu", type=int, default=1, help="--box: virtual federated devices hosted by each GPU (one CTA each)")
+    parser.add_argument("--enc-items", type=int, default=None, help="-e: number of samples that are secret-shared and trained on (reference: 1000)")
     parser.add_argument("--round-deadline-ms", type=float, default=0.0,
                         help="--box: a selected worker that has not delivered its model this many ms after the coordinator started its "
                              "reduce is dropped from that round (weights renormalised); 0 = wait for everyone")
@@ -102,6 +103,8 @@ def arguments_from_cli(ns: argparse.Namespace) -> Arguments:
     a.federate_after_n_batches, a.lr, a.server_lr, a.seed = ns.max_batches, ns.lr, ns.server_lr, ns.seed
     a.log_interval, a.test_path, a.synthetic, a.weighted = ns.log_interval, ns.test_path, ns.synthetic, ns.weighted
     a.no_cuda, a.backend = ns.no_cuda, ns.backend
+    if getattr(ns, "enc_items", None):
+        a.n_train_items_enc = int(ns.enc_items)
     a.dtype, a.save_every = ns.dtype, max(0, ns.save_every)
     a.dataset = ns.dataset
     return a

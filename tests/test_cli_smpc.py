@@ -213,6 +213,44 @@ def test_box_mode_is_a_coordinator_service(tmp_path):
     assert torch.load(ckpt, weights_only=True)["fc4.weight"].shape == (1, 10)
 
 
+def test_box_mode_encrypted_demo_on_three_ranks(tmp_path):
+    """``--box -e``: rank 0 = coordinator + crypto provider (dealer), ranks 1 and 2 = the share holders.  One window admits the
+    devices, the model and the first N samples are secret-shared out, SGD runs on shares (the per-multiplication opens travel
+    between the two share holders), the coordinator reconstructs and saves the model (reference fc.py:394-472)."""
+    ckpt = str(tmp_path / "test.pth")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "3", "--master-addr",
+                          "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "federated_coordinator.py"),
+                          "-t", "topic/state", "--box", "-e", "--model", "ffnn", "--synthetic", "64", "-w", "1", "--checkpoint", ckpt,
+                          "--batch-size", "4", "--enc-items", "32", "--log-interval", "4"], env=env, capture_output=True, text=True,
+                         timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert out.stderr.count("share holder 0:") == 1 and out.stderr.count("share holder 1:") == 1 and "336 opens" in out.stderr   # 8 batches x 42 opens
+    assert "168 Beaver triples, 24 comparisons" in out.stderr
+    state = torch.load(ckpt, weights_only=True)
+    assert state["fc1.weight"].shape == (50, 10) and all(torch.isfinite(v).all() for v in state.values())
+    # same training in one process (both shares side by side): same fixed-point result up to the +-1 ulp of the probabilistic
+    # truncation (which depends on the share randomness)
+    from colearn_federated_learning_b200.control.arguments import Arguments
+    from colearn_federated_learning_b200.data import BaseDataset, synthetic_unsw
+    from colearn_federated_learning_b200.fl.encrypted import train_encrypted
+    from colearn_federated_learning_b200.models import build_model, flatten_params
+    a = Arguments()
+    a.batch_size, a.n_train_items_enc, a.log_interval, a.seed = 4, 32, 4, 1
+    torch.manual_seed(a.seed)
+    ref = build_model("ffnn")
+    init = flatten_params(ref).clone()
+    x, y = synthetic_unsw(64, seed=a.seed)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        train_encrypted(ref, BaseDataset(x, y), ["10.0.0.2", "10.0.0.3"], a)
+    got = build_model("ffnn")
+    got.load_state_dict(state)
+    d_box, d_ref = flatten_params(got) - init, flatten_params(ref) - init
+    assert float(d_ref.abs().max()) > 1e-3 and float((d_box - d_ref).abs().max()) < 5e-3, (float(d_ref.abs().max()), float((d_box - d_ref).abs().max()))
+
+
 def test_box_mode_metrics_jsonl_and_periodic_checkpoints(tmp_path):
     """``--metrics`` / ``--save-every`` in box mode: one JSONL record per round with the fields SURVEY §5 lists
     (selection, n_k, loss_k, device time as max over ranks, bytes of both collective legs, GB/s, link-roofline
