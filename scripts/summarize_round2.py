@@ -156,6 +156,9 @@ def main():
     for src in sorted(glob.glob(os.path.join(G, "r2c*_bench_*.json")) + glob.glob(os.path.join(G, "r2_8_*.json")) + glob.glob(os.path.join(G, "r2_bench_reference*.json"))):
         if os.path.getsize(src) > 0 and "cfg5_x" not in src:
             copy(os.path.basename(src), os.path.basename(src).replace("r2c", "r2_call"))
+    for src in sorted(glob.glob(os.path.join(G, "r2_8_sweep_*.json")) + glob.glob(os.path.join(G, "r2_8_tests.log")) + glob.glob(os.path.join(G, "r2_8_box_cfg3*"))
+                      + glob.glob(os.path.join(G, "r2c7_box*.jsonl")) + glob.glob(os.path.join(G, "r2c7_box.log"))):
+        copy(os.path.basename(src), os.path.basename(src).replace("r2c", "r2_call"))
     exp = os.path.join(G, "experiment_logs")
     if os.path.isdir(exp):
         dst = os.path.join(P, "r2_experiment_logs_b200")

@@ -68,14 +68,15 @@ def test_persistent_mlp_multi_client_scale_and_delta():
         assert torch.allclose(slots[i].cpu(), want, atol=2e-4, rtol=2e-3)
 
 
+@pytest.mark.parametrize("ctor,loss", [(MLP, "xent"), (FFNN, "sse")])
 @pytest.mark.parametrize("variant", [5, 6, 3, 1])
-def test_in_kernel_shuffle_equals_the_tabulated_permutation(variant):
+def test_in_kernel_shuffle_equals_the_tabulated_permutation(variant, ctor, loss):
     """ClientDesc::perm_seed: the gather of the persistent kernel computes the keyed Feistel order itself — same bits as
     training through the table feistel_perm_kernel writes for that seed (rows perm_row0 .. perm_row0 + epochs - 1), and the
     host implementation of the bijection agrees with the device one."""
     torch.manual_seed(4)
     dev = _dev()
-    model = MLP()
+    model = ctor()
     spec = model.spec
     theta = flatten_params(model).clone().to(dev)
     n, epochs, seed, row0 = 333, 3, 987654321, 5
@@ -88,12 +89,12 @@ def test_in_kernel_shuffle_equals_the_tabulated_permutation(variant):
     for kw in (dict(perm=table[row0:].contiguous()), dict(perm_seed=seed, perm_row0=row0, perm_scratch=scratch)):
         out, loss = torch.zeros_like(theta), torch.zeros(2, device=dev)
         descs = ops.build_client_descs([ops.ClientTask(x=x, y=y, theta_in=theta, theta_out=out, loss_out=loss, **kw)], dev)
-        ops.mlp_local_sgd_multi(spec.dims, spec.out_activation, descs, 1, batch_size=1, lr=0.05, epochs=epochs, loss="xent", variant=variant)
+        ops.mlp_local_sgd_multi(spec.dims, spec.out_activation, descs, 1, batch_size=1, lr=0.05, epochs=epochs, loss=loss, variant=variant)
         torch.cuda.synchronize()
         outs.append((out.clone(), loss.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert not torch.equal(outs[0][0], theta)
-    if variant != 1:                                          # (the first-version kernel computes the index inside its gather)
+    if variant != 1 and ctor is MLP:        # (v1 and the 4-layer nets' index ring compute the order inside the gather: no table)
         assert torch.equal(scratch.view(epochs, n), table[row0:])
 
 

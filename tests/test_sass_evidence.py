@@ -57,11 +57,7 @@ def test_comm_kernels_use_multimem_and_system_scope_flags(sass):
     assert mlp and all("STRONG.SYS" in t for t in mlp.values())  # wait / signal flags of the persistent kernel
 
 
-def test_opt_in_paths_compile_to_the_instructions_their_docs_claim(sass):
-    # line-coalesced epilogue: explicit 128-bit shared-memory accesses, no generic LD / ST, in every GEMM instantiation
-    for name, text in {**_kernels(sass, "gemm_tcgen05_kernel"), **_kernels(sass, "gemm_tcgen05_2sm_kernel")}.items():
-        assert text.count("STS.128") >= 16 and text.count("LDS.128") >= 16, name
-        assert not re.search(r"\bST\.E\.128\b|\bLD\.E\.128\b", text), name
+def test_round2_paths_compile_to_the_instructions_their_docs_claim(sass):
     # programmatic dependent launch: every conv / BatchNorm / pooling kernel exists twice, the PDL twin starts with
     # griddepcontrol.wait / launch_dependents; the plain twin has neither
     conv = {k: v for k, v in sass.items() if re.search(r"(im2col|col2im|bn_apply|bn_bwd|bn_reduce|bn_finalize|maxpool|avgpool|pack|splitk_reduce)\w*kernel", k)}
@@ -79,3 +75,11 @@ def test_opt_in_paths_compile_to_the_instructions_their_docs_claim(sass):
     v3 = {k: v for k, v in _kernels(sass, "mlp_local_sgd_kernel_v2").items() if "6v2_128" in k and "Li64ELi64" in k}
     assert len(v5) == 2 and all(t.count("LDS.128") >= 16 for t in v5.values())
     assert len(v3) == 2 and all("LDS.128" not in t for t in v3.values())
+    # variant 6 (default for the 10-64-64-2 MLP): packed fp32 math — FFMA2 carries the dot products and rank-1 updates
+    v6 = {k: v for k, v in _kernels(sass, "mlp_local_sgd_kernel_v2").items() if "7v2_128p" in k and "Li64ELi64" in k}
+    assert len(v6) == 2 and max(t.count("FFMA2") for t in v6.values()) >= 60 and all("FFMA2" in t for t in v6.values())
+    assert all("FFMA2" not in t for t in v5.values())
+    # bounded flag waits: the spin helper reads the nanosecond timer; the comm kernels carry the trap of spin_wait_failed
+    star = next(iter(_kernels(sass, "star_round_kernel").values()))
+    assert "GLOBALTIMER" in star.upper() or "SR_GLOBALTIMER" in star.upper()
+    assert _kernels(sass, "twoshot_resync_kernel") and _kernels(sass, "scale_inplace_kernel")
