@@ -72,6 +72,9 @@ def parse_args():
     ap.add_argument("--local-epochs", type=int, default=None)
     ap.add_argument("--lr", type=float, default=0.01)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nvlink-counters", action="store_true",
+                    help="after the timed region, run the K rounds once more between two reads of this GPU's NVLink payload counters "
+                         "(NVML) and report bytes per round next to the algorithmic count (config.nvlink)")
     ap.add_argument("--no-flush", action="store_true")
     return ap.parse_args()
 
@@ -431,6 +434,30 @@ def run_engine_config(args, name: str, rank: int, world: int, device, full: bool
     check = None
     if full:
         check = engine.verify_round(mask)        # fused round vs dist.broadcast + same local fit + dist.reduce, same inputs
+    nvlink = None
+    if full and getattr(args, "nvlink_counters", False) and world > 1:
+        import time as _time
+        from colearn_federated_learning_b200.utils.monitors import NvlinkCounters
+        ctr = NvlinkCounters(index=device.index or 0, uuid=str(torch.cuda.get_device_properties(device).uuid))
+        if ctr.ok:
+            dist.barrier()
+            torch.cuda.synchronize()
+            _time.sleep(0.3)
+            a = ctr.read()
+            engine.run_rounds(K, masks=mask)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            _time.sleep(0.3)
+            d = ctr.delta(a, ctr.read())
+            mine = torch.tensor([d["tx_bytes"] / K, d["rx_bytes"] / K] if d else [-1.0, -1.0], device=device, dtype=torch.float64)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            nvlink = {"counter": "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX over all links of each rank's GPU (payload bytes), untimed extra pass of K rounds",
+                      "tx_bytes_per_round_by_rank": [float(t[0]) for t in allr], "rx_bytes_per_round_by_rank": [float(t[1]) for t in allr],
+                      "model_bytes": int(engine.P) * 4, "algo": engine.algo}
+        else:
+            nvlink = {"unavailable": ctr.err}
 
     value = K / (dev_ms * 1e-3)
     if rank != 0:
@@ -448,6 +475,8 @@ def run_engine_config(args, name: str, rank: int, world: int, device, full: bool
            "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("COLEARN_")}, **extra}
     if check is not None:
         cfg["self_check"] = check
+    if nvlink is not None:
+        cfg["nvlink"] = nvlink
     if engine.algo == "twoshot":
         # roofline of the round (BASELINE.json: "the slower of its compute at peak and its bytes over NVLink at link bandwidth"):
         # compute = the rank's local fit (MLP: 6 FLOP per parameter and sample) at the MEASURED bf16 matmul peak; link = the

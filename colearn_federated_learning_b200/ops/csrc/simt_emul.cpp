@@ -21,7 +21,8 @@ const float* fptr(const Tensor& t, const char* name) {
 // Returns losses [K, 2] = {last, mean}; flags (int32 [K], optional) receive signal_value = 7 + i.
 Tensor mlp_local_sgd(int64_t net_kind, Tensor theta_in, std::vector<Tensor> theta_outs, std::vector<Tensor> xs, std::vector<Tensor> ys,
                      std::vector<c10::optional<Tensor>> perms, int64_t batch_size, int64_t epochs, int64_t max_steps, int64_t loss,
-                     double lr, int64_t variant, std::vector<double> out_scales, bool delta_mode, c10::optional<Tensor> flags) {
+                     double lr, int64_t variant, std::vector<double> out_scales, bool delta_mode, c10::optional<Tensor> flags,
+                     int64_t perm_seed, int64_t perm_row0, c10::optional<Tensor> perm_scratch) {
   const size_t K = xs.size();
   TORCH_CHECK(K >= 1 && ys.size() == K && perms.size() == K && theta_outs.size() == K && out_scales.size() == K, "one entry per client");
   const int P = colearn::mlp_net_num_params((int)net_kind);
@@ -42,6 +43,14 @@ Tensor mlp_local_sgd(int64_t net_kind, Tensor theta_in, std::vector<Tensor> thet
       TORCH_CHECK(!p.is_cuda() && p.scalar_type() == at::kInt && p.is_contiguous() && p.dim() == 2 && p.size(1) == d.n, "perm int32 [rows, n]");
       d.perm = p.data_ptr<int>();
       d.perm_rows = (int)p.size(0);
+    } else if (perm_seed != 0) {                                   // in-kernel shuffle (ClientDesc::perm_seed): client i keys on seed + i
+      d.perm_seed = (uint64_t)(perm_seed + (int64_t)i);
+      d.perm_row0 = (int)perm_row0;
+      if (perm_scratch.has_value()) {
+        TORCH_CHECK(perm_scratch->scalar_type() == at::kInt && perm_scratch->is_contiguous() && perm_scratch->dim() == 2 &&
+                    perm_scratch->size(0) == (int64_t)K && perm_scratch->size(1) >= epochs * (int64_t)d.n, "perm_scratch int32 [K, epochs * n]");
+        d.perm_scratch = perm_scratch->data_ptr<int>() + (int64_t)i * perm_scratch->size(1);
+      }
     }
     d.theta_in = fptr(theta_in, "theta_in");
     TORCH_CHECK(theta_outs[i].numel() == P, "theta_out size");
@@ -358,7 +367,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "the CUDA kernels of mlp_persistent.cu / elementwise.cu / comm.cu / convnet.cu compiled for the CPU through a SIMT shim (tests only)";
   convbind::register_ops<ConvSimtExec>(m);
   m.def("gemm_tcgen05", &gemm_tcgen05);
-  m.def("mlp_local_sgd", &mlp_local_sgd);
+  m.def("mlp_local_sgd", &mlp_local_sgd, py::arg("net_kind"), py::arg("theta_in"), py::arg("theta_outs"), py::arg("xs"), py::arg("ys"), py::arg("perms"),
+        py::arg("batch_size"), py::arg("epochs"), py::arg("max_steps"), py::arg("loss"), py::arg("lr"), py::arg("variant"), py::arg("out_scales"),
+        py::arg("delta_mode"), py::arg("flags"), py::arg("perm_seed") = 0, py::arg("perm_row0") = 0, py::arg("perm_scratch") = py::none());
   m.def("mlp_forward", &mlp_forward);
   m.def("mlp_net_params", [](int64_t kind) { return (int64_t)colearn::mlp_net_num_params((int)kind); });
   m.def("sgd_step", &sgd_step);

@@ -158,6 +158,58 @@ class NvmlSampler:
                 "bad": sorted(BAD_REASONS & set(reasons))}
 
 
+class NvlinkCounters:
+    """Cumulative NVLink payload bytes sent / received by one GPU, summed over its links (NVML field values
+    ``NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / RX``, KiB).  The difference of two ``read()`` calls around a loop of kernel
+    launches is the hardware's own count of what crossed the links — the evidence for the fused collectives that ncu cannot
+    give (its kernel replay cannot save / restore peer-mapped and multicast memory).  ``uuid`` selects the device the way
+    torch names it, so CUDA_VISIBLE_DEVICES does not shift the index."""
+
+    ALL_LINKS = 0xFFFFFFFF
+
+    def __init__(self, index: int = 0, uuid: Optional[str] = None) -> None:
+        self.ok, self.err = False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = None
+            if uuid:
+                u = str(uuid)
+                try:
+                    self._h = pynvml.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+                except Exception:  # noqa: BLE001 - unknown spelling of the UUID: fall back to the index
+                    self._h = None
+            if self._h is None:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.ok = self.read() is not None
+        except Exception as e:  # noqa: BLE001 - no NVML / no NVLink on this box
+            self.err = repr(e)
+
+    def read(self) -> Optional[Dict[str, int]]:
+        """{"tx_bytes", "rx_bytes"} (payload, cumulative since driver load) or None when the driver does not report them."""
+        nv = self._nv
+        try:
+            vals = nv.nvmlDeviceGetFieldValues(self._h, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, self.ALL_LINKS),
+                                                         (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, self.ALL_LINKS)])
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return None
+        out = {}
+        for name, v in zip(("tx_bytes", "rx_bytes"), vals):
+            if v.nvmlReturn != 0:
+                self.err = "nvmlReturn %d for field %d" % (v.nvmlReturn, v.fieldId)
+                return None
+            out[name] = int(v.value.ullVal) * 1024
+        return out
+
+    @staticmethod
+    def delta(a: Optional[Dict[str, int]], b: Optional[Dict[str, int]]) -> Optional[Dict[str, int]]:
+        if a is None or b is None:
+            return None
+        return {k: b[k] - a[k] for k in a}
+
+
 def monitor_gpu(index: int = 0, path: str = "monitoring_gpu.txt", samples: int = 3000, interval: float = 1.0,
                 stop: Optional[threading.Event] = None) -> None:
     """GPU analogue of :func:`monitor_cpu`: one ``Monitoring: <i> <timestamp>`` block per sample with SM clock,

@@ -20,9 +20,15 @@ import torch.distributed as dist
 from colearn_federated_learning_b200 import ops
 from colearn_federated_learning_b200.parallel import init_distributed, shutdown
 from colearn_federated_learning_b200.parallel.symm import SymmetricArena
+from colearn_federated_learning_b200.utils.monitors import NvlinkCounters
+
+NVL = {"counters": None}
 
 
-def timed(fn, iters, world, device):
+def timed(fn, iters, world, device, nvlink=None):
+    """ms per call (CUDA events, max over ranks).  ``nvlink``: a dict that receives this GPU's NVLink payload bytes per call
+    as the hardware counted them (NVML), next to the time — a second, untimed loop so the NVML reads never sit inside the
+    event bracket."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -37,6 +43,24 @@ def timed(fn, iters, world, device):
     t = torch.tensor([e0.elapsed_time(e1) / iters], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c = NVL["counters"]
+    if nvlink is not None and c is not None and c.ok:
+        import time
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        time.sleep(0.3)                                   # let the counters settle (barrier traffic, NVML's own sampling)
+        a = c.read()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()                                # every peer's stores into this GPU have landed
+        torch.cuda.synchronize()
+        time.sleep(0.3)
+        d = c.delta(a, c.read())
+        if d is not None:
+            nvlink.update({"tx_bytes_per_call": d["tx_bytes"] / iters, "rx_bytes_per_call": d["rx_bytes"] / iters, "calls": iters})
     return float(t.item())
 
 
@@ -49,8 +73,14 @@ def main():
     ap.add_argument("--blocks", type=int, default=0, help="CTAs for the two-shot kernel (0 = auto)")
     ap.add_argument("--tag", default="")
     ap.add_argument("--nvls", type=int, default=1, help="use multimem.ld_reduce/st when a multicast mapping exists")
+    ap.add_argument("--nvlink-counters", action="store_true",
+                    help="also report each kernel's NVLink payload bytes per call from the GPU's own counters (NVML field values)")
     args = ap.parse_args()
     rank, world, device = init_distributed()
+    if args.nvlink_counters:
+        NVL["counters"] = NvlinkCounters(index=device.index or 0, uuid=str(torch.cuda.get_device_properties(device).uuid))
+        if rank == 0 and not NVL["counters"].ok:
+            print("NVLink counters unavailable:", NVL["counters"].err, flush=True)
     ext = ops._ext.require()
     results = []
     for P in [int(s) for s in args.sizes.split(",")]:
@@ -82,9 +112,10 @@ def main():
                                arena.mc_ptr("shadow") if (use_nvls and args.shadow) else 0, 0, 0.0)
 
         iters = 20 if P4 < (1 << 22) else 8
-        ms = timed(ours, iters, world, device)
+        nvl_ours, nvl_nccl = ({}, {}) if args.nvlink_counters else (None, None)
+        ms = timed(ours, iters, world, device, nvl_ours)
         buf = torch.randn(P4, device=device)
-        ms_nccl = timed(lambda: dist.all_reduce(buf), iters, world, device) if world > 1 else float("nan")
+        ms_nccl = timed(lambda: dist.all_reduce(buf), iters, world, device, nvl_nccl) if world > 1 else float("nan")
         bus = 2.0 * (world - 1) / world * 4.0 * P4
         rec = {"P": P, "bytes": 4 * P4, "world": world, "provider": arena.provider, "multicast": arena.has_multicast,
                "twoshot_ms": ms, "twoshot_busbw_GBps": bus / ms / 1e6 if world > 1 else None,
@@ -93,6 +124,16 @@ def main():
                # fraction of NVLink 5's 900 GB/s per direction (BASELINE.json); busbw is directly comparable with it
                "twoshot_frac_of_900GBps": (bus / ms / 1e6 / 900.0) if world > 1 else None,
                "nccl_frac_of_900GBps": (bus / ms_nccl / 1e6 / 900.0) if world > 1 else None}
+        if args.nvlink_counters:
+            # what the algorithm says this GPU must move per call: pull (W-1)/W of the vector for its reduce share + push its
+            # reduced share to W-1 peers (P2P form) = (W-1)/W * 4P each way; with NVLS the switch reduces and multicasts, so
+            # the GPU receives 1/W of the vector once (already reduced) and sends its share once.
+            rec["nvlink"] = {"ours": nvl_ours, "nccl_allreduce": nvl_nccl,
+                             "algorithmic_bytes_each_way_p2p": (world - 1) / world * 4.0 * P4,
+                             "counter": "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX summed over links (payload, KiB granularity), rank 0's GPU"}
+            if nvl_ours and ms > 0:
+                rec["nvlink"]["ours_tx_GBps"] = nvl_ours.get("tx_bytes_per_call", 0) / ms / 1e6
+                rec["nvlink"]["ours_rx_GBps"] = nvl_ours.get("rx_bytes_per_call", 0) / ms / 1e6
         results.append(rec)
         if rank == 0:
             print(json.dumps(rec), flush=True)

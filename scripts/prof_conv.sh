@@ -2,12 +2,15 @@
 # ncu --set full of the ResNet-18 step's own kernels (1 GPU): the conv GEMMs (implicit-GEMM forward / dgrad / wgrad, explicit
 # stem + stride-2 + 1x1 convs, split-K), BatchNorm (single-launch reduction, apply, backward), im2col of the stem, pooling,
 # split-K reduce.  Skips the first eager step (warm-up), captures 60 matching launches of the second.
-#   -> gpurun_out/r2_prof_conv.ncu-rep (+ per-launch times of one whole step: r2_convnet_launch_times.csv)
+#   -> gpurun_out/r2_prof_conv_raw.csv (the report's raw page; the .ncu-rep itself is dropped when it is larger than 20 MB:
+#      gpurun brings back at most 64 MiB) + per-launch times of one whole step: r2_convnet_launch_times.csv
 mkdir -p gpurun_out
-timeout 400 ncu --set full --clock-control none --import-source on \
+timeout 400 ncu --set full --clock-control none \
     -k regex:"gemm_tcgen05_kernel|bn_reduce_finalize|bn_apply|bn_bwd|im2col|col2im|maxpool|avgpool|splitk_reduce|softmax_xent" \
     -s 170 -c 60 -f -o gpurun_out/r2_prof_conv python scripts/prof_convnet_only.py 3 > gpurun_out/r2_prof_conv.log 2>&1
 echo "ncu conv rc=$?"; tail -n 2 gpurun_out/r2_prof_conv.log
+ncu -i gpurun_out/r2_prof_conv.ncu-rep --page raw --csv > gpurun_out/r2_prof_conv_raw.csv 2>/dev/null
+[ "$(stat -c %s gpurun_out/r2_prof_conv.ncu-rep 2>/dev/null || echo 0)" -gt 20000000 ] && rm -f gpurun_out/r2_prof_conv.ncu-rep
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 230 -c 260 --csv --log-file gpurun_out/r2_convnet_launch_times.csv \
     python scripts/prof_convnet_only.py 2 > gpurun_out/r2_convnet_launch_times.log 2>&1
 python - <<'PY'

@@ -87,11 +87,11 @@ def test_in_kernel_shuffle_equals_the_tabulated_permutation(variant, ctor, loss)
     outs = []
     scratch = torch.empty(epochs * n, dtype=torch.int32, device=dev)
     for kw in (dict(perm=table[row0:].contiguous()), dict(perm_seed=seed, perm_row0=row0, perm_scratch=scratch)):
-        out, loss = torch.zeros_like(theta), torch.zeros(2, device=dev)
-        descs = ops.build_client_descs([ops.ClientTask(x=x, y=y, theta_in=theta, theta_out=out, loss_out=loss, **kw)], dev)
+        out, lo = torch.zeros_like(theta), torch.zeros(2, device=dev)
+        descs = ops.build_client_descs([ops.ClientTask(x=x, y=y, theta_in=theta, theta_out=out, loss_out=lo, **kw)], dev)
         ops.mlp_local_sgd_multi(spec.dims, spec.out_activation, descs, 1, batch_size=1, lr=0.05, epochs=epochs, loss=loss, variant=variant)
         torch.cuda.synchronize()
-        outs.append((out.clone(), loss.clone()))
+        outs.append((out.clone(), lo.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert not torch.equal(outs[0][0], theta)
     if variant != 1 and ctor is MLP:        # (v1 and the 4-layer nets' index ring compute the order inside the gather: no table)

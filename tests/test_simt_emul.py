@@ -64,6 +64,30 @@ def test_kernel_source_on_cpu_matches_reference(simt, kind, loss, variant, batch
     assert abs(float(losses[0, 0]) - float(last)) < 2e-3 * max(1.0, abs(float(last)))
 
 
+@pytest.mark.parametrize("kind", sorted(NETS))
+@pytest.mark.parametrize("variant", [5, 6, 3, 1])
+def test_in_kernel_shuffle_from_kernel_source(simt, kind, variant):
+    """ClientDesc::perm_seed on the CPU shim: both gather forms (index ring with the bijection computed per sample for the
+    4-layer net, kernel-made table in perm_scratch for the 3-layer nets, per-element in the smem-weights kernel) train through
+    exactly the order feistel_perm_kernel tabulates for (seed, perm_row0 + epoch) — bit-identical parameters and losses."""
+    name, dims, act, losses = NETS[kind]
+    loss = losses[0]
+    n, epochs, seed, row0 = 37, 3, 987654321, 5
+    x, y = _data(dims, loss, n, seed=kind + 40)
+    torch.manual_seed(kind)
+    flat0 = flatten_params(build_model(name)).clone()
+    table = simt.feistel_permutation(n, row0 + epochs, seed)
+    a, b = flat0.clone(), flat0.clone()
+    la = simt.mlp_local_sgd(kind, flat0, [a], [x], [y], [table[row0:].contiguous()], 1, epochs, -1, LOSS_CODES[loss], 0.05, variant, [1.0], False, None)
+    scratch = torch.full((1, epochs * n), -1, dtype=torch.int32)
+    lb = simt.mlp_local_sgd(kind, flat0, [b], [x], [y], [None], 1, epochs, -1, LOSS_CODES[loss], 0.05, variant, [1.0], False, None,
+                            perm_seed=seed, perm_row0=row0, perm_scratch=scratch)
+    assert torch.equal(a, b) and torch.equal(la, lb)
+    assert not torch.equal(a, flat0)
+    if variant != 1 and len(dims) - 1 < 4:                       # the table form leaves the order it used behind
+        assert torch.equal(scratch.view(epochs, n), table[row0:])
+
+
 def test_step_limit_scale_delta_flags_and_many_clients(simt):
     """max_nr_batches, the FedAvg weight pre-applied by the producer (out = w * theta_k or w * (theta_k - theta_in)), the
     completion flag (st.release) and one CTA per client — the star protocol's worker side."""
