@@ -395,9 +395,8 @@ class ConvNetTrainer:
             a = self._conv_bn(c2, C.nhwc_view(mid, B, c2.h, c2.w, c2.cin), identity, True, xmat=mid)
         C.avgpool_fwd(a, self.feat, B, self.final_hw, self.feat_dim)
         ops.gemm_bf16(self.feat, self._w(self.fc_entry), bias=self._s("fc.bias"), out_f32=self.logits)
-        loss, dlog = ops.softmax_xent(self.logits[:, : self.num_classes].contiguous(), labels)
-        self.dlog[:, : self.num_classes].copy_(dlog)
-        self._s("fc.bias", self.gsp)[: self.num_classes].copy_(dlog.sum(0))
+        # loss head: logits (padded fp32) -> dL/dlogits in the padded bf16 operand of the fc backward GEMMs + fc.bias gradient + loss
+        loss = C.softmax_xent_head(self.logits, labels, B, self.num_classes, dl_bf16=self.dlog, db=self._s("fc.bias", self.gsp))
         self.launches += 8
         return loss
 

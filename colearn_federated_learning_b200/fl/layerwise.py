@@ -24,6 +24,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .. import ops
+from ..ops import conv as conv_ops
 from ..models import MLPSpec
 
 PAD = 128
@@ -219,14 +220,18 @@ class LayerwiseMLPTrainer:
             else:
                 ops.gemm_bf16(self.a[l], self.Ws[l], bias=self._bias(flat, l), out_f32=self.logits, **kw)
         nc = self.dims[-1]
-        loss_val, dlog = self._head_loss(self.logits[:nv, :nc].contiguous(), labels, loss)
         if nv < self._dz_rows:                                   # a shorter batch than before: rows nv.. must carry no gradient
             self.dz[L - 1][nv:self._dz_rows].zero_()
         self._dz_rows = nv
-        self.dz[L - 1][:nv, :nc].copy_(dlog)                     # (only the first nc columns are ever written)
+        if loss == "xent" and nc <= 128:
+            # one launch: padded fp32 logits -> dL/dz in the padded bf16 GEMM operand, head bias gradient, mean loss
+            loss_val = conv_ops.softmax_xent_head(self.logits, labels, nv, nc, dl_bf16=self.dz[L - 1], db=self.db[L - 1])
+        else:
+            loss_val, dlog = self._head_loss(self.logits[:nv, :nc].contiguous(), labels, loss)
+            self.dz[L - 1][:nv, :nc].copy_(dlog)                 # (only the first nc columns are ever written)
+            self.db[L - 1][:nc].copy_(dlog.sum(0))
         if not self.wgrad_mn:
             ops.transpose_bf16(self.dz[L - 1], self.dzT[L - 1])
-        self.db[L - 1][:nc].copy_(dlog.sum(0))
         self.launches += L + 1 + (0 if self.wgrad_mn else 2)       # own kernels: L GEMMs, the loss, two transposes
         return loss_val
 

@@ -97,6 +97,29 @@ def _native(t: torch.Tensor):
     return _EMUL["mod"] if _EMUL["on"] else None
 
 
+def softmax_xent_head(logits: torch.Tensor, labels: torch.Tensor, rows: int, cols: int, dl_bf16: Optional[torch.Tensor] = None,
+                      db: Optional[torch.Tensor] = None, dl_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Loss head of the GEMM-shaped trainers in one launch (``softmax_xent_head_kernel``): mean softmax cross-entropy of
+    ``logits[:rows, :cols]`` (a padded fp32 / bf16 matrix); ``dL/dlogits`` goes straight into ``dl_bf16[:rows, :cols]`` (the
+    padded operand of the backward GEMMs) and / or ``dl_f32``, its column sums (the head's bias gradient) into ``db[:cols]``.
+    One block with a fixed summation order: bit-reproducible.  ``cols <= 128``."""
+    mod = _native(logits)
+    labels = labels.reshape(-1)
+    if labels.dtype != torch.long:
+        labels = labels.long()
+    if mod is not None and hasattr(mod, "softmax_xent_head"):
+        return mod.softmax_xent_head(logits, labels.contiguous(), int(rows), int(cols), dl_f32, dl_bf16, db)
+    from . import reference
+    loss, g = reference.softmax_xent(logits[:rows, :cols].float(), labels[:rows])
+    if dl_f32 is not None:
+        dl_f32[:rows, :cols].copy_(g)
+    if dl_bf16 is not None:
+        dl_bf16[:rows, :cols].copy_(g)
+    if db is not None:
+        db[:cols].copy_(g.sum(0))
+    return loss
+
+
 def out_size(h: int, k: int, stride: int, pad: int) -> int:
     return (h + 2 * pad - k) // stride + 1
 

@@ -155,6 +155,35 @@ std::vector<torch::Tensor> softmax_xent(torch::Tensor logits, torch::Tensor labe
                             loss.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1), cur_stream()), "softmax_xent");
   return {loss, want_bf16_grad ? dlb : dl};
 }
+// Fused loss head on padded operands (see softmax_xent_head_kernel): returns the mean loss; writes dl_bf16[:rows, :cols] and db[:cols].
+torch::Tensor softmax_xent_head(torch::Tensor logits, torch::Tensor labels, int64_t rows, int64_t cols, c10::optional<torch::Tensor> dl_f32,
+                                c10::optional<torch::Tensor> dl_bf16, c10::optional<torch::Tensor> db) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1 && rows >= 1 && rows <= logits.size(0) && cols >= 1 &&
+              cols <= logits.size(1), "logits [>= rows, >= cols], unit column stride");
+  const bool bf16 = logits.scalar_type() == at::kBFloat16;
+  TORCH_CHECK(bf16 || logits.scalar_type() == at::kFloat, "logits dtype");
+  TORCH_CHECK(labels.is_cuda() && labels.scalar_type() == at::kLong && labels.is_contiguous() && labels.numel() >= rows, "labels int64 [rows]");
+  float* dlp = nullptr; int ld_dl = 0; void* dbp16 = nullptr; int ld16 = 0; float* dbp = nullptr;
+  if (dl_f32.has_value()) {
+    TORCH_CHECK(dl_f32->is_cuda() && dl_f32->scalar_type() == at::kFloat && dl_f32->dim() == 2 && dl_f32->stride(1) == 1 &&
+                dl_f32->size(0) >= rows && dl_f32->size(1) >= cols, "dl_f32");
+    dlp = dl_f32->data_ptr<float>(); ld_dl = (int)dl_f32->stride(0);
+  }
+  if (dl_bf16.has_value()) {
+    TORCH_CHECK(dl_bf16->is_cuda() && dl_bf16->scalar_type() == at::kBFloat16 && dl_bf16->dim() == 2 && dl_bf16->stride(1) == 1 &&
+                dl_bf16->size(0) >= rows && dl_bf16->size(1) >= cols, "dl_bf16");
+    dbp16 = dl_bf16->data_ptr(); ld16 = (int)dl_bf16->stride(0);
+  }
+  if (db.has_value()) {
+    TORCH_CHECK(db->is_cuda() && db->scalar_type() == at::kFloat && db->is_contiguous() && db->numel() >= cols, "db fp32 [>= cols]");
+    dbp = db->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto loss = torch::empty({}, logits.options().dtype(at::kFloat));
+  check(launch_softmax_xent_head(logits.data_ptr(), bf16 ? 1 : 0, (int)logits.stride(0), labels.data_ptr<int64_t>(), dlp, ld_dl, dbp16, ld16, dbp,
+                                 loss.data_ptr<float>(), (int)rows, (int)cols, cur_stream()), "softmax_xent_head");
+  return loss;
+}
 std::vector<torch::Tensor> eval_binary(torch::Tensor p, torch::Tensor y) {
   CHECK_CUDA_F32(p); CHECK_CUDA_F32(y);
   c10::cuda::CUDAGuard guard(p.device());
@@ -558,6 +587,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sigmoid_bce", &sigmoid_bce);
   m.def("sse_loss", &sse_loss);
   m.def("softmax_xent", &softmax_xent);
+  m.def("softmax_xent_head", &softmax_xent_head);
   m.def("eval_binary", &eval_binary);
   m.def("argmax_rows", &argmax_rows);
   m.def("minmax_scale", &minmax_scale);

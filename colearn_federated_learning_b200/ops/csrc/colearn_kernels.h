@@ -228,6 +228,10 @@ cudaError_t launch_sse(const float* out, const float* y, float* dz, float* loss_
 cudaError_t launch_softmax_xent(const void* logits, int logits_is_bf16, const int64_t* labels,
                                 float* dlogits, void* dlogits_bf16, float* loss_out, int rows,
                                 int cols, cudaStream_t s);
+// one-block loss head on padded operands: dl / dl_bf16 (either may be null) with their own row strides, db[cols] = column sums of
+// dL/dlogits (may be null), *loss_out = mean loss; bit-reproducible (fixed summation order), cols <= 128
+cudaError_t launch_softmax_xent_head(const void* logits, int logits_is_bf16, int ld_in, const int64_t* labels, float* dl, int ld_dl,
+                                     void* dl_bf16, int ld_bf16, float* db, float* loss_out, int rows, int cols, cudaStream_t s);
 // Eval: sum BCE + number of correct round(p) predictions (cf.py:233-253)
 cudaError_t launch_eval_binary(const float* p, const float* y, float* loss_sum, int* correct,
                                int64_t n, cudaStream_t s);

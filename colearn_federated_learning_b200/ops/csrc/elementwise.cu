@@ -206,6 +206,78 @@ __global__ void softmax_xent_kernel(const void* __restrict__ logits_, const int6
   if (lane == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc * inv_rows);
 }
 
+// Loss head of the GEMM-shaped trainers in ONE launch and ONE block: softmax cross-entropy of the valid rows / columns of a PADDED
+// fp32 (or bf16) logits matrix, dL/dlogits written straight into the padded bf16 operand of the backward GEMMs (and / or an fp32
+// matrix), the head's bias gradient (column sums of dL/dlogits) and the mean loss.  Replaces slice-copy + loss + cast-copy +
+// at::sum + copy (three ATen launches, one of them an 18 us single-block reduction) around the old kernel.  One block, fixed
+// summation order: bit-reproducible, no memset, no atomics.  cols <= kHeadMaxCols.
+constexpr int kHeadMaxCols = 128;
+template <bool BF16_IN>
+__global__ void __launch_bounds__(1024)
+softmax_xent_head_kernel(const void* __restrict__ logits_, int ld_in, const int64_t* __restrict__ labels, float* __restrict__ dl, int ld_dl,
+                         __nv_bfloat16* __restrict__ dl_bf16, int ld_bf16, float* __restrict__ db, float* __restrict__ loss_out, int rows,
+                         int cols) {
+  __shared__ float s_col[32][kHeadMaxCols + 1];
+  __shared__ float s_loss[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float inv_rows = 1.f / (float)rows;
+  float colacc[kHeadMaxCols / 32];
+#pragma unroll
+  for (int j = 0; j < kHeadMaxCols / 32; ++j) colacc[j] = 0.f;
+  float loss_acc = 0.f;
+  for (int r = warp; r < rows; r += nwarps) {
+    auto load = [&](int c) -> float {
+      if (BF16_IN) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(logits_)[(size_t)r * ld_in + c]);
+      return reinterpret_cast<const float*>(logits_)[(size_t)r * ld_in + c];
+    };
+    float z[kHeadMaxCols / 32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kHeadMaxCols / 32; ++j) {
+      const int c = lane + 32 * j;
+      z[j] = c < cols ? load(c) : -INFINITY;
+      m = fmaxf(m, z[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kHeadMaxCols / 32; ++j)
+      if (lane + 32 * j < cols) s += __expf(z[j] - m);
+    s = warp_sum(s);
+    const int label = (int)labels[r];
+    const float inv_s = 1.f / s;
+#pragma unroll
+    for (int j = 0; j < kHeadMaxCols / 32; ++j) {
+      const int c = lane + 32 * j;
+      if (c < cols) {
+        const float g = (__expf(z[j] - m) * inv_s - (c == label ? 1.f : 0.f)) * inv_rows;
+        if (dl) dl[(size_t)r * ld_dl + c] = g;
+        if (dl_bf16) dl_bf16[(size_t)r * ld_bf16 + c] = __float2bfloat16(g);
+        colacc[j] += g;
+        if (c == label) loss_acc += (__logf(s) + m) - z[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kHeadMaxCols / 32; ++j) s_col[warp][lane + 32 * j] = colacc[j];
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0) s_loss[warp] = loss_acc;
+  __syncthreads();
+  if (db) {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += s_col[w][c];
+      db[c] = t;
+    }
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += s_loss[w];
+    *loss_out = t * inv_rows;
+  }
+}
+
 __global__ void eval_binary_kernel(const float* __restrict__ p, const float* __restrict__ y,
                                    float* __restrict__ loss_sum, int* __restrict__ correct, int64_t n) {
   __shared__ float scratch[32];
@@ -408,6 +480,18 @@ cudaError_t launch_softmax_xent(const void* logits, int is_bf16, const int64_t* 
     COLEARN_LAUNCH(softmax_xent_kernel<true>, blocks, kThreads, 0, s, logits, labels, dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16), loss_out, rows, cols);
   else
     COLEARN_LAUNCH(softmax_xent_kernel<false>, blocks, kThreads, 0, s, logits, labels, dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16), loss_out, rows, cols);
+  return cudaGetLastError();
+}
+cudaError_t launch_softmax_xent_head(const void* logits, int is_bf16, int ld_in, const int64_t* labels, float* dl, int ld_dl, void* dl_bf16,
+                                     int ld_bf16, float* db, float* loss_out, int rows, int cols, cudaStream_t s) {
+  if (cols < 1 || cols > kHeadMaxCols || rows < 1) return cudaErrorInvalidValue;
+  int threads = 32 * (rows < 32 ? rows : 32);          // one warp per row in flight, at most 32 warps
+  if (is_bf16)
+    COLEARN_LAUNCH(softmax_xent_head_kernel<true>, 1, threads, 0, s, logits, ld_in, labels, dl, ld_dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16),
+                   ld_bf16, db, loss_out, rows, cols);
+  else
+    COLEARN_LAUNCH(softmax_xent_head_kernel<false>, 1, threads, 0, s, logits, ld_in, labels, dl, ld_dl, reinterpret_cast<__nv_bfloat16*>(dl_bf16),
+                   ld_bf16, db, loss_out, rows, cols);
   return cudaGetLastError();
 }
 cudaError_t launch_eval_binary(const float* p, const float* y, float* loss_sum, int* correct, int64_t n, cudaStream_t s) {

@@ -122,6 +122,17 @@ std::tuple<Tensor, Tensor> softmax_xent(Tensor logits, Tensor labels) {
                                   (int)logits.size(0), (int)logits.size(1), nullptr));
   return {loss, dl};
 }
+Tensor softmax_xent_head(Tensor logits, Tensor labels, int64_t rows, int64_t cols, c10::optional<Tensor> dl_f32, c10::optional<Tensor> dl_bf16,
+                         c10::optional<Tensor> db) {
+  TORCH_CHECK(!logits.is_cuda() && logits.dim() == 2 && logits.stride(1) == 1 && labels.scalar_type() == at::kLong && labels.is_contiguous(), "operands");
+  const bool bf16 = logits.scalar_type() == at::kBFloat16;
+  Tensor loss = torch::zeros({}, torch::kFloat);
+  CK(colearn::launch_softmax_xent_head(logits.data_ptr(), bf16 ? 1 : 0, (int)logits.stride(0), labels.data_ptr<int64_t>(),
+                                       dl_f32.has_value() ? dl_f32->data_ptr<float>() : nullptr, dl_f32.has_value() ? (int)dl_f32->stride(0) : 0,
+                                       dl_bf16.has_value() ? dl_bf16->data_ptr() : nullptr, dl_bf16.has_value() ? (int)dl_bf16->stride(0) : 0,
+                                       db.has_value() ? db->data_ptr<float>() : nullptr, loss.data_ptr<float>(), (int)rows, (int)cols, nullptr));
+  return loss;
+}
 std::tuple<Tensor, Tensor> eval_binary(Tensor p, Tensor y) {
   Tensor loss = torch::zeros({}, torch::kFloat), correct = torch::zeros({}, torch::kInt);
   CK(colearn::launch_eval_binary(fptr(p, "p"), fptr(y, "y"), loss.data_ptr<float>(), correct.data_ptr<int>(), p.numel(), nullptr));
@@ -378,6 +389,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sigmoid_bce", &sigmoid_bce);
   m.def("sse_loss", &sse_loss);
   m.def("softmax_xent", &softmax_xent);
+  m.def("softmax_xent_head", &softmax_xent_head);
   m.def("eval_binary", &eval_binary);
   m.def("argmax_rows", &argmax_rows);
   m.def("minmax_scale", &minmax_scale);

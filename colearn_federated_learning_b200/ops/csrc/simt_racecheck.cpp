@@ -66,6 +66,9 @@ int main() {
     std::vector<int64_t> labels(100);
     for (auto& l : labels) l = rand() % 10;
     CK(launch_softmax_xent(logits.data(), 0, labels.data(), dl.data(), nullptr, loss.data(), 100, 10, nullptr));
+    std::vector<float> hb(10);
+    std::vector<__nv_bfloat16> dl16(1000);
+    CK(launch_softmax_xent_head(logits.data(), 0, 10, labels.data(), dl.data(), 10, dl16.data(), 10, hb.data(), loss.data(), 100, 10, nullptr));
     std::vector<float> p(n);
     for (auto& v : p) v = 0.01f + 0.98f * frand();
     int correct = 0;

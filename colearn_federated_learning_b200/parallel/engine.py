@@ -115,7 +115,12 @@ class FederatedEngine:
         # many virtual clients (federated devices) per GPU: one CTA each, summed locally before the NVLink push
         self.clients_per_rank = max(1, int(clients_per_rank))
         self.use_graphs = os.environ.get("COLEARN_CUDA_GRAPHS", "1") != "0"
-        self.use_nvls = os.environ.get("COLEARN_NVLS", "1") != "0"   # multimem.ld_reduce / multimem.st in the two-shot kernel
+        # multimem.ld_reduce / multimem.st in the two-shot kernel.  Through the switch every GPU sends its whole vector once (each
+        # element is pulled by its owner's ld_reduce) plus its reduced share once, and receives the same: (1 + 1/W) x model bytes
+        # per direction, against 2 (W-1)/W x for peer loads + peer stores.  The GPUs' own NVLink counters agree (profiles/
+        # r2_nvlink_counters.json: W=2 1.50 x vs 1.00 x, and 0.57 vs 0.36 ms for 201 MB), so "auto" takes the switch from W = 4 up
+        nvls_env = os.environ.get("COLEARN_NVLS", "auto")
+        self.use_nvls = nvls_env == "1" or (nvls_env not in ("0", "1") and self.world >= 4)
         # fused wgrad GEMM -> FedAvg reduce (ops/produced.py, opt-in until measured): the two-shot kernel runs on
         # `overlap_ctas` CTAs NEXT TO the last local backward pass and reduces chunks as the wgrad epilogues report them
         if overlap_reduce is None:

@@ -147,6 +147,23 @@ def test_losses():
         assert torch.allclose(d.cpu(), rd, atol=1e-6)
         lb, db = ops.softmax_xent(logits.to(torch.bfloat16), labels, bf16_grad=True)
         assert db.dtype == torch.bfloat16 and abs(lb.item() - rl.item()) < 0.05
+    # one-block loss head on padded operands (both GEMM-shaped trainers): bf16 gradient in place, bias gradient, loss
+    from colearn_federated_learning_b200.ops import conv as C
+    for rows, cols, ld in ((128, 10, 64), (1024, 2, 64), (5, 100, 128), (333, 128, 128)):
+        big = torch.randn(rows + 3, ld, device=dev) * 2
+        lab = torch.randint(0, cols, (rows + 3,), device=dev)
+        dz = torch.full((rows + 3, ld), 7.0, dtype=torch.bfloat16, device=dev)
+        dbias = torch.full((ld,), 7.0, device=dev)
+        outs = []
+        for _ in range(2):
+            loss = C.softmax_xent_head(big, lab, rows, cols, dl_bf16=dz, db=dbias)
+            outs.append((loss.clone(), dz.clone(), dbias.clone()))
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))                 # fixed summation order
+        rl, rdl = R.softmax_xent(big[:rows, :cols].cpu(), lab[:rows].cpu())
+        assert torch.allclose(loss.cpu(), rl, atol=1e-5, rtol=1e-5)
+        assert torch.allclose(dz[:rows, :cols].float().cpu(), rdl, atol=1e-6, rtol=1e-2)
+        assert torch.allclose(dbias[:cols].cpu(), rdl.sum(0), atol=1e-6, rtol=1e-4)
+        assert bool((dz[rows:] == 7).all()) and bool((dz[:, cols:] == 7).all()) and bool((dbias[cols:] == 7).all())
 
 
 def test_eval_argmax_minmax_perm_convert():

@@ -155,6 +155,21 @@ def test_elementwise_kernels_on_cpu(simt):
     rl, rdl = reference.softmax_xent(logits, labels)
     torch.testing.assert_close(loss, rl, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(dl, rdl, rtol=1e-4, atol=1e-6)
+    # the one-block loss head on padded operands (what both GEMM-shaped trainers launch): gradient into a padded bf16 matrix,
+    # head bias gradient, mean loss; rows / columns outside [rows, cols] untouched
+    for rows, cols, ld in ((128, 10, 64), (1000, 2, 64), (5, 100, 128), (37, 128, 128)):
+        big = torch.randn(rows + 3, ld) * 2
+        lab = torch.randint(0, cols, (rows + 3,))
+        dz = torch.full((rows + 3, ld), 7.0, dtype=torch.bfloat16)
+        dlf = torch.full((rows + 3, ld), 7.0)
+        db = torch.full((ld,), 7.0)
+        loss = simt.softmax_xent_head(big, lab, rows, cols, dlf, dz, db)
+        rl, rdl = reference.softmax_xent(big[:rows, :cols], lab[:rows])
+        torch.testing.assert_close(loss, rl, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(dlf[:rows, :cols], rdl, rtol=1e-4, atol=1e-6)
+        assert torch.equal(dz[:rows, :cols], dlf[:rows, :cols].to(torch.bfloat16))
+        torch.testing.assert_close(db[:cols], rdl.sum(0), rtol=1e-4, atol=1e-6)
+        assert bool((dz[rows:] == 7).all()) and bool((dz[:, cols:] == 7).all()) and bool((db[cols:] == 7).all())
     prob = torch.rand(999).clamp(1e-4, 1 - 1e-4)
     tgt = (torch.rand(999) > 0.5).float()
     loss, correct = simt.eval_binary(prob, tgt)
