@@ -12,6 +12,7 @@
 // The SIMT kernels that also run on the CPU for the test-suite (host_shim.h) declare their dynamic shared memory and
 // launch through these two macros; for nvcc they expand to the plain CUDA forms.
 #ifndef COLEARN_HOST_SHIM
+#define COLEARN_NOINLINE __noinline__
 #define COLEARN_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #define COLEARN_DYN_SMEM_UNALIGNED(type, name) extern __shared__ type name[]
 #define COLEARN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)

@@ -222,6 +222,8 @@ inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 #define cudaMemsetAsync(ptr, value, bytes, stream) (memset((ptr), (value), (bytes)), cudaSuccess)
 #define cudaMemset(ptr, value, bytes) (memset((ptr), (value), (bytes)), cudaSuccess)
 
+#undef COLEARN_NOINLINE
+#define COLEARN_NOINLINE
 #define COLEARN_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::colearn_shim::dyn_smem())
 #define COLEARN_DYN_SMEM_UNALIGNED(type, name) COLEARN_DYN_SMEM(type, name)
 #define COLEARN_LAUNCH(kernel, grid, block, smem, stream, ...) \

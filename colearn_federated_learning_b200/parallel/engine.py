@@ -270,6 +270,19 @@ class FederatedEngine:
             return self._run_star(rounds, ms, host_inputs, read_back)
         return self._run_twoshot(rounds, ms, host_inputs, read_back)
 
+    def _align_streams(self) -> None:
+        """Device-side barrier behind the host-side one (``barrier=True`` calls only): every rank raises its slot of an
+        alignment row in every peer's flag block (``signal_peers_kernel``) and waits for the whole row in its own
+        (``wait_flags_kernel``).  Processes leave ``dist.barrier`` tens of microseconds apart; a rank that leaves early would
+        otherwise count its wait for the coordinator's first launch as round time (max-over-ranks event timing of a sub-ms
+        round).  Outside every timed region: the events are recorded after it."""
+        if self.backend != "fused" or self.world <= 1 or self.world > 16:
+            return
+        self._align_seq = getattr(self, "_align_seq", 0) + 1
+        arena, r = self.arena, self.rank
+        self.ext.signal_peers([arena.ptr("flags", k, 32 + r) for k in range(self.world)], self._align_seq)
+        self.ext.wait_flags(arena.ptr("flags", None, 32), self.world, self._align_seq)
+
     # ------------------------------------------------------------------------------------------ tracing
     def _phase(self, name: str):
         """Context manager around the launches of one phase of a round: NVTX range + (with ``phase_timing``) an event pair."""
@@ -402,6 +415,7 @@ class FederatedEngine:
         launches = 0
         if _dist_ready() and W > 1 and self._barrier:
             dist.barrier(group=self.group)
+            self._align_streams()
         torch.cuda.synchronize(dev)
         if getattr(self, "_star_events", None) is None:
             self._star_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -610,6 +624,7 @@ class FederatedEngine:
         e0 = self.epoch
         if _dist_ready() and W > 1 and self._barrier:
             dist.barrier(group=self.group)
+            self._align_streams()
         torch.cuda.synchronize(dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
