@@ -1,3 +1,6 @@
+#!/bin/sh
+# What the driver runs at round end, on one GPU: pytest -m gpu -x, smoke(), both bench arms at N = 1; then the microbench and the
+# ncu captures of the conv step and of the MLP kernels.  -> gpurun_out/rB_*
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_out/rB_pytest_gpu.log 2>&1; echo "pytest -x rc=$?"; tail -n 6 gpurun_out/rB_pytest_gpu.log | cut -c1-250
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/rB_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 2 gpurun_out/rB_smoke.log | cut -c1-200

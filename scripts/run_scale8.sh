@@ -1,3 +1,6 @@
+#!/bin/sh
+# One 8-GPU box (gpurun --gpus 8 -- 'sh scripts/run_scale8.sh'): the default bench line at N = 8 and N = 4 (with the NVLink counters),
+# the fixed cost of a round at N = 8 (scripts/round_overhead.py) and BASELINE config 5 at N = 8 / 4.  -> gpurun_out/rM_*
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 O=gpurun_out/rM

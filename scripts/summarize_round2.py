@@ -77,7 +77,7 @@ def cfg5():
 
 def mlp():
     out = {}
-    for f in sorted(glob.glob(os.path.join(G, "r2*_microbench_mlp.json"))):
+    for f in sorted(glob.glob(os.path.join(G, "r2*_microbench_mlp.json")) + glob.glob(os.path.join(G, "r[A-Z]_microbench_mlp.json"))):
         try:
             d = json.load(open(f))
         except ValueError:
@@ -167,5 +167,60 @@ def main():
         print("copied experiment logs")
 
 
+LATE_CALLS = "ABCDEFGHIJKLM"
+
+
+def late_calls():
+    """Calls A .. M (letters): bench lines, test logs, NVLink counters, round-overhead fits, ncu captures of the final kernels."""
+    for src in sorted(glob.glob(os.path.join(G, "r[A-Z]_*"))):
+        name = os.path.basename(src)
+        if name.endswith((".ncu-rep", ".pth", ".err")) or os.path.getsize(src) == 0 or os.path.getsize(src) > 3_000_000:
+            continue
+        copy(name, "r2_call" + name[1:])
+    copy("r2_prof_conv_raw.csv", "r2_callB_prof_conv_ncu_raw.csv")
+    copy("r2_convnet_launch_times.csv", "r2_convnet_launch_times.csv")
+    # NVLink payload counters (NVML) around the fused collectives
+    nv = {"what": "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / RX (payload bytes, all links of a GPU) read before and after an untimed loop of "
+                  "kernel launches: what the hardware says crossed the links, next to the algorithmic count and the CUDA-event time",
+          "twoshot_kernel_world2": {}, "engine_rounds": {}}
+    for tag, f in (("nvls", "rC_nvlink_twoshot_nvls.json"), ("p2p", "rC_nvlink_twoshot_p2p.json")):
+        try:
+            nv["twoshot_kernel_world2"][tag] = [{k: r.get(k) for k in ("P", "bytes", "world", "nvls", "twoshot_ms", "twoshot_busbw_GBps", "nccl_allreduce_ms",
+                                                                         "nccl_busbw_GBps", "nvlink")} for r in json.load(open(os.path.join(G, f)))]
+        except (OSError, ValueError):
+            pass
+    for tag, f in (("cfg2_star_n2_before_staged_writeout", "rC_bench_cfg2_n2_nvlink.json"), ("cfg5_twoshot_nvls_n2", "rC_bench_cfg5_n2_nvlink.json"),
+                   ("ref_local_star_n2_staged_writeout", "rF_bench_default_n2.json"), ("cfg5_twoshot_p2p_n2", "rE_bench_cfg5_n2_nvlink.json"),
+                   ("ref_local_star_n8", "rM_default_n8.json"), ("cfg5_twoshot_nvls_n8", "rM_cfg5_n8.json")):
+        d = last_json(os.path.join(G, f))
+        if d:
+            nv["engine_rounds"][tag] = {"rounds_per_s": d["value"], "nvls": d["config"].get("nvls"), **(d["config"].get("nvlink") or {})}
+    dump("r2_nvlink_counters.json", nv)
+    # fixed cost of a round: fits of (round time) over (steps per round)
+    ov = {"what": "scripts/round_overhead.py: FFNN, SSE, batch 1; least-squares line through (steps per round, ms per round): slope = us per step, "
+                  "intercept = fixed cost of a round; K rounds in one run_rounds call / K single-round calls; phases = the engine's event timers",
+          "runs": {}}
+    for tag, f in (("n1_callD", "rD_round_overhead_ffnn_n1.json"), ("n2_callE_before_stream_alignment", "rE_round_overhead_ffnn_n2.json"),
+                   ("n2_callF", "rF_round_overhead_ffnn_n2.json"), ("n8_callM_final_kernel", "rM_round_overhead_ffnn_n8.json")):
+        try:
+            ov["runs"][tag] = json.load(open(os.path.join(G, f)))
+        except (OSError, ValueError):
+            pass
+    dump("r2_round_overhead.json", ov)
+    # ncu --set full of the headline kernel at three points of the latency work
+    n = {"callB_before (FFNN v5, BCE / MLP v6)": {"ffnn": ncu("rB_prof_ffnn_default.ncu-rep", 8192), "mlp64": ncu("rB_prof_mlp64_default.ncu-rep", 8192)},
+         "callI_after_fast_sigmoid_and_uniform_loss (FFNN v5, SSE / MLP v6)": {"ffnn": ncu("rI_prof_ffnn_sse.ncu-rep", 8192), "mlp64": ncu("rI_prof_mlp64.ncu-rep", 8192)}}
+    dump("r2_ncu_mlp_late.json", {"what": "ncu --set full --clock-control none --import-source on, 8 192 batch-1 steps, 1 CTA x 128 threads; per-instruction stall "
+                                          "listings: python scripts/ncu_hot_loop.py <rep> (r2_callI_hot_loop_*.txt)", **n})
+    for rep, out in (("rI_prof_ffnn_sse.ncu-rep", "r2_callI_hot_loop_ffnn_sse.txt"), ("rI_prof_mlp64.ncu-rep", "r2_callI_hot_loop_mlp64.txt"),
+                     ("rB_prof_mlp64_default.ncu-rep", "r2_callB_hot_loop_mlp64.txt")):
+        if os.path.exists(os.path.join(G, rep)):
+            txt = subprocess.run(["python", os.path.join(ROOT, "scripts", "ncu_hot_loop.py"), os.path.join(G, rep)], capture_output=True, text=True).stdout
+            with open(os.path.join(P, out), "w") as f:
+                f.write(txt)
+            print("wrote", out)
+
+
 if __name__ == "__main__":
     main()
+    late_calls()
