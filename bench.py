@@ -638,5 +638,16 @@ def main() -> None:
     shutdown()
 
 
+def _keep_stdout_for_the_result_line() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    version banner there at world > 1), so fd 1 is pointed at stderr for the life of the process and Python's ``sys.stdout``
+    — what ``print`` of the result line uses — keeps the original stream."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _keep_stdout_for_the_result_line()
     main()

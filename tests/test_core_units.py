@@ -260,6 +260,21 @@ def test_monitors(tmp_path):
     assert os.path.getsize(gpu) > 0
     ns = monitors.build_parser().parse_args(["-p", "1", "-n", "eth0", "--gpu", "0"])
     assert (ns.pid, ns.network, ns.gpu) == (1, "eth0", 0)
+    # NVLink payload counters: without NVML / NVLink the object says so and its helpers stay total (bench.py / comm_sweep.py branch on .ok)
+    c = monitors.NvlinkCounters(index=0, uuid="GPU-00000000-0000-0000-0000-000000000000")
+    if not c.ok:
+        assert c.err and monitors.NvlinkCounters.delta(None, {"tx_bytes": 1, "rx_bytes": 2}) is None
+    assert monitors.NvlinkCounters.delta({"tx_bytes": 1024, "rx_bytes": 0}, {"tx_bytes": 4096, "rx_bytes": 2048}) == {"tx_bytes": 3072, "rx_bytes": 2048}
+
+
+def test_round_overhead_fit_separates_slope_and_intercept():
+    """scripts/round_overhead.py: per-step time and fixed cost of a round are the slope and intercept over steps per round."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("round_overhead", os.path.join(ROOT, "scripts", "round_overhead.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    slope, icpt = mod.fit_line([(n, 0.000562 * n + 0.0245) for n in (128, 512, 1024)])
+    assert abs(slope - 0.000562) < 1e-9 and abs(icpt - 0.0245) < 1e-9
 
 
 def test_reference_shaped_client_federated_api(tmp_path):
