@@ -113,3 +113,20 @@ def test_bench_ref_local_data_matches_the_reference_arms_csv(tmp_path):
     assert x0.shape == (32, 10) and x1.shape == (32, 10) and y0.shape == (32, 1)
     x = torch.cat([x0, x1])
     assert float(x.min()) == 0.0 and float(x.max()) == 1.0 and set(torch.cat([y0, y1]).view(-1).tolist()) <= {0.0, 1.0}
+
+
+def test_bench_stdout_carries_the_result_line_only():
+    """bench.py points file descriptor 1 at stderr for the life of the process (NCCL prints its version banner to fd 1 at
+    world > 1) and keeps Python's stdout for the one JSON line of the contract."""
+    # a library-style write to fd 1 from inside the process (here: at exit, after bench.py has re-pointed the descriptor)
+    # must land on stderr, not next to the result line
+    probe = ("import os, sys, json, runpy, atexit\n"
+             "atexit.register(lambda: os.write(1, b'banner from a C library\\n'))\n"
+             "sys.argv = ['bench.py', '--gpus', '1']\n"
+             "runpy.run_path(%r, run_name='__main__')\n" % os.path.join(ROOT, "bench.py"))
+    p = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout
+    assert "unavailable" in json.loads(lines[0]) or "value" in json.loads(lines[0])
+    assert "banner from a C library" in p.stderr
